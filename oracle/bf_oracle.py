@@ -1,0 +1,512 @@
+"""CPU oracle for the brainforge layer forward/backward + optimizer hot path.
+
+TEST INFRASTRUCTURE ONLY.  This module is a NumPy (float64) restatement of the
+reference's arithmetic.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the
+product package ``brainforge_b200`` never does (it fails loudly when the CUDA
+library is missing instead of falling back to anything in here).
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real
+reference from ``/root/reference`` (authoring container only), runs seeded
+cases through the reference's NumPy ``atomic`` path (and the Numba ``llatomic``
+path where the two agree) and commits inputs+outputs under ``tests/golden``;
+``tests/test_oracle_golden.py`` checks every function below against them.
+
+Every function cites the reference file:line it restates (paths relative to
+``/root/reference/brainforge``).  Loops over patches / windows / individuals in
+the reference are vectorised here (same arithmetic, BLAS summation order), the
+loop over LSTM time steps is kept because it is a true recurrence.
+"""
+import numpy as np
+from numpy.lib.stride_tricks import sliding_window_view
+
+F64 = np.float64
+
+
+# --------------------------------------------------------------------------
+# activations                                   atomic/activation_op.py:26-135
+# --------------------------------------------------------------------------
+def act_forward(kind, Z):
+    """atomic/activation_op.py: Sigmoid:30-31, Tanh:54-55, ReLU:87-88,
+    Linear:76-77, SoftMax.t1:127-130 (row softmax with max subtraction)."""
+    if kind == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-Z))
+    if kind == "tanh":
+        return np.tanh(Z)
+    if kind == "relu":
+        return np.maximum(0.0, Z)
+    if kind == "linear":
+        return Z
+    if kind == "softmax":
+        eZ = np.exp(Z - Z.max(axis=1, keepdims=True))
+        return eZ / np.sum(eZ, axis=1, keepdims=True)
+    raise ValueError("unknown activation: %r" % (kind,))
+
+
+def act_backward(kind, A):
+    """Derivative expressed from the OUTPUT A.  atomic/activation_op.py:
+    Sigmoid:33-34 A(1-A); Tanh:57-58 1-A^2; ReLU:90-91 (A>0); Linear:79-80 and
+    SoftMax:134-135 return the scalar 1 (softmax Jacobian deliberately skipped)."""
+    if kind == "sigmoid":
+        return A * (1.0 - A)
+    if kind == "tanh":
+        return 1.0 - A ** 2
+    if kind == "relu":
+        return (A > 0.0).astype(A.dtype)
+    if kind in ("linear", "softmax"):
+        return 1.0
+    raise ValueError("unknown activation: %r" % (kind,))
+
+
+# --------------------------------------------------------------------------
+# dense                                               atomic/core_op.py:9-20
+# --------------------------------------------------------------------------
+def dense_forward(X, W, b=0.0):
+    """atomic/core_op.py:12-13  Z = X@W + b."""
+    return np.dot(X, W) + b
+
+
+def dense_backward(X, E, W):
+    """atomic/core_op.py:16-20  returns (dW, db, dX); gradients are batch SUMS."""
+    dW = X.T @ E
+    dX = E @ W.T
+    db = E.sum(axis=0)
+    return dW, db, dX
+
+
+# --------------------------------------------------------------------------
+# convolution                                      atomic/tensor_op.py:6-75
+# --------------------------------------------------------------------------
+def conv_valid(A, F):
+    """atomic/tensor_op.py:9-32.  Cross-correlation, stride 1, no dilation.
+    The reference fills an im2col matrix patch by patch (order c,ky,kx) and
+    multiplies by F.reshape(nf,-1).T; here the patches are a strided view."""
+    im, ic, iy, ix = A.shape
+    nf, fc, fy, fx = F.shape
+    if fc != ic:
+        raise ValueError(
+            "Supplied filter (F) is incompatible with supplied input! (X)\n"
+            "input depth: {} != {} :filter depth".format(ic, fc))
+    win = sliding_window_view(A, (fy, fx), axis=(2, 3))  # (im, ic, oy, ox, fy, fx)
+    out = np.tensordot(win, F, axes=([1, 4, 5], [1, 2, 3]))  # (im, oy, ox, nf)
+    return np.ascontiguousarray(out.transpose(0, 3, 1, 2))
+
+
+def conv_full(A, F):
+    """atomic/tensor_op.py:34-40.  Zero-pad by (f-1) on each side, then valid."""
+    nf, fc, fy, fx = F.shape
+    py, px = fy - 1, fx - 1
+    pA = np.pad(A, ((0, 0), (0, 0), (py, py), (px, px)), mode="constant")
+    return conv_valid(pA, F)
+
+
+def conv_forward(A, F, mode="valid"):
+    """atomic/tensor_op.py:42-46."""
+    return conv_valid(A, F) if mode == "valid" else conv_full(A, F)
+
+
+def conv_backward(X, E, F):
+    """atomic/tensor_op.py:49-61.  dF = valid(X^T(1023), E^T(1023))^T(1023);
+    db = E.sum((0,2,3), keepdims) ; dX = full(E, flip_hw(F)^T(1023))."""
+    dF = conv_forward(X.transpose(1, 0, 2, 3), E.transpose(1, 0, 2, 3), "valid").transpose(1, 0, 2, 3)
+    db = E.sum(axis=(0, 2, 3), keepdims=True)
+    dX = conv_forward(E, F[:, :, ::-1, ::-1].transpose(1, 0, 2, 3), "full")
+    return np.ascontiguousarray(dF), db, dX
+
+
+def conv_outshape(inshape, fshape, mode="valid"):
+    """llatomic/lltensor_op.py:111-119 (the consistent nf,fc,fy,fx unpacking)."""
+    ic, iy, ix = inshape[-3:]
+    nf, fc, fy, fx = fshape
+    if mode == "valid":
+        return nf, iy - fy + 1, ix - fx + 1
+    return nf, iy + fy - 1, ix + fx - 1
+
+
+# --------------------------------------------------------------------------
+# max pooling                                     atomic/tensor_op.py:78-128
+# --------------------------------------------------------------------------
+def maxpool_forward(A, fdim):
+    """atomic/tensor_op.py:93-107.  Non-overlapping fdim x fdim windows; returns
+    (output, filt) where filt has A's shape and is 1.0 at EVERY element equal to
+    its window's max (multi-hot on ties), 0.0 elsewhere."""
+    im, ic, iy, ix = A.shape
+    oy, ox = iy // fdim, ix // fdim
+    W = A[:, :, :oy * fdim, :ox * fdim].reshape(im, ic, oy, fdim, ox, fdim)
+    out = W.max(axis=(3, 5))
+    filt = np.zeros_like(A, dtype=F64)
+    eq = (W == out[:, :, :, None, :, None]).astype(F64)
+    filt[:, :, :oy * fdim, :ox * fdim] = eq.reshape(im, ic, oy * fdim, ox * fdim)
+    return out.astype(F64), filt
+
+
+def maxpool_backward(E, filt):
+    """atomic/tensor_op.py:110-119.  dX[window] = filt[window] * E[m,c,i,j].
+    (The reference does it in place on the cached mask and returns it; the
+    oracle returns a fresh array and leaves ``filt`` untouched.)"""
+    em, ec, ey, ex = E.shape
+    fm, fc, fy, fx = filt.shape
+    fdim = fy // ey
+    up = np.repeat(np.repeat(E, fdim, axis=2), fdim, axis=3)
+    out = np.array(filt, dtype=F64, copy=True)
+    out[:, :, :ey * fdim, :ex * fdim] *= up
+    return out
+
+
+# --------------------------------------------------------------------------
+# costs and metrics                   metrics/costs.py:11-37, metrics.py:13-16
+# --------------------------------------------------------------------------
+def cost_derivative(outputs, targets):
+    """metrics/costs.py:19-21  delta = outputs - targets (for every cost)."""
+    return outputs - targets
+
+
+def cost_value(kind, outputs, targets):
+    """metrics/costs.py:26-27 (mse = 0.5*||o-t||^2, a SUM) and :36-37
+    (cxent = -sum(t*log o)).  The caller divides by m."""
+    if kind in ("mse", "mean_squared_error"):
+        return 0.5 * np.linalg.norm(outputs - targets) ** 2.0
+    if kind in ("cxent", "categorical_crossentropy"):
+        return -(targets * np.log(outputs)).sum()
+    raise ValueError("No such cost function: %r" % (kind,))
+
+
+def accuracy(outputs, targets):
+    """metrics/metrics.py:15-16  count of argmax matches (caller divides by m)."""
+    return np.sum(outputs.argmax(axis=1) == targets.argmax(axis=1))
+
+
+# --------------------------------------------------------------------------
+# LSTM                                        atomic/recurrent_op.py:46-112
+# --------------------------------------------------------------------------
+def lstm_forward(X, W, b, activation="tanh"):
+    """atomic/recurrent_op.py:51-77.  X (T,B,D); W (D+H,4H); gate order along 4H
+    is [cand | f | i | o].  Returns O (T,B,H), Z (T,B,D+H), cache (6,T,B,H)
+    ordered C, Ca, cand, f, i, o.  At t=0, O[t-1] is the still-zero last row."""
+    H = W.shape[-1] // 4
+    T, B, D = X.shape
+    Z = np.zeros((T, B, D + H))
+    O = np.zeros((T, B, H))
+    C, f, i, o, cand, Ca = np.zeros((6, T, B, H))
+    for t in range(T):
+        Z[t] = np.concatenate((X[t], O[t - 1]), axis=-1)
+        p = np.dot(Z[t], W) + b
+        p[:, :H] = act_forward(activation, p[:, :H])
+        p[:, H:] = act_forward("sigmoid", p[:, H:])
+        cand[t] = p[:, :H]
+        f[t] = p[:, H:2 * H]
+        i[t] = p[:, 2 * H:3 * H]
+        o[t] = p[:, 3 * H:]
+        C[t] = C[t - 1] * f[t] + cand[t] * i[t]
+        Ca[t] = act_forward(activation, C[t])
+        O[t] = Ca[t] * o[t]
+    return O, Z, np.stack((C, Ca, cand, f, i, o))
+
+
+def lstm_backward(Z, O, E, W, cache, activation="tanh"):
+    """atomic/recurrent_op.py:79-112.  E (T,B,H) is the error on O (copied, the
+    reference scribbles on the caller's array).  Returns (dX (T,B,D),
+    nablaW (D+H,4H), nablab (4H,))."""
+    H = W.shape[-1] // 4
+    T, B, zdim = Z.shape
+    D = zdim - H
+    E = np.array(E, dtype=F64, copy=True)
+    C, Ca, cand, f, i, o = cache
+    bwgates = np.concatenate(cache[2:], axis=-1)
+    bwgates[..., H:] = act_backward("sigmoid", bwgates[..., H:])
+    bwgates[..., :H] = act_backward(activation, bwgates[..., :H])
+    bwCa = np.atleast_2d(act_backward(activation, Ca))
+    deltaC = np.zeros_like(O[-1])
+    deltaZ = np.zeros_like(Z)
+    dgates = np.zeros((T, B, 4 * H))
+    for t in range(T - 1, -1, -1):
+        deltaC += E[t] * o[t] * bwCa[t]
+        dcand = deltaC * i[t]
+        df = deltaC * (C[t - 1] if t else 0.0)
+        di = deltaC * cand[t]
+        do = Ca[t] * E[t]
+        dgates[t] = np.concatenate((dcand, df, di, do), axis=-1) * bwgates[t]
+        deltaC *= f[t]
+        deltaZ[t] = np.dot(dgates[t], W.T)
+        if t:
+            E[t - 1] += deltaZ[t, :, D:]
+    nablaW = np.matmul(Z.transpose(0, 2, 1), dgates).sum(axis=0)
+    nablab = np.sum(dgates, axis=(0, 1))
+    return deltaZ[:, :, :D], nablaW, nablab
+
+
+# --------------------------------------------------------------------------
+# optimizers          optimizers/gradient_descent.py, optimizers/adaptive_gd.py
+# --------------------------------------------------------------------------
+class Optimizer:
+    """Flat-vector update rules; ``optimize(W, gW, m) -> W'``.  gW is the batch
+    SUM gradient; the 1/m lives here (gradient_descent.py:9)."""
+
+    def __init__(self, kind, nparams, **hp):
+        self.kind = kind
+        d = dict(
+            sgd=dict(eta=0.01),                                   # abstract_optimizer.py:21
+            momentum=dict(eta=0.1, mu=0.9),                       # gradient_descent.py:17
+            nesterov=dict(eta=0.1, mu=0.9),                       # gradient_descent.py:36
+            adagrad=dict(eta=0.01, epsilon=1e-8),                 # adaptive_gd.py:7
+            rmsprop=dict(eta=0.1, decay=0.9, epsilon=1e-8),       # adaptive_gd.py:67
+            adam=dict(eta=0.001, decay_memory=0.999, decay_velocity=0.9, epsilon=1e-5),  # adaptive_gd.py:83
+        )[kind]
+        d.update(hp)
+        self.__dict__.update(d)
+        self.velocity = np.zeros(nparams)
+        self.memory = np.zeros(nparams)
+
+    def optimize(self, W, gW, m):
+        k = self.kind
+        if k == "sgd":                       # gradient_descent.py:8-9
+            return W - gW * (self.eta / m)
+        if k == "momentum":                  # gradient_descent.py:25-28
+            self.velocity = self.velocity * self.mu + gW * (self.eta / m)
+            return W - self.velocity
+        if k == "nesterov":                  # gradient_descent.py:44-50 (literal, incl. its quirks)
+            nabla = gW * (self.eta / m)
+            W_ = self.memory - self.velocity + nabla
+            self.memory = W
+            self.velocity = self.velocity * self.mu + nabla
+            return W_
+        if k == "adagrad":                   # adaptive_gd.py:16-20
+            nabla = gW / m
+            self.memory = self.memory + nabla ** 2
+            return W - (self.eta / np.sqrt(self.memory + self.epsilon)) * nabla
+        if k == "rmsprop":                   # adaptive_gd.py:71-76
+            nabla = gW / m
+            self.memory = self.memory * self.decay + (1.0 - self.decay) * nabla ** 2
+            return W - (self.eta * nabla) / np.sqrt(self.memory + self.epsilon)
+        if k == "adam":                      # adaptive_gd.py:94-99 (non-standard: raw sum gradient in
+            eta = self.eta / m               #  the moments, no bias correction, eps inside the sqrt)
+            self.velocity = self.decay_velocity * self.velocity + (1.0 - self.decay_velocity) * gW
+            self.memory = self.decay_memory * self.memory + (1.0 - self.decay_memory) * gW ** 2
+            return W - (eta * self.velocity) / np.sqrt(self.memory + self.epsilon)
+        raise ValueError(k)
+
+
+# --------------------------------------------------------------------------
+# weight initialisers                                  util/typing.py:22-33
+# --------------------------------------------------------------------------
+def white(*dims):
+    """util/typing.py:22-33.  Draws from the GLOBAL numpy RNG exactly like the
+    reference so that the same seed yields the same weights."""
+    if len(dims) == 2:
+        fanin, fanout = dims
+        return np.random.randn(fanin, fanout) * np.sqrt(2.0 / float(fanin + fanout))
+    nf, fc, fy, fx = dims
+    return np.random.randn(nf, fc, fy, fx) * np.sqrt(2.0 / float(nf * fy * fx + fc * fy * fx))
+
+
+# --------------------------------------------------------------------------
+# layer glue + learner                layers/*.py, learner/backpropagation.py
+# --------------------------------------------------------------------------
+class Stack:
+    """Spec-driven restatement of LayerStack + Backpropagation for the layers on
+    the hot path.  ``spec`` entries:
+
+      ("dense", neurons, activation)            layers/core.py:9-42
+      ("act", activation)                       layers/core.py:45-52
+      ("flatten",)                              layers/core.py:70-100
+      ("conv", nfilters, fx, fy, activation)    layers/tensor.py:43-92
+      ("pool", fdim)                            layers/tensor.py:7-40
+      ("lstm", neurons, activation, return_seq) layers/recurrent.py:12-47,80-113
+
+    Weights are drawn with ``white`` in stack order at construction, i.e. with
+    the same RNG consumption as the reference's ``connect`` calls.
+    """
+
+    def __init__(self, input_shape, spec, cost="mse", optimizer="sgd", **opt_hp):
+        if isinstance(input_shape, int):
+            input_shape = (input_shape,)
+        self.input_shape = tuple(input_shape)
+        self.spec = [tuple(s) for s in spec]
+        self.cost = cost
+        self.L = []
+        shape = self.input_shape
+        for s in self.spec:
+            kind = s[0]
+            lay = dict(kind=kind, inshape=shape)
+            if kind == "dense":
+                if len(shape) != 1:
+                    raise RuntimeError("Dense only accepts input shapes with 1 dimension!")
+                n = int(s[1])
+                lay.update(act=s[2] if len(s) > 2 else "linear",
+                           W=white(shape[0], n), b=np.zeros(n))
+                shape = (n,)
+            elif kind == "act":
+                lay.update(act=s[1])
+            elif kind == "flatten":
+                shape = (int(np.prod(shape)),)
+            elif kind == "conv":
+                nf, fx, fy = int(s[1]), int(s[2]), int(s[3])
+                depth, iy, ix = shape[-3:]
+                if iy < fy or ix < fx:
+                    raise RuntimeError("Incompatible shapes")
+                # layers/tensor.py:70: white(nfilters, depth, fx, fy); the op reads dims 2,3 as (fy,fx)
+                lay.update(act=s[4] if len(s) > 4 else "linear",
+                           W=white(nf, depth, fx, fy), b=np.zeros((1, nf, 1, 1)))
+                shape = conv_outshape(shape, lay["W"].shape, "valid")
+            elif kind == "pool":
+                fdim = int(s[1])
+                ic, iy, ix = shape[-3:]
+                if iy % fdim or ix % fdim:
+                    raise RuntimeError("Incompatible shapes: {} % {}".format((ix, iy), fdim))
+                lay.update(fdim=fdim)
+                shape = (ic, iy // fdim, ix // fdim)
+            elif kind == "lstm":
+                n = int(s[1])
+                zdim = shape[-1] + n
+                lay.update(act=s[2] if len(s) > 2 else "tanh", n=n,
+                           return_seq=bool(s[3]) if len(s) > 3 else False,
+                           W=white(zdim, 4 * n), b=np.zeros(4 * n) + 7.0)  # layers/recurrent.py:82,98
+                shape = (shape[0], n) if lay["return_seq"] else (n,)
+            else:
+                raise ValueError(kind)
+            lay["outshape"] = shape
+            if "W" in lay:
+                lay["gW"] = np.zeros_like(lay["W"])
+                lay["gb"] = np.zeros_like(lay["b"])
+            self.L.append(lay)
+        self.outshape = shape
+        self.opt = Optimizer(optimizer, self.num_params, **opt_hp)
+
+    # ---- flat vectors: model/layerstack.py:46-61, layers/abstract_layer.py:40-55
+    @property
+    def trainable(self):
+        return [l for l in self.L if "W" in l]
+
+    @property
+    def num_params(self):
+        return sum(l["W"].size + l["b"].size for l in self.trainable)
+
+    def get_weights(self):
+        return np.concatenate([np.concatenate((l["W"].ravel(), l["b"].ravel())) for l in self.trainable])
+
+    def set_weights(self, w):
+        w = np.asarray(w, dtype=F64)
+        s = 0
+        for l in self.trainable:
+            nW, nb = l["W"].size, l["b"].size
+            l["W"] = w[s:s + nW].reshape(l["W"].shape).copy()
+            l["b"] = w[s + nW:s + nW + nb].reshape(l["b"].shape).copy()
+            s += nW + nb
+
+    def get_gradients(self):
+        return np.concatenate([np.concatenate((l["gW"].ravel(), l["gb"].ravel())) for l in self.trainable])
+
+    def zero_gradients(self):                      # learner/backpropagation.py:68-73
+        for l in self.trainable:
+            l["gW"] = np.zeros_like(l["W"])
+            l["gb"] = np.zeros_like(l["b"])
+
+    # ---- forward: model/layerstack.py:37-40
+    def feedforward(self, X):
+        X = np.asarray(X, dtype=F64)
+        for l in self.L:
+            k = l["kind"]
+            if k == "dense":                       # layers/core.py:27-32
+                l["inputs"] = X
+                X = act_forward(l["act"], dense_forward(X, l["W"], l["b"]))
+            elif k == "act":                       # layers/core.py:47-49
+                X = act_forward(l["act"], X)
+            elif k == "flatten":                   # layers/core.py:82-83
+                X = X.reshape(X.shape[0], -1)
+            elif k == "conv":                      # layers/tensor.py:75-79 (bias AFTER the activation)
+                l["inputs"] = X
+                X = act_forward(l["act"], conv_forward(X, l["W"], "valid")) + l["b"]
+            elif k == "pool":                      # layers/tensor.py:28-30
+                X, l["filter"] = maxpool_forward(X, l["fdim"])
+            elif k == "lstm":                      # layers/recurrent.py:26,101-106
+                l["inputs"] = X.transpose(1, 0, 2)
+                O, l["Z"], l["cache"] = lstm_forward(l["inputs"], l["W"], l["b"], l["act"])
+                l["O"] = O
+                X = O.transpose(1, 0, 2) if l["return_seq"] else O[-1]
+            l["output"] = X
+        return X
+
+    # ---- backward: learner/backpropagation.py:32-35
+    def backpropagate(self, error):
+        error = np.array(error, dtype=F64, copy=True)
+        for l in self.L[::-1]:
+            k = l["kind"]
+            if k == "dense":                       # layers/core.py:34-39 (ACCUMULATES)
+                error = error * act_backward(l["act"], l["output"])
+                dW, db, error = dense_backward(l["inputs"], error, l["W"])
+                l["gW"] = l["gW"] + dW
+                l["gb"] = l["gb"] + db
+            elif k == "act":                       # layers/core.py:51-52
+                error = error * act_backward(l["act"], l["output"])
+            elif k == "flatten":                   # layers/core.py:85-86
+                error = error.reshape((-1,) + tuple(l["inshape"]))
+            elif k == "conv":                      # layers/tensor.py:81-84 (ASSIGNS)
+                error = error * act_backward(l["act"], l["output"])
+                l["gW"], l["gb"], error = conv_backward(l["inputs"], error, l["W"])
+            elif k == "pool":                      # layers/tensor.py:32-33
+                error = maxpool_backward(error, l["filter"])
+            elif k == "lstm":                      # layers/recurrent.py:31-40,108-113 (ASSIGNS)
+                if l["return_seq"]:
+                    E = error.transpose(1, 0, 2)
+                else:
+                    E = np.zeros((l["inputs"].shape[0], len(error), l["n"]))
+                    E[-1] = error
+                dX, l["gW"], l["gb"] = lstm_backward(l["Z"], l["O"], E, l["W"], l["cache"], l["act"])
+                error = dX.transpose(1, 0, 2)
+        return error
+
+    # ---- learner/backpropagation.py:16-30,37-42
+    def learn_batch(self, X, Y, w=None, update=True, metrics=()):
+        m = len(X)
+        preds = self.feedforward(X)
+        delta = cost_derivative(preds, np.asarray(Y, dtype=F64))
+        if w is not None:
+            delta = delta * np.asarray(w)[:, None]
+        self.backpropagate(delta)
+        if update:
+            self.update(m)
+        out = {"cost": cost_value(self.cost, preds, Y) / m}
+        if "acc" in metrics or "accuracy" in metrics:
+            out["accuracy"] = accuracy(preds, Y) / m
+        return out
+
+    def update(self, m):
+        W = self.get_weights()
+        gW = self.get_gradients()
+        self.set_weights(self.opt.optimize(W, gW, m))
+        self.zero_gradients()
+
+
+# --------------------------------------------------------------------------
+# neuro-evolution fitness    learner/neuroevolution.py:20-22,34-37 (+ SURVEY 7.2#10)
+# --------------------------------------------------------------------------
+def as_weights(genome):
+    """learner/neuroevolution.py:20-22."""
+    return (genome - 0.5) * 20.0
+
+
+def fitness(stack, genome, X, Y):
+    """Parity pin for the config-5 path: set_weights(as_weights(g)) ->
+    feedforward(X) -> cost(out, Y)/m (the reference's default ``fitness`` raises
+    TypeError as shipped, neuroevolution.py:36; this is what it intends)."""
+    stack.set_weights(as_weights(np.asarray(genome, dtype=F64)))
+    out = stack.feedforward(X)
+    return cost_value(stack.cost, out, Y) / len(X)
+
+
+def fitness_mlp_logsoftmax(genomes, X, Y, nin, nh, nout):
+    """Vectorised, underflow-free float64 fitness of the Dense(nh,sigmoid) ->
+    Dense(nout,softmax) MLP under cxent for a batch of genomes (P, loci):
+    -sum(Y*log_softmax(logits))/m.  Equal to ``fitness`` wherever the literal
+    float64 formula does not hit log(0)."""
+    G = as_weights(np.asarray(genomes, dtype=F64))
+    o1 = nin * nh
+    W1 = G[:, :o1].reshape(-1, nin, nh)
+    b1 = G[:, o1:o1 + nh]
+    W2 = G[:, o1 + nh:o1 + nh + nh * nout].reshape(-1, nh, nout)
+    b2 = G[:, o1 + nh + nh * nout:]
+    Hh = 1.0 / (1.0 + np.exp(-(np.einsum("nk,pkh->pnh", X, W1) + b1[:, None, :])))
+    L = np.einsum("pnh,pho->pno", Hh, W2) + b2[:, None, :]
+    L = L - L.max(axis=2, keepdims=True)
+    lsm = L - np.log(np.exp(L).sum(axis=2, keepdims=True))
+    return -(Y[None] * lsm).sum(axis=(1, 2)) / len(X)
