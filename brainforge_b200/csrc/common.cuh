@@ -1,0 +1,97 @@
+// Shared host/device helpers for libbf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/bf_b200.h"
+
+namespace bf {
+
+// ---- error plumbing (thread-local message behind bf_last_error) -----------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+#define BF_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return bf::fail(BF_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+#define BF_LAUNCH_CHECK() BF_CUDA(cudaGetLastError())
+#define BF_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) return bf::fail(code, __VA_ARGS__); \
+  } while (0)
+
+// ---- device properties ------------------------------------------------------
+int num_sms();                       // 148 on B200; queried once per process
+void set_last_path(int p);
+// workspace handed in by the host (bf_set_workspace)
+void* workspace_ptr();
+size_t workspace_bytes();
+int workspace_require(size_t bytes, void** out);  // BF_ERR_WORKSPACE when too small
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Grid for grid-stride elementwise kernels: enough CTAs to cover n work items, capped at a
+// multiple of the SM count so that every SM holds the same number of resident CTAs.
+inline int ew_grid(size_t items, int threads, int ctas_per_sm = 8) {
+  size_t need = (items + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---- device helpers -----------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// act(z) for the elementwise kinds (softmax is a row op and handled separately)
+template <int KIND>
+__device__ __forceinline__ float act_fwd(float z) {
+  if (KIND == BF_ACT_SIGMOID) return sigmoidf_(z);
+  if (KIND == BF_ACT_TANH) return tanhf(z);
+  if (KIND == BF_ACT_RELU) return fmaxf(0.0f, z);
+  return z;
+}
+__device__ __forceinline__ float act_fwd_rt(int kind, float z) {
+  switch (kind) {
+    case BF_ACT_SIGMOID: return sigmoidf_(z);
+    case BF_ACT_TANH: return tanhf(z);
+    case BF_ACT_RELU: return fmaxf(0.0f, z);
+    default: return z;
+  }
+}
+// act'(.) expressed from the output a  (atomic/activation_op.py:33,57,79,90,134)
+template <int KIND>
+__device__ __forceinline__ float act_bwd(float a) {
+  if (KIND == BF_ACT_SIGMOID) return a * (1.0f - a);
+  if (KIND == BF_ACT_TANH) return 1.0f - a * a;
+  if (KIND == BF_ACT_RELU) return a > 0.0f ? 1.0f : 0.0f;
+  return 1.0f;
+}
+__device__ __forceinline__ float act_bwd_rt(int kind, float a) {
+  switch (kind) {
+    case BF_ACT_SIGMOID: return a * (1.0f - a);
+    case BF_ACT_TANH: return 1.0f - a * a;
+    case BF_ACT_RELU: return a > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+
+}  // namespace bf

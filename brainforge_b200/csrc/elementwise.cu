@@ -1,0 +1,375 @@
+// Memory-bound kernels: activations and their derivatives, softmax, cost derivative / value,
+// accuracy and the fused optimizer step.  All are 128-bit vectorised grid-stride kernels sized to a
+// multiple of the SM count; reductions use warp shuffles and a deterministic last-block finish.
+#include "common.cuh"
+
+namespace bf {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------ activations
+template <int KIND>
+__global__ void act_fwd_kernel(const float* __restrict__ Z, float* __restrict__ A, size_t n, int vec) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if (vec) {
+    size_t n4 = n >> 2;
+    const float4* z4 = reinterpret_cast<const float4*>(Z);
+    float4* a4 = reinterpret_cast<float4*>(A);
+    for (size_t i = tid; i < n4; i += stride) {
+      float4 v = z4[i];
+      v.x = act_fwd<KIND>(v.x); v.y = act_fwd<KIND>(v.y); v.z = act_fwd<KIND>(v.z); v.w = act_fwd<KIND>(v.w);
+      a4[i] = v;
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) A[i] = act_fwd<KIND>(Z[i]);
+  } else {
+    for (size_t i = tid; i < n; i += stride) A[i] = act_fwd<KIND>(Z[i]);
+  }
+}
+
+template <int KIND>
+__global__ void act_bwd_kernel(const float* __restrict__ A, const float* __restrict__ din, float* __restrict__ dout,
+                               size_t n, int vec) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if (vec) {
+    size_t n4 = n >> 2;
+    const float4* a4 = reinterpret_cast<const float4*>(A);
+    const float4* d4 = reinterpret_cast<const float4*>(din);
+    float4* o4 = reinterpret_cast<float4*>(dout);
+    for (size_t i = tid; i < n4; i += stride) {
+      float4 a = a4[i], d = d4[i];
+      d.x *= act_bwd<KIND>(a.x); d.y *= act_bwd<KIND>(a.y); d.z *= act_bwd<KIND>(a.z); d.w *= act_bwd<KIND>(a.w);
+      o4[i] = d;
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) dout[i] = din[i] * act_bwd<KIND>(A[i]);
+  } else {
+    for (size_t i = tid; i < n; i += stride) dout[i] = din[i] * act_bwd<KIND>(A[i]);
+  }
+}
+
+// Row softmax, n <= 32: one thread per row, three passes over a row that sits in L1 (rows are
+// n*4 <= 128 B; a warp covers 32 consecutive rows = one contiguous span).
+__global__ void softmax_small_kernel(const float* __restrict__ Z, float* __restrict__ A, int m, int n) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (; row < m; row += stride) {
+    const float* z = Z + (size_t)row * n;
+    float* a = A + (size_t)row * n;
+    float mx = z[0];
+    for (int j = 1; j < n; ++j) mx = fmaxf(mx, z[j]);
+    float s = 0.f;
+    for (int j = 0; j < n; ++j) {
+      float e = expf(z[j] - mx);
+      a[j] = e;
+      s += e;
+    }
+    float inv = 1.0f / s;
+    for (int j = 0; j < n; ++j) a[j] *= inv;
+  }
+}
+// n > 32: one warp per row, shuffle reductions.
+__global__ void softmax_warp_kernel(const float* __restrict__ Z, float* __restrict__ A, int m, int n) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < m; row += nwarps) {
+    const float* z = Z + (size_t)row * n;
+    float* a = A + (size_t)row * n;
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) mx = fmaxf(mx, z[j]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      float e = expf(z[j] - mx);
+      a[j] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    float inv = 1.0f / s;
+    for (int j = lane; j < n; j += 32) a[j] *= inv;
+  }
+}
+
+// ------------------------------------------------------------------ cost / metrics
+__global__ void cost_delta_kernel(const float* __restrict__ o, const float* __restrict__ t,
+                                  const float* __restrict__ w, float* __restrict__ d, size_t total, int n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    float v = o[i] - t[i];
+    if (w) v *= w[i / n];
+    d[i] = v;
+  }
+}
+
+// Deterministic two-level sum: each CTA reduces its grid-stride slice in double, writes one partial,
+// and the last CTA to arrive (atomic ticket) adds the partials in index order.
+__device__ unsigned int g_reduce_ticket = 0;
+
+template <int KIND>
+__global__ void cost_value_kernel(const float* __restrict__ o, const float* __restrict__ t, size_t total,
+                                  double* __restrict__ partial, float* __restrict__ result) {
+  __shared__ double sm[32];
+  __shared__ bool last;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (; i < total; i += stride) {
+    float ov = o[i], tv = t[i];
+    if (KIND == BF_COST_MSE) {
+      float d = ov - tv;
+      acc += 0.5 * (double)d * (double)d;
+    } else {
+      if (tv != 0.0f) acc -= (double)tv * (double)logf(ov);
+    }
+  }
+  acc = warp_sum(acc);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sm[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    acc = lane < (blockDim.x >> 5) ? sm[lane] : 0.0;
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      partial[blockIdx.x] = acc;
+      __threadfence();
+      unsigned int ticket = atomicAdd(&g_reduce_ticket, 1u);
+      last = (ticket == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s += ((volatile double*)partial)[b];
+    result[0] = (float)s;
+    g_reduce_ticket = 0;
+  }
+}
+
+__global__ void accuracy_kernel(const float* __restrict__ o, const float* __restrict__ t, int m, int n,
+                                unsigned int* __restrict__ count) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  unsigned int hits = 0;
+  for (; row < m; row += stride) {
+    const float* orow = o + (size_t)row * n;
+    const float* trow = t + (size_t)row * n;
+    int ao = 0, at = 0;
+    float bo = orow[0], bt = trow[0];
+    for (int j = 1; j < n; ++j) {
+      float ov = orow[j], tv = trow[j];
+      if (ov > bo) { bo = ov; ao = j; }   // strict '>' keeps the FIRST maximum, like numpy.argmax
+      if (tv > bt) { bt = tv; at = j; }
+    }
+    hits += (ao == at);
+  }
+  hits = __reduce_add_sync(0xffffffffu, hits);
+  if ((threadIdx.x & 31) == 0 && hits) atomicAdd(count, hits);
+}
+__global__ void count_to_float_kernel(const unsigned int* c, float* r) { r[0] = (float)c[0]; }
+
+// ------------------------------------------------------------------ optimizer
+struct OptHP {
+  float eta_m;  // eta / m
+  float inv_m;  // 1 / m
+  float eta;
+  float hp0, hp1, hp2;
+};
+
+template <int KIND>
+__device__ __forceinline__ void opt_update(float& w, float g, float& s1, float& s2, const OptHP& h) {
+  if (KIND == BF_OPT_SGD) {                 // gradient_descent.py:8-9
+    w = w - g * h.eta_m;
+  } else if (KIND == BF_OPT_MOMENTUM) {     // gradient_descent.py:25-28
+    s1 = s1 * h.hp0 + g * h.eta_m;
+    w = w - s1;
+  } else if (KIND == BF_OPT_NESTEROV) {     // gradient_descent.py:44-50 (literal)
+    float nabla = g * h.eta_m;
+    float wn = s2 - s1 + nabla;
+    s2 = w;
+    s1 = s1 * h.hp0 + nabla;
+    w = wn;
+  } else if (KIND == BF_OPT_ADAGRAD) {      // adaptive_gd.py:16-20
+    float nabla = g * h.inv_m;
+    s2 = s2 + nabla * nabla;
+    w = w - (h.eta / sqrtf(s2 + h.hp0)) * nabla;
+  } else if (KIND == BF_OPT_RMSPROP) {      // adaptive_gd.py:71-76
+    float nabla = g * h.inv_m;
+    s2 = s2 * h.hp0 + (1.0f - h.hp0) * nabla * nabla;
+    w = w - (h.eta * nabla) / sqrtf(s2 + h.hp1);
+  } else {                                  // ADAM, adaptive_gd.py:94-99 (non-standard form)
+    s1 = h.hp0 * s1 + (1.0f - h.hp0) * g;
+    s2 = h.hp1 * s2 + (1.0f - h.hp1) * g * g;
+    w = w - (h.eta_m * s1) / sqrtf(s2 + h.hp2);
+  }
+}
+
+template <int KIND, bool HAS1, bool HAS2>
+__global__ void opt_kernel(float* __restrict__ W, float* __restrict__ G, float* __restrict__ S1,
+                           float* __restrict__ S2, size_t n, OptHP h, int zero_grad, int vec) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  size_t n4 = vec ? (n >> 2) : 0;
+  float4* W4 = reinterpret_cast<float4*>(W);
+  float4* G4 = reinterpret_cast<float4*>(G);
+  float4* S14 = reinterpret_cast<float4*>(S1);
+  float4* S24 = reinterpret_cast<float4*>(S2);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = tid; i < n4; i += stride) {
+    float4 w = W4[i], g = G4[i];
+    float4 a = HAS1 ? S14[i] : zero4, b = HAS2 ? S24[i] : zero4;
+    opt_update<KIND>(w.x, g.x, a.x, b.x, h);
+    opt_update<KIND>(w.y, g.y, a.y, b.y, h);
+    opt_update<KIND>(w.z, g.z, a.z, b.z, h);
+    opt_update<KIND>(w.w, g.w, a.w, b.w, h);
+    W4[i] = w;
+    if (HAS1) S14[i] = a;
+    if (HAS2) S24[i] = b;
+    if (zero_grad) G4[i] = zero4;
+  }
+  for (size_t i = (n4 << 2) + tid; i < n; i += stride) {
+    float w = W[i], g = G[i], a = HAS1 ? S1[i] : 0.f, b = HAS2 ? S2[i] : 0.f;
+    opt_update<KIND>(w, g, a, b, h);
+    W[i] = w;
+    if (HAS1) S1[i] = a;
+    if (HAS2) S2[i] = b;
+    if (zero_grad) G[i] = 0.f;
+  }
+}
+
+}  // namespace bf
+
+using namespace bf;
+
+extern "C" {
+
+int bf_act_forward(int kind, const float* Z, float* A, size_t n, void* stream) {
+  if (n == 0) return BF_OK;
+  BF_REQUIRE(Z && A, BF_ERR_ARG, "bf_act_forward: null pointer");
+  cudaStream_t s = as_stream(stream);
+  int vec = aligned16(Z) && aligned16(A);
+  int grid = ew_grid((n + 3) / 4, 256);
+  switch (kind) {
+    case BF_ACT_LINEAR:
+      if (Z != A) BF_CUDA(cudaMemcpyAsync(A, Z, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      return BF_OK;
+    case BF_ACT_SIGMOID: act_fwd_kernel<BF_ACT_SIGMOID><<<grid, 256, 0, s>>>(Z, A, n, vec); break;
+    case BF_ACT_TANH: act_fwd_kernel<BF_ACT_TANH><<<grid, 256, 0, s>>>(Z, A, n, vec); break;
+    case BF_ACT_RELU: act_fwd_kernel<BF_ACT_RELU><<<grid, 256, 0, s>>>(Z, A, n, vec); break;
+    default: return fail(BF_ERR_ARG, "bf_act_forward: unsupported activation kind %d (softmax is bf_softmax_forward)", kind);
+  }
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_softmax_forward(const float* Z, float* A, int m, int n, void* stream) {
+  BF_REQUIRE(m >= 0 && n > 0, BF_ERR_ARG, "bf_softmax_forward: bad shape (%d,%d)", m, n);
+  if (m == 0) return BF_OK;
+  cudaStream_t s = as_stream(stream);
+  if (n <= 32)
+    softmax_small_kernel<<<ew_grid(m, 128), 128, 0, s>>>(Z, A, m, n);
+  else
+    softmax_warp_kernel<<<ew_grid((size_t)m * 32, 256), 256, 0, s>>>(Z, A, m, n);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_act_backward(int kind, const float* A, const float* din, float* dout, size_t n, void* stream) {
+  if (n == 0) return BF_OK;
+  BF_REQUIRE(din && dout, BF_ERR_ARG, "bf_act_backward: null pointer");
+  cudaStream_t s = as_stream(stream);
+  int vec = aligned16(A) && aligned16(din) && aligned16(dout);
+  int grid = ew_grid((n + 3) / 4, 256);
+  switch (kind) {
+    case BF_ACT_LINEAR:
+    case BF_ACT_SOFTMAX:  // activation_op.py:79-80,134-135: derivative is the scalar 1
+      if (din != dout) BF_CUDA(cudaMemcpyAsync(dout, din, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      return BF_OK;
+    case BF_ACT_SIGMOID: act_bwd_kernel<BF_ACT_SIGMOID><<<grid, 256, 0, s>>>(A, din, dout, n, vec); break;
+    case BF_ACT_TANH: act_bwd_kernel<BF_ACT_TANH><<<grid, 256, 0, s>>>(A, din, dout, n, vec); break;
+    case BF_ACT_RELU: act_bwd_kernel<BF_ACT_RELU><<<grid, 256, 0, s>>>(A, din, dout, n, vec); break;
+    default: return fail(BF_ERR_ARG, "bf_act_backward: unknown activation kind %d", kind);
+  }
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_cost_delta(const float* out, const float* tgt, const float* w, float* delta, int m, int n, void* stream) {
+  BF_REQUIRE(m >= 0 && n > 0, BF_ERR_ARG, "bf_cost_delta: bad shape (%d,%d)", m, n);
+  size_t total = (size_t)m * n;
+  if (total == 0) return BF_OK;
+  cost_delta_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(out, tgt, w, delta, total, n);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, float* result, void* stream) {
+  BF_REQUIRE(m >= 0 && n > 0 && result, BF_ERR_ARG, "bf_cost_value: bad arguments");
+  size_t total = (size_t)m * n;
+  cudaStream_t s = as_stream(stream);
+  if (total == 0) {
+    BF_CUDA(cudaMemsetAsync(result, 0, sizeof(float), s));
+    return BF_OK;
+  }
+  int grid = ew_grid(total, 256, 1);
+  void* ws = nullptr;
+  int rc = workspace_require((size_t)grid * sizeof(double), &ws);
+  if (rc) return rc;
+  if (kind == BF_COST_MSE)
+    cost_value_kernel<BF_COST_MSE><<<grid, 256, 0, s>>>(out, tgt, total, (double*)ws, result);
+  else if (kind == BF_COST_CXENT)
+    cost_value_kernel<BF_COST_CXENT><<<grid, 256, 0, s>>>(out, tgt, total, (double*)ws, result);
+  else
+    return fail(BF_ERR_ARG, "bf_cost_value: unknown cost kind %d", kind);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_accuracy(const float* out, const float* tgt, int m, int n, float* result, void* stream) {
+  BF_REQUIRE(m >= 0 && n > 0 && result, BF_ERR_ARG, "bf_accuracy: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  void* ws = nullptr;
+  int rc = workspace_require(sizeof(unsigned int), &ws);
+  if (rc) return rc;
+  BF_CUDA(cudaMemsetAsync(ws, 0, sizeof(unsigned int), s));
+  if (m > 0) accuracy_kernel<<<ew_grid(m, 128), 128, 0, s>>>(out, tgt, m, n, (unsigned int*)ws);
+  count_to_float_kernel<<<1, 1, 0, s>>>((const unsigned int*)ws, result);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_opt_step(int kind, float* W, float* g, float* s1, float* s2, size_t n, float eta, float m, float hp0, float hp1,
+                float hp2, int zero_grad, void* stream) {
+  if (n == 0) return BF_OK;
+  BF_REQUIRE(W && g, BF_ERR_ARG, "bf_opt_step: null W or g");
+  BF_REQUIRE(m > 0.f, BF_ERR_ARG, "bf_opt_step: m must be positive");
+  cudaStream_t s = as_stream(stream);
+  OptHP h;
+  h.eta = eta; h.eta_m = eta / m; h.inv_m = 1.0f / m; h.hp0 = hp0; h.hp1 = hp1; h.hp2 = hp2;
+  int vec = aligned16(W) && aligned16(g) && (!s1 || aligned16(s1)) && (!s2 || aligned16(s2));
+  int grid = ew_grid((n + 3) / 4, 256);
+  switch (kind) {
+    case BF_OPT_SGD:
+      opt_kernel<BF_OPT_SGD, false, false><<<grid, 256, 0, s>>>(W, g, nullptr, nullptr, n, h, zero_grad, vec);
+      break;
+    case BF_OPT_MOMENTUM:
+      BF_REQUIRE(s1, BF_ERR_ARG, "bf_opt_step: momentum needs velocity (s1)");
+      opt_kernel<BF_OPT_MOMENTUM, true, false><<<grid, 256, 0, s>>>(W, g, s1, nullptr, n, h, zero_grad, vec);
+      break;
+    case BF_OPT_NESTEROV:
+      BF_REQUIRE(s1 && s2, BF_ERR_ARG, "bf_opt_step: nesterov needs velocity (s1) and memory (s2)");
+      opt_kernel<BF_OPT_NESTEROV, true, true><<<grid, 256, 0, s>>>(W, g, s1, s2, n, h, zero_grad, vec);
+      break;
+    case BF_OPT_ADAGRAD:
+      BF_REQUIRE(s2, BF_ERR_ARG, "bf_opt_step: adagrad needs memory (s2)");
+      opt_kernel<BF_OPT_ADAGRAD, false, true><<<grid, 256, 0, s>>>(W, g, nullptr, s2, n, h, zero_grad, vec);
+      break;
+    case BF_OPT_RMSPROP:
+      BF_REQUIRE(s2, BF_ERR_ARG, "bf_opt_step: rmsprop needs memory (s2)");
+      opt_kernel<BF_OPT_RMSPROP, false, true><<<grid, 256, 0, s>>>(W, g, nullptr, s2, n, h, zero_grad, vec);
+      break;
+    case BF_OPT_ADAM:
+      BF_REQUIRE(s1 && s2, BF_ERR_ARG, "bf_opt_step: adam needs velocity (s1) and memory (s2)");
+      opt_kernel<BF_OPT_ADAM, true, true><<<grid, 256, 0, s>>>(W, g, s1, s2, n, h, zero_grad, vec);
+      break;
+    default: return fail(BF_ERR_ARG, "bf_opt_step: unknown optimizer kind %d", kind);
+  }
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+"""Device plumbing: FP32 arrays resident in HBM behind a NumPy-like facade.
+
+PyTorch is used here for device memory (caching allocator), the current CUDA stream, CUDA graphs and
+`torch.distributed` -- plumbing only.  Every arithmetic kernel is in libbf_b200.so and is reached through
+`call()`; there is no torch op and no CPU path behind any layer.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_state = {"workspace": None, "precision": _lib.PREC["fp32"]}
+DEFAULT_WORKSPACE = 64 << 20
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("brainforge_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback. "
+                           "The float64 CPU oracle lives under oracle/ and is test infrastructure only.")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def set_precision(name):
+    """'fp32' (SIMT FMA, <=1e-5 vs the float64 reference) or 'tf32' (tcgen05 tensor cores)."""
+    _state["precision"] = _lib.PREC[name]
+
+
+def precision():
+    return _state["precision"]
+
+
+def precision_name():
+    return {v: k for k, v in _lib.PREC.items()}[_state["precision"]]
+
+
+def _ensure_workspace(nbytes):
+    ws = _state["workspace"]
+    if ws is None or ws.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("workspace must be sized before CUDA-graph capture (run the step once eagerly)")
+        nbytes = max(int(nbytes), DEFAULT_WORKSPACE)
+        torch.cuda.synchronize()
+        _state["workspace"] = None
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        _state["workspace"] = ws
+        _lib.check(_lib.lib.bf_set_workspace(ctypes.c_void_p(ws.data_ptr()), ws.numel()))
+    return ws
+
+
+def call(fn, *args):
+    """Invoke a libbf_b200 entry point; grows the scratch workspace and retries once if asked to."""
+    if _state["workspace"] is None:
+        _ensure_workspace(DEFAULT_WORKSPACE)
+    try:
+        _lib.check(fn(*args))
+    except _lib.WorkspaceTooSmall as e:
+        _ensure_workspace(int(e.need * 1.25) + 4096)
+        _lib.check(fn(*args))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class DeviceArray:
+    """A C-contiguous FP32 tensor in HBM with the handful of ndarray attributes the reference's callers
+    touch on layer state (`.shape`, `.size`, `.ndim`, `*= 0`, `np.asarray(..)`): SURVEY 7.2#7."""
+
+    __array_priority__ = 100
+
+    def __init__(self, tensor):
+        assert tensor.dtype == torch.float32 and tensor.is_cuda and tensor.is_contiguous(), \
+            (tensor.dtype, tensor.device, tensor.is_contiguous())
+        self.t = tensor
+
+    # ---- construction
+    @staticmethod
+    def empty(*shape):
+        require_cuda()
+        return DeviceArray(torch.empty(tuple(int(s) for s in shape), dtype=torch.float32, device="cuda"))
+
+    @staticmethod
+    def zeros(*shape):
+        require_cuda()
+        return DeviceArray(torch.zeros(tuple(int(s) for s in shape), dtype=torch.float32, device="cuda"))
+
+    @staticmethod
+    def from_host(a):
+        """H2D.  float32 C-contiguous arrays (ideally pinned) are copied as they are; anything else is
+        shipped as float64 and narrowed on the device (bf_cast_f64_to_f32)."""
+        out = DeviceArray.empty(*np.shape(a))
+        out.copy_from_host(a)
+        return out
+
+    def copy_from_host(self, a):
+        a = np.asarray(a)
+        if tuple(a.shape) != self.shape:
+            a = a.reshape(self.shape)
+        if a.size == 0:
+            return self
+        if a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]:
+            call(_lib.lib.bf_memcpy_h2d, self.ptr, ctypes.c_void_p(a.ctypes.data), a.nbytes, stream_ptr())
+            if not _is_pinned(a):
+                call(_lib.lib.bf_stream_sync, stream_ptr())  # pageable source may be reused by the caller
+        else:
+            a64 = np.ascontiguousarray(a, dtype=np.float64)
+            stage = torch.empty(a64.size, dtype=torch.float64, device="cuda")
+            call(_lib.lib.bf_memcpy_h2d, _ptr(stage), ctypes.c_void_p(a64.ctypes.data), a64.nbytes, stream_ptr())
+            call(_lib.lib.bf_cast_f64_to_f32, _ptr(stage), self.ptr, a64.size, stream_ptr())
+            call(_lib.lib.bf_stream_sync, stream_ptr())
+        return self
+
+    # ---- ndarray-like surface
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.t.data_ptr())
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape)
+
+    @property
+    def size(self):
+        return self.t.numel()
+
+    @property
+    def ndim(self):
+        return self.t.dim()
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def __len__(self):
+        return self.t.shape[0]
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return DeviceArray(self.t.view(*[int(s) for s in shape]))
+
+    def ravel(self):
+        return self.reshape(-1)
+
+    def __getitem__(self, idx):
+        v = self.t[idx]
+        if not v.is_contiguous():
+            raise IndexError("DeviceArray only supports slices that stay contiguous")
+        return DeviceArray(v)
+
+    def numpy(self, dtype=np.float64):
+        """D2H copy (synchronises the stream); float64 by default like the reference's arrays."""
+        host = np.empty(self.shape, dtype=np.float32)
+        if host.size:
+            call(_lib.lib.bf_memcpy_d2h, ctypes.c_void_p(host.ctypes.data), self.ptr, host.nbytes, stream_ptr())
+            call(_lib.lib.bf_stream_sync, stream_ptr())
+        return host.astype(dtype, copy=False)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.numpy(np.float64 if dtype is None else dtype)
+
+    def copy(self):
+        out = DeviceArray.empty(*self.shape)
+        if self.size:
+            call(_lib.lib.bf_act_forward, _lib.ACT["linear"], self.ptr, out.ptr, self.size, stream_ptr())
+        return out
+
+    def fill_zero(self):
+        if self.size:
+            call(_lib.lib.bf_affine, self.ptr, self.ptr, self.size, 0.0, 0.0, stream_ptr())
+        return self
+
+    def __imul__(self, scalar):
+        # `layer.nabla_w *= 0` (learner/backpropagation.py:72-73) and friends
+        s = float(scalar)
+        if self.size:
+            call(_lib.lib.bf_affine, self.ptr, self.ptr, self.size, s, 0.0, stream_ptr())
+        return self
+
+    def __repr__(self):
+        return "DeviceArray(shape=%s, fp32 @ cuda)" % (self.shape,)
+
+
+_pinned_ranges = []
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """A NumPy array backed by page-locked host memory (fast, truly asynchronous H2D source)."""
+    tdtype = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+    t = torch.empty(tuple(shape), dtype=tdtype, pin_memory=True)
+    a = t.numpy()
+    _pinned_ranges.append((a.ctypes.data, a.ctypes.data + a.nbytes, t))
+    return a
+
+
+def _is_pinned(a):
+    p = a.ctypes.data
+    return any(lo <= p < hi for lo, hi, _ in _pinned_ranges)
+
+
+def as_device(x):
+    """numpy / DeviceArray -> DeviceArray (no copy when already on the device)."""
+    if isinstance(x, DeviceArray):
+        return x
+    return DeviceArray.from_host(x)
+
+
+def synchronize():
+    call(_lib.lib.bf_stream_sync, stream_ptr())

@@ -1,0 +1,69 @@
+"""Data-parallel plumbing: one process per GPU, `torch.distributed` (NCCL over NVLink / NVSwitch on the
+GPU box, gloo in the CPU tests).  The hot path has exactly one collective per learn_batch: an
+all-reduce(sum) of the flat gradient vector (with the step scalars riding at its tail)."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+
+def initialized():
+    return td.is_available() and td.is_initialized()
+
+
+def world_size():
+    return td.get_world_size() if initialized() else 1
+
+
+def rank():
+    return td.get_rank() if initialized() else 0
+
+
+def init_from_env(backend=None):
+    """Initialise from the torchrun environment (RANK, LOCAL_RANK, WORLD_SIZE, MASTER_ADDR, MASTER_PORT)."""
+    if initialized() or int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        backend = backend or "nccl"
+    else:
+        backend = backend or "gloo"
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    td.init_process_group(backend=backend)
+
+
+def allreduce_sum(flat):
+    """In-place sum over ranks of a DeviceArray (or torch tensor)."""
+    if world_size() == 1:
+        return flat
+    t = flat if isinstance(flat, torch.Tensor) else flat.t
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return flat
+
+
+def global_count(m_local):
+    """Sum of per-rank batch sizes (equal shards: m_local * world_size, no collective needed)."""
+    return m_local * world_size()
+
+
+def shard_bounds(n, r=None, ws=None):
+    """Contiguous, even split of n units over ranks; the first n % ws ranks get one extra."""
+    r = rank() if r is None else r
+    ws = world_size() if ws is None else ws
+    base, rem = divmod(n, ws)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+def gather_concat(local, counts):
+    """All-gather of variable-length 1-D float arrays (fitness values) -> concatenated host array."""
+    if world_size() == 1:
+        return np.asarray(local)
+    dev = "cuda" if td.get_backend() == "nccl" else "cpu"
+    mx = max(counts)
+    buf = torch.zeros(mx, dtype=torch.float64, device=dev)
+    buf[:len(local)] = torch.as_tensor(np.asarray(local, dtype=np.float64), device=dev)
+    outs = [torch.zeros(mx, dtype=torch.float64, device=dev) for _ in counts]
+    td.all_gather(outs, buf)
+    return np.concatenate([o[:c].cpu().numpy() for o, c in zip(outs, counts)])

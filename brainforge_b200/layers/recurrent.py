@@ -1,0 +1,60 @@
+"""layers/recurrent.py of the reference: the LSTM layer (RLayer/GRU/Clockwork/Reservoir are out of scope)."""
+import ctypes
+
+import numpy as np
+
+from .. import atomic, _lib
+from ..device import DeviceArray, call, stream_ptr
+from ..util import white
+from .abstract_layer import FFBase
+
+
+def _transpose01(x):
+    d0, d1, d2 = x.shape
+    out = DeviceArray.empty(d1, d0, d2)
+    call(_lib.lib.bf_transpose01, x.ptr, out.ptr, d0, d1, d2, stream_ptr())
+    return out
+
+
+class LSTM(FFBase):
+    """layers/recurrent.py:12-47,80-113.  Input (B,T,D) batch-major like the reference; weights
+    white(D+H, 4H), biases +7.0 (bias_init_factor, :82,:98); gradients are ASSIGNED (:110)."""
+
+    def __init__(self, neurons, activation, bias_init_factor=7., return_seq=False, **kw):
+        super().__init__(neurons, activation, **kw)
+        self.G = neurons * 3
+        self.Z = 0
+        self.cache = None
+        self.time = 0
+        self.return_seq = return_seq
+        self.bias_init_factor = bias_init_factor
+        self.op = atomic.LSTMOp(activation if isinstance(activation, str) else str(activation))
+
+    def connect(self, brain):
+        self.Z = brain.outshape[-1] + self.neurons
+        self._init_params(white(self.Z, self.neurons * 4), np.zeros(self.neurons * 4) + self.bias_init_factor)
+        super().connect(brain)
+
+    def _fwd(self, x):
+        self.inputs = _transpose01(x)                       # (B,T,D) -> (T,B,D), recurrent.py:26
+        self.time = self.inputs.shape[0]
+        self.output, self.Z, self.cache = self.op.forward(self.inputs, self.weights, self.biases)
+        return _transpose01(self.output) if self.return_seq else self.output[-1]
+
+    def _bwd(self, delta):
+        if self.return_seq:
+            E = _transpose01(delta)                         # recurrent.py:35-36
+        else:
+            E = DeviceArray.zeros(self.time, len(delta), self.neurons)   # recurrent.py:38-40
+            last = E[-1]
+            call(_lib.lib.bf_act_forward, _lib.ACT["linear"], delta.ptr, last.ptr, last.size, stream_ptr())
+        dX, _, _ = self.op.backward(Z=self.Z, O=self.output, E=E, W=self.weights, cache=self.cache,
+                                    nablaW=self.nabla_w, nablab=self.nabla_b)
+        return _transpose01(dX)
+
+    @property
+    def outshape(self):
+        return self.neurons,
+
+    def __str__(self):
+        return self.__class__.__name__ + "-{}-{}".format(self.neurons, str(self.activation)[:4])

@@ -1,0 +1,84 @@
+"""layers/tensor.py of the reference: PoolLayer, ConvLayer."""
+import numpy as np
+
+from .. import atomic
+from ..util import white
+from .abstract_layer import LayerBase, NoParamMixin
+
+
+class PoolLayer(NoParamMixin, LayerBase):
+    """layers/tensor.py:7-40."""
+
+    def __init__(self, filter_size, compiled=True):
+        LayerBase.__init__(self, activation="linear", trainable=False)
+        self.fdim = filter_size
+        self.filter = None
+        self.op = atomic.MaxPoolOp()
+        self._outshape = None
+
+    def connect(self, brain):
+        ic, iy, ix = brain.outshape[-3:]
+        if any((iy % self.fdim, ix % self.fdim)):
+            raise RuntimeError("Incompatible shapes: {} % {}".format((ix, iy), self.fdim))
+        LayerBase.connect(self, brain)
+        self._outshape = (ic, iy // self.fdim, ix // self.fdim)
+
+    def _fwd(self, x):
+        self.output, self.filter = self.op.forward(x, self.fdim)
+        return self.output
+
+    def _bwd(self, delta):
+        return self.op.backward(delta, self.filter)
+
+    @property
+    def outshape(self):
+        return self._outshape
+
+    def __str__(self):
+        return "Pool-{}x{}".format(self.fdim, self.fdim)
+
+
+class ConvLayer(LayerBase):
+    """layers/tensor.py:43-92.  Quirks kept on purpose: the bias is added AFTER the activation (:77-78),
+    gradients are ASSIGNED not accumulated (:83), weights are white(nfilters, depth, fx, fy) (:70) and the
+    op reads dims 2,3 of the filter as (rows, cols).  `outshape` reports the true output shape (the
+    reference swaps the two spatial entries, :86-89; identical for square inputs and filters)."""
+
+    def __init__(self, nfilters, filterx=3, filtery=3, compiled=True, **kw):
+        super().__init__(compiled=compiled, **kw)
+        self.nfilters = nfilters
+        self.fx = filterx
+        self.fy = filtery
+        self.depth = 0
+        self.stride = 1
+        self.inshape = None
+        self.op = None
+
+    def connect(self, brain):
+        depth, iy, ix = brain.outshape[-3:]
+        if any((iy < self.fy, ix < self.fx)):
+            raise RuntimeError("Incompatible shapes: iy ({}) < fy ({}) OR ix ({}) < fx ({})"
+                               .format(iy, self.fy, ix, self.fx))
+        super().connect(brain)
+        self.op = atomic.ConvolutionOp()
+        self.inshape = brain.outshape
+        self.depth = depth
+        self._init_params(white(self.nfilters, self.depth, self.fx, self.fy),
+                          np.zeros((1, self.nfilters, 1, 1)))
+
+    def _fwd(self, x):
+        self.inputs = x
+        self.output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation))
+        return self.output
+
+    def _bwd(self, delta):
+        delta = self.activation.backward_mul(self.output, delta)
+        _, _, dX = self.op.backward(X=self.inputs, E=delta, F=self.weights, dF=self.nabla_w, db=self.nabla_b)
+        return dX
+
+    @property
+    def outshape(self):
+        return self.op.outshape(self.inshape, self.weights.shape, "valid")
+
+    def __str__(self):
+        return "Conv({}x{}x{})-{}".format(self.nfilters, self.fy, self.fx, str(self.activation)[:4])

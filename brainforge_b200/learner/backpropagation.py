@@ -1,0 +1,149 @@
+"""learner/backpropagation.py of the reference: the training step (forward, cost', backward, update).
+
+Device flow of one `learn_batch` (everything between the two host copies stays in HBM):
+  H2D X,Y -> layers._fwd -> bf_cost_delta -> layer._bwd (reverse) -> [all-reduce(sum) of the flat gradient
+  vector + step scalars when data-parallel] -> ONE fused optimizer kernel over the flat parameter vector
+  (also clears the gradients) -> D2H of the step scalars (cost sum, hits).
+Gradients are batch SUMS (atomic/core_op.py:17-19) and the 1/m lives in the optimizer
+(optimizers/gradient_descent.py:9), so sharding the batch over ranks and all-reducing the sums with the
+GLOBAL m is algebraically exact.
+"""
+import numpy as np
+import torch
+
+from .abstract_learner import Learner
+from ..device import DeviceArray, as_device
+from ..metrics import metrics as _metrics
+from ..optimizers import optimizers, GradientDescent
+from .. import dist as _dist
+
+
+class Backpropagation(Learner):
+
+    def __init__(self, layerstack, cost="mse", optimizer="sgd", name="", **kw):
+        super().__init__(layerstack, cost, name, **kw)
+        self.optimizer = optimizer if isinstance(optimizer, GradientDescent) else optimizers[optimizer]()
+        self.optimizer.initialize(nparams=self.layers.num_params)
+        self.layers.flatten_parameters()
+        self.use_graph = kw.get("use_graph", False)
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ the hot path
+    def learn_batch(self, X, Y, w=None, metrics=(), update=True):
+        """learner/backpropagation.py:16-30.  Under torch.distributed (world_size > 1) X, Y are this
+        rank's shard of the global batch; cost and metrics are those of the GLOBAL batch."""
+        metrics = [_metrics.get(m) for m in metrics]
+        self.layers.flatten_parameters()
+        if self.use_graph and w is None and not isinstance(X, DeviceArray):
+            return self._learn_batch_graph(X, Y, metrics, update)
+        x, y = as_device(X), as_device(Y)
+        wd = as_device(w) if w is not None else None
+        m_local = len(x)
+        self._step(x, y, wd, metrics, update, m_local, None)
+        return self._read_scalars(metrics, m_local)
+
+    def _step(self, x, y, wd, metrics, update, m_local, m_global_static):
+        """Device-only part of learn_batch (capturable in a CUDA graph: no host sync inside)."""
+        sc = self.layers.scalars()
+        preds = self.layers._fwd(x)
+        delta = self.cost.derivative(preds, y, wd)
+        self.cost.value_into(preds, y, sc[0:1])          # cost of the PRE-update forward pass (:26)
+        if metrics:
+            _metrics.accuracy.value_into(preds, y, sc[1:2])
+        self._bwd(delta)
+        if _dist.world_size() > 1:
+            # gradients + step scalars in ONE collective (scalars alone when no update follows)
+            _dist.allreduce_sum(self.layers.flat_grads if update else sc)
+        if update:
+            self.update(m_global_static if m_global_static is not None else _dist.global_count(m_local))
+
+    def _read_scalars(self, metrics, m_local):
+        sc = self.layers.scalars().numpy()
+        m = _dist.global_count(m_local)
+        out = {"cost": float(sc[0]) / m}
+        for metric in metrics:
+            out[str(metric).lower()] = float(sc[1]) / m
+        return out
+
+    def _learn_batch_graph(self, X, Y, metrics, update):
+        """CUDA-graph replay of the step for a fixed (shape, metrics, update) signature: the ~dozens of
+        kernel launches of a step collapse into one graph launch (small-batch configs are launch-bound,
+        SURVEY 7.2#6).  Inputs are staged through static device buffers."""
+        X, Y = np.asarray(X), np.asarray(Y)
+        key = (X.shape, Y.shape, tuple(str(m) for m in metrics), bool(update), float(self.optimizer.eta))
+        entry = self._graphs.get(key)
+        m_local = len(X)
+        if entry is None:
+            xs, ys = DeviceArray.empty(*X.shape), DeviceArray.empty(*Y.shape)
+            xs.copy_from_host(X)
+            ys.copy_from_host(Y)
+            m_global = m_local * _dist.world_size()
+            # first call runs eagerly (sizes the workspace, warms every kernel), later calls replay
+            self._step(xs, ys, None, metrics, update, m_local, m_global)
+            out = self._read_scalars(metrics, m_local)
+            self._graphs[key] = {"x": xs, "y": ys, "graph": None, "m_global": m_global, "calls": 1}
+            return out
+        entry["x"].copy_from_host(X)
+        entry["y"].copy_from_host(Y)
+        if entry["graph"] is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    self._step(entry["x"], entry["y"], None, metrics, update, m_local, entry["m_global"])
+            torch.cuda.current_stream().wait_stream(side)
+            entry["graph"] = g
+        entry["graph"].replay()
+        return self._read_scalars(metrics, m_local)
+
+    # ------------------------------------------------------------------ pieces of the public API
+    def _bwd(self, error):
+        for layer in self.layers[-1:0:-1]:
+            error = layer._bwd(error)
+        return error
+
+    def backpropagate(self, error):
+        """learner/backpropagation.py:32-35; returns the delta w.r.t. the network input."""
+        out = self._bwd(as_device(error) if isinstance(error, DeviceArray) else DeviceArray.from_host(error))
+        return out if isinstance(error, DeviceArray) else out.numpy()
+
+    def update(self, m):
+        """learner/backpropagation.py:37-42 without the host round trip: one fused kernel reads W, g (and
+        the optimizer state), writes W (and state) and clears g (zero_gradients, :68-73)."""
+        L = self.layers
+        L.flatten_parameters()
+        n = L.flat_size
+        self.optimizer.optimize(L.flat_weights[0:n], L.flat_grads[0:n], m, zero_grad=True)
+
+    def get_weights(self, unfold=True):
+        return self.layers.get_weights(unfold=unfold)
+
+    def set_weigts(self, ws, fold=True):   # (sic) the reference's spelling, learner/backpropagation.py:47
+        self.layers.set_weights(ws=ws, fold=fold)
+
+    set_weights = set_weigts
+
+    def get_gradients(self, unfold=True):
+        return self.layers.get_gradients(unfold=unfold)
+
+    def zero_gradients(self):
+        self.layers.flatten_parameters()
+        self.layers.flat_grads.fill_zero()
+        for layer in self.layers:
+            if layer.weights is not None and not layer.trainable:
+                layer.nabla_w.fill_zero()
+                layer.nabla_b.fill_zero()
+
+    @property
+    def num_params(self):
+        return self.layers.num_params
+
+    @property
+    def output_shape(self):
+        return self.layers.output_shape
+
+    @property
+    def input_shape(self):
+        return self.layers.input_shape

@@ -1,0 +1,68 @@
+"""metrics/costs.py of the reference: cost value + the `outputs - targets` shortcut derivative.
+
+Values are reduced on the device (bf_cost_value) and come back as one float; derivative stays in HBM.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+from ..device import DeviceArray, as_device, call, stream_ptr
+
+L = _lib.lib
+_NULL = ctypes.c_void_p(0)
+
+
+class CostFunction:
+    kind = None
+
+    def value_into(self, outputs, targets, result):
+        """result[0] = cost, no host sync (used by the learner's fused step)."""
+        o, t = as_device(outputs), as_device(targets)
+        m = o.shape[0]
+        n = o.size // max(m, 1)
+        call(L.bf_cost_value, _lib.COST[self.kind], o.ptr, t.ptr, m, n, result.ptr, stream_ptr())
+
+    def __call__(self, outputs, targets):
+        res = DeviceArray.empty(1)
+        self.value_into(outputs, targets, res)
+        return float(res.numpy()[0])
+
+    def __str__(self):
+        return self.__class__.__name__
+
+    @staticmethod
+    def derivative(outputs, targets, w=None):
+        """metrics/costs.py:19-21 (+ the per-sample weights of learner/backpropagation.py:20-21)."""
+        o, t = as_device(outputs), as_device(targets)
+        m = o.shape[0]
+        n = o.size // max(m, 1)
+        delta = DeviceArray.empty(*o.shape)
+        wd = as_device(w) if w is not None else None
+        call(L.bf_cost_delta, o.ptr, t.ptr, wd.ptr if wd is not None else _NULL, delta.ptr, m, n, stream_ptr())
+        return delta if isinstance(outputs, DeviceArray) else delta.numpy()
+
+
+class _MeanSquaredError(CostFunction):
+    kind = "mse"           # metrics/costs.py:24-31
+
+
+class _CategoricalCrossEntropy(CostFunction):
+    kind = "cxent"         # metrics/costs.py:34-43
+
+
+mean_squared_error = _MeanSquaredError()
+categorical_crossentropy = _CategoricalCrossEntropy()
+mse = mean_squared_error
+cxent = categorical_crossentropy
+
+_costs = {"mean_squared_error": mse, "categorical_crossentropy": cxent, "mse": mse, "cxent": cxent}
+
+
+def get(cost_function):
+    if isinstance(cost_function, CostFunction):
+        return cost_function
+    cost = _costs.get(cost_function)
+    if cost is None:
+        raise ValueError("No such cost function: {}".format(cost_function))
+    return cost

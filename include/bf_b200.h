@@ -1,0 +1,156 @@
+/* bf_b200.h -- C ABI of libbf_b200.so, the B200 (sm_100a) back-end for the
+ * brainforge layer forward/backward + optimizer hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one operator of the
+ * reference's `atomic` / `llatomic` op layer, its cost/metric functions or its
+ * optimizer step (reference paths are relative to /root/reference/brainforge).
+ * Plain pointers and sizes only; no torch / numpy types.  All `float*` /
+ * `uint8_t*` arguments are DEVICE pointers unless the name starts with `h_`.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Tensors are dense, C-contiguous ("row-major"), FP32 in HBM; the reference
+ * computes in float64 (config/numeric.py:1) -- see DESIGN.md for tolerances.
+ *
+ * Error convention: every function returns 0 on success, non-zero on failure;
+ * bf_last_error() then returns a thread-local, NUL-terminated description.  The
+ * Python shim maps BF_ERR_VALUE -> ValueError (tensor_op.py:18-21) and the rest
+ * -> RuntimeError.  Nothing here ever falls back to a CPU implementation.
+ */
+#ifndef BF_B200_H
+#define BF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BF_API __attribute__((visibility("default")))
+#else
+#define BF_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BF_OK 0
+#define BF_ERR_CUDA 1     /* CUDA runtime / launch failure                  */
+#define BF_ERR_VALUE 2    /* incompatible shapes (reference: ValueError)    */
+#define BF_ERR_ARG 3      /* bad enum / null pointer / unsupported size     */
+#define BF_ERR_WORKSPACE 4 /* bf_set_workspace() buffer too small           */
+
+/* activation kinds: atomic/activation_op.py:157-159 registry */
+enum { BF_ACT_LINEAR = 0, BF_ACT_SIGMOID = 1, BF_ACT_TANH = 2, BF_ACT_RELU = 3, BF_ACT_SOFTMAX = 4 };
+/* cost kinds: metrics/costs.py:72-80 */
+enum { BF_COST_MSE = 0, BF_COST_CXENT = 1 };
+/* optimizer kinds: optimizers/__init__.py:4-6 */
+enum { BF_OPT_SGD = 0, BF_OPT_MOMENTUM = 1, BF_OPT_NESTEROV = 2, BF_OPT_ADAGRAD = 3, BF_OPT_RMSPROP = 4, BF_OPT_ADAM = 5 };
+/* conv modes: atomic/tensor_op.py:42-46 */
+enum { BF_CONV_VALID = 0, BF_CONV_FULL = 1 };
+/* arithmetic path of the contraction kernels */
+enum {
+  BF_PREC_FP32 = 0, /* FP32 FMA accumulate on the SIMT pipe: <=1e-5 rel. vs the float64 reference */
+  BF_PREC_TF32 = 1  /* tcgen05 kind::tf32 tensor cores, FP32 accumulate in TMEM: looser bound */
+};
+
+/* ---- library / plumbing ------------------------------------------------ */
+BF_API const char* bf_last_error(void);
+BF_API int bf_version(void);
+/* SM count and compute capability of the current device. */
+BF_API int bf_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Scratch HBM for split-K partials etc.; owned by the caller (the Python host hands a torch buffer). */
+BF_API int bf_set_workspace(void* d_ptr, size_t bytes);
+/* Which kernel family the last contraction call on this thread used: 0 = SIMT FP32, 1 = tcgen05 TF32. */
+BF_API int bf_last_path(void);
+BF_API int bf_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
+BF_API int bf_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+BF_API int bf_stream_sync(void* stream);
+/* float64 <-> float32 on the device (host API speaks float64 like the reference, HBM holds FP32). */
+BF_API int bf_cast_f64_to_f32(const double* d_src, float* d_dst, size_t n, void* stream);
+BF_API int bf_cast_f32_to_f64(const float* d_src, double* d_dst, size_t n, void* stream);
+/* (d0,d1,d2) -> (d1,d0,d2): layers/recurrent.py:26 `X.transpose(1, 0, 2)`. */
+BF_API int bf_transpose01(const float* src, float* dst, int d0, int d1, int d2, void* stream);
+/* dst[i] = a*x[i] + b  (NeuroEvolution.as_weights, learner/neuroevolution.py:20-22, is a=20,b=-10). */
+BF_API int bf_affine(const float* x, float* dst, size_t n, float a, float b, void* stream);
+
+/* ---- activations: atomic/activation_op.py ------------------------------- */
+/* A = act(Z), elementwise; replaces Sigmoid/Tanh/ReLU/Linear.forward (:30,:54,:76,:87) and
+ * llatomic/_llactivation.py:15-52.  In place allowed. */
+BF_API int bf_act_forward(int kind, const float* Z, float* A, size_t n, void* stream);
+/* Row softmax with max subtraction over axis 1: SoftMax.t1 (:127-130). In place allowed. */
+BF_API int bf_softmax_forward(const float* Z, float* A, int m, int n, void* stream);
+/* dout = din * act'(A) with the derivative expressed from the OUTPUT A (:33,:57,:79,:90,:134);
+ * this is `delta *= activation.backward(output)` of layers/core.py:35,:52.  In place allowed. */
+BF_API int bf_act_backward(int kind, const float* A, const float* din, float* dout, size_t n, void* stream);
+
+/* ---- dense: atomic/core_op.py:9-20, llatomic/_llops.py:7-9 -------------- */
+/* out = act(X@W + b); X (m,k), W (k,n), b (n) or NULL, out (m,n).  act fuses the layer's
+ * activation (layers/core.py:29-31); BF_ACT_SOFTMAX applies the row softmax. */
+BF_API int bf_dense_forward(const float* X, const float* W, const float* b, float* out, int m, int k, int n, int act,
+                     int precision, void* stream);
+/* DenseOp.backward(X,E,W) -> (dW,db,dX): dW = X^T@E (k,n), db = E.sum(0) (n), dX = E@W^T (m,k).
+ * accumulate!=0 adds into dW/db (layers/core.py:37-38 `nabla_w += ...`), else assigns.
+ * dX may be NULL (skipped). */
+BF_API int bf_dense_backward(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int k,
+                      int n, int accumulate, int precision, void* stream);
+
+/* ---- convolution: atomic/tensor_op.py:6-75, llatomic/lltensor_op.py:9-40,75-121 ---- */
+/* Y = act(corr(A,F)) + bias   (bias AFTER the activation: layers/tensor.py:77-78).
+ * A (im,ic,iy,ix) NCHW, F (nf,ic,fy,fx), bias (nf) or NULL, stride 1.
+ * VALID: Y (im,nf,iy-fy+1,ix-fx+1); FULL: zero padding f-1, Y (im,nf,iy+fy-1,ix+fx-1).
+ * Returns BF_ERR_VALUE when filter depth != input depth (tensor_op.py:18-21). */
+BF_API int bf_conv_forward(const float* A, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix,
+                    int nf, int fc, int fy, int fx, int mode, int act, int precision, void* stream);
+/* ConvolutionOp.backward(X,E,F) -> (dF,db,dX) for the VALID forward (tensor_op.py:49-61):
+ * dF (nf,ic,fy,fx), db (nf) = E.sum((0,2,3)), dX (im,ic,iy,ix) = full(E, flip(F)^T).
+ * Assigns (layers/tensor.py:83).  dX may be NULL. */
+BF_API int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, float* db, float* dX, int im, int ic,
+                     int iy, int ix, int nf, int fy, int fx, int precision, void* stream);
+
+/* ---- max pooling: atomic/tensor_op.py:78-128, llatomic/lltensor_op.py:43-72 ---- */
+/* Bytes per window of the compact tie mask: 1 when fdim*fdim<=8, else 8 (fdim<=8). */
+BF_API size_t bf_pool_mask_bytes(int im, int ic, int iy, int ix, int fdim);
+/* MaxPoolOp.forward(A,fdim) -> (out, filt).  The multi-hot equality mask (bit dy*fdim+dx set for
+ * EVERY element equal to the window max) is stored compactly, one word per window. */
+BF_API int bf_pool_forward(const float* A, float* out, uint8_t* mask, int im, int ic, int iy, int ix, int fdim, void* stream);
+/* MaxPoolOp.backward(E,filt) -> dX (im,ic,iy,ix) = filt * upsample(E).  Does not consume the mask. */
+BF_API int bf_pool_backward(const float* E, const uint8_t* mask, float* dX, int im, int ic, int iy, int ix, int fdim,
+                     void* stream);
+/* Expands the compact mask to the reference's float `filt` array (A's shape, 0.0/1.0). */
+BF_API int bf_pool_mask_expand(const uint8_t* mask, float* filt, int im, int ic, int iy, int ix, int fdim, void* stream);
+
+/* ---- costs / metrics: metrics/costs.py:11-37, metrics/metrics.py:13-16 ---- */
+/* delta = (out - tgt) * (w ? w[row] : 1): CostFunction.derivative + learner/backpropagation.py:19-21. */
+BF_API int bf_cost_delta(const float* out, const float* tgt, const float* w, float* delta, int m, int n, void* stream);
+/* result[0] (+)= cost: MSE = 0.5*sum((o-t)^2), CXENT = -sum(t*log o) (terms with t==0 contribute 0). */
+BF_API int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, float* result, void* stream);
+/* result[0] = count(argmax_1(out) == argmax_1(tgt)), first maximum wins like numpy. */
+BF_API int bf_accuracy(const float* out, const float* tgt, int m, int n, float* result, void* stream);
+
+/* ---- LSTM: atomic/recurrent_op.py:46-112, llatomic/_lllstm.py:6-67 ---- */
+/* LSTMOp(act).forward(X,W,b) -> (O,Z,cache).  X (T,B,D) time-major, W (D+H,4H) gate order
+ * [cand|f|i|o], b (4H); O (T,B,H), Z (T,B,D+H), cache (6,T,B,H) = C,Ca,cand,f,i,o. */
+BF_API int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, int T, int B,
+                    int D, int H, int act, int precision, void* stream);
+/* LSTMOp.backward(Z,O,E,W,cache) -> (dX (T,B,D), nablaW (D+H,4H), nablab (4H)); E (T,B,H) is read only.
+ * Scratch (deltaZ, dgates, deltaC) comes from the workspace. */
+BF_API int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache, float* dX,
+                     float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream);
+
+/* ---- optimizer step on the flat vectors: optimizers/*.py, learner/backpropagation.py:37-42 ---- */
+/* W <- optimize(W, g, m) in place.  s1 = velocity, s2 = memory (NULL where the rule has none).
+ * hp: SGD{} MOMENTUM{mu} NESTEROV{mu} ADAGRAD{eps} RMSPROP{decay,eps} ADAM{decay_velocity,decay_memory,eps}.
+ * zero_grad!=0 also clears g (zero_gradients, backpropagation.py:68-73) in the same pass. */
+BF_API int bf_opt_step(int kind, float* W, float* g, float* s1, float* s2, size_t n, float eta, float m, float hp0, float hp1,
+                float hp2, int zero_grad, void* stream);
+
+/* ---- neuro-evolution fitness fan-out: evolution/_evolution.py:83-97 + learner/neuroevolution.py:20-22,34-37 ---- */
+/* For each of P genomes (rows of `genomes`, `loci` = nin*nh+nh+nh*nout+nout floats in U(0,1)):
+ * weights = (g-0.5)*20 -> Dense(nh,sigmoid) -> Dense(nout,softmax) on the shared X (N,nin) ->
+ * fitness[p] = -sum(Y*log_softmax(logits))/N  (cxent/m, computed from log-softmax so FP32 does not
+ * underflow where float64 does not).  Scratch for the hidden activations comes from the workspace. */
+BF_API int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* fitness, int P, int N, int nin, int nh,
+                   int nout, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BF_B200_H */

@@ -1,0 +1,213 @@
+"""Network-level parity on the B200 through the unchanged Layer / LayerStack / Backpropagation API:
+golden trajectories from the reference, the five BASELINE configs against the float64 oracle, size-
+independent properties at full size, CUDA-graph replay, and the neuro-evolution fan-out.
+
+Tolerances: FP32 path, norm-wise relative error <= 1e-5 per layer output / gradient / weight vector
+(<= 3e-5 after several Adam steps); costs <= 1e-5; accuracy counts and pooling masks exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+from golden_nets import NETS
+from helpers import CFG, build_b200, build_oracle, onehot
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32():
+    import torch
+    assert torch.cuda.is_available()
+    import brainforge_b200 as bf
+    bf.set_precision("fp32")
+    yield
+
+
+def close(a, b, tol=1e-5):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert relerr(a, b) <= tol, relerr(a, b)
+
+
+@pytest.mark.parametrize("name", sorted(NETS))
+def test_golden_trajectories(name):
+    from brainforge_b200.layers import Flatten, LSTM
+    seed, ishape, spec, cost, optimizer, batch = NETS[name]
+    g = load_golden("net_" + name)
+    net = build_b200(ishape, spec, cost, optimizer, seed=seed)
+    close(net.layers.get_weights(), g["W0"], 1e-7)       # same seed -> same `white` init as the reference
+    X, Y = g["X"], g["Y"]
+    m0 = net.learn_batch(X, Y, metrics=["acc"], update=False)
+    close(m0["cost"], g["cost0"])
+    assert abs(m0["accuracy"] - g["acc0"]) < 1e-12
+    close(net.get_gradients(), g["grad0"])
+    for li, layer in enumerate(net.layers.layers[1:]):
+        if "out%d" % li in g:
+            o = np.asarray(layer.output)
+            if isinstance(layer, LSTM):
+                o = o.transpose(1, 0, 2) if layer.return_seq else o[-1]
+            close(o, g["out%d" % li])
+    preds = net.predict(X)
+    close(net.backpropagate(net.cost.derivative(preds, Y)), g["input_delta"])
+    close(net.get_gradients(), g["grad0_twice"])          # Dense accumulates, Conv/LSTM assign
+    net.zero_gradients()
+    assert not net.get_gradients().any()
+    for step in range(3):
+        mm = net.learn_batch(X, Y)
+        close(mm["cost"], g["costs"][step])
+        close(net.layers.get_weights(), g["weights"][step], 3e-5)
+        assert not net.get_gradients().any()               # update() clears the gradients (backpropagation.py:42)
+
+
+@pytest.mark.parametrize("cfg,batch", [("cfg1", 20), ("cfg2", 32), ("cfg3", 16), ("cfg4", 6)])
+def test_baseline_configs_vs_oracle(cfg, batch):
+    ishape, spec, cost, optimizer = CFG[cfg]
+    net = build_b200(ishape, spec, cost, optimizer, seed=1234)
+    ora = build_oracle(ishape, spec, cost, optimizer, seed=1234)
+    close(net.layers.get_weights(), ora.get_weights(), 1e-7)
+    rs = np.random.RandomState(99)
+    X = rs.randn(batch, *ishape)
+    Y = onehot(rs, batch, 10)
+    a = net.learn_batch(X, Y, metrics=["acc"], update=False)
+    b = ora.learn_batch(X, Y, metrics=("acc",), update=False)
+    close(a["cost"], b["cost"])
+    assert a["accuracy"] == b["accuracy"]
+    close(net.get_gradients(), ora.get_gradients())
+    # per-layer outputs and per-layer gradients
+    for mine, ref in zip(net.layers.layers[1:], ora.L):
+        if ref["kind"] in ("dense", "conv", "act", "pool"):
+            close(np.asarray(mine.output), ref["output"])
+        if ref["kind"] == "pool":
+            assert np.array_equal(np.asarray(mine.filter), ref["filter"])        # bit-exact tie mask
+        if "W" in ref:
+            close(np.asarray(mine.nabla_w), ref["gW"]); close(np.asarray(mine.nabla_b), ref["gb"])
+    net.zero_gradients(); ora.zero_gradients()
+    for _ in range(2):
+        a, b = net.learn_batch(X, Y), ora.learn_batch(X, Y)
+        close(a["cost"], b["cost"])
+    close(net.layers.get_weights(), ora.get_weights(), 3e-5)
+    assert np.array_equal(net.predict(X).argmax(1), ora.feedforward(X).argmax(1))
+
+
+def test_cfg3_full_batch_properties():
+    """Size-independent properties at the BASELINE batch (4096): gradients are batch SUMS, so the gradient
+    of the full batch equals the sum over two halves; pooling masks have >= 1 hit per window; cost is the
+    sum of per-half costs."""
+    ishape, spec, cost, optimizer = CFG["cfg3"]
+    net = build_b200(ishape, spec, cost, optimizer, seed=7)
+    rs = np.random.RandomState(5)
+    B = 4096
+    X = rs.randn(B, *ishape).astype(np.float32)
+    Y = onehot(rs, B, 10).astype(np.float32)
+    full = net.learn_batch(X, Y, metrics=["acc"], update=False)
+    g_full = net.get_gradients().copy()
+    for layer in net.layers.layers:
+        if type(layer).__name__ == "PoolLayer":
+            f = np.asarray(layer.filter)
+            im, ic, iy, ix = f.shape
+            assert f.reshape(im, ic, iy // 2, 2, ix // 2, 2).sum(axis=(3, 5)).min() >= 1
+    net.zero_gradients()
+    h1 = net.learn_batch(X[:B // 2], Y[:B // 2], metrics=["acc"], update=False)
+    g1 = net.get_gradients().copy()
+    net.zero_gradients()
+    h2 = net.learn_batch(X[B // 2:], Y[B // 2:], metrics=["acc"], update=False)
+    g2 = net.get_gradients().copy()
+    close(g_full, g1 + g2, 2e-5)
+    close(full["cost"], (h1["cost"] + h2["cost"]) / 2, 1e-5)
+    assert abs(full["accuracy"] - (h1["accuracy"] + h2["accuracy"]) / 2) < 1e-9
+
+
+def test_cuda_graph_replay_matches_eager():
+    ishape, spec, cost, optimizer = CFG["cfg2"]
+    eager = build_b200(ishape, spec, cost, optimizer, seed=3)
+    graph = build_b200(ishape, spec, cost, optimizer, seed=3, use_graph=True)
+    rs = np.random.RandomState(4)
+    for step in range(5):
+        X = rs.randn(32, *ishape).astype(np.float32)
+        Y = onehot(rs, 32, 10).astype(np.float32)
+        a = eager.learn_batch(X, Y, metrics=["acc"])
+        b = graph.learn_batch(X, Y, metrics=["acc"])
+        assert a == b, (step, a, b)
+    assert np.array_equal(eager.layers.get_weights(), graph.layers.get_weights())
+
+
+def test_api_surface_like_the_reference():
+    """The attributes / methods outside callers poke."""
+    import brainforge_b200 as bf
+    from brainforge_b200.layers import Dense, Flatten
+    np.random.seed(0)
+    net = bf.BackpropNetwork(input_shape=(2, 3), layerstack=[Flatten(), Dense(4, activation="tanh"), Dense(2)],
+                             cost="mse", optimizer="momentum")
+    assert net.layers.num_params == net.num_params == 6 * 4 + 4 + 4 * 2 + 2
+    assert net.layers.outshape == (2,) and net.layers[1].outshape == (6,)
+    d = net.layers[2]
+    assert d.weights.shape == (6, 4) and d.weights.size == 24 and d.biases.shape == (4,)
+    w = net.layers.get_weights()
+    net.layers.set_weights(w * 2)
+    close(net.layers.get_weights(), w * 2, 1e-7)
+    close(np.concatenate([l.get_weights() for l in net.layers.trainable_layers]), w * 2, 1e-7)
+    X = np.random.randn(5, 2, 3)
+    out = net.predict(X)
+    assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (5, 2)
+    assert np.asarray(net.output).shape == (5, 2)
+    net.backpropagate(out - 1.0)
+    d.nabla_w *= 0                                   # learner/backpropagation.py:72
+    assert not np.asarray(d.nabla_w).any() and np.asarray(net.layers[3].nabla_w).any()
+    hist = net.fit(X, np.random.randn(5, 2), batch_size=5, epochs=2, verbose=0, metrics=[])
+    assert len(hist["cost"]) == 2
+    ev = net.evaluate(X, np.random.randn(5, 2))
+    assert "cost" in ev.mean()
+    with pytest.raises(RuntimeError, match="Dense only accepts"):
+        bf.Backpropagation(input_shape=(2, 3), layerstack=[Dense(4)], cost="mse")
+
+
+def test_gradient_check_through_the_api():
+    """The reference's own integration test (gradientcheck/gradientcheck.py:8-24), FP32-adapted: central
+    differences with a larger epsilon, thresholds loosened from 1e-5 to 2e-2 for FP32 cost evaluation."""
+    ishape, spec = (1, 8, 8), [("conv", 3, 3, 3, "linear"), ("pool", 2), ("act", "relu"), ("flatten",), ("dense", 4, "softmax")]
+    net = build_b200(ishape, spec, "cxent", "sgd", seed=2)
+    rs = np.random.RandomState(8)
+    X, Y = rs.randn(6, *ishape), onehot(rs, 6, 4)
+    preds = net.predict(X)
+    net.backpropagate(net.cost.derivative(preds, Y))
+    analytic = net.get_gradients()
+    ws = net.layers.get_weights()
+    numeric = np.zeros_like(ws)
+    eps = 1e-2
+    for i in range(ws.size):
+        p = np.zeros_like(ws); p[i] = eps
+        net.layers.set_weights(ws + p); c1 = net.cost(net.predict(X), Y)
+        net.layers.set_weights(ws - p); c2 = net.cost(net.predict(X), Y)
+        numeric[i] = (c1 - c2) / (2 * eps)
+    assert relerr(analytic, numeric) < 2e-2, relerr(analytic, numeric)
+
+
+def test_neuroevolution_fitness_fanout():
+    import brainforge_b200 as bf
+    from brainforge_b200.layers import Dense
+    from oracle import bf_oracle as O
+    g = load_golden("evolution")
+    nin, nh, nout = (int(v) for v in g["dims"])
+    np.random.seed(0)
+    ne = bf.NeuroEvolution(input_shape=(nin,), layerstack=[Dense(nh, activation="sigmoid"), Dense(nout, activation="softmax")],
+                           cost="cxent", population_size=len(g["genomes"]))
+    # golden fitness from the reference (narrow genomes) through the fused fan-out and the generic per-individual path
+    close(ne.batch_fitness(g["genomes"], g["X"], g["Y"]).ravel(), g["fitness"], 1e-5)
+    close([ne.fitness(gen, g["X"], g["Y"]) for gen in g["genomes"]], g["fitness"], 1e-5)
+    # wide (+-10) genomes: log-softmax form reproduces the float64 value where FP32 probabilities underflow
+    close(ne.batch_fitness(g["genomes_wide"], g["X"], g["Y"]).ravel(),
+          O.fitness_mlp_logsoftmax(g["genomes_wide"], g["X"], g["Y"], nin, nh, nout), 1e-5)
+    # cfg5 shapes (reduced population): 784-60-10, N=256
+    rs = np.random.RandomState(1)
+    np.random.seed(1)
+    ne5 = bf.NeuroEvolution(input_shape=(784,), layerstack=[Dense(60, activation="sigmoid"), Dense(10, activation="softmax")],
+                            cost="cxent", population_size=24)
+    X, Y = rs.randn(256, 784), onehot(rs, 256, 10)
+    ne5.population.update(None, 0, X=X, Y=Y)
+    ref = O.fitness_mlp_logsoftmax(ne5.population.individuals, X, Y, 784, 60, 10)
+    close(ne5.population.grades, ref, 2e-5)
+    # a full learn_batch (selection / mating / mutation on the host, fitness on the device) improves the best grade
+    before = ne5.population.grades.min()
+    ne5.learn_batch(X, Y, epochs=2)
+    assert ne5.population.grades.min() <= before + 1e-9

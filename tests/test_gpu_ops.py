@@ -1,0 +1,221 @@
+"""Op-level parity on the B200: libbf_b200 (through the `b200atomic` mirror of the reference's op API)
+against the golden vectors produced by the reference and against the float64 CPU oracle.
+
+Tolerances (stated): FP32 SIMT path -- relative error ||a-b||/max(||a||,||b||) <= 1e-5 for
+every float result; pooling outputs / masks / pool gradients and argmax counts are bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def bf():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import brainforge_b200 as bf
+    bf.set_precision("fp32")
+    return bf
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import bf_oracle
+    return bf_oracle
+
+
+def close(a, b, tol=TOL):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert relerr(a, b) <= tol, relerr(a, b)
+
+
+# ---------------------------------------------------------------- golden vectors from the reference
+def test_dense_golden(bf, golden_ops):
+    g = golden_ops
+    op = bf.atomic.DenseOp()
+    close(op.forward(g["dense_X"], g["dense_W"], g["dense_b"]), g["dense_Z"])
+    dW, db, dX = op.backward(g["dense_X"], g["dense_E"], g["dense_W"])
+    close(dW, g["dense_dW"]); close(db, g["dense_db"]); close(dX, g["dense_dX"])
+    close(op.forward(g["dense12_X"], g["dense12_W"], g["dense12_b"]), g["dense12_Z"])   # tests/test_numba_ops.py:61-72
+
+
+def test_conv_golden(bf, golden_ops):
+    g = golden_ops
+    op = bf.atomic.ConvolutionOp()
+    close(op.forward(g["conv_A"], g["conv_F"], "valid"), g["conv_valid"])
+    close(op.forward(g["conv_A"], g["conv_F"], "full"), g["conv_full"])
+    dF, db, dX = op.backward(X=g["conv_A"], E=g["conv_E"], F=g["conv_F"])
+    close(dF, g["conv_dF"]); close(db, g["conv_db"]); close(dX, g["conv_dX"])
+    close(op.forward(g["conv12_A"], g["conv12_F"], mode="full"), g["conv12_full"])      # tests/test_numba_ops.py:27-37
+    with pytest.raises(ValueError, match="filter depth"):
+        op.forward(np.zeros((1, 2, 5, 5)), np.zeros((1, 3, 3, 3)))
+
+
+def test_pool_golden_bit_exact(bf, golden_ops):
+    g = golden_ops
+    op = bf.atomic.MaxPoolOp()
+    for p, fd in (("pool", 2), ("pool3", 3), ("pool12", 2)):     # pool12: tests/test_numba_ops.py:42-56
+        A32 = g[p + "_A"].astype(np.float32)
+        assert np.array_equal(A32.astype(np.float64), g[p + "_A"]) or p != "pool"   # the tie fixture is FP32-exact
+        out, filt = op.forward(g[p + "_A"], fd)
+        if p == "pool":
+            assert np.array_equal(out, g[p + "_out"])
+            assert np.array_equal(filt, g[p + "_filt"])       # multi-hot tie mask, bit-exact
+        else:
+            close(out, g[p + "_out"], 1e-7)
+            assert np.array_equal(filt, g[p + "_filt"])       # distinct random values: same argmax after rounding
+        E = g[p + "_E"] if p + "_E" in g else g[p + "_out"]
+        dX = op.backward(E, filt)
+        close(dX, g[p + "_dX"], 1e-7)
+        assert np.array_equal(dX != 0, g[p + "_dX"] != 0)
+
+
+def test_activations_golden(bf, golden_ops):
+    g = golden_ops
+    for kind in ("sigmoid", "tanh", "relu", "linear"):
+        act = bf.atomic.activations[kind]()
+        a = act.forward(g["act_Z"])
+        close(a, g["act_%s_fwd" % kind])
+        bw = act.backward(g["act_%s_fwd" % kind])
+        close(np.asarray(bw) * np.ones(len(g["act_Z"])), g["act_%s_bwd" % kind])
+    close(bf.atomic.SoftMax().forward(g["softmax_Z"]), g["softmax_A"])
+    assert bf.atomic.ReLU().backward(np.zeros(3))[0] == 0.0   # NumPy semantics: relu'(0) = 0
+
+
+def test_costs_and_accuracy_golden(bf, golden_ops):
+    g = golden_ops
+    close(bf.metrics.mse(g["cost_O"], g["cost_T"]), g["cost_mse"])
+    close(bf.metrics.cxent(g["cost_O"], g["cost_T"]), g["cost_cxent"])
+    close(bf.metrics.mse.derivative(g["cost_O"], g["cost_T"]), g["cost_delta"])
+    assert bf.metrics.accuracy(g["cost_O"], g["cost_T"]) == int(g["cost_acc"])
+
+
+def test_lstm_golden(bf, golden_ops):
+    g = golden_ops
+    O_, Z_, C_ = bf.atomic.LSTMOp("tanh").forward(g["lstm20_X"], g["lstm20_W"], g["lstm20_b"])   # tests/test_numba_ops.py:91-115
+    close(O_, g["lstm20_O"]); close(Z_, g["lstm20_Z"]); close(C_, g["lstm20_cache"])
+    for act in ("tanh", "relu"):
+        op = bf.atomic.LSTMOp(act)
+        O_, Z_, C_ = op.forward(g["lstm_X"], g["lstm_W"], g["lstm_b"])
+        close(O_, g["lstm_%s_O" % act]); close(Z_, g["lstm_%s_Z" % act]); close(C_, g["lstm_%s_cache" % act])
+        dX, gW, gb = op.backward(Z=g["lstm_%s_Z" % act], O=g["lstm_%s_O" % act], E=g["lstm_%s_E" % act],
+                                 W=g["lstm_W"], cache=g["lstm_%s_cache" % act])
+        close(dX, g["lstm_%s_dX" % act]); close(gW, g["lstm_%s_gW" % act]); close(gb, g["lstm_%s_gb" % act])
+
+
+@pytest.mark.parametrize("name", ["sgd", "momentum", "nesterov", "adagrad", "rmsprop", "adam"])
+def test_optimizers_golden(bf, golden_ops, name):
+    g = golden_ops
+    opt = bf.optimizers.optimizers[name]()
+    opt.initialize(nparams=g["opt_W0"].size)
+    W = g["opt_W0"].copy()
+    for step, grad in enumerate(g["opt_g"]):
+        W = opt.optimize(W, grad, 7)
+        close(W, g["opt_" + name][step], 2e-6)
+
+
+# ---------------------------------------------------------------- oracle at ragged / awkward shapes
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (20, 784, 60), (20, 60, 10), (33, 17, 5), (257, 130, 129), (4096, 512, 10)])
+def test_dense_vs_oracle(bf, O, m, k, n):
+    rs = np.random.RandomState(m * 131 + k)
+    X, W, b, E = rs.randn(m, k), rs.randn(k, n) * 0.2, rs.randn(n), rs.randn(m, n)
+    op = bf.atomic.DenseOp()
+    close(op.forward(X, W, b), O.dense_forward(X, W, b))
+    for act in ("sigmoid", "tanh", "relu", "softmax"):
+        close(op.forward(X, W, b, activation=act), O.act_forward(act, O.dense_forward(X, W, b)))
+    dW, db, dX = op.backward(X, E, W)
+    rW, rb, rX = O.dense_backward(X, E, W)
+    close(dW, rW); close(db, rb); close(dX, rX)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 1, 28, 28, 8, 3, 3), (3, 3, 30, 30, 32, 3, 3), (2, 32, 14, 14, 64, 3, 3), (5, 64, 6, 6, 128, 3, 3),
+    (1, 1, 3, 3, 1, 3, 3), (2, 5, 9, 7, 3, 2, 4), (1, 2, 6, 6, 17, 5, 1), (3, 4, 8, 8, 6, 1, 1),
+])
+def test_conv_vs_oracle(bf, O, shape):
+    im, ic, iy, ix, nf, fy, fx = shape
+    rs = np.random.RandomState(sum(shape))
+    A, F, bias = rs.randn(im, ic, iy, ix), rs.randn(nf, ic, fy, fx) * 0.3, rs.randn(nf)
+    op = bf.atomic.ConvolutionOp()
+    yv = O.conv_forward(A, F, "valid")
+    close(op.forward(A, F, "valid"), yv)
+    close(op.forward(A, F, "full"), O.conv_forward(A, F, "full"))
+    # layer epilogue: act(conv) + bias, bias AFTER the activation (layers/tensor.py:77-78)
+    close(op.forward(A, F, "valid", bias=bias, activation="tanh"), np.tanh(yv) + bias[None, :, None, None])
+    E = rs.randn(*yv.shape)
+    dF, db, dX = op.backward(X=A, E=E, F=F)
+    rF, rb, rX = O.conv_backward(A, E, F)
+    close(dF, rF); close(db, rb); close(dX, rX)
+
+
+@pytest.mark.parametrize("shape,fdim", [((2, 8, 26, 26), 2), ((3, 32, 28, 28), 2), ((2, 3, 9, 12), 3), ((1, 2, 8, 8), 4),
+                                        ((1, 1, 16, 8), 8), ((2, 2, 5, 7), 1)])
+def test_pool_vs_oracle_bit_exact(bf, O, shape, fdim):
+    rs = np.random.RandomState(fdim)
+    A = np.maximum(0, np.round(rs.randn(*shape) * 2) / 2).astype(np.float32).astype(np.float64)   # relu'd, many ties
+    op = bf.atomic.MaxPoolOp()
+    out, filt = op.forward(A, fdim)
+    ro, rf = O.maxpool_forward(A, fdim)
+    assert np.array_equal(out, ro) and np.array_equal(filt, rf)
+    E = rs.randn(*ro.shape).astype(np.float32).astype(np.float64)
+    assert np.array_equal(op.backward(E, filt), O.maxpool_backward(E, rf))
+    # device-resident mask object behaves like the reference's filt array
+    from brainforge_b200 import DeviceArray
+    o2, mask = op.forward(DeviceArray.from_host(A), fdim)
+    assert np.array_equal(np.asarray(mask), rf) and mask.shape == A.shape
+    assert np.array_equal(op.backward(DeviceArray.from_host(E), mask).numpy(), O.maxpool_backward(E, rf))
+
+
+def test_pool_rejects_non_divisible(bf):
+    with pytest.raises(ValueError, match="Incompatible shapes"):
+        bf.atomic.MaxPoolOp().forward(np.zeros((1, 1, 5, 4)), 2)
+
+
+@pytest.mark.parametrize("T,B,D,H,act", [(1, 1, 1, 1, "tanh"), (7, 3, 5, 4, "tanh"), (4, 33, 20, 17, "relu"), (16, 8, 128, 256, "tanh")])
+def test_lstm_vs_oracle(bf, O, T, B, D, H, act):
+    rs = np.random.RandomState(T * 7 + H)
+    X, W, b = rs.randn(T, B, D), rs.randn(D + H, 4 * H) * np.sqrt(2.0 / (D + 5 * H)), rs.randn(4 * H) * 0.1
+    op = bf.atomic.LSTMOp(act)
+    O_, Z_, C_ = op.forward(X, W, b)
+    rO, rZ, rC = O.lstm_forward(X, W, b, act)
+    close(O_, rO); close(Z_, rZ); close(C_, rC)
+    E = rs.randn(T, B, H)
+    dX, gW, gb = op.backward(Z=rZ, O=rO, E=E, W=W, cache=rC)
+    rX, rW, rb = O.lstm_backward(rZ, rO, E, W, rC, act)
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
+def test_empty_batch(bf):
+    op = bf.atomic.DenseOp()
+    assert op.forward(np.zeros((0, 5)), np.ones((5, 3)), np.zeros(3)).shape == (0, 3)
+    dW, db, dX = op.backward(np.zeros((0, 5)), np.zeros((0, 3)), np.ones((5, 3)))
+    assert not dW.any() and not db.any() and dX.shape == (0, 5)
+    assert bf.atomic.ConvolutionOp().forward(np.zeros((0, 2, 6, 6)), np.ones((3, 2, 3, 3))).shape == (0, 3, 4, 4)
+
+
+def test_softmax_wide_rows_and_large_logits(bf, O):
+    rs = np.random.RandomState(0)
+    Z = rs.randn(37, 200) * 50
+    close(bf.atomic.SoftMax().forward(Z), O.act_forward("softmax", Z))
+
+
+def test_accuracy_first_max_wins(bf):
+    o = np.array([[1., 1., 0.], [0., 2., 2.], [3., 1., 3.]])
+    t = np.array([[1., 0., 0.], [0., 0., 1.], [0., 0., 1.]])
+    assert bf.metrics.accuracy(o, t) == int(np.sum(o.argmax(1) == t.argmax(1))) == 1
+
+
+def test_large_cost_reduction_is_deterministic(bf, O):
+    rs = np.random.RandomState(1)
+    o = O.act_forward("softmax", rs.randn(50000, 10))
+    t = np.eye(10)[rs.randint(0, 10, 50000)]
+    a, b = bf.metrics.cxent(o, t), bf.metrics.cxent(o, t)
+    assert a == b
+    close(a, O.cost_value("cxent", o, t), 1e-6)
+    close(bf.metrics.mse(o, t), O.cost_value("mse", o, t), 1e-6)

@@ -1,0 +1,104 @@
+"""CPU tests of the host logic: sharding, the host GA, and the N>1 plumbing over gloo (world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_everything_once():
+    from brainforge_b200 import dist
+    for n in (0, 1, 7, 8, 4096, 4097):
+        for ws in (1, 2, 3, 8):
+            spans = [dist.shard_bounds(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_population_minimises_with_host_fitness():
+    """The GA operators stay host NumPy; same toy as xperiments/xp_evolution.py."""
+    from brainforge_b200.evolution import Population
+    np.random.seed(3)
+    target = np.array([3., 3.])
+    pop = Population(loci=2, fitness_function=lambda ind: (np.linalg.norm(target - ind * 10.),), limit=60)
+    means, stds, bests = pop.run(15, verbosity=0, mutation_rate=0.01)
+    assert bests[-1] <= bests[0] and bests[-1] < 1.0
+    assert pop.best.shape == (2,)
+
+
+def test_population_batch_fitness_matches_serial():
+    from brainforge_b200.evolution import Population
+    f = lambda g: (float(np.sum((g - 0.25) ** 2)),)
+    fb = lambda G: np.sum((G - 0.25) ** 2, axis=1, keepdims=True)
+    np.random.seed(5)
+    a = Population(loci=6, fitness_function=f, limit=20)
+    np.random.seed(5)
+    b = Population(loci=6, fitness_function=f, limit=20, batch_fitness_function=fb)
+    a.update()
+    b.update()
+    assert np.allclose(a.grades, b.grades)
+    b.update(np.array([3, 7, 11]))
+    assert np.allclose(a.grades, b.grades)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except Exception as e:  # surface the failure instead of a queue timeout
+        q.put((rank, "error: %r" % (e,)))
+
+
+def _worker_body(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as td
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from brainforge_b200 import dist
+    from brainforge_b200.evolution import Population
+    # (1) the one training collective: all-reduce(sum) of a flat gradient vector with the scalars at its tail
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    dist.allreduce_sum(g)
+    ok1 = torch.allclose(g, torch.arange(10, dtype=torch.float32) * sum(range(1, world + 1)))
+    # (2) population fitness sharded over ranks, only fitness values gathered
+    np.random.seed(11)                       # same population on every rank (host GA is replicated)
+    seen = []
+
+    def fb(G):
+        seen.append(len(G))
+        return np.sum(G ** 2, axis=1, keepdims=True)
+    pop = Population(loci=5, fitness_function=None, limit=9, batch_fitness_function=fb)
+    pop.update()
+    expect = np.sum(pop.individuals ** 2, axis=1)
+    ok2 = np.allclose(pop.grades, expect) and seen[0] in (4, 5)
+    pop.update(np.array([1, 2, 8]))
+    ok3 = np.allclose(pop.grades, expect)
+    q.put((rank, bool(ok1), bool(ok2), bool(ok3), dist.global_count(7)))
+    td.destroy_process_group()
+
+
+def test_gloo_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True, True, True, 14), (1, True, True, True, 14)], res
