@@ -1,0 +1,536 @@
+#!/usr/bin/env python
+"""bench.py -- train samples/s (fwd + bwd + update) of the brainforge hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 back-end
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU, NCCL
+
+Workload (default): BASELINE.json configs[2] ("cfg3") -- the 3-conv stack
+[ConvLayer(n,3,3) -> ReLU -> PoolLayer(2)] for n = 32,64,128 -> Flatten -> Dense(10,softmax), cxent, the
+reference's Adam, synthetic X (4096,3,30,30) ~ N(0,1), one-hot Y; GLOBAL batch 4096 sharded over the N
+ranks (strong scaling), one all-reduce of the flat gradient vector per step.  It is the config the metric
+("at 1/2/4/8 B200") is quoted on and it fits one GPU; `--workload cfg1|cfg2|cfg4|cfg5` select the others.
+
+One JSON line on stdout (rank 0):
+  value          samples/s with the inputs already resident in HBM (device-timed, max over ranks)
+  e2e            the same metric through the public API `Backpropagation.learn_batch(X_host, Y_host)`:
+                 H2D of the step's inputs from pinned host memory + D2H of the cost inside the timed region
+  roofline       the dominant kernel of the step: algorithmic bytes (or FLOPs) / its CUDA-event duration,
+                 against the measured peak in MEASURED_PEAKS.json
+  cpu_baseline   the float64 NumPy oracle (a port of the reference's algorithm, oracle/bf_oracle.py) timed on
+                 this box's host cores on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = {
+    "cfg1": dict(ishape=(784,), spec=[("dense", 60, "sigmoid"), ("dense", 10, "softmax")], cost="cxent",
+                 opt="sgd", batch=20, ncls=10, cpu_batch=20),
+    "cfg2": dict(ishape=(1, 28, 28), spec=[("conv", 8, 3, 3, "linear"), ("pool", 2), ("act", "relu"), ("flatten",),
+                                          ("dense", 10, "softmax")], cost="cxent", opt="sgd", batch=32, ncls=10,
+                 cpu_batch=32),
+    "cfg3": dict(ishape=(3, 30, 30), spec=[("conv", 32, 3, 3, "linear"), ("act", "relu"), ("pool", 2),
+                                          ("conv", 64, 3, 3, "linear"), ("act", "relu"), ("pool", 2),
+                                          ("conv", 128, 3, 3, "linear"), ("act", "relu"), ("pool", 2),
+                                          ("flatten",), ("dense", 10, "softmax")], cost="cxent", opt="adam",
+                 batch=4096, ncls=10, cpu_batch=256),
+    "cfg4": dict(ishape=(64, 128), spec=[("lstm", 256, "tanh", False), ("dense", 10, "softmax")], cost="cxent",
+                 opt="sgd", batch=1024, ncls=10, cpu_batch=32),
+}
+WORKLOAD_NAME = {
+    "cfg1": "Dense MLP 784-60-10 sigmoid/softmax, SGD, batch 20 (BASELINE configs[0])",
+    "cfg2": "ConvLayer(8,3x3)+PoolLayer(2)+ReLU+Dense10 on 1x28x28, SGD, batch 32 (BASELINE configs[1])",
+    "cfg3": "3-conv stack 32/64/128 3x3 + ReLU + MaxPool2 + Dense10 on 3x30x30, Adam, global batch 4096 (BASELINE configs[2])",
+    "cfg4": "LSTM(256,tanh) T=64 D=128 + Dense10, SGD, global batch 1024 (BASELINE configs[3])",
+    "cfg5": "NeuroEvolution fitness of 4096 genomes of the 784-60-10 MLP on X (1024,784) (BASELINE configs[4])",
+}
+
+
+# --------------------------------------------------------------------------------------- helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16_burst=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_data(cfg, n, seed, dtype=np.float32):
+    rs = np.random.RandomState(seed)
+    X = rs.randn(n, *cfg["ishape"]).astype(dtype)
+    Y = np.eye(cfg["ncls"], dtype=dtype)[rs.randint(0, cfg["ncls"], n)]
+    return X, Y
+
+
+def build_oracle(cfg):
+    from oracle import bf_oracle as O
+    np.random.seed(1234)
+    return O.Stack(cfg["ishape"], cfg["spec"], cost=cfg["cost"], optimizer=cfg["opt"])
+
+
+def build_b200(cfg, use_graph):
+    import brainforge_b200 as bf
+    from brainforge_b200.layers import Dense, ConvLayer, PoolLayer, Flatten, Activation, LSTM
+    np.random.seed(1234)     # same seed on every rank -> identical replicas (weights are never broadcast)
+    layers = []
+    for s in cfg["spec"]:
+        k = s[0]
+        layers.append({"dense": lambda: Dense(s[1], activation=s[2]), "act": lambda: Activation(s[1]),
+                       "flatten": lambda: Flatten(), "conv": lambda: ConvLayer(s[1], s[2], s[3], activation=s[4]),
+                       "pool": lambda: PoolLayer(s[1]),
+                       "lstm": lambda: LSTM(s[1], activation=s[2], return_seq=s[3])}[k]())
+    return bf.Backpropagation(input_shape=cfg["ishape"], layerstack=layers, cost=cfg["cost"], optimizer=cfg["opt"],
+                              use_graph=use_graph)
+
+
+# --------------------------------------------------------------------------------------- CPU arms
+def time_oracle(cfg, steps, warmup, batch):
+    net = build_oracle(cfg)
+    X, Y = make_data(cfg, batch, 7, np.float64)
+    for _ in range(warmup):
+        net.learn_batch(X, Y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        net.learn_batch(X, Y)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def time_oracle_fitness(P, N, steps, warmup):
+    from oracle import bf_oracle as O
+    rs = np.random.RandomState(3)
+    X = rs.randn(N, 784)
+    Y = np.eye(10)[rs.randint(0, 10, N)]
+    G = rs.uniform(size=(P, 47710))
+    for _ in range(warmup):
+        O.fitness_mlp_logsoftmax(G[:4], X, Y, 784, 60, 10)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.fitness_mlp_logsoftmax(G, X, Y, 784, 60, 10)
+    dt = time.perf_counter() - t0
+    return P * steps / dt, dt / steps
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  The reference is pure Python/NumPy and does not
+    exist on the GPU box, so this times the oracle port (float64 NumPy + BLAS on all host cores)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count()
+    if args.workload == "cfg5":
+        val, spu = time_oracle_fitness(32, 1024, args.steps, min(args.warmup, 1))
+        sample, unit, metric = "32 genomes x N=1024 per step", "individuals/s", "fitness evaluations/s"
+        cfgd = {"workload": WORKLOAD_NAME["cfg5"]}
+    else:
+        cfg = CFG[args.workload]
+        b = cfg["cpu_batch"]
+        val, spu = time_oracle(cfg, args.steps, args.warmup, b)
+        sample, unit, metric = "batch %d per step (of the %d-sample step)" % (b, cfg["batch"]), "samples/s", \
+            "train samples/s (fwd+bwd+update)"
+        cfgd = {"workload": WORKLOAD_NAME[args.workload], "global_batch": cfg["batch"]}
+    line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": spu * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfgd,
+            "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- roofline
+def parse_label(label):
+    name = label.split("(")[0]
+    ints = [int(v) for v in label[label.index("(") + 1:label.index(")")].split(",") if v.strip().lstrip("-").isdigit()]
+    tag = label[label.index("[") + 1:-1] if "[" in label else ""
+    return name, ints, tag
+
+
+def algorithmic_cost(label):
+    """(bytes, flops) a launch must move / execute: every operand read once, every result written once."""
+    name, a, tag = parse_label(label)
+    f = 4
+    if name == "bf_conv_forward":
+        im, ic, iy, ix, nf, fc, fy, fx, mode = a[:9]
+        oy, ox = (iy - fy + 1, ix - fx + 1) if mode == 0 else (iy + fy - 1, ix + fx - 1)
+        return f * (im * ic * iy * ix + nf * ic * fy * fx + nf + im * nf * oy * ox), 2.0 * im * oy * ox * nf * ic * fy * fx
+    if name == "bf_conv_backward":
+        im, ic, iy, ix, nf, fy, fx = a[:7]
+        oy, ox = iy - fy + 1, ix - fx + 1
+        X, E, F = im * ic * iy * ix, im * nf * oy * ox, nf * ic * fy * fx
+        flops = 2.0 * im * oy * ox * nf * ic * fy * fx
+        return (f * (X + E + F + nf), flops) if tag == "dF" else (f * (E + F + X), flops)
+    if name == "bf_pool_forward":
+        im, ic, iy, ix, fd = a[:5]
+        n = im * ic * iy * ix
+        return f * n + f * n // (fd * fd) + n // (fd * fd), 0.0
+    if name == "bf_pool_backward":
+        im, ic, iy, ix, fd = a[:5]
+        n = im * ic * iy * ix
+        return f * n + f * n // (fd * fd) + n // (fd * fd), 0.0
+    if name in ("bf_act_forward",):
+        return 2 * f * a[1], 0.0
+    if name == "bf_act_backward":
+        return 3 * f * a[1], 0.0
+    if name == "bf_dense_forward":
+        m, k, n = a[:3]
+        return f * (m * k + k * n + n + m * n), 2.0 * m * k * n
+    if name == "bf_dense_backward":
+        m, k, n = a[:3]
+        return f * (2 * m * k + 2 * m * n + 2 * k * n + n), 4.0 * m * k * n
+    if name == "bf_lstm_forward":
+        T, B, D, H = a[:4]
+        return f * T * B * (D + (D + H) + H + 11 * H) + f * (D + H) * 4 * H, 2.0 * T * B * (D + H) * 4 * H
+    if name == "bf_lstm_backward":
+        T, B, D, H = a[:4]
+        return f * T * B * ((D + H) + 12 * H + D + 8 * H) + 2 * f * (D + H) * 4 * H, 4.0 * T * B * (D + H) * 4 * H
+    if name == "bf_opt_step":
+        n = a[1] if len(a) > 1 else a[0]
+        return 7 * f * n, 0.0
+    if name == "bf_fitness_mlp":
+        P, N, nin, nh, nout = a[:5]
+        return f * (P * (nin * nh + nh + nh * nout + nout) + N * nin + N * nout + P), 2.0 * P * N * (nin * nh + nh * nout)
+    return 0, 0.0
+
+
+def roofline_entry(times, peaks, tf32):
+    """times: {label: [ms]} from the instrumented pass.  Picks the call with the largest total time."""
+    if not times:
+        return None, []
+    tot = {k: float(np.sum(v)) for k, v in times.items()}
+    step_total = sum(tot.values())
+    ranked = sorted(tot, key=tot.get, reverse=True)
+    top = ranked[0]
+    avg_ms = float(np.mean(times[top]))
+    nbytes, flops = algorithmic_cost(top)
+    gbs = nbytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    tfs = flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+    # ridge point of the machine balance: which roof bounds this launch
+    tensor_peak = peaks["bf16_sustained"] / 2.0     # kind::tf32 runs at half the bf16 rate (nominal 1.1 vs 2.25 PF)
+    t_hbm = nbytes / (peaks["hbm"] * 1e9)
+    t_tensor = flops / (tensor_peak * 1e12) if flops else 0.0
+    if t_tensor > t_hbm:
+        entry = {"bound": "tensor", "achieved": tfs, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tfs / tensor_peak,
+                 "peak_note": "tf32 tensor peak taken as measured sustained bf16 (%s) / 2" % peaks["source"]}
+    else:
+        entry = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                 "peak_note": "HBM copy bandwidth, %s" % peaks["source"]}
+    entry.update({"kernel": top, "avg_ms": avg_ms, "share_of_step": tot[top] / step_total if step_total else None,
+                  "algorithmic_bytes": nbytes, "algorithmic_flops": flops, "traffic": None,
+                  "path": "tcgen05-tf32" if tf32 else "simt-fp32"})
+    table = [{"kernel": k, "calls": len(times[k]), "avg_ms": float(np.mean(times[k])),
+              "share": tot[k] / step_total if step_total else None} for k in ranked[:12]]
+    return entry, table
+
+
+# --------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import brainforge_b200 as bf
+    from brainforge_b200 import dist, device
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback (use --impl reference)"
+    dist.init_from_env()
+    rank, ws = dist.rank(), dist.world_size()
+    if ws == 1:
+        torch.cuda.set_device(0)
+    bf.set_precision(args.precision)
+    peaks = load_peaks()
+    K, W = args.steps, max(args.warmup, 3)
+
+    if args.workload == "cfg5":
+        return run_b200_fitness(args, bf, dist, device, torch, peaks, K, W)
+
+    cfg = CFG[args.workload]
+    gb = args.batch or cfg["batch"]
+    lo, hi = dist.shard_bounds(gb)
+    mb = hi - lo
+    net = build_b200(cfg, use_graph=not args.no_graph)
+    # distinct input batches, rotated every step: with cfg3 the rotation set (4 x 44 MB) plus the step's
+    # activations (>1 GB) exceeds the 126 MB L2, so no step finds its inputs cached
+    nrot = 4
+    hostX, hostY, devX, devY = [], [], [], []
+    for r in range(nrot):
+        X, Y = make_data(cfg, gb, 100 + r)
+        px, py = bf.pinned_empty((mb,) + cfg["ishape"]), bf.pinned_empty((mb, cfg["ncls"]))
+        px[...] = X[lo:hi]; py[...] = Y[lo:hi]
+        hostX.append(px); hostY.append(py)
+        devX.append(bf.DeviceArray.from_host(px)); devY.append(bf.DeviceArray.from_host(py))
+    h2d = hostX[0].nbytes + hostY[0].nbytes
+    bf.synchronize()
+
+    def barrier():
+        if ws > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    graph_ok = not args.no_graph
+    # ---- (A) end-to-end through the public API: learn_batch(host X, host Y) -> {"cost": float}
+    try:
+        for i in range(W + 1):
+            out = net.learn_batch(hostX[i % nrot], hostY[i % nrot])
+    except Exception as e:            # CUDA-graph capture not possible in this configuration: run eagerly
+        if args.no_graph:
+            raise
+        sys.stderr.write("[bench] graph capture failed (%r); falling back to eager launches\n" % (e,))
+        graph_ok = False
+        net = build_b200(cfg, use_graph=False)
+        for i in range(W + 1):
+            out = net.learn_batch(hostX[i % nrot], hostY[i % nrot])
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        out = net.learn_batch(hostX[i % nrot], hostY[i % nrot])
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---- (B) inputs resident in HBM: the device part of the step, K times back to back
+    launches0 = device.launch_count()
+    metrics = []
+
+    def dev_step(i):
+        net._step(devX[i % nrot], devY[i % nrot], None, metrics, True, mb, gb)
+
+    graphs = []
+    if graph_ok:
+        try:
+            for i in range(nrot):
+                dev_step(i)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(nrot):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        dev_step(i)
+                    graphs.append(g)
+            torch.cuda.current_stream().wait_stream(side)
+        except Exception as e:
+            sys.stderr.write("[bench] device-step graph capture failed (%r); eager\n" % (e,))
+            graphs = []
+    per_step_launches = None
+    l0 = device.launch_count()
+    dev_step(0)
+    per_step_launches = device.launch_count() - l0
+    for i in range(W):
+        graphs[i % nrot].replay() if graphs else dev_step(i)
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for i in range(K):
+        graphs[i % nrot].replay() if graphs else dev_step(i)
+    d1.record()
+    barrier()
+    dev_ms = d0.elapsed_time(d1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if ws > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- (C) per-kernel CUDA-event timing of the same step (eager, instrumented) for the roofline
+    roof, table = None, []
+    if rank == 0 or ws > 1:
+        device.start_timing()
+        for i in range(max(2, min(K, 5))):
+            dev_step(i)
+        times = device.stop_timing()
+        if rank == 0:
+            roof, table = roofline_entry(times, peaks, args.precision == "tf32")
+    barrier()
+
+    if rank != 0:
+        return
+    # ---- CPU baseline: the oracle on a bounded sample of the same workload (N=1 only)
+    cpu = None
+    if ws == 1 and not args.no_cpu:
+        b = cfg["cpu_batch"]
+        val, spu = time_oracle(cfg, 3 if spu_guess(cfg) < 3 else 1, 1, b)
+        cpu = {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "float64 NumPy oracle, batch %d, %.2f s/step" % (b, spu)}
+    line = {
+        "metric": "train samples/s (fwd+bwd+update)", "value": gb * K / (dev_ms * 1e-3), "unit": "samples/s",
+        "n_gpus": ws, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME[args.workload], "global_batch": gb, "per_gpu_batch": mb,
+                   "parallelism": "dp%d" % ws, "precision_path": args.precision, "cuda_graph": bool(graphs),
+                   "l2": "4 rotating input batches + >1 GB of activations per step exceed the 126 MB L2",
+                   "cost_last_step": out["cost"]},
+        "e2e": {"value": gb * K / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms / K,
+                "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": 256 * ws,
+                "api": "Backpropagation.learn_batch(X_host_pinned_f32, Y_host_pinned_f32)"},
+        "gpu_launches": int(per_step_launches * K),
+        "clocks": clocks, "roofline": roof, "kernels": table, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def spu_guess(cfg):
+    return {4096: 1.5, 1024: 1.0}.get(cfg["batch"], 0.01)
+
+
+def run_b200_fitness(args, bf, dist, device, torch, peaks, K, W):
+    """cfg5: one 'step' = fitness of the whole population (P genomes) on the shared (X, Y)."""
+    from brainforge_b200.layers import Dense
+    rank, ws = dist.rank(), dist.world_size()
+    P, N = args.batch or 4096, 1024
+    lo, hi = dist.shard_bounds(P)
+    np.random.seed(1234)
+    ne = bf.NeuroEvolution(input_shape=(784,), layerstack=[Dense(60, activation="sigmoid"), Dense(10, activation="softmax")],
+                           cost="cxent", population_size=8)
+    rs = np.random.RandomState(5)
+    X = rs.randn(N, 784).astype(np.float32)
+    Y = np.eye(10, dtype=np.float32)[rs.randint(0, 10, N)]
+    G = bf.pinned_empty((hi - lo, 47710))
+    G[...] = rs.uniform(size=G.shape)
+    import ctypes
+    from brainforge_b200 import _lib
+    xd, yd = bf.DeviceArray.from_host(X), bf.DeviceArray.from_host(Y)
+    gd = bf.DeviceArray.from_host(G)
+    out = bf.DeviceArray.empty(hi - lo)
+
+    def dev_step():
+        device.call(_lib.lib.bf_fitness_mlp, gd.ptr, xd.ptr, yd.ptr, out.ptr, hi - lo, N, 784, 60, 10, device.precision(),
+                    device.stream_ptr())
+
+    def barrier():
+        if ws > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+    for _ in range(W):
+        dev_step()
+        ne.batch_fitness(G, X, Y)
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    l0 = device.launch_count()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(K):
+        dev_step()
+    d1.record()
+    barrier()
+    launches = device.launch_count() - l0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        fit = ne.batch_fitness(G, X, Y)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([d0.elapsed_time(d1), e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if ws > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    device.start_timing()
+    dev_step()
+    times = device.stop_timing()
+    if rank != 0:
+        return
+    roof, table = roofline_entry(times, peaks, args.precision == "tf32")
+    cpu = None
+    if ws == 1 and not args.no_cpu:
+        val, spu = time_oracle_fitness(32, N, 2, 1)
+        cpu = {"value": val, "unit": "individuals/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "float64 NumPy oracle, 32 genomes x N=%d, %.2f s/step" % (N, spu)}
+    line = {"metric": "fitness evaluations/s", "value": P * K / (dev_ms * 1e-3), "unit": "individuals/s", "n_gpus": ws,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME["cfg5"], "population": P, "samples": N, "parallelism": "dp%d" % ws,
+                       "l2": "genome matrix (%.0f MB per rank) exceeds the 126 MB L2" % (G.nbytes / 1e6),
+                       "mean_fitness": float(np.mean(fit))},
+            "e2e": {"value": P * K / (e2e_ms * 1e-3), "unit": "individuals/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": int(G.nbytes) * ws, "d2h_bytes_per_step": 4 * P,
+                    "api": "NeuroEvolution.batch_fitness(genomes_host_pinned_f32, X, Y)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": table, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--precision", default=os.environ.get("BF_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--batch", type=int, default=0, help="override the global batch / population")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

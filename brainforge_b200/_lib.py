@@ -29,6 +29,7 @@ SIGNATURES = {
     "bf_device_info": (_i, [_c.POINTER(_i)] * 3),
     "bf_set_workspace": (_i, [_vp, _sz]),
     "bf_last_path": (_i, []),
+    "bf_launch_count": (_c.c_ulonglong, []),
     "bf_memcpy_h2d": (_i, [_vp, _vp, _sz, _vp]),
     "bf_memcpy_d2h": (_i, [_vp, _vp, _sz, _vp]),
     "bf_stream_sync": (_i, [_vp]),
@@ -50,8 +51,8 @@ SIGNATURES = {
     "bf_cost_delta": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bf_cost_value": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp]),
     "bf_accuracy": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
-    "bf_lstm_forward": (_i, [_vp] * 6 + [_i] * 6 + [_vp]),
-    "bf_lstm_backward": (_i, [_vp] * 8 + [_i] * 6 + [_vp]),
+    "bf_lstm_forward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
+    "bf_lstm_backward": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
     "bf_opt_step": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _vp]),
     "bf_fitness_mlp": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
 }
@@ -66,7 +67,7 @@ def header_symbols(path=HEADER):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "brainforge_b200: %s is missing. Build it with `python -m brainforge_b200.build` "
+            "brainforge_b200: %s is missing. Build it with `python brainforge_b200/build.py` "
             "(there is no CPU or PyTorch fallback for this path)." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

@@ -180,8 +180,12 @@ class ConvolutionOp:
         dF = DeviceArray.empty(nf, fc, fy, fx) if dF is None else dF
         db = DeviceArray.empty(1, nf, 1, 1) if db is None else db
         dX = DeviceArray.empty(im, ic, iy, ix) if need_dX else None
-        call(L.bf_conv_backward, x.ptr, e.ptr, f.ptr, dF.ptr, db.ptr, dX.ptr if dX is not None else _NULL, im, ic, iy,
-             ix, nf, fy, fx, precision(), stream_ptr())
+        # two calls (filter-gradient half, data-gradient half) so that each kernel can be timed on its own
+        call(L.bf_conv_backward, x.ptr, e.ptr, f.ptr, dF.ptr, db.ptr, _NULL, im, ic, iy, ix, nf, fy, fx, precision(),
+             stream_ptr(), tag="dF")
+        if dX is not None:
+            call(L.bf_conv_backward, x.ptr, e.ptr, f.ptr, _NULL, _NULL, dX.ptr, im, ic, iy, ix, nf, fy, fx,
+                 precision(), stream_ptr(), tag="dX")
         return _ret(X, dF, db, dX)
 
     @staticmethod
@@ -291,18 +295,29 @@ class LSTMOp:
         O = DeviceArray.empty(T, B, H)
         Z = DeviceArray.empty(T, B, D + H)
         cache = DeviceArray.empty(6, T, B, H)
-        call(L.bf_lstm_forward, x.ptr, w.ptr, bd.ptr, O.ptr, Z.ptr, cache.ptr, T, B, D, H, _lib.ACT[self.activation],
-             precision(), stream_ptr())
+        cache.bw = DeviceArray.empty(5, T, B, H)   # act'(.) of Ca,cand,f,i,o from the pre-activations
+        call(L.bf_lstm_forward, x.ptr, w.ptr, bd.ptr, O.ptr, Z.ptr, cache.ptr, cache.bw.ptr, T, B, D, H,
+             _lib.ACT[self.activation], precision(), stream_ptr())
         return _ret(X, O, Z, cache)
 
     def backward(self, Z, O, E, W, cache, nablaW=None, nablab=None):
         z, o, e, w, c = as_device(Z), as_device(O), as_device(E), as_device(W), as_device(cache)
+        bw = getattr(cache, "bw", None)
+        if bw is None and not isinstance(cache, DeviceArray):
+            # host float64 cache: form the reference's bwCa / bwgates (recurrent_op.py:85-88) before narrowing
+            ch = np.asarray(cache, dtype=np.float64)
+            def d(kind, a):
+                return {"sigmoid": a * (1. - a), "tanh": 1. - a ** 2, "relu": (a > 0.).astype(np.float64),
+                        "linear": np.ones_like(a)}[kind]
+            bw = DeviceArray.from_host(np.stack([d(self.activation, ch[1]), d(self.activation, ch[2]),
+                                                 d("sigmoid", ch[3]), d("sigmoid", ch[4]), d("sigmoid", ch[5])]))
         T, B, ZD = z.shape
         H = w.shape[-1] // 4
         D = ZD - H
         dX = DeviceArray.empty(T, B, D)
         nablaW = DeviceArray.empty(ZD, 4 * H) if nablaW is None else nablaW
         nablab = DeviceArray.empty(4 * H) if nablab is None else nablab
-        call(L.bf_lstm_backward, z.ptr, o.ptr, e.ptr, w.ptr, c.ptr, dX.ptr, nablaW.ptr, nablab.ptr, T, B, D, H,
+        call(L.bf_lstm_backward, z.ptr, o.ptr, e.ptr, w.ptr, c.ptr, bw.ptr if bw is not None else _NULL, dX.ptr,
+             nablaW.ptr, nablab.ptr, T, B, D, H,
              _lib.ACT[self.activation], precision(), stream_ptr())
         return _ret(Z, dX, nablaW, nablab)

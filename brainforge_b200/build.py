@@ -1,6 +1,6 @@
 """Build libbf_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m brainforge_b200.build [--force] [--verbose]
+    python brainforge_b200/build.py [--force] [--verbose]      (or: python __graft_entry__.py)
 
 One object per .cu under csrc/, compiled in parallel, linked into brainforge_b200/libbf_b200.so with
 the static CUDA runtime (no torch, no Python in the library: the boundary is the C ABI of

@@ -8,6 +8,9 @@ static thread_local char g_err[1024] = "";
 static thread_local int g_last_path = 0;
 static void* g_ws_ptr = nullptr;
 static size_t g_ws_bytes = 0;
+static unsigned long long g_launches = 0;
+
+void count_launch() { ++g_launches; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -83,6 +86,7 @@ extern "C" {
 const char* bf_last_error(void) { return g_err; }
 int bf_version(void) { return 100; }
 int bf_last_path(void) { return g_last_path; }
+unsigned long long bf_launch_count(void) { return g_launches; }
 
 int bf_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

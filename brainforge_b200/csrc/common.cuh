@@ -17,7 +17,12 @@ int fail(int code, const char* fmt, ...);
     if (e__ != cudaSuccess)                                                                   \
       return bf::fail(BF_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
   } while (0)
-#define BF_LAUNCH_CHECK() BF_CUDA(cudaGetLastError())
+void count_launch();                 // every kernel launch of this library is counted (bf_launch_count)
+#define BF_LAUNCH_CHECK()        \
+  do {                           \
+    bf::count_launch();          \
+    BF_CUDA(cudaGetLastError()); \
+  } while (0)
 #define BF_REQUIRE(cond, code, ...) \
   do {                              \
     if (!(cond)) return bf::fail(code, __VA_ARGS__); \

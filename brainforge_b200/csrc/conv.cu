@@ -160,7 +160,7 @@ extern "C" {
 int bf_conv_forward(const float* A, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix,
                     int nf, int fc, int fy, int fx, int mode, int act, int precision, void* stream) {
   (void)precision;
-  BF_REQUIRE(A && F && Y, BF_ERR_ARG, "bf_conv_forward: null pointer");
+  BF_REQUIRE(F && (im == 0 || (A && Y)), BF_ERR_ARG, "bf_conv_forward: null pointer");
   BF_REQUIRE(im >= 0 && ic > 0 && iy > 0 && ix > 0 && nf > 0 && fy > 0 && fx > 0, BF_ERR_ARG,
              "bf_conv_forward: bad shape");
   if (fc != ic)  // atomic/tensor_op.py:18-21
@@ -194,7 +194,7 @@ int bf_conv_forward(const float* A, const float* F, const float* bias, float* Y,
 int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, float* db, float* dX, int im, int ic,
                      int iy, int ix, int nf, int fy, int fx, int precision, void* stream) {
   (void)precision;
-  BF_REQUIRE(X && E && F && dF, BF_ERR_ARG, "bf_conv_backward: null pointer");
+  BF_REQUIRE(F && (im == 0 || (X && E)), BF_ERR_ARG, "bf_conv_backward: null pointer");
   BF_REQUIRE(im >= 0 && ic > 0 && iy > 0 && ix > 0 && nf > 0 && fy > 0 && fx > 0, BF_ERR_ARG,
              "bf_conv_backward: bad shape");
   int oy = iy - fy + 1, ox = ix - fx + 1;
@@ -204,7 +204,7 @@ int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, 
   set_last_path(0);
   int rc;
   // ---- dF and db in one split-K contraction over (img, pixel)
-  {
+  if (dF) {
     int rows = K + 1;
     long Kred = (long)im * Ppad;
     BF_REQUIRE(Kred < 2147483647L, BF_ERR_ARG, "bf_conv_backward: reduction too long");

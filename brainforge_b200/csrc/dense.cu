@@ -52,9 +52,9 @@ extern "C" {
 int bf_dense_forward(const float* X, const float* W, const float* b, float* out, int m, int k, int n, int act,
                      int precision, void* stream) {
   BF_REQUIRE(m >= 0 && k > 0 && n > 0, BF_ERR_ARG, "bf_dense_forward: bad shape m=%d k=%d n=%d", m, k, n);
-  BF_REQUIRE(X && W && out, BF_ERR_ARG, "bf_dense_forward: null pointer");
   BF_REQUIRE(act >= BF_ACT_LINEAR && act <= BF_ACT_SOFTMAX, BF_ERR_ARG, "bf_dense_forward: bad activation %d", act);
   if (m == 0) return BF_OK;
+  BF_REQUIRE(X && W && out, BF_ERR_ARG, "bf_dense_forward: null pointer");
   cudaStream_t s = as_stream(stream);
   int ep_act = act == BF_ACT_SOFTMAX ? BF_ACT_LINEAR : act;
   int rc = BF_OK;
@@ -76,7 +76,7 @@ int bf_dense_forward(const float* X, const float* W, const float* b, float* out,
 int bf_dense_backward(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int k,
                       int n, int accumulate, int precision, void* stream) {
   BF_REQUIRE(m >= 0 && k > 0 && n > 0, BF_ERR_ARG, "bf_dense_backward: bad shape m=%d k=%d n=%d", m, k, n);
-  BF_REQUIRE(X && E && W && dW, BF_ERR_ARG, "bf_dense_backward: null pointer");
+  BF_REQUIRE(W && dW && (m == 0 || (X && E)), BF_ERR_ARG, "bf_dense_backward: null pointer");
   cudaStream_t s = as_stream(stream);
   int rc;
   // dW = X^T @ E with a virtual all-ones row appended to X^T: row k of the product is db = E.sum(0).

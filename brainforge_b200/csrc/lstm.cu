@@ -26,11 +26,26 @@ __global__ void lstm_fill_z_kernel(const float* __restrict__ X, float* __restric
   }
 }
 
+// act'(z) computed from the pre-activation z (a = act(z) given), free of cancellation
+__device__ __forceinline__ float act_deriv_from_z(int act, float z, float a) {
+  switch (act) {
+    case BF_ACT_SIGMOID: return a * sigmoidf_(-z);
+    case BF_ACT_TANH: {   // sech^2(z) = 4 e^{-2|z|} / (1 + e^{-2|z|})^2
+      float e = expf(-2.0f * fabsf(z));
+      float d = 1.0f + e;
+      return 4.0f * e / (d * d);
+    }
+    case BF_ACT_RELU: return a > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+
 // gates (B,4H) pre-activations [cand|f|i|o] -> cache rows at time t, O[t], and the recurrent half of Z[t+1]
 __global__ void lstm_gates_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Cprev,
                                       float* __restrict__ C, float* __restrict__ Ca, float* __restrict__ cand,
                                       float* __restrict__ f, float* __restrict__ ig, float* __restrict__ o,
-                                      float* __restrict__ O, float* __restrict__ Znext, int B, int D, int H, int act) {
+                                      float* __restrict__ O, float* __restrict__ Znext, float* __restrict__ bw,
+                                      long bw_stride, int B, int D, int H, int act) {
   long total = (long)B * H;
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; idx < total; idx += stride) {
@@ -47,6 +62,15 @@ __global__ void lstm_gates_fwd_kernel(const float* __restrict__ P, const float* 
     float out = ca * ov;               // recurrent_op.py:74-75
     C[idx] = c; Ca[idx] = ca; cand[idx] = cv; f[idx] = fv; ig[idx] = iv; o[idx] = ov;
     O[idx] = out;
+    if (bw) {
+      // act'(.) of the five cached activations, evaluated from the PRE-activations: forming A(1-A) or
+      // 1-A^2 from FP32-rounded saturated outputs (all biases start at +7) would cancel catastrophically
+      bw[idx] = act_deriv_from_z(act, c, ca);
+      bw[bw_stride + idx] = act_deriv_from_z(act, p[j], cv);
+      bw[2 * bw_stride + idx] = fv * sigmoidf_(-p[H + j]);
+      bw[3 * bw_stride + idx] = iv * sigmoidf_(-p[2 * H + j]);
+      bw[4 * bw_stride + idx] = ov * sigmoidf_(-p[3 * H + j]);
+    }
     if (Znext) Znext[b * (D + H) + D + j] = out;
   }
 }
@@ -56,8 +80,8 @@ __global__ void lstm_gates_bwd_kernel(const float* __restrict__ E, const float* 
                                       const float* __restrict__ Cprev, const float* __restrict__ Ca,
                                       const float* __restrict__ cand, const float* __restrict__ f,
                                       const float* __restrict__ ig, const float* __restrict__ o,
-                                      float* __restrict__ deltaC, float* __restrict__ dgates, int B, int H, int act,
-                                      int first) {
+                                      const float* __restrict__ bw, long bw_stride, float* __restrict__ deltaC,
+                                      float* __restrict__ dgates, int B, int H, int act, int first) {
   long total = (long)B * H;
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; idx < total; idx += stride) {
@@ -65,13 +89,21 @@ __global__ void lstm_gates_bwd_kernel(const float* __restrict__ E, const float* 
     int j = (int)(idx - b * H);
     float e = E[idx] + (dH ? dH[idx] : 0.f);
     float cav = Ca[idx], cv = cand[idx], fv = f[idx], iv = ig[idx], ov = o[idx];
-    float dC = (first ? 0.f : deltaC[idx]) + e * ov * act_bwd_rt(act, cav);
+    float bCa, bcand, bf_, bi, bo;
+    if (bw) {
+      bCa = bw[idx]; bcand = bw[bw_stride + idx]; bf_ = bw[2 * bw_stride + idx];
+      bi = bw[3 * bw_stride + idx]; bo = bw[4 * bw_stride + idx];
+    } else {  // derivative-from-output exactly as recurrent_op.py:85-88 (FP32 cancellation when saturated)
+      bCa = act_bwd_rt(act, cav); bcand = act_bwd_rt(act, cv);
+      bf_ = fv * (1.f - fv); bi = iv * (1.f - iv); bo = ov * (1.f - ov);
+    }
+    float dC = (first ? 0.f : deltaC[idx]) + e * ov * bCa;
     float cp = Cprev ? Cprev[idx] : 0.f;
     float* dg = dgates + b * 4 * H;
-    dg[j] = dC * iv * act_bwd_rt(act, cv);
-    dg[H + j] = dC * cp * (fv * (1.f - fv));
-    dg[2 * H + j] = dC * cv * (iv * (1.f - iv));
-    dg[3 * H + j] = cav * e * (ov * (1.f - ov));
+    dg[j] = dC * iv * bcand;
+    dg[H + j] = dC * cp * bf_;
+    dg[2 * H + j] = dC * cv * bi;
+    dg[3 * H + j] = cav * e * bo;
     deltaC[idx] = dC * fv;
   }
 }
@@ -97,8 +129,8 @@ using namespace bf;
 
 extern "C" {
 
-int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, int T, int B,
-                    int D, int H, int act, int precision, void* stream) {
+int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
+                    int T, int B, int D, int H, int act, int precision, void* stream) {
   (void)precision;
   BF_REQUIRE(X && W && b && O && Z && cache, BF_ERR_ARG, "bf_lstm_forward: null pointer");
   BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_lstm_forward: bad shape");
@@ -130,14 +162,15 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
     long off = (long)t * BH;
     lstm_gates_fwd_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(
         gates, t ? C + off - BH : nullptr, C + off, Ca + off, cand + off, f + off, ig + off, o + off, O + off,
-        t + 1 < T ? Z + (long)(t + 1) * B * ZD : nullptr, B, D, H, act);
+        t + 1 < T ? Z + (long)(t + 1) * B * ZD : nullptr, bw ? bw + off : nullptr, TB * H, B, D, H, act);
     BF_LAUNCH_CHECK();
   }
   return BF_OK;
 }
 
-int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache, float* dX,
-                     float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream) {
+int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache,
+                     const float* bw, float* dX, float* nablaW, float* nablab, int T, int B, int D, int H, int act,
+                     int precision, void* stream) {
   (void)precision; (void)O;
   BF_REQUIRE(Z && E && W && cache && dX && nablaW && nablab, BF_ERR_ARG, "bf_lstm_backward: null pointer");
   BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_lstm_backward: bad shape");
@@ -181,7 +214,8 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
     float* dg_t = dgates + (long)t * B * N4;
     lstm_gates_bwd_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(E + off, t == T - 1 ? nullptr : dH,
                                                           t ? C + off - BH : nullptr, Ca + off, cand + off, f + off,
-                                                          ig + off, o + off, deltaC, dg_t, B, H, act, t == T - 1);
+                                                          ig + off, o + off, bw ? bw + off : nullptr, TB * H, deltaC, dg_t, B, H,
+                                                          act, t == T - 1);
     BF_LAUNCH_CHECK();
     // deltaZ[t] = dgates[t] @ W^T : M=B, N=D+H, K=4H ; B(k, n) = W[n*4H + k]
     LoadKContig al{dg_t, (long)N4};

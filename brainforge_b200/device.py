@@ -52,15 +52,41 @@ def _ensure_workspace(nbytes):
     return ws
 
 
-def call(fn, *args):
-    """Invoke a libbf_b200 entry point; grows the scratch workspace and retries once if asked to."""
+def call(fn, *args, tag=None):
+    """Invoke a libbf_b200 entry point; grows the scratch workspace and retries once if asked to.
+    With timing enabled (bench.py's roofline pass) the call is bracketed by CUDA events on the launching
+    stream and filed under `name(int args)[tag]`."""
     if _state["workspace"] is None:
         _ensure_workspace(DEFAULT_WORKSPACE)
+    timing = _state.get("timing")
+    if timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     try:
         _lib.check(fn(*args))
     except _lib.WorkspaceTooSmall as e:
         _ensure_workspace(int(e.need * 1.25) + 4096)
         _lib.check(fn(*args))
+    if timing is not None:
+        e1.record()
+        label = "%s(%s)%s" % (fn.__name__, ",".join(str(a) for a in args if isinstance(a, int)),
+                              "[%s]" % tag if tag else "")
+        timing.setdefault(label, []).append((e0, e1))
+
+
+def start_timing():
+    _state["timing"] = {}
+
+
+def stop_timing():
+    """-> {label: [ms per call]} for every library call made since start_timing()."""
+    torch.cuda.synchronize()
+    timing, _state["timing"] = _state.get("timing") or {}, None
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in timing.items()}
+
+
+def launch_count():
+    return int(_lib.lib.bf_launch_count())
 
 
 def _ptr(t):

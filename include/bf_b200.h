@@ -60,6 +60,8 @@ BF_API int bf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 BF_API int bf_set_workspace(void* d_ptr, size_t bytes);
 /* Which kernel family the last contraction call on this thread used: 0 = SIMT FP32, 1 = tcgen05 TF32. */
 BF_API int bf_last_path(void);
+/* Number of kernels this library has launched so far in this process (for bench.py gpu_launches). */
+BF_API unsigned long long bf_launch_count(void);
 BF_API int bf_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
 BF_API int bf_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 BF_API int bf_stream_sync(void* stream);
@@ -101,7 +103,7 @@ BF_API int bf_conv_forward(const float* A, const float* F, const float* bias, fl
                     int nf, int fc, int fy, int fx, int mode, int act, int precision, void* stream);
 /* ConvolutionOp.backward(X,E,F) -> (dF,db,dX) for the VALID forward (tensor_op.py:49-61):
  * dF (nf,ic,fy,fx), db (nf) = E.sum((0,2,3)), dX (im,ic,iy,ix) = full(E, flip(F)^T).
- * Assigns (layers/tensor.py:83).  dX may be NULL. */
+ * Assigns (layers/tensor.py:83).  dF (with db) or dX may be NULL to skip that half. */
 BF_API int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, float* db, float* dX, int im, int ic,
                      int iy, int ix, int nf, int fy, int fx, int precision, void* stream);
 
@@ -127,13 +129,18 @@ BF_API int bf_accuracy(const float* out, const float* tgt, int m, int n, float* 
 
 /* ---- LSTM: atomic/recurrent_op.py:46-112, llatomic/_lllstm.py:6-67 ---- */
 /* LSTMOp(act).forward(X,W,b) -> (O,Z,cache).  X (T,B,D) time-major, W (D+H,4H) gate order
- * [cand|f|i|o], b (4H); O (T,B,H), Z (T,B,D+H), cache (6,T,B,H) = C,Ca,cand,f,i,o. */
-BF_API int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, int T, int B,
-                    int D, int H, int act, int precision, void* stream);
+ * [cand|f|i|o], b (4H); O (T,B,H), Z (T,B,D+H), cache (6,T,B,H) = C,Ca,cand,f,i,o.
+ * bw (5,T,B,H) or NULL: act'(.) of Ca,cand,f,i,o (the reference's bwCa/bwgates, recurrent_op.py:85-88)
+ * evaluated from the pre-activations, so that the saturated gates the +7 bias init produces do not
+ * lose their derivative to FP32 cancellation in A(1-A). */
+BF_API int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
+                    int T, int B, int D, int H, int act, int precision, void* stream);
 /* LSTMOp.backward(Z,O,E,W,cache) -> (dX (T,B,D), nablaW (D+H,4H), nablab (4H)); E (T,B,H) is read only.
- * Scratch (deltaZ, dgates, deltaC) comes from the workspace. */
-BF_API int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache, float* dX,
-                     float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream);
+ * bw as produced by bf_lstm_forward, or NULL to form the derivatives from the cached outputs in FP32.
+ * Scratch (dgates, deltaC, split-K partials) comes from the workspace. */
+BF_API int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache,
+                     const float* bw, float* dX, float* nablaW, float* nablab, int T, int B, int D, int H, int act,
+                     int precision, void* stream);
 
 /* ---- optimizer step on the flat vectors: optimizers/*.py, learner/backpropagation.py:37-42 ---- */
 /* W <- optimize(W, g, m) in place.  s1 = velocity, s2 = memory (NULL where the rule has none).
