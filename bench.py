@@ -421,6 +421,8 @@ def run_b200(args):
         "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME[args.workload], "global_batch": gb, "per_gpu_batch": mb,
                    "parallelism": "dp%d" % ws, "precision_path": args.precision, "cuda_graph": bool(graphs),
+                   "input_delta": "first layer's dX is not computed inside learn_batch (the reference discards it; "
+                                  "its FLOPs are excluded per SURVEY 8d)",
                    "l2": "4 rotating input batches + >1 GB of activations per step exceed the 126 MB L2",
                    "cost_last_step": out["cost"]},
         "e2e": {"value": gb * K / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms / K,

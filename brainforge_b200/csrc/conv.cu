@@ -5,7 +5,7 @@
 //   forward  : Y[(img,y,x), f]   = sum_{c,ky,kx} X[img,c,y+ky-py,x+kx-px] * F[f,c,ky,kx]
 //   dX       : dX[(img,y,x), c]  = sum_{f,ky,kx} E[img,f,y+ky-(fy-1),x+kx-(fx-1)] * F[f,c,fy-1-ky,fx-1-kx]
 //   dF (+db) : dF[(c,ky,kx), f]  = sum_{img,y,x} X[img,c,y+ky,x+kx] * E[img,f,y,x]   (+ ones row -> db[f])
-#include "gemm_simt.cuh"
+#include "gemm_umma.cuh"
 
 namespace bf {
 
@@ -159,7 +159,6 @@ extern "C" {
 
 int bf_conv_forward(const float* A, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix,
                     int nf, int fc, int fy, int fx, int mode, int act, int precision, void* stream) {
-  (void)precision;
   BF_REQUIRE(F && (im == 0 || (A && Y)), BF_ERR_ARG, "bf_conv_forward: null pointer");
   BF_REQUIRE(im >= 0 && ic > 0 && iy > 0 && ix > 0 && nf > 0 && fy > 0 && fx > 0, BF_ERR_ARG,
              "bf_conv_forward: bad shape");
@@ -182,26 +181,23 @@ int bf_conv_forward(const float* A, const float* F, const float* bias, float* Y,
   LoadKContig bl{F, (long)K};
   EpiConv ep{Y, bias, nf, oy * ox, act};
   int kps = (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
-  set_last_path(0);
   if (mode == BF_CONV_VALID) {
     ConvPatchA<false> al{A, ic, iy, ix, oy, ox, fy, fx, 0, 0, K, 0, nullptr, nullptr};
-    return launch_gemm_simt(al, bl, ep, (int)M, nf, K, 1, kps, (size_t)2 * K * sizeof(int), s);
+    return launch_gemm(precision, al, bl, ep, (int)M, nf, K, 1, kps, (size_t)2 * K * sizeof(int), s);
   }
   ConvPatchA<true> al{A, ic, iy, ix, oy, ox, fy, fx, py, px, K, 0, nullptr, nullptr};
-  return launch_gemm_simt(al, bl, ep, (int)M, nf, K, 1, kps, (size_t)2 * K * sizeof(int), s);
+  return launch_gemm(precision, al, bl, ep, (int)M, nf, K, 1, kps, (size_t)2 * K * sizeof(int), s);
 }
 
 int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, float* db, float* dX, int im, int ic,
                      int iy, int ix, int nf, int fy, int fx, int precision, void* stream) {
-  (void)precision;
   BF_REQUIRE(F && (im == 0 || (X && E)), BF_ERR_ARG, "bf_conv_backward: null pointer");
   BF_REQUIRE(im >= 0 && ic > 0 && iy > 0 && ix > 0 && nf > 0 && fy > 0 && fx > 0, BF_ERR_ARG,
              "bf_conv_backward: bad shape");
   int oy = iy - fy + 1, ox = ix - fx + 1;
   BF_REQUIRE(oy > 0 && ox > 0, BF_ERR_VALUE, "bf_conv_backward: filter larger than input");
   cudaStream_t s = as_stream(stream);
-  int K = ic * fy * fx, P = oy * ox, Ppad = (P + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
-  set_last_path(0);
+  int K = ic * fy * fx, P = oy * ox, Ppad = (P + GEMM_KALIGN - 1) / GEMM_KALIGN * GEMM_KALIGN;
   int rc;
   // ---- dF and db in one split-K contraction over (img, pixel)
   if (dF) {
@@ -221,7 +217,7 @@ int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, 
       ConvPatchT al{X, ic, iy, ix, oy, ox, fy, fx, K, P, Ppad, 0, nullptr, nullptr};
       ConvErrB bl{E, nf, P, Ppad};
       EpiPartial ep{(float*)ws, (long)rows * nf, nf};
-      rc = launch_gemm_simt(al, bl, ep, rows, nf, (int)Kred, splits, kps, (size_t)(K + Ppad) * sizeof(int), s);
+      rc = launch_gemm(precision, al, bl, ep, rows, nf, (int)Kred, splits, kps, (size_t)(K + Ppad) * sizeof(int), s);
       if (rc) return rc;
     }
     // partial is (kidx | ones, f); dF is (f, kidx): write transposed, route the ones row to db
@@ -237,7 +233,7 @@ int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, 
     ConvFlipB bl{F, nf, ic, fy, fx, K2, 2 * K2, nullptr};
     EpiConv ep{dX, nullptr, ic, iy * ix, BF_ACT_LINEAR};
     int kps = (K2 + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
-    rc = launch_gemm_simt(al, bl, ep, (int)M, ic, K2, 1, kps, (size_t)3 * K2 * sizeof(int), s);
+    rc = launch_gemm(precision, al, bl, ep, (int)M, ic, K2, 1, kps, (size_t)3 * K2 * sizeof(int), s);
     if (rc) return rc;
   }
   return BF_OK;

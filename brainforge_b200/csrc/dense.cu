@@ -1,6 +1,5 @@
 // Dense layer contractions: atomic/core_op.py:9-20 (DenseOp.forward / backward).
-#include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_umma.cuh"
 
 namespace bf {
 
@@ -58,15 +57,11 @@ int bf_dense_forward(const float* X, const float* W, const float* b, float* out,
   cudaStream_t s = as_stream(stream);
   int ep_act = act == BF_ACT_SOFTMAX ? BF_ACT_LINEAR : act;
   int rc = BF_OK;
-  if (precision == BF_PREC_TF32 && tc_gemm_supported(m, n, k, /*a_kmajor=*/true, /*b_kmajor=*/false)) {
-    rc = tc_gemm(X, k, true, W, n, false, out, n, m, n, k, b, ep_act, /*accumulate=*/0, s);
-    set_last_path(1);
-  } else {
+  {
     LoadKContig al{X, (long)k};
     LoadMNContig bl{W, (long)n};
     EpiDenseFwd ep{out, b, n, ep_act};
-    rc = launch_gemm_simt(al, bl, ep, m, n, k, 1, (k + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
-    set_last_path(0);
+    rc = launch_gemm(precision, al, bl, ep, m, n, k, 1, (k + GEMM_KALIGN - 1) / GEMM_KALIGN * GEMM_KALIGN, 0, s);
   }
   if (rc) return rc;
   if (act == BF_ACT_SOFTMAX) return bf_softmax_forward(out, out, m, n, stream);
@@ -96,7 +91,7 @@ int bf_dense_backward(const float* X, const float* E, const float* W, float* dW,
       LoadMNContigOnes al{X, (long)k, k};
       LoadMNContig bl{E, (long)n};
       EpiPartial ep{(float*)ws, (long)rows * n, n};
-      rc = launch_gemm_simt(al, bl, ep, rows, n, m, splits, kps, 0, s);
+      rc = launch_gemm(precision, al, bl, ep, rows, n, m, splits, kps, 0, s);
       if (rc) return rc;
     }
     rc = launch_splitk_reduce((const float*)ws, dW, db, rows, n, k, splits, accumulate, n, 1, s);
@@ -104,16 +99,10 @@ int bf_dense_backward(const float* X, const float* E, const float* W, float* dW,
   }
   // dX = E @ W^T
   if (dX && m > 0) {
-    if (precision == BF_PREC_TF32 && tc_gemm_supported(m, k, n, true, true)) {
-      rc = tc_gemm(E, n, true, W, n, true, dX, k, m, k, n, nullptr, BF_ACT_LINEAR, 0, s);
-      set_last_path(1);
-    } else {
-      LoadKContig al{E, (long)n};
-      LoadKContig bl{W, (long)n};
-      EpiPlain ep{dX, k};
-      rc = launch_gemm_simt(al, bl, ep, m, k, n, 1, (n + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
-      set_last_path(0);
-    }
+    LoadKContig al{E, (long)n};
+    LoadKContig bl{W, (long)n};
+    EpiPlain ep{dX, k};
+    rc = launch_gemm(precision, al, bl, ep, m, k, n, 1, (n + GEMM_KALIGN - 1) / GEMM_KALIGN * GEMM_KALIGN, 0, s);
     if (rc) return rc;
   }
   return BF_OK;

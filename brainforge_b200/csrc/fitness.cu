@@ -3,7 +3,7 @@
 // All individuals share X, so the P first-layer products collapse into ONE wide GEMM
 //   (N x nin) @ (nin x P*nh)      with B read straight out of the genome matrix, (g-0.5)*20 applied on load,
 // followed by a per-individual fused second layer + log-softmax + cross-entropy reduction.
-#include "gemm_simt.cuh"
+#include "gemm_umma.cuh"
 
 namespace bf {
 
@@ -93,7 +93,6 @@ extern "C" {
 
 int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* fitness, int P, int N, int nin, int nh,
                    int nout, int precision, void* stream) {
-  (void)precision;
   BF_REQUIRE(genomes && X && Y && fitness, BF_ERR_ARG, "bf_fitness_mlp: null pointer");
   BF_REQUIRE(P >= 0 && N > 0 && nin > 0 && nh > 0 && nout > 0, BF_ERR_ARG, "bf_fitness_mlp: bad shape");
   BF_REQUIRE(nout <= FIT_MAX_OUT, BF_ERR_ARG, "bf_fitness_mlp: nout %d > %d", nout, FIT_MAX_OUT);
@@ -110,7 +109,6 @@ int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* 
   float* Hbuf = (float*)workspace_ptr();
   size_t head_smem = (size_t)(nh * nout + nout) * sizeof(float);
   BF_REQUIRE(head_smem <= 40 * 1024, BF_ERR_ARG, "bf_fitness_mlp: second layer too large for shared memory");
-  set_last_path(0);
   for (long p0 = 0; p0 < P; p0 += chunk) {
     int pc = (int)((P - p0) < chunk ? (P - p0) : chunk);
     const float* G = genomes + p0 * loci;
@@ -119,7 +117,7 @@ int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* 
     LoadKContig al{X, (long)nin};
     GenomeW1 bl{G, loci, nh};
     EpiHidden ep{Hbuf, G, loci, nin, nh, N};
-    int rc = launch_gemm_simt(al, bl, ep, N, pc * nh, nin, 1, (nin + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    int rc = launch_gemm(precision, al, bl, ep, N, pc * nh, nin, 1, (nin + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
     if (rc) return rc;
     fitness_head_kernel<<<pc, 256, head_smem, s>>>(Hbuf, G, Y, fitness + p0, loci, nin, nh, nout, N);
     BF_LAUNCH_CHECK();

@@ -19,6 +19,7 @@ namespace bf {
 
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_KALIGN = 32;   // K granularity shared by the SIMT (16) and tcgen05 (32) cores
 
 template <int BM, int BN, class AL, class BL, class EP>
 __global__ void __launch_bounds__(GEMM_THREADS)
@@ -189,11 +190,11 @@ int launch_splitk_reduce(const float* ws, float* out, float* aux, int rows, int 
 inline int choose_splits(int tiles_mn, int K, int* k_per_split) {
   int target = 2 * num_sms();
   int splits = tiles_mn >= target ? 1 : (target + tiles_mn - 1) / tiles_mn;
-  int max_splits = (K + 4 * GEMM_BK - 1) / (4 * GEMM_BK);  // at least 64 k per split
+  int max_splits = (K + 4 * GEMM_KALIGN - 1) / (4 * GEMM_KALIGN);  // at least 128 k per split
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int kps = (K + splits - 1) / splits;
-  kps = (kps + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+  kps = (kps + GEMM_KALIGN - 1) / GEMM_KALIGN * GEMM_KALIGN;   // splits start on a K-chunk boundary of both cores
   splits = (K + kps - 1) / kps;
   *k_per_split = kps;
   return splits;

@@ -3,8 +3,7 @@
 // (B x (D+H)) @ ((D+H) x 4H) plus one fused elementwise gate kernel.  The weight gradient is ONE
 // split-K contraction over all T*B rows after the loop (recurrent_op.py:109), with the bias gradient
 // riding along as an all-ones row.
-#include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_umma.cuh"
 
 namespace bf {
 
@@ -131,7 +130,6 @@ extern "C" {
 
 int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
                     int T, int B, int D, int H, int act, int precision, void* stream) {
-  (void)precision;
   BF_REQUIRE(X && W && b && O && Z && cache, BF_ERR_ARG, "bf_lstm_forward: null pointer");
   BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_lstm_forward: bad shape");
   BF_REQUIRE(act == BF_ACT_TANH || act == BF_ACT_RELU || act == BF_ACT_SIGMOID || act == BF_ACT_LINEAR, BF_ERR_ARG,
@@ -152,12 +150,11 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
   float* ig = cache + 4 * TB * H;
   float* o = cache + 5 * TB * H;
   const int K = D + H, N = 4 * H;
-  set_last_path(0);
   for (int t = 0; t < T; ++t) {
     LoadKContig al{Z + (long)t * B * ZD, (long)ZD};
     LoadMNContig bl{W, (long)N};
     EpiBias ep{gates, b, N};
-    rc = launch_gemm_simt(al, bl, ep, B, N, K, 1, (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    rc = launch_gemm(precision, al, bl, ep, B, N, K, 1, (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
     if (rc) return rc;
     long off = (long)t * BH;
     lstm_gates_fwd_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(
@@ -171,7 +168,7 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
 int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache,
                      const float* bw, float* dX, float* nablaW, float* nablab, int T, int B, int D, int H, int act,
                      int precision, void* stream) {
-  (void)precision; (void)O;
+  (void)O;
   BF_REQUIRE(Z && E && W && cache && dX && nablaW && nablab, BF_ERR_ARG, "bf_lstm_backward: null pointer");
   BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_lstm_backward: bad shape");
   cudaStream_t s = as_stream(stream);
@@ -208,7 +205,6 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
   const float* f = cache + 3 * TB * H;
   const float* ig = cache + 4 * TB * H;
   const float* o = cache + 5 * TB * H;
-  set_last_path(0);
   for (int t = T - 1; t >= 0; --t) {
     long off = (long)t * BH;
     float* dg_t = dgates + (long)t * B * N4;
@@ -221,7 +217,7 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
     LoadKContig al{dg_t, (long)N4};
     LoadKContig bl{W, (long)N4};
     EpiLstmDz ep{dX + (long)t * B * D, dH, D, H};
-    rc = launch_gemm_simt(al, bl, ep, B, ZD, N4, 1, (N4 + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    rc = launch_gemm(precision, al, bl, ep, B, ZD, N4, 1, (N4 + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
     if (rc) return rc;
   }
   // nablaW = sum_t Z[t]^T @ dgates[t]  (+ ones row -> nablab)
@@ -229,7 +225,7 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
     LoadMNContigOnes al{Z, (long)ZD, ZD};
     LoadMNContig bl{dgates, (long)N4};
     EpiPartial ep{partial, (long)rows * N4, N4};
-    rc = launch_gemm_simt(al, bl, ep, rows, N4, (int)TB, splits, kps, 0, s);
+    rc = launch_gemm(precision, al, bl, ep, rows, N4, (int)TB, splits, kps, 0, s);
     if (rc) return rc;
     rc = launch_splitk_reduce(partial, nablaW, nablab, rows, N4, ZD, splits, 0, N4, 1, s);
     if (rc) return rc;

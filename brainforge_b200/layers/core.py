@@ -25,10 +25,12 @@ class Dense(FFBase):
         self.output = self.op.forward(x, self.weights, self.biases, activation=str(self.activation))
         return self.output
 
-    def _bwd(self, delta):
+    _can_skip_dx = True
+
+    def _bwd(self, delta, need_dX=True):
         delta = self.activation.backward_mul(self.output, delta)             # core.py:35, in place
         _, _, dX = self.op.backward(self.inputs, delta, self.weights, dW=self.nabla_w, db=self.nabla_b,
-                                    accumulate=True)                         # core.py:37-38 `+=`
+                                    accumulate=True, need_dX=need_dX)        # core.py:37-38 `+=`
         return dX
 
     def __str__(self):

@@ -71,9 +71,12 @@ class ConvLayer(LayerBase):
         self.output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation))
         return self.output
 
-    def _bwd(self, delta):
+    _can_skip_dx = True
+
+    def _bwd(self, delta, need_dX=True):
         delta = self.activation.backward_mul(self.output, delta)
-        _, _, dX = self.op.backward(X=self.inputs, E=delta, F=self.weights, dF=self.nabla_w, db=self.nabla_b)
+        _, _, dX = self.op.backward(X=self.inputs, E=delta, F=self.weights, dF=self.nabla_w, db=self.nabla_b,
+                                    need_dX=need_dX)
         return dX
 
     @property

@@ -50,7 +50,9 @@ class Backpropagation(Learner):
         self.cost.value_into(preds, y, sc[0:1])          # cost of the PRE-update forward pass (:26)
         if metrics:
             _metrics.accuracy.value_into(preds, y, sc[1:2])
-        self._bwd(delta)
+        # learn_batch discards the delta w.r.t. the network input (learner/backpropagation.py:22 ignores the
+        # return value), so the first layer's dX contraction is not computed here; backpropagate() still does.
+        self._bwd(delta, need_input_delta=False)
         if _dist.world_size() > 1:
             # gradients + step scalars in ONE collective (scalars alone when no update follows)
             _dist.allreduce_sum(self.layers.flat_grads if update else sc)
@@ -99,9 +101,13 @@ class Backpropagation(Learner):
         return self._read_scalars(metrics, m_local)
 
     # ------------------------------------------------------------------ pieces of the public API
-    def _bwd(self, error):
+    def _bwd(self, error, need_input_delta=True):
+        first = self.layers[1] if len(self.layers.layers) > 1 else None
         for layer in self.layers[-1:0:-1]:
-            error = layer._bwd(error)
+            if layer is first and not need_input_delta and getattr(layer, "_can_skip_dx", False):
+                error = layer._bwd(error, need_dX=False)
+            else:
+                error = layer._bwd(error)
         return error
 
     def backpropagate(self, error):
