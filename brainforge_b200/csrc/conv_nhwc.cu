@@ -1,0 +1,588 @@
+// Channels-last (NHWC) implicit-GEMM convolution on the tcgen05 tensor cores, operands staged by TMA only.
+//
+// Why channels-last: with the activations stored as [pixel][channel] a 32-channel slice of a pixel is one
+// 128-byte row of the canonical SWIZZLE_128B shared-memory layout, so TMA drops a (rows x width x 32 channel)
+// box of the tensor into shared memory in exactly the form tcgen05.mma reads, and a filter tap (ky,kx) is a
+// ROW OFFSET of ky*pitch + kx into that staged box: the nine taps of a 3x3 filter are nine matrix descriptors
+// over the same bytes.  No im2col, no SIMT instruction touches an operand (reference: atomic/tensor_op.py:9-61
+// builds the patch matrix with a Python loop, llatomic/lltensor_op.py:9-40 materialises it).
+//
+//   forward / dX ("igemm"):  out[q, n] = sum_{tap, c} in[q + shift(tap), c] * Wt[tap][n][c]
+//        q runs over the staged box in row-major (pitch PW) order; positions whose x >= out_x (or y >= out rows)
+//        are computed and dropped.  The "full" correlation of the data gradient (tensor_op.py:34-40,56-60) is the
+//        same kernel: TMA's out-of-bounds zero fill supplies the padding (box origin at -(f-1)), the flipped and
+//        transposed filter is a different repack of Wt.
+//   dF (+db):  dF[tap][f, c] = sum_{b, q} E[b, q, f] * X[b, q + shift(tap), c]
+//        both operands are MN-major here (the contraction index is the pixel = the row); kind::tf32 takes
+//        MN-major operands in the 128B-swizzle/32B-atom layout that TMA's SWIZZLE_128B_ATOM_32B writes.
+//        E is loaded with the pitch of X (TMA zero-fills x >= ox, y >= oy), one accumulator per tap lives in
+//        TMEM for the whole kernel, an all-ones operand adds db as a tenth accumulator.
+//
+// Pipeline (both kernels): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue
+// (TMEM -> registers -> global); mbarrier rings between them; persistent CTAs, one per SM.
+#include "tma.cuh"
+#include "conv_nhwc.cuh"
+
+namespace bf {
+
+constexpr int IG_THREADS = 192;
+constexpr int IG_ACCSET_COLS = 256;   // two accumulator sets in the 512 TMEM columns
+
+struct IgemmParams {
+  int nstages, nbands, G, IR, PW, T, slot_rows, ntaps, fx;
+  int x0, y0, RO, out_y, out_x, nimg, N, act, nbs;
+};
+
+template <int NB, int KH>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, IgemmParams p,
+                  float* __restrict__ out, const float* __restrict__ bias) {
+  extern __shared__ int dyn_smem[];
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], b_full[8], b_empty[8];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const uint32_t half_bytes = (uint32_t)p.slot_rows * 128u;
+  const uint32_t a_slot_bytes = KH * half_bytes;
+  const uint32_t b_base0 = base + 2 * a_slot_bytes;
+  constexpr uint32_t B_SLOT = KH * NB * 128;
+  const int n0 = blockIdx.y * NB;
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4);
+    }
+    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // rows of the A slots that TMA never writes are read by the taps of dropped positions only; give them a
+  // defined value once so that no NaN pattern lingers there
+  for (uint32_t o = tid * 16u; o < 2 * a_slot_bytes; o += IG_THREADS * 16u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================================== TMA producer
+    uint32_t bcount = 0;
+    int it = 0;
+    for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
+      const int as = it & 1, au = it >> 1;
+      const int grp = st / p.nbands, band = st - grp * p.nbands;
+      if (au > 0) mbar_wait(&a_empty[as], (uint32_t)((au - 1) & 1));
+      mbar_expect_tx(&a_full[as], (uint32_t)(KH * p.G * p.IR * 128));
+#pragma unroll
+      for (int h = 0; h < KH; ++h)
+        tma_load_4d(base + as * a_slot_bytes + h * half_bytes, &mapA, &a_full[as], h * 32, p.x0, p.y0 + band * p.RO,
+                    grp * p.G);
+      for (int tap = 0; tap < p.ntaps; ++tap, ++bcount) {
+        const uint32_t bs = bcount % (uint32_t)p.nbs, bu = bcount / (uint32_t)p.nbs;
+        if (bu > 0) mbar_wait(&b_empty[bs], (bu - 1) & 1);
+        mbar_expect_tx(&b_full[bs], B_SLOT);
+#pragma unroll
+        for (int h = 0; h < KH; ++h)
+          tma_load_3d(b_base0 + bs * B_SLOT + h * NB * 128, &mapB, &b_full[bs], h * 32, n0, tap);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = idesc_tf32(128, NB);
+    uint32_t bcount = 0;
+    int it = 0;
+    for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
+      const int as = it & 1, au = it >> 1;   // the accumulator set follows the same alternation
+      mbar_wait(&a_full[as], (uint32_t)(au & 1));
+      if (au > 0) mbar_wait(&t_empty[as], (uint32_t)((au - 1) & 1));
+      tc_fence_after();
+      const uint32_t a_slot = base + as * a_slot_bytes;
+      const uint32_t acc = tmem + as * IG_ACCSET_COLS;
+      for (int tap = 0; tap < p.ntaps; ++tap, ++bcount) {
+        const uint32_t bs = bcount % (uint32_t)p.nbs, bu = bcount / (uint32_t)p.nbs;
+        mbar_wait(&b_full[bs], bu & 1);
+        tc_fence_after();
+        const int ty = tap / p.fx, tx = tap - ty * p.fx;
+        const uint32_t shift_bytes = (uint32_t)(ty * p.PW + tx) * 128u;
+        const uint32_t b_slot = b_base0 + bs * B_SLOT;
+        for (int t = 0; t < p.T; ++t) {
+#pragma unroll
+          for (int h = 0; h < KH; ++h) {
+            const uint64_t ad = desc_k_sw128(a_slot + h * half_bytes + (uint32_t)t * 16384u + shift_bytes);
+            const uint64_t bd = desc_k_sw128(b_slot + h * NB * 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(acc + t * NB, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc,
+                        (tap > 0 || h > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&b_empty[bs]);
+      }
+      umma_commit(&a_empty[as]);
+      umma_commit(&t_full[as]);
+    }
+  } else if (warp >= 2) {
+    // ===================================================================== epilogue (TMEM lanes 32*(warp%4)..+31)
+    const int quad = warp & 3;
+    int it = 0;
+    for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
+      const int as = it & 1, au = it >> 1;
+      const int grp = st / p.nbands, band = st - grp * p.nbands;
+      mbar_wait(&t_full[as], (uint32_t)(au & 1));
+      tc_fence_after();
+      for (int t = 0; t < p.T; ++t) {
+        const int q = t * 128 + quad * 32 + lane;
+        const int g = q / p.IR, ql = q - g * p.IR;
+        const int y = ql / p.PW, x = ql - y * p.PW;
+        const int img = grp * p.G + g, yo = band * p.RO + y;
+        const bool ok = g < p.G && img < p.nimg && y < p.RO && yo < p.out_y && x < p.out_x;
+        float* dst = out + ((size_t)((size_t)img * p.out_y + yo) * p.out_x + x) * p.N + n0;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + as * IG_ACCSET_COLS + t * NB;
+#pragma unroll
+        for (int c0 = 0; c0 < NB; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 r;
+              r.x = act_fwd_rt(p.act, __uint_as_float(v[j]));
+              r.y = act_fwd_rt(p.act, __uint_as_float(v[j + 1]));
+              r.z = act_fwd_rt(p.act, __uint_as_float(v[j + 2]));
+              r.w = act_fwd_rt(p.act, __uint_as_float(v[j + 3]));
+              if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+              }
+              *reinterpret_cast<float4*>(dst + c0 + j) = r;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// --------------------------------------------------------------------------------------------- dF (+ db)
+struct DfParams {
+  int nstages, nbands, G, IR, PW, RO, Krows, x_rows, ntaps, fx, nimg, nsplit, e_rows_box;
+};
+
+template <int MH>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__ CUtensorMap mapX, DfParams p,
+               float* __restrict__ partial) {
+  extern __shared__ int dyn_smem[];
+  __shared__ __align__(8) uint64_t full[2], empty[2], done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const uint32_t e_half = (uint32_t)p.Krows * 128u, e_slot = MH * e_half, x_slot = (uint32_t)p.x_rows * 128u;
+  const uint32_t x_base = base + 2 * e_slot, ones_base = x_base + 2 * x_slot;
+  const uint32_t total_bytes = 2 * e_slot + 2 * x_slot + 1024u;
+  const int split = blockIdx.x, ch = blockIdx.y;
+  const int ntap_acc = p.ntaps + (ch == 0 ? 1 : 0);   // channel half 0 also accumulates db (all-ones operand)
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero everything once: the K-padding rows of E and the tail rows of X are never written by TMA and must stay 0
+  for (uint32_t o = tid * 16u; o < total_bytes; o += IG_THREADS * 16u) {
+    const uint32_t v = (base + o >= ones_base) ? 0x3f800000u : 0u;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(v) : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  int my_stages = 0;
+  for (int st = split; st < p.nstages; st += p.nsplit) ++my_stages;
+
+  if (warp == 0 && lane == 0) {
+    int it = 0;
+    const uint32_t e_box_bytes = (uint32_t)(p.G * p.e_rows_box * p.PW) * 128u;
+    const uint32_t x_box_bytes = (uint32_t)(p.G * p.IR) * 128u;
+    for (int st = split; st < p.nstages; st += p.nsplit, ++it) {
+      const int s = it & 1, u = it >> 1;
+      const int grp = st / p.nbands, band = st - grp * p.nbands;
+      if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
+      mbar_expect_tx(&full[s], MH * e_box_bytes + x_box_bytes);
+#pragma unroll
+      for (int h = 0; h < MH; ++h)
+        tma_load_4d(base + s * e_slot + h * e_half, &mapE, &full[s], h * 32, 0, band * p.RO, grp * p.G);
+      tma_load_4d(x_base + s * x_slot, &mapX, &full[s], ch * 32, 0, band * p.RO, grp * p.G);
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = idesc_tf32(128, 32, true, true);
+    int it = 0;
+    const int ksteps = p.Krows / 8;
+    for (int st = split; st < p.nstages; st += p.nsplit, ++it) {
+      const int s = it & 1, u = it >> 1;
+      mbar_wait(&full[s], (uint32_t)(u & 1));
+      tc_fence_after();
+      const uint32_t e0 = base + s * e_slot, x0 = x_base + s * x_slot;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ad = desc_mn_sw128_32b(e0 + (uint32_t)ks * 1024u, e_half, 512u);
+        const uint32_t acc_flag = (it > 0 || ks > 0) ? 1u : 0u;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int ty = tap / p.fx, tx = tap - ty * p.fx;
+          const uint64_t bd = desc_mn_sw128_32b(x0 + (uint32_t)(ks * 8 + ty * p.PW + tx) * 128u, 4096u, 512u);
+          umma_tf32(tmem + tap * 32, ad, bd, idesc, acc_flag);
+        }
+        if (ch == 0) umma_tf32(tmem + p.ntaps * 32, ad, desc_mn_sw128_32b(ones_base, 4096u, 512u), idesc, acc_flag);
+      }
+      umma_commit(&empty[s]);
+    }
+    umma_commit(&done);
+  } else if (warp >= 2) {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    if (my_stages > 0) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+    }
+    // partial[split][ch][tap][m][32]
+    float* dst = partial + (((size_t)split * gridDim.y + ch) * (p.ntaps + 1)) * 128 * 32 + (size_t)m * 32;
+    for (int tap = 0; tap < p.ntaps + 1; ++tap) {
+      uint32_t v[32];
+      if (my_stages > 0 && tap < ntap_acc) {
+        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + tap * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (m < MH * 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(dst + (size_t)tap * 128 * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// dF[f][c][tap] = sum_z partial[z][c/32][tap][f][c%32];  db[f] = sum_z partial[z][0][ntaps][f][0]
+__global__ void conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
+                                           int nsplit, int nch, int ntaps, int nf, int ic) {
+  const long total = (long)nf * ic * ntaps + nf;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const bool is_db = i >= (long)nf * ic * ntaps;
+    int f, c, tap;
+    if (is_db) { f = (int)(i - (long)nf * ic * ntaps); c = 0; tap = ntaps; }
+    else { tap = (int)(i % ntaps); long r = i / ntaps; c = (int)(r % ic); f = (int)(r / ic); }
+    const size_t off = ((size_t)(c >> 5) * (ntaps + 1) + tap) * 128 * 32 + (size_t)f * 32 + (c & 31);
+    const size_t zstride = (size_t)nch * (ntaps + 1) * 128 * 32;
+    float s = 0.f;
+    for (int z = 0; z < nsplit; ++z) s += partial[z * zstride + off];
+    if (is_db) { if (db) db[f] = s; }
+    else dF[i] = s;
+  }
+}
+
+// Wt[tap][n][k]:  forward  n = f, k = c, tap = (ky,kx)        -> F[f][c][ky][kx]
+//                 data grad n = c, k = f, tap = (ty,tx)        -> F[f][c][fy-1-ty][fx-1-tx]   (flip + transpose)
+__global__ void conv_repack_nhwc_kernel(const float* __restrict__ F, float* __restrict__ Wt, int nf, int ic, int fy, int fx,
+                                        int transpose) {
+  const int ntaps = fy * fx, N = transpose ? ic : nf, K = transpose ? nf : ic;
+  const long total = (long)ntaps * N * K;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int k = (int)(i % K);
+    long r = i / K;
+    const int n = (int)(r % N), tap = (int)(r / N);
+    const int ty = tap / fx, tx = tap - ty * fx;
+    float v;
+    if (transpose) v = F[(((long)k * ic + n) * fy + (fy - 1 - ty)) * fx + (fx - 1 - tx)];
+    else v = F[(((long)n * ic + k) * fy + ty) * fx + tx];
+    Wt[i] = v;
+  }
+}
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+// dF kernel: [E slot 0 | E slot 1 | X slot 0 | X slot 1 | ones]; the A operand always spans four 32-filter groups
+// (M = 128), so for nf < 128 the junk groups of E slot 1 must still fall inside the allocation
+static inline size_t df_smem_bytes(int MH, int Krows, int x_rows) {
+  size_t rows = 2 * ((size_t)MH * Krows + x_rows) + 8;
+  const size_t reach = (size_t)MH * Krows + 4 * (size_t)Krows;
+  if (rows < reach) rows = reach;
+  return rows * 128 + 1024;
+}
+constexpr size_t IG_SMEM_BUDGET = 220 * 1024;
+
+struct IgemmPlan {
+  IgemmParams p;
+  int PH_box;
+  size_t smem;
+  bool ok;
+};
+
+// Picks images-per-stage (or output-row bands for large planes) so that the accumulators fit one TMEM set and two
+// A slots + the B ring fit shared memory; maximises useful positions per 128-row tile.
+static IgemmPlan plan_igemm(int B, int H, int W, int KH, int NB, int N, int fy, int fx, int pad_y, int pad_x, int act) {
+  IgemmPlan pl;
+  pl.ok = false;
+  IgemmParams& p = pl.p;
+  const int PW = W + 2 * pad_x, PH = H + 2 * pad_y;
+  const int out_y = PH - fy + 1, out_x = PW - fx + 1;
+  if (out_y <= 0 || out_x <= 0 || PW > 256) return pl;
+  const int max_shift = (fy - 1) * PW + fx - 1;
+  const int Tmax = IG_ACCSET_COLS / NB;
+  const int ntaps = fy * fx;
+  const size_t b_slot = (size_t)KH * NB * 128;
+  double best = -1;
+  // mode 1: G whole images per stage
+  if (PH <= 256) {
+    const int IR = PH * PW;
+    for (int G = 1; G <= 256 && G <= B + 8; ++G) {
+      const long last = (long)(G - 1) * IR + (long)(out_y - 1) * PW + out_x;   // positions to cover
+      const int T = (int)((last + 127) / 128);
+      if (T > Tmax) break;
+      long rows = (long)T * 128 + max_shift;
+      if (rows < (long)G * IR) rows = (long)G * IR;
+      rows = (rows + 7) / 8 * 8;
+      const size_t a_bytes = 2 * (size_t)KH * rows * 128;
+      if (a_bytes + 2 * b_slot + 2048 > IG_SMEM_BUDGET) break;
+      const double eff = (double)G * out_y * out_x / (T * 128.0);
+      if (eff > best + 1e-9) {
+        best = eff;
+        int nbs = (int)((IG_SMEM_BUDGET - 2048 - a_bytes) / b_slot);
+        if (nbs > 8) nbs = 8;
+        if (nbs > ntaps) nbs = ntaps;
+        p = IgemmParams{(B + G - 1) / G, 1, G, IR, PW, T, (int)rows, ntaps, fx, -pad_x, -pad_y, out_y, out_y, out_x, B, N, act, nbs};
+        pl.PH_box = PH;
+        pl.smem = 1024 + a_bytes + (size_t)nbs * b_slot;
+        pl.ok = true;
+      }
+    }
+  }
+  if (pl.ok) return pl;
+  // mode 2: one image, bands of RO output rows
+  for (int RO = out_y < 256 ? out_y : 255; RO >= 1; --RO) {
+    const int PHb = RO + fy - 1;
+    if (PHb > 256) continue;
+    const int IR = PHb * PW;
+    const long last = (long)(RO - 1) * PW + out_x;
+    const int T = (int)((last + 127) / 128);
+    if (T > Tmax) continue;
+    long rows = (long)T * 128 + max_shift;
+    if (rows < IR) rows = IR;
+    rows = (rows + 7) / 8 * 8;
+    const size_t a_bytes = 2 * (size_t)KH * rows * 128;
+    if (a_bytes + 2 * b_slot + 2048 > IG_SMEM_BUDGET) continue;
+    int nbs = (int)((IG_SMEM_BUDGET - 2048 - a_bytes) / b_slot);
+    if (nbs > 8) nbs = 8;
+    if (nbs > ntaps) nbs = ntaps;
+    const int nbands = (out_y + RO - 1) / RO;
+    p = IgemmParams{B * nbands, nbands, 1, IR, PW, T, (int)rows, ntaps, fx, -pad_x, -pad_y, RO, out_y, out_x, B, N, act, nbs};
+    pl.PH_box = PHb;
+    pl.smem = 1024 + a_bytes + (size_t)nbs * b_slot;
+    pl.ok = true;
+    return pl;
+  }
+  return pl;
+}
+
+template <int NB, int KH>
+static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, const IgemmPlan& pl, float* out, const float* bias,
+                        cudaStream_t s) {
+  BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  const int ctas = pl.p.nstages < num_sms() ? pl.p.nstages : num_sms();
+  dim3 grid(ctas, pl.p.N / NB);
+  conv_igemm_kernel<NB, KH><<<grid, IG_THREADS, pl.smem, s>>>(mA, mB, pl.p, out, bias);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+static inline int pick_nb(int N) {
+  if (N == 32 || N == 64 || N == 128) return N;
+  if (N > 128 && N % 128 == 0) return 128;
+  return 0;
+}
+
+bool conv_nhwc_supported(int C, int N, int fy, int fx) {
+  if (!tma_encode_fn()) return false;
+  const int KH = C / 32;
+  if (C % 32 != 0 || !(KH == 1 || KH == 2 || KH == 4)) return false;
+  if (pick_nb(N) == 0) return false;
+  if (fy * fx > 15 || fy < 1 || fx < 1) return false;
+  return true;
+}
+
+// out[(b,y,x), n] = act( sum_{ty,tx,c} in[b, y - pad_y + ty, x - pad_x + tx, c] * Wt[(ty,tx)][n][c] ) + bias[n]
+static int conv_nhwc_igemm(const float* in, const float* Wt, const float* bias, float* out, int B, int H, int W, int C,
+                           int N, int fy, int fx, int pad_y, int pad_x, int act, cudaStream_t s) {
+  const int KH = C / 32, NB = pick_nb(N);
+  IgemmPlan pl = plan_igemm(B, H, W, KH, NB, N, fy, fx, pad_y, pad_x, act);
+  if (!pl.ok) return fail(BF_ERR_ARG, "conv_nhwc: no tiling for plane %dx%d, %d->%d channels", H, W, C, N);
+  CUtensorMap mA, mB;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C, (uint64_t)C * W, (uint64_t)C * W * H};
+    uint32_t box[4] = {32, (uint32_t)pl.p.PW, (uint32_t)pl.PH_box, (uint32_t)pl.p.G};
+    if (!tma_make_map(&mA, in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return fail(BF_ERR_CUDA, "conv_nhwc: cuTensorMapEncodeTiled failed (activations %dx%dx%dx%d)", B, H, W, C);
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)(fy * fx)};
+    uint64_t str[2] = {(uint64_t)C, (uint64_t)C * N};
+    uint32_t box[3] = {32, (uint32_t)NB, 1};
+    if (!tma_make_map(&mB, Wt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return fail(BF_ERR_CUDA, "conv_nhwc: cuTensorMapEncodeTiled failed (filter)");
+  }
+#define BF_IG_CASE(NB_, KH_) if (NB == NB_ && KH == KH_) return launch_igemm<NB_, KH_>(mA, mB, pl, out, bias, s);
+  BF_IG_CASE(32, 1) BF_IG_CASE(32, 2) BF_IG_CASE(32, 4)
+  BF_IG_CASE(64, 1) BF_IG_CASE(64, 2) BF_IG_CASE(64, 4)
+  BF_IG_CASE(128, 1) BF_IG_CASE(128, 2) BF_IG_CASE(128, 4)
+#undef BF_IG_CASE
+  return fail(BF_ERR_ARG, "conv_nhwc: unsupported channel counts %d -> %d", C, N);
+}
+
+}  // namespace bf
+
+using namespace bf;
+
+// Y (im,oy,ox,nf) = act(valid_corr(X (im,iy,ix,ic), F (nf,ic,fy,fx))) + bias      [NHWC activations]
+int bf_conv_nhwc_forward(const float* X, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix, int nf,
+                         int fy, int fx, int act, void* stream) {
+  BF_REQUIRE(conv_nhwc_supported(ic, nf, fy, fx), BF_ERR_ARG, "bf_conv_nhwc_forward: unsupported shape (ic=%d nf=%d)", ic, nf);
+  if (im <= 0) return BF_OK;
+  cudaStream_t s = as_stream(stream);
+  void* ws = nullptr;
+  int rc = workspace_require(al256((size_t)nf * ic * fy * fx * 4), &ws);
+  if (rc) return rc;
+  conv_repack_nhwc_kernel<<<ew_grid((size_t)nf * ic * fy * fx, 256), 256, 0, s>>>(F, (float*)ws, nf, ic, fy, fx, 0);
+  BF_LAUNCH_CHECK();
+  set_last_path(2);
+  return conv_nhwc_igemm(X, (const float*)ws, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act, s);
+}
+
+// dX (im,iy,ix,ic) = full_corr(E (im,oy,ox,nf), flip(F)^T)                           [NHWC]
+int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX, int im, int ic, int iy, int ix, int nf, int fy,
+                               int fx, void* stream) {
+  BF_REQUIRE(conv_nhwc_supported(nf, ic, fy, fx), BF_ERR_ARG, "bf_conv_nhwc_backward_data: unsupported shape (ic=%d nf=%d)", ic, nf);
+  if (im <= 0) return BF_OK;
+  cudaStream_t s = as_stream(stream);
+  const int oy = iy - fy + 1, ox = ix - fx + 1;
+  void* ws = nullptr;
+  int rc = workspace_require(al256((size_t)nf * ic * fy * fx * 4), &ws);
+  if (rc) return rc;
+  conv_repack_nhwc_kernel<<<ew_grid((size_t)nf * ic * fy * fx, 256), 256, 0, s>>>(F, (float*)ws, nf, ic, fy, fx, 1);
+  BF_LAUNCH_CHECK();
+  set_last_path(2);
+  return conv_nhwc_igemm(E, (const float*)ws, nullptr, dX, im, oy, ox, nf, ic, fy, fx, fy - 1, fx - 1, BF_ACT_LINEAR, s);
+}
+
+// dF (nf,ic,fy,fx), db (nf) from X (im,iy,ix,ic), E (im,oy,ox,nf)                      [NHWC activations]
+int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix,
+                                 int nf, int fy, int fx, void* stream) {
+  BF_REQUIRE(ic % 32 == 0 && (nf == 32 || nf == 64 || nf == 128) && fy * fx <= 15 && tma_encode_fn() != nullptr, BF_ERR_ARG,
+             "bf_conv_nhwc_backward_filter: unsupported shape (ic=%d nf=%d)", ic, nf);
+  cudaStream_t s = as_stream(stream);
+  const int oy = iy - fy + 1, ox = ix - fx + 1, ntaps = fy * fx, MH = nf / 32, nch = ic / 32;
+  BF_REQUIRE(oy > 0 && ox > 0 && ix <= 256, BF_ERR_ARG, "bf_conv_nhwc_backward_filter: bad plane %dx%d", iy, ix);
+  if (im <= 0) {
+    BF_CUDA(cudaMemsetAsync(dF, 0, (size_t)nf * ic * ntaps * 4, s));
+    if (db) BF_CUDA(cudaMemsetAsync(db, 0, (size_t)nf * 4, s));
+    return BF_OK;
+  }
+  const int max_shift = (fy - 1) * ix + fx - 1;
+  DfParams p;
+  bool ok = false;
+  size_t smem = 0;
+  // mode 1: G whole images per stage (E loaded with iy rows so that both operands share the row index)
+  if (iy <= 256) {
+    const int IR = iy * ix;
+    for (int G = 1; G <= 256 && G <= im + 8; ++G) {
+      const int Krows = (G * IR + 7) / 8 * 8;
+      const int x_rows = (Krows + max_shift + 7) / 8 * 8;
+      const size_t bytes = df_smem_bytes(MH, Krows, x_rows);
+      if (bytes > IG_SMEM_BUDGET) break;
+      p = DfParams{(im + G - 1) / G, 1, G, IR, ix, iy, Krows, x_rows, ntaps, fx, im, 1, iy};
+      smem = bytes;
+      ok = true;
+    }
+  }
+  if (!ok) {
+    for (int RO = oy < 255 ? oy : 255; RO >= 1 && !ok; --RO) {
+      const int xr = RO + fy - 1;
+      if (xr > 256) continue;
+      const int Krows = (RO * ix + 7) / 8 * 8;
+      int x_rows = Krows + max_shift;
+      if (x_rows < xr * ix) x_rows = xr * ix;
+      x_rows = (x_rows + 7) / 8 * 8;
+      const size_t bytes = df_smem_bytes(MH, Krows, x_rows);
+      if (bytes > IG_SMEM_BUDGET) continue;
+      const int nbands = (oy + RO - 1) / RO;
+      p = DfParams{im * nbands, nbands, 1, xr * ix, ix, RO, Krows, x_rows, ntaps, fx, im, 1, RO};
+      smem = bytes;
+      ok = true;
+    }
+  }
+  BF_REQUIRE(ok, BF_ERR_ARG, "bf_conv_nhwc_backward_filter: no tiling for plane %dx%d", iy, ix);
+  int nsplit = num_sms() / nch;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > p.nstages) nsplit = p.nstages;
+  p.nsplit = nsplit;
+  const size_t part_bytes = al256((size_t)nsplit * nch * (ntaps + 1) * 128 * 32 * 4);
+  void* ws = nullptr;
+  int rc = workspace_require(part_bytes, &ws);
+  if (rc) return rc;
+  CUtensorMap mE, mX;
+  {
+    uint64_t dims[4] = {(uint64_t)nf, (uint64_t)ox, (uint64_t)oy, (uint64_t)im};
+    uint64_t str[3] = {(uint64_t)nf, (uint64_t)nf * ox, (uint64_t)nf * ox * oy};
+    uint32_t box[4] = {32, (uint32_t)ix, (uint32_t)p.e_rows_box, (uint32_t)p.G};
+    if (!tma_make_map(&mE, E, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return fail(BF_ERR_CUDA, "bf_conv_nhwc_backward_filter: cuTensorMapEncodeTiled failed (E)");
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)ic, (uint64_t)ix, (uint64_t)iy, (uint64_t)im};
+    uint64_t str[3] = {(uint64_t)ic, (uint64_t)ic * ix, (uint64_t)ic * ix * iy};
+    uint32_t box[4] = {32, (uint32_t)ix, (uint32_t)(p.IR / ix), (uint32_t)p.G};
+    if (!tma_make_map(&mX, X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return fail(BF_ERR_CUDA, "bf_conv_nhwc_backward_filter: cuTensorMapEncodeTiled failed (X)");
+  }
+  dim3 grid(nsplit, nch);
+#define BF_DF_CASE(MH_)                                                                                              \
+  if (MH == MH_) {                                                                                                   \
+    BF_CUDA(cudaFuncSetAttribute(conv_df_kernel<MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    conv_df_kernel<MH_><<<grid, IG_THREADS, smem, s>>>(mE, mX, p, (float*)ws);                                       \
+  }
+  BF_DF_CASE(1) BF_DF_CASE(2) BF_DF_CASE(4)
+#undef BF_DF_CASE
+  BF_LAUNCH_CHECK();
+  conv_df_reduce_nhwc_kernel<<<ew_grid((size_t)nf * ic * ntaps + nf, 256), 256, 0, s>>>((const float*)ws, dF, db, nsplit,
+                                                                                         nch, ntaps, nf, ic);
+  BF_LAUNCH_CHECK();
+  set_last_path(2);
+  return BF_OK;
+}
+
+int bf_conv_nhwc_supported(int ic, int nf, int fy, int fx) {
+  // forward needs (ic -> nf), the data gradient (nf -> ic), the filter gradient nf in {32,64,128}
+  return (conv_nhwc_supported(ic, nf, fy, fx) && conv_nhwc_supported(nf, ic, fy, fx) && (nf == 32 || nf == 64 || nf == 128))
+             ? 1 : 0;
+}

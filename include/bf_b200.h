@@ -107,6 +107,19 @@ BF_API int bf_conv_forward(const float* A, const float* F, const float* bias, fl
 BF_API int bf_conv_backward(const float* X, const float* E, const float* F, float* dF, float* db, float* dX, int im, int ic,
                      int iy, int ix, int nf, int fy, int fx, int precision, void* stream);
 
+/* ---- channels-last (NHWC) convolution on TMA + tcgen05 (the BF_PREC_TF32 fast path of ConvLayer) ----
+ * Same arithmetic as bf_conv_forward / bf_conv_backward (atomic/tensor_op.py:9-61) on activations stored
+ * (im, y, x, channel); the filter F stays (nf,ic,fy,fx) as the reference holds it.  Operands are staged by TMA
+ * only (no im2col), a filter tap is a row offset into the staged tile.  Shapes: ic and nf multiples of 32
+ * (bf_conv_nhwc_supported); everything else goes through bf_conv_forward / bf_conv_backward. */
+BF_API int bf_conv_nhwc_supported(int ic, int nf, int fy, int fx);
+BF_API int bf_conv_nhwc_forward(const float* X, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix,
+                         int nf, int fy, int fx, int act, void* stream);
+BF_API int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX, int im, int ic, int iy, int ix, int nf,
+                               int fy, int fx, void* stream);
+BF_API int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy,
+                                 int ix, int nf, int fy, int fx, void* stream);
+
 /* ---- max pooling: atomic/tensor_op.py:78-128, llatomic/lltensor_op.py:43-72 ---- */
 /* Bytes per window of the compact tie mask: 1 when fdim*fdim<=8, else 8 (fdim<=8). */
 BF_API size_t bf_pool_mask_bytes(int im, int ic, int iy, int ix, int fdim);
