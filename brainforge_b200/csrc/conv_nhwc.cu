@@ -22,30 +22,45 @@
 // (TMEM -> registers -> global); mbarrier rings between them; persistent CTAs, one per SM.
 #include "tma.cuh"
 #include "conv_nhwc.cuh"
+#include <stdlib.h>
 
 namespace bf {
 
-constexpr int IG_THREADS = 192;
+constexpr int IG_THREADS = 224;   // igemm: warp 0 TMA, warps 1-2 MMA issuers (tiles of even / odd index), warps 3-6 epilogue
+constexpr int DF_THREADS = 192;
 constexpr int IG_ACCSET_COLS = 256;   // two accumulator sets in the 512 TMEM columns
 
 struct IgemmParams {
   int nstages, nbands, G, IR, PW, T, slot_rows, ntaps, fx;
-  int x0, y0, RO, out_y, out_x, nimg, N, act, nbs;
+  int x0, y0, RO, out_y, out_x, nimg, N, relu, nbs;
+  int resident;   // the whole repacked filter stays in shared memory: no per-tap traffic or waits
+  int nkp;        // K passes per stage: the contraction channels are staged KH*32 at a time (C = nkp * KH * 32)
+  int na;         // depth of the A (activation tile) ring: HBM latency is hidden by na-1 tiles in flight
+  long long* prof;   // debug (BF_PROF_IGEMM=1): per-role cycle counters of CTA 0, else null
 };
 
-template <int NB, int KH>
+#define IG_T(var) long long var = p.prof ? clock64() : 0
+#define IG_ACC(slot, t0) do { if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) p.prof[slot] += clock64() - (t0); } while (0)
+constexpr int IG_STAGE_LD = 36;                                  // floats per staged epilogue row (32 + 4 pad)
+constexpr int IG_STAGING_BYTES = 4 * 32 * IG_STAGE_LD * 4;       // four epilogue warps
+
+template <int NB, int KH, bool RELU>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, IgemmParams p,
                   float* __restrict__ out, const float* __restrict__ bias) {
   extern __shared__ int dyn_smem[];
-  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2], b_full[8], b_empty[8];
+  __shared__ __align__(8) uint64_t a_full[8], a_empty[8], t_full[2], t_empty[2], b_full[16], b_empty[16];
   __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ __align__(16) float sbias[NB];
+  // warp-uniform role index (the shuffle tells the compiler it is uniform: the TMA / MMA operands then live in
+  // uniform registers instead of being broadcast lane by lane before every UTMALDG / UTCHMMA)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
   const uint32_t half_bytes = (uint32_t)p.slot_rows * 128u;
   const uint32_t a_slot_bytes = KH * half_bytes;
-  const uint32_t b_base0 = base + 2 * a_slot_bytes;
+  const uint32_t b_base0 = base + (uint32_t)p.na * a_slot_bytes;
   constexpr uint32_t B_SLOT = KH * NB * 128;
+  const uint32_t stage_base = b_base0 + (uint32_t)p.nbs * B_SLOT;
   const int n0 = blockIdx.y * NB;
 
   if (warp == 1) {
@@ -53,87 +68,131 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4);
-    }
-    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 2); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+    for (int i = 0; i < 16; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < NB) sbias[tid] = bias ? bias[n0 + tid] : 0.f;
   // rows of the A slots that TMA never writes are read by the taps of dropped positions only; give them a
   // defined value once so that no NaN pattern lingers there
-  for (uint32_t o = tid * 16u; o < 2 * a_slot_bytes; o += IG_THREADS * 16u)
+  for (uint32_t o = tid * 16u; o < (uint32_t)p.na * a_slot_bytes; o += IG_THREADS * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================================== TMA producer
+  if (warp == 0) {
+    // ===================================================================== TMA producer (whole warp loops, one
+    // elected lane issues)
+    const bool leader = elect_one_sync();
     uint32_t bcount = 0;
-    int it = 0;
-    for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
-      const int as = it & 1, au = it >> 1;
-      const int grp = st / p.nbands, band = st - grp * p.nbands;
-      if (au > 0) mbar_wait(&a_empty[as], (uint32_t)((au - 1) & 1));
-      mbar_expect_tx(&a_full[as], (uint32_t)(KH * p.G * p.IR * 128));
+    int ss = 0;   // sub-stage counter: (stage, K pass)
+    IG_T(tp);
+    if (p.resident && leader) {
+      mbar_expect_tx(&b_full[0], (uint32_t)(p.ntaps * p.nkp) * B_SLOT);
+      for (int kp = 0; kp < p.nkp; ++kp)
+        for (int tap = 0; tap < p.ntaps; ++tap)
 #pragma unroll
-      for (int h = 0; h < KH; ++h)
-        tma_load_4d(base + as * a_slot_bytes + h * half_bytes, &mapA, &a_full[as], h * 32, p.x0, p.y0 + band * p.RO,
-                    grp * p.G);
-      for (int tap = 0; tap < p.ntaps; ++tap, ++bcount) {
-        const uint32_t bs = bcount % (uint32_t)p.nbs, bu = bcount / (uint32_t)p.nbs;
-        if (bu > 0) mbar_wait(&b_empty[bs], (bu - 1) & 1);
-        mbar_expect_tx(&b_full[bs], B_SLOT);
-#pragma unroll
-        for (int h = 0; h < KH; ++h)
-          tma_load_3d(b_base0 + bs * B_SLOT + h * NB * 128, &mapB, &b_full[bs], h * 32, n0, tap);
-      }
+          for (int h = 0; h < KH; ++h)
+            tma_load_3d(b_base0 + (kp * p.ntaps + tap) * B_SLOT + h * NB * 128, &mapB, &b_full[0], (kp * KH + h) * 32, n0, tap);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================================== MMA issuer
-    constexpr uint32_t idesc = idesc_tf32(128, NB);
-    uint32_t bcount = 0;
-    int it = 0;
-    for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
-      const int as = it & 1, au = it >> 1;   // the accumulator set follows the same alternation
-      mbar_wait(&a_full[as], (uint32_t)(au & 1));
-      if (au > 0) mbar_wait(&t_empty[as], (uint32_t)((au - 1) & 1));
-      tc_fence_after();
-      const uint32_t a_slot = base + as * a_slot_bytes;
-      const uint32_t acc = tmem + as * IG_ACCSET_COLS;
-      for (int tap = 0; tap < p.ntaps; ++tap, ++bcount) {
-        const uint32_t bs = bcount % (uint32_t)p.nbs, bu = bcount / (uint32_t)p.nbs;
-        mbar_wait(&b_full[bs], bu & 1);
-        tc_fence_after();
-        const int ty = tap / p.fx, tx = tap - ty * p.fx;
-        const uint32_t shift_bytes = (uint32_t)(ty * p.PW + tx) * 128u;
-        const uint32_t b_slot = b_base0 + bs * B_SLOT;
-        for (int t = 0; t < p.T; ++t) {
+    for (int st = blockIdx.x; st < p.nstages; st += gridDim.x) {
+      const int grp = st / p.nbands, band = st - grp * p.nbands;
+      for (int kp = 0; kp < p.nkp; ++kp, ++ss) {
+        const int as = ss % p.na, au = ss / p.na;
+        { IG_T(t0); if (au > 0) mbar_wait(&a_empty[as], (uint32_t)((au - 1) & 1)); IG_ACC(0, t0); }
+        if (leader) {
+          mbar_expect_tx(&a_full[as], (uint32_t)(KH * p.G * p.IR * 128));
 #pragma unroll
-          for (int h = 0; h < KH; ++h) {
-            const uint64_t ad = desc_k_sw128(a_slot + h * half_bytes + (uint32_t)t * 16384u + shift_bytes);
-            const uint64_t bd = desc_k_sw128(b_slot + h * NB * 128);
+          for (int h = 0; h < KH; ++h)
+            tma_load_4d(base + as * a_slot_bytes + h * half_bytes, &mapA, &a_full[as], (kp * KH + h) * 32, p.x0,
+                        p.y0 + band * p.RO, grp * p.G);
+        }
+        if (!p.resident) {
+          for (int tap = 0; tap < p.ntaps; ++tap, ++bcount) {
+            const uint32_t bs = bcount % (uint32_t)p.nbs, bu = bcount / (uint32_t)p.nbs;
+            if (bu > 0) mbar_wait(&b_empty[bs], (bu - 1) & 1);
+            if (leader) {
+              mbar_expect_tx(&b_full[bs], B_SLOT);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_tf32(acc + t * NB, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc,
-                        (tap > 0 || h > 0 || ks > 0) ? 1u : 0u);
+              for (int h = 0; h < KH; ++h)
+                tma_load_3d(b_base0 + bs * B_SLOT + h * NB * 128, &mapB, &b_full[bs], (kp * KH + h) * 32, n0, tap);
+            }
           }
         }
-        umma_commit(&b_empty[bs]);
       }
-      umma_commit(&a_empty[as]);
-      umma_commit(&t_full[as]);
     }
-  } else if (warp >= 2) {
+    IG_ACC(1, tp);
+  } else if (warp == 1 || warp == 2) {
+    // ===================================================================== MMA issuers: warp 1 takes the even tiles of
+    // every stage, warp 2 the odd ones (one thread cannot issue tcgen05.mma faster than ~1 per 50-100 cycles,
+    // scripts/umma_rate2.cu); both wait on the same full barriers and both arrive on the empty ones
+    const int wsel = warp - 1;
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = idesc_tf32(128, NB);
+    const uint32_t half_units = half_bytes >> 4;
+    uint32_t bcount = 0;
+    int it = 0, ss = 0;
+    IG_T(tm);
+    for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
+      const int acc_set = it & 1, tu = it >> 1;
+      { IG_T(t0); if (tu > 0) mbar_wait(&t_empty[acc_set], (uint32_t)((tu - 1) & 1)); if (wsel == 0) IG_ACC(2, t0); }
+      const uint32_t acc = tmem + acc_set * IG_ACCSET_COLS;
+      for (int kp = 0; kp < p.nkp; ++kp, ++ss) {
+        const int as = ss % p.na, au = ss / p.na;
+        { IG_T(t0); mbar_wait(&a_full[as], (uint32_t)(au & 1)); if (wsel == 0) IG_ACC(3, t0); }
+        tc_fence_after();
+        const uint64_t a_desc0 = desc_k_sw128(base + as * a_slot_bytes);
+        int ty = 0, tx = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          uint32_t bs;
+          if (p.resident) {
+            bs = (uint32_t)(kp * p.ntaps + tap);
+            if (ss == 0 && tap == 0) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+          } else {
+            bs = bcount % (uint32_t)p.nbs;
+            mbar_wait(&b_full[bs], (bcount / (uint32_t)p.nbs) & 1);
+            tc_fence_after();
+            ++bcount;
+          }
+          const uint64_t a_tap = a_desc0 + (uint64_t)((uint32_t)(ty * p.PW + tx) * 8u);   // 128 B per pixel row = 8 units
+          const uint64_t b_tap = desc_k_sw128(b_base0 + bs * B_SLOT);
+          if (++tx == p.fx) { tx = 0; ++ty; }
+          for (int t = wsel; t < p.T; t += 2) {
+#pragma unroll
+            for (int h = 0; h < KH; ++h) {
+              const uint64_t ad = a_tap + (uint64_t)(h * half_units + (uint32_t)t * 1024u);
+              const uint64_t bd = b_tap + (uint64_t)(h * NB * 8);
+              if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_tf32(acc + t * NB, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc,
+                            (kp > 0 || tap > 0 || h > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+          }
+          if (!p.resident && leader) umma_commit(&b_empty[bs]);
+        }
+        if (leader) umma_commit(&a_empty[as]);
+      }
+      if (leader) umma_commit(&t_full[acc_set]);
+    }
+    if (wsel == 0) IG_ACC(4, tm);
+  } else if (warp >= 3) {
     // ===================================================================== epilogue (TMEM lanes 32*(warp%4)..+31)
+    // TMEM -> registers (+ReLU, +bias) -> a padded per-warp staging tile -> global, so that every store
+    // instruction writes whole 128-byte lines (4 rows x 32 channels) instead of 32 scattered 16-byte pieces.
     const int quad = warp & 3;
+    float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + quad * 32 * IG_STAGE_LD;
     int it = 0;
+    IG_T(te);
     for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
       const int as = it & 1, au = it >> 1;
       const int grp = st / p.nbands, band = st - grp * p.nbands;
-      mbar_wait(&t_full[as], (uint32_t)(au & 1));
+      { IG_T(t0); mbar_wait(&t_full[as], (uint32_t)(au & 1)); if (warp == 3 && lane == 0) IG_ACC(5, t0); }
       tc_fence_after();
       for (int t = 0; t < p.T; ++t) {
         const int q = t * 128 + quad * 32 + lane;
@@ -141,34 +200,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int y = ql / p.PW, x = ql - y * p.PW;
         const int img = grp * p.G + g, yo = band * p.RO + y;
         const bool ok = g < p.G && img < p.nimg && y < p.RO && yo < p.out_y && x < p.out_x;
-        float* dst = out + ((size_t)((size_t)img * p.out_y + yo) * p.out_x + x) * p.N + n0;
+        const int orow = (img * p.out_y + yo) * p.out_x + x;          // output pixel index (rows of N floats)
+        const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+        if (okmask == 0u) continue;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + as * IG_ACCSET_COLS + t * NB;
 #pragma unroll
-        for (int c0 = 0; c0 < NB; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (ok) {
+        for (int cb = 0; cb < NB; cb += 32) {
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + cb + c0, v);
+            tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              float4 r;
-              r.x = act_fwd_rt(p.act, __uint_as_float(v[j]));
-              r.y = act_fwd_rt(p.act, __uint_as_float(v[j + 1]));
-              r.z = act_fwd_rt(p.act, __uint_as_float(v[j + 2]));
-              r.w = act_fwd_rt(p.act, __uint_as_float(v[j + 3]));
-              if (bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-                r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
-              }
-              *reinterpret_cast<float4*>(dst + c0 + j) = r;
+              const float4 bb = *reinterpret_cast<const float4*>(&sbias[cb + c0 + j]);
+              float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+              r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+              *reinterpret_cast<float4*>(stg + lane * IG_STAGE_LD + c0 + j) = r;
             }
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            const int dst_row = __shfl_sync(0xffffffffu, orow, r);
+            const float4 val = *reinterpret_cast<const float4*>(stg + r * IG_STAGE_LD + (lane & 7) * 4);
+            if ((okmask >> r) & 1u)
+              *reinterpret_cast<float4*>(out + (size_t)dst_row * p.N + n0 + cb + (lane & 7) * 4) = val;
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[as]);
     }
+    if (warp == 3 && lane == 0) IG_ACC(6, te);
   }
   tc_fence_before();
   __syncthreads();
@@ -178,20 +247,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // --------------------------------------------------------------------------------------------- dF (+ db)
 struct DfParams {
   int nstages, nbands, G, IR, PW, RO, Krows, x_rows, ntaps, fx, nimg, nsplit, e_rows_box;
+  int ns;   // ring depth (stages in flight)
 };
 
 template <int MH>
-__global__ void __launch_bounds__(IG_THREADS, 1)
+__global__ void __launch_bounds__(DF_THREADS, 1)
 conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__ CUtensorMap mapX, DfParams p,
                float* __restrict__ partial) {
   extern __shared__ int dyn_smem[];
-  __shared__ __align__(8) uint64_t full[2], empty[2], done;
+  __shared__ __align__(8) uint64_t full[8], empty[8], done;
   __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
   const uint32_t e_half = (uint32_t)p.Krows * 128u, e_slot = MH * e_half, x_slot = (uint32_t)p.x_rows * 128u;
-  const uint32_t x_base = base + 2 * e_slot, ones_base = x_base + 2 * x_slot;
-  const uint32_t total_bytes = 2 * e_slot + 2 * x_slot + 1024u;
+  const uint32_t x_base = base + (uint32_t)p.ns * e_slot, ones_base = x_base + (uint32_t)p.ns * x_slot;
+  const uint32_t total_bytes = (uint32_t)p.ns * (e_slot + x_slot) + 1024u;
   const int split = blockIdx.x, ch = blockIdx.y;
   const int ntap_acc = p.ntaps + (ch == 0 ? 1 : 0);   // channel half 0 also accumulates db (all-ones operand)
 
@@ -200,12 +270,12 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero everything once: the K-padding rows of E and the tail rows of X are never written by TMA and must stay 0
-  for (uint32_t o = tid * 16u; o < total_bytes; o += IG_THREADS * 16u) {
+  for (uint32_t o = tid * 16u; o < total_bytes; o += DF_THREADS * 16u) {
     const uint32_t v = (base + o >= ones_base) ? 0x3f800000u : 0u;
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(v) : "memory");
   }
@@ -213,46 +283,56 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
   int my_stages = 0;
   for (int st = split; st < p.nstages; st += p.nsplit) ++my_stages;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+    const bool leader = elect_one_sync();
     int it = 0;
     const uint32_t e_box_bytes = (uint32_t)(p.G * p.e_rows_box * p.PW) * 128u;
     const uint32_t x_box_bytes = (uint32_t)(p.G * p.IR) * 128u;
     for (int st = split; st < p.nstages; st += p.nsplit, ++it) {
-      const int s = it & 1, u = it >> 1;
+      const int s = it % p.ns, u = it / p.ns;
       const int grp = st / p.nbands, band = st - grp * p.nbands;
       if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
-      mbar_expect_tx(&full[s], MH * e_box_bytes + x_box_bytes);
+      if (leader) {
+        mbar_expect_tx(&full[s], MH * e_box_bytes + x_box_bytes);
 #pragma unroll
-      for (int h = 0; h < MH; ++h)
-        tma_load_4d(base + s * e_slot + h * e_half, &mapE, &full[s], h * 32, 0, band * p.RO, grp * p.G);
-      tma_load_4d(x_base + s * x_slot, &mapX, &full[s], ch * 32, 0, band * p.RO, grp * p.G);
+        for (int h = 0; h < MH; ++h)
+          tma_load_4d(base + s * e_slot + h * e_half, &mapE, &full[s], h * 32, 0, band * p.RO, grp * p.G);
+        tma_load_4d(x_base + s * x_slot, &mapX, &full[s], ch * 32, 0, band * p.RO, grp * p.G);
+      }
     }
-  } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = idesc_tf32(128, 32, true, true);
+  } else if (warp == 1) {
+    const bool leader = elect_one_sync();
+    // One MMA per filter ROW: the fx taps of a row are fx 32-channel N groups of the SAME operand, one pixel
+    // (128 B = LBO) apart, landing in fx consecutive 32-column accumulators.
+    const int fy = p.ntaps / p.fx;
+    const uint32_t idesc_row = idesc_tf32(128, 32 * p.fx, true, true);
+    constexpr uint32_t idesc_one = idesc_tf32(128, 32, true, true);
+    const uint64_t ones_desc = desc_mn_sw128_32b(ones_base, 4096u, 512u);
+    const uint32_t row_step = (uint32_t)(p.PW * 128) >> 4;   // descriptor units (16 B) per filter row
     int it = 0;
     const int ksteps = p.Krows / 8;
     for (int st = split; st < p.nstages; st += p.nsplit, ++it) {
-      const int s = it & 1, u = it >> 1;
+      const int s = it % p.ns, u = it / p.ns;
       mbar_wait(&full[s], (uint32_t)(u & 1));
       tc_fence_after();
-      const uint32_t e0 = base + s * e_slot, x0 = x_base + s * x_slot;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t ad = desc_mn_sw128_32b(e0 + (uint32_t)ks * 1024u, e_half, 512u);
+      uint64_t ad = desc_mn_sw128_32b(base + s * e_slot, e_half, 512u);
+      uint64_t bd = desc_mn_sw128_32b(x_base + s * x_slot, 128u, 512u);
+      for (int ks = 0; ks < ksteps; ++ks, ad += 64, bd += 64) {   // 8 pixel rows = 1024 B per K step
         const uint32_t acc_flag = (it > 0 || ks > 0) ? 1u : 0u;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int ty = tap / p.fx, tx = tap - ty * p.fx;
-          const uint64_t bd = desc_mn_sw128_32b(x0 + (uint32_t)(ks * 8 + ty * p.PW + tx) * 128u, 4096u, 512u);
-          umma_tf32(tmem + tap * 32, ad, bd, idesc, acc_flag);
+        uint64_t bdr = bd;
+        if (leader) {
+          for (int ty = 0; ty < fy; ++ty, bdr += row_step)
+            umma_tf32(tmem + ty * p.fx * 32, ad, bdr, idesc_row, acc_flag);
+          if (ch == 0) umma_tf32(tmem + p.ntaps * 32, ad, ones_desc, idesc_one, acc_flag);
         }
-        if (ch == 0) umma_tf32(tmem + p.ntaps * 32, ad, desc_mn_sw128_32b(ones_base, 4096u, 512u), idesc, acc_flag);
       }
-      umma_commit(&empty[s]);
+      if (leader) umma_commit(&empty[s]);
     }
-    umma_commit(&done);
+    if (leader) umma_commit(&done);
   } else if (warp >= 2) {
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
@@ -322,15 +402,15 @@ __global__ void conv_repack_nhwc_kernel(const float* __restrict__ F, float* __re
 }
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-// dF kernel: [E slot 0 | E slot 1 | X slot 0 | X slot 1 | ones]; the A operand always spans four 32-filter groups
-// (M = 128), so for nf < 128 the junk groups of E slot 1 must still fall inside the allocation
-static inline size_t df_smem_bytes(int MH, int Krows, int x_rows) {
-  size_t rows = 2 * ((size_t)MH * Krows + x_rows) + 8;
-  const size_t reach = (size_t)MH * Krows + 4 * (size_t)Krows;
+// dF kernel: [E slots | X slots | ones]; the A operand always spans four 32-filter groups (M = 128), so for
+// nf < 128 the junk groups read behind the last E slot must still fall inside the allocation
+static inline size_t df_smem_bytes(int MH, int Krows, int x_rows, int ns) {
+  size_t rows = (size_t)ns * ((size_t)MH * Krows + x_rows) + 8;
+  const size_t reach = (size_t)(ns - 1) * MH * Krows + 4 * (size_t)Krows;
   if (rows < reach) rows = reach;
   return rows * 128 + 1024;
 }
-constexpr size_t IG_SMEM_BUDGET = 220 * 1024;
+constexpr size_t IG_SMEM_BUDGET = 224 * 1024;
 
 struct IgemmPlan {
   IgemmParams p;
@@ -339,12 +419,12 @@ struct IgemmPlan {
   bool ok;
 };
 
-// Picks images-per-stage (or output-row bands for large planes) so that the accumulators fit one TMEM set and two
-// A slots + the B ring fit shared memory; maximises useful positions per 128-row tile.
-static IgemmPlan plan_igemm(int B, int H, int W, int KH, int NB, int N, int fy, int fx, int pad_y, int pad_x, int act) {
+// Picks images-per-stage or output-row bands so that the accumulators fit one TMEM set and two A slots + the
+// filter (resident if it fits, else a ring of taps) + the epilogue staging fit shared memory.
+static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N, int fy, int fx, int pad_y, int pad_x,
+                            int relu) {
   IgemmPlan pl;
   pl.ok = false;
-  IgemmParams& p = pl.p;
   const int PW = W + 2 * pad_x, PH = H + 2 * pad_y;
   const int out_y = PH - fy + 1, out_x = PW - fx + 1;
   if (out_y <= 0 || out_x <= 0 || PW > 256) return pl;
@@ -352,67 +432,92 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int NB, int N, int fy, 
   const int Tmax = IG_ACCSET_COLS / NB;
   const int ntaps = fy * fx;
   const size_t b_slot = (size_t)KH * NB * 128;
+  const size_t fixed = 2048 + IG_STAGING_BYTES;
   double best = -1;
-  // mode 1: G whole images per stage
-  if (PH <= 256) {
-    const int IR = PH * PW;
-    for (int G = 1; G <= 256 && G <= B + 8; ++G) {
-      const long last = (long)(G - 1) * IR + (long)(out_y - 1) * PW + out_x;   // positions to cover
-      const int T = (int)((last + 127) / 128);
-      if (T > Tmax) break;
-      long rows = (long)T * 128 + max_shift;
-      if (rows < (long)G * IR) rows = (long)G * IR;
-      rows = (rows + 7) / 8 * 8;
-      const size_t a_bytes = 2 * (size_t)KH * rows * 128;
-      if (a_bytes + 2 * b_slot + 2048 > IG_SMEM_BUDGET) break;
-      const double eff = (double)G * out_y * out_x / (T * 128.0);
-      if (eff > best + 1e-9) {
-        best = eff;
-        int nbs = (int)((IG_SMEM_BUDGET - 2048 - a_bytes) / b_slot);
-        if (nbs > 8) nbs = 8;
-        if (nbs > ntaps) nbs = ntaps;
-        p = IgemmParams{(B + G - 1) / G, 1, G, IR, PW, T, (int)rows, ntaps, fx, -pad_x, -pad_y, out_y, out_y, out_x, B, N, act, nbs};
-        pl.PH_box = PH;
-        pl.smem = 1024 + a_bytes + (size_t)nbs * b_slot;
-        pl.ok = true;
-      }
-    }
-  }
-  if (pl.ok) return pl;
-  // mode 2: one image, bands of RO output rows
-  for (int RO = out_y < 256 ? out_y : 255; RO >= 1; --RO) {
-    const int PHb = RO + fy - 1;
-    if (PHb > 256) continue;
+  // cost model (cycles per stage on one SM): the MMAs are bound by shared-memory operand reads for NB < 128
+  // ((128 + NB) rows x 32 B per K=8 step at 128 B/clk) or by the tensor pipe (NB/2 clk per step); the loads by the
+  // SM's share of HBM/L2 bandwidth (~24 B/clk); a shallow ring leaves the load latency exposed.
+  auto consider = [&](int G, int nbands, int RO, int PHb) {
     const int IR = PHb * PW;
-    const long last = (long)(RO - 1) * PW + out_x;
+    const long last = (long)(G - 1) * IR + (long)(RO - 1) * PW + out_x;   // positions to cover
     const int T = (int)((last + 127) / 128);
-    if (T > Tmax) continue;
+    if (T > Tmax) return false;
     long rows = (long)T * 128 + max_shift;
-    if (rows < IR) rows = IR;
+    if (rows < (long)G * IR) rows = (long)G * IR;
     rows = (rows + 7) / 8 * 8;
-    const size_t a_bytes = 2 * (size_t)KH * rows * 128;
-    if (a_bytes + 2 * b_slot + 2048 > IG_SMEM_BUDGET) continue;
-    int nbs = (int)((IG_SMEM_BUDGET - 2048 - a_bytes) / b_slot);
-    if (nbs > 8) nbs = 8;
-    if (nbs > ntaps) nbs = ntaps;
-    const int nbands = (out_y + RO - 1) / RO;
-    p = IgemmParams{B * nbands, nbands, 1, IR, PW, T, (int)rows, ntaps, fx, -pad_x, -pad_y, RO, out_y, out_x, B, N, act, nbs};
-    pl.PH_box = PHb;
-    pl.smem = 1024 + a_bytes + (size_t)nbs * b_slot;
-    pl.ok = true;
-    return pl;
+    const size_t a_slot = (size_t)KH * rows * 128;
+    if (2 * a_slot + 2 * b_slot + fixed > IG_SMEM_BUDGET) return false;
+    const size_t b_all = (size_t)ntaps * nkp * b_slot;
+    const bool resident = 2 * a_slot + b_all + fixed <= IG_SMEM_BUDGET;
+    int na, nbs;
+    if (resident) {
+      nbs = ntaps * nkp;
+      na = (int)((IG_SMEM_BUDGET - fixed - b_all) / a_slot);
+    } else {
+      na = 4;
+      while (na > 2 && (IG_SMEM_BUDGET - fixed - na * a_slot) / b_slot < (size_t)(ntaps < 4 ? ntaps : 4)) --na;
+      if (na * a_slot + 2 * b_slot + fixed > IG_SMEM_BUDGET) na = 2;
+      nbs = (int)((IG_SMEM_BUDGET - fixed - na * a_slot) / b_slot);
+      if (nbs > 16) nbs = 16;
+    }
+    if (na > 8) na = 8;
+    // per K=8 step a 128-row tile costs max(tensor NB/2, shared-memory operand reads (128+NB)/4) cycles, but one
+    // issuing thread sustains only ~1 MMA per 100 cycles (two issuers when T >= 2)
+    const double mma_step = NB / 2.0 > (128 + NB) / 4.0 ? NB / 2.0 : (128 + NB) / 4.0;
+    const double issue = T >= 2 ? 60.0 : 120.0;
+    const double mma_clk = (double)ntaps * nkp * T * KH * 4 * (mma_step > issue ? mma_step : issue);
+    const double bytes = (double)KH * nkp * G * IR * 128 + (resident ? 0.0 : (double)b_all);
+    double stage_clk = mma_clk > bytes / 24.0 ? mma_clk : bytes / 24.0;
+    stage_clk += 600.0 + (na == 2 ? 1500.0 : 0.0) + (!resident && nbs < 4 ? 1500.0 : 0.0);
+    const double score = (double)G * RO * out_x / stage_clk;
+    if (score > best) {
+      best = score;
+      pl.p = IgemmParams{nbands == 1 ? (B + G - 1) / G : B * nbands, nbands, G, IR, PW, T, (int)rows, ntaps, fx, -pad_x, -pad_y,
+                         RO, out_y, out_x, B, N, relu, nbs, resident ? 1 : 0, nkp, na, nullptr};
+      pl.PH_box = PHb;
+      pl.smem = 1024 + (size_t)na * a_slot + (size_t)nbs * b_slot + IG_STAGING_BYTES;
+      pl.ok = true;
+    }
+    return true;
+  };
+  if (PH <= 256)
+    for (int G = 1; G <= 256 && G <= B + 8; ++G)
+      if (!consider(G, 1, out_y, PH)) break;
+  for (int RO = (out_y < 254 ? out_y - 1 : 254); RO >= 1; --RO) {
+    if (RO + fy - 1 > 256) continue;
+    consider(1, (out_y + RO - 1) / RO, RO, RO + fy - 1);
   }
   return pl;
 }
 
 template <int NB, int KH>
-static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, const IgemmPlan& pl, float* out, const float* bias,
+static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, IgemmPlan& pl, float* out, const float* bias,
                         cudaStream_t s) {
-  BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  static long long* d_prof = nullptr;
+  const bool prof = getenv("BF_PROF_IGEMM") != nullptr;
+  if (prof) {
+    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), s);
+    pl.p.prof = d_prof;
+  }
   const int ctas = pl.p.nstages < num_sms() ? pl.p.nstages : num_sms();
   dim3 grid(ctas, pl.p.N / NB);
-  conv_igemm_kernel<NB, KH><<<grid, IG_THREADS, pl.smem, s>>>(mA, mB, pl.p, out, bias);
+  if (pl.p.relu) {
+    BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    conv_igemm_kernel<NB, KH, true><<<grid, IG_THREADS, pl.smem, s>>>(mA, mB, pl.p, out, bias);
+  } else {
+    BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    conv_igemm_kernel<NB, KH, false><<<grid, IG_THREADS, pl.smem, s>>>(mA, mB, pl.p, out, bias);
+  }
   BF_LAUNCH_CHECK();
+  if (prof) {
+    long long h[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    const int mine = (pl.p.nstages + ctas - 1) / ctas;
+    fprintf(stderr, "[igemm prof, CTA 0, %d stages] producer: wait a_empty %lld, total %lld | mma: wait t_empty %lld, wait a_full %lld, "
+            "total %lld | epilogue: wait t_full %lld, total %lld  (cycles)\n", mine, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+  }
   return BF_OK;
 }
 
@@ -424,8 +529,7 @@ static inline int pick_nb(int N) {
 
 bool conv_nhwc_supported(int C, int N, int fy, int fx) {
   if (!tma_encode_fn()) return false;
-  const int KH = C / 32;
-  if (C % 32 != 0 || !(KH == 1 || KH == 2 || KH == 4)) return false;
+  if (C % 32 != 0 || C <= 0 || C > 1024) return false;
   if (pick_nb(N) == 0) return false;
   if (fy * fx > 15 || fy < 1 || fx < 1) return false;
   return true;
@@ -433,10 +537,15 @@ bool conv_nhwc_supported(int C, int N, int fy, int fx) {
 
 // out[(b,y,x), n] = act( sum_{ty,tx,c} in[b, y - pad_y + ty, x - pad_x + tx, c] * Wt[(ty,tx)][n][c] ) + bias[n]
 static int conv_nhwc_igemm(const float* in, const float* Wt, const float* bias, float* out, int B, int H, int W, int C,
-                           int N, int fy, int fx, int pad_y, int pad_x, int act, cudaStream_t s) {
-  const int KH = C / 32, NB = pick_nb(N);
-  IgemmPlan pl = plan_igemm(B, H, W, KH, NB, N, fy, fx, pad_y, pad_x, act);
+                           int N, int fy, int fx, int pad_y, int pad_x, int relu, cudaStream_t s) {
+  const int KH = (C % 64 == 0) ? 2 : 1, nkp = C / (32 * KH), NB = pick_nb(N);
+  IgemmPlan pl = plan_igemm(B, H, W, KH, nkp, NB, N, fy, fx, pad_y, pad_x, relu);
   if (!pl.ok) return fail(BF_ERR_ARG, "conv_nhwc: no tiling for plane %dx%d, %d->%d channels", H, W, C, N);
+  if ((long)B * pl.p.out_y * pl.p.out_x >= 2147483647L) return fail(BF_ERR_ARG, "conv_nhwc: too many output pixels");
+  if (getenv("BF_DEBUG_PLAN"))
+    fprintf(stderr, "[igemm %dx%dx%d->%d pad %d] G=%d bands=%d RO=%d T=%d rows=%d KH=%d nkp=%d NB=%d na=%d nbs=%d resident=%d smem=%zu stages=%d\n",
+            H, W, C, N, pad_y, pl.p.G, pl.p.nbands, pl.p.RO, pl.p.T, pl.p.slot_rows, KH, nkp, NB, pl.p.na, pl.p.nbs, pl.p.resident, pl.smem,
+            pl.p.nstages);
   CUtensorMap mA, mB;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -453,9 +562,7 @@ static int conv_nhwc_igemm(const float* in, const float* Wt, const float* bias, 
       return fail(BF_ERR_CUDA, "conv_nhwc: cuTensorMapEncodeTiled failed (filter)");
   }
 #define BF_IG_CASE(NB_, KH_) if (NB == NB_ && KH == KH_) return launch_igemm<NB_, KH_>(mA, mB, pl, out, bias, s);
-  BF_IG_CASE(32, 1) BF_IG_CASE(32, 2) BF_IG_CASE(32, 4)
-  BF_IG_CASE(64, 1) BF_IG_CASE(64, 2) BF_IG_CASE(64, 4)
-  BF_IG_CASE(128, 1) BF_IG_CASE(128, 2) BF_IG_CASE(128, 4)
+  BF_IG_CASE(32, 1) BF_IG_CASE(32, 2) BF_IG_CASE(64, 1) BF_IG_CASE(64, 2) BF_IG_CASE(128, 1) BF_IG_CASE(128, 2)
 #undef BF_IG_CASE
   return fail(BF_ERR_ARG, "conv_nhwc: unsupported channel counts %d -> %d", C, N);
 }
@@ -468,6 +575,8 @@ using namespace bf;
 int bf_conv_nhwc_forward(const float* X, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix, int nf,
                          int fy, int fx, int act, void* stream) {
   BF_REQUIRE(conv_nhwc_supported(ic, nf, fy, fx), BF_ERR_ARG, "bf_conv_nhwc_forward: unsupported shape (ic=%d nf=%d)", ic, nf);
+  BF_REQUIRE(act == BF_ACT_LINEAR || act == BF_ACT_RELU, BF_ERR_ARG,
+             "bf_conv_nhwc_forward: only linear / relu are fused into the epilogue (got act %d)", act);
   if (im <= 0) return BF_OK;
   cudaStream_t s = as_stream(stream);
   void* ws = nullptr;
@@ -476,7 +585,7 @@ int bf_conv_nhwc_forward(const float* X, const float* F, const float* bias, floa
   conv_repack_nhwc_kernel<<<ew_grid((size_t)nf * ic * fy * fx, 256), 256, 0, s>>>(F, (float*)ws, nf, ic, fy, fx, 0);
   BF_LAUNCH_CHECK();
   set_last_path(2);
-  return conv_nhwc_igemm(X, (const float*)ws, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act, s);
+  return conv_nhwc_igemm(X, (const float*)ws, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act == BF_ACT_RELU ? 1 : 0, s);
 }
 
 // dX (im,iy,ix,ic) = full_corr(E (im,oy,ox,nf), flip(F)^T)                           [NHWC]
@@ -492,13 +601,13 @@ int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX, int im
   conv_repack_nhwc_kernel<<<ew_grid((size_t)nf * ic * fy * fx, 256), 256, 0, s>>>(F, (float*)ws, nf, ic, fy, fx, 1);
   BF_LAUNCH_CHECK();
   set_last_path(2);
-  return conv_nhwc_igemm(E, (const float*)ws, nullptr, dX, im, oy, ox, nf, ic, fy, fx, fy - 1, fx - 1, BF_ACT_LINEAR, s);
+  return conv_nhwc_igemm(E, (const float*)ws, nullptr, dX, im, oy, ox, nf, ic, fy, fx, fy - 1, fx - 1, 0, s);
 }
 
 // dF (nf,ic,fy,fx), db (nf) from X (im,iy,ix,ic), E (im,oy,ox,nf)                      [NHWC activations]
 int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix,
                                  int nf, int fy, int fx, void* stream) {
-  BF_REQUIRE(ic % 32 == 0 && (nf == 32 || nf == 64 || nf == 128) && fy * fx <= 15 && tma_encode_fn() != nullptr, BF_ERR_ARG,
+  BF_REQUIRE(ic % 32 == 0 && (nf == 32 || nf == 64 || nf == 128) && fy * fx <= 15 && fx <= 8 && tma_encode_fn() != nullptr, BF_ERR_ARG,
              "bf_conv_nhwc_backward_filter: unsupported shape (ic=%d nf=%d)", ic, nf);
   cudaStream_t s = as_stream(stream);
   const int oy = iy - fy + 1, ox = ix - fx + 1, ntaps = fy * fx, MH = nf / 32, nch = ic / 32;
@@ -512,36 +621,42 @@ int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, floa
   DfParams p;
   bool ok = false;
   size_t smem = 0;
-  // mode 1: G whole images per stage (E loaded with iy rows so that both operands share the row index)
-  if (iy <= 256) {
-    const int IR = iy * ix;
-    for (int G = 1; G <= 256 && G <= im + 8; ++G) {
-      const int Krows = (G * IR + 7) / 8 * 8;
-      const int x_rows = (Krows + max_shift + 7) / 8 * 8;
-      const size_t bytes = df_smem_bytes(MH, Krows, x_rows);
-      if (bytes > IG_SMEM_BUDGET) break;
-      p = DfParams{(im + G - 1) / G, 1, G, IR, ix, iy, Krows, x_rows, ntaps, fx, im, 1, iy};
-      smem = bytes;
+  double best = -1;
+  // candidates: G whole images per stage (E loaded with iy rows so that both operands share the row index) or
+  // bands of RO filter-gradient rows of one image; score = useful pixels per estimated stage time, where a
+  // ring of fewer than 4 stages leaves the load latency exposed
+  auto consider = [&](int G, int nbands, int RO, int e_rows, int xr) {
+    const int IRx = xr * ix;
+    const int Krows = (G * (nbands == 1 ? IRx : RO * ix) + 7) / 8 * 8;
+    int x_rows = Krows + max_shift;
+    if (x_rows < G * IRx) x_rows = G * IRx;
+    x_rows = (x_rows + 7) / 8 * 8;
+    int ns = 8;
+    while (ns >= 2 && df_smem_bytes(MH, Krows, x_rows, ns) > IG_SMEM_BUDGET) --ns;
+    if (ns < 2) return false;
+    const double mma_clk = (Krows / 8) * (fy * ((128 + 32.0 * fx) / 4.0) + 40.0);
+    const double bytes = (double)G * (MH * e_rows + xr) * ix * 128.0;
+    double stage_clk = (mma_clk > bytes / 24.0 ? mma_clk : bytes / 24.0) + 400.0 + (ns == 2 ? 3000.0 : ns == 3 ? 1000.0 : 0.0);
+    const double score = (double)G * RO * ox / stage_clk;
+    if (score > best) {
+      best = score;
+      p = DfParams{nbands == 1 ? (im + G - 1) / G : im * nbands, nbands, G, IRx, ix, RO, Krows, x_rows, ntaps, fx, im, 1, e_rows, ns};
+      smem = df_smem_bytes(MH, Krows, x_rows, ns);
       ok = true;
     }
-  }
-  if (!ok) {
-    for (int RO = oy < 255 ? oy : 255; RO >= 1 && !ok; --RO) {
-      const int xr = RO + fy - 1;
-      if (xr > 256) continue;
-      const int Krows = (RO * ix + 7) / 8 * 8;
-      int x_rows = Krows + max_shift;
-      if (x_rows < xr * ix) x_rows = xr * ix;
-      x_rows = (x_rows + 7) / 8 * 8;
-      const size_t bytes = df_smem_bytes(MH, Krows, x_rows);
-      if (bytes > IG_SMEM_BUDGET) continue;
-      const int nbands = (oy + RO - 1) / RO;
-      p = DfParams{im * nbands, nbands, 1, xr * ix, ix, RO, Krows, x_rows, ntaps, fx, im, 1, RO};
-      smem = bytes;
-      ok = true;
-    }
+    return true;
+  };
+  if (iy <= 256)
+    for (int G = 1; G <= 256 && G <= im + 8; ++G)
+      if (!consider(G, 1, oy, iy, iy)) break;
+  for (int RO = (oy < 254 ? oy - 1 : 254); RO >= 1; --RO) {
+    if (RO + fy - 1 > 256) continue;
+    consider(1, (oy + RO - 1) / RO, RO, RO, RO + fy - 1);
   }
   BF_REQUIRE(ok, BF_ERR_ARG, "bf_conv_nhwc_backward_filter: no tiling for plane %dx%d", iy, ix);
+  if (getenv("BF_DEBUG_PLAN"))
+    fprintf(stderr, "[df %dx%dx%d->%d] G=%d bands=%d RO=%d Krows=%d x_rows=%d ns=%d smem=%zu stages=%d\n", iy, ix, ic, nf, p.G,
+            p.nbands, p.RO, p.Krows, p.x_rows, p.ns, smem, p.nstages);
   int nsplit = num_sms() / nch;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > p.nstages) nsplit = p.nstages;
@@ -569,7 +684,7 @@ int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, floa
 #define BF_DF_CASE(MH_)                                                                                              \
   if (MH == MH_) {                                                                                                   \
     BF_CUDA(cudaFuncSetAttribute(conv_df_kernel<MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    conv_df_kernel<MH_><<<grid, IG_THREADS, smem, s>>>(mE, mX, p, (float*)ws);                                       \
+    conv_df_kernel<MH_><<<grid, DF_THREADS, smem, s>>>(mE, mX, p, (float*)ws);                                       \
   }
   BF_DF_CASE(1) BF_DF_CASE(2) BF_DF_CASE(4)
 #undef BF_DF_CASE
