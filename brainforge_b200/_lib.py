@@ -48,6 +48,9 @@ SIGNATURES = {
     "bf_conv_nhwc_forward": (_i, [_vp] * 4 + [_i] * 8 + [_vp]),
     "bf_conv_nhwc_backward_data": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "bf_conv_nhwc_backward_filter": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
+    "bf_conv_c3_supported": (_i, [_i] * 6),
+    "bf_conv_c3_forward": (_i, [_vp] * 4 + [_i] * 8 + [_vp]),
+    "bf_conv_c3_backward_filter": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
     "bf_pool_mask_bytes": (_sz, [_i] * 5),
     "bf_pool_forward": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "bf_pool_backward": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),

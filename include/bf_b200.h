@@ -120,6 +120,15 @@ BF_API int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX,
 BF_API int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy,
                                  int ix, int nf, int fy, int fx, void* stream);
 
+/* First layer (ic <= 4 input channels, e.g. RGB): X stays NCHW as the reference holds it, the 32/64/128-channel
+ * side (Y, E) is channels-last.  Forward = Toeplitz-descriptor implicit GEMM (no im2col), filter gradient = TMA-fed
+ * E operand + SIMT-gathered patch rows; both on tcgen05 (atomic/tensor_op.py:9-32,49-55). */
+BF_API int bf_conv_c3_supported(int ic, int iy, int ix, int nf, int fy, int fx);
+BF_API int bf_conv_c3_forward(const float* X, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix,
+                       int nf, int fy, int fx, int act, void* stream);
+BF_API int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix,
+                               int nf, int fy, int fx, void* stream);
+
 /* ---- max pooling: atomic/tensor_op.py:78-128, llatomic/lltensor_op.py:43-72 ---- */
 /* Bytes per window of the compact tie mask: 1 when fdim*fdim<=8, else 8 (fdim<=8). */
 BF_API size_t bf_pool_mask_bytes(int im, int ic, int iy, int ix, int fdim);
