@@ -219,6 +219,27 @@ def algorithmic_cost(label):
         X, E, F = im * ic * iy * ix, im * nf * oy * ox, nf * ic * fy * fx
         flops = 2.0 * im * oy * ox * nf * ic * fy * fx
         return (f * (X + E + F + nf), flops) if tag == "dF" else (f * (E + F + X), flops)
+    if name in ("bf_conv_nhwc_forward", "bf_conv_c3_forward"):
+        im, ic, iy, ix, nf, fy, fx = a[:7]
+        oy, ox = iy - fy + 1, ix - fx + 1
+        return f * (im * ic * iy * ix + nf * ic * fy * fx + nf + im * nf * oy * ox), 2.0 * im * oy * ox * nf * ic * fy * fx
+    if name in ("bf_conv_nhwc_backward_filter", "bf_conv_c3_backward_filter", "bf_conv_nhwc_backward_data"):
+        im, ic, iy, ix, nf, fy, fx = a[:7]
+        oy, ox = iy - fy + 1, ix - fx + 1
+        X, E, F = im * ic * iy * ix, im * nf * oy * ox, nf * ic * fy * fx
+        flops = 2.0 * im * oy * ox * nf * ic * fy * fx
+        return (f * (E + F + X), flops) if name.endswith("data") else (f * (X + E + F + nf), flops)
+    if name == "bf_pool_nhwc_forward":      # read A, write pooled out + 1 mask byte per window
+        im, c, iy, ix, fd = a[:5]
+        n = im * c * iy * ix
+        return f * n + f * n // (fd * fd) + n // (fd * fd), 0.0
+    if name == "bf_pool_nhwc_backward":     # read E, mask (+ gate = pooled output), write dX
+        im, c, iy, ix, fd = a[:5]
+        n = im * c * iy * ix
+        return f * n + 2 * f * n // (fd * fd) + n // (fd * fd), 0.0
+    if name in ("bf_layout_nchw_to_nhwc", "bf_layout_nhwc_to_nchw"):
+        im, c, hw = a[:3]
+        return 2 * f * im * c * hw, 0.0
     if name == "bf_pool_forward":
         im, ic, iy, ix, fd = a[:5]
         n = im * ic * iy * ix

@@ -55,6 +55,10 @@ SIGNATURES = {
     "bf_pool_forward": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "bf_pool_backward": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "bf_pool_mask_expand": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "bf_layout_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "bf_layout_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "bf_pool_nhwc_forward": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
+    "bf_pool_nhwc_backward": (_i, [_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "bf_cost_delta": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bf_cost_value": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp]),
     "bf_accuracy": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -96,6 +100,10 @@ class WorkspaceTooSmall(RuntimeError):
         self.need = need
 
 
+class Unsupported(RuntimeError):
+    """BF_ERR_ARG: the kernel family asked for cannot take this shape (callers may pick another family)."""
+
+
 def last_error():
     return (lib.bf_last_error() or b"").decode("utf-8", "replace")
 
@@ -110,4 +118,6 @@ def check(rc):
     if rc == ERR_WORKSPACE:
         m = re.search(r"need (\d+) bytes", msg)
         raise WorkspaceTooSmall(msg, int(m.group(1)) if m else 0)
+    if rc == ERR_ARG:
+        raise Unsupported("libbf_b200: " + msg)
     raise RuntimeError("libbf_b200: " + msg)

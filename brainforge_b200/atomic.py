@@ -33,25 +33,26 @@ class ActivationFunction:
 
     def forward(self, Z):
         z = as_device(Z)
-        out = DeviceArray.empty(*z.shape)
+        out = DeviceArray.empty_like(z)      # elementwise: the storage layout rides along
         self._forward_into(z, out)
         return _ret(Z, out)
 
     def _forward_into(self, z, out):
-        call(L.bf_act_forward, _lib.ACT[self.type], z.ptr, out.ptr, z.size, stream_ptr())
+        call(L.bf_act_forward, _lib.ACT[self.type], z.pptr, out.pptr, z.size, stream_ptr())
 
     def backward(self, A):
         a = as_device(A)
-        ones = DeviceArray.empty(*a.shape)
-        call(L.bf_affine, a.ptr, ones.ptr, a.size, 0.0, 1.0, stream_ptr())
-        call(L.bf_act_backward, _lib.ACT[self.type], a.ptr, ones.ptr, ones.ptr, a.size, stream_ptr())
+        ones = DeviceArray.empty_like(a)
+        call(L.bf_affine, a.pptr, ones.pptr, a.size, 0.0, 1.0, stream_ptr())
+        call(L.bf_act_backward, _lib.ACT[self.type], a.pptr, ones.pptr, ones.pptr, a.size, stream_ptr())
         return _ret(A, ones)
 
     def backward_mul(self, A, delta, out=None):
         """delta * act'(A) (layers/core.py:35,52); in place when out is None."""
         a, d = as_device(A), as_device(delta)
+        d = d.like_layout(a)
         out = d if out is None else out
-        call(L.bf_act_backward, _lib.ACT[self.type], a.ptr, d.ptr, out.ptr, d.size, stream_ptr())
+        call(L.bf_act_backward, _lib.ACT[self.type], a.pptr, d.pptr, out.pptr, d.size, stream_ptr())
         return out
 
     def __str__(self):
@@ -146,7 +147,25 @@ class ReshapeOp:
 
 # --------------------------------------------------------------------------- convolution
 class ConvolutionOp:
-    """atomic/tensor_op.py:6-75 / llatomic/lltensor_op.py:75-121.  Filter layout (nf, fc, fy, fx)."""
+    """atomic/tensor_op.py:6-75 / llatomic/lltensor_op.py:75-121.  Filter layout (nf, fc, fy, fx).
+
+    Kernel selection (BF_PREC_TF32 only; BF_PREC_FP32 always takes the SIMT implicit GEMM on NCHW):
+      * input channels-last (or NCHW with ic % 32 == 0, converted once) and nf in {32,64,128}: the TMA + tcgen05
+        channels-last kernels (`bf_conv_nhwc_*`), output channels-last;
+      * NCHW input with ic <= 4 (the first layer): `bf_conv_c3_*`, NCHW in, channels-last out;
+      * anything else: the gather-staged implicit GEMM on NCHW (`bf_conv_forward/backward`)."""
+
+    @staticmethod
+    def _route(a_nhwc, ic, iy, ix, nf, fy, fx, mode, activation):
+        if precision() != _lib.PREC["tf32"] or mode != "valid" or activation not in ("linear", "relu"):
+            return "generic"
+        if iy < fy or ix < fx:
+            return "generic"
+        if L.bf_conv_nhwc_supported(ic, nf, fy, fx) and ix <= 256:
+            return "nhwc"
+        if not a_nhwc and L.bf_conv_c3_supported(ic, iy, ix, nf, fy, fx):
+            return "c3"
+        return "generic"
 
     @staticmethod
     def forward(A, F, mode="valid", bias=None, activation="linear"):
@@ -156,9 +175,23 @@ class ConvolutionOp:
         if mode not in _lib.CONV_MODE:
             raise RuntimeError("Unsupported mode: %s" % (mode,))
         _, oy, ox = ConvolutionOp.outshape(a.shape, f.shape, mode)
-        out = DeviceArray.empty(im, nf, max(oy, 0), max(ox, 0))
         bd = as_device(bias).reshape(-1) if bias is not None else None
-        call(L.bf_conv_forward, a.ptr, f.ptr, bd.ptr if bd is not None else _NULL, out.ptr, im, ic, iy, ix, nf, fc, fy,
+        bptr = bd.ptr if bd is not None else _NULL
+        route = ConvolutionOp._route(a.nhwc, ic, iy, ix, nf, fy, fx, mode, activation) if fc == ic else "generic"
+        if route != "generic":
+            out = DeviceArray.empty_nhwc(im, nf, oy, ox)
+            try:
+                if route == "nhwc":
+                    call(L.bf_conv_nhwc_forward, a.to_nhwc().pptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
+                         _lib.ACT[activation], stream_ptr())
+                else:
+                    call(L.bf_conv_c3_forward, a.ptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
+                         _lib.ACT[activation], stream_ptr())
+                return _ret(A, out)
+            except _lib.Unsupported:
+                pass                             # no tiling for this plane: the generic kernel takes it
+        out = DeviceArray.empty(im, nf, max(oy, 0), max(ox, 0))
+        call(L.bf_conv_forward, a.to_nchw().ptr, f.ptr, bptr, out.ptr, im, ic, iy, ix, nf, fc, fy,
              fx, _lib.CONV_MODE[mode], _lib.ACT[activation], precision(), stream_ptr())
         return _ret(A, out)
 
@@ -173,19 +206,43 @@ class ConvolutionOp:
     @staticmethod
     def backward(X, E, F, dF=None, db=None, need_dX=True):
         """-> (dF, db, dX); keyword call like layers/tensor.py:83 (the two reference back-ends disagree on
-        the positional order).  db has the NumPy back-end's shape (1,nf,1,1)."""
+        the positional order).  db has the NumPy back-end's shape (1,nf,1,1).  dX comes back in
+        the storage layout of X where a channels-last kernel exists, NCHW otherwise."""
         x, e, f = as_device(X), as_device(E), as_device(F)
         im, ic, iy, ix = x.shape
         nf, fc, fy, fx = f.shape
         dF = DeviceArray.empty(nf, fc, fy, fx) if dF is None else dF
         db = DeviceArray.empty(1, nf, 1, 1) if db is None else db
-        dX = DeviceArray.empty(im, ic, iy, ix) if need_dX else None
+        route = ConvolutionOp._route(x.nhwc, ic, iy, ix, nf, fy, fx, "valid", "linear")
         # two calls (filter-gradient half, data-gradient half) so that each kernel can be timed on its own
-        call(L.bf_conv_backward, x.ptr, e.ptr, f.ptr, dF.ptr, db.ptr, _NULL, im, ic, iy, ix, nf, fy, fx, precision(),
-             stream_ptr(), tag="dF")
-        if dX is not None:
-            call(L.bf_conv_backward, x.ptr, e.ptr, f.ptr, _NULL, _NULL, dX.ptr, im, ic, iy, ix, nf, fy, fx,
-                 precision(), stream_ptr(), tag="dX")
+        done = False
+        if route != "generic":
+            try:
+                if route == "nhwc":
+                    call(L.bf_conv_nhwc_backward_filter, x.to_nhwc().pptr, e.to_nhwc().pptr, dF.ptr, db.ptr, im, ic, iy, ix,
+                         nf, fy, fx, stream_ptr(), tag="dF")
+                else:
+                    call(L.bf_conv_c3_backward_filter, x.ptr, e.to_nhwc().pptr, dF.ptr, db.ptr, im, ic, iy, ix, nf, fy, fx,
+                         stream_ptr(), tag="dF")
+                done = True
+            except _lib.Unsupported:
+                pass
+        if not done:
+            call(L.bf_conv_backward, x.to_nchw().ptr, e.to_nchw().ptr, f.ptr, dF.ptr, db.ptr, _NULL, im, ic, iy, ix, nf, fy,
+                 fx, precision(), stream_ptr(), tag="dF")
+        dX = None
+        if need_dX:
+            if route == "nhwc":
+                try:
+                    dX = DeviceArray.empty_nhwc(im, ic, iy, ix)
+                    call(L.bf_conv_nhwc_backward_data, e.to_nhwc().pptr, f.ptr, dX.pptr, im, ic, iy, ix, nf, fy, fx,
+                         stream_ptr(), tag="dX")
+                except _lib.Unsupported:
+                    dX = None
+            if dX is None:
+                dX = DeviceArray.empty(im, ic, iy, ix)
+                call(L.bf_conv_backward, x.to_nchw().ptr, e.to_nchw().ptr, f.ptr, _NULL, _NULL, dX.ptr, im, ic, iy, ix, nf,
+                     fy, fx, precision(), stream_ptr(), tag="dX")
         return _ret(X, dF, db, dX)
 
     @staticmethod
@@ -205,20 +262,30 @@ class ConvolutionOp:
 # --------------------------------------------------------------------------- max pooling
 class PoolMask:
     """The reference's `filt` (A-shaped 0/1 float array, multi-hot on ties) stored compactly: one word
-    of fdim*fdim bits per window.  `np.asarray(mask)` expands it to the reference's array."""
+    of fdim*fdim bits per window (window order follows the activation's storage layout).
+    `np.asarray(mask)` expands it to the reference's NCHW array."""
 
-    def __init__(self, words, ashape, fdim):
-        self.words, self.ashape, self.fdim = words, tuple(ashape), fdim
+    def __init__(self, words, ashape, fdim, nhwc=False):
+        self.words, self.ashape, self.fdim, self.nhwc = words, tuple(ashape), fdim, nhwc
 
     @property
     def shape(self):
         return self.ashape
 
+    @property
+    def wptr(self):
+        return ctypes.c_void_p(self.words.data_ptr())
+
     def expand(self):
         im, ic, iy, ix = self.ashape
+        if self.nhwc:   # scatter ones through the mask, then the usual layout change
+            ones = DeviceArray.empty_nhwc(im, ic, iy // self.fdim, ix // self.fdim)
+            call(L.bf_affine, ones.pptr, ones.pptr, ones.size, 0.0, 1.0, stream_ptr())
+            out = DeviceArray.empty_nhwc(im, ic, iy, ix)
+            call(L.bf_pool_nhwc_backward, ones.pptr, self.wptr, _NULL, out.pptr, im, ic, iy, ix, self.fdim, stream_ptr())
+            return out.to_nchw()
         out = DeviceArray.empty(*self.ashape)
-        call(L.bf_pool_mask_expand, ctypes.c_void_p(self.words.data_ptr()), out.ptr, im, ic, iy, ix, self.fdim,
-             stream_ptr())
+        call(L.bf_pool_mask_expand, self.wptr, out.ptr, im, ic, iy, ix, self.fdim, stream_ptr())
         return out
 
     def __array__(self, dtype=None, copy=None):
@@ -232,23 +299,32 @@ class MaxPoolOp:
         return "MaxPool"
 
     @staticmethod
-    def forward(A, fdim):
+    def forward(A, fdim, relu_in=False):
+        """-> (out, filt).  Channels-last inputs stay channels-last.  relu_in (channels-last only) applies
+        max(0, .) to A while reading it -- the fused form of `Activation("relu") -> PoolLayer`."""
         import torch
         a = as_device(A)
         im, ic, iy, ix = a.shape
         nbytes = L.bf_pool_mask_bytes(im, ic, iy, ix, fdim)
-        out = DeviceArray.empty(im, ic, iy // fdim, ix // fdim)
         words = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device="cuda")
-        call(L.bf_pool_forward, a.ptr, out.ptr, ctypes.c_void_p(words.data_ptr()), im, ic, iy, ix, fdim, stream_ptr())
-        mask = PoolMask(words, a.shape, fdim)
+        wptr = ctypes.c_void_p(words.data_ptr())
+        if a.nhwc:
+            out = DeviceArray.empty_nhwc(im, ic, iy // fdim, ix // fdim)
+            call(L.bf_pool_nhwc_forward, a.pptr, out.pptr, wptr, im, ic, iy, ix, fdim, 1 if relu_in else 0, stream_ptr())
+        else:
+            assert not relu_in
+            out = DeviceArray.empty(im, ic, iy // fdim, ix // fdim)
+            call(L.bf_pool_forward, a.ptr, out.ptr, wptr, im, ic, iy, ix, fdim, stream_ptr())
+        mask = PoolMask(words, a.shape, fdim, nhwc=a.nhwc)
         if isinstance(A, DeviceArray):
             return out, mask
         return out.numpy(), np.asarray(mask)
 
     @staticmethod
-    def backward(E, filt):
+    def backward(E, filt, gate=None):
         """E (im,ic,oy,ox), filt = the mask from forward (PoolMask, or a host 0/1 array as the reference
-        returns it).  Unlike the reference (tensor_op.py:118-119) the cached mask is not consumed."""
+        returns it).  Unlike the reference (tensor_op.py:118-119) the cached mask is not consumed.
+        gate (channels-last only): the pooled forward output; multiplies E by (gate > 0)."""
         import torch
         e = as_device(E)
         if isinstance(filt, PoolMask):
@@ -263,9 +339,14 @@ class MaxPoolOp:
             wt = torch.from_numpy(words.view(np.uint8).copy()).cuda()
             mask = PoolMask(wt, f.shape, fdim)
         im, ic, iy, ix = mask.ashape
-        dX = DeviceArray.empty(im, ic, iy, ix)
-        call(L.bf_pool_backward, e.ptr, ctypes.c_void_p(mask.words.data_ptr()), dX.ptr, im, ic, iy, ix, mask.fdim,
-             stream_ptr())
+        if mask.nhwc:
+            dX = DeviceArray.empty_nhwc(im, ic, iy, ix)
+            call(L.bf_pool_nhwc_backward, e.to_nhwc().pptr, mask.wptr, gate.pptr if gate is not None else _NULL, dX.pptr,
+                 im, ic, iy, ix, mask.fdim, stream_ptr())
+        else:
+            assert gate is None
+            dX = DeviceArray.empty(im, ic, iy, ix)
+            call(L.bf_pool_backward, e.to_nchw().ptr, mask.wptr, dX.ptr, im, ic, iy, ix, mask.fdim, stream_ptr())
         return _ret(E, dX)
 
     @staticmethod

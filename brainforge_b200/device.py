@@ -95,20 +95,38 @@ def _ptr(t):
 
 class DeviceArray:
     """A C-contiguous FP32 tensor in HBM with the handful of ndarray attributes the reference's callers
-    touch on layer state (`.shape`, `.size`, `.ndim`, `*= 0`, `np.asarray(..)`): SURVEY 7.2#7."""
+    touch on layer state (`.shape`, `.size`, `.ndim`, `*= 0`, `np.asarray(..)`): SURVEY 7.2#7.
+
+    `nhwc=True` marks a 4-D activation tensor whose LOGICAL shape is the reference's (im, c, y, x) but whose
+    storage is channels-last (im, y, x, c) -- what the TMA + tcgen05 convolutions read and write.  `.shape`,
+    `.numpy()`, `reshape`, indexing always speak the logical NCHW order (converting on the device when they
+    must); only layout-aware code (ConvolutionOp, MaxPoolOp, elementwise ops) touches the physical buffer
+    through `.pptr`.  `.ptr` refuses channels-last arrays so that a layout-unaware op cannot misread one."""
 
     __array_priority__ = 100
 
-    def __init__(self, tensor):
+    def __init__(self, tensor, nhwc=False):
         assert tensor.dtype == torch.float32 and tensor.is_cuda and tensor.is_contiguous(), \
             (tensor.dtype, tensor.device, tensor.is_contiguous())
+        assert not nhwc or tensor.dim() == 4
         self.t = tensor
+        self.nhwc = nhwc
 
     # ---- construction
     @staticmethod
     def empty(*shape):
         require_cuda()
         return DeviceArray(torch.empty(tuple(int(s) for s in shape), dtype=torch.float32, device="cuda"))
+
+    @staticmethod
+    def empty_nhwc(im, c, y, x):
+        """Channels-last storage for the logical shape (im, c, y, x)."""
+        require_cuda()
+        return DeviceArray(torch.empty((int(im), int(y), int(x), int(c)), dtype=torch.float32, device="cuda"), nhwc=True)
+
+    @staticmethod
+    def empty_like(other):
+        return DeviceArray(torch.empty_like(other.t), nhwc=other.nhwc)
 
     @staticmethod
     def zeros(*shape):
@@ -124,6 +142,7 @@ class DeviceArray:
         return out
 
     def copy_from_host(self, a):
+        assert not self.nhwc
         a = np.asarray(a)
         if tuple(a.shape) != self.shape:
             a = a.reshape(self.shape)
@@ -141,13 +160,47 @@ class DeviceArray:
             call(_lib.lib.bf_stream_sync, stream_ptr())
         return self
 
+    # ---- layout
+    def to_nchw(self):
+        """The reference's index order; a device transpose when the storage is channels-last."""
+        if not self.nhwc:
+            return self
+        im, y, x, c = self.t.shape
+        out = DeviceArray.empty(im, c, y, x)
+        if self.size:
+            call(_lib.lib.bf_layout_nhwc_to_nchw, self.pptr, out.pptr, im, c, y * x, stream_ptr())
+        return out
+
+    def to_nhwc(self):
+        if self.nhwc:
+            return self
+        im, c, y, x = self.t.shape
+        out = DeviceArray.empty_nhwc(im, c, y, x)
+        if self.size:
+            call(_lib.lib.bf_layout_nchw_to_nhwc, self.pptr, out.pptr, im, c, y * x, stream_ptr())
+        return out
+
+    def like_layout(self, other):
+        """This array in the storage layout of `other`."""
+        return self.to_nhwc() if other.nhwc else self.to_nchw()
+
     # ---- ndarray-like surface
     @property
+    def pptr(self):
+        """Pointer to the physical buffer, whatever its layout (layout-aware callers only)."""
+        return ctypes.c_void_p(self.t.data_ptr())
+
+    @property
     def ptr(self):
+        if self.nhwc:
+            raise RuntimeError("layout-unaware access to a channels-last DeviceArray (use .to_nchw() or .pptr)")
         return ctypes.c_void_p(self.t.data_ptr())
 
     @property
     def shape(self):
+        if self.nhwc:
+            im, y, x, c = self.t.shape
+            return (im, c, y, x)
         return tuple(self.t.shape)
 
     @property
@@ -168,22 +221,23 @@ class DeviceArray:
     def reshape(self, *shape):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
-        return DeviceArray(self.t.view(*[int(s) for s in shape]))
+        return DeviceArray(self.to_nchw().t.view(*[int(s) for s in shape]))
 
     def ravel(self):
         return self.reshape(-1)
 
     def __getitem__(self, idx):
-        v = self.t[idx]
+        v = self.to_nchw().t[idx]
         if not v.is_contiguous():
             raise IndexError("DeviceArray only supports slices that stay contiguous")
         return DeviceArray(v)
 
     def numpy(self, dtype=np.float64):
         """D2H copy (synchronises the stream); float64 by default like the reference's arrays."""
-        host = np.empty(self.shape, dtype=np.float32)
+        src = self.to_nchw()
+        host = np.empty(src.shape, dtype=np.float32)
         if host.size:
-            call(_lib.lib.bf_memcpy_d2h, ctypes.c_void_p(host.ctypes.data), self.ptr, host.nbytes, stream_ptr())
+            call(_lib.lib.bf_memcpy_d2h, ctypes.c_void_p(host.ctypes.data), src.ptr, host.nbytes, stream_ptr())
             call(_lib.lib.bf_stream_sync, stream_ptr())
         return host.astype(dtype, copy=False)
 
@@ -191,25 +245,25 @@ class DeviceArray:
         return self.numpy(np.float64 if dtype is None else dtype)
 
     def copy(self):
-        out = DeviceArray.empty(*self.shape)
+        out = DeviceArray.empty_like(self)
         if self.size:
-            call(_lib.lib.bf_act_forward, _lib.ACT["linear"], self.ptr, out.ptr, self.size, stream_ptr())
+            call(_lib.lib.bf_act_forward, _lib.ACT["linear"], self.pptr, out.pptr, self.size, stream_ptr())
         return out
 
     def fill_zero(self):
         if self.size:
-            call(_lib.lib.bf_affine, self.ptr, self.ptr, self.size, 0.0, 0.0, stream_ptr())
+            call(_lib.lib.bf_affine, self.pptr, self.pptr, self.size, 0.0, 0.0, stream_ptr())
         return self
 
     def __imul__(self, scalar):
         # `layer.nabla_w *= 0` (learner/backpropagation.py:72-73) and friends
         s = float(scalar)
         if self.size:
-            call(_lib.lib.bf_affine, self.ptr, self.ptr, self.size, s, 0.0, stream_ptr())
+            call(_lib.lib.bf_affine, self.pptr, self.pptr, self.size, s, 0.0, stream_ptr())
         return self
 
     def __repr__(self):
-        return "DeviceArray(shape=%s, fp32 @ cuda)" % (self.shape,)
+        return "DeviceArray(shape=%s, fp32 @ cuda%s)" % (self.shape, ", channels-last" if self.nhwc else "")
 
 
 _pinned_ranges = []

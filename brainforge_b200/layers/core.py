@@ -3,6 +3,7 @@ import numpy as np
 
 from .. import atomic
 from ..util import white
+from ..device import DeviceArray
 from .abstract_layer import LayerBase, NoParamMixin, FFBase
 
 
@@ -40,15 +41,41 @@ class Dense(FFBase):
 class Activation(NoParamMixin, LayerBase):
     """layers/core.py:45-59."""
 
+    _next_layer = None     # set by LayerStack.add: lets relu hand its pass to a following PoolLayer
+    _lazy_input = None
+
     def _fwd(self, x):
+        self._lazy_input = None
         if str(self.activation) == "linear":
-            self.output = x
+            self._output = x
+        elif (str(self.activation) == "relu" and x.nhwc and type(self._next_layer).__name__ == "PoolLayer"
+              and self._next_layer.fdim <= 2):
+            # channels-last conv block: the pooling kernel applies max(0,.) while it reads (and relu' while it
+            # scatters), so this layer moves no bytes.  `self.output` is materialised only if somebody reads it.
+            self._lazy_input, self._output = x, None
+            y = DeviceArray(x.t, nhwc=True)
+            y.pending_relu = True
+            return y
         else:
-            self.output = self.activation.forward(x)
-        return self.output
+            self._output = self.activation.forward(x)
+        return self._output
+
+    @property
+    def output(self):
+        if self._output is None and self._lazy_input is not None:
+            self._output = self.activation.forward(self._lazy_input)
+        return self._output
+
+    @output.setter
+    def output(self, value):
+        self._output = value
 
     def _bwd(self, delta):
-        return self.activation.backward_mul(self.output, delta)
+        if self._lazy_input is not None:
+            if getattr(delta, "relu_applied", False):
+                return delta
+            return self.activation.backward_mul(self.output, delta)
+        return self.activation.backward_mul(self._output, delta)
 
     @property
     def outshape(self):

@@ -24,10 +24,17 @@ class PoolLayer(NoParamMixin, LayerBase):
         self._outshape = (ic, iy // self.fdim, ix // self.fdim)
 
     def _fwd(self, x):
-        self.output, self.filter = self.op.forward(x, self.fdim)
+        # a channels-last input flagged `pending_relu` comes from an Activation("relu") layer that left its
+        # max(0,.) to this layer's kernel (layers/core.py Activation._fwd): one pass instead of two
+        self._fused_relu = bool(getattr(x, "pending_relu", False))
+        self.output, self.filter = self.op.forward(x, self.fdim, relu_in=self._fused_relu)
         return self.output
 
     def _bwd(self, delta):
+        if getattr(self, "_fused_relu", False):
+            dX = self.op.backward(delta, self.filter, gate=self.output)   # pool' and relu' in one scatter
+            dX.relu_applied = True
+            return dX
         return self.op.backward(delta, self.filter)
 
     @property
@@ -67,6 +74,10 @@ class ConvLayer(LayerBase):
                           np.zeros((1, self.nfilters, 1, 1)))
 
     def _fwd(self, x):
+        im, ic, iy, ix = x.shape
+        if not x.nhwc and self.op._route(False, ic, iy, ix, self.nfilters, self.fy, self.fx, "valid",
+                                         str(self.activation)) == "nhwc":
+            x = x.to_nhwc()          # converted once here, reused by the filter gradient
         self.inputs = x
         self.output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation))
         return self.output

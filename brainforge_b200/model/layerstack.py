@@ -44,12 +44,14 @@ class LayerStack:
 
     def add(self, layer):
         layer.connect(self)
+        self.layers[-1]._next_layer = layer
         self.layers.append(layer)
         self.architecture.append(str(layer))
         self._flat_dirty = True
 
     def pop(self):
         self.layers.pop()
+        self.layers[-1]._next_layer = None
         self.architecture.pop()
         self._flat_dirty = True
 

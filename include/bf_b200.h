@@ -141,6 +141,23 @@ BF_API int bf_pool_backward(const float* E, const uint8_t* mask, float* dX, int 
 /* Expands the compact mask to the reference's float `filt` array (A's shape, 0.0/1.0). */
 BF_API int bf_pool_mask_expand(const uint8_t* mask, float* filt, int im, int ic, int iy, int ix, int fdim, void* stream);
 
+/* ---- channels-last companions of the TMA convolution path (csrc/nhwc_ops.cu) ---- */
+/* Layout change of an activation tensor: (im, c, hw) <-> (im, hw, c).  The reference holds every tensor NCHW
+ * (atomic/tensor_op.py:9-15); the tcgen05 convolutions read and write channels-last, the host converts at the
+ * edges of a convolutional block (Flatten, user reads of layer.output). */
+BF_API int bf_layout_nchw_to_nhwc(const float* src, float* dst, int im, int c, int hw, void* stream);
+BF_API int bf_layout_nhwc_to_nchw(const float* src, float* dst, int im, int c, int hw, void* stream);
+/* MaxPoolOp.forward / backward (atomic/tensor_op.py:93-119) on channels-last tensors: A (im,iy,ix,c),
+ * out / mask / E (im,oy,ox,c); mask words as in bf_pool_forward (same bits, channels-last order); c % 4 == 0.
+ * relu_in != 0 applies max(0,.) to A while reading it: the Activation("relu") layer that precedes the pooling
+ * layer (layers/core.py:50) costs no pass of its own.  gate != NULL (the pooled OUTPUT of the forward call)
+ * multiplies E by (gate > 0): that layer's `delta * relu'(output)` (layers/core.py:52), exact because every
+ * masked element of a window equals the pooled output. */
+BF_API int bf_pool_nhwc_forward(const float* A, float* out, uint8_t* mask, int im, int c, int iy, int ix, int fdim, int relu_in,
+                         void* stream);
+BF_API int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate, float* dX, int im, int c, int iy,
+                          int ix, int fdim, void* stream);
+
 /* ---- costs / metrics: metrics/costs.py:11-37, metrics/metrics.py:13-16 ---- */
 /* delta = (out - tgt) * (w ? w[row] : 1): CostFunction.derivative + learner/backpropagation.py:19-21. */
 BF_API int bf_cost_delta(const float* out, const float* tgt, const float* w, float* delta, int m, int n, void* stream);

@@ -1,0 +1,188 @@
+"""The channels-last (NHWC) block of the tensor-core path: layout changes, channels-last max pooling (bit-exact,
+with and without the fused ReLU), the TMA + tcgen05 convolution kernels reached through the unchanged
+`atomic.ConvolutionOp` / layer API, and whole networks whose conv blocks run channels-last under the hood while
+every array a caller can see keeps the reference's NCHW index order.
+
+Bounds: layout changes and pooling bit-exact (integer / compare work); convolutions <= 5e-3 (TF32 operands);
+whole-network gradients of gated conv nets <= 3e-2."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from helpers import CFG, build_b200, build_oracle, onehot
+
+pytestmark = pytest.mark.gpu
+TOL = 5e-3
+
+
+@pytest.fixture(scope="module")
+def bf():
+    import torch
+    assert torch.cuda.is_available()
+    import brainforge_b200 as bf
+    bf.set_precision("tf32")
+    yield bf
+    bf.set_precision("fp32")
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import bf_oracle
+    return bf_oracle
+
+
+def close(a, b, tol=TOL):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    e = relerr(a, b)
+    assert e <= tol, e
+    return e
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (3, 4, 5, 7), (2, 32, 14, 14), (5, 128, 2, 2), (7, 3, 30, 30),
+                                   (2, 64, 33, 17), (0, 32, 4, 4), (70000, 4, 1, 2)])
+def test_layout_round_trip(bf, shape):
+    rs = np.random.RandomState(sum(shape))
+    A = rs.randn(*shape).astype(np.float32)
+    d = bf.DeviceArray.from_host(A)
+    n = d.to_nhwc()
+    assert n.nhwc and n.shape == A.shape
+    phys = n.t.cpu().numpy()
+    assert phys.shape == (shape[0], shape[2], shape[3], shape[1])
+    assert np.array_equal(phys, A.transpose(0, 2, 3, 1))
+    assert np.array_equal(n.numpy(np.float32), A)                   # .numpy() speaks NCHW
+    assert np.array_equal(n.to_nchw().numpy(np.float32), A)
+    flat = shape[1] * shape[2] * shape[3]
+    assert np.array_equal(n.reshape(shape[0], flat).numpy(np.float32), A.reshape(shape[0], flat))
+    with pytest.raises(RuntimeError):
+        n.ptr                                                       # layout-unaware access is refused
+
+
+@pytest.mark.parametrize("shape,fdim", [((2, 4, 4, 4), 2), ((3, 32, 28, 28), 2), ((5, 128, 4, 4), 2), ((2, 8, 6, 9), 3),
+                                        ((2, 4, 8, 8), 1), ((1, 12, 16, 8), 8), ((0, 4, 4, 4), 2)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_pool_nhwc_bit_exact(bf, O, shape, fdim, relu):
+    """MaxPoolOp on channels-last storage == the reference on NCHW, bit for bit, ties (multi-hot) included;
+    relu_in / gate reproduce Activation("relu") -> PoolLayer and its backward exactly."""
+    rs = np.random.RandomState(sum(shape) + fdim)
+    A = rs.randn(*shape).astype(np.float32)
+    A[rs.rand(*shape) < 0.3] = 0.0                                  # plenty of exact ties
+    if shape[0]:
+        A[0, :, :fdim, :fdim] = -1.0                                # an all-negative window: relu makes it a 4-way tie at 0
+    op = bf.atomic.MaxPoolOp()
+    a = bf.DeviceArray.from_host(A).to_nhwc()
+    out, mask = op.forward(a, fdim, relu_in=relu)
+    assert out.nhwc and mask.nhwc
+    Ar = np.maximum(A, 0) if relu else A
+    ro, rf = O.maxpool_forward(Ar.astype(np.float64), fdim)
+    assert np.array_equal(out.numpy(np.float32), ro.astype(np.float32))
+    assert np.array_equal(np.asarray(mask), rf)
+    E = rs.randn(*ro.shape).astype(np.float32)
+    dX = op.backward(bf.DeviceArray.from_host(E), mask, gate=out if relu else None)
+    ref = O.maxpool_backward(E.astype(np.float64), rf.copy())
+    if relu:
+        ref = ref * (Ar > 0)                                        # layers/core.py:52 with relu'(0) = 0
+    assert dX.nhwc
+    assert np.array_equal(dX.numpy(np.float32), ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 32, 14, 14, 64, 3, 3), (9, 64, 6, 6, 128, 3, 3), (3, 32, 8, 8, 32, 3, 3), (5, 128, 7, 9, 64, 2, 3),
+    (2, 3, 30, 30, 32, 3, 3), (5, 1, 28, 28, 32, 3, 3), (3, 4, 17, 40, 64, 2, 4), (130, 32, 14, 14, 64, 3, 3),
+])
+def test_conv_routes_to_tma_kernels(bf, O, shape):
+    """atomic.ConvolutionOp (unchanged signature) picks the TMA-fed channels-last kernels when it can; the
+    caller sees NCHW results."""
+    im, ic, iy, ix, nf, fy, fx = shape
+    rs = np.random.RandomState(sum(shape))
+    A, F, bias = rs.randn(im, ic, iy, ix), rs.randn(nf, ic, fy, fx) * 0.3, rs.randn(nf)
+    op = bf.atomic.ConvolutionOp()
+    yv = O.conv_forward(A, F, "valid")
+    close(op.forward(A, F, "valid"), yv)
+    assert bf._lib.lib.bf_last_path() == 2
+    close(op.forward(A, F, "valid", bias=bias, activation="relu"), np.maximum(yv, 0) + bias[None, :, None, None])
+    E = rs.randn(*yv.shape)
+    dF, db, dX = op.backward(X=A, E=E, F=F)
+    rF, rb, rX = O.conv_backward(A, E, F)
+    close(dF, rF); close(db.ravel(), rb.ravel()); close(dX, rX)
+    # device-resident: channels-last in, channels-last out
+    if ic % 32 == 0:
+        a = bf.DeviceArray.from_host(A).to_nhwc()
+        y = op.forward(a, bf.DeviceArray.from_host(F), "valid")
+        assert y.nhwc
+        close(y, yv)
+        dFd, dbd, dXd = op.backward(X=a, E=bf.DeviceArray.from_host(E), F=bf.DeviceArray.from_host(F))
+        assert dXd.nhwc
+        close(dFd, rF); close(dXd, rX)
+
+
+def _cfg3(bf, batch, **kw):
+    ishape, spec, cost, optimizer = CFG["cfg3"]
+    return build_b200(ishape, spec, cost, optimizer, seed=1234, **kw), build_oracle(ishape, spec, cost, optimizer, seed=1234)
+
+
+def test_cfg3_runs_channels_last_and_matches(bf, O):
+    from brainforge_b200.layers import ConvLayer, PoolLayer, Activation
+    net, ora = _cfg3(bf, 37)
+    rs = np.random.RandomState(5)
+    X, Y = rs.randn(37, 3, 30, 30), onehot(rs, 37, 10)
+    a = net.learn_batch(X, Y, metrics=["acc"], update=False)
+    b = ora.learn_batch(X, Y, update=False, metrics=["acc"])
+    close(a["cost"], b["cost"])
+    close(net.get_gradients(), ora.get_gradients(), 3e-2)
+    # the conv blocks really ran channels-last, with the ReLU folded into the pooling kernels
+    convs = [l for l in net.layers.layers if isinstance(l, ConvLayer)]
+    pools = [l for l in net.layers.layers if isinstance(l, PoolLayer)]
+    acts = [l for l in net.layers.layers[1:] if isinstance(l, Activation)]
+    assert all(c.output.nhwc for c in convs) and all(p.output.nhwc and p._fused_relu for p in pools)
+    assert not convs[0].inputs.nhwc and convs[1].inputs.nhwc
+    # every array a caller can read keeps the reference's NCHW order and values (lazy ReLU outputs included)
+    for layer, ol in zip(net.layers.layers[1:], ora.L):
+        close(np.asarray(layer.output), ol["output"], 1e-2)
+    for act, conv in zip(acts, convs):
+        assert np.array_equal(np.asarray(act.output), np.maximum(np.asarray(conv.output), 0))
+    for p, act in zip(pools, acts):
+        ro, rf = O.maxpool_forward(np.asarray(act.output), 2)
+        assert np.array_equal(np.asarray(p.output), ro)              # bit-exact given the same inputs
+        assert np.array_equal(np.asarray(p.filter), rf)
+    # input delta through backpropagate() (first layer's dX: generic kernel on NCHW)
+    preds = net.predict(X)
+    d = net.backpropagate(net.cost.derivative(preds, Y))
+    ora.zero_gradients()
+    dref = ora.backpropagate(O.cost_derivative(ora.feedforward(X), Y))
+    close(d, dref, 3e-2)
+    assert d.shape == X.shape
+
+
+def test_cfg3_trajectory_and_graph(bf):
+    net, ora = _cfg3(bf, 64)
+    netg, _ = _cfg3(bf, 64, use_graph=True)
+    rs = np.random.RandomState(6)
+    X, Y = rs.randn(64, 3, 30, 30), onehot(rs, 64, 10)
+    for step in range(4):
+        a, g, b = net.learn_batch(X, Y), netg.learn_batch(X, Y), ora.learn_batch(X, Y)
+        close(a["cost"], b["cost"], 2e-2)
+        assert a["cost"] == g["cost"]                                # graph replay == eager, bit for bit
+    close(net.layers.get_weights(), ora.get_weights(), 2e-2)
+    assert np.array_equal(net.layers.get_weights(), netg.layers.get_weights())
+
+
+def test_cfg3_full_size_properties(bf):
+    """Size-independent properties at BASELINE's full batch (4096): the gradient of the batch is the sum of the
+    gradients of its halves, cost additivity, every pooling window has at least one mask hit."""
+    from brainforge_b200.layers import PoolLayer
+    net, _ = _cfg3(bf, 4096)
+    rs = np.random.RandomState(7)
+    X = rs.randn(4096, 3, 30, 30).astype(np.float32)
+    Y = onehot(rs, 4096, 10).astype(np.float32)
+    full = net.learn_batch(X, Y, update=False)
+    g = net.get_gradients(); net.zero_gradients()
+    pool = [l for l in net.layers.layers if isinstance(l, PoolLayer)][-1]
+    words = pool.filter.words.cpu().numpy()
+    assert words.min() >= 1 and words.max() <= 15
+    h1 = net.learn_batch(X[:2048], Y[:2048], update=False)
+    g1 = net.get_gradients(); net.zero_gradients()
+    h2 = net.learn_batch(X[2048:], Y[2048:], update=False)
+    g2 = net.get_gradients(); net.zero_gradients()
+    close(g, g1 + g2, 1e-4)
+    assert abs(full["cost"] * 4096 - (h1["cost"] + h2["cost"]) * 2048) <= 1e-4 * abs(full["cost"] * 4096)
