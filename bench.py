@@ -544,7 +544,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--precision", default=os.environ.get("BF_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("BF_PRECISION", "tf32"), choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 tensor-core contractions (default, north_star); fp32: SIMT FMA path (<=1e-5 parity)")
     ap.add_argument("--batch", type=int, default=0, help="override the global batch / population")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -155,8 +155,12 @@ class ConvolutionOp:
       * NCHW input with ic <= 4 (the first layer): `bf_conv_c3_*`, NCHW in, channels-last out;
       * anything else: the gather-staged implicit GEMM on NCHW (`bf_conv_forward/backward`)."""
 
+    channels_last = True      # class-wide switch: False keeps every convolution on the NCHW gather kernels
+
     @staticmethod
     def _route(a_nhwc, ic, iy, ix, nf, fy, fx, mode, activation):
+        if not ConvolutionOp.channels_last:
+            return "generic"
         if precision() != _lib.PREC["tf32"] or mode != "valid" or activation not in ("linear", "relu"):
             return "generic"
         if iy < fy or ix < fx:
@@ -182,7 +186,8 @@ class ConvolutionOp:
             out = DeviceArray.empty_nhwc(im, nf, oy, ox)
             try:
                 if route == "nhwc":
-                    call(L.bf_conv_nhwc_forward, a.to_nhwc().pptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
+                    an = a.to_nhwc()      # (a named local: a temporary's block could be reused before the launch)
+                    call(L.bf_conv_nhwc_forward, an.pptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
                          _lib.ACT[activation], stream_ptr())
                 else:
                     call(L.bf_conv_c3_forward, a.ptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
@@ -191,7 +196,8 @@ class ConvolutionOp:
             except _lib.Unsupported:
                 pass                             # no tiling for this plane: the generic kernel takes it
         out = DeviceArray.empty(im, nf, max(oy, 0), max(ox, 0))
-        call(L.bf_conv_forward, a.to_nchw().ptr, f.ptr, bptr, out.ptr, im, ic, iy, ix, nf, fc, fy,
+        ac = a.to_nchw()
+        call(L.bf_conv_forward, ac.ptr, f.ptr, bptr, out.ptr, im, ic, iy, ix, nf, fc, fy,
              fx, _lib.CONV_MODE[mode], _lib.ACT[activation], precision(), stream_ptr())
         return _ret(A, out)
 
@@ -214,34 +220,41 @@ class ConvolutionOp:
         dF = DeviceArray.empty(nf, fc, fy, fx) if dF is None else dF
         db = DeviceArray.empty(1, nf, 1, 1) if db is None else db
         route = ConvolutionOp._route(x.nhwc, ic, iy, ix, nf, fy, fx, "valid", "linear")
-        # two calls (filter-gradient half, data-gradient half) so that each kernel can be timed on its own
+        # two calls (filter-gradient half, data-gradient half) so that each kernel can be timed on its own.
+        # Layout conversions are bound to locals: a temporary's block could be recycled before the launch.
+        en = e.to_nhwc() if route != "generic" else None
         done = False
         if route != "generic":
             try:
                 if route == "nhwc":
-                    call(L.bf_conv_nhwc_backward_filter, x.to_nhwc().pptr, e.to_nhwc().pptr, dF.ptr, db.ptr, im, ic, iy, ix,
+                    xn = x.to_nhwc()
+                    call(L.bf_conv_nhwc_backward_filter, xn.pptr, en.pptr, dF.ptr, db.ptr, im, ic, iy, ix,
                          nf, fy, fx, stream_ptr(), tag="dF")
                 else:
-                    call(L.bf_conv_c3_backward_filter, x.ptr, e.to_nhwc().pptr, dF.ptr, db.ptr, im, ic, iy, ix, nf, fy, fx,
+                    call(L.bf_conv_c3_backward_filter, x.ptr, en.pptr, dF.ptr, db.ptr, im, ic, iy, ix, nf, fy, fx,
                          stream_ptr(), tag="dF")
                 done = True
             except _lib.Unsupported:
                 pass
+        xc = ec = None
         if not done:
-            call(L.bf_conv_backward, x.to_nchw().ptr, e.to_nchw().ptr, f.ptr, dF.ptr, db.ptr, _NULL, im, ic, iy, ix, nf, fy,
+            xc, ec = x.to_nchw(), e.to_nchw()
+            call(L.bf_conv_backward, xc.ptr, ec.ptr, f.ptr, dF.ptr, db.ptr, _NULL, im, ic, iy, ix, nf, fy,
                  fx, precision(), stream_ptr(), tag="dF")
         dX = None
         if need_dX:
             if route == "nhwc":
                 try:
                     dX = DeviceArray.empty_nhwc(im, ic, iy, ix)
-                    call(L.bf_conv_nhwc_backward_data, e.to_nhwc().pptr, f.ptr, dX.pptr, im, ic, iy, ix, nf, fy, fx,
+                    call(L.bf_conv_nhwc_backward_data, en.pptr, f.ptr, dX.pptr, im, ic, iy, ix, nf, fy, fx,
                          stream_ptr(), tag="dX")
                 except _lib.Unsupported:
                     dX = None
             if dX is None:
                 dX = DeviceArray.empty(im, ic, iy, ix)
-                call(L.bf_conv_backward, x.to_nchw().ptr, e.to_nchw().ptr, f.ptr, _NULL, _NULL, dX.ptr, im, ic, iy, ix, nf,
+                xc = x.to_nchw() if xc is None else xc
+                ec = e.to_nchw() if ec is None else ec
+                call(L.bf_conv_backward, xc.ptr, ec.ptr, f.ptr, _NULL, _NULL, dX.ptr, im, ic, iy, ix, nf,
                      fy, fx, precision(), stream_ptr(), tag="dX")
         return _ret(X, dF, db, dX)
 
@@ -341,12 +354,14 @@ class MaxPoolOp:
         im, ic, iy, ix = mask.ashape
         if mask.nhwc:
             dX = DeviceArray.empty_nhwc(im, ic, iy, ix)
-            call(L.bf_pool_nhwc_backward, e.to_nhwc().pptr, mask.wptr, gate.pptr if gate is not None else _NULL, dX.pptr,
+            en = e.to_nhwc()
+            call(L.bf_pool_nhwc_backward, en.pptr, mask.wptr, gate.pptr if gate is not None else _NULL, dX.pptr,
                  im, ic, iy, ix, mask.fdim, stream_ptr())
         else:
             assert gate is None
             dX = DeviceArray.empty(im, ic, iy, ix)
-            call(L.bf_pool_backward, e.to_nchw().ptr, mask.wptr, dX.ptr, im, ic, iy, ix, mask.fdim, stream_ptr())
+            ec = e.to_nchw()
+            call(L.bf_pool_backward, ec.ptr, mask.wptr, dX.ptr, im, ic, iy, ix, mask.fdim, stream_ptr())
         return _ret(E, dX)
 
     @staticmethod

@@ -212,6 +212,7 @@ int bf_pool_nhwc_forward(const float* A, float* out, uint8_t* mask, int im, int 
                          void* stream) {
   int rc = pool_nhwc_check("bf_pool_nhwc_forward", im, c, iy, ix, fdim);
   if (rc) return rc;
+  if (im == 0) return BF_OK;
   BF_REQUIRE(A && out && mask, BF_ERR_ARG, "bf_pool_nhwc_forward: null pointer");
   const int oy = iy / fdim, ox = ix / fdim;
   cudaStream_t s = as_stream(stream);
@@ -239,6 +240,7 @@ int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate
                           int fdim, void* stream) {
   int rc = pool_nhwc_check("bf_pool_nhwc_backward", im, c, iy, ix, fdim);
   if (rc) return rc;
+  if (im == 0) return BF_OK;
   BF_REQUIRE(E && dX && mask, BF_ERR_ARG, "bf_pool_nhwc_backward: null pointer");
   const int oy = iy / fdim, ox = ix / fdim;
   cudaStream_t s = as_stream(stream);

@@ -138,7 +138,8 @@ def test_cfg3_runs_channels_last_and_matches(bf, O):
     assert not convs[0].inputs.nhwc and convs[1].inputs.nhwc
     # every array a caller can read keeps the reference's NCHW order and values (lazy ReLU outputs included)
     for layer, ol in zip(net.layers.layers[1:], ora.L):
-        close(np.asarray(layer.output), ol["output"], 1e-2)
+        if layer.output is not None:                                 # Reshape/Flatten keep none (layers/core.py:81-82)
+            close(np.asarray(layer.output), ol["output"], 1e-2)
     for act, conv in zip(acts, convs):
         assert np.array_equal(np.asarray(act.output), np.maximum(np.asarray(conv.output), 0))
     for p, act in zip(pools, acts):
@@ -150,8 +151,21 @@ def test_cfg3_runs_channels_last_and_matches(bf, O):
     d = net.backpropagate(net.cost.derivative(preds, Y))
     ora.zero_gradients()
     dref = ora.backpropagate(O.cost_derivative(ora.feedforward(X), Y))
-    close(d, dref, 3e-2)
     assert d.shape == X.shape
+    # the input delta crosses all three ReLU/max-pool gates: a TF32-sized perturbation flips a gate in a few
+    # samples (discontinuous), every other sample agrees to operand-rounding accuracy
+    close(d, dref, 1e-1)
+    # against the same TF32 arithmetic on the NCHW gather kernels (same operand rounding, different summation
+    # order) gate flips are rare: the typical sample agrees to accumulation-order accuracy
+    bf.atomic.ConvolutionOp.channels_last = False
+    try:
+        net2, _ = _cfg3(bf, 37)
+        d2 = net2.backpropagate(net2.cost.derivative(net2.predict(X), Y))
+        assert not any(l.output.nhwc for l in net2.layers.layers[1:] if l.output is not None)
+    finally:
+        bf.atomic.ConvolutionOp.channels_last = True
+    per_sample = np.array([relerr(d[i], d2[i]) for i in range(len(X))])
+    assert np.median(per_sample) <= 1e-4, per_sample
 
 
 def test_cfg3_trajectory_and_graph(bf):
