@@ -174,155 +174,239 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
 }
 
 // --------------------------------------------------------------------------------------------- dF + db
-constexpr int C3DF_THREADS = 224;     // warp 0 TMA, warps 1-2 MMA (even / odd chunks, one accumulator each), warps 3-6 epilogue
+// Work unit = one BAND of RB output rows of one image (px = RB*ox pixels, cut into k-blocks of 32 pixels).
+//   warp 0      producer: per band one tensor-TMA box of E ([px][32 filters] per 32-filter group, MN-major
+//               SWIZZLE_128B/32B-atom operand exactly as it lies in HBM) + one 1-D bulk copy per input plane of the
+//               (RB+fy-1) raw NCHW rows the band's patches touch (16-byte aligned start, `lead` floats of slack);
+//   warps 4-7   builders: turn the raw rows into the K-major SWIZZLE_128B patch tile of one k-block
+//               A[r = (c,ky,kx)][k = pixel] = X[c][y+ky][x+kx]  (row Mrows = 1 -> db; padding pixels = 0),
+//               shared -> shared, TF32-rounded, conflict-free; a ring of `na` tiles decouples them from the MMAs;
+//   warps 1-2   MMA issuers: even / odd k-blocks, one TMEM accumulator each (two issuing threads reach twice the
+//               issue rate of one for these small N), four K=8 tcgen05.mma per k-block;
+//   warps 4-7   final epilogue: sum of the two accumulators -> per-CTA partial; a small kernel adds the partials.
+constexpr int C3DF_THREADS = 384;      // warp 0 TMA, 1-2 MMA, 3 TMEM, 4-11 patch-tile builders (4-7 also the epilogue)
+constexpr int C3DF_BUILDERS = 8;
+constexpr int C3DF_A_SLOT = 32 * 128;     // 32 patch rows per tile; the M=128 descriptor runs on into the next tiles (rows >= 32 of D are never read)
+constexpr int C3DF_A_TAIL = 96 * 128;     // so that the last tile's descriptor stays inside the ring
 struct C3DfParams {
-  int nimg, ic, iy, ix, oy, ox, fy, fx, nseg, nchunks, Mrows, ns, nf, KB;
-  long long* prof;
+  int nimg, ic, iy, ix, oy, ox, fy, fx, nf;
+  int RB, nbands, nunits, px_band, nkb, Mrows, ns, na;
+  int e_stage_bytes, x_plane_f, x_stage_bytes;
+  long long x_total_f;
 };
-#define C3_T(var) long long var = p.prof ? clock64() : 0
-#define C3_ACC(slot, t0) do { if (p.prof && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.prof[slot] += clock64() - (t0); } while (0)
 
-// TMA can only start a box on a 16-byte boundary of the innermost dimension (an unaligned coordinate traps), but a
-// horizontal filter tap kx shifts the pixels by 4*kx bytes.  So the (small) input is re-laid once per call as fx
-// copies, copy kx shifted left by kx pixels, rows padded to a multiple of 4 floats:
-//   Xs[kx][plane row r][x] = X[r][x + kx]   (0 past the end of the row)
-__global__ void shift_rows_kernel(const float* __restrict__ X, float* __restrict__ Xs, long rows, int ix, int pitch, int fx) {
-  const long per = rows * pitch, total = per * fx;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    const int kx = (int)(i / per);
-    const long j = i - (long)kx * per;
-    const long r = j / pitch;
-    const int x = (int)(j - r * pitch) + kx;
-    Xs[i] = x < ix ? X[r * ix + x] : 0.f;
-  }
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// One chunk = 32 output pixels of one output row (b, y).  Patch tile (K-major SWIZZLE_128B, 128 B per row):
-// row kx*KB + c*fy + ky = X[b][c][y+ky][x0+kx .. +31] (KB = ic*fy) -- all fx*ic*fy rows are ONE 5-D TMA box
-// (32 x, fy rows, ic planes, 1 image, fx shifted copies); row Mrows (= fx*KB) is constant 1 (-> db).
 template <int MH>
 __global__ void __launch_bounds__(C3DF_THREADS, 1)
-conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__ CUtensorMap mapX, C3DfParams p,
-                  float* __restrict__ partial) {
+conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restrict__ X, C3DfParams p, float* __restrict__ partial) {
   extern __shared__ int dyn_smem[];
-  __shared__ __align__(8) uint64_t full[8], empty[8], done;
+  __shared__ __align__(8) uint64_t full[4], empty[4], a_full[16], a_empty[16], done;
   __shared__ uint32_t tmem_slot;
+  __shared__ int roff[128];
+  constexpr int NF = MH * 32;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
-  constexpr uint32_t A_SLOT = 128 * 128, B_SLOT = MH * 4096;
-  const uint32_t b_base = base + (uint32_t)p.ns * A_SLOT;
-  constexpr int NF = MH * 32;
+  const uint32_t e_base = base;
+  const uint32_t a_base = e_base + (uint32_t)p.ns * p.e_stage_bytes;
+  const uint32_t x_base = a_base + (uint32_t)p.na * C3DF_A_SLOT + C3DF_A_TAIL;
 
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(256));
+  if (warp == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * NF));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2 + C3DF_BUILDERS); }
+    for (int i = 0; i < 16; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     mbar_init(&done, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // patch tiles: rows >= Mrows stay 0 except row Mrows = all ones (-> db); TMA only ever writes rows < Mrows
-  for (uint32_t o = tid * 16u; o < (uint32_t)p.ns * A_SLOT; o += C3DF_THREADS * 16u) {
-    const uint32_t row = (o % A_SLOT) / 128u;
-    const uint32_t v = (row == (uint32_t)p.Mrows) ? 0x3f800000u : 0u;
-    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(v) : "memory");
+  // E stages and patch tiles start as zeros: rows the loads / builders never write must read as finite zeros
+  for (uint32_t o = tid * 16u; o < x_base - base; o += C3DF_THREADS * 16u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
+  // row r = (c*fy + ky)*fx + kx (the reference's filter order) -> offset of its first element inside the raw stage
+  for (int r = tid; r < 128; r += C3DF_THREADS) {
+    int v = 0;
+    if (r < p.Mrows) {
+      const int kx = r % p.fx, t = r / p.fx, ky = t % p.fy, c = t / p.fy;
+      v = (c << 24) | (c * p.x_plane_f + ky * p.ix + kx);
+    }
+    roff[r] = v;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
-  int my_chunks = 0;
-  for (int c = blockIdx.x; c < p.nchunks; c += gridDim.x) ++my_chunks;
+  int my_units = 0;
+  for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) ++my_units;
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ producer
     const bool leader = elect_one_sync();
-    const uint32_t kx_bytes = (uint32_t)p.KB * 128u, box_bytes = (uint32_t)(p.ic * p.fy) * 128u;
     int it = 0;
-    for (int c = blockIdx.x; c < p.nchunks; c += gridDim.x, ++it) {
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
       const int s = it % p.ns, u = it / p.ns;
-      const int seg = c % p.nseg, row = c / p.nseg;
-      const int y = row % p.oy, b = row / p.oy;
-      { C3_T(t0); if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1)); C3_ACC(0, t0); }
+      const int b = unit / p.nbands, band = unit - b * p.nbands, y0 = band * p.RB;
+      if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
       if (leader) {
-        mbar_expect_tx(&full[s], B_SLOT + (uint32_t)p.fx * box_bytes);
+        int rows_in = p.RB + p.fy - 1;
+        if (rows_in > p.iy - y0) rows_in = p.iy - y0;
+        uint32_t bytes = (uint32_t)MH * (uint32_t)p.px_band * 128u;
+        uint32_t xb[4];
+        long long xo[4];
 #pragma unroll
-        for (int h = 0; h < MH; ++h) tma_load_4d(b_base + s * B_SLOT + h * 4096, &mapE, &full[s], h * 32, seg * 32, y, b);
-        tma_load_5d(base + s * A_SLOT, &mapX, &full[s], seg * 32, y, 0, b, 0);
+        for (int c = 0; c < 4; ++c) {
+          xb[c] = 0; xo[c] = 0;
+          if (c < p.ic) {
+            const long long off = ((long long)(b * p.ic + c) * p.iy + y0) * p.ix;
+            const long long st = off & ~3ll;
+            long long nfl = ((off - st) + (long long)rows_in * p.ix + 3) & ~3ll;
+            if (st + nfl > p.x_total_f) nfl = p.x_total_f - st;
+            xo[c] = st; xb[c] = (uint32_t)nfl * 4u;
+            bytes += xb[c];
+          }
+        }
+        mbar_expect_tx(&full[s], bytes);
+        const int px0 = (b * p.oy + y0) * p.ox;
+#pragma unroll
+        for (int h = 0; h < MH; ++h)
+          tma_load_2d(e_base + s * p.e_stage_bytes + h * p.nkb * 4096, &mapE, &full[s], h * 32, px0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < p.ic) bulk_load_1d(x_base + s * p.x_stage_bytes + c * p.x_plane_f * 4, X + xo[c], xb[c], &full[s]);
       }
     }
   } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers (k-block parity)
     const bool leader = elect_one_sync();
     const int wsel = warp - 1;
     constexpr uint32_t idesc = idesc_tf32(128, NF, false, true);
-    int mine = 0;
-    C3_T(tm);
-    for (int it = wsel; it < my_chunks; it += 2, ++mine) {
+    int g = 0, mine = 0;
+    for (int it = 0; it < my_units; ++it) {
       const int s = it % p.ns, u = it / p.ns;
-      { C3_T(t0); mbar_wait(&full[s], (uint32_t)(u & 1)); if (wsel == 0) C3_ACC(1, t0); }
-      tc_fence_after();
-      if (leader) {
-        const uint64_t ad = desc_k_sw128(base + s * A_SLOT);
-        const uint64_t bd = desc_mn_sw128_32b(b_base + s * B_SLOT, 4096u, 512u);
+      mbar_wait(&full[s], (uint32_t)(u & 1));
+      bool any = false;
+      for (int j = 0; j < p.nkb; ++j, ++g) {
+        if ((g & 1) != wsel) continue;
+        const int slot = g % p.na, ua = g / p.na;
+        mbar_wait(&a_full[slot], (uint32_t)(ua & 1));
+        tc_fence_after();
+        if (leader) {
+          const uint64_t ad = desc_k_sw128(a_base + slot * C3DF_A_SLOT);
+          const uint64_t bd = desc_mn_sw128_32b(e_base + s * p.e_stage_bytes + j * 4096, (uint32_t)p.nkb * 4096u, 512u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_tf32(tmem + wsel * NF, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 64), idesc, (mine > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&empty[s]);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32(tmem + wsel * NF, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 64), idesc, (mine > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&a_empty[slot]);
+        }
+        ++mine;
+        any = true;
       }
+      if (leader) { if (any) umma_commit(&empty[s]); else mbar_arrive(&empty[s]); }
     }
     if (leader) umma_commit(&done);
-    if (wsel == 0) C3_ACC(2, tm);
-  } else if (warp >= 3) {
-    // ---- final epilogue: partial[cta][m][NF] = accumulator of the even chunks + accumulator of the odd chunks
-    const int quad = warp & 3;
-    const int m = quad * 32 + lane;
-    mbar_wait(&done, 0);
-    tc_fence_after();
-    float* dst = partial + ((size_t)blockIdx.x * 128 + m) * NF;
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ patch-tile builders
+    // builder warp bw owns the k-blocks g = bw (mod 8): eight tiles are under construction at any time.  Lane =
+    // pixel of the k-block.  Per patch row: one add, one shared load, TF32 rounding, one select, one conflict-free
+    // swizzled store; every per-row offset is band-invariant and lives in registers (planes are multiples of
+    // 4 floats, host-checked, so the 16-byte alignment slack `lead` of the raw rows is the same for every plane).
+    const int bw = warp - 4;
+    const char* xs_all = reinterpret_cast<const char*>(dyn_smem) + (x_base - smem_u32(dyn_smem));
+    char* a_tiles = reinterpret_cast<char*>(dyn_smem) + (a_base - smem_u32(dyn_smem));
+    int rowoff[31];                      // byte offset of row r's first element inside a raw stage
 #pragma unroll
-    for (int c0 = 0; c0 < NF; c0 += 16) {
-      uint32_t v0[16], v1[16];
-      float o[16];
+    for (int r = 0; r < 31; ++r) rowoff[r] = r < p.Mrows ? (roff[r] & 0xffffff) * 4 : 0;
+    const int sw = lane >> 2, l3 = (lane & 3) * 4;
+    int swz[8];                          // byte offset of this lane's 16-byte chunk in a tile row with (r & 7) = i
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = 0.f;
-      if (my_chunks > 0) {
-        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + c0, v0);
-        tmem_ld_wait();
+    for (int i = 0; i < 8; ++i) swz[i] = ((sw ^ i) << 4) + l3;
+    const int ones_off = p.Mrows * 128 + (((sw ^ (p.Mrows & 7)) << 4) + l3);
+    int g = 0, it = 0;
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
+      const int s = it % p.ns, u = it / p.ns;
+      const int band = unit % p.nbands, y0 = band * p.RB;
+      int rb = p.RB;
+      if (rb > p.oy - y0) rb = p.oy - y0;
+      const int npx = rb * p.ox;
+      const int lead = (y0 * p.ix) & 3;
+      const char* xs = xs_all + s * p.x_stage_bytes;
+      bool waited = false;
+      for (int j = 0; j < p.nkb; ++j, ++g) {
+        if ((g & (C3DF_BUILDERS - 1)) != bw) continue;
+        if (!waited) { mbar_wait(&full[s], (uint32_t)(u & 1)); waited = true; }
+        const int slot = g % p.na, ua = g / p.na;
+        const int px = j * 32 + lane;
+        const bool valid = px < npx;
+        const int yy = px / p.ox, xx = px - yy * p.ox;
+        const char* src = xs + (valid ? (lead + yy * p.ix + xx) * 4 : 0);
+        float v[31];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v0[j]);
+        for (int r = 0; r < 31; ++r)
+          if (r < p.Mrows) v[r] = *reinterpret_cast<const float*>(src + rowoff[r]);
+        if (ua > 0) mbar_wait(&a_empty[slot], (uint32_t)((ua - 1) & 1));
+        char* tile = a_tiles + slot * C3DF_A_SLOT;
+#pragma unroll
+        for (int r = 0; r < 31; ++r)
+          if (r < p.Mrows) *reinterpret_cast<uint32_t*>(tile + r * 128 + swz[r & 7]) = valid ? to_tf32(v[r]) : 0u;
+        *reinterpret_cast<uint32_t*>(tile + ones_off) = valid ? 0x3f800000u : 0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[slot]);
       }
-      if (my_chunks > 1) {
-        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + NF + c0, v1);
-        tmem_ld_wait();
+      if (!waited) mbar_wait(&full[s], (uint32_t)(u & 1));   // keep this warp's phase bookkeeping in step
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);      // this warp no longer reads the band's raw rows
+    }
+    // ---- final epilogue: partial[cta][r][NF] = accumulator of the even k-blocks + accumulator of the odd ones
+    const int m = bw * 32 + lane;
+    if (bw < 4 && bw * 32 <= p.Mrows) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+      float* dst = partial + ((size_t)blockIdx.x * (p.Mrows + 1) + m) * NF;
+      const int total_kb = my_units * p.nkb;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(v1[j]);
-      }
-      if (m <= p.Mrows) {
+      for (int c0 = 0; c0 < NF; c0 += 16) {
+        uint32_t v0[16], v1[16];
+        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        for (int j = 0; j < 16; ++j) o[j] = 0.f;
+        if (total_kb > 0) {
+          tmem_ld16(tmem + ((uint32_t)(bw * 32) << 16) + c0, v0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v0[j]);
+        }
+        if (total_kb > 1) {
+          tmem_ld16(tmem + ((uint32_t)(bw * 32) << 16) + NF + c0, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(v1[j]);
+        }
+        if (m <= p.Mrows) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NF));
 }
 
-// dF[f][c][ky][kx] = sum_cta partial[cta][kx*KB + c*fy + ky][f];  db[f] = sum_cta partial[cta][fx*KB][f]
+// dF[f][r] = sum_cta partial[cta][r][f] (r = (c,ky,kx) in the reference's order);  db[f] = sum_cta partial[cta][Mrows][f]
 __global__ void conv_c3_df_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
-                                         int nctas, int ic, int fy, int fx, int nf, int KB) {
-  const int Mrows = ic * fy * fx, total = nf * (Mrows + 1);
+                                         int nctas, int Mrows, int nf) {
+  const int total = nf * (Mrows + 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int f = i / (Mrows + 1), r = i - f * (Mrows + 1);   // r = (c, ky, kx) in the reference's order, or Mrows
-    int m = fx * KB;
-    if (r < Mrows) {
-      const int kx = r % fx, t = r / fx, ky = t % fy, c = t / fy;
-      m = kx * KB + c * fy + ky;
-    }
+    const int r = i / nf, f = i - r * nf;        // consecutive threads -> consecutive filters: coalesced reads
     float s = 0.f;
-    for (int z = 0; z < nctas; ++z) s += partial[((size_t)z * 128 + m) * nf + f];
+    for (int z = 0; z < nctas; ++z) s += partial[((size_t)z * (Mrows + 1) + r) * nf + f];
     if (r == Mrows) { if (db) db[f] = s; }
     else dF[(size_t)f * Mrows + r] = s;
   }
@@ -397,70 +481,61 @@ int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float*
                                int fy, int fx, void* stream) {
   BF_REQUIRE(conv_c3_supported(ic, iy, ix, nf, fy, fx), BF_ERR_ARG, "bf_conv_c3_backward_filter: unsupported shape");
   cudaStream_t s = as_stream(stream);
-  const int oy = iy - fy + 1, ox = ix - fx + 1, KB = ic * fy, Mrows = fx * KB;   // Mrows: index of the ones row
+  const int oy = iy - fy + 1, ox = ix - fx + 1, Mrows = ic * fy * fx;
   if (im <= 0) {
     BF_CUDA(cudaMemsetAsync(dF, 0, (size_t)nf * ic * fy * fx * 4, s));
     if (db) BF_CUDA(cudaMemsetAsync(db, 0, (size_t)nf * 4, s));
     return BF_OK;
   }
-  C3DfParams p;
-  p.nimg = im; p.ic = ic; p.iy = iy; p.ix = ix; p.oy = oy; p.ox = ox; p.fy = fy; p.fx = fx; p.nseg = (ox + 31) / 32;
-  BF_REQUIRE((long)im * oy * p.nseg < 2147483647L, BF_ERR_ARG, "bf_conv_c3_backward_filter: too many rows");
-  p.nchunks = im * oy * p.nseg; p.Mrows = Mrows; p.nf = nf; p.KB = KB; p.prof = nullptr;
-  static long long* d_prof = nullptr;
-  const bool prof = getenv("BF_PROF_IGEMM") != nullptr;
-  if (prof) {
-    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
-    cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), s);
-    p.prof = d_prof;
-  }
   const int MH = nf / 32;
-  p.ns = 8;
-  while (p.ns > 2 && 1024 + (size_t)p.ns * (128 * 128 + MH * 4096) > 200 * 1024) --p.ns;
-  const size_t smem = 1024 + (size_t)p.ns * (128 * 128 + MH * 4096);
-  const int ctas = p.nchunks < num_sms() ? p.nchunks : num_sms();
-  // workspace: [split-K partials | fx shifted, row-padded copies of X]
-  const int pitch = (ix + 3) / 4 * 4;
-  const long xrows = (long)im * ic * iy;
-  const size_t part_bytes = c3_al256((size_t)ctas * 128 * nf * 4);
-  const size_t xs_bytes = c3_al256((size_t)fx * xrows * pitch * 4);
+  const int cap_px = nf == 32 ? 224 : nf == 64 ? 128 : 64;     // E stage <= 32 KB
+  const long long x_total = (long long)im * ic * iy * ix;
+  BF_REQUIRE(Mrows + 1 <= 32, BF_ERR_ARG, "bf_conv_c3_backward_filter: more than 31 patch rows (ic*fy*fx = %d)", Mrows);
+  BF_REQUIRE(((iy * ix) & 3) == 0, BF_ERR_ARG, "bf_conv_c3_backward_filter: plane size %dx%d is not a multiple of 4", iy, ix);
+  BF_REQUIRE(ox <= cap_px && (x_total & 3) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)E & 15) == 0, BF_ERR_ARG,
+             "bf_conv_c3_backward_filter: unsupported plane / alignment");
+  BF_REQUIRE((long long)im * oy * ox < 2147483647LL, BF_ERR_ARG, "bf_conv_c3_backward_filter: too many pixels");
+  C3DfParams p;
+  p.nimg = im; p.ic = ic; p.iy = iy; p.ix = ix; p.oy = oy; p.ox = ox; p.fy = fy; p.fx = fx; p.nf = nf;
+  p.RB = cap_px / ox; if (p.RB > oy) p.RB = oy;
+  p.nbands = (oy + p.RB - 1) / p.RB;
+  p.nunits = im * p.nbands;
+  p.px_band = p.RB * ox;
+  p.nkb = (p.px_band + 31) / 32;
+  p.Mrows = Mrows;
+  p.e_stage_bytes = MH * p.nkb * 4096;
+  p.x_plane_f = ((p.RB + fy - 1) * ix + 3 + 3) & ~3;
+  p.x_stage_bytes = ic * p.x_plane_f * 4;
+  p.x_total_f = x_total;
+  p.na = 16;
+  p.ns = 4;
+  auto smem_of = [&](int ns) {
+    return (size_t)1024 + (size_t)ns * p.e_stage_bytes + (size_t)p.na * C3DF_A_SLOT + C3DF_A_TAIL + (size_t)ns * p.x_stage_bytes;
+  };
+  while (p.ns > 2 && smem_of(p.ns) > 220 * 1024) --p.ns;
+  BF_REQUIRE(smem_of(p.ns) <= 220 * 1024, BF_ERR_ARG, "bf_conv_c3_backward_filter: stage does not fit shared memory");
+  const size_t smem = smem_of(p.ns);
+  const int ctas = p.nunits < num_sms() ? p.nunits : num_sms();
   void* ws = nullptr;
-  int rc = workspace_require(part_bytes + xs_bytes, &ws);
+  int rc = workspace_require(c3_al256((size_t)ctas * (Mrows + 1) * nf * 4), &ws);
   if (rc) return rc;
-  float* Xs = (float*)((char*)ws + part_bytes);
-  shift_rows_kernel<<<ew_grid((size_t)fx * xrows * pitch, 256), 256, 0, s>>>(X, Xs, xrows, ix, pitch, fx);
-  BF_LAUNCH_CHECK();
-  CUtensorMap mE, mX;
+  CUtensorMap mE;
   {
-    uint64_t dims[4] = {(uint64_t)nf, (uint64_t)ox, (uint64_t)oy, (uint64_t)im};
-    uint64_t str[3] = {(uint64_t)nf, (uint64_t)nf * ox, (uint64_t)nf * ox * oy};
-    uint32_t box[4] = {32, 32, 1, 1};
-    if (!tma_make_map(&mE, E, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    uint64_t dims[2] = {(uint64_t)nf, (uint64_t)im * oy * ox};
+    uint64_t str[1] = {(uint64_t)nf};
+    uint32_t box[2] = {32, (uint32_t)p.px_band};
+    if (!tma_make_map(&mE, E, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
       return fail(BF_ERR_CUDA, "bf_conv_c3_backward_filter: cuTensorMapEncodeTiled failed (E)");
-  }
-  {
-    uint64_t dims[5] = {(uint64_t)pitch, (uint64_t)iy, (uint64_t)ic, (uint64_t)im, (uint64_t)fx};
-    uint64_t str[4] = {(uint64_t)pitch, (uint64_t)pitch * iy, (uint64_t)pitch * iy * ic, (uint64_t)pitch * xrows};
-    uint32_t box[5] = {32, (uint32_t)fy, (uint32_t)ic, 1, (uint32_t)fx};
-    if (!tma_make_map(&mX, Xs, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
-      return fail(BF_ERR_CUDA, "bf_conv_c3_backward_filter: cuTensorMapEncodeTiled failed (X)");
   }
 #define BF_C3DF_CASE(MH_)                                                                                            \
   if (MH == MH_) {                                                                                                   \
     BF_CUDA(cudaFuncSetAttribute(conv_c3_df_kernel<MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    conv_c3_df_kernel<MH_><<<ctas, C3DF_THREADS, smem, s>>>(mE, mX, p, (float*)ws);                                  \
+    conv_c3_df_kernel<MH_><<<ctas, C3DF_THREADS, smem, s>>>(mE, X, p, (float*)ws);                                   \
   }
   BF_C3DF_CASE(1) BF_C3DF_CASE(2) BF_C3DF_CASE(4)
 #undef BF_C3DF_CASE
   BF_LAUNCH_CHECK();
-  if (prof) {
-    long long h[16];
-    cudaStreamSynchronize(s);
-    cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[c3 dF prof, CTA 0, %d chunks] producer wait empty %lld | mma warp 1: wait full %lld of total %lld\n",
-            (p.nchunks + ctas - 1) / ctas, h[0], h[1], h[2]);
-  }
-  conv_c3_df_reduce_kernel<<<ew_grid((size_t)nf * (ic * fy * fx + 1), 128), 128, 0, s>>>((const float*)ws, dF, db, ctas, ic, fy, fx, nf, KB);
+  conv_c3_df_reduce_kernel<<<ew_grid((size_t)nf * (Mrows + 1), 128), 128, 0, s>>>((const float*)ws, dF, db, ctas, Mrows, nf);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;

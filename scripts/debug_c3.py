@@ -10,7 +10,7 @@ L = _lib.lib
 def dev(a): return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
 def P(t): return ctypes.c_void_p(t.data_ptr())
 def err(a, b): return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-30))
-shapes = [(2, 3, 30, 30, 32, 3, 3), (5, 1, 28, 28, 32, 3, 3), (3, 4, 17, 40, 64, 2, 4), (37, 3, 30, 30, 32, 3, 3), (2, 2, 12, 50, 128, 3, 2)]
+shapes = [(2, 3, 30, 30, 32, 3, 3), (5, 1, 28, 28, 32, 3, 3), (3, 4, 17, 40, 64, 2, 3), (37, 3, 30, 30, 32, 3, 3), (2, 2, 12, 50, 128, 3, 2)]
 for (im, ic, iy, ix, nf, fy, fx) in shapes:
     rs = np.random.RandomState(1)
     A = rs.randn(im, ic, iy, ix); F = rs.randn(nf, ic, fy, fx) * 0.2; b = rs.randn(nf)
