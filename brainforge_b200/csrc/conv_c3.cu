@@ -187,12 +187,13 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
 constexpr int C3DF_THREADS = 384;      // warp 0 TMA, 1-2 MMA, 3 TMEM, 4-11 patch-tile builders (4-7 also the epilogue)
 constexpr int C3DF_BUILDERS = 8;
 constexpr int C3DF_A_SLOT = 32 * 128;     // 32 patch rows per tile; the M=128 descriptor runs on into the next tiles (rows >= 32 of D are never read)
-constexpr int C3DF_A_TAIL = 96 * 128;     // so that the last tile's descriptor stays inside the ring
+// after the ring: zeros, >= 4 KB (the M=64 descriptor of the last tile reads 8 KB) and >= one raw stage (source of padding lanes)
 struct C3DfParams {
   int nimg, ic, iy, ix, oy, ox, fy, fx, nf;
   int RB, nbands, nunits, px_band, nkb, Mrows, ns, na;
   int e_stage_bytes, x_plane_f, x_stage_bytes;
   long long x_total_f;
+  int a_tail_bytes;
 };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -200,11 +201,11 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int MH>
+template <int MH, int NR>
 __global__ void __launch_bounds__(C3DF_THREADS, 1)
 conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restrict__ X, C3DfParams p, float* __restrict__ partial) {
   extern __shared__ int dyn_smem[];
-  __shared__ __align__(8) uint64_t full[4], empty[4], a_full[16], a_empty[16], done;
+  __shared__ __align__(8) uint64_t full[6], empty[6], built[4], afree[4], done;
   __shared__ uint32_t tmem_slot;
   __shared__ int roff[128];
   constexpr int NF = MH * 32;
@@ -212,15 +213,15 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
   const uint32_t e_base = base;
   const uint32_t a_base = e_base + (uint32_t)p.ns * p.e_stage_bytes;
-  const uint32_t x_base = a_base + (uint32_t)p.na * C3DF_A_SLOT + C3DF_A_TAIL;
+  const uint32_t x_base = a_base + (uint32_t)(p.na * p.nkb) * C3DF_A_SLOT + (uint32_t)p.a_tail_bytes;   // two band tiles of nkb k-block tiles
 
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * NF));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2 + C3DF_BUILDERS); }
-    for (int i = 0; i < 16; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 6; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2 + C3DF_BUILDERS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&built[i], C3DF_BUILDERS); mbar_init(&afree[i], 2); }
     mbar_init(&done, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -281,90 +282,88 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       }
     }
   } else if (warp == 1 || warp == 2) {
-    // ------------------------------------------------------------------ MMA issuers (k-block parity)
+    // ------------------------------------------------------------------ MMA issuers (k-block parity inside a band)
     const bool leader = elect_one_sync();
     const int wsel = warp - 1;
-    constexpr uint32_t idesc = idesc_tf32(128, NF, false, true);
-    int g = 0, mine = 0;
+    constexpr uint32_t idesc = idesc_tf32(64, NF, false, true);   // M=64: half the shared-memory reads of M=128 per MMA
+    int mine = 0;
     for (int it = 0; it < my_units; ++it) {
-      const int s = it % p.ns, u = it / p.ns;
-      mbar_wait(&full[s], (uint32_t)(u & 1));
-      bool any = false;
-      for (int j = 0; j < p.nkb; ++j, ++g) {
-        if ((g & 1) != wsel) continue;
-        const int slot = g % p.na, ua = g / p.na;
-        mbar_wait(&a_full[slot], (uint32_t)(ua & 1));
-        tc_fence_after();
-        if (leader) {
-          const uint64_t ad = desc_k_sw128(a_base + slot * C3DF_A_SLOT);
+      const int s = it % p.ns, u = it / p.ns, t = it % p.na, ut = it / p.na;
+      mbar_wait(&full[s], (uint32_t)(u & 1));          // E landed
+      mbar_wait(&built[t], (uint32_t)(ut & 1));        // patch tiles of the band written
+      tc_fence_after();
+      if (leader) {
+        bool any = false;
+        for (int j = wsel; j < p.nkb; j += 2) {
+          const uint64_t ad = desc_k_sw128(a_base + (uint32_t)(t * p.nkb + j) * C3DF_A_SLOT);
           const uint64_t bd = desc_mn_sw128_32b(e_base + s * p.e_stage_bytes + j * 4096, (uint32_t)p.nkb * 4096u, 512u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_tf32(tmem + wsel * NF, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 64), idesc, (mine > 0 || ks > 0) ? 1u : 0u);
-          umma_commit(&a_empty[slot]);
+          ++mine;
+          any = true;
         }
-        ++mine;
-        any = true;
+        if (any) { umma_commit(&afree[t]); umma_commit(&empty[s]); }
+        else { mbar_arrive(&afree[t]); mbar_arrive(&empty[s]); }
       }
-      if (leader) { if (any) umma_commit(&empty[s]); else mbar_arrive(&empty[s]); }
+      __syncwarp();
     }
     if (leader) umma_commit(&done);
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ patch-tile builders
-    // builder warp bw owns the k-blocks g = bw (mod 8): eight tiles are under construction at any time.  Lane =
-    // pixel of the k-block.  Per patch row: one add, one shared load, TF32 rounding, one select, one conflict-free
-    // swizzled store; every per-row offset is band-invariant and lives in registers (planes are multiples of
-    // 4 floats, host-checked, so the 16-byte alignment slack `lead` of the raw rows is the same for every plane).
+    // builder warp bw writes the k-block tiles j = bw, bw+8, .. of every band (hand-off to the MMA warps once per
+    // band).  Lane = pixel of the k-block.  Per patch row: add, shared load, round (add half an ulp of TF32; the
+    // MMA drops the low 13 bits), conflict-free swizzled store.  Every per-row offset is band-invariant and pinned
+    // in a register (planes are multiples of 4 floats, host-checked, so the alignment slack `lead` of the raw rows
+    // is the same for every plane).  Lanes beyond the band's pixels read zeros from the never-written tail of the
+    // tile ring.  Rows Mrows+1 .. NR-1 of a tile are don't-care rows (their accumulator rows are never read).
     const int bw = warp - 4;
-    const char* xs_all = reinterpret_cast<const char*>(dyn_smem) + (x_base - smem_u32(dyn_smem));
-    char* a_tiles = reinterpret_cast<char*>(dyn_smem) + (a_base - smem_u32(dyn_smem));
-    int rowoff[31];                      // byte offset of row r's first element inside a raw stage
+    uint32_t rowoff[NR];                 // byte offset of row r's first element inside a raw stage
 #pragma unroll
-    for (int r = 0; r < 31; ++r) rowoff[r] = r < p.Mrows ? (roff[r] & 0xffffff) * 4 : 0;
-    const int sw = lane >> 2, l3 = (lane & 3) * 4;
-    int swz[8];                          // byte offset of this lane's 16-byte chunk in a tile row with (r & 7) = i
+    for (int r = 0; r < NR; ++r) {
+      rowoff[r] = r < p.Mrows ? (uint32_t)(roff[r] & 0xffffff) * 4u : 0u;
+      asm volatile("" : "+r"(rowoff[r]));          // keep it in a register (no rematerialisation from the table)
+    }
+    const uint32_t sw = lane >> 2, l3 = (lane & 3) * 4;
+    uint32_t swz[8];                     // byte offset of this lane's 16-byte chunk in a tile row with (r & 7) = i
 #pragma unroll
-    for (int i = 0; i < 8; ++i) swz[i] = ((sw ^ i) << 4) + l3;
-    const int ones_off = p.Mrows * 128 + (((sw ^ (p.Mrows & 7)) << 4) + l3);
-    int g = 0, it = 0;
+    for (int i = 0; i < 8; ++i) { swz[i] = ((sw ^ i) << 4) + l3; asm volatile("" : "+r"(swz[i])); }
+    const uint32_t ones_off = (uint32_t)p.Mrows * 128u + (((sw ^ (uint32_t)(p.Mrows & 7)) << 4) + l3);
+    const uint32_t zero_src = a_base + (uint32_t)(p.na * p.nkb) * C3DF_A_SLOT;     // a_tail_bytes of zeros
+    int it = 0;
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
-      const int s = it % p.ns, u = it / p.ns;
+      const int s = it % p.ns, u = it / p.ns, t = it % p.na, ut = it / p.na;
       const int band = unit % p.nbands, y0 = band * p.RB;
       int rb = p.RB;
       if (rb > p.oy - y0) rb = p.oy - y0;
       const int npx = rb * p.ox;
       const int lead = (y0 * p.ix) & 3;
-      const char* xs = xs_all + s * p.x_stage_bytes;
-      bool waited = false;
-      for (int j = 0; j < p.nkb; ++j, ++g) {
-        if ((g & (C3DF_BUILDERS - 1)) != bw) continue;
-        if (!waited) { mbar_wait(&full[s], (uint32_t)(u & 1)); waited = true; }
-        const int slot = g % p.na, ua = g / p.na;
+      const uint32_t xs = x_base + (uint32_t)s * p.x_stage_bytes;
+      mbar_wait(&full[s], (uint32_t)(u & 1));                       // raw rows landed
+      if (ut > 0) mbar_wait(&afree[t], (uint32_t)((ut - 1) & 1));   // MMAs of the band tile's previous use are done
+      for (int j = bw; j < p.nkb; j += C3DF_BUILDERS) {
         const int px = j * 32 + lane;
         const bool valid = px < npx;
         const int yy = px / p.ox, xx = px - yy * p.ox;
-        const char* src = xs + (valid ? (lead + yy * p.ix + xx) * 4 : 0);
-        float v[31];
+        const uint32_t src = valid ? xs + (uint32_t)(lead + yy * p.ix + xx) * 4u : zero_src;
+        const uint32_t tile = a_base + (uint32_t)(t * p.nkb + j) * C3DF_A_SLOT;
+        uint32_t v[NR];
 #pragma unroll
-        for (int r = 0; r < 31; ++r)
-          if (r < p.Mrows) v[r] = *reinterpret_cast<const float*>(src + rowoff[r]);
-        if (ua > 0) mbar_wait(&a_empty[slot], (uint32_t)((ua - 1) & 1));
-        char* tile = a_tiles + slot * C3DF_A_SLOT;
+        for (int r = 0; r < NR; ++r) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[r]) : "r"(src + rowoff[r]));
 #pragma unroll
-        for (int r = 0; r < 31; ++r)
-          if (r < p.Mrows) *reinterpret_cast<uint32_t*>(tile + r * 128 + swz[r & 7]) = valid ? to_tf32(v[r]) : 0u;
-        *reinterpret_cast<uint32_t*>(tile + ones_off) = valid ? 0x3f800000u : 0u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[slot]);
+        for (int r = 0; r < NR; ++r)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + swz[r & 7] + (uint32_t)(r * 128)), "r"(v[r] + 0x1000u));
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + ones_off), "r"(valid ? 0x3f800000u : 0u));
       }
-      if (!waited) mbar_wait(&full[s], (uint32_t)(u & 1));   // keep this warp's phase bookkeeping in step
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);      // this warp no longer reads the band's raw rows
+      if (lane == 0) { mbar_arrive(&built[t]); mbar_arrive(&empty[s]); }   // tiles written; raw rows no longer read
     }
     // ---- final epilogue: partial[cta][r][NF] = accumulator of the even k-blocks + accumulator of the odd ones
-    const int m = bw * 32 + lane;
-    if (bw < 4 && bw * 32 <= p.Mrows) {
+    // M=64 accumulator (cta_group::1): row r lives in TMEM lane (r/16)*32 + r%16, 16 rows per 32-lane quadrant
+    // (pinned on a B200: the other candidate, lane = r, fails parity)
+    const int m = lane < 16 ? bw * 16 + lane : 1 << 20;
+    if (bw < 4 && bw * 16 <= p.Mrows) {
       mbar_wait(&done, 0);
       tc_fence_after();
       float* dst = partial + ((size_t)blockIdx.x * (p.Mrows + 1) + m) * NF;
@@ -507,13 +506,14 @@ int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float*
   p.x_plane_f = ((p.RB + fy - 1) * ix + 3 + 3) & ~3;
   p.x_stage_bytes = ic * p.x_plane_f * 4;
   p.x_total_f = x_total;
-  p.na = 16;
-  p.ns = 4;
+  p.a_tail_bytes = p.x_stage_bytes > 4096 ? (p.x_stage_bytes + 1023) / 1024 * 1024 : 4096;
+  p.na = 2;                      // band tiles in the patch ring
+  p.ns = 6;
   auto smem_of = [&](int ns) {
-    return (size_t)1024 + (size_t)ns * p.e_stage_bytes + (size_t)p.na * C3DF_A_SLOT + C3DF_A_TAIL + (size_t)ns * p.x_stage_bytes;
+    return (size_t)1024 + (size_t)ns * p.e_stage_bytes + (size_t)p.na * p.nkb * C3DF_A_SLOT + p.a_tail_bytes + (size_t)ns * p.x_stage_bytes;
   };
-  while (p.ns > 2 && smem_of(p.ns) > 220 * 1024) --p.ns;
-  BF_REQUIRE(smem_of(p.ns) <= 220 * 1024, BF_ERR_ARG, "bf_conv_c3_backward_filter: stage does not fit shared memory");
+  while (p.ns > 2 && smem_of(p.ns) > 224 * 1024) --p.ns;
+  BF_REQUIRE(smem_of(p.ns) <= 224 * 1024, BF_ERR_ARG, "bf_conv_c3_backward_filter: stage does not fit shared memory");
   const size_t smem = smem_of(p.ns);
   const int ctas = p.nunits < num_sms() ? p.nunits : num_sms();
   void* ws = nullptr;
@@ -527,12 +527,15 @@ int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float*
     if (!tma_make_map(&mE, E, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
       return fail(BF_ERR_CUDA, "bf_conv_c3_backward_filter: cuTensorMapEncodeTiled failed (E)");
   }
-#define BF_C3DF_CASE(MH_)                                                                                            \
-  if (MH == MH_) {                                                                                                   \
-    BF_CUDA(cudaFuncSetAttribute(conv_c3_df_kernel<MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    conv_c3_df_kernel<MH_><<<ctas, C3DF_THREADS, smem, s>>>(mE, X, p, (float*)ws);                                   \
+  const int NR = Mrows <= 12 ? 12 : Mrows <= 20 ? 20 : Mrows <= 27 ? 27 : 31;   // patch rows a builder writes per tile
+#define BF_C3DF_CASE(MH_, NR_)                                                                                          \
+  if (MH == MH_ && NR == NR_) {                                                                                         \
+    BF_CUDA(cudaFuncSetAttribute(conv_c3_df_kernel<MH_, NR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_c3_df_kernel<MH_, NR_><<<ctas, C3DF_THREADS, smem, s>>>(mE, X, p, (float*)ws);                                 \
   }
-  BF_C3DF_CASE(1) BF_C3DF_CASE(2) BF_C3DF_CASE(4)
+  BF_C3DF_CASE(1, 12) BF_C3DF_CASE(1, 20) BF_C3DF_CASE(1, 27) BF_C3DF_CASE(1, 31)
+  BF_C3DF_CASE(2, 12) BF_C3DF_CASE(2, 20) BF_C3DF_CASE(2, 27) BF_C3DF_CASE(2, 31)
+  BF_C3DF_CASE(4, 12) BF_C3DF_CASE(4, 20) BF_C3DF_CASE(4, 27) BF_C3DF_CASE(4, 31)
 #undef BF_C3DF_CASE
   BF_LAUNCH_CHECK();
   conv_c3_df_reduce_kernel<<<ew_grid((size_t)nf * (Mrows + 1), 128), 128, 0, s>>>((const float*)ws, dF, db, ctas, Mrows, nf);

@@ -12,6 +12,7 @@
 #pragma once
 #include "gemm_umma.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace bf {
 
