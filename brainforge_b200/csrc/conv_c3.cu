@@ -19,9 +19,9 @@
 
 namespace bf {
 
-constexpr int C3_THREADS = 224;       // warp 0 TMA, warp 1 MMA, warp 2 spare, warps 3-6 epilogue
+constexpr int C3_THREADS = 352;       // warp 0 TMA, warp 1 MMA, warp 2 spare, warps 3-6 / 7-10 epilogue of the even / odd tiles
 constexpr int C3_STAGE_LD = 36;
-constexpr int C3_STAGING_BYTES = 4 * 32 * C3_STAGE_LD * 4;
+constexpr int C3_STAGING_BYTES = 2 * 4 * 32 * C3_STAGE_LD * 4;
 
 struct C3FwdParams {
   int nimg, IR, ix, oy, ox, RT, tiles_per_img, ntiles, fy, fx, ic, N, box_rows, na;
@@ -118,12 +118,15 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
       }
     }
   } else if (warp >= 3) {
-    const int quad = warp & 3;
-    float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + quad * 32 * C3_STAGE_LD;
+    // two epilogue groups of four warps (one warp per TMEM lane quadrant): group g drains accumulator g, i.e. the
+    // even / odd tiles, so that the drain of one tile overlaps the drain of the next
+    const int quad = warp & 3, grp = (warp - 3) >> 2;
+    float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + (grp * 4 + quad) * 32 * C3_STAGE_LD;
     int it = 0;
     const int m = quad * 32 + lane;
     const int r = m / p.ix, x = m - r * p.ix;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
       const int acc_set = it & 1, tu = it >> 1;
       const int b = tile / p.tiles_per_img, t = tile - b * p.tiles_per_img;
       const int y = t * p.RT + r;
