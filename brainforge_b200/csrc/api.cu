@@ -115,6 +115,10 @@ int bf_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream) {
   BF_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
   return BF_OK;
 }
+int bf_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+  BF_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return BF_OK;
+}
 int bf_stream_sync(void* stream) {
   BF_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return BF_OK;

@@ -48,10 +48,23 @@ class Learner:
         history = MetricLogs.from_metric_list(updates_per_epoch, ["cost"], metrics)
         self.layers.learning = True
         batch_size = 0
+        # Learners that can stage a batch ahead of time (Backpropagation.stage_batch) get the NEXT batch's
+        # host->device copy overlapped with the current step: launch step i, upload batch i+1 on the copy
+        # stream, then read step i's scalars.  The generator is still drawn exactly updates_per_epoch times.
+        stage = getattr(self, "stage_batch", None) if "w" not in kw else None
+        staged = None
         for i in range(updates_per_epoch):
-            batch = next(generator)
-            batch_size = len(batch[0])
-            epoch_metrics = self.learn_batch(*batch, metrics=metrics, **kw)
+            if stage is None:
+                batch = next(generator)
+                batch_size = len(batch[0])
+                epoch_metrics = self.learn_batch(*batch, metrics=metrics, **kw)
+            else:
+                if staged is None:
+                    staged = stage(*next(generator)[:2])
+                batch_size = len(staged)
+                pending = self.learn_batch_async(staged, None, metrics=metrics, **kw)
+                staged = stage(*next(generator)[:2]) if i + 1 < updates_per_epoch else None
+                epoch_metrics = pending()
             history.record(epoch_metrics)
             if verbose:
                 history.log(prefix="\rTraining ", end="", add_progress=True)

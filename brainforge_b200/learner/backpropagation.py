@@ -12,10 +12,24 @@ import numpy as np
 import torch
 
 from .abstract_learner import Learner
-from ..device import DeviceArray, as_device
+from .. import _lib
+from ..device import DeviceArray, as_device, call, stream_ptr
 from ..metrics import metrics as _metrics
 from ..optimizers import optimizers, GradientDescent
 from .. import dist as _dist
+
+
+class StagedBatch:
+    """A batch whose host->device copy is in flight on the copy stream (Backpropagation.stage_batch)."""
+
+    def __init__(self, x, y, event):
+        self.x, self.y, self.event = x, y, event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+    def __len__(self):
+        return len(self.x)
 
 
 class Backpropagation(Learner):
@@ -32,15 +46,37 @@ class Backpropagation(Learner):
     def learn_batch(self, X, Y, w=None, metrics=(), update=True):
         """learner/backpropagation.py:16-30.  Under torch.distributed (world_size > 1) X, Y are this
         rank's shard of the global batch; cost and metrics are those of the GLOBAL batch."""
+        return self.learn_batch_async(X, Y, w=w, metrics=metrics, update=update)()
+
+    def learn_batch_async(self, X, Y, w=None, metrics=(), update=True):
+        """Enqueue the whole device step and return a callable that reads the step's scalars back (the only
+        host synchronisation of a step).  `Learner.epoch` uses the gap to upload the NEXT batch on a copy stream."""
         metrics = [_metrics.get(m) for m in metrics]
         self.layers.flatten_parameters()
-        if self.use_graph and w is None and not isinstance(X, DeviceArray):
-            return self._learn_batch_graph(X, Y, metrics, update)
+        if isinstance(X, StagedBatch):
+            X.wait()
+            X, Y = X.x, X.y
+        if self.use_graph and w is None:
+            return self._launch_graph(X, Y, metrics, update)
         x, y = as_device(X), as_device(Y)
         wd = as_device(w) if w is not None else None
         m_local = len(x)
         self._step(x, y, wd, metrics, update, m_local, None)
-        return self._read_scalars(metrics, m_local)
+        return lambda: self._read_scalars(metrics, m_local)
+
+    def stage_batch(self, X, Y):
+        """Start the host->device copy of a batch on a side stream; the returned handle is accepted by
+        learn_batch / learn_batch_async in place of (X, Y)."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            xd, yd = DeviceArray.from_host(X), DeviceArray.from_host(Y)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        xd.t.record_stream(main)
+        yd.t.record_stream(main)
+        return StagedBatch(xd, yd, ev)
 
     def _step(self, x, y, wd, metrics, update, m_local, m_global_static):
         """Device-only part of learn_batch (capturable in a CUDA graph: no host sync inside)."""
@@ -67,26 +103,38 @@ class Backpropagation(Learner):
             out[str(metric).lower()] = float(sc[1]) / m
         return out
 
-    def _learn_batch_graph(self, X, Y, metrics, update):
+    def _launch_graph(self, X, Y, metrics, update):
         """CUDA-graph replay of the step for a fixed (shape, metrics, update) signature: the ~dozens of
         kernel launches of a step collapse into one graph launch (small-batch configs are launch-bound,
-        SURVEY 7.2#6).  Inputs are staged through static device buffers."""
-        X, Y = np.asarray(X), np.asarray(Y)
-        key = (X.shape, Y.shape, tuple(str(m) for m in metrics), bool(update), float(self.optimizer.eta))
+        SURVEY 7.2#6).  Inputs are staged through static device buffers (host arrays: one H2D; arrays already
+        in HBM, e.g. prefetched by `stage_batch`: one device-to-device copy)."""
+        if not isinstance(X, DeviceArray):
+            X = np.asarray(X)
+        if not isinstance(Y, DeviceArray):
+            Y = np.asarray(Y)
+        key = (tuple(X.shape), tuple(Y.shape), tuple(str(m) for m in metrics), bool(update), float(self.optimizer.eta))
         entry = self._graphs.get(key)
         m_local = len(X)
+
+        def fill(dst, src):
+            if isinstance(src, DeviceArray):
+                src = src.to_nchw()
+                if src.size:
+                    call(_lib.lib.bf_memcpy_d2d, dst.ptr, src.ptr, src.size * 4, stream_ptr())
+            else:
+                dst.copy_from_host(src)
+
         if entry is None:
             xs, ys = DeviceArray.empty(*X.shape), DeviceArray.empty(*Y.shape)
-            xs.copy_from_host(X)
-            ys.copy_from_host(Y)
+            fill(xs, X)
+            fill(ys, Y)
             m_global = m_local * _dist.world_size()
             # first call runs eagerly (sizes the workspace, warms every kernel), later calls replay
             self._step(xs, ys, None, metrics, update, m_local, m_global)
-            out = self._read_scalars(metrics, m_local)
             self._graphs[key] = {"x": xs, "y": ys, "graph": None, "m_global": m_global, "calls": 1}
-            return out
-        entry["x"].copy_from_host(X)
-        entry["y"].copy_from_host(Y)
+            return lambda: self._read_scalars(metrics, m_local)
+        fill(entry["x"], X)
+        fill(entry["y"], Y)
         if entry["graph"] is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -98,7 +146,7 @@ class Backpropagation(Learner):
             torch.cuda.current_stream().wait_stream(side)
             entry["graph"] = g
         entry["graph"].replay()
-        return self._read_scalars(metrics, m_local)
+        return lambda: self._read_scalars(metrics, m_local)
 
     # ------------------------------------------------------------------ pieces of the public API
     def _bwd(self, error, need_input_delta=True):

@@ -64,6 +64,7 @@ BF_API int bf_last_path(void);
 BF_API unsigned long long bf_launch_count(void);
 BF_API int bf_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
 BF_API int bf_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
+BF_API int bf_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);
 BF_API int bf_stream_sync(void* stream);
 /* float64 <-> float32 on the device (host API speaks float64 like the reference, HBM holds FP32). */
 BF_API int bf_cast_f64_to_f32(const double* d_src, float* d_dst, size_t n, void* stream);

@@ -217,3 +217,28 @@ def test_neuroevolution_fitness_fanout():
     before = ne5.population.grades.min()
     ne5.learn_batch(X, Y, epochs=2)
     assert ne5.population.grades.min() <= before + 1e-9
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_epoch_prefetch_matches_learn_batch(use_graph):
+    """Learner.epoch uploads batch i+1 on a copy stream while step i runs (stage_batch / learn_batch_async); the
+    trajectory must equal plain learn_batch calls bit for bit, and the generator is drawn exactly n times."""
+    ishape, spec, cost, optimizer = CFG["cfg2"]
+    a = build_b200(ishape, spec, cost, optimizer, seed=11, use_graph=use_graph)
+    b = build_b200(ishape, spec, cost, optimizer, seed=11)
+    rs = np.random.RandomState(3)
+    data = [(rs.randn(32, *ishape), onehot(rs, 32, 10)) for _ in range(5)]
+    drawn = []
+
+    def gen():
+        for i, d in enumerate(data):
+            drawn.append(i)
+            yield d
+
+    hist = a.epoch(gen(), updates_per_epoch=5, verbose=0, metrics=["acc"])
+    ref = [b.learn_batch(x, y, metrics=["acc"]) for x, y in data]
+    assert drawn == [0, 1, 2, 3, 4]
+    assert hist["cost"] == [r["cost"] for r in ref]
+    assert hist["accuracy"] == [r["accuracy"] for r in ref]
+    assert np.array_equal(a.layers.get_weights(), b.layers.get_weights())
+    assert a.age == 5
