@@ -42,6 +42,167 @@ struct EpiPlain {
   __device__ void store(int m, int n, float v, int) const { out[(long)m * N + n] = v; }
 };
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Skinny dense layers (n <= 32 output columns, e.g. the 10-class heads of every BASELINE config).  At n = 10 the
+// contraction has 5 FLOP per byte of X: it is HBM-bound, a 128 x 16 tensor-core tile would idle 3/4 of its columns
+// and (measured, B200) costs ~40 us of fixed pipeline latency per call, so these run as FP32 FMA kernels that
+// stream X once at full width, with W resident in shared memory / registers.  (Exact FP32 on both precision paths.)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SKINNY_ROWS = 4;          // rows per warp iteration (forward)
+
+// forward: one warp per SKINNY_ROWS rows, lanes split K; W staged once per CTA as [k][NT + pad] (conflict-free LDS.128)
+template <int NT>
+__global__ void __launch_bounds__(256)
+dense_skinny_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
+                        float* __restrict__ out, int m, int k, int n, int act) {
+  extern __shared__ __align__(16) float sw[];
+  constexpr int PITCH = NT == 4 ? 4 : NT + 4;
+  for (int i = threadIdx.x; i < k * NT; i += blockDim.x) {
+    const int kk = i / NT, j = i - kk * NT;
+    sw[kk * PITCH + j] = j < n ? W[(size_t)kk * n + j] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int ngroups = (m + SKINNY_ROWS - 1) / SKINNY_ROWS;
+  for (int grp = blockIdx.x * wpb + warp; grp < ngroups; grp += gridDim.x * wpb) {
+    const int m0 = grp * SKINNY_ROWS;
+    float acc[SKINNY_ROWS][NT];
+#pragma unroll
+    for (int r = 0; r < SKINNY_ROWS; ++r)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[r][j] = 0.f;
+    for (int kk = lane; kk < k; kk += 32) {
+      float x[SKINNY_ROWS];
+#pragma unroll
+      for (int r = 0; r < SKINNY_ROWS; ++r) x[r] = (m0 + r < m) ? __ldg(X + (size_t)(m0 + r) * k + kk) : 0.f;
+      const float4* wr = reinterpret_cast<const float4*>(sw + kk * PITCH);
+#pragma unroll
+      for (int q = 0; q < NT / 4; ++q) {
+        const float4 w4 = wr[q];
+#pragma unroll
+        for (int r = 0; r < SKINNY_ROWS; ++r) {
+          acc[r][4 * q + 0] = fmaf(x[r], w4.x, acc[r][4 * q + 0]);
+          acc[r][4 * q + 1] = fmaf(x[r], w4.y, acc[r][4 * q + 1]);
+          acc[r][4 * q + 2] = fmaf(x[r], w4.z, acc[r][4 * q + 2]);
+          acc[r][4 * q + 3] = fmaf(x[r], w4.w, acc[r][4 * q + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SKINNY_ROWS; ++r) {
+      float mine = 0.f;                      // lane j ends up with column j of row m0 + r
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const float t = warp_sum(acc[r][j]);
+        if (lane == j) mine = t;
+      }
+      const bool col = lane < n;
+      if (b && col) mine += __ldg(b + lane);
+      if (act == BF_ACT_SOFTMAX) {           // SoftMax.t1, atomic/activation_op.py:127-130
+        const float mx = warp_max(col ? mine : -INFINITY);
+        const float e = col ? expf(mine - mx) : 0.f;
+        mine = e / warp_sum(e);
+      } else {
+        mine = act_fwd_rt(act, mine);
+      }
+      if (col && m0 + r < m) out[(size_t)(m0 + r) * n + lane] = mine;
+    }
+  }
+}
+
+// backward: CTA = (row chunk, 256-column slab of K), thread = one column kk.  Per row: dX[m][kk] = E[m,:] . W[kk,:]
+// and the running dW[kk,:] += X[m][kk] * E[m,:]; per-chunk partials (row k of a partial = db) go to the workspace and
+// are summed in chunk order by splitk_reduce_kernel (deterministic).
+template <int NT>
+__global__ void __launch_bounds__(256)
+dense_skinny_bwd_kernel(const float* __restrict__ X, const float* __restrict__ E, const float* __restrict__ W,
+                        float* __restrict__ partial, float* __restrict__ dX, int m, int k, int n, int rows_per_chunk) {
+  extern __shared__ __align__(16) float se[];     // [rows_per_chunk][NT]
+  const int m0 = blockIdx.x * rows_per_chunk;
+  int rows = m - m0;
+  if (rows > rows_per_chunk) rows = rows_per_chunk;
+  for (int i = threadIdx.x; i < rows * NT; i += blockDim.x) {
+    const int r = i / NT, j = i - r * NT;
+    se[i] = j < n ? E[(size_t)(m0 + r) * n + j] : 0.f;
+  }
+  __syncthreads();
+  const int kk = blockIdx.y * blockDim.x + threadIdx.x;
+  float* part = partial + (size_t)blockIdx.x * (k + 1) * n;
+  if (kk < k) {
+    float w[NT], acc[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { w[j] = j < n ? __ldg(W + (size_t)kk * n + j) : 0.f; acc[j] = 0.f; }
+    for (int r = 0; r < rows; ++r) {
+      const float x = __ldg(X + (size_t)(m0 + r) * k + kk);
+      const float4* e4 = reinterpret_cast<const float4*>(se + r * NT);
+      float dx = 0.f;
+#pragma unroll
+      for (int q = 0; q < NT / 4; ++q) {
+        const float4 e = e4[q];
+        acc[4 * q + 0] = fmaf(x, e.x, acc[4 * q + 0]); dx = fmaf(e.x, w[4 * q + 0], dx);
+        acc[4 * q + 1] = fmaf(x, e.y, acc[4 * q + 1]); dx = fmaf(e.y, w[4 * q + 1], dx);
+        acc[4 * q + 2] = fmaf(x, e.z, acc[4 * q + 2]); dx = fmaf(e.z, w[4 * q + 2], dx);
+        acc[4 * q + 3] = fmaf(x, e.w, acc[4 * q + 3]); dx = fmaf(e.w, w[4 * q + 3], dx);
+      }
+      if (dX) dX[(size_t)(m0 + r) * k + kk] = dx;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      if (j < n) part[(size_t)kk * n + j] = acc[j];
+  }
+  if (blockIdx.y == 0 && threadIdx.x < n) {       // db partial = column sums of the chunk's E rows
+    float sacc = 0.f;
+    for (int r = 0; r < rows; ++r) sacc += se[r * NT + threadIdx.x];
+    part[(size_t)k * n + threadIdx.x] = sacc;
+  }
+}
+
+static inline int skinny_nt(int n) { return n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+static inline bool skinny_ok(int m, int k, int n) {
+  if (n > 32 || m < 1) return false;
+  const int nt = skinny_nt(n);
+  return (size_t)k * (nt == 4 ? 4 : nt + 4) * 4 <= 200 * 1024;
+}
+
+static int launch_skinny_fwd(const float* X, const float* W, const float* b, float* out, int m, int k, int n, int act,
+                             cudaStream_t s) {
+  const int nt = skinny_nt(n);
+  const size_t smem = (size_t)k * (nt == 4 ? 4 : nt + 4) * 4;
+  int grid = (m + 8 * SKINNY_ROWS - 1) / (8 * SKINNY_ROWS);
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+#define BF_SK(NT_)                                                                                                  \
+  if (nt == NT_) {                                                                                                  \
+    BF_CUDA(cudaFuncSetAttribute(dense_skinny_fwd_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dense_skinny_fwd_kernel<NT_><<<grid, 256, smem, s>>>(X, W, b, out, m, k, n, act);                               \
+  }
+  BF_SK(4) BF_SK(8) BF_SK(16) BF_SK(32)
+#undef BF_SK
+  BF_LAUNCH_CHECK();
+  set_last_path(0);
+  return BF_OK;
+}
+
+static int launch_skinny_bwd(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m,
+                             int k, int n, int accumulate, cudaStream_t s) {
+  const int nt = skinny_nt(n);
+  int rows_per_chunk = (m + 63) / 64;
+  if (rows_per_chunk < 16) rows_per_chunk = 16;
+  if (rows_per_chunk > 256) rows_per_chunk = 256;
+  const int chunks = (m + rows_per_chunk - 1) / rows_per_chunk;
+  void* ws = nullptr;
+  int rc = workspace_require((size_t)chunks * (k + 1) * n * sizeof(float), &ws);
+  if (rc) return rc;
+  dim3 grid(chunks, (k + 255) / 256);
+  const size_t smem = (size_t)rows_per_chunk * nt * 4;
+#define BF_SK(NT_) if (nt == NT_) dense_skinny_bwd_kernel<NT_><<<grid, 256, smem, s>>>(X, E, W, (float*)ws, dX, m, k, n, rows_per_chunk);
+  BF_SK(4) BF_SK(8) BF_SK(16) BF_SK(32)
+#undef BF_SK
+  BF_LAUNCH_CHECK();
+  set_last_path(0);
+  return launch_splitk_reduce((const float*)ws, dW, db, k + 1, n, k, chunks, accumulate, n, 1, s);
+}
+
 }  // namespace bf
 
 using namespace bf;
@@ -55,6 +216,7 @@ int bf_dense_forward(const float* X, const float* W, const float* b, float* out,
   if (m == 0) return BF_OK;
   BF_REQUIRE(X && W && out, BF_ERR_ARG, "bf_dense_forward: null pointer");
   cudaStream_t s = as_stream(stream);
+  if (skinny_ok(m, k, n)) return launch_skinny_fwd(X, W, b, out, m, k, n, act, s);
   int ep_act = act == BF_ACT_SOFTMAX ? BF_ACT_LINEAR : act;
   int rc = BF_OK;
   {
@@ -73,6 +235,7 @@ int bf_dense_backward(const float* X, const float* E, const float* W, float* dW,
   BF_REQUIRE(m >= 0 && k > 0 && n > 0, BF_ERR_ARG, "bf_dense_backward: bad shape m=%d k=%d n=%d", m, k, n);
   BF_REQUIRE(W && dW && (m == 0 || (X && E)), BF_ERR_ARG, "bf_dense_backward: null pointer");
   cudaStream_t s = as_stream(stream);
+  if (skinny_ok(m, k, n)) return launch_skinny_bwd(X, E, W, dW, db, dX, m, k, n, accumulate, s);
   int rc;
   // dW = X^T @ E with a virtual all-ones row appended to X^T: row k of the product is db = E.sum(0).
   {

@@ -48,13 +48,14 @@ def test_dense_tf32(bf, O, m, k, n):
     X, W, b, E = rs.randn(m, k), rs.randn(k, n) * 0.2, rs.randn(n), rs.randn(m, n)
     op = bf.atomic.DenseOp()
     e = close(op.forward(X, W, b), O.dense_forward(X, W, b))
-    assert used_tensor_cores(bf)
+    # n <= 32 output columns: HBM-bound skinny layer, exact-FP32 FMA kernel on both precision paths (dense.cu)
+    assert used_tensor_cores(bf) == (n > 32)
     close(op.forward(X, W, b, activation="tanh"), np.tanh(O.dense_forward(X, W, b)))
     dW, db, dX = op.backward(X, E, W)
     rW, rb, rX = O.dense_backward(X, E, W)
     close(dW, rW); close(db, rb); close(dX, rX)
     # the tensor-core path must not be (accidentally) the FP32 path: operands are rounded to TF32
-    if k >= 64:
+    if k >= 64 and n > 32:
         assert e > 1e-6, e
 
 
