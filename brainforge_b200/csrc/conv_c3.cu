@@ -402,15 +402,24 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
 }
 
 // dF[f][r] = sum_cta partial[cta][r][f] (r = (c,ky,kx) in the reference's order);  db[f] = sum_cta partial[cta][Mrows][f]
-__global__ void conv_c3_df_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
-                                         int nctas, int Mrows, int nf) {
+// block = 32 consecutive outputs x 8 slices of the CTA range; a fixed-order shared-memory tree adds the slices.
+__global__ void __launch_bounds__(256)
+conv_c3_df_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
+                         int nctas, int Mrows, int nf) {
+  __shared__ float red[8][33];
   const int total = nf * (Mrows + 1);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int r = i / nf, f = i - r * nf;        // consecutive threads -> consecutive filters: coalesced reads
-    float s = 0.f;
-    for (int z = 0; z < nctas; ++z) s += partial[((size_t)z * (Mrows + 1) + r) * nf + f];
-    if (r == Mrows) { if (db) db[f] = s; }
-    else dF[(size_t)f * Mrows + r] = s;
+  const int o = blockIdx.x * 32 + threadIdx.x, zs = threadIdx.y;
+  float s = 0.f;
+  if (o < total)
+    for (int z = zs; z < nctas; z += 8) s += partial[(size_t)z * total + o];
+  red[zs][threadIdx.x] = s;
+  __syncthreads();
+  if (zs == 0 && o < total) {
+    const float sum = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x])) +
+                      ((red[4][threadIdx.x] + red[5][threadIdx.x]) + (red[6][threadIdx.x] + red[7][threadIdx.x]));
+    const int r = o / nf, f = o - r * nf;        // partial rows are [r][f]: consecutive threads -> consecutive filters
+    if (r == Mrows) { if (db) db[f] = sum; }
+    else dF[(size_t)f * Mrows + r] = sum;
   }
 }
 
@@ -541,7 +550,7 @@ int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float*
   BF_C3DF_CASE(4, 12) BF_C3DF_CASE(4, 20) BF_C3DF_CASE(4, 27) BF_C3DF_CASE(4, 31)
 #undef BF_C3DF_CASE
   BF_LAUNCH_CHECK();
-  conv_c3_df_reduce_kernel<<<ew_grid((size_t)nf * (Mrows + 1), 128), 128, 0, s>>>((const float*)ws, dF, db, ctas, Mrows, nf);
+  conv_c3_df_reduce_kernel<<<(nf * (Mrows + 1) + 31) / 32, dim3(32, 8), 0, s>>>((const float*)ws, dF, db, ctas, Mrows, nf);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;

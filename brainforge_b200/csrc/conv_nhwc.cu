@@ -364,21 +364,41 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
 }
 
 // dF[f][c][tap] = sum_z partial[z][c/32][tap][f][c%32];  db[f] = sum_z partial[z][0][ntaps][f][0]
+// Threads walk the PARTIAL's own order (32 channels innermost), so every split is read with full 128-byte lines;
+// the (small) result is scattered into the reference's (nf, ic, fy, fx) order.
 __global__ void conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
                                            int nsplit, int nch, int ntaps, int nf, int ic) {
-  const long total = (long)nf * ic * ntaps + nf;
+  const long nmain = (long)nch * ntaps * nf * 32, total = nmain + nf;
+  const size_t zstride = (size_t)nch * (ntaps + 1) * 128 * 32;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
-    const bool is_db = i >= (long)nf * ic * ntaps;
-    int f, c, tap;
-    if (is_db) { f = (int)(i - (long)nf * ic * ntaps); c = 0; tap = ntaps; }
-    else { tap = (int)(i % ntaps); long r = i / ntaps; c = (int)(r % ic); f = (int)(r / ic); }
-    const size_t off = ((size_t)(c >> 5) * (ntaps + 1) + tap) * 128 * 32 + (size_t)f * 32 + (c & 31);
-    const size_t zstride = (size_t)nch * (ntaps + 1) * 128 * 32;
-    float s = 0.f;
-    for (int z = 0; z < nsplit; ++z) s += partial[z * zstride + off];
-    if (is_db) { if (db) db[f] = s; }
-    else dF[i] = s;
+    size_t off;
+    long dst;
+    if (i < nmain) {
+      const int cl = (int)(i & 31);
+      long r = i >> 5;
+      const int f = (int)(r % nf);
+      r /= nf;
+      const int tap = (int)(r % ntaps), ch = (int)(r / ntaps);
+      off = ((size_t)(ch * (ntaps + 1) + tap) * 128 + f) * 32 + cl;
+      dst = ((long)f * ic + ch * 32 + cl) * ntaps + tap;
+    } else {
+      const int f = (int)(i - nmain);
+      off = ((size_t)ntaps * 128 + f) * 32;
+      dst = -1 - f;
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+    for (; z + 4 <= nsplit; z += 4) {
+      s0 += partial[(size_t)z * zstride + off];
+      s1 += partial[(size_t)(z + 1) * zstride + off];
+      s2 += partial[(size_t)(z + 2) * zstride + off];
+      s3 += partial[(size_t)(z + 3) * zstride + off];
+    }
+    for (; z < nsplit; ++z) s0 += partial[(size_t)z * zstride + off];
+    const float sum = (s0 + s1) + (s2 + s3);
+    if (dst >= 0) dF[dst] = sum;
+    else if (db) db[-1 - dst] = sum;
   }
 }
 
