@@ -202,6 +202,31 @@ class ConvolutionOp:
         return _ret(A, out)
 
     @staticmethod
+    def forward_pool(A, F, bias=None, activation="linear", relu_in=False):
+        """valid convolution (+ bias) -> [ReLU] -> 2x2 max pooling in ONE kernel, for the first-layer (ic <= 4) route:
+        returns (pooled, mask) exactly as `MaxPoolOp.forward([relu](ConvolutionOp.forward(A, F, bias=..)), 2)` would,
+        without the full-resolution activation ever reaching HBM; None when the shape cannot take the fused kernel."""
+        a, f = as_device(A), as_device(F)
+        im, ic, iy, ix = a.shape
+        nf, fc, fy, fx = f.shape
+        if fc != ic or a.nhwc or ConvolutionOp._route(False, ic, iy, ix, nf, fy, fx, "valid", activation) != "c3":
+            return None
+        oy, ox = iy - fy + 1, ix - fx + 1
+        if oy % 2 or ox % 2 or (128 // ix) < 2:
+            return None
+        import torch
+        bd = as_device(bias).reshape(-1) if bias is not None else None
+        pooled = DeviceArray.empty_nhwc(im, nf, oy // 2, ox // 2)
+        words = torch.empty(max(pooled.size, 1), dtype=torch.uint8, device="cuda")
+        try:
+            call(L.bf_conv_c3_forward_pool, a.ptr, f.ptr, bd.ptr if bd is not None else _NULL, pooled.pptr,
+                 ctypes.c_void_p(words.data_ptr()), im, ic, iy, ix, nf, fy, fx, _lib.ACT[activation], 1 if relu_in else 0,
+                 stream_ptr())
+        except _lib.Unsupported:
+            return None
+        return pooled, PoolMask(words, (im, nf, oy, ox), 2, nhwc=True)
+
+    @staticmethod
     def valid(A, F):
         return ConvolutionOp.forward(A, F, "valid")
 

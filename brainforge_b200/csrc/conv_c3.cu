@@ -19,12 +19,23 @@
 
 namespace bf {
 
-constexpr int C3_THREADS = 352;       // warp 0 TMA, warp 1 MMA, warp 2 spare, warps 3-6 / 7-10 epilogue of the even / odd tiles
+constexpr int C3_GROUPS = 4;          // epilogue groups of four warps; group g drains accumulator set g (tiles it = g mod 4)
+constexpr int C3_THREADS = 96 + C3_GROUPS * 128;   // warp 0 loads, warps 1-2 MMA (even / odd tiles), then the epilogue groups
 constexpr int C3_STAGE_LD = 36;
-constexpr int C3_STAGING_BYTES = 2 * 4 * 32 * C3_STAGE_LD * 4;
+constexpr int C3_STAGING_BYTES = C3_GROUPS * 4 * 32 * C3_STAGE_LD * 4;
+
+// 1-D bulk copy global -> shared (16-byte aligned on both sides, size a multiple of 16), completes on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct C3FwdParams {
   int nimg, IR, ix, oy, ox, RT, tiles_per_img, ntiles, fy, fx, ic, N, box_rows, na;
+  int pool_relu;            // POOL variant: apply max(0,.) before pooling (the Activation("relu") layer in between)
+  uint8_t* mask;            // POOL variant: 2x2 tie mask, one byte per pooled element, (im, oy/2, ox/2, N)
+  const float4* X4;         // the pixel stream (channel-padded channels-last copy of the input)
+  long long npix;           // pixels in X4
 };
 
 // NCHW (im, ic, iy*ix) -> (im*iy*ix, 4): channel-padded channels-last copy of the input
@@ -34,17 +45,23 @@ __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ X, float4* __rest
     const long b = i / plane;
     const int q = (int)(i - b * plane);
     const float* src = X + b * ic * plane + q;
-    float4 v = make_float4(src[0], ic > 1 ? src[plane] : 0.f, ic > 2 ? src[2 * (long)plane] : 0.f, ic > 3 ? src[3 * (long)plane] : 0.f);
+    // rounded to TF32 here (round-to-nearest; the MMA alone would truncate): the stream is only ever an MMA operand
+    float4 v = make_float4(__uint_as_float(to_tf32(src[0])), ic > 1 ? __uint_as_float(to_tf32(src[plane])) : 0.f,
+                           ic > 2 ? __uint_as_float(to_tf32(src[2 * (long)plane])) : 0.f,
+                           ic > 3 ? __uint_as_float(to_tf32(src[3 * (long)plane])) : 0.f);
     X4[i] = v;
   }
 }
 
-template <int NB, bool RELU>
+// POOL: the epilogue max-pools 2x2 windows of the tile (staged in shared memory) and writes the pooled tensor + tie
+// mask instead of the convolution output -- ConvLayer -> [ReLU] -> PoolLayer(2) in one pass (layers/tensor.py:28-30,
+// 75-79; atomic/tensor_op.py:93-107): the full-resolution activation never goes to HBM.
+template <int NB, bool RELU, bool POOL>
 __global__ void __launch_bounds__(C3_THREADS, 1)
 conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, const float* __restrict__ F,
                    float* __restrict__ out, const float* __restrict__ bias) {
   extern __shared__ int dyn_smem[];
-  __shared__ __align__(8) uint64_t a_full[8], a_empty[8], t_full[2], t_empty[2];
+  __shared__ __align__(8) uint64_t a_full[32], a_empty[32], t_full[4], t_empty[4];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float sbias[NB];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -58,12 +75,12 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
   const int n0 = blockIdx.y * NB;
 
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 32; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < NB) sbias[tid] = bias ? bias[n0 + tid] : 0.f;
@@ -90,16 +107,24 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
       const int b = tile / p.tiles_per_img, t = tile - b * p.tiles_per_img;
       if (au > 0) mbar_wait(&a_empty[as], (uint32_t)((au - 1) & 1));
       if (leader) {
-        mbar_expect_tx(&a_full[as], a_slot);
-        tma_load_2d(base + as * a_slot, &mapX, &a_full[as], 0, b * p.IR + t * p.RT * p.ix);
+        // the tile's pixels + halo are ONE contiguous run of the stream: a 1-D bulk copy (a tensor box with a
+        // 16-byte inner extent is serviced row by row and was the bottleneck of this kernel)
+        const long long px0 = (long long)b * p.IR + (long long)t * p.RT * p.ix;
+        long long npx = p.box_rows;
+        if (px0 + npx > p.npix) npx = p.npix - px0;
+        mbar_expect_tx(&a_full[as], (uint32_t)npx * 16u);
+        bulk_load_1d(base + as * a_slot, p.X4 + px0, (uint32_t)npx * 16u, &a_full[as]);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
+    // two issuing warps, one per accumulator set (even / odd tiles): a single thread issues a K=8 MMA only every
+    // ~50-100 cycles, which at 2*fy MMAs per 128-position tile was the limit of this kernel
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = idesc_tf32(128, NB);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int as = it % p.na, au = it / p.na, acc_set = it & 1, tu = it >> 1;
+      if ((it & 1) != warp - 1) continue;
+      const int as = it % p.na, au = it / p.na, acc_set = it & 3, tu = it >> 2;   // each MMA warp / epilogue group pair owns two sets
       if (tu > 0) mbar_wait(&t_empty[acc_set], (uint32_t)((tu - 1) & 1));
       mbar_wait(&a_full[as], (uint32_t)(au & 1));
       tc_fence_after();
@@ -118,16 +143,16 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
       }
     }
   } else if (warp >= 3) {
-    // two epilogue groups of four warps (one warp per TMEM lane quadrant): group g drains accumulator g, i.e. the
-    // even / odd tiles, so that the drain of one tile overlaps the drain of the next
+    // C3_GROUPS epilogue groups of four warps (one warp per TMEM lane quadrant): group g drains accumulator set g,
+    // so that the drains of consecutive tiles overlap (one drain is a serial TMEM -> shared -> global chain)
     const int quad = warp & 3, grp = (warp - 3) >> 2;
     float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + (grp * 4 + quad) * 32 * C3_STAGE_LD;
     int it = 0;
     const int m = quad * 32 + lane;
     const int r = m / p.ix, x = m - r * p.ix;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      const int acc_set = it & 1, tu = it >> 1;
+      if ((it & 3) != grp) continue;
+      const int acc_set = it & 3, tu = it >> 2;
       const int b = tile / p.tiles_per_img, t = tile - b * p.tiles_per_img;
       const int y = t * p.RT + r;
       const bool ok = r < p.RT && x < p.ox && y < p.oy;
@@ -135,7 +160,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
       const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
       mbar_wait(&t_full[acc_set], (uint32_t)(tu & 1));
       tc_fence_after();
-      if (okmask != 0u) {
+      if (POOL || okmask != 0u) {
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc_set * NB;
 #pragma unroll
         for (int cb = 0; cb < NB; cb += 32) {
@@ -151,19 +176,51 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
                                      __uint_as_float(v[j + 3]));
               if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
               o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              if (POOL && p.pool_relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
               *reinterpret_cast<float4*>(stg + lane * C3_STAGE_LD + c0 + j) = o;
             }
           }
-          __syncwarp();
+          if (POOL) {
+            // the four warps of the group have staged the whole tile [128 positions][32 channels]
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            const float* tile_stg = stg - quad * 32 * C3_STAGE_LD;
+            const int pw = p.ox >> 1, npool = (p.RT >> 1) * pw, poy = p.oy >> 1;
+            for (int item = quad * 32 + lane; item < npool * 8; item += 128) {
+              const int q = item & 7, pp = item >> 3;
+              const int py = pp / pw, pxx = pp - py * pw;
+              const int yg = t * p.RT + 2 * py;                    // first conv row of the window
+              if (yg + 1 < p.oy) {
+                const float* s00 = tile_stg + (2 * py * p.ix + 2 * pxx) * C3_STAGE_LD + q * 4;
+                const float4 a = *reinterpret_cast<const float4*>(s00);
+                const float4 bq = *reinterpret_cast<const float4*>(s00 + C3_STAGE_LD);
+                const float4 c = *reinterpret_cast<const float4*>(s00 + p.ix * C3_STAGE_LD);
+                const float4 d = *reinterpret_cast<const float4*>(s00 + (p.ix + 1) * C3_STAGE_LD);
+                float4 mx;
+                mx.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(c.x, d.x)); mx.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(c.y, d.y));
+                mx.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(c.z, d.z)); mx.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(c.w, d.w));
+                uchar4 mk;
+                mk.x = (unsigned char)((a.x == mx.x) | ((bq.x == mx.x) << 1) | ((c.x == mx.x) << 2) | ((d.x == mx.x) << 3));
+                mk.y = (unsigned char)((a.y == mx.y) | ((bq.y == mx.y) << 1) | ((c.y == mx.y) << 2) | ((d.y == mx.y) << 3));
+                mk.z = (unsigned char)((a.z == mx.z) | ((bq.z == mx.z) << 1) | ((c.z == mx.z) << 2) | ((d.z == mx.z) << 3));
+                mk.w = (unsigned char)((a.w == mx.w) | ((bq.w == mx.w) << 1) | ((c.w == mx.w) << 2) | ((d.w == mx.w) << 3));
+                const size_t o = ((size_t)(b * poy + (yg >> 1)) * pw + pxx) * p.N + n0 + cb + q * 4;
+                *reinterpret_cast<float4*>(out + o) = mx;
+                *reinterpret_cast<uchar4*>(p.mask + o) = mk;
+              }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // staging is rewritten by the next block / tile
+          } else {
+            __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + (lane >> 3);
-            const int dst_row = __shfl_sync(0xffffffffu, orow, rr);
-            const float4 val = *reinterpret_cast<const float4*>(stg + rr * C3_STAGE_LD + (lane & 7) * 4);
-            if ((okmask >> rr) & 1u)
-              *reinterpret_cast<float4*>(out + (size_t)dst_row * p.N + n0 + cb + (lane & 7) * 4) = val;
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3);
+              const int dst_row = __shfl_sync(0xffffffffu, orow, rr);
+              const float4 val = *reinterpret_cast<const float4*>(stg + rr * C3_STAGE_LD + (lane & 7) * 4);
+              if ((okmask >> rr) & 1u)
+                *reinterpret_cast<float4*>(out + (size_t)dst_row * p.N + n0 + cb + (lane & 7) * 4) = val;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       tc_fence_before();
@@ -173,7 +230,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 // --------------------------------------------------------------------------------------------- dF + db
@@ -198,11 +255,6 @@ struct C3DfParams {
   long long x_total_f;
   int a_tail_bytes;
 };
-
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 template <int MH, int NR>
 __global__ void __launch_bounds__(C3DF_THREADS, 1)
@@ -441,13 +493,8 @@ using namespace bf;
 
 int bf_conv_c3_supported(int ic, int iy, int ix, int nf, int fy, int fx) { return conv_c3_supported(ic, iy, ix, nf, fy, fx) ? 1 : 0; }
 
-// Y (im,oy,ox,nf) NHWC = act(valid_corr(X (im,ic,iy,ix) NCHW, F)) + bias
-int bf_conv_c3_forward(const float* X, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix, int nf,
-                       int fy, int fx, int act, void* stream) {
-  BF_REQUIRE(conv_c3_supported(ic, iy, ix, nf, fy, fx), BF_ERR_ARG, "bf_conv_c3_forward: unsupported shape");
-  BF_REQUIRE(act == BF_ACT_LINEAR || act == BF_ACT_RELU, BF_ERR_ARG, "bf_conv_c3_forward: only linear / relu are fused");
-  if (im <= 0) return BF_OK;
-  cudaStream_t s = as_stream(stream);
+static int c3_forward_impl(const float* X, const float* F, const float* bias, float* Y, uint8_t* mask, int pool, int pool_relu,
+                           int im, int ic, int iy, int ix, int nf, int fy, int fx, int act, cudaStream_t s) {
   const int oy = iy - fy + 1, ox = ix - fx + 1, IR = iy * ix;
   BF_REQUIRE((long)im * IR < 2147483647L, BF_ERR_ARG, "bf_conv_c3_forward: too many pixels");
   void* ws = nullptr;
@@ -457,8 +504,16 @@ int bf_conv_c3_forward(const float* X, const float* F, const float* bias, float*
   BF_LAUNCH_CHECK();
   C3FwdParams p;
   p.nimg = im; p.IR = IR; p.ix = ix; p.oy = oy; p.ox = ox; p.RT = 128 / ix; if (p.RT > oy) p.RT = oy;
+  if (pool) {
+    p.RT &= ~1;              // tiles start on even rows and hold whole 2x2 windows
+    BF_REQUIRE(p.RT >= 2 && (oy & 1) == 0 && (ox & 1) == 0, BF_ERR_ARG, "bf_conv_c3_forward_pool: plane %dx%d cannot be pooled in-tile", oy, ox);
+  }
   p.tiles_per_img = (oy + p.RT - 1) / p.RT; p.ntiles = im * p.tiles_per_img; p.fy = fy; p.fx = fx; p.ic = ic; p.N = nf;
-  p.box_rows = (128 + (fy - 1) * ix + 4 + 7) / 8 * 8; p.na = 8;
+  p.box_rows = (128 + (fy - 1) * ix + 4 + 7) / 8 * 8;
+  p.na = getenv("BF_C3_NA") ? atoi(getenv("BF_C3_NA")) : 24;   // tiles in flight: the loads are small (3 KB), latency-bound
+  while (p.na > 4 && (size_t)p.na * p.box_rows * 16 > 96 * 1024) --p.na;
+  p.pool_relu = pool_relu; p.mask = mask;
+  p.X4 = (const float4*)ws; p.npix = (long long)im * IR;
   CUtensorMap mX;
   {
     uint64_t dims[2] = {4, (uint64_t)im * IR};
@@ -470,21 +525,42 @@ int bf_conv_c3_forward(const float* X, const float* F, const float* bias, float*
   const size_t smem = 1024 + (size_t)p.na * p.box_rows * 16 + (size_t)nf * fy * 16 * 4 + 128 + C3_STAGING_BYTES;
   const int ctas = p.ntiles < num_sms() ? p.ntiles : num_sms();
   const bool relu = act == BF_ACT_RELU;
-#define BF_C3_CASE(NB_)                                                                                                  \
-  if (nf == NB_) {                                                                                                       \
-    if (relu) {                                                                                                          \
-      BF_CUDA(cudaFuncSetAttribute(conv_c3_fwd_kernel<NB_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-      conv_c3_fwd_kernel<NB_, true><<<ctas, C3_THREADS, smem, s>>>(mX, p, F, Y, bias);                                   \
-    } else {                                                                                                             \
-      BF_CUDA(cudaFuncSetAttribute(conv_c3_fwd_kernel<NB_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      conv_c3_fwd_kernel<NB_, false><<<ctas, C3_THREADS, smem, s>>>(mX, p, F, Y, bias);                                  \
-    }                                                                                                                    \
+#define BF_C3_LAUNCH(NB_, R_, P_)                                                                                           \
+  {                                                                                                                         \
+    BF_CUDA(cudaFuncSetAttribute(conv_c3_fwd_kernel<NB_, R_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_c3_fwd_kernel<NB_, R_, P_><<<ctas, C3_THREADS, smem, s>>>(mX, p, F, Y, bias);                                      \
+  }
+#define BF_C3_CASE(NB_)                                                                              \
+  if (nf == NB_) {                                                                                   \
+    if (pool) { if (relu) BF_C3_LAUNCH(NB_, true, true) else BF_C3_LAUNCH(NB_, false, true) }        \
+    else { if (relu) BF_C3_LAUNCH(NB_, true, false) else BF_C3_LAUNCH(NB_, false, false) }           \
   }
   BF_C3_CASE(32) BF_C3_CASE(64) BF_C3_CASE(128)
 #undef BF_C3_CASE
+#undef BF_C3_LAUNCH
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;
+}
+
+// Y (im,oy,ox,nf) NHWC = act(valid_corr(X (im,ic,iy,ix) NCHW, F)) + bias
+int bf_conv_c3_forward(const float* X, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix, int nf,
+                       int fy, int fx, int act, void* stream) {
+  BF_REQUIRE(conv_c3_supported(ic, iy, ix, nf, fy, fx), BF_ERR_ARG, "bf_conv_c3_forward: unsupported shape");
+  BF_REQUIRE(act == BF_ACT_LINEAR || act == BF_ACT_RELU, BF_ERR_ARG, "bf_conv_c3_forward: only linear / relu are fused");
+  if (im <= 0) return BF_OK;
+  return c3_forward_impl(X, F, bias, Y, nullptr, 0, 0, im, ic, iy, ix, nf, fy, fx, act, as_stream(stream));
+}
+
+// P (im,oy/2,ox/2,nf), mask = maxpool2x2( [relu]( act(valid_corr(X, F)) + bias ) ): the convolution output itself is never
+// written.  relu_in != 0: an Activation("relu") layer sits between the convolution and the pooling layer.
+int bf_conv_c3_forward_pool(const float* X, const float* F, const float* bias, float* P, uint8_t* mask, int im, int ic, int iy,
+                            int ix, int nf, int fy, int fx, int act, int relu_in, void* stream) {
+  BF_REQUIRE(conv_c3_supported(ic, iy, ix, nf, fy, fx), BF_ERR_ARG, "bf_conv_c3_forward_pool: unsupported shape");
+  BF_REQUIRE(act == BF_ACT_LINEAR || act == BF_ACT_RELU, BF_ERR_ARG, "bf_conv_c3_forward_pool: only linear / relu are fused");
+  BF_REQUIRE(P && mask, BF_ERR_ARG, "bf_conv_c3_forward_pool: null pointer");
+  if (im <= 0) return BF_OK;
+  return c3_forward_impl(X, F, bias, P, mask, 1, relu_in ? 1 : 0, im, ic, iy, ix, nf, fy, fx, act, as_stream(stream));
 }
 
 // dF (nf,ic,fy,fx), db (nf) from X (im,ic,iy,ix) NCHW and E (im,oy,ox,nf) NHWC

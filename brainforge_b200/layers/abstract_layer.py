@@ -86,8 +86,14 @@ class LayerBase(abc.ABC):
         return self.weights.size + self.biases.size
 
     # ---- compute: host arrays in -> host float64 out; DeviceArray in -> DeviceArray out
+    _standalone = False    # True while a layer is driven on its own through feedforward(): no cross-layer fusion
+
     def feedforward(self, X):
-        out = self._fwd(as_device(X))
+        self._standalone = True
+        try:
+            out = self._fwd(as_device(X))
+        finally:
+            self._standalone = False
         return out if isinstance(X, DeviceArray) else out.numpy()
 
     def backpropagate(self, delta):

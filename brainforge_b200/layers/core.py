@@ -42,17 +42,22 @@ class Activation(NoParamMixin, LayerBase):
     """layers/core.py:45-59."""
 
     _next_layer = None     # set by LayerStack.add: lets relu hand its pass to a following PoolLayer
-    _lazy_input = None
+    _lazy_src = None       # callable -> the pre-activation array, when this layer moved no bytes
 
     def _fwd(self, x):
-        self._lazy_input = None
+        self._lazy_src = None
+        if type(x).__name__ == "FusedConvPool":
+            # the convolution kernel upstream already applied max(0,.) and pooled (layers/tensor.py ConvLayer._fwd)
+            conv = x.conv
+            self._lazy_src, self._output = (lambda: conv.output), None
+            return x
         if str(self.activation) == "linear":
             self._output = x
-        elif (str(self.activation) == "relu" and x.nhwc and type(self._next_layer).__name__ == "PoolLayer"
-              and self._next_layer.fdim <= 2):
+        elif (str(self.activation) == "relu" and x.nhwc and not self._standalone
+              and type(self._next_layer).__name__ == "PoolLayer"):
             # channels-last conv block: the pooling kernel applies max(0,.) while it reads (and relu' while it
             # scatters), so this layer moves no bytes.  `self.output` is materialised only if somebody reads it.
-            self._lazy_input, self._output = x, None
+            self._lazy_src, self._output = (lambda: x), None
             y = DeviceArray(x.t, nhwc=True)
             y.pending_relu = True
             return y
@@ -62,8 +67,8 @@ class Activation(NoParamMixin, LayerBase):
 
     @property
     def output(self):
-        if self._output is None and self._lazy_input is not None:
-            self._output = self.activation.forward(self._lazy_input)
+        if self._output is None and self._lazy_src is not None:
+            self._output = self.activation.forward(self._lazy_src())
         return self._output
 
     @output.setter
@@ -71,11 +76,9 @@ class Activation(NoParamMixin, LayerBase):
         self._output = value
 
     def _bwd(self, delta):
-        if self._lazy_input is not None:
-            if getattr(delta, "relu_applied", False):
-                return delta
-            return self.activation.backward_mul(self.output, delta)
-        return self.activation.backward_mul(self._output, delta)
+        if self._lazy_src is not None and getattr(delta, "relu_applied", False):
+            return delta
+        return self.activation.backward_mul(self.output, delta)
 
     @property
     def outshape(self):

@@ -6,6 +6,14 @@ from ..util import white
 from .abstract_layer import LayerBase, NoParamMixin
 
 
+class FusedConvPool:
+    """What a ConvLayer hands downstream when its kernel has already done the [ReLU ->] 2x2 pooling that follows it:
+    the pooled tensor and tie mask, plus the way back to the (never materialised) convolution output."""
+
+    def __init__(self, conv, pooled, mask, relu_in):
+        self.conv, self.pooled, self.mask, self.relu_in = conv, pooled, mask, relu_in
+
+
 class PoolLayer(NoParamMixin, LayerBase):
     """layers/tensor.py:7-40."""
 
@@ -24,6 +32,10 @@ class PoolLayer(NoParamMixin, LayerBase):
         self._outshape = (ic, iy // self.fdim, ix // self.fdim)
 
     def _fwd(self, x):
+        if isinstance(x, FusedConvPool):      # the convolution kernel pooled its own tile (ConvLayer._fwd)
+            self._fused_relu = x.relu_in
+            self.output, self.filter = x.pooled, x.mask
+            return self.output
         # a channels-last input flagged `pending_relu` comes from an Activation("relu") layer that left its
         # max(0,.) to this layer's kernel (layers/core.py Activation._fwd): one pass instead of two
         self._fused_relu = bool(getattr(x, "pending_relu", False))
@@ -73,19 +85,53 @@ class ConvLayer(LayerBase):
         self._init_params(white(self.nfilters, self.depth, self.fx, self.fy),
                           np.zeros((1, self.nfilters, 1, 1)))
 
+    fuse_pool = True     # class-wide switch: let the first-layer kernel absorb a following [ReLU ->] PoolLayer(2)
+
+    def _pool_after(self):
+        """(PoolLayer, relu_in) when this layer's output is consumed only by [Activation("relu") ->] PoolLayer(2)."""
+        nxt = getattr(self, "_next_layer", None)
+        if isinstance(nxt, PoolLayer) and nxt.fdim == 2:
+            return nxt, False
+        if type(nxt).__name__ == "Activation" and str(nxt.activation) == "relu":
+            nn = getattr(nxt, "_next_layer", None)
+            if isinstance(nn, PoolLayer) and nn.fdim == 2:
+                return nn, True
+        return None, False
+
     def _fwd(self, x):
         im, ic, iy, ix = x.shape
-        if not x.nhwc and self.op._route(False, ic, iy, ix, self.nfilters, self.fy, self.fx, "valid",
-                                         str(self.activation)) == "nhwc":
+        route = self.op._route(x.nhwc, ic, iy, ix, self.nfilters, self.fy, self.fx, "valid", str(self.activation))
+        if not x.nhwc and route == "nhwc":
             x = x.to_nhwc()          # converted once here, reused by the filter gradient
         self.inputs = x
-        self.output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation))
-        return self.output
+        self._output = None
+        if self.fuse_pool and not self._standalone and route == "c3" and str(self.activation) == "linear":
+            pool, relu_in = self._pool_after()
+            if pool is not None:
+                fused = self.op.forward_pool(x, self.weights, bias=self.biases, relu_in=relu_in)
+                if fused is not None:
+                    # the convolution output is not materialised; `self.output` re-runs the plain kernel on demand
+                    return FusedConvPool(self, fused[0], fused[1], relu_in)
+        self._output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation))
+        return self._output
+
+    @property
+    def output(self):
+        if self._output is None and self.inputs is not None:
+            # fused path: recomputed from the cached inputs and the CURRENT weights (exact until the next update)
+            self._output = self.op.forward(self.inputs, self.weights, "valid", bias=self.biases,
+                                           activation=str(self.activation))
+        return self._output
+
+    @output.setter
+    def output(self, value):
+        self._output = value
 
     _can_skip_dx = True
 
     def _bwd(self, delta, need_dX=True):
-        delta = self.activation.backward_mul(self.output, delta)
+        if str(self.activation) != "linear":
+            delta = self.activation.backward_mul(self.output, delta)
         _, _, dX = self.op.backward(X=self.inputs, E=delta, F=self.weights, dF=self.nabla_w, db=self.nabla_b,
                                     need_dX=need_dX)
         return dX

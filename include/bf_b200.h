@@ -127,6 +127,13 @@ BF_API int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* d
 BF_API int bf_conv_c3_supported(int ic, int iy, int ix, int nf, int fy, int fx);
 BF_API int bf_conv_c3_forward(const float* X, const float* F, const float* bias, float* Y, int im, int ic, int iy, int ix,
                        int nf, int fy, int fx, int act, void* stream);
+/* Convolution + [ReLU] + 2x2 max pooling in one pass: P (im,oy/2,ox/2,nf) and the tie mask (one byte per pooled
+ * element, bits as in bf_pool_nhwc_forward) = MaxPoolOp.forward( [relu]( act(corr(X,F)) + bias ), 2 ), i.e.
+ * ConvLayer -> [Activation("relu")] -> PoolLayer(2) (layers/tensor.py:28-30,75-79; layers/core.py:47-49).  The
+ * full-resolution convolution output is never written to HBM (the host re-runs bf_conv_c3_forward if a caller reads
+ * ConvLayer.output).  Needs an even output plane. */
+BF_API int bf_conv_c3_forward_pool(const float* X, const float* F, const float* bias, float* P, uint8_t* mask, int im, int ic,
+                            int iy, int ix, int nf, int fy, int fx, int act, int relu_in, void* stream);
 BF_API int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix,
                                int nf, int fy, int fx, void* stream);
 

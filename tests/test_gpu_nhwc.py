@@ -116,6 +116,29 @@ def test_conv_routes_to_tma_kernels(bf, O, shape):
         close(dFd, rF); close(dXd, rX)
 
 
+@pytest.mark.parametrize("shape", [(3, 3, 30, 30, 32, 3, 3), (5, 1, 28, 28, 32, 3, 3), (2, 4, 18, 40, 64, 3, 3), (130, 3, 30, 30, 32, 3, 3),
+                                   (2, 2, 13, 50, 128, 2, 3)])
+@pytest.mark.parametrize("relu_in", [False, True])
+def test_conv_pool_fused_epilogue_bit_exact(bf, O, shape, relu_in):
+    """bf_conv_c3_forward_pool == MaxPoolOp.forward([relu](ConvolutionOp.forward(..)), 2) bit for bit (pooled values
+    and multi-hot tie mask): same MMA sequence, pooling done on the staged tile instead of a second pass over HBM."""
+    im, ic, iy, ix, nf, fy, fx = shape
+    rs = np.random.RandomState(sum(shape))
+    A, F, bias = rs.randn(im, ic, iy, ix), rs.randn(nf, ic, fy, fx) * 0.3, rs.randn(nf)
+    op, pool = bf.atomic.ConvolutionOp(), bf.atomic.MaxPoolOp()
+    a, f, b = bf.DeviceArray.from_host(A), bf.DeviceArray.from_host(F), bf.DeviceArray.from_host(bias)
+    fused = op.forward_pool(a, f, bias=b, relu_in=relu_in)
+    assert fused is not None
+    y = op.forward(a, f, "valid", bias=b)
+    assert y.nhwc
+    ref_out, ref_mask = pool.forward(y, 2, relu_in=relu_in)
+    assert np.array_equal(fused[0].numpy(np.float32), ref_out.numpy(np.float32))
+    assert np.array_equal(np.asarray(fused[1]), np.asarray(ref_mask))
+    yo = O.conv_forward(A, F, "valid") + bias[None, :, None, None]
+    ro, _ = O.maxpool_forward(np.maximum(yo, 0) if relu_in else yo, 2)
+    close(fused[0], ro)
+
+
 def _cfg3(bf, batch, **kw):
     ishape, spec, cost, optimizer = CFG["cfg3"]
     return build_b200(ishape, spec, cost, optimizer, seed=1234, **kw), build_oracle(ishape, spec, cost, optimizer, seed=1234)
