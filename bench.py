@@ -223,6 +223,11 @@ def algorithmic_cost(label):
         im, ic, iy, ix, nf, fy, fx = a[:7]
         oy, ox = iy - fy + 1, ix - fx + 1
         return f * (im * ic * iy * ix + nf * ic * fy * fx + nf + im * nf * oy * ox), 2.0 * im * oy * ox * nf * ic * fy * fx
+    if name == "bf_conv_c3_forward_pool":   # read X, F, bias; write the POOLED output + 1 mask byte per pooled element
+        im, ic, iy, ix, nf, fy, fx = a[:7]
+        oy, ox = iy - fy + 1, ix - fx + 1
+        pooled = im * nf * (oy // 2) * (ox // 2)
+        return f * (im * ic * iy * ix + nf * ic * fy * fx + nf + pooled) + pooled, 2.0 * im * oy * ox * nf * ic * fy * fx
     if name in ("bf_conv_nhwc_backward_filter", "bf_conv_c3_backward_filter", "bf_conv_nhwc_backward_data"):
         im, ic, iy, ix, nf, fy, fx = a[:7]
         oy, ox = iy - fy + 1, ix - fx + 1
@@ -273,6 +278,29 @@ def algorithmic_cost(label):
     return 0, 0.0
 
 
+KERNEL_OF_CALL = {   # C-ABI call -> its dominant kernel, for the kernels that have ONE instance per step (an ncu capture of
+    # the other families is one of several layer shapes and would not match the launch the roofline entry describes)
+    "bf_conv_c3_forward_pool": "conv_c3_fwd_kernel", "bf_conv_c3_forward": "conv_c3_fwd_kernel",
+    "bf_conv_c3_backward_filter": "conv_c3_df_kernel",
+}
+
+
+def measured_traffic(call_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the call's dominant kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (None when that kernel was not captured)."""
+    kern = KERNEL_OF_CALL.get(call_name)
+    pdir = os.path.join(ROOT, "profiles")
+    if kern is None or not os.path.isdir(pdir):
+        return None
+    files = sorted(f for f in os.listdir(pdir) if f.endswith("_traffic.json"))
+    if not files:
+        return None
+    try:
+        return json.load(open(os.path.join(pdir, files[-1]))).get(kern, {}).get("bytes")
+    except Exception:
+        return None
+
+
 def roofline_entry(times, peaks, tf32):
     """times: {label: [ms]} from the instrumented pass.  Picks the call with the largest total time."""
     if not times:
@@ -296,7 +324,8 @@ def roofline_entry(times, peaks, tf32):
         entry = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                  "peak_note": "HBM copy bandwidth, %s" % peaks["source"]}
     entry.update({"kernel": top, "avg_ms": avg_ms, "share_of_step": tot[top] / step_total if step_total else None,
-                  "algorithmic_bytes": nbytes, "algorithmic_flops": flops, "traffic": None,
+                  "algorithmic_bytes": nbytes, "algorithmic_flops": flops,
+                  "traffic": measured_traffic(parse_label(top)[0]),
                   "path": "tcgen05-tf32" if tf32 else "simt-fp32"})
     table = [{"kernel": k, "calls": len(times[k]), "avg_ms": float(np.mean(times[k])),
               "share": tot[k] / step_total if step_total else None} for k in ranked[:12]]
