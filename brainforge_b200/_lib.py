@@ -53,6 +53,7 @@ SIGNATURES = {
     "bf_conv_c3_forward": (_i, [_vp] * 4 + [_i] * 8 + [_vp]),
     "bf_conv_c3_forward_pool": (_i, [_vp] * 5 + [_i] * 9 + [_vp]),
     "bf_conv_c3_backward_filter": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
+    "bf_conv_c3_backward_filter_unpool": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "bf_pool_mask_bytes": (_sz, [_i] * 5),
     "bf_pool_forward": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "bf_pool_backward": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),

@@ -227,6 +227,25 @@ class ConvolutionOp:
         return pooled, PoolMask(words, (im, nf, oy, ox), 2, nhwc=True)
 
     @staticmethod
+    def backward_filter_unpool(X, dP, mask, gate, fshape, dF, db):
+        """Filter gradient of conv -> [relu] -> 2x2 pool taken directly from the pooling layer's delta dP (the
+        un-pooling and the ReLU gate are folded into the kernel's operand construction).  Writes dF / db and returns
+        True, or returns False when the shape cannot take the fused kernel (caller materialises E instead)."""
+        x = as_device(X)
+        im, ic, iy, ix = x.shape
+        nf, fc, fy, fx = fshape
+        if x.nhwc or not mask.nhwc or mask.fdim != 2 or \
+                ConvolutionOp._route(False, ic, iy, ix, nf, fy, fx, "valid", "linear") != "c3":
+            return False
+        dp = as_device(dP).to_nhwc()
+        try:
+            call(L.bf_conv_c3_backward_filter_unpool, x.ptr, dp.pptr, mask.wptr, gate.pptr if gate is not None else _NULL,
+                 dF.ptr, db.ptr, im, ic, iy, ix, nf, fy, fx, stream_ptr(), tag="dF")
+        except _lib.Unsupported:
+            return False
+        return True
+
+    @staticmethod
     def valid(A, F):
         return ConvolutionOp.forward(A, F, "valid")
 

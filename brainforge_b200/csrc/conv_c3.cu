@@ -16,6 +16,7 @@
 #include "tma.cuh"
 #include "conv_nhwc.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace bf {
 
@@ -254,9 +255,21 @@ struct C3DfParams {
   int e_stage_bytes, x_plane_f, x_stage_bytes;
   long long x_total_f;
   int a_tail_bytes;
+  // UNPOOL variant: E is not read from HBM but rebuilt per band from the pooling layer's state
+  const float* dP;          // delta w.r.t. the pooled output   (im, oy/2, ox/2, nf)
+  const float* gate;        // pooled forward output (ReLU gate: delta passes where gate > 0), or null
+  const uint8_t* mask;      // 2x2 tie mask, one byte per pooled element
+  int pool_bytes;           // bytes of dP (= of gate) of one full band; a load stage = [raw rows | dP | gate | mask]
+  int stage_bytes;          // stride of the load ring (x_stage_bytes, + the pooled-resolution state when un-pooling)
 };
 
-template <int MH, int NR>
+// UNPOOL: the E operand (delta w.r.t. the convolution output) is never materialised in HBM: the builder warps
+// scatter `dP * mask * (gate > 0)` -- MaxPoolOp.backward followed by the ReLU layer's derivative
+// (atomic/tensor_op.py:110-119, layers/core.py:51-52) -- straight into the MN-major SWIZZLE_128B/32B-atom tile the
+// MMA reads.  The band's dP / gate / mask slices are contiguous in HBM and arrive by 1-D bulk copies in the load ring.
+// Per band that is 16 KB of reads instead of a 25 KB E box, and the 411 MB write + read of the full-resolution
+// delta disappears.
+template <int MH, int NR, bool UNPOOL>
 __global__ void __launch_bounds__(C3DF_THREADS, 1)
 conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restrict__ X, C3DfParams p, float* __restrict__ partial) {
   extern __shared__ int dyn_smem[];
@@ -266,16 +279,18 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
   constexpr int NF = MH * 32;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  // shared memory: [E tiles: ns load stages (TMA) or na band tiles (UNPOOL)][na band tiles of nkb patch tiles][zeros][raw-row ring]
   const uint32_t e_base = base;
-  const uint32_t a_base = e_base + (uint32_t)p.ns * p.e_stage_bytes;
-  const uint32_t x_base = a_base + (uint32_t)(p.na * p.nkb) * C3DF_A_SLOT + (uint32_t)p.a_tail_bytes;   // two band tiles of nkb k-block tiles
+  const uint32_t a_base = e_base + (uint32_t)(UNPOOL ? p.na : p.ns) * p.e_stage_bytes;
+  const uint32_t zero_base = a_base + (uint32_t)(p.na * p.nkb) * C3DF_A_SLOT;
+  const uint32_t x_base = zero_base + (uint32_t)p.a_tail_bytes;
 
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * NF));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2 + C3DF_BUILDERS); }
+    for (int i = 0; i < 6; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (UNPOOL ? 0 : 2) + C3DF_BUILDERS); }
     for (int i = 0; i < 4; ++i) { mbar_init(&built[i], C3DF_BUILDERS); mbar_init(&afree[i], 2); }
     mbar_init(&done, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -311,7 +326,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       if (leader) {
         int rows_in = p.RB + p.fy - 1;
         if (rows_in > p.iy - y0) rows_in = p.iy - y0;
-        uint32_t bytes = (uint32_t)MH * (uint32_t)p.px_band * 128u;
+        uint32_t bytes = UNPOOL ? 0u : (uint32_t)MH * (uint32_t)p.px_band * 128u;
         uint32_t xb[4];
         long long xo[4];
 #pragma unroll
@@ -326,14 +341,31 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
             bytes += xb[c];
           }
         }
+        uint32_t pb = 0;
+        size_t pe = 0;
+        if (UNPOOL) {
+          int rbp = p.RB;
+          if (rbp > p.oy - y0) rbp = p.oy - y0;
+          pb = (uint32_t)((rbp >> 1) * (p.ox >> 1) * p.nf) * 4u;                                  // bytes of dP of this band
+          pe = ((size_t)b * (p.oy >> 1) + (y0 >> 1)) * (size_t)(p.ox >> 1) * p.nf;                // first pooled element
+          bytes += pb + (p.gate ? pb : 0u) + pb / 4u;
+        }
         mbar_expect_tx(&full[s], bytes);
-        const int px0 = (b * p.oy + y0) * p.ox;
+        const uint32_t st0 = x_base + (uint32_t)s * p.stage_bytes;
+        if (!UNPOOL) {
+          const int px0 = (b * p.oy + y0) * p.ox;
 #pragma unroll
-        for (int h = 0; h < MH; ++h)
-          tma_load_2d(e_base + s * p.e_stage_bytes + h * p.nkb * 4096, &mapE, &full[s], h * 32, px0);
+          for (int h = 0; h < MH; ++h)
+            tma_load_2d(e_base + s * p.e_stage_bytes + h * p.nkb * 4096, &mapE, &full[s], h * 32, px0);
+        }
+        if (UNPOOL) {
+          bulk_load_1d(st0 + p.x_stage_bytes, p.dP + pe, pb, &full[s]);
+          if (p.gate) bulk_load_1d(st0 + p.x_stage_bytes + p.pool_bytes, p.gate + pe, pb, &full[s]);
+          bulk_load_1d(st0 + p.x_stage_bytes + 2 * p.pool_bytes, p.mask + pe, pb / 4u, &full[s]);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c < p.ic) bulk_load_1d(x_base + s * p.x_stage_bytes + c * p.x_plane_f * 4, X + xo[c], xb[c], &full[s]);
+          if (c < p.ic) bulk_load_1d(st0 + c * p.x_plane_f * 4, X + xo[c], xb[c], &full[s]);
       }
     }
   } else if (warp == 1 || warp == 2) {
@@ -344,22 +376,27 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
     int mine = 0;
     for (int it = 0; it < my_units; ++it) {
       const int s = it % p.ns, u = it / p.ns, t = it % p.na, ut = it / p.na;
-      mbar_wait(&full[s], (uint32_t)(u & 1));          // E landed
-      mbar_wait(&built[t], (uint32_t)(ut & 1));        // patch tiles of the band written
+      if (!UNPOOL) mbar_wait(&full[s], (uint32_t)(u & 1));          // E landed
+      mbar_wait(&built[t], (uint32_t)(ut & 1));        // patch tiles (and, UNPOOL, the E tile) of the band written
       tc_fence_after();
       if (leader) {
+        const int unit = blockIdx.x + it * gridDim.x, band = unit % p.nbands;
+        int rb = p.RB;
+        if (rb > p.oy - band * p.RB) rb = p.oy - band * p.RB;
+        const int nkb_eff = (rb * p.ox + 31) >> 5;         // k-blocks that hold pixels of this band
+        const uint32_t e_tile = e_base + (uint32_t)(UNPOOL ? t : s) * p.e_stage_bytes;
         bool any = false;
-        for (int j = wsel; j < p.nkb; j += 2) {
+        for (int j = wsel; j < nkb_eff; j += 2) {
           const uint64_t ad = desc_k_sw128(a_base + (uint32_t)(t * p.nkb + j) * C3DF_A_SLOT);
-          const uint64_t bd = desc_mn_sw128_32b(e_base + s * p.e_stage_bytes + j * 4096, (uint32_t)p.nkb * 4096u, 512u);
+          const uint64_t bd = desc_mn_sw128_32b(e_tile + j * 4096, (uint32_t)p.nkb * 4096u, 512u);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_tf32(tmem + wsel * NF, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 64), idesc, (mine > 0 || ks > 0) ? 1u : 0u);
           ++mine;
           any = true;
         }
-        if (any) { umma_commit(&afree[t]); umma_commit(&empty[s]); }
-        else { mbar_arrive(&afree[t]); mbar_arrive(&empty[s]); }
+        if (any) { umma_commit(&afree[t]); if (!UNPOOL) umma_commit(&empty[s]); }
+        else { mbar_arrive(&afree[t]); if (!UNPOOL) mbar_arrive(&empty[s]); }
       }
       __syncwarp();
     }
@@ -384,7 +421,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
 #pragma unroll
     for (int i = 0; i < 8; ++i) { swz[i] = ((sw ^ i) << 4) + l3; asm volatile("" : "+r"(swz[i])); }
     const uint32_t ones_off = (uint32_t)p.Mrows * 128u + (((sw ^ (uint32_t)(p.Mrows & 7)) << 4) + l3);
-    const uint32_t zero_src = a_base + (uint32_t)(p.na * p.nkb) * C3DF_A_SLOT;     // a_tail_bytes of zeros
+    const uint32_t zero_src = zero_base;     // a_tail_bytes of zeros
     int it = 0;
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
       const int s = it % p.ns, u = it / p.ns, t = it % p.na, ut = it / p.na;
@@ -393,10 +430,14 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       if (rb > p.oy - y0) rb = p.oy - y0;
       const int npx = rb * p.ox;
       const int lead = (y0 * p.ix) & 3;
-      const uint32_t xs = x_base + (uint32_t)s * p.x_stage_bytes;
+      const uint32_t xs = x_base + (uint32_t)s * p.stage_bytes;
+      const int pw = p.ox >> 1, nq = p.nf >> 2;
+      const int nitems = UNPOOL ? (rb >> 1) * pw * nq : 0;      // (pooled pixel of the band, channel quad), quads fastest
+      constexpr int UI = 2;                                     // items per builder thread (host checks the band fits)
       mbar_wait(&full[s], (uint32_t)(u & 1));                       // raw rows landed
       if (ut > 0) mbar_wait(&afree[t], (uint32_t)((ut - 1) & 1));   // MMAs of the band tile's previous use are done
-      for (int j = bw; j < p.nkb; j += C3DF_BUILDERS) {
+      const int nkb_eff = (npx + 31) >> 5;
+      for (int j = bw; j < nkb_eff; j += C3DF_BUILDERS) {
         const int px = j * 32 + lane;
         const bool valid = px < npx;
         const int yy = px / p.ox, xx = px - yy * p.ox;
@@ -409,6 +450,39 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
         for (int r = 0; r < NR; ++r)
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + swz[r & 7] + (uint32_t)(r * 128)), "r"(v[r] + 0x1000u));
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + ones_off), "r"(valid ? 0x3f800000u : 0u));
+      }
+      if (UNPOOL) {
+        const uint32_t e_tile = e_base + (uint32_t)t * p.e_stage_bytes;
+        const uint32_t dp_s = xs + (uint32_t)p.x_stage_bytes, g_s = dp_s + (uint32_t)p.pool_bytes, m_s = g_s + (uint32_t)p.pool_bytes;
+#pragma unroll
+        for (int i = 0; i < UI; ++i) {
+          const int item = (bw * 32 + lane) + i * (C3DF_BUILDERS * 32);
+          if (item < nitems) {
+            uint32_t d0, d1, d2, d3, g0 = 0x3f800000u, g1 = 0x3f800000u, g2 = 0x3f800000u, g3 = 0x3f800000u, mw;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(dp_s + (uint32_t)item * 16u));
+            if (p.gate)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(g0), "=r"(g1), "=r"(g2), "=r"(g3) : "r"(g_s + (uint32_t)item * 16u));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(mw) : "r"(m_s + (uint32_t)item * 4u));
+            // relu'(gate) folded in, then TF32 rounding (+half ulp; the MMA drops the low 13 bits)
+            d0 = __uint_as_float(g0) > 0.f ? d0 + 0x1000u : 0u;
+            d1 = __uint_as_float(g1) > 0.f ? d1 + 0x1000u : 0u;
+            d2 = __uint_as_float(g2) > 0.f ? d2 + 0x1000u : 0u;
+            d3 = __uint_as_float(g3) > 0.f ? d3 + 0x1000u : 0u;
+            const int q = item % nq, pp = item / nq;
+            const int py = pp / pw, pxx = pp - py * pw;
+            const int f0 = q * 4;
+            const uint32_t sub = e_tile + (uint32_t)(f0 >> 5) * (uint32_t)p.nkb * 4096u;
+            const uint32_t chunk = (uint32_t)((f0 & 31) >> 3), inner = (uint32_t)(f0 & 7) * 4u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {           // window element k = dy*2 + dx -> conv-output pixel of the band
+              const int pl = (2 * py + (k >> 1)) * p.ox + 2 * pxx + (k & 1);
+              const uint32_t addr = sub + (uint32_t)pl * 128u + ((chunk ^ (uint32_t)(pl & 3)) << 5) + inner;
+              const uint32_t e0 = (mw >> k) & 1u ? d0 : 0u, e1 = (mw >> (8 + k)) & 1u ? d1 : 0u;
+              const uint32_t e2 = (mw >> (16 + k)) & 1u ? d2 : 0u, e3 = (mw >> (24 + k)) & 1u ? d3 : 0u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(e0), "r"(e1), "r"(e2), "r"(e3));
+            }
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -563,11 +637,9 @@ int bf_conv_c3_forward_pool(const float* X, const float* F, const float* bias, f
   return c3_forward_impl(X, F, bias, P, mask, 1, relu_in ? 1 : 0, im, ic, iy, ix, nf, fy, fx, act, as_stream(stream));
 }
 
-// dF (nf,ic,fy,fx), db (nf) from X (im,ic,iy,ix) NCHW and E (im,oy,ox,nf) NHWC
-int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix, int nf,
-                               int fy, int fx, void* stream) {
-  BF_REQUIRE(conv_c3_supported(ic, iy, ix, nf, fy, fx), BF_ERR_ARG, "bf_conv_c3_backward_filter: unsupported shape");
-  cudaStream_t s = as_stream(stream);
+static int c3_backward_filter_impl(const float* X, const float* E, const float* dP, const uint8_t* mask, const float* gate,
+                                   int unpool, float* dF, float* db, int im, int ic, int iy, int ix, int nf, int fy, int fx,
+                                   cudaStream_t s) {
   const int oy = iy - fy + 1, ox = ix - fx + 1, Mrows = ic * fy * fx;
   if (im <= 0) {
     BF_CUDA(cudaMemsetAsync(dF, 0, (size_t)nf * ic * fy * fx * 4, s));
@@ -575,16 +647,24 @@ int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float*
     return BF_OK;
   }
   const int MH = nf / 32;
-  const int cap_px = nf == 32 ? 224 : nf == 64 ? 128 : 64;     // E stage <= 32 KB
+  const int cap_px = nf == 32 ? 224 : nf == 64 ? 128 : 64;     // E tile <= 32 KB
   const long long x_total = (long long)im * ic * iy * ix;
   BF_REQUIRE(Mrows + 1 <= 32, BF_ERR_ARG, "bf_conv_c3_backward_filter: more than 31 patch rows (ic*fy*fx = %d)", Mrows);
   BF_REQUIRE(((iy * ix) & 3) == 0, BF_ERR_ARG, "bf_conv_c3_backward_filter: plane size %dx%d is not a multiple of 4", iy, ix);
-  BF_REQUIRE(ox <= cap_px && (x_total & 3) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)E & 15) == 0, BF_ERR_ARG,
+  BF_REQUIRE(ox <= cap_px && (x_total & 3) == 0 && ((uintptr_t)X & 15) == 0, BF_ERR_ARG,
              "bf_conv_c3_backward_filter: unsupported plane / alignment");
   BF_REQUIRE((long long)im * oy * ox < 2147483647LL, BF_ERR_ARG, "bf_conv_c3_backward_filter: too many pixels");
   C3DfParams p;
   p.nimg = im; p.ic = ic; p.iy = iy; p.ix = ix; p.oy = oy; p.ox = ox; p.fy = fy; p.fx = fx; p.nf = nf;
   p.RB = cap_px / ox; if (p.RB > oy) p.RB = oy;
+  if (unpool) {
+    p.RB &= ~1;              // bands hold whole 2x2 windows
+    BF_REQUIRE(p.RB >= 2 && (oy & 1) == 0 && (ox & 1) == 0 && ((uintptr_t)dP & 15) == 0 && ((uintptr_t)mask & 3) == 0 &&
+                   ((uintptr_t)gate & 15) == 0 && (p.RB / 2) * (ox / 2) * (nf / 4) <= 2 * C3DF_BUILDERS * 32,
+               BF_ERR_ARG, "bf_conv_c3_backward_filter_unpool: plane %dx%d x %d filters cannot be un-pooled in-band", oy, ox, nf);
+  } else {
+    BF_REQUIRE(((uintptr_t)E & 15) == 0, BF_ERR_ARG, "bf_conv_c3_backward_filter: E is not 16-byte aligned");
+  }
   p.nbands = (oy + p.RB - 1) / p.RB;
   p.nunits = im * p.nbands;
   p.px_band = p.RB * ox;
@@ -595,20 +675,27 @@ int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float*
   p.x_stage_bytes = ic * p.x_plane_f * 4;
   p.x_total_f = x_total;
   p.a_tail_bytes = p.x_stage_bytes > 4096 ? (p.x_stage_bytes + 1023) / 1024 * 1024 : 4096;
-  p.na = 2;                      // band tiles in the patch ring
-  p.ns = 6;
-  auto smem_of = [&](int ns) {
-    return (size_t)1024 + (size_t)ns * p.e_stage_bytes + (size_t)p.na * p.nkb * C3DF_A_SLOT + p.a_tail_bytes + (size_t)ns * p.x_stage_bytes;
+  p.dP = dP; p.gate = gate; p.mask = mask;
+  p.pool_bytes = unpool ? (p.RB / 2) * (ox / 2) * nf * 4 : 0;
+  p.stage_bytes = p.x_stage_bytes + (unpool ? 2 * p.pool_bytes + p.pool_bytes / 4 : 0);
+  // ring depths: na band tiles of patch tiles (+ E tiles when un-pooling), ns load stages (E box + raw rows, or raw rows only)
+  auto smem_of = [&](int ns, int na) {
+    return (size_t)1024 + (size_t)(unpool ? na : ns) * p.e_stage_bytes + (size_t)na * p.nkb * C3DF_A_SLOT + p.a_tail_bytes +
+           (size_t)ns * p.stage_bytes;
   };
-  while (p.ns > 2 && smem_of(p.ns) > 224 * 1024) --p.ns;
-  BF_REQUIRE(smem_of(p.ns) <= 224 * 1024, BF_ERR_ARG, "bf_conv_c3_backward_filter: stage does not fit shared memory");
-  const size_t smem = smem_of(p.ns);
+  p.na = 2;
+  p.ns = 6;
+  while (p.ns > 2 && smem_of(p.ns, p.na) > 224 * 1024) --p.ns;
+  if (smem_of(p.ns, p.na) > 224 * 1024 && p.na > 2) p.na = 2;
+  BF_REQUIRE(smem_of(p.ns, p.na) <= 224 * 1024, BF_ERR_ARG, "bf_conv_c3_backward_filter: stage does not fit shared memory");
+  const size_t smem = smem_of(p.ns, p.na);
   const int ctas = p.nunits < num_sms() ? p.nunits : num_sms();
   void* ws = nullptr;
   int rc = workspace_require(c3_al256((size_t)ctas * (Mrows + 1) * nf * 4), &ws);
   if (rc) return rc;
   CUtensorMap mE;
-  {
+  memset(&mE, 0, sizeof(mE));
+  if (!unpool) {
     uint64_t dims[2] = {(uint64_t)nf, (uint64_t)im * oy * ox};
     uint64_t str[1] = {(uint64_t)nf};
     uint32_t box[2] = {32, (uint32_t)p.px_band};
@@ -616,18 +703,37 @@ int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float*
       return fail(BF_ERR_CUDA, "bf_conv_c3_backward_filter: cuTensorMapEncodeTiled failed (E)");
   }
   const int NR = Mrows <= 12 ? 12 : Mrows <= 20 ? 20 : Mrows <= 27 ? 27 : 31;   // patch rows a builder writes per tile
-#define BF_C3DF_CASE(MH_, NR_)                                                                                          \
-  if (MH == MH_ && NR == NR_) {                                                                                         \
-    BF_CUDA(cudaFuncSetAttribute(conv_c3_df_kernel<MH_, NR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_c3_df_kernel<MH_, NR_><<<ctas, C3DF_THREADS, smem, s>>>(mE, X, p, (float*)ws);                                 \
+#define BF_C3DF_LAUNCH(MH_, NR_, U_)                                                                                          \
+  {                                                                                                                           \
+    BF_CUDA(cudaFuncSetAttribute(conv_c3_df_kernel<MH_, NR_, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    conv_c3_df_kernel<MH_, NR_, U_><<<ctas, C3DF_THREADS, smem, s>>>(mE, X, p, (float*)ws);                                   \
   }
+#define BF_C3DF_CASE(MH_, NR_) \
+  if (MH == MH_ && NR == NR_) { if (unpool) BF_C3DF_LAUNCH(MH_, NR_, true) else BF_C3DF_LAUNCH(MH_, NR_, false) }
   BF_C3DF_CASE(1, 12) BF_C3DF_CASE(1, 20) BF_C3DF_CASE(1, 27) BF_C3DF_CASE(1, 31)
   BF_C3DF_CASE(2, 12) BF_C3DF_CASE(2, 20) BF_C3DF_CASE(2, 27) BF_C3DF_CASE(2, 31)
   BF_C3DF_CASE(4, 12) BF_C3DF_CASE(4, 20) BF_C3DF_CASE(4, 27) BF_C3DF_CASE(4, 31)
 #undef BF_C3DF_CASE
+#undef BF_C3DF_LAUNCH
   BF_LAUNCH_CHECK();
   conv_c3_df_reduce_kernel<<<(nf * (Mrows + 1) + 31) / 32, dim3(32, 8), 0, s>>>((const float*)ws, dF, db, ctas, Mrows, nf);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;
+}
+
+// dF (nf,ic,fy,fx), db (nf) from X (im,ic,iy,ix) NCHW and E (im,oy,ox,nf) NHWC
+int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix, int nf,
+                               int fy, int fx, void* stream) {
+  BF_REQUIRE(conv_c3_supported(ic, iy, ix, nf, fy, fx), BF_ERR_ARG, "bf_conv_c3_backward_filter: unsupported shape");
+  return c3_backward_filter_impl(X, E, nullptr, nullptr, nullptr, 0, dF, db, im, ic, iy, ix, nf, fy, fx, as_stream(stream));
+}
+
+// Same result with E = MaxPoolOp.backward(dP, mask) [* (gate > 0)] formed on the fly (2x2 pooling, channels-last pooled
+// tensors): the filter gradient of ConvLayer -> [Activation("relu")] -> PoolLayer(2) straight from the pooling layer's delta.
+int bf_conv_c3_backward_filter_unpool(const float* X, const float* dP, const uint8_t* mask, const float* gate, float* dF,
+                                      float* db, int im, int ic, int iy, int ix, int nf, int fy, int fx, void* stream) {
+  BF_REQUIRE(conv_c3_supported(ic, iy, ix, nf, fy, fx), BF_ERR_ARG, "bf_conv_c3_backward_filter_unpool: unsupported shape");
+  BF_REQUIRE(im <= 0 || (dP && mask), BF_ERR_ARG, "bf_conv_c3_backward_filter_unpool: null pointer");
+  return c3_backward_filter_impl(X, nullptr, dP, mask, gate, 1, dF, db, im, ic, iy, ix, nf, fy, fx, as_stream(stream));
 }

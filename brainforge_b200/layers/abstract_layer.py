@@ -98,7 +98,11 @@ class LayerBase(abc.ABC):
 
     def backpropagate(self, delta):
         d = as_device(delta) if isinstance(delta, DeviceArray) else DeviceArray.from_host(delta)
-        out = self._bwd(d)
+        self._standalone = True
+        try:
+            out = self._bwd(d)
+        finally:
+            self._standalone = False
         return out if isinstance(delta, DeviceArray) else out.numpy()
 
     @abc.abstractmethod

@@ -77,7 +77,9 @@ class Activation(NoParamMixin, LayerBase):
 
     def _bwd(self, delta):
         if self._lazy_src is not None and getattr(delta, "relu_applied", False):
-            return delta
+            return delta                 # relu' was applied by the pooling scatter (or will be, by the fused un-pool)
+        if type(delta).__name__ == "FusedUnpool":
+            delta = delta.materialize()
         return self.activation.backward_mul(self.output, delta)
 
     @property

@@ -14,6 +14,23 @@ class FusedConvPool:
         self.conv, self.pooled, self.mask, self.relu_in = conv, pooled, mask, relu_in
 
 
+class FusedUnpool:
+    """The delta a PoolLayer sends upstream when the convolution right below it can un-pool inside its own
+    filter-gradient kernel: the pooled-resolution delta plus the pooling state, materialised only if somebody
+    needs the full-resolution array."""
+
+    def __init__(self, pool, delta):
+        self.pool, self.delta = pool, delta
+        self.gate = pool.output if pool._fused_relu else None
+        self.relu_applied = pool._fused_relu
+
+    def materialize(self):
+        dX = self.pool.op.backward(self.delta, self.pool.filter, gate=self.gate)
+        if self.relu_applied:
+            dX.relu_applied = True
+        return dX
+
+
 class PoolLayer(NoParamMixin, LayerBase):
     """layers/tensor.py:7-40."""
 
@@ -32,8 +49,10 @@ class PoolLayer(NoParamMixin, LayerBase):
         self._outshape = (ic, iy // self.fdim, ix // self.fdim)
 
     def _fwd(self, x):
+        self._conv_src = None
         if isinstance(x, FusedConvPool):      # the convolution kernel pooled its own tile (ConvLayer._fwd)
             self._fused_relu = x.relu_in
+            self._conv_src = x.conv
             self.output, self.filter = x.pooled, x.mask
             return self.output
         # a channels-last input flagged `pending_relu` comes from an Activation("relu") layer that left its
@@ -43,6 +62,8 @@ class PoolLayer(NoParamMixin, LayerBase):
         return self.output
 
     def _bwd(self, delta):
+        if getattr(self, "_conv_src", None) is not None and not self._standalone:
+            return FusedUnpool(self, delta)   # the convolution's filter-gradient kernel un-pools on the fly
         if getattr(self, "_fused_relu", False):
             dX = self.op.backward(delta, self.filter, gate=self.output)   # pool' and relu' in one scatter
             dX.relu_applied = True
@@ -130,6 +151,11 @@ class ConvLayer(LayerBase):
     _can_skip_dx = True
 
     def _bwd(self, delta, need_dX=True):
+        if isinstance(delta, FusedUnpool):
+            if not need_dX and str(self.activation) == "linear" and self.op.backward_filter_unpool(
+                    self.inputs, delta.delta, delta.pool.filter, delta.gate, self.weights.shape, self.nabla_w, self.nabla_b):
+                return None
+            delta = delta.materialize()
         if str(self.activation) != "linear":
             delta = self.activation.backward_mul(self.output, delta)
         _, _, dX = self.op.backward(X=self.inputs, E=delta, F=self.weights, dF=self.nabla_w, db=self.nabla_b,

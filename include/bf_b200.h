@@ -137,6 +137,13 @@ BF_API int bf_conv_c3_forward_pool(const float* X, const float* F, const float* 
 BF_API int bf_conv_c3_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix,
                                int nf, int fy, int fx, void* stream);
 
+/* Filter gradient of ConvLayer -> [Activation("relu")] -> PoolLayer(2) straight from the pooling layer's delta: E =
+ * MaxPoolOp.backward(dP, mask) (atomic/tensor_op.py:110-119) [* (gate > 0), layers/core.py:51-52] is formed on the fly
+ * inside the kernel, the full-resolution delta never exists in HBM.  dP, gate (pooled forward output, or NULL for no
+ * ReLU) (im,oy/2,ox/2,nf) channels-last, mask as written by bf_conv_c3_forward_pool / bf_pool_nhwc_forward. */
+BF_API int bf_conv_c3_backward_filter_unpool(const float* X, const float* dP, const uint8_t* mask, const float* gate, float* dF,
+                                      float* db, int im, int ic, int iy, int ix, int nf, int fy, int fx, void* stream);
+
 /* ---- max pooling: atomic/tensor_op.py:78-128, llatomic/lltensor_op.py:43-72 ---- */
 /* Bytes per window of the compact tie mask: 1 when fdim*fdim<=8, else 8 (fdim<=8). */
 BF_API size_t bf_pool_mask_bytes(int im, int ic, int iy, int ix, int fdim);

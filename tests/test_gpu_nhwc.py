@@ -139,6 +139,34 @@ def test_conv_pool_fused_epilogue_bit_exact(bf, O, shape, relu_in):
     close(fused[0], ro)
 
 
+@pytest.mark.parametrize("shape", [(3, 3, 30, 30, 32, 3, 3), (5, 1, 28, 28, 32, 3, 3), (2, 3, 18, 42, 64, 3, 3), (130, 3, 30, 30, 32, 3, 3),
+                                   (2, 2, 13, 50, 128, 2, 3), (7, 3, 12, 12, 32, 3, 3)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_filter_gradient_with_fused_unpool(bf, O, shape, relu):
+    """bf_conv_c3_backward_filter_unpool(X, dP, mask, gate) == conv filter gradient of E = pool'(dP) [* relu'] without E
+    ever existing in HBM: equal to the two-kernel route up to summation order, and to the oracle within the TF32 bound."""
+    im, ic, iy, ix, nf, fy, fx = shape
+    rs = np.random.RandomState(sum(shape) + relu)
+    A, F, bias = rs.randn(im, ic, iy, ix), rs.randn(nf, ic, fy, fx) * 0.3, rs.randn(nf) * 0.1
+    op, pool = bf.atomic.ConvolutionOp(), bf.atomic.MaxPoolOp()
+    a, f, b = bf.DeviceArray.from_host(A), bf.DeviceArray.from_host(F), bf.DeviceArray.from_host(bias)
+    pooled, mask = op.forward_pool(a, f, bias=b, relu_in=relu)
+    dP = rs.randn(*pooled.shape)
+    dPd = bf.DeviceArray.from_host(dP).to_nhwc()
+    gate = pooled if relu else None
+    dF, db = bf.DeviceArray.empty(*F.shape), bf.DeviceArray.empty(1, nf, 1, 1)
+    done = op.backward_filter_unpool(a, dPd, mask, gate, F.shape, dF, db)
+    E = pool.backward(dPd, mask, gate=gate)                       # the materialised route
+    if nf == 128:            # a band of this plane does not fit the in-kernel un-pooling: the caller must fall back
+        assert not done
+        return
+    assert done
+    dF2, db2, _ = op.backward(X=a, E=E, F=f, need_dX=False)
+    close(dF, dF2, 5e-5); close(db, db2, 5e-5)
+    rF, rb, _ = O.conv_backward(A, np.asarray(E), F)              # oracle on the SAME (device-made) E: isolates the kernel
+    close(dF, rF); close(db.numpy().ravel(), rb.ravel())
+
+
 def _cfg3(bf, batch, **kw):
     ishape, spec, cost, optimizer = CFG["cfg3"]
     return build_b200(ishape, spec, cost, optimizer, seed=1234, **kw), build_oracle(ishape, spec, cost, optimizer, seed=1234)
