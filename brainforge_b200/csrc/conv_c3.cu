@@ -8,11 +8,13 @@
 //             stream IS the patch matrix of one filter row: A[m][dx*4 + c] = X4[m + ky*ix + dx][c].  TMA drops
 //             (128 + halo) pixels into shared memory, 2*fy MMAs (K = 8: two pixels x 4 channels) produce 128
 //             output positions x nf filters; no im2col is ever formed (reference: tensor_op.py:9-32).
-//   dF + db:  contraction over pixels.  E arrives by TMA as [pixel][32 filters] = MN-major operand (128B swizzle,
-//             32B atoms), the patch rows (c,ky,kx) x 32 pixels are gathered by four SIMT warps straight from the
-//             NCHW planes (27 coalesced 128-byte row reads per 32 pixels) into a K-major SWIZZLE_128B tile; an
-//             all-ones row yields db.  One accumulator (rows = (c,ky,kx), columns = filters) lives in TMEM for
-//             the whole kernel; CTAs split the pixels, a small kernel adds the partials (tensor_op.py:49-55).
+//   dF + db:  contraction over pixels, in bands of RB output rows.  E is the MN-major operand (128B swizzle, 32B
+//             atoms): either one tensor-TMA box per band, used in place, or -- the un-pooling variant -- rebuilt in
+//             shared memory from the pooling layer's delta, tie mask and output, so that the full-resolution delta
+//             never exists in HBM.  The raw NCHW rows of the band arrive by 1-D bulk copies; eight builder warps turn
+//             them shared->shared into K-major SWIZZLE_128B patch tiles (row (c,ky,kx) x 32 pixels, plus an all-ones
+//             row that yields db).  Two MMA-issuing warps (M = 64) accumulate in TMEM for the whole kernel; CTAs split
+//             the bands, a small kernel adds the per-CTA partials (tensor_op.py:49-55).
 #include "tma.cuh"
 #include "conv_nhwc.cuh"
 #include <stdlib.h>
@@ -245,8 +247,8 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
 //   warps 1-2   MMA issuers: even / odd k-blocks, one TMEM accumulator each (two issuing threads reach twice the
 //               issue rate of one for these small N), four K=8 tcgen05.mma per k-block;
 //   warps 4-7   final epilogue: sum of the two accumulators -> per-CTA partial; a small kernel adds the partials.
-constexpr int C3DF_THREADS = 384;      // warp 0 TMA, 1-2 MMA, 3 TMEM, 4-11 patch-tile builders (4-7 also the epilogue)
-constexpr int C3DF_BUILDERS = 8;
+constexpr int C3DF_BUILDERS = 8;        // 16 measured no faster (un-pooling variant) / slower (TMA variant)
+constexpr int C3DF_THREADS = 128 + C3DF_BUILDERS * 32;      // warp 0 loads, 1-2 MMA, 3 TMEM, then the tile builders (the first four also drain the accumulators)
 constexpr int C3DF_A_SLOT = 32 * 128;     // 32 patch rows per tile; the M=128 descriptor runs on into the next tiles (rows >= 32 of D are never read)
 // after the ring: zeros, >= 4 KB (the M=64 descriptor of the last tile reads 8 KB) and >= one raw stage (source of padding lanes)
 struct C3DfParams {
