@@ -4,6 +4,7 @@
 //   (N x nin) @ (nin x P*nh)      with B read straight out of the genome matrix, (g-0.5)*20 applied on load,
 // followed by a per-individual fused second layer + log-softmax + cross-entropy reduction.
 #include "gemm_umma.cuh"
+#include <stdlib.h>
 
 namespace bf {
 
@@ -85,6 +86,11 @@ fitness_head_kernel(const float* __restrict__ Hbuf, const float* __restrict__ G,
   }
 }
 
+// fitness_tma.cu: the same computation on TMA-fed tcgen05 with the whole network in the epilogue
+bool fitness_tma_supported(int P, int N, int nin, int nh, int nout);
+int fitness_tma(const float* genomes, const float* X, const float* Y, float* fitness, int P, int N, int nin, int nh, int nout,
+                cudaStream_t s);
+
 }  // namespace bf
 
 using namespace bf;
@@ -98,6 +104,8 @@ int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* 
   BF_REQUIRE(nout <= FIT_MAX_OUT, BF_ERR_ARG, "bf_fitness_mlp: nout %d > %d", nout, FIT_MAX_OUT);
   if (P == 0) return BF_OK;
   cudaStream_t s = as_stream(stream);
+  if (precision == BF_PREC_TF32 && fitness_tma_supported(P, N, nin, nh, nout) && getenv("BF_FITNESS_GATHER") == nullptr)
+    return fitness_tma(genomes, X, Y, fitness, P, N, nin, nh, nout, s);
   const long loci = (long)nin * nh + nh + (long)nh * nout + nout;
   size_t per_ind = (size_t)nh * N * sizeof(float);
   size_t have = workspace_bytes();
