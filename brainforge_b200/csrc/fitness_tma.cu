@@ -2,11 +2,10 @@
 // for P genomes the first layers are ONE contraction  H = X (N x nin) @ W1all (nin x P*nh)  on the shared input X.
 //
 //   1. relayout pre-pass: the genome matrix (P, loci) cannot be a TMA operand in place (loci*4 bytes is not a multiple
-//      of 16), so W1 of every genome is written once as Bt[k][p*64 + h] = (g - 0.5)*20 (as_weights, neuroevolution.py:
-//      20-22), hidden units padded to 64, TF32-rounded: a (nin x P*64) matrix with the N index contiguous = the
-//      MN-major B operand.
+//      of 16), so W1 of every genome is written once, transposed, as Bt[p*64 + h][k] = (g - 0.5)*20 (as_weights,
+//      neuroevolution.py:20-22), hidden units padded to 64, TF32-rounded: a (P*64 x nin) K-major B operand.
 //   2. GEMM: CTA tile 256 samples x 128 columns (= 2 genomes), K blocks of 32; A = X through a K-major SWIZZLE_128B
-//      map, B through SWIZZLE_128B/32B-atom boxes; 4-stage TMA ring; two MMA-issuing warps (one per 128-row half);
+//      map, B likewise (MN-major 32-byte-atom boxes measured 3x slower to load); 4-stage TMA ring; two MMA-issuing warps (one per 128-row half);
 //      two accumulator sets in TMEM so that the epilogue of one tile overlaps the MMAs of the next.
 //   3. epilogue = the rest of the network: +b1, sigmoid, the (nh x nout) second layer from shared memory, log-softmax,
 //      -sum(Y * log p) per sample, summed over the tile's rows; per-tile partial sums go to a small buffer that a
@@ -16,10 +15,10 @@
 
 namespace bf {
 
-constexpr int FT_THREADS = 384;      // warp 0 TMA, warps 1-2 MMA (row half 0 / 1), warp 3 TMEM, warps 4-7 / 8-11 epilogue of half 0 / 1
+constexpr int FT_THREADS = 640;      // warp 0 TMA, warps 1-2 MMA (row half 0 / 1), warp 3 TMEM, warps 4-19: four epilogue groups = (row half, genome of the tile)
 constexpr int FT_STAGES = 4;
 constexpr int FT_A_BYTES = 2 * 128 * 128;     // two 128-row halves x 32 k floats
-constexpr int FT_B_BYTES = 4 * 32 * 128;      // four 32-column groups x 32 k rows
+constexpr int FT_B_BYTES = 128 * 128;         // 128 columns (2 genomes x 64 hidden) x 32 k floats, K-major
 constexpr int FT_STAGE_BYTES = FT_A_BYTES + FT_B_BYTES;
 constexpr int FT_HP = 64;                     // hidden units per genome, padded
 constexpr int FT_MAX_OUT = 16;
@@ -33,19 +32,29 @@ struct FtParams {
   float* partial;       // [P][m_passes * 8]
 };
 
-// Bt[k][p*64 + h] = (G[p][k*nh + h] - 0.5) * 20, zero padding for h >= nh and p >= P
-__global__ void fitness_relayout_kernel(const float* __restrict__ G, float* __restrict__ Bt, int P, int Ppad, int nin, int nh, long loci) {
-  const size_t ncol = (size_t)Ppad * FT_HP, total = ncol * nin;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    const size_t k = i / ncol, n = i - k * ncol;
-    const int p = (int)(n >> 6), h = (int)(n & 63);
+// Bt[p*64 + h][k] = (G[p][k*nh + h] - 0.5) * 20, zero padding for h >= nh and p >= P: every genome's (nin x nh) first
+// layer transposed through a padded shared-memory tile, so that the GEMM's B operand is K-major like A
+// (a variant moving 112-row chunks per block with per-element index divisions measured 1.5x slower)
+__global__ void fitness_relayout_kernel(const float* __restrict__ G, float* __restrict__ Bt, int P, int nin, int nh, long loci) {
+  __shared__ float tile[32][33];
+  const int p = blockIdx.z, k0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;     // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int k = k0 + ty + j, h = h0 + tx;
     float v = 0.f;
-    if (p < P && h < nh) v = (__ldg(G + (size_t)p * loci + k * nh + h) - 0.5f) * 20.f;
-    Bt[i] = __uint_as_float(to_tf32(v));
+    if (p < P && k < nin && h < nh) v = (__ldg(G + (size_t)p * loci + (size_t)k * nh + h) - 0.5f) * 20.f;
+    tile[ty + j][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int h = h0 + ty + j, k = k0 + tx;
+    if (k < nin) Bt[((size_t)p * FT_HP + h) * nin + k] = __uint_as_float(to_tf32(tile[tx][ty + j]));
   }
 }
 
+template <int NQ>      // float4 groups of output classes actually computed: nout <= 4*NQ
 __global__ void __launch_bounds__(FT_THREADS, 1)
 fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, FtParams p) {
   extern __shared__ int dyn_smem[];
@@ -61,9 +70,10 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
   if (tid == 0) {
     for (int i = 0; i < FT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 2); mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 2); mbar_init(&t_empty[i], 16); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < 2 * 2 * FT_PARAM_F; i += FT_THREADS) (&sparam[0][0][0])[i] = 0.f;   // padding entries stay zero
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,8 +93,7 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           mbar_expect_tx(&full[s], FT_STAGE_BYTES);
           tma_load_2d(st, &mapA, &full[s], kb * 32, mp * 256);
           tma_load_2d(st + 128 * 128, &mapA, &full[s], kb * 32, mp * 256 + 128);
-#pragma unroll
-          for (int h = 0; h < 4; ++h) tma_load_2d(st + FT_A_BYTES + h * 4096, &mapB, &full[s], nt * 128 + h * 32, kb * 32);
+          tma_load_2d(st + FT_A_BYTES, &mapB, &full[s], kb * 32, nt * 128);
         }
       }
     }
@@ -92,7 +101,7 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // ------------------------------------------------------------------ MMA issuers: warp w owns the rows 128*w.. of the tile
     const bool leader = elect_one_sync();
     const int half = warp - 1;
-    constexpr uint32_t idesc = idesc_tf32(128, 128, false, true);
+    constexpr uint32_t idesc = idesc_tf32(128, 128);
     int g = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int set = it & 1, tu = it >> 1;
@@ -105,10 +114,10 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (leader) {
           const uint32_t st = base + (uint32_t)s * FT_STAGE_BYTES;
           const uint64_t ad = desc_k_sw128(st + (uint32_t)half * 128u * 128u);
-          const uint64_t bd = desc_mn_sw128_32b(st + FT_A_BYTES, 4096u, 512u);
+          const uint64_t bd = desc_k_sw128(st + FT_A_BYTES);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 64), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
           umma_commit(&empty[s]);
         }
       }
@@ -117,59 +126,69 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: the rest of the network, per sample row
-    const int half = (warp - 4) >> 2, quad = warp & 3, gt = (warp - 4) * 32 + lane - half * 128;   // thread index in the group
+    // group = (row half, genome gi of the tile): 128 threads, one TMEM lane quadrant per warp
+    const int grp = (warp - 4) >> 2, half = grp & 1, gi = grp >> 1, quad = warp & 3, gt = quad * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int set = it & 1, tu = it >> 1;
       const int nt = tile / p.m_passes, mp = tile - nt * p.m_passes;
-      // second-layer parameters of the tile's two genomes -> shared memory (as_weights applied), while the MMAs run
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");       // previous tile's readers are done
-      for (int i = gt; i < 2 * FT_PARAM_F; i += 128) {
-        const int gi = i / FT_PARAM_F, j = i - gi * FT_PARAM_F;
-        const int pg = nt * 2 + gi;
-        float v = 0.f;
-        if (pg < p.P) {
-          const float* Gp = p.G + (size_t)pg * p.loci;
-          if (j < FT_HP) { if (j < p.nh) v = (Gp[(size_t)p.nin * p.nh + j] - 0.5f) * 20.f; }                       // b1
-          else if (j < FT_HP + FT_HP * FT_MAX_OUT) {
-            const int h = (j - FT_HP) / FT_MAX_OUT, c = (j - FT_HP) % FT_MAX_OUT;
-            if (h < p.nh && c < p.nout) v = (Gp[(size_t)p.nin * p.nh + p.nh + (size_t)h * p.nout + c] - 0.5f) * 20.f;   // W2
-          } else {
-            const int c = j - FT_HP - FT_HP * FT_MAX_OUT;
-            if (c < p.nout) v = (Gp[(size_t)p.nin * p.nh + p.nh + (size_t)p.nh * p.nout + c] - 0.5f) * 20.f;           // b2
-          }
-        }
-        sparam[half][gi][j] = v;
+      const int pg = nt * 2 + gi;
+      // second-layer parameters of the group's genome -> shared memory (as_weights applied), while the MMAs run
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // previous tile's readers are done
+      // (b1 | W2 | b2 are one contiguous run of nh + nh*nout + nout loci behind W1: coalesced reads, scattered into the
+      // padded [b1 64 | W2 64x16 | b2 16] layout)
+      const int ntail = p.nh + p.nh * p.nout + p.nout;
+      constexpr int PF = (FT_PARAM_F + 127) / 128;       // all loads first (independent), then the scatter
+      float pv[PF];
+#pragma unroll
+      for (int q = 0; q < PF; ++q) {
+        const int j = gt + q * 128;
+        pv[q] = (j < ntail && pg < p.P) ? __ldg(p.G + (size_t)pg * p.loci + (size_t)p.nin * p.nh + j) : 0.5f;
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+      for (int q = 0; q < PF; ++q) {
+        const int j = gt + q * 128;
+        if (j < ntail) {
+          int dst;
+          if (j < p.nh) dst = j;
+          else if (j < p.nh + p.nh * p.nout) { const int t = j - p.nh, h = t / p.nout; dst = FT_HP + h * FT_MAX_OUT + (t - h * p.nout); }
+          else dst = FT_HP + FT_HP * FT_MAX_OUT + (j - p.nh - p.nh * p.nout);
+          sparam[half][gi][dst] = (pv[q] - 0.5f) * 20.f;
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       const int row = mp * 256 + half * 128 + quad * 32 + lane;
       const bool rok = row < p.N;
-      float yv[FT_MAX_OUT];
+      constexpr int NO = 4 * NQ;
+      float yv[NO];
 #pragma unroll
-      for (int c = 0; c < FT_MAX_OUT; ++c) yv[c] = (rok && c < p.nout) ? __ldg(p.Y + (size_t)row * p.nout + c) : 0.f;
+      for (int c = 0; c < NO; ++c) yv[c] = (rok && c < p.nout) ? __ldg(p.Y + (size_t)row * p.nout + c) : 0.f;
       mbar_wait(&t_full[set], (uint32_t)(tu & 1));
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * 2 + half) * 128u;
-#pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
+      {
         const float* pb1 = sparam[half][gi];
         const float* pw2 = pb1 + FT_HP;
         const float* pb2 = pw2 + FT_HP * FT_MAX_OUT;
-        float logit[FT_MAX_OUT];
+        float logit[NO];
 #pragma unroll
-        for (int c = 0; c < FT_MAX_OUT; ++c) logit[c] = pb2[c];
+        for (int c = 0; c < NO; ++c) logit[c] = pb2[c];
 #pragma unroll
         for (int c0 = 0; c0 < FT_HP; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + gi * FT_HP + c0, v);
           tmem_ld_wait();
+          float act[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)     // sigmoid (atomic/activation_op.py:30); branch-free reciprocal so that the 16 chains interleave
+            act[j] = __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(v[j]) + pb1[c0 + j])));
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int h = c0 + j;
-            const float a = 1.0f / (1.0f + __expf(-(__uint_as_float(v[j]) + pb1[h])));      // sigmoid (atomic/activation_op.py:30)
+            const float a = act[j];
             const float4* w4 = reinterpret_cast<const float4*>(pw2 + h * FT_MAX_OUT);        // zero rows for h >= nh
 #pragma unroll
-            for (int q = 0; q < FT_MAX_OUT / 4; ++q) {
+            for (int q = 0; q < NQ; ++q) {
               const float4 w = w4[q];
               logit[4 * q + 0] = fmaf(a, w.x, logit[4 * q + 0]); logit[4 * q + 1] = fmaf(a, w.y, logit[4 * q + 1]);
               logit[4 * q + 2] = fmaf(a, w.z, logit[4 * q + 2]); logit[4 * q + 3] = fmaf(a, w.w, logit[4 * q + 3]);
@@ -178,16 +197,15 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < FT_MAX_OUT; ++c) if (c < p.nout) mx = fmaxf(mx, logit[c]);
+        for (int c = 0; c < NO; ++c) if (c < p.nout) mx = fmaxf(mx, logit[c]);
         float se = 0.f;
 #pragma unroll
-        for (int c = 0; c < FT_MAX_OUT; ++c) if (c < p.nout) se += expf(logit[c] - mx);
+        for (int c = 0; c < NO; ++c) if (c < p.nout) se += expf(logit[c] - mx);
         const float lse = mx + logf(se);
         float loss = 0.f;
 #pragma unroll
-        for (int c = 0; c < FT_MAX_OUT; ++c) if (c < p.nout && yv[c] != 0.f) loss -= yv[c] * (logit[c] - lse);
+        for (int c = 0; c < NO; ++c) if (c < p.nout && yv[c] != 0.f) loss -= yv[c] * (logit[c] - lse);
         loss = warp_sum(rok ? loss : 0.f);
-        const int pg = nt * 2 + gi;
         if (lane == 0 && pg < p.P) p.partial[(size_t)pg * (p.m_passes * 8) + mp * 8 + half * 4 + quad] = loss;
       }
       tc_fence_before();
@@ -232,7 +250,8 @@ int fitness_tma(const float* genomes, const float* X, const float* Y, float* fit
   float* Bt = (float*)ws;
   p.partial = (float*)((char*)ws + bt_bytes);
   BF_REQUIRE(((uintptr_t)X & 15) == 0 && (long long)Ppad * FT_HP < 2147483647LL, BF_ERR_ARG, "bf_fitness_mlp: operand alignment / size");
-  fitness_relayout_kernel<<<ew_grid((size_t)nin * Ppad * FT_HP, 256), 256, 0, s>>>(genomes, Bt, P, Ppad, nin, nh, loci);
+  BF_REQUIRE(Ppad <= 65535, BF_ERR_ARG, "bf_fitness_mlp: more than 65534 genomes per call");
+  fitness_relayout_kernel<<<dim3((nin + 31) / 32, FT_HP / 32, Ppad), dim3(32, 8), 0, s>>>(genomes, Bt, P, nin, nh, loci);
   BF_LAUNCH_CHECK();
   CUtensorMap mA, mB;
   {
@@ -243,16 +262,22 @@ int fitness_tma(const float* genomes, const float* X, const float* Y, float* fit
       return fail(BF_ERR_CUDA, "bf_fitness_mlp: cuTensorMapEncodeTiled failed (X)");
   }
   {
-    uint64_t dims[2] = {(uint64_t)Ppad * FT_HP, (uint64_t)nin};
-    uint64_t str[1] = {(uint64_t)Ppad * FT_HP};
-    uint32_t box[2] = {32, 32};
-    if (!tma_make_map(&mB, Bt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, false))
+    uint64_t dims[2] = {(uint64_t)nin, (uint64_t)Ppad * FT_HP};
+    uint64_t str[1] = {(uint64_t)nin};
+    uint32_t box[2] = {32, 128};
+    if (!tma_make_map(&mB, Bt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false))
       return fail(BF_ERR_CUDA, "bf_fitness_mlp: cuTensorMapEncodeTiled failed (genome operand)");
   }
   const size_t smem = 1024 + (size_t)FT_STAGES * FT_STAGE_BYTES;
-  BF_CUDA(cudaFuncSetAttribute(fitness_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ctas = p.ntiles < num_sms() ? p.ntiles : num_sms();
-  fitness_tma_kernel<<<ctas, FT_THREADS, smem, s>>>(mA, mB, p);
+  const int nq = (nout + 3) / 4;
+#define BF_FT_CASE(NQ_)                                                                                              \
+  if (nq == NQ_) {                                                                                                   \
+    BF_CUDA(cudaFuncSetAttribute(fitness_tma_kernel<NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    fitness_tma_kernel<NQ_><<<ctas, FT_THREADS, smem, s>>>(mA, mB, p);                                               \
+  }
+  BF_FT_CASE(1) BF_FT_CASE(2) BF_FT_CASE(3) BF_FT_CASE(4)
+#undef BF_FT_CASE
   BF_LAUNCH_CHECK();
   fitness_finish_kernel<<<(P + 127) / 128, 128, 0, s>>>(p.partial, fitness, P, p.m_passes * 8, N);
   BF_LAUNCH_CHECK();
