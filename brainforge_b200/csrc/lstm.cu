@@ -3,7 +3,8 @@
 // (B x (D+H)) @ ((D+H) x 4H) plus one fused elementwise gate kernel.  The weight gradient is ONE
 // split-K contraction over all T*B rows after the loop (recurrent_op.py:109), with the bias gradient
 // riding along as an all-ones row.
-#include "gemm_umma.cuh"
+#include "gemm_tma.cuh"
+#include <stdlib.h>
 
 namespace bf {
 
@@ -122,6 +123,23 @@ struct EpiBias {
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// dst (C x R) = src (R x C)^T through a padded shared-memory tile
+__global__ void lstm_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int r = r0 + ty + j, c = c0 + tx;
+    if (r < R && c < C) tile[ty + j][tx] = src[(size_t)r * C + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c0 + ty + j, r = r0 + tx;
+    if (r < R && c < C) dst[(size_t)c * R + r] = tile[tx][ty + j];
+  }
+}
+
 }  // namespace bf
 
 using namespace bf;
@@ -136,11 +154,19 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
              "bf_lstm_forward: bad activation %d", act);
   if (T == 0 || B == 0) return BF_OK;
   cudaStream_t s = as_stream(stream);
+  const long TB = (long)T * B, BH = (long)B * H, ZD = D + H;
   void* ws = nullptr;
-  int rc = workspace_require((size_t)B * 4 * H * sizeof(float), &ws);
+  const size_t gates_bytes = align_up((size_t)B * 4 * H * sizeof(float));
+  int rc = workspace_require(gates_bytes + (size_t)ZD * 4 * H * sizeof(float), &ws);
   if (rc) return rc;
   float* gates = (float*)ws;
-  const long TB = (long)T * B, BH = (long)B * H, ZD = D + H;
+  float* Wt = (float*)((char*)ws + gates_bytes);     // W^T (4H x (D+H)): the K-major B operand of the TMA-fed gate GEMM
+  const bool tma = precision == BF_PREC_TF32 && gemm_tma_ok(Z, Wt, B, 4 * H, (int)ZD) && ((ZD * 4) % 16) == 0 &&
+                   getenv("BF_LSTM_GATHER") == nullptr;
+  if (tma) {
+    lstm_transpose_kernel<<<dim3((4 * H + 31) / 32, ((int)ZD + 31) / 32), dim3(32, 8), 0, s>>>(W, Wt, (int)ZD, 4 * H);
+    BF_LAUNCH_CHECK();
+  }
   lstm_fill_z_kernel<<<ew_grid(TB * D + BH, 256), 256, 0, s>>>(X, Z, TB, B, D, H);
   BF_LAUNCH_CHECK();
   float* C = cache;               // cache (6,T,B,H): C, Ca, cand, f, i, o  (recurrent_op.py:77)
@@ -151,10 +177,14 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
   float* o = cache + 5 * TB * H;
   const int K = D + H, N = 4 * H;
   for (int t = 0; t < T; ++t) {
-    LoadKContig al{Z + (long)t * B * ZD, (long)ZD};
-    LoadMNContig bl{W, (long)N};
     EpiBias ep{gates, b, N};
-    rc = launch_gemm(precision, al, bl, ep, B, N, K, 1, (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    if (tma) {
+      rc = launch_gemm_tma(Z + (long)t * B * ZD, Wt, B, N, K, ep, s);
+    } else {
+      LoadKContig al{Z + (long)t * B * ZD, (long)ZD};
+      LoadMNContig bl{W, (long)N};
+      rc = launch_gemm(precision, al, bl, ep, B, N, K, 1, (K + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
     if (rc) return rc;
     long off = (long)t * BH;
     lstm_gates_fwd_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(
@@ -214,10 +244,14 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
                                                           act, t == T - 1);
     BF_LAUNCH_CHECK();
     // deltaZ[t] = dgates[t] @ W^T : M=B, N=D+H, K=4H ; B(k, n) = W[n*4H + k]
-    LoadKContig al{dg_t, (long)N4};
-    LoadKContig bl{W, (long)N4};
     EpiLstmDz ep{dX + (long)t * B * D, dH, D, H};
-    rc = launch_gemm(precision, al, bl, ep, B, ZD, N4, 1, (N4 + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    if (precision == BF_PREC_TF32 && gemm_tma_ok(dg_t, W, B, ZD, N4) && getenv("BF_LSTM_GATHER") == nullptr) {
+      rc = launch_gemm_tma(dg_t, W, B, ZD, N4, ep, s);     // both operands are K-major as stored: no copy, no transpose
+    } else {
+      LoadKContig al{dg_t, (long)N4};
+      LoadKContig bl{W, (long)N4};
+      rc = launch_gemm(precision, al, bl, ep, B, ZD, N4, 1, (N4 + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
     if (rc) return rc;
   }
   // nablaW = sum_t Z[t]^T @ dgates[t]  (+ ones row -> nablab)
