@@ -1,6 +1,7 @@
 // Library plumbing: error string, device info, workspace, copies, casts.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace bf {
 
@@ -39,6 +40,11 @@ int num_sms() {
 }
 
 void set_last_path(int p) { g_last_path = p; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BF_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 void* workspace_ptr() { return g_ws_ptr; }
 size_t workspace_bytes() { return g_ws_bytes; }
 

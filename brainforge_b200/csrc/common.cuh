@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include "../../include/bf_b200.h"
 
 namespace bf {
@@ -46,6 +47,29 @@ inline int ew_grid(size_t items, int threads, int ctas_per_sm = 8) {
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// Every kernel of the training step is launched with cudaLaunchAttributeProgrammaticStreamSerialization and calls
+// pdl_launch_dependents() on entry and pdl_wait() before its first read of anything an earlier kernel wrote: the NEXT
+// kernel's launch latency and prologue (barrier init, TMEM allocation, shared-memory clearing) then overlap this
+// kernel's execution instead of following its last CTA.  The step is ~28 launches; at the 8-GPU shard size (512
+// samples) their fixed cost is more than half of the step.  BF_PDL=0 disables the attribute (the device calls become no-ops).
+bool pdl_enabled();
+template <typename K, typename... Args>
+inline cudaError_t launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- device helpers -----------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

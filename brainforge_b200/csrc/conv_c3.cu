@@ -43,6 +43,8 @@ struct C3FwdParams {
 
 // NCHW (im, ic, iy*ix) -> (im*iy*ix, 4): channel-padded channels-last copy of the input
 __global__ void nchw_to_nhwc4_kernel(const float* __restrict__ X, float4* __restrict__ X4, long npix_total, int plane, int ic) {
+  pdl_launch_dependents();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < npix_total; i += stride) {
     const long b = i / plane;
@@ -76,6 +78,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
   const uint32_t b_bytes = (uint32_t)(NB / 8) * b_sbo;
   const uint32_t stage_base = (b_base + b_bytes + 127u) & ~127u;
   const int n0 = blockIdx.y * NB;
+  pdl_launch_dependents();
 
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
@@ -86,6 +89,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
     for (int i = 0; i < 32; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_wait();          // everything above touched only this CTA's shared memory / TMEM
   if (tid < NB) sbias[tid] = bias ? bias[n0 + tid] : 0.f;
   // weight operand W[n][ky*16 + dx*4 + c] = F[n][c][ky][dx], K-major SWIZZLE_NONE core matrices (8 filters x 16 B)
   for (int idx = tid; idx < NB * Kt; idx += C3_THREADS) {
@@ -287,6 +291,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
   const uint32_t zero_base = a_base + (uint32_t)(p.na * p.nkb) * C3DF_A_SLOT;
   const uint32_t x_base = zero_base + (uint32_t)p.a_tail_bytes;
 
+  pdl_launch_dependents();
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * NF));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -310,6 +315,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
     roff[r] = v;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  pdl_wait();          // the prologue above touched only this CTA's shared memory / TMEM
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -535,6 +541,8 @@ __global__ void __launch_bounds__(256)
 conv_c3_df_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
                          int nctas, int Mrows, int nf) {
   __shared__ float red[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int total = nf * (Mrows + 1);
   const int o = blockIdx.x * 32 + threadIdx.x, zs = threadIdx.y;
   float s = 0.f;
@@ -576,7 +584,7 @@ static int c3_forward_impl(const float* X, const float* F, const float* bias, fl
   void* ws = nullptr;
   int rc = workspace_require(c3_al256((size_t)im * IR * 16), &ws);
   if (rc) return rc;
-  nchw_to_nhwc4_kernel<<<ew_grid((size_t)im * IR, 256), 256, 0, s>>>(X, (float4*)ws, (long)im * IR, IR, ic);
+  launch_pdl(nchw_to_nhwc4_kernel, dim3(ew_grid((size_t)im * IR, 256)), dim3(256), 0, s, X, (float4*)ws, (long)im * IR, IR, ic);
   BF_LAUNCH_CHECK();
   C3FwdParams p;
   p.nimg = im; p.IR = IR; p.ix = ix; p.oy = oy; p.ox = ox; p.RT = 128 / ix; if (p.RT > oy) p.RT = oy;
@@ -604,7 +612,7 @@ static int c3_forward_impl(const float* X, const float* F, const float* bias, fl
 #define BF_C3_LAUNCH(NB_, R_, P_)                                                                                           \
   {                                                                                                                         \
     BF_CUDA(cudaFuncSetAttribute(conv_c3_fwd_kernel<NB_, R_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_c3_fwd_kernel<NB_, R_, P_><<<ctas, C3_THREADS, smem, s>>>(mX, p, F, Y, bias);                                      \
+    launch_pdl(conv_c3_fwd_kernel<NB_, R_, P_>, dim3(ctas), dim3(C3_THREADS), smem, s, mX, p, F, Y, bias);                                      \
   }
 #define BF_C3_CASE(NB_)                                                                              \
   if (nf == NB_) {                                                                                   \
@@ -708,7 +716,7 @@ static int c3_backward_filter_impl(const float* X, const float* E, const float* 
 #define BF_C3DF_LAUNCH(MH_, NR_, U_)                                                                                          \
   {                                                                                                                           \
     BF_CUDA(cudaFuncSetAttribute(conv_c3_df_kernel<MH_, NR_, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    conv_c3_df_kernel<MH_, NR_, U_><<<ctas, C3DF_THREADS, smem, s>>>(mE, X, p, (float*)ws);                                   \
+    launch_pdl(conv_c3_df_kernel<MH_, NR_, U_>, dim3(ctas), dim3(C3DF_THREADS), smem, s, mE, X, p, (float*)ws);                                   \
   }
 #define BF_C3DF_CASE(MH_, NR_) \
   if (MH == MH_ && NR == NR_) { if (unpool) BF_C3DF_LAUNCH(MH_, NR_, true) else BF_C3DF_LAUNCH(MH_, NR_, false) }
@@ -718,7 +726,7 @@ static int c3_backward_filter_impl(const float* X, const float* E, const float* 
 #undef BF_C3DF_CASE
 #undef BF_C3DF_LAUNCH
   BF_LAUNCH_CHECK();
-  conv_c3_df_reduce_kernel<<<(nf * (Mrows + 1) + 31) / 32, dim3(32, 8), 0, s>>>((const float*)ws, dF, db, ctas, Mrows, nf);
+  launch_pdl(conv_c3_df_reduce_kernel, dim3((nf * (Mrows + 1) + 31) / 32), dim3(dim3(32, 8)), 0, s, (const float*)ws, dF, db, ctas, Mrows, nf);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;

@@ -73,11 +73,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int i = 0; i < 16; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < NB) sbias[tid] = bias ? bias[n0 + tid] : 0.f;
+  pdl_launch_dependents();
   // rows of the A slots that TMA never writes are read by the taps of dropped positions only; give them a
   // defined value once so that no NaN pattern lingers there
   for (uint32_t o = tid * 16u; o < (uint32_t)p.na * a_slot_bytes; o += IG_THREADS * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
+  pdl_wait();          // the prologue above touched only this CTA's shared memory / TMEM
+  if (tid < NB) sbias[tid] = bias ? bias[n0 + tid] : 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -263,6 +265,7 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
   const uint32_t x_base = base + (uint32_t)p.ns * e_slot, ones_base = x_base + (uint32_t)p.ns * x_slot;
   const uint32_t total_bytes = (uint32_t)p.ns * (e_slot + x_slot) + 1024u;
   const int split = blockIdx.x, ch = blockIdx.y;
+  pdl_launch_dependents();
   const int ntap_acc = p.ntaps + (ch == 0 ? 1 : 0);   // channel half 0 also accumulates db (all-ones operand)
 
   if (warp == 1) {
@@ -279,6 +282,7 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
     const uint32_t v = (base + o >= ones_base) ? 0x3f800000u : 0u;
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(v) : "memory");
   }
+  pdl_wait();          // the prologue above touched only this CTA's shared memory / TMEM
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -368,6 +372,8 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
 // the (small) result is scattered into the reference's (nf, ic, fy, fx) order.
 __global__ void conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
                                            int nsplit, int nch, int ntaps, int nf, int ic) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long nmain = (long)nch * ntaps * nf * 32, total = nmain + nf;
   const size_t zstride = (size_t)nch * (ntaps + 1) * 128 * 32;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
@@ -406,6 +412,8 @@ __global__ void conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, fl
 //                 data grad n = c, k = f, tap = (ty,tx)        -> F[f][c][fy-1-ty][fx-1-tx]   (flip + transpose)
 __global__ void conv_repack_nhwc_kernel(const float* __restrict__ F, float* __restrict__ Wt, int nf, int ic, int fy, int fx,
                                         int transpose) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ntaps = fy * fx, N = transpose ? ic : nf, K = transpose ? nf : ic;
   const long total = (long)ntaps * N * K;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
@@ -524,10 +532,10 @@ static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, IgemmPlan&
   dim3 grid(ctas, pl.p.N / NB);
   if (pl.p.relu) {
     BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    conv_igemm_kernel<NB, KH, true><<<grid, IG_THREADS, pl.smem, s>>>(mA, mB, pl.p, out, bias);
+    launch_pdl(conv_igemm_kernel<NB, KH, true>, dim3(grid), dim3(IG_THREADS), pl.smem, s, mA, mB, pl.p, out, bias);
   } else {
     BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    conv_igemm_kernel<NB, KH, false><<<grid, IG_THREADS, pl.smem, s>>>(mA, mB, pl.p, out, bias);
+    launch_pdl(conv_igemm_kernel<NB, KH, false>, dim3(grid), dim3(IG_THREADS), pl.smem, s, mA, mB, pl.p, out, bias);
   }
   BF_LAUNCH_CHECK();
   if (prof) {
@@ -602,7 +610,7 @@ int bf_conv_nhwc_forward(const float* X, const float* F, const float* bias, floa
   void* ws = nullptr;
   int rc = workspace_require(al256((size_t)nf * ic * fy * fx * 4), &ws);
   if (rc) return rc;
-  conv_repack_nhwc_kernel<<<ew_grid((size_t)nf * ic * fy * fx, 256), 256, 0, s>>>(F, (float*)ws, nf, ic, fy, fx, 0);
+  launch_pdl(conv_repack_nhwc_kernel, dim3(ew_grid((size_t)nf * ic * fy * fx, 256)), dim3(256), 0, s, F, (float*)ws, nf, ic, fy, fx, 0);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return conv_nhwc_igemm(X, (const float*)ws, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act == BF_ACT_RELU ? 1 : 0, s);
@@ -618,7 +626,7 @@ int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX, int im
   void* ws = nullptr;
   int rc = workspace_require(al256((size_t)nf * ic * fy * fx * 4), &ws);
   if (rc) return rc;
-  conv_repack_nhwc_kernel<<<ew_grid((size_t)nf * ic * fy * fx, 256), 256, 0, s>>>(F, (float*)ws, nf, ic, fy, fx, 1);
+  launch_pdl(conv_repack_nhwc_kernel, dim3(ew_grid((size_t)nf * ic * fy * fx, 256)), dim3(256), 0, s, F, (float*)ws, nf, ic, fy, fx, 1);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return conv_nhwc_igemm(E, (const float*)ws, nullptr, dX, im, oy, ox, nf, ic, fy, fx, fy - 1, fx - 1, 0, s);
@@ -704,12 +712,12 @@ int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, floa
 #define BF_DF_CASE(MH_)                                                                                              \
   if (MH == MH_) {                                                                                                   \
     BF_CUDA(cudaFuncSetAttribute(conv_df_kernel<MH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    conv_df_kernel<MH_><<<grid, DF_THREADS, smem, s>>>(mE, mX, p, (float*)ws);                                       \
+    launch_pdl(conv_df_kernel<MH_>, dim3(grid), dim3(DF_THREADS), smem, s, mE, mX, p, (float*)ws);                                       \
   }
   BF_DF_CASE(1) BF_DF_CASE(2) BF_DF_CASE(4)
 #undef BF_DF_CASE
   BF_LAUNCH_CHECK();
-  conv_df_reduce_nhwc_kernel<<<ew_grid((size_t)nf * ic * ntaps + nf, 256), 256, 0, s>>>((const float*)ws, dF, db, nsplit,
+  launch_pdl(conv_df_reduce_nhwc_kernel, dim3(ew_grid((size_t)nf * ic * ntaps + nf, 256)), dim3(256), 0, s, (const float*)ws, dF, db, nsplit,
                                                                                          nch, ntaps, nf, ic);
   BF_LAUNCH_CHECK();
   set_last_path(2);

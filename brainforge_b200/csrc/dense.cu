@@ -6,6 +6,8 @@ namespace bf {
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, float* __restrict__ aux,
                                      int rows, int N, int aux_row, int splits, int accumulate, long out_rs,
                                      long out_cs) {
+  pdl_launch_dependents();
+  pdl_wait();
   long total = (long)rows * N;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
@@ -23,7 +25,7 @@ int launch_splitk_reduce(const float* ws, float* out, float* aux, int rows, int 
                          int accumulate, long out_rs, long out_cs, cudaStream_t s) {
   long total = (long)rows * N;
   if (total == 0) return BF_OK;
-  splitk_reduce_kernel<<<ew_grid(total, 256), 256, 0, s>>>(ws, out, aux, rows, N, aux_row, splits, accumulate,
+  launch_pdl(splitk_reduce_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, s, ws, out, aux, rows, N, aux_row, splits, accumulate,
                                                              out_rs, out_cs);
   BF_LAUNCH_CHECK();
   return BF_OK;
@@ -58,9 +60,25 @@ dense_skinny_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W
                         float* __restrict__ out, int m, int k, int n, int act) {
   extern __shared__ __align__(16) float sw[];
   constexpr int PITCH = NT == 4 ? 4 : NT + 4;
-  for (int i = threadIdx.x; i < k * NT; i += blockDim.x) {
-    const int kk = i / NT, j = i - kk * NT;
-    sw[kk * PITCH + j] = j < n ? W[(size_t)kk * n + j] : 0.f;
+  pdl_launch_dependents();
+  pdl_wait();
+  // W is (k x n) contiguous: read it flat (coalesced, 8 independent loads in flight per thread -- a one-load-at-a-time
+  // loop made this staging the whole cost of the kernel at small batch), scatter into the padded [k][PITCH] tile
+  for (int i = threadIdx.x; i < k * PITCH; i += blockDim.x) sw[i] = 0.f;
+  __syncthreads();
+  const int total = k * n;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = i < total ? __ldg(W + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) { const int kk = i / n; sw[kk * PITCH + (i - kk * n)] = v[u]; }
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -119,6 +137,8 @@ __global__ void __launch_bounds__(256)
 dense_skinny_bwd_kernel(const float* __restrict__ X, const float* __restrict__ E, const float* __restrict__ W,
                         float* __restrict__ partial, float* __restrict__ dX, int m, int k, int n, int rows_per_chunk) {
   extern __shared__ __align__(16) float se[];     // [rows_per_chunk][NT]
+  pdl_launch_dependents();
+  pdl_wait();
   const int m0 = blockIdx.x * rows_per_chunk;
   int rows = m - m0;
   if (rows > rows_per_chunk) rows = rows_per_chunk;
@@ -174,7 +194,7 @@ static int launch_skinny_fwd(const float* X, const float* W, const float* b, flo
 #define BF_SK(NT_)                                                                                                  \
   if (nt == NT_) {                                                                                                  \
     BF_CUDA(cudaFuncSetAttribute(dense_skinny_fwd_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dense_skinny_fwd_kernel<NT_><<<grid, 256, smem, s>>>(X, W, b, out, m, k, n, act);                               \
+    launch_pdl(dense_skinny_fwd_kernel<NT_>, dim3(grid), dim3(256), smem, s, X, W, b, out, m, k, n, act);                               \
   }
   BF_SK(4) BF_SK(8) BF_SK(16) BF_SK(32)
 #undef BF_SK
@@ -195,7 +215,7 @@ static int launch_skinny_bwd(const float* X, const float* E, const float* W, flo
   if (rc) return rc;
   dim3 grid(chunks, (k + 255) / 256);
   const size_t smem = (size_t)rows_per_chunk * nt * 4;
-#define BF_SK(NT_) if (nt == NT_) dense_skinny_bwd_kernel<NT_><<<grid, 256, smem, s>>>(X, E, W, (float*)ws, dX, m, k, n, rows_per_chunk);
+#define BF_SK(NT_) if (nt == NT_) launch_pdl(dense_skinny_bwd_kernel<NT_>, dim3(grid), dim3(256), smem, s, X, E, W, (float*)ws, dX, m, k, n, rows_per_chunk);
   BF_SK(4) BF_SK(8) BF_SK(16) BF_SK(32)
 #undef BF_SK
   BF_LAUNCH_CHECK();

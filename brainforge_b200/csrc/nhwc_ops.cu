@@ -13,6 +13,8 @@ namespace bf {
 // src (B, R, C) -> dst (B, C, R)
 __global__ void batched_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int R, int C) {
   __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   for (int b = blockIdx.z; b < B; b += gridDim.z) {
@@ -35,6 +37,8 @@ __global__ void batched_transpose_kernel(const float* __restrict__ src, float* _
 
 // Small planes (R or C below a tile): one thread per destination element, reads strided but L1/L2 resident.
 __global__ void batched_transpose_small_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t total, int R, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   const size_t plane = (size_t)R * C;
   for (; i < total; i += stride) {
@@ -53,10 +57,10 @@ static int batched_transpose(const float* src, float* dst, int B, int R, int C, 
   }
   if (R < 16 || C < 16) {
     const size_t total = (size_t)B * R * C;
-    batched_transpose_small_kernel<<<ew_grid(total, 256), 256, 0, s>>>(src, dst, total, R, C);
+    launch_pdl(batched_transpose_small_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, s, src, dst, total, R, C);
   } else {
     dim3 grid((C + 31) / 32, (R + 31) / 32, B < 16384 ? B : 16384), block(32, 8);
-    batched_transpose_kernel<<<grid, block, 0, s>>>(src, dst, B, R, C);
+    launch_pdl(batched_transpose_kernel, dim3(grid), dim3(block), 0, s, src, dst, B, R, C);
   }
   BF_LAUNCH_CHECK();
   return BF_OK;
@@ -68,6 +72,8 @@ __device__ __forceinline__ float4 relu4(float4 v) { return make_float4(fmaxf(v.x
 template <int FD, bool RELU>
 __global__ void pool_nhwc_fwd_kernel(const float4* __restrict__ A, float4* __restrict__ out, uchar4* __restrict__ mask,
                                      long total, int oy, int ox, int c4, int ix) {
+  pdl_launch_dependents();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     const int q = (int)(i % c4);
@@ -105,6 +111,8 @@ __global__ void pool_nhwc_fwd_kernel(const float4* __restrict__ A, float4* __res
 template <int FD, bool GATE>
 __global__ void pool_nhwc_bwd_kernel(const float4* __restrict__ E, const uchar4* __restrict__ mask, const float4* __restrict__ gate,
                                      float4* __restrict__ dX, long total, int oy, int ox, int c4, int ix) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int fd = FD;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
@@ -136,6 +144,8 @@ __global__ void pool_nhwc_bwd_kernel(const float4* __restrict__ E, const uchar4*
 template <bool RELU>
 __global__ void pool_nhwc_fwd_wide_kernel(const float* __restrict__ A, float* __restrict__ out, unsigned long long* __restrict__ mask,
                                           long total, int oy, int ox, int c, int ix, int fd) {
+  pdl_launch_dependents();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     const int q = (int)(i % c);
@@ -167,6 +177,8 @@ __global__ void pool_nhwc_fwd_wide_kernel(const float* __restrict__ A, float* __
 __global__ void pool_nhwc_bwd_wide_kernel(const float* __restrict__ E, const unsigned long long* __restrict__ mask,
                                           const float* __restrict__ gate, float* __restrict__ dX, long total, int oy, int ox,
                                           int c, int ix, int fd) {
+  pdl_launch_dependents();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     const int q = (int)(i % c);
@@ -221,7 +233,7 @@ int bf_pool_nhwc_forward(const float* A, float* out, uint8_t* mask, int im, int 
     const long total = (long)im * oy * ox * c4;
     if (total == 0) return BF_OK;
     const int grid = ew_grid(total, 256);
-#define BF_PF(FD_, R_) pool_nhwc_fwd_kernel<FD_, R_><<<grid, 256, 0, s>>>((const float4*)A, (float4*)out, (uchar4*)mask, total, oy, ox, c4, ix)
+#define BF_PF(FD_, R_) launch_pdl(pool_nhwc_fwd_kernel<FD_, R_>, dim3(grid), dim3(256), 0, s, (const float4*)A, (float4*)out, (uchar4*)mask, total, oy, ox, c4, ix)
     if (fdim == 2) { if (relu_in) BF_PF(2, true); else BF_PF(2, false); }
     else { if (relu_in) BF_PF(1, true); else BF_PF(1, false); }
 #undef BF_PF
@@ -229,8 +241,8 @@ int bf_pool_nhwc_forward(const float* A, float* out, uint8_t* mask, int im, int 
     const long total = (long)im * oy * ox * c;
     if (total == 0) return BF_OK;
     const int grid = ew_grid(total, 256);
-    if (relu_in) pool_nhwc_fwd_wide_kernel<true><<<grid, 256, 0, s>>>(A, out, (unsigned long long*)mask, total, oy, ox, c, ix, fdim);
-    else pool_nhwc_fwd_wide_kernel<false><<<grid, 256, 0, s>>>(A, out, (unsigned long long*)mask, total, oy, ox, c, ix, fdim);
+    if (relu_in) launch_pdl(pool_nhwc_fwd_wide_kernel<true>, dim3(grid), dim3(256), 0, s, A, out, (unsigned long long*)mask, total, oy, ox, c, ix, fdim);
+    else launch_pdl(pool_nhwc_fwd_wide_kernel<false>, dim3(grid), dim3(256), 0, s, A, out, (unsigned long long*)mask, total, oy, ox, c, ix, fdim);
   }
   BF_LAUNCH_CHECK();
   return BF_OK;
@@ -249,14 +261,14 @@ int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate
     const long total = (long)im * oy * ox * c4;
     if (total == 0) return BF_OK;
     const int grid = ew_grid(total, 256);
-#define BF_PB(FD_, G_) pool_nhwc_bwd_kernel<FD_, G_><<<grid, 256, 0, s>>>((const float4*)E, (const uchar4*)mask, (const float4*)gate, (float4*)dX, total, oy, ox, c4, ix)
+#define BF_PB(FD_, G_) launch_pdl(pool_nhwc_bwd_kernel<FD_, G_>, dim3(grid), dim3(256), 0, s, (const float4*)E, (const uchar4*)mask, (const float4*)gate, (float4*)dX, total, oy, ox, c4, ix)
     if (fdim == 2) { if (gate) BF_PB(2, true); else BF_PB(2, false); }
     else { if (gate) BF_PB(1, true); else BF_PB(1, false); }
 #undef BF_PB
   } else {
     const long total = (long)im * oy * ox * c;
     if (total == 0) return BF_OK;
-    pool_nhwc_bwd_wide_kernel<<<ew_grid(total, 256), 256, 0, s>>>(E, (const unsigned long long*)mask, gate, dX, total, oy, ox, c, ix, fdim);
+    launch_pdl(pool_nhwc_bwd_wide_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, s, E, (const unsigned long long*)mask, gate, dX, total, oy, ox, c, ix, fdim);
   }
   BF_LAUNCH_CHECK();
   return BF_OK;
