@@ -228,6 +228,11 @@ def algorithmic_cost(label):
         oy, ox = iy - fy + 1, ix - fx + 1
         pooled = im * nf * (oy // 2) * (ox // 2)
         return f * (im * ic * iy * ix + nf * ic * fy * fx + nf + pooled) + pooled, 2.0 * im * oy * ox * nf * ic * fy * fx
+    if name == "bf_conv_c3_backward_filter_unpool":   # read X, the pooled-resolution delta + gate + 1 mask byte each; write dF, db
+        im, ic, iy, ix, nf, fy, fx = a[:7]
+        oy, ox = iy - fy + 1, ix - fx + 1
+        pooled = im * nf * (oy // 2) * (ox // 2)
+        return f * (im * ic * iy * ix + 2 * pooled + nf * ic * fy * fx + nf) + pooled, 2.0 * im * oy * ox * nf * ic * fy * fx
     if name in ("bf_conv_nhwc_backward_filter", "bf_conv_c3_backward_filter", "bf_conv_nhwc_backward_data"):
         im, ic, iy, ix, nf, fy, fx = a[:7]
         oy, ox = iy - fy + 1, ix - fx + 1
@@ -281,7 +286,7 @@ def algorithmic_cost(label):
 KERNEL_OF_CALL = {   # C-ABI call -> its dominant kernel, for the kernels that have ONE instance per step (an ncu capture of
     # the other families is one of several layer shapes and would not match the launch the roofline entry describes)
     "bf_conv_c3_forward_pool": "conv_c3_fwd_kernel", "bf_conv_c3_forward": "conv_c3_fwd_kernel",
-    "bf_conv_c3_backward_filter": "conv_c3_df_kernel",
+    "bf_conv_c3_backward_filter": "conv_c3_df_kernel", "bf_conv_c3_backward_filter_unpool": "conv_c3_df_kernel",
 }
 
 

@@ -51,7 +51,7 @@ struct EpiPlain {
 // and (measured, B200) costs ~40 us of fixed pipeline latency per call, so these run as FP32 FMA kernels that
 // stream X once at full width, with W resident in shared memory / registers.  (Exact FP32 on both precision paths.)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SKINNY_ROWS = 4;          // rows per warp iteration (forward)
+constexpr int SKINNY_ROWS = 2;          // rows per warp iteration (forward): more warps in flight beats W reuse here
 
 // forward: one warp per SKINNY_ROWS rows, lanes split K; W staged once per CTA as [k][NT + pad] (conflict-free LDS.128)
 template <int NT>
@@ -90,6 +90,7 @@ dense_skinny_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W
     for (int r = 0; r < SKINNY_ROWS; ++r)
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[r][j] = 0.f;
+#pragma unroll 4
     for (int kk = lane; kk < k; kk += 32) {
       float x[SKINNY_ROWS];
 #pragma unroll
@@ -153,19 +154,28 @@ dense_skinny_bwd_kernel(const float* __restrict__ X, const float* __restrict__ E
     float w[NT], acc[NT];
 #pragma unroll
     for (int j = 0; j < NT; ++j) { w[j] = j < n ? __ldg(W + (size_t)kk * n + j) : 0.f; acc[j] = 0.f; }
-    for (int r = 0; r < rows; ++r) {
-      const float x = __ldg(X + (size_t)(m0 + r) * k + kk);
-      const float4* e4 = reinterpret_cast<const float4*>(se + r * NT);
-      float dx = 0.f;
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+      float xv[8];
 #pragma unroll
-      for (int q = 0; q < NT / 4; ++q) {
-        const float4 e = e4[q];
-        acc[4 * q + 0] = fmaf(x, e.x, acc[4 * q + 0]); dx = fmaf(e.x, w[4 * q + 0], dx);
-        acc[4 * q + 1] = fmaf(x, e.y, acc[4 * q + 1]); dx = fmaf(e.y, w[4 * q + 1], dx);
-        acc[4 * q + 2] = fmaf(x, e.z, acc[4 * q + 2]); dx = fmaf(e.z, w[4 * q + 2], dx);
-        acc[4 * q + 3] = fmaf(x, e.w, acc[4 * q + 3]); dx = fmaf(e.w, w[4 * q + 3], dx);
+      for (int u = 0; u < 8; ++u) xv[u] = r0 + u < rows ? __ldg(X + (size_t)(m0 + r0 + u) * k + kk) : 0.f;   // 8 loads in flight
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u;
+        if (r < rows) {
+          const float x = xv[u];
+          const float4* e4 = reinterpret_cast<const float4*>(se + r * NT);
+          float dx = 0.f;
+#pragma unroll
+          for (int q = 0; q < NT / 4; ++q) {
+            const float4 e = e4[q];
+            acc[4 * q + 0] = fmaf(x, e.x, acc[4 * q + 0]); dx = fmaf(e.x, w[4 * q + 0], dx);
+            acc[4 * q + 1] = fmaf(x, e.y, acc[4 * q + 1]); dx = fmaf(e.y, w[4 * q + 1], dx);
+            acc[4 * q + 2] = fmaf(x, e.z, acc[4 * q + 2]); dx = fmaf(e.z, w[4 * q + 2], dx);
+            acc[4 * q + 3] = fmaf(x, e.w, acc[4 * q + 3]); dx = fmaf(e.w, w[4 * q + 3], dx);
+          }
+          if (dX) dX[(size_t)(m0 + r) * k + kk] = dx;
+        }
       }
-      if (dX) dX[(size_t)(m0 + r) * k + kk] = dx;
     }
 #pragma unroll
     for (int j = 0; j < NT; ++j)
@@ -190,7 +200,7 @@ static int launch_skinny_fwd(const float* X, const float* W, const float* b, flo
   const int nt = skinny_nt(n);
   const size_t smem = (size_t)k * (nt == 4 ? 4 : nt + 4) * 4;
   int grid = (m + 8 * SKINNY_ROWS - 1) / (8 * SKINNY_ROWS);
-  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
 #define BF_SK(NT_)                                                                                                  \
   if (nt == NT_) {                                                                                                  \
     BF_CUDA(cudaFuncSetAttribute(dense_skinny_fwd_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -206,7 +216,7 @@ static int launch_skinny_fwd(const float* X, const float* W, const float* b, flo
 static int launch_skinny_bwd(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m,
                              int k, int n, int accumulate, cudaStream_t s) {
   const int nt = skinny_nt(n);
-  int rows_per_chunk = (m + 63) / 64;
+  int rows_per_chunk = (m + 127) / 128;
   if (rows_per_chunk < 16) rows_per_chunk = 16;
   if (rows_per_chunk > 256) rows_per_chunk = 256;
   const int chunks = (m + rows_per_chunk - 1) / rows_per_chunk;
