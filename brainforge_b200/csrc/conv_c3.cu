@@ -108,9 +108,8 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
 
   if (warp == 0) {
     const bool leader = elect_one_sync();
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int as = it % p.na, au = it / p.na;
+    int as = 0, au = 0;                // ring slot and its use count (running counters: no divisions by p.na in the loop)
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_img, t = tile - b * p.tiles_per_img;
       if (au > 0) mbar_wait(&a_empty[as], (uint32_t)((au - 1) & 1));
       if (leader) {
@@ -122,16 +121,17 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
         mbar_expect_tx(&a_full[as], (uint32_t)npx * 16u);
         bulk_load_1d(base + as * a_slot, p.X4 + px0, (uint32_t)npx * 16u, &a_full[as]);
       }
+      if (++as == p.na) { as = 0; ++au; }
     }
   } else if (warp == 1 || warp == 2) {
     // two issuing warps, one per accumulator set (even / odd tiles): a single thread issues a K=8 MMA only every
     // ~50-100 cycles, which at 2*fy MMAs per 128-position tile was the limit of this kernel
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = idesc_tf32(128, NB);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    int it = 0, as = 0, au = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it, as = (as + 1 == p.na ? 0 : as + 1), au += (as == 0)) {
       if ((it & 1) != warp - 1) continue;
-      const int as = it % p.na, au = it / p.na, acc_set = it & 3, tu = it >> 2;   // each MMA warp / epilogue group pair owns two sets
+      const int acc_set = it & 3, tu = it >> 2;   // each MMA warp / epilogue group pair owns two sets
       if (tu > 0) mbar_wait(&t_empty[acc_set], (uint32_t)((tu - 1) & 1));
       mbar_wait(&a_full[as], (uint32_t)(au & 1));
       tc_fence_after();
@@ -326,9 +326,8 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     const bool leader = elect_one_sync();
-    int it = 0;
-    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
-      const int s = it % p.ns, u = it / p.ns;
+    int s = 0, u = 0;                  // load-ring slot and its use count (running counters: no divisions in the loop)
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
       const int b = unit / p.nbands, band = unit - b * p.nbands, y0 = band * p.RB;
       if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
       if (leader) {
@@ -375,15 +374,15 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
         for (int c = 0; c < 4; ++c)
           if (c < p.ic) bulk_load_1d(st0 + c * p.x_plane_f * 4, X + xo[c], xb[c], &full[s]);
       }
+      if (++s == p.ns) { s = 0; ++u; }
     }
   } else if (warp == 1 || warp == 2) {
     // ------------------------------------------------------------------ MMA issuers (k-block parity inside a band)
     const bool leader = elect_one_sync();
     const int wsel = warp - 1;
     constexpr uint32_t idesc = idesc_tf32(64, NF, false, true);   // M=64: half the shared-memory reads of M=128 per MMA
-    int mine = 0;
+    int mine = 0, s = 0, u = 0, t = 0, ut = 0;
     for (int it = 0; it < my_units; ++it) {
-      const int s = it % p.ns, u = it / p.ns, t = it % p.na, ut = it / p.na;
       if (!UNPOOL) mbar_wait(&full[s], (uint32_t)(u & 1));          // E landed
       mbar_wait(&built[t], (uint32_t)(ut & 1));        // patch tiles (and, UNPOOL, the E tile) of the band written
       tc_fence_after();
@@ -407,6 +406,8 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
         else { mbar_arrive(&afree[t]); if (!UNPOOL) mbar_arrive(&empty[s]); }
       }
       __syncwarp();
+      if (++s == p.ns) { s = 0; ++u; }
+      if (++t == p.na) { t = 0; ++ut; }
     }
     if (leader) umma_commit(&done);
   } else if (warp >= 4) {
@@ -430,26 +431,47 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
     for (int i = 0; i < 8; ++i) { swz[i] = ((sw ^ i) << 4) + l3; asm volatile("" : "+r"(swz[i])); }
     const uint32_t ones_off = (uint32_t)p.Mrows * 128u + (((sw ^ (uint32_t)(p.Mrows & 7)) << 4) + l3);
     const uint32_t zero_src = zero_base;     // a_tail_bytes of zeros
-    int it = 0;
-    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x, ++it) {
-      const int s = it % p.ns, u = it / p.ns, t = it % p.na, ut = it / p.na;
+    // band-invariant geometry, computed once: this lane's pixel of the warp's own k-block (j = bw), and for the
+    // un-pooling variant the four E-tile addresses of each pooled item this thread expands
+    const int pxA = bw * 32 + lane, yyA = pxA / p.ox;
+    const uint32_t offA = (uint32_t)(yyA * p.ix + (pxA - yyA * p.ox)) * 4u;
+    constexpr int UI = 2;                                     // items per builder thread (host checks the band fits)
+    const int pw = p.ox >> 1, nq = p.nf >> 2;
+    uint32_t eoff[UI][4];
+    if (UNPOOL) {
+#pragma unroll
+      for (int i = 0; i < UI; ++i) {
+        const int item = (bw * 32 + lane) + i * (C3DF_BUILDERS * 32);
+        const int q = item % nq, pp = item / nq;
+        const int py = pp / pw, pxx = pp - py * pw;
+        const int f0 = q * 4;
+        const uint32_t sub = (uint32_t)(f0 >> 5) * (uint32_t)p.nkb * 4096u;
+        const uint32_t chunk = (uint32_t)((f0 & 31) >> 3), inner = (uint32_t)(f0 & 7) * 4u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {           // window element k = dy*2 + dx -> conv-output pixel of the band
+          const int pl = (2 * py + (k >> 1)) * p.ox + 2 * pxx + (k & 1);
+          eoff[i][k] = sub + (uint32_t)pl * 128u + ((chunk ^ (uint32_t)(pl & 3)) << 5) + inner;
+        }
+      }
+    }
+    int s = 0, u = 0, t = 0, ut = 0;
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
       const int band = unit % p.nbands, y0 = band * p.RB;
       int rb = p.RB;
       if (rb > p.oy - y0) rb = p.oy - y0;
       const int npx = rb * p.ox;
       const int lead = (y0 * p.ix) & 3;
       const uint32_t xs = x_base + (uint32_t)s * p.stage_bytes;
-      const int pw = p.ox >> 1, nq = p.nf >> 2;
       const int nitems = UNPOOL ? (rb >> 1) * pw * nq : 0;      // (pooled pixel of the band, channel quad), quads fastest
-      constexpr int UI = 2;                                     // items per builder thread (host checks the band fits)
-      mbar_wait(&full[s], (uint32_t)(u & 1));                       // raw rows landed
+      mbar_wait(&full[s], (uint32_t)(u & 1));                       // raw rows (and the pooled-resolution state) landed
       if (ut > 0) mbar_wait(&afree[t], (uint32_t)((ut - 1) & 1));   // MMAs of the band tile's previous use are done
       const int nkb_eff = (npx + 31) >> 5;
       for (int j = bw; j < nkb_eff; j += C3DF_BUILDERS) {
         const int px = j * 32 + lane;
         const bool valid = px < npx;
-        const int yy = px / p.ox, xx = px - yy * p.ox;
-        const uint32_t src = valid ? xs + (uint32_t)(lead + yy * p.ix + xx) * 4u : zero_src;
+        uint32_t off = offA;
+        if (j != bw) { const int yy = px / p.ox; off = (uint32_t)(yy * p.ix + (px - yy * p.ox)) * 4u; }
+        const uint32_t src = valid ? xs + (uint32_t)lead * 4u + off : zero_src;
         const uint32_t tile = a_base + (uint32_t)(t * p.nkb + j) * C3DF_A_SLOT;
         uint32_t v[NR];
 #pragma unroll
@@ -476,15 +498,9 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
             d1 = __uint_as_float(g1) > 0.f ? d1 + 0x1000u : 0u;
             d2 = __uint_as_float(g2) > 0.f ? d2 + 0x1000u : 0u;
             d3 = __uint_as_float(g3) > 0.f ? d3 + 0x1000u : 0u;
-            const int q = item % nq, pp = item / nq;
-            const int py = pp / pw, pxx = pp - py * pw;
-            const int f0 = q * 4;
-            const uint32_t sub = e_tile + (uint32_t)(f0 >> 5) * (uint32_t)p.nkb * 4096u;
-            const uint32_t chunk = (uint32_t)((f0 & 31) >> 3), inner = (uint32_t)(f0 & 7) * 4u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {           // window element k = dy*2 + dx -> conv-output pixel of the band
-              const int pl = (2 * py + (k >> 1)) * p.ox + 2 * pxx + (k & 1);
-              const uint32_t addr = sub + (uint32_t)pl * 128u + ((chunk ^ (uint32_t)(pl & 3)) << 5) + inner;
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t addr = e_tile + eoff[i][k];
               const uint32_t e0 = (mw >> k) & 1u ? d0 : 0u, e1 = (mw >> (8 + k)) & 1u ? d1 : 0u;
               const uint32_t e2 = (mw >> (16 + k)) & 1u ? d2 : 0u, e3 = (mw >> (24 + k)) & 1u ? d3 : 0u;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(e0), "r"(e1), "r"(e2), "r"(e3));
@@ -495,6 +511,8 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(&built[t]); mbar_arrive(&empty[s]); }   // tiles written; raw rows no longer read
+      if (++s == p.ns) { s = 0; ++u; }
+      if (++t == p.na) { t = 0; ++ut; }
     }
     // ---- final epilogue: partial[cta][r][NF] = accumulator of the even k-blocks + accumulator of the odd ones
     // M=64 accumulator (cta_group::1): row r lives in TMEM lane (r/16)*32 + r%16, 16 rows per 32-lane quadrant

@@ -90,8 +90,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // ===================================================================== TMA producer (whole warp loops, one
     // elected lane issues)
     const bool leader = elect_one_sync();
-    uint32_t bcount = 0;
-    int ss = 0;   // sub-stage counter: (stage, K pass)
+    int as = 0, au = 0;            // A-ring slot and its use count; B-ring likewise (running counters, no divisions)
+    uint32_t bs = 0, bu = 0;
     IG_T(tp);
     if (p.resident && leader) {
       mbar_expect_tx(&b_full[0], (uint32_t)(p.ntaps * p.nkp) * B_SLOT);
@@ -103,8 +103,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
     for (int st = blockIdx.x; st < p.nstages; st += gridDim.x) {
       const int grp = st / p.nbands, band = st - grp * p.nbands;
-      for (int kp = 0; kp < p.nkp; ++kp, ++ss) {
-        const int as = ss % p.na, au = ss / p.na;
+      for (int kp = 0; kp < p.nkp; ++kp) {
         { IG_T(t0); if (au > 0) mbar_wait(&a_empty[as], (uint32_t)((au - 1) & 1)); IG_ACC(0, t0); }
         if (leader) {
           mbar_expect_tx(&a_full[as], (uint32_t)(KH * p.G * p.IR * 128));
@@ -114,8 +113,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         p.y0 + band * p.RO, grp * p.G);
         }
         if (!p.resident) {
-          for (int tap = 0; tap < p.ntaps; ++tap, ++bcount) {
-            const uint32_t bs = bcount % (uint32_t)p.nbs, bu = bcount / (uint32_t)p.nbs;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
             if (bu > 0) mbar_wait(&b_empty[bs], (bu - 1) & 1);
             if (leader) {
               mbar_expect_tx(&b_full[bs], B_SLOT);
@@ -123,8 +121,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               for (int h = 0; h < KH; ++h)
                 tma_load_3d(b_base0 + bs * B_SLOT + h * NB * 128, &mapB, &b_full[bs], (kp * KH + h) * 32, n0, tap);
             }
+            if (++bs == (uint32_t)p.nbs) { bs = 0; ++bu; }
           }
         }
+        if (++as == p.na) { as = 0; ++au; }
       }
     }
     IG_ACC(1, tp);
@@ -136,15 +136,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = idesc_tf32(128, NB);
     const uint32_t half_units = half_bytes >> 4;
-    uint32_t bcount = 0;
-    int it = 0, ss = 0;
+    uint32_t bsm = 0, bum = 0;       // B-ring slot / use count of the next tap (running counters)
+    int it = 0, as = 0, au = 0;
     IG_T(tm);
     for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
       const int acc_set = it & 1, tu = it >> 1;
       { IG_T(t0); if (tu > 0) mbar_wait(&t_empty[acc_set], (uint32_t)((tu - 1) & 1)); if (wsel == 0) IG_ACC(2, t0); }
       const uint32_t acc = tmem + acc_set * IG_ACCSET_COLS;
-      for (int kp = 0; kp < p.nkp; ++kp, ++ss) {
-        const int as = ss % p.na, au = ss / p.na;
+      for (int kp = 0; kp < p.nkp; ++kp) {
         { IG_T(t0); mbar_wait(&a_full[as], (uint32_t)(au & 1)); if (wsel == 0) IG_ACC(3, t0); }
         tc_fence_after();
         const uint64_t a_desc0 = desc_k_sw128(base + as * a_slot_bytes);
@@ -155,10 +154,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             bs = (uint32_t)(kp * p.ntaps + tap);
             if (ss == 0 && tap == 0) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
           } else {
-            bs = bcount % (uint32_t)p.nbs;
-            mbar_wait(&b_full[bs], (bcount / (uint32_t)p.nbs) & 1);
+            bs = bsm;
+            mbar_wait(&b_full[bs], bum & 1);
             tc_fence_after();
-            ++bcount;
+            if (++bsm == (uint32_t)p.nbs) { bsm = 0; ++bum; }
           }
           const uint64_t a_tap = a_desc0 + (uint64_t)((uint32_t)(ty * p.PW + tx) * 8u);   // 128 B per pixel row = 8 units
           const uint64_t b_tap = desc_k_sw128(b_base0 + bs * B_SLOT);
@@ -179,6 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (!p.resident && leader) umma_commit(&b_empty[bs]);
         }
         if (leader) umma_commit(&a_empty[as]);
+        if (++as == p.na) { as = 0; ++au; }
       }
       if (leader) umma_commit(&t_full[acc_set]);
     }
