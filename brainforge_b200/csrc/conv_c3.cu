@@ -157,6 +157,23 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
     int it = 0;
     const int m = quad * 32 + lane;
     const int r = m / p.ix, x = m - r * p.ix;
+    // POOL: tile-invariant geometry of the (at most two) pooled items this thread produces per tile and channel block:
+    // item = (pooled position of the tile, channel quad), quads fastest
+    bool pi_ok[2];
+    int pi_y2[2], pi_soff[2], pi_ooff[2];
+    {
+      const int pw = p.ox >> 1, npool = (p.RT >> 1) * pw;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int item = m + i * 128;
+        const int q = item & 7, pp = item >> 3;
+        const int py = pp / (pw > 0 ? pw : 1), pxx = pp - py * pw;
+        pi_ok[i] = POOL && item < npool * 8;
+        pi_y2[i] = 2 * py;
+        pi_soff[i] = (2 * py * p.ix + 2 * pxx) * C3_STAGE_LD + q * 4;
+        pi_ooff[i] = (py * pw + pxx) * p.N + q * 4;
+      }
+    }
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       if ((it & 3) != grp) continue;
       const int acc_set = it & 3, tu = it >> 2;
@@ -191,13 +208,11 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
             // the four warps of the group have staged the whole tile [128 positions][32 channels]
             asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
             const float* tile_stg = stg - quad * 32 * C3_STAGE_LD;
-            const int pw = p.ox >> 1, npool = (p.RT >> 1) * pw, poy = p.oy >> 1;
-            for (int item = quad * 32 + lane; item < npool * 8; item += 128) {
-              const int q = item & 7, pp = item >> 3;
-              const int py = pp / pw, pxx = pp - py * pw;
-              const int yg = t * p.RT + 2 * py;                    // first conv row of the window
-              if (yg + 1 < p.oy) {
-                const float* s00 = tile_stg + (2 * py * p.ix + 2 * pxx) * C3_STAGE_LD + q * 4;
+            const size_t obase = ((size_t)(b * (p.oy >> 1) + ((t * p.RT) >> 1)) * (p.ox >> 1)) * p.N + n0 + cb;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (pi_ok[i] && t * p.RT + pi_y2[i] + 1 < p.oy) {
+                const float* s00 = tile_stg + pi_soff[i];
                 const float4 a = *reinterpret_cast<const float4*>(s00);
                 const float4 bq = *reinterpret_cast<const float4*>(s00 + C3_STAGE_LD);
                 const float4 c = *reinterpret_cast<const float4*>(s00 + p.ix * C3_STAGE_LD);
@@ -210,7 +225,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
                 mk.y = (unsigned char)((a.y == mx.y) | ((bq.y == mx.y) << 1) | ((c.y == mx.y) << 2) | ((d.y == mx.y) << 3));
                 mk.z = (unsigned char)((a.z == mx.z) | ((bq.z == mx.z) << 1) | ((c.z == mx.z) << 2) | ((d.z == mx.z) << 3));
                 mk.w = (unsigned char)((a.w == mx.w) | ((bq.w == mx.w) << 1) | ((c.w == mx.w) << 2) | ((d.w == mx.w) << 3));
-                const size_t o = ((size_t)(b * poy + (yg >> 1)) * pw + pxx) * p.N + n0 + cb + q * 4;
+                const size_t o = obase + pi_ooff[i];
                 *reinterpret_cast<float4*>(out + o) = mx;
                 *reinterpret_cast<uchar4*>(p.mask + o) = mk;
               }

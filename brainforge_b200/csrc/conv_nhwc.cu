@@ -152,7 +152,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           uint32_t bs;
           if (p.resident) {
             bs = (uint32_t)(kp * p.ntaps + tap);
-            if (ss == 0 && tap == 0) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+            if (as == 0 && au == 0 && tap == 0) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
           } else {
             bs = bsm;
             mbar_wait(&b_full[bs], bum & 1);
