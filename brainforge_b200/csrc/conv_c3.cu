@@ -627,7 +627,7 @@ static int c3_forward_impl(const float* X, const float* F, const float* bias, fl
   }
   p.tiles_per_img = (oy + p.RT - 1) / p.RT; p.ntiles = im * p.tiles_per_img; p.fy = fy; p.fx = fx; p.ic = ic; p.N = nf;
   p.box_rows = (128 + (fy - 1) * ix + 4 + 7) / 8 * 8;
-  p.na = getenv("BF_C3_NA") ? atoi(getenv("BF_C3_NA")) : 24;   // tiles in flight: the loads are small (3 KB), latency-bound
+  p.na = 16;   // tiles in flight (8..32 measured equal: the kernel is not load-bound)
   while (p.na > 4 && (size_t)p.na * p.box_rows * 16 > 96 * 1024) --p.na;
   p.pool_relu = pool_relu; p.mask = mask;
   p.X4 = (const float4*)ws; p.npix = (long long)im * IR;

@@ -3,7 +3,7 @@
 // (gemm_umma.cuh) was issue-bound on plain matrices: the LSTM gate GEMM per time step (A = Z[t], B = W^T) and the
 // LSTM deltaZ GEMM (A = dgates[t], B = W as stored) -- atomic/recurrent_op.py:62,106.
 //
-// 128 x BN tiles, K blocks of 32 (one 128-byte swizzle row), 4-stage TMA ring, one MMA-issuing warp, two accumulator
+// 128 x BN tiles, K blocks of 32 (one 128-byte swizzle row), 6-8-stage TMA ring, one MMA-issuing warp, two accumulator
 // sets in TMEM so that the epilogue of a tile overlaps the MMAs of the next, persistent CTAs.  The epilogue functor is
 // the same `store(m, n, value, 0)` the other contraction cores use.
 #pragma once
@@ -12,17 +12,17 @@
 namespace bf {
 
 constexpr int GT_THREADS = 256;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM, warp 3 spare, warps 4-7 epilogue
-constexpr int GT_STAGES = 4;
+constexpr int GT_SMEM_RING = 192 * 1024;   // ring depth = as many stages as fit: a CTA streaming its K range alone is latency-bound
 
 struct GtParams {
-  int M, N, K, nkb, m_tiles, n_tiles, ntiles;
+  int M, N, K, nkb, m_tiles, n_tiles, ntiles, nstages;
 };
 
 template <int BN, class EP>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GtParams p, EP ep) {
   extern __shared__ int dyn_smem[];
-  __shared__ __align__(8) uint64_t full[GT_STAGES], empty[GT_STAGES], t_full[2], t_empty[2];
+  __shared__ __align__(8) uint64_t full[8], empty[8], t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
   constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -33,7 +33,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -44,11 +44,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
   if (warp == 0) {
     const bool leader = elect_one_sync();
-    int g = 0;
+    int s = 0, u = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
-      for (int kb = 0; kb < p.nkb; ++kb, ++g) {
-        const int s = g % GT_STAGES, u = g / GT_STAGES;
+      for (int kb = 0; kb < p.nkb; ++kb) {
         if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
         if (leader) {
           const uint32_t st = base + (uint32_t)s * STAGE;
@@ -56,18 +55,18 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           tma_load_2d(st, &mapA, &full[s], kb * 32, mt * 128);
           tma_load_2d(st + A_BYTES, &mapB, &full[s], kb * 32, nt * BN);
         }
+        if (++s == p.nstages) { s = 0; ++u; }
       }
     }
   } else if (warp == 1) {
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = idesc_tf32(128, BN);
-    int g = 0, it = 0;
+    int s = 0, u = 0, it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int set = it & 1, tu = it >> 1;
       if (tu > 0) mbar_wait(&t_empty[set], (uint32_t)((tu - 1) & 1));
       const uint32_t acc = tmem + (uint32_t)set * BN;
-      for (int kb = 0; kb < p.nkb; ++kb, ++g) {
-        const int s = g % GT_STAGES, u = g / GT_STAGES;
+      for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(&full[s], (uint32_t)(u & 1));
         tc_fence_after();
         if (leader) {
@@ -78,6 +77,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             umma_tf32(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
           umma_commit(&empty[s]);
         }
+        if (++s == p.nstages) { s = 0; ++u; }
       }
       if (leader) umma_commit(&t_full[set]);
       __syncwarp();
@@ -142,12 +142,14 @@ int launch_gemm_tma(const float* A, const float* B, int M, int N, int K, EP ep, 
     if (!tma_make_map(&mB, B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return fail(BF_ERR_CUDA, "gemm_tma: cuTensorMapEncodeTiled failed (B)");
   }
   const int ctas = p.ntiles < num_sms() ? p.ntiles : num_sms();
+  p.nstages = GT_SMEM_RING / (128 * 128 + bn * 128);
+  if (p.nstages > 8) p.nstages = 8;
   if (bn == 128) {
-    const size_t smem = 1024 + (size_t)GT_STAGES * (128 * 128 + 128 * 128);
+    const size_t smem = 1024 + (size_t)p.nstages * (128 * 128 + 128 * 128);
     BF_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<128, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_tma_kernel<128, EP><<<ctas, GT_THREADS, smem, s>>>(mA, mB, p, ep);
   } else {
-    const size_t smem = 1024 + (size_t)GT_STAGES * (128 * 128 + 64 * 128);
+    const size_t smem = 1024 + (size_t)p.nstages * (128 * 128 + 64 * 128);
     BF_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<64, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_tma_kernel<64, EP><<<ctas, GT_THREADS, smem, s>>>(mA, mB, p, ep);
   }
