@@ -43,6 +43,8 @@ SIGNATURES = {
     "bf_act_backward": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),
     "bf_dense_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "bf_dense_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "bf_dense_forward_cl": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "bf_dense_backward_cl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "bf_conv_forward": (_i, [_vp, _vp, _vp, _vp] + [_i] * 11 + [_vp]),
     "bf_conv_backward": (_i, [_vp] * 6 + [_i] * 8 + [_vp]),
     "bf_conv_nhwc_supported": (_i, [_i] * 4),

@@ -109,6 +109,15 @@ class DenseOp:
     @staticmethod
     def forward(X, W, b=None, activation="linear"):
         x, w = as_device(X), as_device(W)
+        if x.cl_flat is not None:
+            if w.shape[1] <= 32 and x.shape[1] == w.shape[0]:
+                c, y, xx = x.cl_flat
+                bd = as_device(b) if b is not None else None
+                out = DeviceArray.empty(x.shape[0], w.shape[1])
+                call(L.bf_dense_forward_cl, x.pptr, w.ptr, bd.ptr if bd is not None else _NULL, out.ptr, x.shape[0], c, y * xx,
+                     w.shape[1], _lib.ACT[activation], stream_ptr())
+                return out
+            x = x.to_nchw()
         m, k = x.shape
         k2, n = w.shape
         if k != k2:
@@ -122,6 +131,17 @@ class DenseOp:
     @staticmethod
     def backward(X, E, W, dW=None, db=None, accumulate=False, need_dX=True):
         x, e, w = as_device(X), as_device(E), as_device(W)
+        if x.cl_flat is not None:
+            if w.shape[1] <= 32 and len(x) > 0:
+                c, y, xx = x.cl_flat
+                m, n = x.shape[0], w.shape[1]
+                dW = DeviceArray.empty(*w.shape) if dW is None else dW
+                db = DeviceArray.empty(n) if db is None else db
+                dX = DeviceArray(DeviceArray.empty(m, c * y * xx).t, cl_flat=x.cl_flat) if need_dX else None
+                call(L.bf_dense_backward_cl, x.pptr, e.ptr, w.ptr, dW.ptr, db.ptr, dX.pptr if dX is not None else _NULL, m, c,
+                     y * xx, n, 1 if accumulate else 0, stream_ptr())
+                return dW, db, dX
+            x = x.to_nchw()
         m, k = x.shape
         n = w.shape[1]
         dW = DeviceArray.empty(k, n) if dW is None else dW

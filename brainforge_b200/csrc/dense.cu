@@ -57,7 +57,7 @@ constexpr int SKINNY_ROWS = 2;          // rows per warp iteration (forward): mo
 template <int NT>
 __global__ void __launch_bounds__(256)
 dense_skinny_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
-                        float* __restrict__ out, int m, int k, int n, int act) {
+                        float* __restrict__ out, int m, int k, int n, int act, int pc, int phw) {
   extern __shared__ __align__(16) float sw[];
   constexpr int PITCH = NT == 4 ? 4 : NT + 4;
   pdl_launch_dependents();
@@ -77,7 +77,11 @@ dense_skinny_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * blockDim.x;
-      if (i < total) { const int kk = i / n; sw[kk * PITCH + (i - kk * n)] = v[u]; }
+      if (i < total) {
+        const int kl = i / n;                                         // logical row of W: feature (c, yx) of an NCHW flatten
+        const int kk = pc ? (kl % phw) * pc + kl / phw : kl;          // row of X's PHYSICAL (channels-last) feature order
+        sw[kk * PITCH + (i - kl * n)] = v[u];
+      }
     }
   }
   __syncthreads();
@@ -136,7 +140,8 @@ dense_skinny_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W
 template <int NT>
 __global__ void __launch_bounds__(256)
 dense_skinny_bwd_kernel(const float* __restrict__ X, const float* __restrict__ E, const float* __restrict__ W,
-                        float* __restrict__ partial, float* __restrict__ dX, int m, int k, int n, int rows_per_chunk) {
+                        float* __restrict__ partial, float* __restrict__ dX, int m, int k, int n, int rows_per_chunk,
+                        int pc, int phw) {
   extern __shared__ __align__(16) float se[];     // [rows_per_chunk][NT]
   pdl_launch_dependents();
   pdl_wait();
@@ -151,9 +156,11 @@ dense_skinny_bwd_kernel(const float* __restrict__ X, const float* __restrict__ E
   const int kk = blockIdx.y * blockDim.x + threadIdx.x;
   float* part = partial + (size_t)blockIdx.x * (k + 1) * n;
   if (kk < k) {
+    // kk = PHYSICAL column of X / dX; kl = the row of W / dW it belongs to (differs for a channels-last flatten)
+    const int kl = pc ? (kk % pc) * phw + kk / pc : kk;
     float w[NT], acc[NT];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { w[j] = j < n ? __ldg(W + (size_t)kk * n + j) : 0.f; acc[j] = 0.f; }
+    for (int j = 0; j < NT; ++j) { w[j] = j < n ? __ldg(W + (size_t)kl * n + j) : 0.f; acc[j] = 0.f; }
     for (int r0 = 0; r0 < rows; r0 += 8) {
       float xv[8];
 #pragma unroll
@@ -179,7 +186,7 @@ dense_skinny_bwd_kernel(const float* __restrict__ X, const float* __restrict__ E
     }
 #pragma unroll
     for (int j = 0; j < NT; ++j)
-      if (j < n) part[(size_t)kk * n + j] = acc[j];
+      if (j < n) part[(size_t)kl * n + j] = acc[j];
   }
   if (blockIdx.y == 0 && threadIdx.x < n) {       // db partial = column sums of the chunk's E rows
     float sacc = 0.f;
@@ -196,7 +203,7 @@ static inline bool skinny_ok(int m, int k, int n) {
 }
 
 static int launch_skinny_fwd(const float* X, const float* W, const float* b, float* out, int m, int k, int n, int act,
-                             cudaStream_t s) {
+                             int pc, int phw, cudaStream_t s) {
   const int nt = skinny_nt(n);
   const size_t smem = (size_t)k * (nt == 4 ? 4 : nt + 4) * 4;
   int grid = (m + 8 * SKINNY_ROWS - 1) / (8 * SKINNY_ROWS);
@@ -204,7 +211,7 @@ static int launch_skinny_fwd(const float* X, const float* W, const float* b, flo
 #define BF_SK(NT_)                                                                                                  \
   if (nt == NT_) {                                                                                                  \
     BF_CUDA(cudaFuncSetAttribute(dense_skinny_fwd_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    launch_pdl(dense_skinny_fwd_kernel<NT_>, dim3(grid), dim3(256), smem, s, X, W, b, out, m, k, n, act);                               \
+    launch_pdl(dense_skinny_fwd_kernel<NT_>, dim3(grid), dim3(256), smem, s, X, W, b, out, m, k, n, act, pc, phw);                               \
   }
   BF_SK(4) BF_SK(8) BF_SK(16) BF_SK(32)
 #undef BF_SK
@@ -214,7 +221,7 @@ static int launch_skinny_fwd(const float* X, const float* W, const float* b, flo
 }
 
 static int launch_skinny_bwd(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m,
-                             int k, int n, int accumulate, cudaStream_t s) {
+                             int k, int n, int accumulate, int pc, int phw, cudaStream_t s) {
   const int nt = skinny_nt(n);
   int rows_per_chunk = (m + 127) / 128;
   if (rows_per_chunk < 16) rows_per_chunk = 16;
@@ -225,7 +232,7 @@ static int launch_skinny_bwd(const float* X, const float* E, const float* W, flo
   if (rc) return rc;
   dim3 grid(chunks, (k + 255) / 256);
   const size_t smem = (size_t)rows_per_chunk * nt * 4;
-#define BF_SK(NT_) if (nt == NT_) launch_pdl(dense_skinny_bwd_kernel<NT_>, dim3(grid), dim3(256), smem, s, X, E, W, (float*)ws, dX, m, k, n, rows_per_chunk);
+#define BF_SK(NT_) if (nt == NT_) launch_pdl(dense_skinny_bwd_kernel<NT_>, dim3(grid), dim3(256), smem, s, X, E, W, (float*)ws, dX, m, k, n, rows_per_chunk, pc, phw);
   BF_SK(4) BF_SK(8) BF_SK(16) BF_SK(32)
 #undef BF_SK
   BF_LAUNCH_CHECK();
@@ -246,7 +253,7 @@ int bf_dense_forward(const float* X, const float* W, const float* b, float* out,
   if (m == 0) return BF_OK;
   BF_REQUIRE(X && W && out, BF_ERR_ARG, "bf_dense_forward: null pointer");
   cudaStream_t s = as_stream(stream);
-  if (skinny_ok(m, k, n)) return launch_skinny_fwd(X, W, b, out, m, k, n, act, s);
+  if (skinny_ok(m, k, n)) return launch_skinny_fwd(X, W, b, out, m, k, n, act, 0, 0, s);
   int ep_act = act == BF_ACT_SOFTMAX ? BF_ACT_LINEAR : act;
   int rc = BF_OK;
   {
@@ -265,7 +272,7 @@ int bf_dense_backward(const float* X, const float* E, const float* W, float* dW,
   BF_REQUIRE(m >= 0 && k > 0 && n > 0, BF_ERR_ARG, "bf_dense_backward: bad shape m=%d k=%d n=%d", m, k, n);
   BF_REQUIRE(W && dW && (m == 0 || (X && E)), BF_ERR_ARG, "bf_dense_backward: null pointer");
   cudaStream_t s = as_stream(stream);
-  if (skinny_ok(m, k, n)) return launch_skinny_bwd(X, E, W, dW, db, dX, m, k, n, accumulate, s);
+  if (skinny_ok(m, k, n)) return launch_skinny_bwd(X, E, W, dW, db, dX, m, k, n, accumulate, 0, 0, s);
   int rc;
   // dW = X^T @ E with a virtual all-ones row appended to X^T: row k of the product is db = E.sum(0).
   {
@@ -299,6 +306,26 @@ int bf_dense_backward(const float* X, const float* E, const float* W, float* dW,
     if (rc) return rc;
   }
   return BF_OK;
+}
+
+// Dense layer directly behind a channels-last convolutional block: X (m, hw*chan) holds the features of an
+// (chan, hw) activation in PHYSICAL channels-last order (yx, c) while W (k, n) is indexed by the reference's NCHW flatten
+// (c, yx) -- layers/core.py:82-86 + layers/core.py:27-39.  The permutation is applied while W is staged / addressed, so
+// the two layout-change passes around Flatten disappear.  n <= 32 only (the skinny kernels); dX comes back in X's order.
+int bf_dense_forward_cl(const float* X, const float* W, const float* b, float* out, int m, int chan, int hw, int n, int act,
+                        void* stream) {
+  const int k = chan * hw;
+  BF_REQUIRE(m >= 0 && chan > 0 && hw > 0 && n > 0 && skinny_ok(m > 0 ? m : 1, k, n), BF_ERR_ARG, "bf_dense_forward_cl: unsupported shape");
+  BF_REQUIRE(act >= BF_ACT_LINEAR && act <= BF_ACT_SOFTMAX, BF_ERR_ARG, "bf_dense_forward_cl: bad activation %d", act);
+  if (m == 0) return BF_OK;
+  return launch_skinny_fwd(X, W, b, out, m, k, n, act, chan, hw, as_stream(stream));
+}
+
+int bf_dense_backward_cl(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int chan,
+                         int hw, int n, int accumulate, void* stream) {
+  const int k = chan * hw;
+  BF_REQUIRE(m > 0 && chan > 0 && hw > 0 && n > 0 && skinny_ok(m, k, n), BF_ERR_ARG, "bf_dense_backward_cl: unsupported shape");
+  return launch_skinny_bwd(X, E, W, dW, db, dX, m, k, n, accumulate, chan, hw, as_stream(stream));
 }
 
 }  // extern "C"

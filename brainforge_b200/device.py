@@ -105,12 +105,16 @@ class DeviceArray:
 
     __array_priority__ = 100
 
-    def __init__(self, tensor, nhwc=False):
+    def __init__(self, tensor, nhwc=False, cl_flat=None):
         assert tensor.dtype == torch.float32 and tensor.is_cuda and tensor.is_contiguous(), \
             (tensor.dtype, tensor.device, tensor.is_contiguous())
         assert not nhwc or tensor.dim() == 4
         self.t = tensor
         self.nhwc = nhwc
+        # (c, y, x) when this 2-D array is the FLATTENED view of a channels-last activation: features are stored in
+        # (y, x, c) order, the logical (reference) order is (c, y, x).  Only the skinny Dense kernels read it as is.
+        self.cl_flat = cl_flat
+        assert cl_flat is None or (tensor.dim() == 2 and not nhwc)
 
     # ---- construction
     @staticmethod
@@ -126,7 +130,7 @@ class DeviceArray:
 
     @staticmethod
     def empty_like(other):
-        return DeviceArray(torch.empty_like(other.t), nhwc=other.nhwc)
+        return DeviceArray(torch.empty_like(other.t), nhwc=other.nhwc, cl_flat=other.cl_flat)
 
     @staticmethod
     def zeros(*shape):
@@ -163,6 +167,10 @@ class DeviceArray:
     # ---- layout
     def to_nchw(self):
         """The reference's index order; a device transpose when the storage is channels-last."""
+        if self.cl_flat is not None:
+            c, y, x = self.cl_flat
+            m = self.t.shape[0]
+            return DeviceArray(DeviceArray(self.t.view(m, y, x, c), nhwc=True).to_nchw().t.view(m, c * y * x))
         if not self.nhwc:
             return self
         im, y, x, c = self.t.shape
@@ -174,6 +182,7 @@ class DeviceArray:
     def to_nhwc(self):
         if self.nhwc:
             return self
+        assert self.cl_flat is None
         im, c, y, x = self.t.shape
         out = DeviceArray.empty_nhwc(im, c, y, x)
         if self.size:
@@ -192,7 +201,7 @@ class DeviceArray:
 
     @property
     def ptr(self):
-        if self.nhwc:
+        if self.nhwc or self.cl_flat is not None:
             raise RuntimeError("layout-unaware access to a channels-last DeviceArray (use .to_nchw() or .pptr)")
         return ctypes.c_void_p(self.t.data_ptr())
 

@@ -112,10 +112,22 @@ class Reshape(NoParamMixin, LayerBase):
             self.shape = int(np.prod(brain.outshape)),
         super().connect(brain)
 
+    _next_layer = None
+
     def _fwd(self, x):
+        nxt = self._next_layer
+        if (x.nhwc and not self._standalone and len(self.shape) == 1 and type(nxt).__name__ == "Dense"
+                and nxt.neurons <= 32):
+            # channels-last block -> skinny Dense: no data moves; the Dense kernels index W through the (c,y,x) <-> (y,x,c)
+            # permutation (bf_dense_forward_cl), so the layout-change pass disappears
+            im, c, y, xx = x.shape
+            return DeviceArray(x.t.view(im, c * y * xx), cl_flat=(c, y, xx))
         return atomic.ReshapeOp.forward(x, self.shape)
 
     def _bwd(self, delta):
+        if getattr(delta, "cl_flat", None) is not None:
+            c, y, xx = delta.cl_flat
+            return DeviceArray(delta.t.view(delta.t.shape[0], y, xx, c), nhwc=True)
         return atomic.ReshapeOp.forward(delta, self.inshape)
 
     @property

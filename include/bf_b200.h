@@ -95,6 +95,14 @@ BF_API int bf_dense_forward(const float* X, const float* W, const float* b, floa
 BF_API int bf_dense_backward(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int k,
                       int n, int accumulate, int precision, void* stream);
 
+/* Dense layer (n <= 32 outputs) directly behind a channels-last convolutional block: X / dX (m, hw*chan) are in
+ * physical channels-last feature order (yx, c); W / dW (chan*hw, n) keep the reference's NCHW-flatten row order
+ * (c, yx) (layers/core.py:82-86 Flatten + :27-39 Dense).  Saves the two layout-change passes around Flatten. */
+BF_API int bf_dense_forward_cl(const float* X, const float* W, const float* b, float* out, int m, int chan, int hw, int n, int act,
+                        void* stream);
+BF_API int bf_dense_backward_cl(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int chan,
+                         int hw, int n, int accumulate, void* stream);
+
 /* ---- convolution: atomic/tensor_op.py:6-75, llatomic/lltensor_op.py:9-40,75-121 ---- */
 /* Y = act(corr(A,F)) + bias   (bias AFTER the activation: layers/tensor.py:77-78).
  * A (im,ic,iy,ix) NCHW, F (nf,ic,fy,fx), bias (nf) or NULL, stride 1.

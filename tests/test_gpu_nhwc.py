@@ -167,6 +167,30 @@ def test_filter_gradient_with_fused_unpool(bf, O, shape, relu):
     close(dF, rF); close(db.numpy().ravel(), rb.ravel())
 
 
+@pytest.mark.parametrize("m,c,y,x,n,act", [(37, 128, 2, 2, 10, "softmax"), (5, 32, 3, 5, 7, "linear"), (300, 64, 1, 1, 32, "tanh"),
+                                           (1, 4, 2, 3, 1, "sigmoid")])
+def test_dense_behind_channels_last_flatten(bf, O, m, c, y, x, n, act):
+    """bf_dense_forward_cl / bf_dense_backward_cl: a Dense layer fed by the flattened view of a channels-last
+    activation (features stored (y,x,c), weights indexed by the reference's (c,y,x) flatten) == the reference on the
+    NCHW flatten; exact FP32 FMA kernels, so the FP32 bound applies even on the TF32 path."""
+    rs = np.random.RandomState(m + c + n)
+    A = rs.randn(m, c, y, x)
+    W, b, E = rs.randn(c * y * x, n) * 0.2, rs.randn(n), rs.randn(m, n)
+    a = bf.DeviceArray.from_host(A).to_nhwc()
+    flat = bf.DeviceArray(a.t.view(m, c * y * x), cl_flat=(c, y, x))
+    assert np.array_equal(flat.numpy(np.float32), A.reshape(m, -1).astype(np.float32))      # readers still see NCHW order
+    op = bf.atomic.DenseOp()
+    w, bd = bf.DeviceArray.from_host(W), bf.DeviceArray.from_host(b)
+    out = op.forward(flat, w, bd, activation=act)
+    ref = O.act_forward(act, O.dense_forward(A.reshape(m, -1), W, b))
+    close(out, ref, 1e-5)
+    dW, db, dX = op.backward(flat, bf.DeviceArray.from_host(E), w)
+    rW, rb, rX = O.dense_backward(A.reshape(m, -1), E, W)
+    close(dW, rW, 1e-5); close(db, rb, 1e-5)
+    assert dX.cl_flat == (c, y, x)
+    close(dX, rX, 1e-5)                                                                    # .numpy() converts back
+
+
 def _cfg3(bf, batch, **kw):
     ishape, spec, cost, optimizer = CFG["cfg3"]
     return build_b200(ishape, spec, cost, optimizer, seed=1234, **kw), build_oracle(ishape, spec, cost, optimizer, seed=1234)
@@ -186,6 +210,7 @@ def test_cfg3_runs_channels_last_and_matches(bf, O):
     pools = [l for l in net.layers.layers if isinstance(l, PoolLayer)]
     acts = [l for l in net.layers.layers[1:] if isinstance(l, Activation)]
     assert all(c.output.nhwc for c in convs) and all(p.output.nhwc and p._fused_relu for p in pools)
+    assert net.layers.layers[-1].inputs.cl_flat == (128, 2, 2)      # Flatten moved no data; Dense reads channels-last
     assert not convs[0].inputs.nhwc and convs[1].inputs.nhwc
     # every array a caller can read keeps the reference's NCHW order and values (lazy ReLU outputs included)
     for layer, ol in zip(net.layers.layers[1:], ora.L):
