@@ -66,6 +66,7 @@ SIGNATURES = {
     "bf_pool_nhwc_backward": (_i, [_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "bf_cost_delta": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bf_cost_value": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp]),
+    "bf_cost_delta_value": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bf_accuracy": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "bf_lstm_forward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
     "bf_lstm_backward": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),

@@ -49,11 +49,13 @@ inline int ew_grid(size_t items, int threads, int ctas_per_sm = 8) {
 }
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
-// Every kernel of the training step is launched with cudaLaunchAttributeProgrammaticStreamSerialization and calls
-// pdl_launch_dependents() on entry and pdl_wait() before its first read of anything an earlier kernel wrote: the NEXT
-// kernel's launch latency and prologue (barrier init, TMEM allocation, shared-memory clearing) then overlap this
-// kernel's execution instead of following its last CTA.  The step is ~28 launches; at the 8-GPU shard size (512
-// samples) their fixed cost is more than half of the step.  BF_PDL=0 disables the attribute (the device calls become no-ops).
+// Every kernel of the training step can be launched with cudaLaunchAttributeProgrammaticStreamSerialization; it calls
+// pdl_launch_dependents() on entry and pdl_wait() before its first read of anything an earlier kernel wrote, so that
+// the NEXT kernel's launch latency and prologue (barrier init, TMEM allocation, shared-memory clearing) overlap this
+// kernel's execution.  MEASURED on B200 (cfg3, CUDA graph): 0.830 ms/step without vs 0.875 ms with the attribute at
+// batch 4096, 0.225 vs 0.231 ms at batch 512 -- the persistent kernels own their SMs (200 KB of shared memory each), so
+// an early-launched dependent cannot become resident anyway, and the waiting CTAs of the small kernels only get in the
+// way.  The attribute is therefore OFF by default (BF_PDL=1 enables it); without it the device calls are no-ops.
 bool pdl_enabled();
 template <typename K, typename... Args>
 inline cudaError_t launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {

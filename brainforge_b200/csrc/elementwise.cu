@@ -102,15 +102,21 @@ __global__ void cost_delta_kernel(const float* __restrict__ o, const float* __re
 // and the last CTA to arrive (atomic ticket) adds the partials in index order.
 __device__ unsigned int g_reduce_ticket = 0;
 
+// delta != null: also writes delta = (o - t) * (w ? w[row] : 1) -- CostFunction.derivative (metrics/costs.py:19-21)
+// and the cost value of the same forward pass in ONE pass over the predictions (learner/backpropagation.py:19-27)
 template <int KIND>
 __global__ void cost_value_kernel(const float* __restrict__ o, const float* __restrict__ t, size_t total,
-                                  double* __restrict__ partial, float* __restrict__ result) {
+                                  double* __restrict__ partial, float* __restrict__ result, float* __restrict__ delta,
+                                  const float* __restrict__ w, int n) {
   __shared__ double sm[32];
   __shared__ bool last;
+  pdl_launch_dependents();
+  pdl_wait();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   double acc = 0.0;
   for (; i < total; i += stride) {
     float ov = o[i], tv = t[i];
+    if (delta) delta[i] = (ov - tv) * (w ? w[i / n] : 1.0f);
     if (KIND == BF_COST_MSE) {
       float d = ov - tv;
       acc += 0.5 * (double)d * (double)d;
@@ -310,11 +316,34 @@ int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, fl
   int rc = workspace_require((size_t)grid * sizeof(double), &ws);
   if (rc) return rc;
   if (kind == BF_COST_MSE)
-    cost_value_kernel<BF_COST_MSE><<<grid, 256, 0, s>>>(out, tgt, total, (double*)ws, result);
+    launch_pdl(cost_value_kernel<BF_COST_MSE>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, (float*)nullptr, (const float*)nullptr, n);
   else if (kind == BF_COST_CXENT)
-    cost_value_kernel<BF_COST_CXENT><<<grid, 256, 0, s>>>(out, tgt, total, (double*)ws, result);
+    launch_pdl(cost_value_kernel<BF_COST_CXENT>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, (float*)nullptr, (const float*)nullptr, n);
   else
     return fail(BF_ERR_ARG, "bf_cost_value: unknown cost kind %d", kind);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+// delta = (out - tgt) * w[row]  AND  result[0] = cost(out, tgt)  in one kernel
+int bf_cost_delta_value(int kind, const float* out, const float* tgt, const float* w, float* delta, float* result, int m, int n,
+                        void* stream) {
+  BF_REQUIRE(m >= 0 && n > 0 && result && (m == 0 || (out && tgt && delta)), BF_ERR_ARG, "bf_cost_delta_value: bad arguments");
+  BF_REQUIRE(kind == BF_COST_MSE || kind == BF_COST_CXENT, BF_ERR_ARG, "bf_cost_delta_value: unknown cost kind %d", kind);
+  cudaStream_t s = as_stream(stream);
+  size_t total = (size_t)m * n;
+  if (total == 0) {
+    BF_CUDA(cudaMemsetAsync(result, 0, sizeof(float), s));
+    return BF_OK;
+  }
+  int grid = ew_grid(total, 256, 1);
+  void* ws = nullptr;
+  int rc = workspace_require((size_t)grid * sizeof(double), &ws);
+  if (rc) return rc;
+  if (kind == BF_COST_MSE)
+    launch_pdl(cost_value_kernel<BF_COST_MSE>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, delta, w, n);
+  else
+    launch_pdl(cost_value_kernel<BF_COST_CXENT>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, delta, w, n);
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

@@ -82,8 +82,7 @@ class Backpropagation(Learner):
         """Device-only part of learn_batch (capturable in a CUDA graph: no host sync inside)."""
         sc = self.layers.scalars()
         preds = self.layers._fwd(x)
-        delta = self.cost.derivative(preds, y, wd)
-        self.cost.value_into(preds, y, sc[0:1])          # cost of the PRE-update forward pass (:26)
+        delta = self.cost.derivative_and_value(preds, y, wd, sc[0:1])   # cost of the PRE-update forward pass (:26)
         if metrics:
             _metrics.accuracy.value_into(preds, y, sc[1:2])
         # learn_batch discards the delta w.r.t. the network input (learner/backpropagation.py:22 ignores the

@@ -23,6 +23,17 @@ class CostFunction:
         n = o.size // max(m, 1)
         call(L.bf_cost_value, _lib.COST[self.kind], o.ptr, t.ptr, m, n, result.ptr, stream_ptr())
 
+    def derivative_and_value(self, outputs, targets, w, result):
+        """delta (device) and result[0] = cost in ONE kernel: what the training step needs of a forward pass."""
+        o, t = as_device(outputs), as_device(targets)
+        m = o.shape[0]
+        n = o.size // max(m, 1)
+        delta = DeviceArray.empty(*o.shape)
+        wd = as_device(w) if w is not None else None
+        call(L.bf_cost_delta_value, _lib.COST[self.kind], o.ptr, t.ptr, wd.ptr if wd is not None else _NULL, delta.ptr,
+             result.ptr, m, n, stream_ptr())
+        return delta
+
     def __call__(self, outputs, targets):
         res = DeviceArray.empty(1)
         self.value_into(outputs, targets, res)

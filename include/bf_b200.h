@@ -186,6 +186,10 @@ BF_API int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const floa
 BF_API int bf_cost_delta(const float* out, const float* tgt, const float* w, float* delta, int m, int n, void* stream);
 /* result[0] (+)= cost: MSE = 0.5*sum((o-t)^2), CXENT = -sum(t*log o) (terms with t==0 contribute 0). */
 BF_API int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, float* result, void* stream);
+/* Both of the above in one pass over the predictions (the training step needs the delta and the cost of the same
+ * forward pass, learner/backpropagation.py:19-27). */
+BF_API int bf_cost_delta_value(int kind, const float* out, const float* tgt, const float* w, float* delta, float* result, int m,
+                        int n, void* stream);
 /* result[0] = count(argmax_1(out) == argmax_1(tgt)), first maximum wins like numpy. */
 BF_API int bf_accuracy(const float* out, const float* tgt, int m, int n, float* result, void* stream);
 
