@@ -266,8 +266,10 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
 //   warps 1-2   MMA issuers: even / odd k-blocks, one TMEM accumulator each (two issuing threads reach twice the
 //               issue rate of one for these small N), four K=8 tcgen05.mma per k-block;
 //   warps 4-7   final epilogue: sum of the two accumulators -> per-CTA partial; a small kernel adds the partials.
-constexpr int C3DF_BUILDERS = 8;        // 16 measured no faster (un-pooling variant) / slower (TMA variant)
-constexpr int C3DF_THREADS = 128 + C3DF_BUILDERS * 32;      // warp 0 loads, 1-2 MMA, 3 TMEM, then the tile builders (the first four also drain the accumulators)
+constexpr int C3DF_BUILDERS = 8;        // warps per builder group
+// warp 0 loads, 1-2 MMA, 3 TMEM, 4-11 patch-tile builders (4-7 also drain the accumulators); the un-pooling variant
+// adds warps 12-19, which build the E tile concurrently (one group doing both, in sequence, was the kernel's limit)
+constexpr int c3df_threads(bool unpool) { return 128 + (unpool ? 2 : 1) * C3DF_BUILDERS * 32; }
 constexpr int C3DF_A_SLOT = 32 * 128;     // 32 patch rows per tile; the M=128 descriptor runs on into the next tiles (rows >= 32 of D are never read)
 // after the ring: zeros, >= 4 KB (the M=64 descriptor of the last tile reads 8 KB) and >= one raw stage (source of padding lanes)
 struct C3DfParams {
@@ -291,7 +293,7 @@ struct C3DfParams {
 // Per band that is 16 KB of reads instead of a 25 KB E box, and the 411 MB write + read of the full-resolution
 // delta disappears.
 template <int MH, int NR, bool UNPOOL>
-__global__ void __launch_bounds__(C3DF_THREADS, 1)
+__global__ void __launch_bounds__(c3df_threads(UNPOOL), 1)
 conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restrict__ X, C3DfParams p, float* __restrict__ partial) {
   extern __shared__ int dyn_smem[];
   __shared__ __align__(8) uint64_t full[6], empty[6], built[4], afree[4], done;
@@ -312,16 +314,17 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (UNPOOL ? 0 : 2) + C3DF_BUILDERS); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&built[i], C3DF_BUILDERS); mbar_init(&afree[i], 2); }
+    constexpr int NBW = (UNPOOL ? 2 : 1) * C3DF_BUILDERS;      // builder warps that arrive per band
+    for (int i = 0; i < 6; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (UNPOOL ? 0 : 2) + NBW); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&built[i], NBW); mbar_init(&afree[i], 2); }
     mbar_init(&done, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // E stages and patch tiles start as zeros: rows the loads / builders never write must read as finite zeros
-  for (uint32_t o = tid * 16u; o < x_base - base; o += C3DF_THREADS * 16u)
+  for (uint32_t o = tid * 16u; o < x_base - base; o += blockDim.x * 16u)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
   // row r = (c*fy + ky)*fx + kx (the reference's filter order) -> offset of its first element inside the raw stage
-  for (int r = tid; r < 128; r += C3DF_THREADS) {
+  for (int r = tid; r < 128; r += blockDim.x) {
     int v = 0;
     if (r < p.Mrows) {
       const int kx = r % p.fx, t = r / p.fx, ky = t % p.fy, c = t / p.fy;
@@ -448,7 +451,9 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
     const uint32_t zero_src = zero_base;     // a_tail_bytes of zeros
     // band-invariant geometry, computed once: this lane's pixel of the warp's own k-block (j = bw), and for the
     // un-pooling variant the four E-tile addresses of each pooled item this thread expands
-    const int pxA = bw * 32 + lane, yyA = pxA / p.ox;
+    const bool do_a = bw < C3DF_BUILDERS, do_e = UNPOOL && bw >= C3DF_BUILDERS;
+    const int bi = do_e ? bw - C3DF_BUILDERS : bw;           // index inside the group
+    const int pxA = bi * 32 + lane, yyA = pxA / p.ox;
     const uint32_t offA = (uint32_t)(yyA * p.ix + (pxA - yyA * p.ox)) * 4u;
     constexpr int UI = 2;                                     // items per builder thread (host checks the band fits)
     const int pw = p.ox >> 1, nq = p.nf >> 2;
@@ -456,7 +461,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
     if (UNPOOL) {
 #pragma unroll
       for (int i = 0; i < UI; ++i) {
-        const int item = (bw * 32 + lane) + i * (C3DF_BUILDERS * 32);
+        const int item = (bi * 32 + lane) + i * (C3DF_BUILDERS * 32);
         const int q = item % nq, pp = item / nq;
         const int py = pp / pw, pxx = pp - py * pw;
         const int f0 = q * 4;
@@ -481,11 +486,11 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       mbar_wait(&full[s], (uint32_t)(u & 1));                       // raw rows (and the pooled-resolution state) landed
       if (ut > 0) mbar_wait(&afree[t], (uint32_t)((ut - 1) & 1));   // MMAs of the band tile's previous use are done
       const int nkb_eff = (npx + 31) >> 5;
-      for (int j = bw; j < nkb_eff; j += C3DF_BUILDERS) {
+      for (int j = do_a ? bi : nkb_eff; j < nkb_eff; j += C3DF_BUILDERS) {
         const int px = j * 32 + lane;
         const bool valid = px < npx;
         uint32_t off = offA;
-        if (j != bw) { const int yy = px / p.ox; off = (uint32_t)(yy * p.ix + (px - yy * p.ox)) * 4u; }
+        if (j != bi) { const int yy = px / p.ox; off = (uint32_t)(yy * p.ix + (px - yy * p.ox)) * 4u; }
         const uint32_t src = valid ? xs + (uint32_t)lead * 4u + off : zero_src;
         const uint32_t tile = a_base + (uint32_t)(t * p.nkb + j) * C3DF_A_SLOT;
         uint32_t v[NR];
@@ -496,12 +501,12 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + swz[r & 7] + (uint32_t)(r * 128)), "r"(v[r] + 0x1000u));
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + ones_off), "r"(valid ? 0x3f800000u : 0u));
       }
-      if (UNPOOL) {
+      if (do_e) {
         const uint32_t e_tile = e_base + (uint32_t)t * p.e_stage_bytes;
         const uint32_t dp_s = xs + (uint32_t)p.x_stage_bytes, g_s = dp_s + (uint32_t)p.pool_bytes, m_s = g_s + (uint32_t)p.pool_bytes;
 #pragma unroll
         for (int i = 0; i < UI; ++i) {
-          const int item = (bw * 32 + lane) + i * (C3DF_BUILDERS * 32);
+          const int item = (bi * 32 + lane) + i * (C3DF_BUILDERS * 32);
           if (item < nitems) {
             uint32_t d0, d1, d2, d3, g0 = 0x3f800000u, g1 = 0x3f800000u, g2 = 0x3f800000u, g3 = 0x3f800000u, mw;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(dp_s + (uint32_t)item * 16u));
@@ -749,7 +754,7 @@ static int c3_backward_filter_impl(const float* X, const float* E, const float* 
 #define BF_C3DF_LAUNCH(MH_, NR_, U_)                                                                                          \
   {                                                                                                                           \
     BF_CUDA(cudaFuncSetAttribute(conv_c3_df_kernel<MH_, NR_, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    launch_pdl(conv_c3_df_kernel<MH_, NR_, U_>, dim3(ctas), dim3(C3DF_THREADS), smem, s, mE, X, p, (float*)ws);                                   \
+    launch_pdl(conv_c3_df_kernel<MH_, NR_, U_>, dim3(ctas), dim3(c3df_threads(U_)), smem, s, mE, X, p, (float*)ws);                                   \
   }
 #define BF_C3DF_CASE(MH_, NR_) \
   if (MH == MH_ && NR == NR_) { if (unpool) BF_C3DF_LAUNCH(MH_, NR_, true) else BF_C3DF_LAUNCH(MH_, NR_, false) }
