@@ -267,7 +267,8 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
 //               issue rate of one for these small N), four K=8 tcgen05.mma per k-block;
 //   warps 4-7   final epilogue: sum of the two accumulators -> per-CTA partial; a small kernel adds the partials.
 constexpr int C3DF_BUILDERS = 8;        // warps per builder group
-// warp 0 loads, 1-2 MMA, 3 TMEM, 4-11 patch-tile builders (4-7 also drain the accumulators); the un-pooling variant
+constexpr int C3DF_ISSUERS = 3;         // MMA-issuing warps (1-3), one accumulator each: k-block j of a band goes to issuer j % 3
+// warp 0 loads, 1-3 MMA (3 also owns the TMEM allocation), 4-11 patch-tile builders (4-7 also drain the accumulators); the un-pooling variant
 // adds warps 12-19, which build the E tile concurrently (one group doing both, in sequence, was the kernel's limit)
 constexpr int c3df_threads(bool unpool) { return 128 + (unpool ? 2 : 1) * C3DF_BUILDERS * 32; }
 constexpr int C3DF_A_SLOT = 32 * 128;     // 32 patch rows per tile; the M=128 descriptor runs on into the next tiles (rows >= 32 of D are never read)
@@ -299,6 +300,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
   __shared__ __align__(8) uint64_t full[6], empty[6], built[4], afree[4], done;
   __shared__ uint32_t tmem_slot;
   __shared__ int roff[128];
+  __shared__ int acc_used[C3DF_ISSUERS];
   constexpr int NF = MH * 32;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
@@ -310,14 +312,14 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
 
   pdl_launch_dependents();
   if (warp == 3) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * NF));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(4 * NF));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
     constexpr int NBW = (UNPOOL ? 2 : 1) * C3DF_BUILDERS;      // builder warps that arrive per band
-    for (int i = 0; i < 6; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (UNPOOL ? 0 : 2) + NBW); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&built[i], NBW); mbar_init(&afree[i], 2); }
-    mbar_init(&done, 2);
+    for (int i = 0; i < 6; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (UNPOOL ? 0 : C3DF_ISSUERS) + NBW); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&built[i], NBW); mbar_init(&afree[i], C3DF_ISSUERS); }
+    mbar_init(&done, 2 * C3DF_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // E stages and patch tiles start as zeros: rows the loads / builders never write must read as finite zeros
@@ -394,8 +396,9 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       }
       if (++s == p.ns) { s = 0; ++u; }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ------------------------------------------------------------------ MMA issuers (k-block parity inside a band)
+  } else if (warp >= 1 && warp <= C3DF_ISSUERS) {
+    // ------------------------------------------------------------------ MMA issuers: k-block j of a band -> issuer j % 3
+    // (one thread issues a K=8 MMA only every 50-70 cycles; the tensor pipe takes an M=64 x N=32 one every ~24)
     const bool leader = elect_one_sync();
     const int wsel = warp - 1;
     constexpr uint32_t idesc = idesc_tf32(64, NF, false, true);   // M=64: half the shared-memory reads of M=128 per MMA
@@ -411,7 +414,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
         const int nkb_eff = (rb * p.ox + 31) >> 5;         // k-blocks that hold pixels of this band
         const uint32_t e_tile = e_base + (uint32_t)(UNPOOL ? t : s) * p.e_stage_bytes;
         bool any = false;
-        for (int j = wsel; j < nkb_eff; j += 2) {
+        for (int j = wsel; j < nkb_eff; j += C3DF_ISSUERS) {
           const uint64_t ad = desc_k_sw128(a_base + (uint32_t)(t * p.nkb + j) * C3DF_A_SLOT);
           const uint64_t bd = desc_mn_sw128_32b(e_tile + j * 4096, (uint32_t)p.nkb * 4096u, 512u);
 #pragma unroll
@@ -427,7 +430,11 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       if (++s == p.ns) { s = 0; ++u; }
       if (++t == p.na) { t = 0; ++ut; }
     }
-    if (leader) umma_commit(&done);
+    if (leader) {
+      acc_used[wsel] = mine > 0 ? 1 : 0;     // an accumulator nobody wrote holds garbage: the epilogue must skip it
+      umma_commit(&done);                    // arrives when this warp's MMAs have completed
+      mbar_arrive(&done);                    // releases the flag write
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ patch-tile builders
     // builder warp bw writes the k-block tiles j = bw, bw+8, .. of every band (hand-off to the MMA warps once per
@@ -542,24 +549,20 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
       mbar_wait(&done, 0);
       tc_fence_after();
       float* dst = partial + ((size_t)blockIdx.x * (p.Mrows + 1) + m) * NF;
-      const int total_kb = my_units * p.nkb;
 #pragma unroll
       for (int c0 = 0; c0 < NF; c0 += 16) {
-        uint32_t v0[16], v1[16];
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = 0.f;
-        if (total_kb > 0) {
-          tmem_ld16(tmem + ((uint32_t)(bw * 32) << 16) + c0, v0);
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v0[j]);
-        }
-        if (total_kb > 1) {
-          tmem_ld16(tmem + ((uint32_t)(bw * 32) << 16) + NF + c0, v1);
-          tmem_ld_wait();
+        for (int a = 0; a < C3DF_ISSUERS; ++a) {
+          if (acc_used[a]) {
+            uint32_t v[16];
+            tmem_ld16(tmem + ((uint32_t)(bw * 32) << 16) + a * NF + c0, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(v1[j]);
+            for (int j = 0; j < 16; ++j) o[j] += __uint_as_float(v[j]);
+          }
         }
         if (m <= p.Mrows) {
 #pragma unroll
@@ -570,7 +573,7 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NF));
+  if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(4 * NF));
 }
 
 // dF[f][r] = sum_cta partial[cta][r][f] (r = (c,ky,kx) in the reference's order);  db[f] = sum_cta partial[cta][Mrows][f]
