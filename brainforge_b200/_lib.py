@@ -14,7 +14,8 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "bf_b200.h")
 # enums (mirrors of include/bf_b200.h)
 OK, ERR_CUDA, ERR_VALUE, ERR_ARG, ERR_WORKSPACE = 0, 1, 2, 3, 4
 ACT = {"linear": 0, "sigmoid": 1, "tanh": 2, "relu": 3, "softmax": 4}
-COST = {"mse": 0, "mean_squared_error": 0, "cxent": 1, "categorical_crossentropy": 1}
+COST = {"mse": 0, "mean_squared_error": 0, "cxent": 1, "categorical_crossentropy": 1, "bxent": 2, "binary_crossentropy": 2,
+        "hinge": 3}
 OPT = {"sgd": 0, "momentum": 1, "nesterov": 2, "adagrad": 3, "rmsprop": 4, "adam": 5}
 CONV_MODE = {"valid": 0, "full": 1}
 PREC = {"fp32": 0, "tf32": 1}

@@ -116,12 +116,20 @@ __global__ void cost_value_kernel(const float* __restrict__ o, const float* __re
   double acc = 0.0;
   for (; i < total; i += stride) {
     float ov = o[i], tv = t[i];
-    if (delta) delta[i] = (ov - tv) * (w ? w[i / n] : 1.0f);
+    if (delta) {   // every cost uses outputs - targets (costs.py:19-21) except hinge: -y where output <= 1 (costs.py:58-66)
+      const float d = KIND == BF_COST_HINGE ? (ov > 1.0f ? 0.0f : -tv) : ov - tv;
+      delta[i] = d * (w ? w[i / n] : 1.0f);
+    }
     if (KIND == BF_COST_MSE) {
       float d = ov - tv;
       acc += 0.5 * (double)d * (double)d;
-    } else {
+    } else if (KIND == BF_COST_CXENT) {
       if (tv != 0.0f) acc -= (double)tv * (double)logf(ov);
+    } else if (KIND == BF_COST_BXENT) {        // -(t log o + (1-t) log(1-o)), costs.py:48-49; 0*log 0 terms contribute 0
+      if (tv != 0.0f) acc -= (double)tv * (double)logf(ov);
+      if (tv != 1.0f) acc -= (double)(1.0f - tv) * (double)logf(1.0f - ov);
+    } else {                                   // hinge: max(0, 1 - t*o), costs.py:54-55
+      acc += (double)fmaxf(0.0f, 1.0f - tv * ov);
     }
   }
   acc = warp_sum(acc);
@@ -315,12 +323,12 @@ int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, fl
   void* ws = nullptr;
   int rc = workspace_require((size_t)grid * sizeof(double), &ws);
   if (rc) return rc;
-  if (kind == BF_COST_MSE)
-    launch_pdl(cost_value_kernel<BF_COST_MSE>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, (float*)nullptr, (const float*)nullptr, n);
-  else if (kind == BF_COST_CXENT)
-    launch_pdl(cost_value_kernel<BF_COST_CXENT>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, (float*)nullptr, (const float*)nullptr, n);
-  else
-    return fail(BF_ERR_ARG, "bf_cost_value: unknown cost kind %d", kind);
+#define BF_COST_CASE(K_) case K_: launch_pdl(cost_value_kernel<K_>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, (float*)nullptr, (const float*)nullptr, n); break;
+  switch (kind) {
+    BF_COST_CASE(BF_COST_MSE) BF_COST_CASE(BF_COST_CXENT) BF_COST_CASE(BF_COST_BXENT) BF_COST_CASE(BF_COST_HINGE)
+    default: return fail(BF_ERR_ARG, "bf_cost_value: unknown cost kind %d", kind);
+  }
+#undef BF_COST_CASE
   BF_LAUNCH_CHECK();
   return BF_OK;
 }
@@ -329,7 +337,7 @@ int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, fl
 int bf_cost_delta_value(int kind, const float* out, const float* tgt, const float* w, float* delta, float* result, int m, int n,
                         void* stream) {
   BF_REQUIRE(m >= 0 && n > 0 && result && (m == 0 || (out && tgt && delta)), BF_ERR_ARG, "bf_cost_delta_value: bad arguments");
-  BF_REQUIRE(kind == BF_COST_MSE || kind == BF_COST_CXENT, BF_ERR_ARG, "bf_cost_delta_value: unknown cost kind %d", kind);
+  BF_REQUIRE(kind >= BF_COST_MSE && kind <= BF_COST_HINGE, BF_ERR_ARG, "bf_cost_delta_value: unknown cost kind %d", kind);
   cudaStream_t s = as_stream(stream);
   size_t total = (size_t)m * n;
   if (total == 0) {
@@ -340,10 +348,12 @@ int bf_cost_delta_value(int kind, const float* out, const float* tgt, const floa
   void* ws = nullptr;
   int rc = workspace_require((size_t)grid * sizeof(double), &ws);
   if (rc) return rc;
-  if (kind == BF_COST_MSE)
-    launch_pdl(cost_value_kernel<BF_COST_MSE>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, delta, w, n);
-  else
-    launch_pdl(cost_value_kernel<BF_COST_CXENT>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, delta, w, n);
+#define BF_COST_CASE(K_) case K_: launch_pdl(cost_value_kernel<K_>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, delta, w, n); break;
+  switch (kind) {
+    BF_COST_CASE(BF_COST_MSE) BF_COST_CASE(BF_COST_CXENT) BF_COST_CASE(BF_COST_BXENT) BF_COST_CASE(BF_COST_HINGE)
+    default: break;
+  }
+#undef BF_COST_CASE
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

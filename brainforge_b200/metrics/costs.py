@@ -62,12 +62,29 @@ class _CategoricalCrossEntropy(CostFunction):
     kind = "cxent"         # metrics/costs.py:34-43
 
 
+class _BinaryCrossEntropy(CostFunction):
+    kind = "bxent"         # metrics/costs.py:46-53
+
+
+class _Hinge(CostFunction):
+    kind = "hinge"         # metrics/costs.py:55-66: value sum(max(0, 1 - t*o)); sub-derivative -t where o <= 1, else 0
+
+    def derivative(self, outputs, targets, w=None):
+        scratch = DeviceArray.empty(1)
+        delta = self.derivative_and_value(outputs, targets, w, scratch)
+        return delta if isinstance(outputs, DeviceArray) else delta.numpy()
+
+
 mean_squared_error = _MeanSquaredError()
 categorical_crossentropy = _CategoricalCrossEntropy()
+binary_crossentropy = _BinaryCrossEntropy()
+hinge = _Hinge()
 mse = mean_squared_error
 cxent = categorical_crossentropy
+bxent = binary_crossentropy
 
-_costs = {"mean_squared_error": mse, "categorical_crossentropy": cxent, "mse": mse, "cxent": cxent}
+_costs = {"mean_squared_error": mse, "categorical_crossentropy": cxent, "binary_crossentropy": bxent, "hinge": hinge,
+          "mse": mse, "cxent": cxent, "bxent": bxent}
 
 
 def get(cost_function):

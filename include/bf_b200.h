@@ -39,8 +39,8 @@ extern "C" {
 
 /* activation kinds: atomic/activation_op.py:157-159 registry */
 enum { BF_ACT_LINEAR = 0, BF_ACT_SIGMOID = 1, BF_ACT_TANH = 2, BF_ACT_RELU = 3, BF_ACT_SOFTMAX = 4 };
-/* cost kinds: metrics/costs.py:72-80 */
-enum { BF_COST_MSE = 0, BF_COST_CXENT = 1 };
+/* cost kinds: metrics/costs.py:24-80 (mse, cxent, bxent, hinge) */
+enum { BF_COST_MSE = 0, BF_COST_CXENT = 1, BF_COST_BXENT = 2, BF_COST_HINGE = 3 };
 /* optimizer kinds: optimizers/__init__.py:4-6 */
 enum { BF_OPT_SGD = 0, BF_OPT_MOMENTUM = 1, BF_OPT_NESTEROV = 2, BF_OPT_ADAGRAD = 3, BF_OPT_RMSPROP = 4, BF_OPT_ADAM = 5 };
 /* conv modes: atomic/tensor_op.py:42-46 */
@@ -184,9 +184,11 @@ BF_API int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const floa
 /* ---- costs / metrics: metrics/costs.py:11-37, metrics/metrics.py:13-16 ---- */
 /* delta = (out - tgt) * (w ? w[row] : 1): CostFunction.derivative + learner/backpropagation.py:19-21. */
 BF_API int bf_cost_delta(const float* out, const float* tgt, const float* w, float* delta, int m, int n, void* stream);
-/* result[0] (+)= cost: MSE = 0.5*sum((o-t)^2), CXENT = -sum(t*log o) (terms with t==0 contribute 0). */
+/* result[0] = cost: MSE = 0.5*sum((o-t)^2), CXENT = -sum(t*log o) (terms with t==0 contribute 0),
+ * BXENT = -sum(t*log o + (1-t)*log(1-o)) (costs.py:48-49), HINGE = sum(max(0, 1 - t*o)) (costs.py:54-55). */
 BF_API int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, float* result, void* stream);
-/* Both of the above in one pass over the predictions (the training step needs the delta and the cost of the same
+/* Both of the above in one pass over the predictions; the delta is `out - tgt` for every kind except HINGE, whose
+ * sub-derivative is -tgt where out <= 1 and 0 elsewhere (costs.py:58-66) (the training step needs the delta and the cost of the same
  * forward pass, learner/backpropagation.py:19-27). */
 BF_API int bf_cost_delta_value(int kind, const float* out, const float* tgt, const float* w, float* delta, float* result, int m,
                         int n, void* stream);

@@ -156,8 +156,13 @@ def maxpool_backward(E, filt):
 # --------------------------------------------------------------------------
 # costs and metrics                   metrics/costs.py:11-37, metrics.py:13-16
 # --------------------------------------------------------------------------
-def cost_derivative(outputs, targets):
-    """metrics/costs.py:19-21  delta = outputs - targets (for every cost)."""
+def cost_derivative(outputs, targets, kind="mse"):
+    """metrics/costs.py:19-21  delta = outputs - targets (for every cost), except hinge (:58-66):
+    -targets, zeroed where outputs > 1."""
+    if kind == "hinge":
+        out = -np.asarray(targets, dtype=F64)
+        out[np.asarray(outputs) > 1.0] = 0.0
+        return out
     return outputs - targets
 
 
@@ -168,6 +173,10 @@ def cost_value(kind, outputs, targets):
         return 0.5 * np.linalg.norm(outputs - targets) ** 2.0
     if kind in ("cxent", "categorical_crossentropy"):
         return -(targets * np.log(outputs)).sum()
+    if kind in ("bxent", "binary_crossentropy"):          # metrics/costs.py:48-49
+        return -(targets * np.log(outputs) + (1.0 - targets) * np.log(1.0 - outputs)).sum()
+    if kind == "hinge":                                   # metrics/costs.py:54-55
+        return np.maximum(0.0, 1.0 - targets * outputs).sum()
     raise ValueError("No such cost function: %r" % (kind,))
 
 
@@ -459,7 +468,7 @@ class Stack:
     def learn_batch(self, X, Y, w=None, update=True, metrics=()):
         m = len(X)
         preds = self.feedforward(X)
-        delta = cost_derivative(preds, np.asarray(Y, dtype=F64))
+        delta = cost_derivative(preds, np.asarray(Y, dtype=F64), self.cost)
         if w is not None:
             delta = delta * np.asarray(w)[:, None]
         self.backpropagate(delta)

@@ -211,6 +211,34 @@ def test_accuracy_first_max_wins(bf):
     assert bf.metrics.accuracy(o, t) == int(np.sum(o.argmax(1) == t.argmax(1))) == 1
 
 
+def test_costs_bxent_hinge_golden(bf, O):
+    """binary cross-entropy and hinge (metrics/costs.py:46-69) against values produced by the reference."""
+    from conftest import load_golden
+    g = load_golden("costs2")
+    close(bf.metrics.bxent(g["O"], g["T"]), g["bxent"])
+    close(bf.metrics.bxent.derivative(g["O"], g["T"]), g["bxent_delta"])
+    close(bf.metrics.hinge(g["S"], g["Y"]), g["hinge"])
+    d = bf.metrics.hinge.derivative(g["S"], g["Y"])
+    assert np.array_equal(d, g["hinge_delta"])            # -y where output <= 1, exactly 0 elsewhere
+    assert bf.metrics.costs.get("binary_crossentropy") is bf.metrics.bxent and bf.metrics.costs.get("hinge") is bf.metrics.hinge
+
+
+@pytest.mark.parametrize("cost,act", [("bxent", "sigmoid"), ("hinge", "tanh")])
+def test_training_step_with_bxent_hinge(bf, cost, act):
+    """A learn_batch trajectory under the two costs equals the oracle's (the delta kernel is cost-specific for hinge)."""
+    from helpers import build_b200, build_oracle
+    spec = [("dense", 12, "tanh"), ("dense", 5, act)]
+    net = build_b200((9,), spec, cost, "momentum", seed=3)
+    ora = build_oracle((9,), spec, cost, "momentum", seed=3)
+    rs = np.random.RandomState(8)
+    X = rs.randn(17, 9)
+    Y = (rs.uniform(size=(17, 5)) < 0.5).astype(np.float64) if cost == "bxent" else np.where(rs.uniform(size=(17, 5)) < 0.5, -1.0, 1.0)
+    for _ in range(3):
+        a, b = net.learn_batch(X, Y), ora.learn_batch(X, Y)
+        close(a["cost"], b["cost"])
+    close(net.layers.get_weights(), ora.get_weights(), 3e-5)
+
+
 def test_large_cost_reduction_is_deterministic(bf, O):
     rs = np.random.RandomState(1)
     o = O.act_forward("softmax", rs.randn(50000, 10))

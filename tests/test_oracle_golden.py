@@ -56,6 +56,16 @@ def test_activations(golden_ops):
     assert O.act_backward("relu", np.array([0.0]))[0] == 0.0  # NumPy path: relu'(0) = 0
 
 
+def test_costs_bxent_hinge():
+    """The remaining costs of the registry (metrics/costs.py:46-69) against values from the reference
+    (tests/golden/make_golden_costs.py)."""
+    g = load_golden("costs2")
+    close(O.cost_value("bxent", g["O"], g["T"]), g["bxent"])
+    close(O.cost_derivative(g["O"], g["T"], "bxent"), g["bxent_delta"])
+    close(O.cost_value("hinge", g["S"], g["Y"]), g["hinge"])
+    assert np.array_equal(O.cost_derivative(g["S"], g["Y"], "hinge"), g["hinge_delta"])
+
+
 def test_costs(golden_ops):
     g = golden_ops
     close(O.cost_value("mse", g["cost_O"], g["cost_T"]), g["cost_mse"])
