@@ -65,6 +65,8 @@ SIGNATURES = {
     "bf_layout_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "bf_pool_nhwc_forward": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
     "bf_pool_nhwc_backward": (_i, [_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp]),
+    "bf_gap_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "bf_gap_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "bf_cost_delta": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bf_cost_value": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp]),
     "bf_cost_delta_value": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

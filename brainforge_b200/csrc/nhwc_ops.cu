@@ -196,6 +196,43 @@ __global__ void pool_nhwc_bwd_wide_kernel(const float* __restrict__ E, const uns
   }
 }
 
+// ---- global average pooling: layers/tensor.py:95-114 (X.mean(axis=(2,3)); backward repeats delta / (H*W))
+// NCHW: one warp per (image, channel) plane, coalesced along the plane; channels-last: one thread per (image, channel),
+// a warp reads 32 consecutive channels of each pixel.
+__global__ void gap_fwd_nchw_kernel(const float* __restrict__ A, float* __restrict__ out, long planes, int hw) {
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long pl = warp; pl < planes; pl += nwarps) {
+    const float* src = A + pl * hw;
+    float s = 0.f;
+    for (int i = lane; i < hw; i += 32) s += src[i];
+    s = warp_sum(s);
+    if (lane == 0) out[pl] = s / (float)hw;
+  }
+}
+__global__ void gap_fwd_nhwc_kernel(const float* __restrict__ A, float* __restrict__ out, long total, int c, int hw) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long b = i / c;
+    const int ch = (int)(i - b * c);
+    const float* src = A + b * hw * c + ch;
+    float s = 0.f;
+    for (int p = 0; p < hw; ++p) s += src[(long)p * c];
+    out[i] = s / (float)hw;
+  }
+}
+// dX[b, c, p] = delta[b, c] / hw   (either layout: idx -> (b, c))
+__global__ void gap_bwd_kernel(const float* __restrict__ delta, float* __restrict__ dX, long total, int c, int hw, int nhwc) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  const float inv = 1.0f / (float)hw;
+  for (; i < total; i += stride) {
+    long bc;
+    if (nhwc) { const long b = i / ((long)hw * c); bc = b * c + (i % c); }
+    else bc = i / hw;
+    dX[i] = delta[bc] * inv;
+  }
+}
+
 static int pool_nhwc_check(const char* who, int im, int c, int iy, int ix, int fdim) {
   if (im < 0 || c <= 0 || iy <= 0 || ix <= 0) return fail(BF_ERR_ARG, "%s: bad shape", who);
   if (fdim < 1 || fdim > 8) return fail(BF_ERR_ARG, "%s: fdim %d not in [1,8]", who, fdim);
@@ -270,6 +307,28 @@ int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate
     if (total == 0) return BF_OK;
     launch_pdl(pool_nhwc_bwd_wide_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, s, E, (const unsigned long long*)mask, gate, dX, total, oy, ox, c, ix, fdim);
   }
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_gap_forward(const float* A, float* out, int im, int c, int hw, int nhwc, void* stream) {
+  BF_REQUIRE(im >= 0 && c > 0 && hw > 0, BF_ERR_ARG, "bf_gap_forward: bad shape");
+  if (im == 0) return BF_OK;
+  BF_REQUIRE(A && out, BF_ERR_ARG, "bf_gap_forward: null pointer");
+  cudaStream_t s = as_stream(stream);
+  const long planes = (long)im * c;
+  if (nhwc) gap_fwd_nhwc_kernel<<<ew_grid(planes, 256), 256, 0, s>>>(A, out, planes, c, hw);
+  else gap_fwd_nchw_kernel<<<ew_grid(planes * 32, 256), 256, 0, s>>>(A, out, planes, hw);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_gap_backward(const float* delta, float* dX, int im, int c, int hw, int nhwc, void* stream) {
+  BF_REQUIRE(im >= 0 && c > 0 && hw > 0, BF_ERR_ARG, "bf_gap_backward: bad shape");
+  if (im == 0) return BF_OK;
+  BF_REQUIRE(delta && dX, BF_ERR_ARG, "bf_gap_backward: null pointer");
+  const long total = (long)im * c * hw;
+  gap_bwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(delta, dX, total, c, hw, nhwc);
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

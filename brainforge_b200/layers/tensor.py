@@ -168,3 +168,40 @@ class ConvLayer(LayerBase):
 
     def __str__(self):
         return "Conv({}x{}x{})-{}".format(self.nfilters, self.fy, self.fx, str(self.activation)[:4])
+
+
+class GlobalAveragePooling(NoParamMixin, LayerBase):
+    """layers/tensor.py:95-114: (im, c, y, x) -> (im, c) mean over the plane; backward repeats delta / (y*x).
+    Takes either storage layout of the incoming activation and answers in the same one."""
+
+    def __init__(self):
+        LayerBase.__init__(self, activation="linear", trainable=False)
+        self.repeats = 0
+        self._nhwc = False
+
+    def _fwd(self, x):
+        from ..device import DeviceArray, call, stream_ptr
+        from .. import _lib
+        im, c, y, xx = x.shape
+        self.repeats = y * xx
+        self._nhwc = x.nhwc
+        out = DeviceArray.empty(im, c)
+        call(_lib.lib.bf_gap_forward, x.pptr, out.ptr, im, c, y * xx, 1 if x.nhwc else 0, stream_ptr())
+        self.output = out
+        return out
+
+    def _bwd(self, delta):
+        from ..device import DeviceArray, call, stream_ptr
+        from .. import _lib
+        c, y, xx = self.inshape[-3:]
+        im = delta.shape[0]
+        dX = DeviceArray.empty_nhwc(im, c, y, xx) if self._nhwc else DeviceArray.empty(im, c, y, xx)
+        call(_lib.lib.bf_gap_backward, delta.to_nchw().ptr, dX.pptr, im, c, y * xx, 1 if self._nhwc else 0, stream_ptr())
+        return dX
+
+    @property
+    def outshape(self):
+        return self.inshape[0],
+
+    def __str__(self):
+        return "GlobalAveragePooling"

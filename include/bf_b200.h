@@ -181,6 +181,12 @@ BF_API int bf_pool_nhwc_forward(const float* A, float* out, uint8_t* mask, int i
 BF_API int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate, float* dX, int im, int c, int iy,
                           int ix, int fdim, void* stream);
 
+/* ---- global average pooling: layers/tensor.py:95-114 ---- */
+/* out (im, c) = A.mean over the hw pixels of every (image, channel) plane; nhwc != 0: A is stored (im, hw, c). */
+BF_API int bf_gap_forward(const float* A, float* out, int im, int c, int hw, int nhwc, void* stream);
+/* dX = repeat(delta / hw) over the plane (layers/tensor.py:106-110), written in the layout `nhwc` selects. */
+BF_API int bf_gap_backward(const float* delta, float* dX, int im, int c, int hw, int nhwc, void* stream);
+
 /* ---- costs / metrics: metrics/costs.py:11-37, metrics/metrics.py:13-16 ---- */
 /* delta = (out - tgt) * (w ? w[row] : 1): CostFunction.derivative + learner/backpropagation.py:19-21. */
 BF_API int bf_cost_delta(const float* out, const float* tgt, const float* w, float* delta, int m, int n, void* stream);

@@ -320,6 +320,7 @@ class Stack:
       ("flatten",)                              layers/core.py:70-100
       ("conv", nfilters, fx, fy, activation)    layers/tensor.py:43-92
       ("pool", fdim)                            layers/tensor.py:7-40
+      ("gap",)                                  layers/tensor.py:95-114 (GlobalAveragePooling)
       ("lstm", neurons, activation, return_seq) layers/recurrent.py:12-47,80-113
 
     Weights are drawn with ``white`` in stack order at construction, i.e. with
@@ -364,6 +365,8 @@ class Stack:
                     raise RuntimeError("Incompatible shapes: {} % {}".format((ix, iy), fdim))
                 lay.update(fdim=fdim)
                 shape = (ic, iy // fdim, ix // fdim)
+            elif kind == "gap":                    # layers/tensor.py:95-114
+                shape = (shape[0],)
             elif kind == "lstm":
                 n = int(s[1])
                 zdim = shape[-1] + n
@@ -427,6 +430,9 @@ class Stack:
                 X = act_forward(l["act"], conv_forward(X, l["W"], "valid")) + l["b"]
             elif k == "pool":                      # layers/tensor.py:28-30
                 X, l["filter"] = maxpool_forward(X, l["fdim"])
+            elif k == "gap":                       # layers/tensor.py:102-104
+                l["repeats"] = int(np.prod(X.shape[2:]))
+                X = X.mean(axis=(2, 3))
             elif k == "lstm":                      # layers/recurrent.py:26,101-106
                 l["inputs"] = X.transpose(1, 0, 2)
                 O, l["Z"], l["cache"] = lstm_forward(l["inputs"], l["W"], l["b"], l["act"])
@@ -454,6 +460,9 @@ class Stack:
                 l["gW"], l["gb"], error = conv_backward(l["inputs"], error, l["W"])
             elif k == "pool":                      # layers/tensor.py:32-33
                 error = maxpool_backward(error, l["filter"])
+            elif k == "gap":                       # layers/tensor.py:106-110
+                m = len(error)
+                error = np.repeat(error / float(l["repeats"]), l["repeats"]).reshape((m,) + tuple(l["inshape"]))
             elif k == "lstm":                      # layers/recurrent.py:31-40,108-113 (ASSIGNS)
                 if l["return_seq"]:
                     E = error.transpose(1, 0, 2)

@@ -239,6 +239,43 @@ def test_training_step_with_bxent_hinge(bf, cost, act):
     close(net.layers.get_weights(), ora.get_weights(), 3e-5)
 
 
+def test_global_average_pooling_known_answer(bf):
+    """The reference's own known-answer test (tests/test_layers.py:9-30): planes filled with 1, 2, 3 -> means 1, 2, 3;
+    the backward pass of [1, 2, 3] gives inputs / 25."""
+    from brainforge_b200.layers import GlobalAveragePooling
+    inputs = np.empty([3, 5, 5], dtype="float32")
+    for ch in range(3):
+        inputs[ch] = np.full([5, 5], fill_value=ch + 1, dtype="float32")
+    stack = bf.LayerStack((3, 5, 5), [GlobalAveragePooling()])
+    layer = stack.layers[-1]
+    assert layer.outshape == (3,)
+    out = layer.feedforward(inputs[None, ...])[0]
+    np.testing.assert_equal(out, np.array([1., 2., 3.]))
+    delta = layer.backpropagate(np.array([[1., 2., 3.]]))[0]
+    np.testing.assert_allclose(delta, inputs / 25)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_global_average_pooling_in_a_net(bf, O, prec):
+    """conv -> relu -> GlobalAveragePooling -> dense against the oracle; on the TF32 path the layer is fed channels-last."""
+    from helpers import build_b200, build_oracle
+    bf.set_precision(prec)
+    try:
+        spec = [("conv", 32, 3, 3, "linear"), ("act", "relu"), ("gap",), ("dense", 4, "softmax")]
+        net = build_b200((3, 12, 10), spec, "cxent", "sgd", seed=21)
+        ora = build_oracle((3, 12, 10), spec, "cxent", "sgd", seed=21)
+        rs = np.random.RandomState(2)
+        X, Y = rs.randn(9, 3, 12, 10), np.eye(4)[rs.randint(0, 4, 9)]
+        a, b = net.learn_batch(X, Y, update=False), ora.learn_batch(X, Y, update=False)
+        tol = 1e-5 if prec == "fp32" else 5e-3
+        close(a["cost"], b["cost"], tol)
+        close(net.get_gradients(), ora.get_gradients(), tol if prec == "fp32" else 3e-2)
+        if prec == "tf32":
+            assert net.layers.layers[2].output.nhwc and net.layers.layers[3]._nhwc
+    finally:
+        bf.set_precision("fp32")
+
+
 def test_large_cost_reduction_is_deterministic(bf, O):
     rs = np.random.RandomState(1)
     o = O.act_forward("softmax", rs.randn(50000, 10))

@@ -56,6 +56,16 @@ def test_activations(golden_ops):
     assert O.act_backward("relu", np.array([0.0]))[0] == 0.0  # NumPy path: relu'(0) = 0
 
 
+def test_global_average_pooling_known_answer():
+    """The reference's own known-answer test for GlobalAveragePooling (tests/test_layers.py:9-30) on the oracle."""
+    inputs = np.empty([3, 5, 5])
+    for ch in range(3):
+        inputs[ch] = np.full([5, 5], fill_value=ch + 1.0)
+    st = O.Stack((3, 5, 5), [("gap",)])
+    np.testing.assert_equal(st.feedforward(inputs[None, ...])[0], np.array([1., 2., 3.]))
+    np.testing.assert_allclose(st.backpropagate(np.array([[1., 2., 3.]]))[0], inputs / 25)
+
+
 def test_costs_bxent_hinge():
     """The remaining costs of the registry (metrics/costs.py:46-69) against values from the reference
     (tests/golden/make_golden_costs.py)."""
