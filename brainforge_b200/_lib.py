@@ -39,6 +39,7 @@ SIGNATURES = {
     "bf_cast_f32_to_f64": (_i, [_vp, _vp, _sz, _vp]),
     "bf_transpose01": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "bf_affine": (_i, [_vp, _vp, _sz, _f, _f, _vp]),
+    "bf_mul_rowmask": (_i, [_vp, _vp, _vp, _sz, _sz, _f, _vp]),
     "bf_act_forward": (_i, [_i, _vp, _vp, _sz, _vp]),
     "bf_softmax_forward": (_i, [_vp, _vp, _i, _i, _vp]),
     "bf_act_backward": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),

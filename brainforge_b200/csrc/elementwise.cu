@@ -104,6 +104,12 @@ __device__ unsigned int g_reduce_ticket = 0;
 
 // delta != null: also writes delta = (o - t) * (w ? w[row] : 1) -- CostFunction.derivative (metrics/costs.py:19-21)
 // and the cost value of the same forward pass in ONE pass over the predictions (learner/backpropagation.py:19-27)
+__global__ void mul_rowmask_kernel(const float* __restrict__ x, const float* __restrict__ m, float* __restrict__ out, size_t total,
+                                   size_t cols, float scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) out[i] = x[i] * (m ? m[i % cols] : 1.0f) * scale;
+}
+
 template <int KIND>
 __global__ void cost_value_kernel(const float* __restrict__ o, const float* __restrict__ t, size_t total,
                                   double* __restrict__ partial, float* __restrict__ result, float* __restrict__ delta,
@@ -407,6 +413,16 @@ int bf_opt_step(int kind, float* W, float* g, float* s1, float* s2, size_t n, fl
       break;
     default: return fail(BF_ERR_ARG, "bf_opt_step: unknown optimizer kind %d", kind);
   }
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+// out[r, i] = x[r, i] * (m ? m[i] : 1) * scale -- DropOut's mask has the shape of ONE sample and is shared by the batch
+// (layers/fancy.py:73-76,80)
+int bf_mul_rowmask(const float* x, const float* m, float* out, size_t rows, size_t cols, float scale, void* stream) {
+  if (rows * cols == 0) return BF_OK;
+  BF_REQUIRE(x && out, BF_ERR_ARG, "bf_mul_rowmask: null pointer");
+  mul_rowmask_kernel<<<ew_grid(rows * cols, 256), 256, 0, as_stream(stream)>>>(x, m, out, rows * cols, cols, scale);
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

@@ -40,6 +40,8 @@ class Backpropagation(Learner):
         self.optimizer.initialize(nparams=self.layers.num_params)
         self.layers.flatten_parameters()
         self.use_graph = kw.get("use_graph", False)
+        if any(type(l).__name__ == "DropOut" for l in self.layers.layers):
+            self.use_graph = False       # the mask is drawn on the host every forward pass: nothing to replay
         self._graphs = {}
 
     # ------------------------------------------------------------------ the hot path

@@ -84,6 +84,10 @@ BF_API int bf_softmax_forward(const float* Z, float* A, int m, int n, void* stre
  * this is `delta *= activation.backward(output)` of layers/core.py:35,:52.  In place allowed. */
 BF_API int bf_act_backward(int kind, const float* A, const float* din, float* dout, size_t n, void* stream);
 
+/* out[r, i] = x[r, i] * (m ? m[i] : 1) * scale: DropOut (layers/fancy.py:60-90), whose mask has the shape of one
+ * sample and is shared by the whole batch. */
+BF_API int bf_mul_rowmask(const float* x, const float* m, float* out, size_t rows, size_t cols, float scale, void* stream);
+
 /* ---- dense: atomic/core_op.py:9-20, llatomic/_llops.py:7-9 -------------- */
 /* out = act(X@W + b); X (m,k), W (k,n), b (n) or NULL, out (m,n).  act fuses the layer's
  * activation (layers/core.py:29-31); BF_ACT_SOFTMAX applies the row softmax. */

@@ -321,6 +321,7 @@ class Stack:
       ("conv", nfilters, fx, fy, activation)    layers/tensor.py:43-92
       ("pool", fdim)                            layers/tensor.py:7-40
       ("gap",)                                  layers/tensor.py:95-114 (GlobalAveragePooling)
+      ("dropout", dropchance)                   layers/fancy.py:60-90 (set `stack.learning = True` while training)
       ("lstm", neurons, activation, return_seq) layers/recurrent.py:12-47,80-113
 
     Weights are drawn with ``white`` in stack order at construction, i.e. with
@@ -367,6 +368,8 @@ class Stack:
                 shape = (ic, iy // fdim, ix // fdim)
             elif kind == "gap":                    # layers/tensor.py:95-114
                 shape = (shape[0],)
+            elif kind == "dropout":                # layers/fancy.py:60-90
+                lay.update(keep=1.0 - float(s[1]), mask=None)
             elif kind == "lstm":
                 n = int(s[1])
                 zdim = shape[-1] + n
@@ -433,6 +436,9 @@ class Stack:
             elif k == "gap":                       # layers/tensor.py:102-104
                 l["repeats"] = int(np.prod(X.shape[2:]))
                 X = X.mean(axis=(2, 3))
+            elif k == "dropout":                   # layers/fancy.py:73-77: one mask of the SAMPLE shape, global NumPy RNG
+                l["mask"] = np.random.uniform(0, 1, l["inshape"]) < l["keep"]
+                X = X * (l["mask"] if getattr(self, "learning", False) else l["keep"])
             elif k == "lstm":                      # layers/recurrent.py:26,101-106
                 l["inputs"] = X.transpose(1, 0, 2)
                 O, l["Z"], l["cache"] = lstm_forward(l["inputs"], l["W"], l["b"], l["act"])
@@ -460,6 +466,9 @@ class Stack:
                 l["gW"], l["gb"], error = conv_backward(l["inputs"], error, l["W"])
             elif k == "pool":                      # layers/tensor.py:32-33
                 error = maxpool_backward(error, l["filter"])
+            elif k == "dropout":                   # layers/fancy.py:79-82 (the mask is reset to the keep probability)
+                error = error * l["mask"]
+                l["mask"] = np.ones_like(l["mask"], dtype=F64) * l["keep"]
             elif k == "gap":                       # layers/tensor.py:106-110
                 m = len(error)
                 error = np.repeat(error / float(l["repeats"]), l["repeats"]).reshape((m,) + tuple(l["inshape"]))

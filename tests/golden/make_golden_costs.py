@@ -25,6 +25,22 @@ Y = np.where(rs.uniform(size=(m, n)) < 0.5, -1.0, 1.0)        # +-1 labels
 out = dict(O=O, T=T, S=S, Y=Y,
            bxent=ref_costs.bxent(O, T), bxent_delta=ref_costs.bxent.derivative(O, T),
            hinge=ref_costs.hinge(S, Y), hinge_delta=ref_costs.hinge.derivative(S, Y.copy()))
+# DropOut (layers/fancy.py:60-90): one mask of the sample shape from the global RNG, shared by the batch
+from brainforge.layers import DropOut  # noqa: E402
+from brainforge.util import testing  # noqa: E402
+brain = testing.NoBrainer(outshape=(4, 3))
+brain.learning = True
+layer = DropOut(0.3)
+layer.connect(brain)
+DX, DD = rs.randn(5, 4, 3), rs.randn(5, 4, 3)
+np.random.seed(99)
+d_train = layer.feedforward(DX).copy()
+d_back = layer.backpropagate(DD).copy()
+d_mask_after = np.asarray(layer.mask, dtype=np.float64).copy()
+brain.learning = False
+np.random.seed(99)
+d_eval = layer.feedforward(DX).copy()
+out.update(drop_X=DX, drop_D=DD, drop_train=d_train, drop_back=d_back, drop_mask_after=d_mask_after, drop_eval=d_eval)
 path = os.path.join(HERE, "costs2.npz")
 np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
 print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), float(out["bxent"]), float(out["hinge"]))

@@ -20,6 +20,9 @@ def build_b200(input_shape, spec, cost, optimizer, seed=None, **kw):
             layers.append(ConvLayer(s[1], s[2], s[3], activation=s[4] if len(s) > 4 else "linear"))
         elif k == "pool":
             layers.append(PoolLayer(s[1]))
+        elif k == "dropout":
+            from brainforge_b200.layers import DropOut
+            layers.append(DropOut(s[1]))
         elif k == "gap":
             from brainforge_b200.layers import GlobalAveragePooling
             layers.append(GlobalAveragePooling())

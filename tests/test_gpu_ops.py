@@ -239,6 +239,24 @@ def test_training_step_with_bxent_hinge(bf, cost, act):
     close(net.layers.get_weights(), ora.get_weights(), 3e-5)
 
 
+def test_dropout_against_reference(bf):
+    """DropOut: the mask is drawn on the host from the global NumPy RNG exactly like the reference, so the same seed
+    reproduces the reference's outputs bit for bit (up to FP32 storage)."""
+    from conftest import load_golden
+    from brainforge_b200.layers import DropOut
+    g = load_golden("costs2")
+    stack = bf.LayerStack((4, 3), [DropOut(0.3)])
+    layer = stack.layers[-1]
+    stack.learning = True
+    np.random.seed(99)
+    close(layer.feedforward(g["drop_X"]), g["drop_train"], 1e-7)
+    close(layer.backpropagate(g["drop_D"]), g["drop_back"], 1e-7)
+    assert np.array_equal(np.asarray(layer.mask), g["drop_mask_after"])
+    stack.learning = False
+    np.random.seed(99)
+    close(layer.feedforward(g["drop_X"]), g["drop_eval"], 1e-7)
+
+
 def test_global_average_pooling_known_answer(bf):
     """The reference's own known-answer test (tests/test_layers.py:9-30): planes filled with 1, 2, 3 -> means 1, 2, 3;
     the backward pass of [1, 2, 3] gives inputs / 25."""

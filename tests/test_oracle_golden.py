@@ -66,6 +66,20 @@ def test_global_average_pooling_known_answer():
     np.testing.assert_allclose(st.backpropagate(np.array([[1., 2., 3.]]))[0], inputs / 25)
 
 
+def test_dropout_against_reference():
+    """DropOut (layers/fancy.py:60-90) with the reference's RNG consumption: same seed, same mask."""
+    g = load_golden("costs2")
+    st = O.Stack((4, 3), [("dropout", 0.3)])
+    st.learning = True
+    np.random.seed(99)
+    assert np.array_equal(st.feedforward(g["drop_X"]), g["drop_train"])
+    assert np.array_equal(st.backpropagate(g["drop_D"]), g["drop_back"])
+    assert np.array_equal(st.L[0]["mask"], g["drop_mask_after"])
+    st.learning = False
+    np.random.seed(99)
+    close(st.feedforward(g["drop_X"]), g["drop_eval"])
+
+
 def test_costs_bxent_hinge():
     """The remaining costs of the registry (metrics/costs.py:46-69) against values from the reference
     (tests/golden/make_golden_costs.py)."""
