@@ -220,7 +220,12 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
   size_t off_dh = align_up(off_dg + (size_t)TB * N4 * sizeof(float));
   size_t off_dc = align_up(off_dh + (size_t)BH * sizeof(float));
   size_t off_pw = align_up(off_dc + (size_t)BH * sizeof(float));
-  size_t need = off_pw + (size_t)splits * rows * N4 * sizeof(float);
+  // Z and dgates are both stored with the contraction index (t, b) slowest: the MN-major TMA kernel reads them in place
+  const bool use_mn = precision == BF_PREC_TF32 && getenv("BF_LSTM_GATHER") == nullptr && gemm_tma_mn_ok(Z, nullptr, ZD, N4, TB);
+  int mn_splits = num_sms() / (((ZD + 127) / 128) * ((N4 + 127) / 128));
+  if (mn_splits < 1) mn_splits = 1;
+  const size_t partial_bytes = (size_t)(use_mn ? mn_splits : splits) * rows * N4 * sizeof(float);
+  size_t need = off_pw + partial_bytes;
   void* ws = nullptr;
   int rc = workspace_require(need, &ws);
   if (rc) return rc;
@@ -255,7 +260,13 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
     if (rc) return rc;
   }
   // nablaW = sum_t Z[t]^T @ dgates[t]  (+ ones row -> nablab)
-  {
+  if (use_mn) {
+    int used = 1;
+    rc = launch_gemm_tma_mn(Z, dgates, ZD, N4, (int)TB, partial, partial_bytes, &used, s);
+    if (rc) return rc;
+    rc = launch_splitk_reduce(partial, nablaW, nablab, rows, N4, ZD, used, 0, N4, 1, s);
+    if (rc) return rc;
+  } else {
     LoadMNContigOnes al{Z, (long)ZD, ZD};
     LoadMNContig bl{dgates, (long)N4};
     EpiPartial ep{partial, (long)rows * N4, N4};

@@ -79,7 +79,7 @@ def test_conv_tf32(bf, O, shape):
     close(dF, rF); close(db, rb); close(dX, rX)
 
 
-@pytest.mark.parametrize("T,B,D,H", [(3, 5, 4, 6), (8, 64, 128, 256)])
+@pytest.mark.parametrize("T,B,D,H", [(3, 5, 4, 6), (8, 64, 128, 256), (20, 100, 60, 70), (7, 33, 3, 1)])
 def test_lstm_tf32(bf, O, T, B, D, H):
     rs = np.random.RandomState(T + H)
     X, W, b = rs.randn(T, B, D), rs.randn(D + H, 4 * H) * np.sqrt(2.0 / (D + 5 * H)), rs.randn(4 * H) * 0.1
