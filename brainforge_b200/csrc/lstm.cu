@@ -121,6 +121,349 @@ struct EpiBias {
   __device__ void store(int m, int n, float v, int) const { out[(long)m * N + n] = v + __ldg(b + n); }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// One forward time step as ONE kernel (TF32 path): the gate GEMM Z[t] @ W with the whole elementwise gate update in
+// its epilogue.  A tile is 128 batch rows x 16 hidden units x 4 gates: the B operand gathers the four gates' rows of
+// W^T with four TMA boxes, so one thread owns all four pre-activations of a (row, unit) pair and the (B, 4H) gate
+// matrix never goes to HBM.  Writes the six cache rows, O[t], the recurrent half of Z[t+1] and the derivative rows.
+constexpr int LF_UNITS = 16, LF_N = 4 * LF_UNITS, LF_THREADS = 384, LF_STAGES = 8;
+constexpr uint32_t LF_A_BYTES = 128 * 128, LF_B_BYTES = LF_N * 128, LF_STAGE = LF_A_BYTES + LF_B_BYTES;
+
+struct LstmFwdParams {
+  int t, T, B, D, H, nkb, m_tiles, act;
+  long TBH;
+  const float* bias;
+  float *cache, *O, *Z, *bw;
+};
+
+__device__ __forceinline__ void store8(float* p, const float (&v)[8], int nvalid, bool vec) {
+  if (vec && nvalid == 8) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nvalid) p[i] = v[i];
+  }
+}
+
+__global__ void __launch_bounds__(LF_THREADS, 1)
+lstm_step_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapW, LstmFwdParams p) {
+  extern __shared__ int dyn_smem[];
+  __shared__ __align__(8) uint64_t full[LF_STAGES], empty[LF_STAGES], done;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const int nt = blockIdx.x / p.m_tiles, mt = blockIdx.x - nt * p.m_tiles;
+  const int j0 = nt * LF_UNITS;
+
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(LF_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < LF_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int sl = 0, u = 0;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        if (u > 0) mbar_wait(&empty[sl], (uint32_t)((u - 1) & 1));
+        const uint32_t st = base + (uint32_t)sl * LF_STAGE;
+        mbar_expect_tx(&full[sl], LF_STAGE);
+        tma_load_3d(st, &mapZ, &full[sl], kb * 32, mt * 128, p.t);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          tma_load_2d(st + LF_A_BYTES + g * (LF_UNITS * 128), &mapW, &full[sl], kb * 32, g * p.H + j0);
+        if (++sl == LF_STAGES) { sl = 0; ++u; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = idesc_tf32(128, LF_N);
+    int sl = 0, u = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      mbar_wait(&full[sl], (uint32_t)(u & 1));
+      tc_fence_after();
+      if (leader) {
+        const uint32_t st = base + (uint32_t)sl * LF_STAGE;
+        const uint64_t ad = desc_k_sw128(st), bd = desc_k_sw128(st + LF_A_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_tf32(tmem, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&empty[sl]);
+      }
+      __syncwarp();
+      if (++sl == LF_STAGES) { sl = 0; ++u; }
+    }
+    if (leader) umma_commit(&done);
+  } else if (warp >= 4) {
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int m = mt * 128 + quad * 32 + lane;
+    const int jb = j0 + half * 8;                 // this thread's eight hidden units
+    int nvalid = p.H - jb;
+    nvalid = nvalid > 8 ? 8 : nvalid;
+    const bool vec = (p.H & 3) == 0 && (p.D & 3) == 0;
+    // operands that do not depend on the accumulator are fetched while the MMAs run
+    float cp[8], bc[8], bf_[8], bi[8], bo[8];
+    const long row = (long)m * p.H + jb;
+    const long off = (long)p.t * p.B * p.H;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = m < p.B && i < nvalid;
+      cp[i] = (ok && p.t > 0) ? __ldg(p.cache + off - (long)p.B * p.H + row + i) : 0.f;
+      bc[i] = ok ? __ldg(p.bias + jb + i) : 0.f;
+      bf_[i] = ok ? __ldg(p.bias + p.H + jb + i) : 0.f;
+      bi[i] = ok ? __ldg(p.bias + 2 * p.H + jb + i) : 0.f;
+      bo[i] = ok ? __ldg(p.bias + 3 * p.H + jb + i) : 0.f;
+    }
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    uint32_t pc[8], pf[8], pi[8], po[8];
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 8);
+    tmem_ld8(taddr, pc);
+    tmem_ld8(taddr + LF_UNITS, pf);
+    tmem_ld8(taddr + 2 * LF_UNITS, pi);
+    tmem_ld8(taddr + 3 * LF_UNITS, po);
+    tmem_ld_wait();
+    if (m < p.B && nvalid > 0) {
+      float c[8], ca[8], cv[8], fv[8], iv[8], ov[8], out[8], d0[8], d1[8], d2[8], d3[8], d4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float zc = __uint_as_float(pc[i]) + bc[i], zf = __uint_as_float(pf[i]) + bf_[i];
+        const float zi = __uint_as_float(pi[i]) + bi[i], zo = __uint_as_float(po[i]) + bo[i];
+        cv[i] = act_fwd_rt(p.act, zc);
+        fv[i] = sigmoidf_(zf);
+        iv[i] = sigmoidf_(zi);
+        ov[i] = sigmoidf_(zo);
+        c[i] = cp[i] * fv[i] + cv[i] * iv[i];       // recurrent_op.py:72
+        ca[i] = act_fwd_rt(p.act, c[i]);
+        out[i] = ca[i] * ov[i];                     // recurrent_op.py:74-75
+        d0[i] = act_deriv_from_z(p.act, c[i], ca[i]);
+        d1[i] = act_deriv_from_z(p.act, zc, cv[i]);
+        d2[i] = fv[i] * sigmoidf_(-zf);
+        d3[i] = iv[i] * sigmoidf_(-zi);
+        d4[i] = ov[i] * sigmoidf_(-zo);
+      }
+      float* q = p.cache + off + row;
+      store8(q, c, nvalid, vec);
+      store8(q + p.TBH, ca, nvalid, vec);
+      store8(q + 2 * p.TBH, cv, nvalid, vec);
+      store8(q + 3 * p.TBH, fv, nvalid, vec);
+      store8(q + 4 * p.TBH, iv, nvalid, vec);
+      store8(q + 5 * p.TBH, ov, nvalid, vec);
+      store8(p.O + off + row, out, nvalid, vec);
+      if (p.bw) {
+        float* w = p.bw + off + row;
+        store8(w, d0, nvalid, vec);
+        store8(w + p.TBH, d1, nvalid, vec);
+        store8(w + 2 * p.TBH, d2, nvalid, vec);
+        store8(w + 3 * p.TBH, d3, nvalid, vec);
+        store8(w + 4 * p.TBH, d4, nvalid, vec);
+      }
+      if (p.t + 1 < p.T)
+        store8(p.Z + ((long)(p.t + 1) * p.B + m) * (p.D + p.H) + p.D + jb, out, nvalid, vec);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(LF_N));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The whole forward recurrence as ONE persistent cooperative kernel.  Same tiling as the per-step kernel, one CTA per
+// (128 batch rows, 16 hidden units) for all T steps:
+//   * the CTA's slice of W^T (64 rows x (D+H)) is loaded once and stays in shared memory;
+//   * the cell state of a (row, unit) pair lives in the registers of the thread that owns it;
+//   * Z[t]'s input columns do not depend on the recurrence: their K blocks are prefetched and multiplied while step
+//     t-1 is still finishing; only the K blocks holding O[t-1] wait;
+//   * the wait is a release/acquire counter per (batch tile, step) shared by the CTAs of one batch tile -- a tile of
+//     batch rows never waits for the rest of the grid.  The producer orders the acquire before its TMA reads with a
+//     generic->async proxy fence;
+//   * of the thirteen output rows only O[t] -> Z[t+1] is on the critical path; it is stored and published first.
+constexpr int LS_RING = 6;
+
+struct LstmSeqParams {
+  int T, B, D, H, nkb, kb_dep, m_tiles, n_tiles, act;
+  long TBH;
+  const float* bias;
+  float *cache, *O, *Z, *bw;
+  unsigned* flags;      // [m_tiles][T], zeroed before the launch
+};
+
+__global__ void __launch_bounds__(LF_THREADS, 1)
+lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapW, LstmSeqParams p) {
+  extern __shared__ int dyn_smem[];
+  __shared__ __align__(8) uint64_t w_full, full[LS_RING], empty[LS_RING], t_full[2], t_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const uint32_t wbase = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const uint32_t ring = wbase + (uint32_t)p.nkb * LF_B_BYTES;
+  const int nt = blockIdx.x / p.m_tiles, mt = blockIdx.x - nt * p.m_tiles;
+  const int j0 = nt * LF_UNITS;
+
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * LF_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < LS_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_expect_tx(&w_full, (uint32_t)p.nkb * LF_B_BYTES);
+      for (int kb = 0; kb < p.nkb; ++kb)
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          tma_load_2d(wbase + (uint32_t)kb * LF_B_BYTES + g * (LF_UNITS * 128), &mapW, &w_full, kb * 32, g * p.H + j0);
+      int sl = 0, u = 0;
+      for (int t = 0; t < p.T; ++t) {
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          if (kb == p.kb_dep && t > 0) {
+            const unsigned* flag = p.flags + (size_t)mt * p.T + (t - 1);
+            unsigned v;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            } while (v < (unsigned)p.n_tiles);
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          if (u > 0) mbar_wait(&empty[sl], (uint32_t)((u - 1) & 1));
+          mbar_expect_tx(&full[sl], LF_A_BYTES);
+          tma_load_3d(ring + (uint32_t)sl * LF_A_BYTES, &mapZ, &full[sl], kb * 32, mt * 128, t);
+          if (++sl == LS_RING) { sl = 0; ++u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = idesc_tf32(128, LF_N);
+    mbar_wait(&w_full, 0);
+    int sl = 0, u = 0;
+    for (int t = 0; t < p.T; ++t) {
+      const int set = t & 1, tu = t >> 1;
+      if (tu > 0) mbar_wait(&t_empty[set], (uint32_t)((tu - 1) & 1));
+      tc_fence_after();
+      const uint32_t acc = tmem + (uint32_t)set * LF_N;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(&full[sl], (uint32_t)(u & 1));
+        tc_fence_after();
+        if (leader) {
+          const uint64_t ad = desc_k_sw128(ring + (uint32_t)sl * LF_A_BYTES), bd = desc_k_sw128(wbase + (uint32_t)kb * LF_B_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&empty[sl]);
+        }
+        __syncwarp();
+        if (++sl == LS_RING) { sl = 0; ++u; }
+      }
+      if (leader) umma_commit(&t_full[set]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int m = mt * 128 + quad * 32 + lane;
+    const int jb = j0 + half * 8;
+    int nvalid = p.H - jb;
+    nvalid = nvalid > 8 ? 8 : nvalid;
+    const bool vec = (p.H & 3) == 0 && (p.D & 3) == 0;
+    const bool live = m < p.B && nvalid > 0;
+    const long row = (long)m * p.H + jb;
+    float c[8], bc[8], bf_[8], bi[8], bo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool ok = live && i < nvalid;
+      c[i] = 0.f;
+      bc[i] = ok ? __ldg(p.bias + jb + i) : 0.f;
+      bf_[i] = ok ? __ldg(p.bias + p.H + jb + i) : 0.f;
+      bi[i] = ok ? __ldg(p.bias + 2 * p.H + jb + i) : 0.f;
+      bo[i] = ok ? __ldg(p.bias + 3 * p.H + jb + i) : 0.f;
+    }
+    for (int t = 0; t < p.T; ++t) {
+      const int set = t & 1, tu = t >> 1;
+      mbar_wait(&t_full[set], (uint32_t)(tu & 1));
+      tc_fence_after();
+      uint32_t pc[8], pf[8], pi[8], po[8];
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * LF_N + half * 8);
+      tmem_ld8(taddr, pc);
+      tmem_ld8(taddr + LF_UNITS, pf);
+      tmem_ld8(taddr + 2 * LF_UNITS, pi);
+      tmem_ld8(taddr + 3 * LF_UNITS, po);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[set]);      // the accumulator is in registers: the MMA warp may reuse the set
+      float ca[8], cv[8], fv[8], iv[8], ov[8], out[8], zc[8], zf[8], zi[8], zo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        zc[i] = __uint_as_float(pc[i]) + bc[i]; zf[i] = __uint_as_float(pf[i]) + bf_[i];
+        zi[i] = __uint_as_float(pi[i]) + bi[i]; zo[i] = __uint_as_float(po[i]) + bo[i];
+        cv[i] = act_fwd_rt(p.act, zc[i]);
+        fv[i] = sigmoidf_(zf[i]);
+        iv[i] = sigmoidf_(zi[i]);
+        ov[i] = sigmoidf_(zo[i]);
+        c[i] = c[i] * fv[i] + cv[i] * iv[i];        // recurrent_op.py:72
+        ca[i] = act_fwd_rt(p.act, c[i]);
+        out[i] = ca[i] * ov[i];                     // recurrent_op.py:74-75
+      }
+      const long off = (long)t * p.B * p.H;
+      if (t + 1 < p.T) {
+        if (live) store8(p.Z + ((long)(t + 1) * p.B + m) * (p.D + p.H) + p.D + jb, out, nvalid, vec);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 128) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + (size_t)mt * p.T + t) : "memory");
+      }
+      if (live) {
+        float* q = p.cache + off + row;
+        store8(q, c, nvalid, vec);
+        store8(q + p.TBH, ca, nvalid, vec);
+        store8(q + 2 * p.TBH, cv, nvalid, vec);
+        store8(q + 3 * p.TBH, fv, nvalid, vec);
+        store8(q + 4 * p.TBH, iv, nvalid, vec);
+        store8(q + 5 * p.TBH, ov, nvalid, vec);
+        store8(p.O + off + row, out, nvalid, vec);
+        if (p.bw) {
+          float d[8];
+          float* w = p.bw + off + row;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = act_deriv_from_z(p.act, c[i], ca[i]);
+          store8(w, d, nvalid, vec);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = act_deriv_from_z(p.act, zc[i], cv[i]);
+          store8(w + p.TBH, d, nvalid, vec);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = fv[i] * sigmoidf_(-zf[i]);
+          store8(w + 2 * p.TBH, d, nvalid, vec);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = iv[i] * sigmoidf_(-zi[i]);
+          store8(w + 3 * p.TBH, d, nvalid, vec);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = ov[i] * sigmoidf_(-zo[i]);
+          store8(w + 4 * p.TBH, d, nvalid, vec);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * LF_N));
+}
+
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // dst (C x R) = src (R x C)^T through a padded shared-memory tile
@@ -157,10 +500,13 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
   const long TB = (long)T * B, BH = (long)B * H, ZD = D + H;
   void* ws = nullptr;
   const size_t gates_bytes = align_up((size_t)B * 4 * H * sizeof(float));
-  int rc = workspace_require(gates_bytes + (size_t)ZD * 4 * H * sizeof(float), &ws);
+  const size_t wt_bytes = align_up((size_t)ZD * 4 * H * sizeof(float));
+  const size_t flag_bytes = (size_t)((B + 127) / 128) * T * sizeof(unsigned);
+  int rc = workspace_require(gates_bytes + wt_bytes + flag_bytes, &ws);
   if (rc) return rc;
   float* gates = (float*)ws;
-  float* Wt = (float*)((char*)ws + gates_bytes);     // W^T (4H x (D+H)): the K-major B operand of the TMA-fed gate GEMM
+  float* Wt = (float*)((char*)ws + gates_bytes);
+  unsigned* flags = (unsigned*)((char*)ws + gates_bytes + wt_bytes);     // W^T (4H x (D+H)): the K-major B operand of the TMA-fed gate GEMM
   const bool tma = precision == BF_PREC_TF32 && gemm_tma_ok(Z, Wt, B, 4 * H, (int)ZD) && ((ZD * 4) % 16) == 0 &&
                    getenv("BF_LSTM_GATHER") == nullptr;
   if (tma) {
@@ -176,6 +522,52 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
   float* ig = cache + 4 * TB * H;
   float* o = cache + 5 * TB * H;
   const int K = D + H, N = 4 * H;
+  // whole step in one kernel
+  if (tma && getenv("BF_LSTM_UNFUSED") == nullptr) {
+    CUtensorMap mZ, mW;
+    {
+      uint64_t dims[3] = {(uint64_t)ZD, (uint64_t)B, (uint64_t)T};
+      uint64_t str[2] = {(uint64_t)ZD, (uint64_t)B * ZD};
+      uint32_t box[3] = {32, 128, 1};
+      if (!tma_make_map(&mZ, Z, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return fail(BF_ERR_CUDA, "bf_lstm_forward: cuTensorMapEncodeTiled failed (Z)");
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)ZD, (uint64_t)N};
+      uint64_t str[1] = {(uint64_t)ZD};
+      uint32_t box[2] = {32, LF_UNITS};
+      if (!tma_make_map(&mW, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return fail(BF_ERR_CUDA, "bf_lstm_forward: cuTensorMapEncodeTiled failed (W)");
+    }
+    {
+      // persistent form: every tile resident at once (one CTA per SM), W slice + A ring within shared memory
+      const int nkb = (K + 31) / 32, m_tiles = (B + 127) / 128, n_tiles = (H + LF_UNITS - 1) / LF_UNITS;
+      const size_t smem = 1024 + (size_t)nkb * LF_B_BYTES + (size_t)LS_RING * LF_A_BYTES;
+      if (m_tiles * n_tiles <= num_sms() && smem <= 220 * 1024 && getenv("BF_LSTM_STEPWISE") == nullptr) {
+        LstmSeqParams q;
+        q.T = T; q.B = B; q.D = D; q.H = H; q.nkb = nkb; q.kb_dep = D / 32; q.m_tiles = m_tiles; q.n_tiles = n_tiles;
+        q.act = act; q.TBH = TB * H; q.bias = b; q.cache = cache; q.O = O; q.Z = Z; q.bw = bw; q.flags = flags;
+        BF_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, s));
+        BF_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void* args[] = {(void*)&mZ, (void*)&mW, (void*)&q};
+        BF_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_fwd_kernel, dim3(m_tiles * n_tiles), dim3(LF_THREADS), args, smem, s));
+        count_launch();
+        set_last_path(2);
+        return BF_OK;
+      }
+    }
+    LstmFwdParams p;
+    p.T = T; p.B = B; p.D = D; p.H = H; p.nkb = (K + 31) / 32; p.m_tiles = (B + 127) / 128; p.act = act;
+    p.TBH = TB * H; p.bias = b; p.cache = cache; p.O = O; p.Z = Z; p.bw = bw;
+    const int n_tiles = (H + LF_UNITS - 1) / LF_UNITS;
+    const size_t smem = 1024 + (size_t)LF_STAGES * LF_STAGE;
+    BF_CUDA(cudaFuncSetAttribute(lstm_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int t = 0; t < T; ++t) {
+      p.t = t;
+      lstm_step_fwd_kernel<<<p.m_tiles * n_tiles, LF_THREADS, smem, s>>>(mZ, mW, p);
+      BF_LAUNCH_CHECK();
+    }
+    set_last_path(2);
+    return BF_OK;
+  }
   for (int t = 0; t < T; ++t) {
     EpiBias ep{gates, b, N};
     if (tma) {
