@@ -438,6 +438,41 @@ class MaxPoolOp:
             return iy // fdim, ix // fdim
 
 
+# --------------------------------------------------------------------------- plain recurrence
+class RecurrentOp:
+    """atomic/recurrent_op.py:9-43.  X is time-major (T,B,D), W (D+H,H).  `backward` returns the reference's
+    results literally, including `dX = E[:, :, :indim]` (:40): a slice of the scaled error tensor."""
+
+    def __init__(self, activation):
+        self.activation = activation
+        self.actfn = activations[activation]()
+
+    def forward(self, X, W, b):
+        x, w, bd = as_device(X), as_device(W), as_device(b)
+        T, B, D = x.shape
+        H = w.shape[-1]
+        if w.shape[0] != D + H:
+            raise ValueError("recurrent weight shape %s does not match D+H=%d" % (w.shape, D + H))
+        O = DeviceArray.empty(T, B, H)
+        Z = DeviceArray.empty(T, B, D + H)
+        call(L.bf_rnn_forward, x.ptr, w.ptr, bd.ptr, O.ptr, Z.ptr, T, B, D, H, _lib.ACT[self.activation], precision(),
+             stream_ptr())
+        return _ret(X, O, Z)
+
+    def backward(self, Z, O, E, W, nablaW=None, nablab=None):
+        z, o, e, w = as_device(Z), as_device(O), as_device(E), as_device(W)
+        T, B, ZD = z.shape
+        H = w.shape[-1]
+        D = ZD - H
+        Eout = DeviceArray.empty(T, B, H)
+        nablaW = DeviceArray.empty(ZD, H) if nablaW is None else nablaW
+        nablab = DeviceArray.empty(H) if nablab is None else nablab
+        call(L.bf_rnn_backward, z.ptr, o.ptr, e.ptr, w.ptr, Eout.ptr, nablaW.ptr, nablab.ptr, T, B, D, H,
+             _lib.ACT[self.activation], precision(), stream_ptr())
+        dX = Eout if D >= H else DeviceArray(Eout.t[:, :, :D].contiguous())      # recurrent_op.py:40
+        return _ret(Z, dX, nablaW, nablab)
+
+
 # --------------------------------------------------------------------------- LSTM
 class LSTMOp:
     """atomic/recurrent_op.py:46-112.  X is time-major (T,B,D); gate order along 4H is [cand|f|i|o]."""

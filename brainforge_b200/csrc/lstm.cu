@@ -483,6 +483,28 @@ __global__ void lstm_transpose_kernel(const float* __restrict__ src, float* __re
   }
 }
 
+// ---- plain recurrent layer (atomic/recurrent_op.py:9-43): O[t] = act([X[t], O[t-1]] @ W + b)
+struct EpiRnnFwd {
+  float* O; float* Znext; const float* b; int D, H, act;
+  __device__ void store(int m, int n, float v, int) const {
+    const float a = act_fwd_rt(act, v + __ldg(b + n));
+    O[(long)m * H + n] = a;
+    if (Znext) Znext[(long)m * (D + H) + D + n] = a;
+  }
+};
+// E'[t-1] = (E[t-1] + deltaZ[t][:, D:]) * act'(O[t-1])  -- recurrent_op.py:35-38 with the next step's product folded in
+struct EpiRnnBwd {
+  const float* Eprev; const float* Oprev; float* out; int H, act;
+  __device__ void store(int m, int n, float v, int) const {
+    const long i = (long)m * H + n;
+    out[i] = (__ldg(Eprev + i) + v) * act_bwd_rt(act, __ldg(Oprev + i));
+  }
+};
+__global__ void rnn_scale_kernel(const float* __restrict__ E, const float* __restrict__ O, float* __restrict__ out, long n, int act) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = E[i] * act_bwd_rt(act, O[i]);
+}
+
 }  // namespace bf
 
 using namespace bf;
@@ -668,6 +690,102 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
     if (rc) return rc;
   }
   return BF_OK;
+}
+
+// Plain recurrent layer, atomic/recurrent_op.py:14-27.  X (T,B,D), W (D+H,H), b (H) -> O (T,B,H), Z (T,B,D+H).
+int bf_rnn_forward(const float* X, const float* W, const float* b, float* O, float* Z, int T, int B, int D, int H,
+                   int act, int precision, void* stream) {
+  BF_REQUIRE(X && W && b && O && Z, BF_ERR_ARG, "bf_rnn_forward: null pointer");
+  BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_rnn_forward: bad shape");
+  BF_REQUIRE(act == BF_ACT_TANH || act == BF_ACT_RELU || act == BF_ACT_SIGMOID || act == BF_ACT_LINEAR, BF_ERR_ARG,
+             "bf_rnn_forward: bad activation %d", act);
+  if (T == 0 || B == 0) return BF_OK;
+  cudaStream_t s = as_stream(stream);
+  const long TB = (long)T * B, BH = (long)B * H;
+  const int ZD = D + H;
+  void* ws = nullptr;
+  int rc = workspace_require((size_t)ZD * H * sizeof(float), &ws);
+  if (rc) return rc;
+  float* Wt = (float*)ws;
+  const bool tma = precision == BF_PREC_TF32 && gemm_tma_ok(Z, Wt, B, H, ZD) && getenv("BF_LSTM_GATHER") == nullptr;
+  if (tma) {
+    lstm_transpose_kernel<<<dim3((H + 31) / 32, (ZD + 31) / 32), dim3(32, 8), 0, s>>>(W, Wt, ZD, H);
+    BF_LAUNCH_CHECK();
+  }
+  lstm_fill_z_kernel<<<ew_grid(TB * D + BH, 256), 256, 0, s>>>(X, Z, TB, B, D, H);
+  BF_LAUNCH_CHECK();
+  for (int t = 0; t < T; ++t) {
+    EpiRnnFwd ep{O + (long)t * BH, t + 1 < T ? Z + (long)(t + 1) * B * ZD : nullptr, b, D, H, act};
+    if (tma) {
+      rc = launch_gemm_tma(Z + (long)t * B * ZD, Wt, B, H, ZD, ep, s);
+    } else {
+      LoadKContig al{Z + (long)t * B * ZD, (long)ZD};
+      LoadMNContig bl{W, (long)H};
+      rc = launch_gemm(precision, al, bl, ep, B, H, ZD, 1, (ZD + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
+    if (rc) return rc;
+  }
+  return BF_OK;
+}
+
+// atomic/recurrent_op.py:29-43.  Eout (T,B,H) receives the reference's in-place modified E (its `dX` is the slice
+// Eout[:, :, :D], taken by the caller); nablaW (D+H,H), nablab (H).
+int bf_rnn_backward(const float* Z, const float* O, const float* E, const float* W, float* Eout, float* nablaW,
+                    float* nablab, int T, int B, int D, int H, int act, int precision, void* stream) {
+  BF_REQUIRE(Z && O && E && W && Eout && nablaW && nablab, BF_ERR_ARG, "bf_rnn_backward: null pointer");
+  BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_rnn_backward: bad shape");
+  cudaStream_t s = as_stream(stream);
+  const long TB = (long)T * B, BH = (long)B * H;
+  const int ZD = D + H;
+  if (T == 0 || B == 0) {
+    BF_CUDA(cudaMemsetAsync(nablaW, 0, (size_t)ZD * H * sizeof(float), s));
+    BF_CUDA(cudaMemsetAsync(nablab, 0, (size_t)H * sizeof(float), s));
+    return BF_OK;
+  }
+  BF_REQUIRE(TB < 2147483647L, BF_ERR_ARG, "bf_rnn_backward: T*B too large");
+  const int rows = ZD + 1;
+  int bm = rows <= 32 ? 32 : (rows <= 64 ? 64 : 128), bn = H <= 16 ? 16 : (H <= 32 ? 32 : (H <= 64 ? 64 : 128));
+  int tiles = ((rows + bm - 1) / bm) * ((H + bn - 1) / bn);
+  int kps = 0;
+  int splits = choose_splits(tiles, (int)TB, &kps);
+  const bool use_mn = precision == BF_PREC_TF32 && getenv("BF_LSTM_GATHER") == nullptr && gemm_tma_mn_ok(Z, Eout, ZD, H, TB);
+  int mn_splits = num_sms() / (((ZD + 127) / 128) * ((H + 127) / 128));
+  if (mn_splits < 1) mn_splits = 1;
+  const size_t partial_bytes = (size_t)(use_mn ? mn_splits : splits) * rows * H * sizeof(float);
+  void* ws = nullptr;
+  int rc = workspace_require(partial_bytes, &ws);
+  if (rc) return rc;
+  float* partial = (float*)ws;
+  const float* Wh = W + (long)D * H;      // rows D.. of W: B(n, k) = W[(D + n) * H + k], K-major as stored
+  rnn_scale_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(E + (T - 1) * BH, O + (T - 1) * BH, Eout + (T - 1) * BH, BH, act);
+  BF_LAUNCH_CHECK();
+  for (int t = T - 1; t >= 1; --t) {
+    const float* Et = Eout + (long)t * BH;
+    EpiRnnBwd ep{E + (long)(t - 1) * BH, O + (long)(t - 1) * BH, Eout + (long)(t - 1) * BH, H, act};
+    if (precision == BF_PREC_TF32 && gemm_tma_ok(Et, Wh, B, H, H) && getenv("BF_LSTM_GATHER") == nullptr) {
+      rc = launch_gemm_tma(Et, Wh, B, H, H, ep, s);
+    } else {
+      LoadKContig al{Et, (long)H};
+      LoadKContig bl{Wh, (long)H};
+      rc = launch_gemm(precision, al, bl, ep, B, H, H, 1, (H + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
+    if (rc) return rc;
+  }
+  // nablaW = sum_t Z[t]^T @ E'[t], nablab = column sums of E'  (recurrent_op.py:41-42)
+  if (use_mn) {
+    int used = 1;
+    rc = launch_gemm_tma_mn(Z, Eout, ZD, H, (int)TB, partial, partial_bytes, &used, s);
+    if (rc) return rc;
+    rc = launch_splitk_reduce(partial, nablaW, nablab, rows, H, ZD, used, 0, H, 1, s);
+  } else {
+    LoadMNContigOnes al{Z, (long)ZD, ZD};
+    LoadMNContig bl{Eout, (long)H};
+    EpiPartial ep{partial, (long)rows * H, H};
+    rc = launch_gemm(precision, al, bl, ep, rows, H, (int)TB, splits, kps, 0, s);
+    if (rc) return rc;
+    rc = launch_splitk_reduce(partial, nablaW, nablab, rows, H, ZD, splits, 0, H, 1, s);
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-"""layers/recurrent.py of the reference: the LSTM layer (RLayer/GRU/Clockwork/Reservoir are out of scope)."""
+"""layers/recurrent.py of the reference: RLayer and LSTM (GRU/Clockwork/Reservoir are out of scope)."""
 import ctypes
 
 import numpy as np
@@ -14,6 +14,46 @@ def _transpose01(x):
     out = DeviceArray.empty(d1, d0, d2)
     call(_lib.lib.bf_transpose01, x.ptr, out.ptr, d0, d1, d2, stream_ptr())
     return out
+
+
+class RLayer(FFBase):
+    """layers/recurrent.py:12-47,50-77.  Input (B,T,D); weights white(D+H, H), zero biases; gradients ASSIGNED (:74)."""
+
+    def __init__(self, neurons, activation, return_seq=False, **kw):
+        super().__init__(neurons, activation, **kw)
+        self.Z = 0
+        self.time = 0
+        self.return_seq = return_seq
+        self.op = atomic.RecurrentOp(activation if isinstance(activation, str) else str(activation))
+
+    def connect(self, brain):
+        self.Z = brain.outshape[-1] + self.neurons
+        self._init_params(white(self.Z, self.neurons), np.zeros(self.neurons))
+        super().connect(brain)
+
+    def _fwd(self, x):
+        self.inputs = _transpose01(x)
+        self.time = self.inputs.shape[0]
+        self.output, self.Z = self.op.forward(self.inputs, self.weights, self.biases)
+        return _transpose01(self.output) if self.return_seq else self.output[-1]
+
+    def _bwd(self, delta):
+        if self.return_seq:
+            E = _transpose01(delta)
+        else:
+            E = DeviceArray.zeros(self.time, len(delta), self.neurons)
+            last = E[-1]
+            call(_lib.lib.bf_act_forward, _lib.ACT["linear"], delta.ptr, last.ptr, last.size, stream_ptr())
+        dX, _, _ = self.op.backward(Z=self.Z, O=self.output, E=E, W=self.weights, nablaW=self.nabla_w,
+                                    nablab=self.nabla_b)
+        return _transpose01(dX)
+
+    @property
+    def outshape(self):
+        return self.neurons,
+
+    def __str__(self):
+        return self.__class__.__name__ + "-{}-{}".format(self.neurons, str(self.activation)[:4])
 
 
 class LSTM(FFBase):

@@ -220,6 +220,16 @@ BF_API int bf_lstm_backward(const float* Z, const float* O, const float* E, cons
                      const float* bw, float* dX, float* nablaW, float* nablab, int T, int B, int D, int H, int act,
                      int precision, void* stream);
 
+/* ---- plain recurrent layer: atomic/recurrent_op.py:9-43 (RLayer, layers/recurrent.py:50-77) ---- */
+/* RecurrentOp(act).forward(X,W,b) -> (O,Z).  X (T,B,D) time-major, W (D+H,H), b (H); O (T,B,H), Z (T,B,D+H). */
+BF_API int bf_rnn_forward(const float* X, const float* W, const float* b, float* O, float* Z, int T, int B, int D, int H,
+                   int act, int precision, void* stream);
+/* RecurrentOp.backward(Z,O,E,W) -> (dX, nablaW (D+H,H), nablab (H)).  E (T,B,H) is read only; Eout (T,B,H) receives
+ * the array the reference leaves in E (each step scaled by act'(O[t]) and fed back through W[D:]); the reference's
+ * dX is literally its slice [:, :, :D] (recurrent_op.py:40), which the caller takes. */
+BF_API int bf_rnn_backward(const float* Z, const float* O, const float* E, const float* W, float* Eout, float* nablaW,
+                    float* nablab, int T, int B, int D, int H, int act, int precision, void* stream);
+
 /* ---- optimizer step on the flat vectors: optimizers/*.py, learner/backpropagation.py:37-42 ---- */
 /* W <- optimize(W, g, m) in place.  s1 = velocity, s2 = memory (NULL where the rule has none).
  * hp: SGD{} MOMENTUM{mu} NESTEROV{mu} ADAGRAD{eps} RMSPROP{decay,eps} ADAM{decay_velocity,decay_memory,eps}.

@@ -186,6 +186,39 @@ def accuracy(outputs, targets):
 
 
 # --------------------------------------------------------------------------
+# plain recurrence                              atomic/recurrent_op.py:9-43
+# --------------------------------------------------------------------------
+def rnn_forward(X, W, b, activation="tanh"):
+    """atomic/recurrent_op.py:14-27.  X (T,B,D); W (D+H,H).  Returns O (T,B,H), Z (T,B,D+H)."""
+    H = W.shape[-1]
+    T, B, D = X.shape
+    Z = np.zeros((T, B, D + H))
+    O = np.zeros((T, B, H))
+    for t in range(T):
+        Z[t] = np.concatenate((X[t], O[t - 1]), axis=-1)
+        O[t] = act_forward(activation, np.dot(Z[t], W) + b)
+    return O, Z
+
+
+def rnn_backward(Z, O, E, W, activation="tanh"):
+    """atomic/recurrent_op.py:29-43 (E copied; the reference scribbles on the caller's array).  The returned dX is the
+    reference's `E[:, :, :indim]` (:40) -- a slice of the scaled error tensor, not deltaZ; kept as is."""
+    H = W.shape[-1]
+    T, B, zdim = Z.shape
+    D = zdim - H
+    E = np.array(E, dtype=F64, copy=True)
+    bwO = act_backward(activation, O)
+    for t in range(T - 1, -1, -1):
+        E[t] *= bwO[t]
+        deltaZ = np.dot(E[t], W.T)
+        if t:
+            E[t - 1] += deltaZ[:, D:]
+    nablaW = np.matmul(Z.transpose(0, 2, 1), E).sum(axis=0)
+    nablab = E.sum(axis=(0, 1))
+    return E[:, :, :D], nablaW, nablab
+
+
+# --------------------------------------------------------------------------
 # LSTM                                        atomic/recurrent_op.py:46-112
 # --------------------------------------------------------------------------
 def lstm_forward(X, W, b, activation="tanh"):
@@ -323,6 +356,7 @@ class Stack:
       ("gap",)                                  layers/tensor.py:95-114 (GlobalAveragePooling)
       ("dropout", dropchance)                   layers/fancy.py:60-90 (set `stack.learning = True` while training)
       ("lstm", neurons, activation, return_seq) layers/recurrent.py:12-47,80-113
+      ("rnn", neurons, activation, return_seq)  layers/recurrent.py:12-47,50-77 (RLayer)
 
     Weights are drawn with ``white`` in stack order at construction, i.e. with
     the same RNG consumption as the reference's ``connect`` calls.
@@ -376,6 +410,13 @@ class Stack:
                 lay.update(act=s[2] if len(s) > 2 else "tanh", n=n,
                            return_seq=bool(s[3]) if len(s) > 3 else False,
                            W=white(zdim, 4 * n), b=np.zeros(4 * n) + 7.0)  # layers/recurrent.py:82,98
+                shape = (shape[0], n) if lay["return_seq"] else (n,)
+            elif kind == "rnn":
+                n = int(s[1])
+                zdim = shape[-1] + n
+                lay.update(act=s[2] if len(s) > 2 else "tanh", n=n,
+                           return_seq=bool(s[3]) if len(s) > 3 else False,
+                           W=white(zdim, n), b=np.zeros(n))                # layers/recurrent.py:61-64
                 shape = (shape[0], n) if lay["return_seq"] else (n,)
             else:
                 raise ValueError(kind)
@@ -444,6 +485,11 @@ class Stack:
                 O, l["Z"], l["cache"] = lstm_forward(l["inputs"], l["W"], l["b"], l["act"])
                 l["O"] = O
                 X = O.transpose(1, 0, 2) if l["return_seq"] else O[-1]
+            elif k == "rnn":                       # layers/recurrent.py:26,66-69
+                l["inputs"] = X.transpose(1, 0, 2)
+                O, l["Z"] = rnn_forward(l["inputs"], l["W"], l["b"], l["act"])
+                l["O"] = O
+                X = O.transpose(1, 0, 2) if l["return_seq"] else O[-1]
             l["output"] = X
         return X
 
@@ -479,6 +525,14 @@ class Stack:
                     E = np.zeros((l["inputs"].shape[0], len(error), l["n"]))
                     E[-1] = error
                 dX, l["gW"], l["gb"] = lstm_backward(l["Z"], l["O"], E, l["W"], l["cache"], l["act"])
+                error = dX.transpose(1, 0, 2)
+            elif k == "rnn":                       # layers/recurrent.py:31-40,71-77 (ASSIGNS)
+                if l["return_seq"]:
+                    E = error.transpose(1, 0, 2)
+                else:
+                    E = np.zeros((l["inputs"].shape[0], len(error), l["n"]))
+                    E[-1] = error
+                dX, l["gW"], l["gb"] = rnn_backward(l["Z"], l["O"], E, l["W"], l["act"])
                 error = dX.transpose(1, 0, 2)
         return error
 

@@ -28,6 +28,9 @@ def build_b200(input_shape, spec, cost, optimizer, seed=None, **kw):
             layers.append(GlobalAveragePooling())
         elif k == "lstm":
             layers.append(LSTM(s[1], activation=s[2], return_seq=s[3] if len(s) > 3 else False))
+        elif k == "rnn":
+            from brainforge_b200.layers import RLayer
+            layers.append(RLayer(s[1], activation=s[2], return_seq=s[3] if len(s) > 3 else False))
         else:
             raise ValueError(k)
     return bf.Backpropagation(input_shape=input_shape, layerstack=layers, cost=cost, optimizer=optimizer, **kw)

@@ -191,6 +191,59 @@ def test_lstm_vs_oracle(bf, O, T, B, D, H, act):
     close(dX, rX); close(gW, rW); close(gb, rb)
 
 
+def test_rnn_against_reference(bf):
+    """RecurrentOp / RLayer against arrays produced by the reference (tests/golden/make_golden_rnn.py)."""
+    from conftest import load_golden
+    from brainforge_b200.layers import RLayer
+    g = load_golden("rnn")
+    for tag in "abc":
+        X, W, b, E = (g["%s_%s" % (tag, k)] for k in "XWbE")
+        for act in ("tanh", "sigmoid", "relu"):
+            op = bf.atomic.RecurrentOp(act)
+            o, z = op.forward(X, W, b)
+            close(o, g["%s_%s_O" % (tag, act)]); close(z, g["%s_%s_Z" % (tag, act)])
+            E0 = E.copy()
+            dX, gW, gb = op.backward(Z=g["%s_%s_Z" % (tag, act)], O=g["%s_%s_O" % (tag, act)], E=E, W=W)
+            assert np.array_equal(E, E0)                     # the caller's array is left alone
+            assert dX.shape == g["%s_%s_dX" % (tag, act)].shape
+            close(dX, g["%s_%s_dX" % (tag, act)]); close(gW, g["%s_%s_gW" % (tag, act)]); close(gb, g["%s_%s_gb" % (tag, act)])
+    for seq in (0, 1):
+        k = "layer_seq%d_" % seq
+        stack = bf.LayerStack((6, 5), [RLayer(4, "tanh", return_seq=bool(seq))])
+        layer = stack.layers[-1]
+        layer.set_weights([g[k + "W"], g[k + "b"]], fold=False)
+        close(layer.feedforward(g[k + "X"]), g[k + "Y"])
+        close(layer.backpropagate(g[k + "D"]), g[k + "dX"])
+        close(layer.nabla_w, g[k + "gW"]); close(layer.nabla_b, g[k + "gb"])
+
+
+@pytest.mark.parametrize("T,B,D,H,act", [(1, 1, 1, 1, "tanh"), (9, 33, 20, 17, "relu"), (16, 200, 64, 128, "tanh")])
+def test_rnn_vs_oracle(bf, O, T, B, D, H, act):
+    rs = np.random.RandomState(T * 5 + H)
+    X, W, b = rs.randn(T, B, D), rs.randn(D + H, H) * np.sqrt(2.0 / (D + 2 * H)), rs.randn(H) * 0.1
+    op = bf.atomic.RecurrentOp(act)
+    O_, Z_ = op.forward(X, W, b)
+    rO, rZ = O.rnn_forward(X, W, b, act)
+    close(O_, rO); close(Z_, rZ)
+    E = rs.randn(T, B, H)
+    dX, gW, gb = op.backward(Z=rZ, O=rO, E=E, W=W)
+    rX, rW, rb = O.rnn_backward(rZ, rO, E, W, act)
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
+def test_rnn_network_trains_like_oracle(bf):
+    """Stacked recurrent layers (return_seq=True feeding an LSTM, as in the reference's README examples) + Dense."""
+    from helpers import build_b200, build_oracle, onehot
+    spec = [("rnn", 12, "tanh", True), ("lstm", 9, "tanh", False), ("dense", 5, "softmax")]
+    net = build_b200((7, 12), spec, "cxent", "adam", seed=5)
+    ora = build_oracle((7, 12), spec, "cxent", "adam", seed=5)
+    rs = np.random.RandomState(3)
+    for _ in range(3):
+        X, Y = rs.randn(10, 7, 12), onehot(rs, 10, 5)
+        close(net.learn_batch(X, Y)["cost"], ora.learn_batch(X, Y)["cost"], 1e-4)
+    close(net.layers.get_weights(), ora.get_weights(), 1e-4)
+
+
 def test_empty_batch(bf):
     op = bf.atomic.DenseOp()
     assert op.forward(np.zeros((0, 5)), np.ones((5, 3)), np.zeros(3)).shape == (0, 3)

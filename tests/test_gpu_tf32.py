@@ -93,6 +93,21 @@ def test_lstm_tf32(bf, O, T, B, D, H):
     close(dX, rX); close(gW, rW); close(gb, rb)
 
 
+@pytest.mark.parametrize("T,B,D,H", [(6, 50, 12, 20), (10, 300, 64, 128)])
+def test_rnn_tf32(bf, O, T, B, D, H):
+    rs = np.random.RandomState(T + H)
+    X, W, b = rs.randn(T, B, D), rs.randn(D + H, H) * np.sqrt(2.0 / (D + 2 * H)), rs.randn(H) * 0.1
+    op = bf.atomic.RecurrentOp("tanh")
+    O_, Z_ = op.forward(X, W, b)
+    assert used_tensor_cores(bf)
+    rO, rZ = O.rnn_forward(X, W, b, "tanh")
+    close(O_, rO); close(Z_, rZ)
+    E = rs.randn(T, B, H)
+    dX, gW, gb = op.backward(Z=rZ, O=rO, E=E, W=W)
+    rX, rW, rb = O.rnn_backward(rZ, rO, E, W, "tanh")
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
 @pytest.mark.parametrize("cfg,batch", [("cfg1", 20), ("cfg2", 32), ("cfg3", 16), ("cfg4", 4)])
 def test_configs_tf32(bf, cfg, batch):
     ishape, spec, cost, optimizer = CFG[cfg]

@@ -80,6 +80,27 @@ def test_dropout_against_reference():
     close(st.feedforward(g["drop_X"]), g["drop_eval"])
 
 
+def test_rnn_against_reference():
+    """RecurrentOp / RLayer (atomic/recurrent_op.py:9-43, layers/recurrent.py:50-77) against arrays produced by the
+    reference (tests/golden/make_golden_rnn.py) -- including its `dX = E[:, :, :indim]` slice."""
+    g = load_golden("rnn")
+    for tag in "abc":
+        X, W, b, E = (g["%s_%s" % (tag, k)] for k in "XWbE")
+        for act in ("tanh", "sigmoid", "relu"):
+            o, z = O.rnn_forward(X, W, b, act)
+            close(o, g["%s_%s_O" % (tag, act)]); close(z, g["%s_%s_Z" % (tag, act)])
+            dX, gW, gb = O.rnn_backward(z, o, E, W, act)
+            assert dX.shape == g["%s_%s_dX" % (tag, act)].shape
+            close(dX, g["%s_%s_dX" % (tag, act)]); close(gW, g["%s_%s_gW" % (tag, act)]); close(gb, g["%s_%s_gb" % (tag, act)])
+    for seq in (0, 1):
+        k = "layer_seq%d_" % seq
+        st = O.Stack((6, 5), [("rnn", 4, "tanh", bool(seq))])
+        st.L[0]["W"], st.L[0]["b"] = g[k + "W"].copy(), g[k + "b"].copy()
+        close(st.feedforward(g[k + "X"]), g[k + "Y"])
+        close(st.backpropagate(g[k + "D"]), g[k + "dX"])
+        close(st.L[0]["gW"], g[k + "gW"]); close(st.L[0]["gb"], g[k + "gb"])
+
+
 def test_costs_bxent_hinge():
     """The remaining costs of the registry (metrics/costs.py:46-69) against values from the reference
     (tests/golden/make_golden_costs.py)."""
