@@ -473,6 +473,42 @@ class RecurrentOp:
         return _ret(Z, dX, nablaW, nablab)
 
 
+# --------------------------------------------------------------------------- GRU
+class GRUOp:
+    """The time loops of the reference's GRU layer (layers/recurrent.py:123-190; it has no atomic op of its own).
+    X is time-major (T,B,D), W (D+H,3H) with columns [U|R|O]."""
+
+    def __init__(self, activation):
+        self.activation = activation
+        self.actfn = activations[activation]()
+
+    def forward(self, X, W, b):
+        x, w, bd = as_device(X), as_device(W), as_device(b)
+        T, B, D = x.shape
+        H = w.shape[-1] // 3
+        if w.shape[0] != D + H:
+            raise ValueError("GRU weight shape %s does not match D+H=%d" % (w.shape, D + H))
+        hs = DeviceArray.empty(T, B, H)
+        Z = DeviceArray.empty(T, B, D + H)
+        Zk = DeviceArray.empty(T, B, D + H)
+        gates = DeviceArray.empty(3, T, B, H)
+        call(L.bf_gru_forward, x.ptr, w.ptr, bd.ptr, hs.ptr, Z.ptr, Zk.ptr, gates.ptr, T, B, D, H,
+             _lib.ACT[self.activation], precision(), stream_ptr())
+        return _ret(X, hs, Z, Zk, gates)
+
+    def backward(self, Z, Zk, gates, E, W, nablaW=None, nablab=None):
+        z, zk, g, e, w = as_device(Z), as_device(Zk), as_device(gates), as_device(E), as_device(W)
+        T, B, ZD = z.shape
+        H = w.shape[-1] // 3
+        D = ZD - H
+        dX = DeviceArray.empty(T, B, D)
+        nablaW = DeviceArray.empty(ZD, 3 * H) if nablaW is None else nablaW
+        nablab = DeviceArray.empty(3 * H) if nablab is None else nablab
+        call(L.bf_gru_backward, z.ptr, zk.ptr, g.ptr, e.ptr, w.ptr, dX.ptr, nablaW.ptr, nablab.ptr, T, B, D, H,
+             _lib.ACT[self.activation], precision(), stream_ptr())
+        return _ret(Z, dX, nablaW, nablab)
+
+
 # --------------------------------------------------------------------------- LSTM
 class LSTMOp:
     """atomic/recurrent_op.py:46-112.  X is time-major (T,B,D); gate order along 4H is [cand|f|i|o]."""

@@ -121,7 +121,9 @@ inline bool gemm_tma_ok(const float* A, const float* B, int M, int N, int K) {
 
 // C = A (M x K, lda = K) @ B^T (B: N x K, ldb = K), through `ep.store`
 template <class EP>
-int launch_gemm_tma(const float* A, const float* B, int M, int N, int K, EP ep, cudaStream_t s) {
+int launch_gemm_tma(const float* A, const float* B, int M, int N, int K, EP ep, cudaStream_t s, long lda = 0, long ldb = 0) {
+  if (lda == 0) lda = K;      // row strides in floats (multiples of 4: the tensor map wants 16-byte strides)
+  if (ldb == 0) ldb = K;
   GtParams p;
   p.M = M; p.N = N; p.K = K; p.nkb = (K + 31) / 32; p.m_tiles = (M + 127) / 128;
   // narrower tiles when 128-wide ones would leave most SMs idle
@@ -131,13 +133,13 @@ int launch_gemm_tma(const float* A, const float* B, int M, int N, int K, EP ep, 
   CUtensorMap mA, mB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-    uint64_t str[1] = {(uint64_t)K};
+    uint64_t str[1] = {(uint64_t)lda};
     uint32_t box[2] = {32, 128};
     if (!tma_make_map(&mA, A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return fail(BF_ERR_CUDA, "gemm_tma: cuTensorMapEncodeTiled failed (A)");
   }
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
-    uint64_t str[1] = {(uint64_t)K};
+    uint64_t str[1] = {(uint64_t)ldb};
     uint32_t box[2] = {32, (uint32_t)bn};
     if (!tma_make_map(&mB, B, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return fail(BF_ERR_CUDA, "gemm_tma: cuTensorMapEncodeTiled failed (B)");
   }

@@ -505,6 +505,76 @@ __global__ void rnn_scale_kernel(const float* __restrict__ E, const float* __res
   for (; i < n; i += stride) out[i] = E[i] * act_bwd_rt(act, O[i]);
 }
 
+// ---- GRU (layers/recurrent.py:116-190; the reference keeps it at layer level, no atomic op).  W (D+H, 3H), columns [U|R|O].
+// gate GEMM epilogue: U, R = sigmoid(Z @ Wur + bur);  Zk[:, D:] = R * h_prev   (recurrent.py:137-140)
+struct EpiGruUR {
+  float *U, *R, *Zk; const float* Z; const float* b; int D, H;
+  __device__ void store(int m, int n, float v, int) const {
+    const float a = sigmoidf_(v + __ldg(b + n));
+    if (n < H) {
+      U[(long)m * H + n] = a;
+    } else {
+      const int j = n - H;
+      R[(long)m * H + j] = a;
+      Zk[(long)m * (D + H) + D + j] = a * __ldg(Z + (long)m * (D + H) + D + j);
+    }
+  }
+};
+// candidate GEMM epilogue: O = act(Zk @ Wo + bo);  h = U h_prev + (1 - U) O   (recurrent.py:141-142)
+struct EpiGruO {
+  float *O, *hs, *Znext; const float *U, *Z, *b; int D, H, act;
+  __device__ void store(int m, int n, float v, int) const {
+    const long i = (long)m * H + n;
+    const float o = act_fwd_rt(act, v + __ldg(b + n));
+    const float u = __ldg(U + i), hp = __ldg(Z + (long)m * (D + H) + D + n);
+    const float h = u * hp + (1.f - u) * o;
+    O[i] = o; hs[i] = h;
+    if (Znext) Znext[(long)m * (D + H) + D + n] = h;
+  }
+};
+// dh += delta[t];  dU = (h_prev - O) U(1-U) dh;  dO = (1-U) act'(O) dh   (recurrent.py:170-172)
+__global__ void gru_bwd_pre_kernel(const float* __restrict__ delta, float* __restrict__ dh, const float* __restrict__ Z,
+                                   const float* __restrict__ U, const float* __restrict__ O, float* __restrict__ dUR,
+                                   float* __restrict__ dO, int B, int D, int H, int act) {
+  long total = (long)B * H;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long m = i / H;
+    const int j = (int)(i - m * H);
+    const float d = dh[i] + delta[i], u = U[i], o = O[i], hp = Z[m * (D + H) + D + j];
+    dUR[m * 2 * H + j] = (hp - o) * (u * (1.f - u)) * d;
+    dO[i] = (1.f - u) * act_bwd_rt(act, o) * d;
+    dh[i] = d;
+  }
+}
+// dZk = dO @ Wo^T:  columns < D start dX[t];  dK = columns >= D:  dR = h_prev R(1-R) dK,  keep R dK   (recurrent.py:173-175,181)
+struct EpiGruDzk {
+  float *dX, *dUR, *RdK; const float *Z, *R; int D, H;
+  __device__ void store(int m, int n, float v, int) const {
+    if (n < D) {
+      dX[(long)m * D + n] = v;
+    } else {
+      const int j = n - D;
+      const long i = (long)m * H + j;
+      const float r = __ldg(R + i), hp = __ldg(Z + (long)m * (D + H) + n);
+      dUR[(long)m * 2 * H + H + j] = hp * (r * (1.f - r)) * v;
+      RdK[i] = r * v;
+    }
+  }
+};
+// dZ = [dU, dR] @ Wur^T:  dX[t] += columns < D;  dh = dZ[:, D:] + R dK + U dh   (recurrent.py:176,181-182)
+struct EpiGruDz {
+  float *dX, *dh; const float *RdK, *U; int D, H;
+  __device__ void store(int m, int n, float v, int) const {
+    if (n < D) {
+      dX[(long)m * D + n] += v;
+    } else {
+      const long i = (long)m * H + (n - D);
+      dh[i] = v + __ldg(RdK + i) + __ldg(U + i) * dh[i];
+    }
+  }
+};
+
 }  // namespace bf
 
 using namespace bf;
@@ -563,12 +633,19 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
       // persistent form: every tile resident at once (one CTA per SM), W slice + A ring within shared memory
       const int nkb = (K + 31) / 32, m_tiles = (B + 127) / 128, n_tiles = (H + LF_UNITS - 1) / LF_UNITS;
       const size_t smem = 1024 + (size_t)nkb * LF_B_BYTES + (size_t)LS_RING * LF_A_BYTES;
-      if (m_tiles * n_tiles <= num_sms() && smem <= 220 * 1024 && getenv("BF_LSTM_STEPWISE") == nullptr) {
+      bool fits = m_tiles * n_tiles <= num_sms() && smem <= 220 * 1024 && getenv("BF_LSTM_STEPWISE") == nullptr;
+      if (fits) {
+        // the flag protocol needs every CTA resident: ask the runtime instead of assuming one CTA per SM is available
+        BF_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_seq_fwd_kernel, LF_THREADS, smem));
+        fits = (long)per_sm * num_sms() >= (long)m_tiles * n_tiles;
+      }
+      if (fits) {
         LstmSeqParams q;
         q.T = T; q.B = B; q.D = D; q.H = H; q.nkb = nkb; q.kb_dep = D / 32; q.m_tiles = m_tiles; q.n_tiles = n_tiles;
         q.act = act; q.TBH = TB * H; q.bias = b; q.cache = cache; q.O = O; q.Z = Z; q.bw = bw; q.flags = flags;
         BF_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, s));
-        BF_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         void* args[] = {(void*)&mZ, (void*)&mW, (void*)&q};
         BF_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_fwd_kernel, dim3(m_tiles * n_tiles), dim3(LF_THREADS), args, smem, s));
         count_launch();
@@ -786,6 +863,147 @@ int bf_rnn_backward(const float* Z, const float* O, const float* E, const float*
     rc = launch_splitk_reduce(partial, nablaW, nablab, rows, H, ZD, splits, 0, H, 1, s);
   }
   return rc;
+}
+
+// GRU layer forward, layers/recurrent.py:123-153.  X (T,B,D) time-major, W (D+H,3H) columns [U|R|O], b (3H).
+// Outputs: hs (T,B,H) hidden states, Z and Zk (T,B,D+H) the two concatenated operands, gates (3,T,B,H) = U, R, O.
+int bf_gru_forward(const float* X, const float* W, const float* b, float* hs, float* Z, float* Zk, float* gates, int T,
+                   int B, int D, int H, int act, int precision, void* stream) {
+  BF_REQUIRE(X && W && b && hs && Z && Zk && gates, BF_ERR_ARG, "bf_gru_forward: null pointer");
+  BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_gru_forward: bad shape");
+  BF_REQUIRE(act == BF_ACT_TANH || act == BF_ACT_RELU || act == BF_ACT_SIGMOID || act == BF_ACT_LINEAR, BF_ERR_ARG,
+             "bf_gru_forward: bad activation %d", act);
+  if (T == 0 || B == 0) return BF_OK;
+  cudaStream_t s = as_stream(stream);
+  const long TB = (long)T * B, BH = (long)B * H;
+  const int ZD = D + H;
+  void* ws = nullptr;
+  int rc = workspace_require((size_t)ZD * 3 * H * sizeof(float), &ws);
+  if (rc) return rc;
+  float* Wt = (float*)ws;      // W^T (3H x ZD): rows [0,2H) = Wur^T, rows [2H,3H) = Wo^T
+  const bool tma = precision == BF_PREC_TF32 && gemm_tma_ok(Z, Wt, B, H, ZD) && gemm_tma_ok(Zk, Wt + (long)2 * H * ZD, B, H, ZD) &&
+                   getenv("BF_LSTM_GATHER") == nullptr;
+  if (tma) {
+    lstm_transpose_kernel<<<dim3((3 * H + 31) / 32, (ZD + 31) / 32), dim3(32, 8), 0, s>>>(W, Wt, ZD, 3 * H);
+    BF_LAUNCH_CHECK();
+  }
+  lstm_fill_z_kernel<<<ew_grid(TB * D + BH, 256), 256, 0, s>>>(X, Z, TB, B, D, H);
+  BF_LAUNCH_CHECK();
+  lstm_fill_z_kernel<<<ew_grid(TB * D + BH, 256), 256, 0, s>>>(X, Zk, TB, B, D, H);
+  BF_LAUNCH_CHECK();
+  float *U = gates, *R = gates + TB * H, *O = gates + 2 * TB * H;
+  for (int t = 0; t < T; ++t) {
+    const long zo = (long)t * B * ZD, ho = (long)t * BH;
+    EpiGruUR e1{U + ho, R + ho, Zk + zo, Z + zo, b, D, H};
+    EpiGruO e2{O + ho, hs + ho, t + 1 < T ? Z + zo + (long)B * ZD : nullptr, U + ho, Z + zo, b + 2 * H, D, H, act};
+    if (tma) {
+      rc = launch_gemm_tma(Z + zo, Wt, B, 2 * H, ZD, e1, s);
+      if (rc) return rc;
+      rc = launch_gemm_tma(Zk + zo, Wt + (long)2 * H * ZD, B, H, ZD, e2, s);
+    } else {
+      const int kp = (ZD + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+      LoadKContig a1{Z + zo, (long)ZD};
+      LoadMNContig b1{W, (long)3 * H};
+      rc = launch_gemm(precision, a1, b1, e1, B, 2 * H, ZD, 1, kp, 0, s);
+      if (rc) return rc;
+      LoadKContig a2{Zk + zo, (long)ZD};
+      LoadMNContig b2{W + 2 * H, (long)3 * H};
+      rc = launch_gemm(precision, a2, b2, e2, B, H, ZD, 1, kp, 0, s);
+    }
+    if (rc) return rc;
+  }
+  return BF_OK;
+}
+
+// GRU layer backward, layers/recurrent.py:155-190.  delta (T,B,H) -> dX (T,B,D), nablaW (D+H,3H), nablab (3H) (the
+// reference zeroes and then accumulates them over time, i.e. assigns).
+int bf_gru_backward(const float* Z, const float* Zk, const float* gates, const float* delta, const float* W, float* dX,
+                    float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream) {
+  BF_REQUIRE(Z && Zk && gates && delta && W && dX && nablaW && nablab, BF_ERR_ARG, "bf_gru_backward: null pointer");
+  BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_gru_backward: bad shape");
+  cudaStream_t s = as_stream(stream);
+  const long TB = (long)T * B, BH = (long)B * H;
+  const int ZD = D + H, H2 = 2 * H, H3 = 3 * H;
+  if (T == 0 || B == 0) {
+    BF_CUDA(cudaMemsetAsync(nablaW, 0, (size_t)ZD * H3 * sizeof(float), s));
+    BF_CUDA(cudaMemsetAsync(nablab, 0, (size_t)H3 * sizeof(float), s));
+    return BF_OK;
+  }
+  BF_REQUIRE(TB < 2147483647L, BF_ERR_ARG, "bf_gru_backward: T*B too large");
+  const int rows = ZD + 1;
+  int bm = rows <= 32 ? 32 : (rows <= 64 ? 64 : 128), bn = H2 <= 16 ? 16 : (H2 <= 32 ? 32 : (H2 <= 64 ? 64 : 128));
+  int tiles = ((rows + bm - 1) / bm) * ((H2 + bn - 1) / bn);
+  int kps = 0;
+  int splits = choose_splits(tiles, (int)TB, &kps);      // sized for the wider (2H) product, reused for the H-wide one
+  const bool tf = precision == BF_PREC_TF32 && getenv("BF_LSTM_GATHER") == nullptr;
+  const bool use_mn = tf && gemm_tma_mn_ok(Z, nullptr, ZD, H, TB) && (H & 3) == 0;
+  int mn_splits = num_sms() / ((ZD + 127) / 128);
+  if (mn_splits < 1) mn_splits = 1;
+  size_t off_dh = 0;
+  size_t off_rdk = align_up(off_dh + (size_t)BH * sizeof(float));
+  size_t off_dur = align_up(off_rdk + (size_t)BH * sizeof(float));
+  size_t off_do = align_up(off_dur + (size_t)TB * H2 * sizeof(float));
+  size_t off_pw = align_up(off_do + (size_t)TB * H * sizeof(float));
+  const size_t partial_bytes = (size_t)(use_mn ? mn_splits : splits) * rows * H2 * sizeof(float);
+  void* ws = nullptr;
+  int rc = workspace_require(off_pw + partial_bytes, &ws);
+  if (rc) return rc;
+  char* base = (char*)ws;
+  float* dh = (float*)(base + off_dh);
+  float* RdK = (float*)(base + off_rdk);
+  float* dUR = (float*)(base + off_dur);
+  float* dO = (float*)(base + off_do);
+  float* partial = (float*)(base + off_pw);
+  const float *U = gates, *R = gates + TB * H, *O = gates + 2 * TB * H;
+  BF_CUDA(cudaMemsetAsync(dh, 0, (size_t)BH * sizeof(float), s));
+  const bool tma3 = tf && (H & 3) == 0 && gemm_tma_ok(dO, W + H2, B, ZD, H);        // B(n, k) = W[n * 3H + 2H + k]
+  const bool tma4 = tf && (H & 3) == 0 && gemm_tma_ok(dUR, W, B, ZD, H2);           // B(n, k) = W[n * 3H + k]
+  for (int t = T - 1; t >= 0; --t) {
+    const long zo = (long)t * B * ZD, ho = (long)t * BH;
+    float* dUR_t = dUR + (long)t * B * H2;
+    float* dO_t = dO + ho;
+    gru_bwd_pre_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(delta + ho, dh, Z + zo, U + ho, O + ho, dUR_t, dO_t, B, D, H, act);
+    BF_LAUNCH_CHECK();
+    EpiGruDzk e3{dX + (long)t * B * D, dUR_t, RdK, Z + zo, R + ho, D, H};
+    if (tma3) {
+      rc = launch_gemm_tma(dO_t, W + H2, B, ZD, H, e3, s, H, H3);
+    } else {
+      LoadKContig al{dO_t, (long)H};
+      LoadKContig bl{W + H2, (long)H3};
+      rc = launch_gemm(precision, al, bl, e3, B, ZD, H, 1, (H + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
+    if (rc) return rc;
+    EpiGruDz e4{dX + (long)t * B * D, dh, RdK, U + ho, D, H};
+    if (tma4) {
+      rc = launch_gemm_tma(dUR_t, W, B, ZD, H2, e4, s, H2, H3);
+    } else {
+      LoadKContig al{dUR_t, (long)H2};
+      LoadKContig bl{W, (long)H3};
+      rc = launch_gemm(precision, al, bl, e4, B, ZD, H2, 1, (H2 + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
+    if (rc) return rc;
+  }
+  // nabla_W[:, :2H] = sum_t Z[t]^T [dU, dR],  nabla_W[:, 2H:] = sum_t Zk[t]^T dO;  biases = column sums (recurrent.py:178-186)
+  for (int part = 0; part < 2; ++part) {
+    const float* A = part ? Zk : Z;
+    const float* Bm = part ? dO : dUR;
+    const int N = part ? H : H2;
+    float* outW = nablaW + (part ? H2 : 0);
+    float* outb = nablab + (part ? H2 : 0);
+    int used = splits;
+    if (use_mn) {
+      rc = launch_gemm_tma_mn(A, Bm, ZD, N, (int)TB, partial, partial_bytes, &used, s);
+    } else {
+      LoadMNContigOnes al{A, (long)ZD, ZD};
+      LoadMNContig bl{Bm, (long)N};
+      EpiPartial ep{partial, (long)rows * N, N};
+      rc = launch_gemm(precision, al, bl, ep, rows, N, (int)TB, splits, kps, 0, s);
+    }
+    if (rc) return rc;
+    rc = launch_splitk_reduce(partial, outW, outb, rows, N, ZD, used, 0, H3, 1, s);
+    if (rc) return rc;
+  }
+  return BF_OK;
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-"""layers/recurrent.py of the reference: RLayer and LSTM (GRU/Clockwork/Reservoir are out of scope)."""
+"""layers/recurrent.py of the reference: RLayer, LSTM and GRU (Clockwork/Reservoir are out of scope)."""
 import ctypes
 
 import numpy as np
@@ -46,6 +46,47 @@ class RLayer(FFBase):
             call(_lib.lib.bf_act_forward, _lib.ACT["linear"], delta.ptr, last.ptr, last.size, stream_ptr())
         dX, _, _ = self.op.backward(Z=self.Z, O=self.output, E=E, W=self.weights, nablaW=self.nabla_w,
                                     nablab=self.nabla_b)
+        return _transpose01(dX)
+
+    @property
+    def outshape(self):
+        return self.neurons,
+
+    def __str__(self):
+        return self.__class__.__name__ + "-{}-{}".format(self.neurons, str(self.activation)[:4])
+
+
+class GRU(FFBase):
+    """layers/recurrent.py:12-47,116-190.  Input (B,T,D); weights white(D+H, 3H) with columns [U|R|O], zero biases."""
+
+    def __init__(self, neurons, activation, return_seq=False, **kw):
+        super().__init__(neurons, activation, **kw)
+        self.time = 0
+        self.return_seq = return_seq
+        self.Zs = self.gates = None
+        self.op = atomic.GRUOp(activation if isinstance(activation, str) else str(activation))
+
+    def connect(self, brain):
+        self._init_params(white(brain.outshape[-1] + self.neurons, self.neurons * 3), np.zeros(self.neurons * 3))
+        super().connect(brain)
+
+    def _fwd(self, x):
+        self.inputs = _transpose01(x)
+        self.time = self.inputs.shape[0]
+        hs, Z, Zk, self.gates = self.op.forward(self.inputs, self.weights, self.biases)
+        self.Zs = (Z, Zk)
+        self.output = _transpose01(hs) if self.return_seq else hs[-1]      # recurrent.py:148-151
+        return self.output
+
+    def _bwd(self, delta):
+        if self.return_seq:
+            E = _transpose01(delta)
+        else:
+            E = DeviceArray.zeros(self.time, len(delta), self.neurons)
+            last = E[-1]
+            call(_lib.lib.bf_act_forward, _lib.ACT["linear"], delta.ptr, last.ptr, last.size, stream_ptr())
+        dX, _, _ = self.op.backward(Z=self.Zs[0], Zk=self.Zs[1], gates=self.gates, E=E, W=self.weights,
+                                    nablaW=self.nabla_w, nablab=self.nabla_b)
         return _transpose01(dX)
 
     @property

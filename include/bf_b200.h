@@ -230,6 +230,15 @@ BF_API int bf_rnn_forward(const float* X, const float* W, const float* b, float*
 BF_API int bf_rnn_backward(const float* Z, const float* O, const float* E, const float* W, float* Eout, float* nablaW,
                     float* nablab, int T, int B, int D, int H, int act, int precision, void* stream);
 
+/* ---- GRU layer: layers/recurrent.py:116-190 (implemented at layer level in the reference, no atomic op) ---- */
+/* feedforward: X (T,B,D) time-major, W (D+H,3H) columns [U|R|O], b (3H) -> hs (T,B,H) hidden states, Z / Zk (T,B,D+H)
+ * the operands [X[t], h] and [X[t], R*h] (self.Zs), gates (3,T,B,H) = U, R, O (self.gates). */
+BF_API int bf_gru_forward(const float* X, const float* W, const float* b, float* hs, float* Z, float* Zk, float* gates, int T,
+                   int B, int D, int H, int act, int precision, void* stream);
+/* backpropagate: delta (T,B,H) -> dX (T,B,D), nablaW (D+H,3H), nablab (3H). */
+BF_API int bf_gru_backward(const float* Z, const float* Zk, const float* gates, const float* delta, const float* W, float* dX,
+                    float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream);
+
 /* ---- optimizer step on the flat vectors: optimizers/*.py, learner/backpropagation.py:37-42 ---- */
 /* W <- optimize(W, g, m) in place.  s1 = velocity, s2 = memory (NULL where the rule has none).
  * hp: SGD{} MOMENTUM{mu} NESTEROV{mu} ADAGRAD{eps} RMSPROP{decay,eps} ADAM{decay_velocity,decay_memory,eps}.

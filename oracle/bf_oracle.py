@@ -219,6 +219,57 @@ def rnn_backward(Z, O, E, W, activation="tanh"):
 
 
 # --------------------------------------------------------------------------
+# GRU                                           layers/recurrent.py:116-190
+# --------------------------------------------------------------------------
+def gru_forward(X, W, b, activation="tanh"):
+    """layers/recurrent.py:123-153.  X (T,B,D) time-major; W (D+H,3H), columns [U|R|O].  Returns the hidden states
+    hs (T,B,H), the operands Z = [X[t], h] and Zk = [X[t], R*h] (T,B,D+H), gates (3,T,B,H) = U, R, O."""
+    H = W.shape[-1] // 3
+    T, B, D = X.shape
+    Wur, Wo = W[:, :-H], W[:, -H:]
+    bur, bo = b[:-H], b[-H:]
+    h = np.zeros((B, H))
+    hs, Zs, Zks, gates = [], [], [], []
+    for t in range(T):
+        Z = np.concatenate((X[t], h), axis=1)
+        U, R = np.split(act_forward("sigmoid", Z @ Wur + bur), 2, axis=1)
+        Zk = np.concatenate((X[t], R * h), axis=1)
+        O = act_forward(activation, Zk @ Wo + bo)
+        h = U * h + (1.0 - U) * O
+        hs.append(h); Zs.append(Z); Zks.append(Zk); gates.append((U, R, O))
+    g = np.array(gates).transpose(1, 0, 2, 3) if T else np.zeros((3, 0, B, H))
+    return np.array(hs), np.array(Zs), np.array(Zks), g
+
+
+def gru_backward(Z, Zk, gates, delta, W, activation="tanh"):
+    """layers/recurrent.py:155-190.  delta (T,B,H).  Returns dX (T,B,D), nablaW (D+H,3H), nablab (3H)."""
+    H = W.shape[-1] // 3
+    T, B, zdim = Z.shape
+    D = zdim - H
+    Wu, Wr, Wo = np.split(W, 3, axis=1)
+    Wur = np.concatenate((Wu, Wr), axis=1)
+    dh = np.zeros((B, H))
+    dX = np.zeros((T, B, D))
+    nW, nb = np.zeros_like(W), np.zeros(3 * H)
+    for t in range(T - 1, -1, -1):
+        U, R, O = gates[0][t], gates[1][t], gates[2][t]
+        prevout = Z[t][:, -H:]
+        dh = dh + delta[t]
+        dU = (prevout - O) * act_backward("sigmoid", U) * dh
+        dO = (1.0 - U) * act_backward(activation, O) * dh
+        dZk = dO @ Wo.T
+        dK = dZk[:, -H:]
+        dR = prevout * act_backward("sigmoid", R) * dK
+        dUR = np.concatenate((dU, dR), axis=1)
+        dZ = dUR @ Wur.T
+        nW += np.concatenate((Z[t].T @ dUR, Zk[t].T @ dO), axis=1)
+        nb += np.concatenate((dU, dR, dO), axis=1).sum(axis=0)
+        dh = dZ[:, -H:] + R * dK + U * dh
+        dX[t] = dZ[:, :-H] + dZk[:, :-H]
+    return dX, nW, nb
+
+
+# --------------------------------------------------------------------------
 # LSTM                                        atomic/recurrent_op.py:46-112
 # --------------------------------------------------------------------------
 def lstm_forward(X, W, b, activation="tanh"):
@@ -357,6 +408,7 @@ class Stack:
       ("dropout", dropchance)                   layers/fancy.py:60-90 (set `stack.learning = True` while training)
       ("lstm", neurons, activation, return_seq) layers/recurrent.py:12-47,80-113
       ("rnn", neurons, activation, return_seq)  layers/recurrent.py:12-47,50-77 (RLayer)
+      ("gru", neurons, activation, return_seq)  layers/recurrent.py:12-47,116-190
 
     Weights are drawn with ``white`` in stack order at construction, i.e. with
     the same RNG consumption as the reference's ``connect`` calls.
@@ -410,6 +462,12 @@ class Stack:
                 lay.update(act=s[2] if len(s) > 2 else "tanh", n=n,
                            return_seq=bool(s[3]) if len(s) > 3 else False,
                            W=white(zdim, 4 * n), b=np.zeros(4 * n) + 7.0)  # layers/recurrent.py:82,98
+                shape = (shape[0], n) if lay["return_seq"] else (n,)
+            elif kind == "gru":
+                n = int(s[1])
+                lay.update(act=s[2] if len(s) > 2 else "tanh", n=n,
+                           return_seq=bool(s[3]) if len(s) > 3 else False,
+                           W=white(shape[-1] + n, 3 * n), b=np.zeros(3 * n))     # layers/recurrent.py:118-121
                 shape = (shape[0], n) if lay["return_seq"] else (n,)
             elif kind == "rnn":
                 n = int(s[1])
@@ -485,6 +543,10 @@ class Stack:
                 O, l["Z"], l["cache"] = lstm_forward(l["inputs"], l["W"], l["b"], l["act"])
                 l["O"] = O
                 X = O.transpose(1, 0, 2) if l["return_seq"] else O[-1]
+            elif k == "gru":                       # layers/recurrent.py:123-153
+                l["inputs"] = X.transpose(1, 0, 2)
+                hs, l["Z"], l["Zk"], l["gates"] = gru_forward(l["inputs"], l["W"], l["b"], l["act"])
+                X = hs.transpose(1, 0, 2) if l["return_seq"] else hs[-1]
             elif k == "rnn":                       # layers/recurrent.py:26,66-69
                 l["inputs"] = X.transpose(1, 0, 2)
                 O, l["Z"] = rnn_forward(l["inputs"], l["W"], l["b"], l["act"])
@@ -525,6 +587,14 @@ class Stack:
                     E = np.zeros((l["inputs"].shape[0], len(error), l["n"]))
                     E[-1] = error
                 dX, l["gW"], l["gb"] = lstm_backward(l["Z"], l["O"], E, l["W"], l["cache"], l["act"])
+                error = dX.transpose(1, 0, 2)
+            elif k == "gru":                       # layers/recurrent.py:31-40,155-190
+                if l["return_seq"]:
+                    E = error.transpose(1, 0, 2)
+                else:
+                    E = np.zeros((l["inputs"].shape[0], len(error), l["n"]))
+                    E[-1] = error
+                dX, l["gW"], l["gb"] = gru_backward(l["Z"], l["Zk"], l["gates"], E, l["W"], l["act"])
                 error = dX.transpose(1, 0, 2)
             elif k == "rnn":                       # layers/recurrent.py:31-40,71-77 (ASSIGNS)
                 if l["return_seq"]:

@@ -13,7 +13,7 @@ import numpy as np  # noqa: E402
 
 np.asscalar = lambda a: a.item()  # noqa: E731  (util/typing.py:11 needs it)
 from brainforge.atomic import RecurrentOp  # noqa: E402
-from brainforge.layers import RLayer  # noqa: E402
+from brainforge.layers import RLayer, GRU  # noqa: E402
 from brainforge.util import testing  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -45,6 +45,21 @@ for seq in (False, True):
     k = "layer_seq%d_" % int(seq)
     out.update({k + "X": LX, k + "W": layer.weights.copy(), k + "b": layer.biases.copy(), k + "Y": y, k + "D": LD,
                 k + "dX": dx, k + "gW": layer.nabla_w.copy(), k + "gb": layer.nabla_b.copy()})
+# GRU (layers/recurrent.py:116-190): layer level only (the reference has no atomic op for it)
+for seq in (False, True):
+    for act in ("tanh", "relu"):
+        brain = testing.NoBrainer(outshape=(6, 5))
+        np.random.seed(47)
+        layer = GRU(4, act, return_seq=seq)
+        layer.connect(brain)
+        layer.biases = rs.randn(12) * 0.1
+        GX = rs.randn(8, 6, 5)
+        y = np.array(layer.feedforward(GX))
+        GD = rs.randn(*y.shape)
+        dx = np.array(layer.backpropagate(GD.copy()))
+        k = "gru_%s_seq%d_" % (act, int(seq))
+        out.update({k + "X": GX, k + "W": layer.weights.copy(), k + "b": layer.biases.copy(), k + "Y": y, k + "D": GD,
+                    k + "dX": dx, k + "gW": layer.nabla_w.copy(), k + "gb": layer.nabla_b.copy()})
 path = os.path.join(HERE, "rnn.npz")
 np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
 print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), len(out), "arrays")

@@ -28,6 +28,9 @@ def build_b200(input_shape, spec, cost, optimizer, seed=None, **kw):
             layers.append(GlobalAveragePooling())
         elif k == "lstm":
             layers.append(LSTM(s[1], activation=s[2], return_seq=s[3] if len(s) > 3 else False))
+        elif k == "gru":
+            from brainforge_b200.layers import GRU
+            layers.append(GRU(s[1], activation=s[2], return_seq=s[3] if len(s) > 3 else False))
         elif k == "rnn":
             from brainforge_b200.layers import RLayer
             layers.append(RLayer(s[1], activation=s[2], return_seq=s[3] if len(s) > 3 else False))

@@ -244,6 +244,48 @@ def test_rnn_network_trains_like_oracle(bf):
     close(net.layers.get_weights(), ora.get_weights(), 1e-4)
 
 
+def test_gru_against_reference(bf):
+    """GRU layer against arrays produced by the reference (tests/golden/make_golden_rnn.py)."""
+    from conftest import load_golden
+    from brainforge_b200.layers import GRU
+    g = load_golden("rnn")
+    for seq in (0, 1):
+        for act in ("tanh", "relu"):
+            k = "gru_%s_seq%d_" % (act, seq)
+            stack = bf.LayerStack((6, 5), [GRU(4, act, return_seq=bool(seq))])
+            layer = stack.layers[-1]
+            layer.set_weights([g[k + "W"], g[k + "b"]], fold=False)
+            close(layer.feedforward(g[k + "X"]), g[k + "Y"])
+            close(layer.backpropagate(g[k + "D"]), g[k + "dX"])
+            close(layer.nabla_w, g[k + "gW"]); close(layer.nabla_b, g[k + "gb"])
+
+
+@pytest.mark.parametrize("T,B,D,H,act", [(1, 1, 1, 1, "tanh"), (9, 33, 20, 17, "relu"), (12, 150, 64, 96, "tanh")])
+def test_gru_vs_oracle(bf, O, T, B, D, H, act):
+    rs = np.random.RandomState(T * 3 + H)
+    X, W, b = rs.randn(T, B, D), rs.randn(D + H, 3 * H) * np.sqrt(2.0 / (D + 4 * H)), rs.randn(3 * H) * 0.1
+    op = bf.atomic.GRUOp(act)
+    hs, Z, Zk, gates = op.forward(X, W, b)
+    rh, rZ, rZk, rg = O.gru_forward(X, W, b, act)
+    close(hs, rh); close(Z, rZ); close(Zk, rZk); close(gates, rg)
+    E = rs.randn(T, B, H)
+    dX, gW, gb = op.backward(Z=rZ, Zk=rZk, gates=rg, E=E, W=W)
+    rX, rW, rb = O.gru_backward(rZ, rZk, rg, E, W, act)
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
+def test_gru_network_trains_like_oracle(bf):
+    from helpers import build_b200, build_oracle, onehot
+    spec = [("gru", 12, "tanh", True), ("gru", 8, "relu", False), ("dense", 5, "softmax")]
+    net = build_b200((7, 10), spec, "cxent", "adam", seed=6)
+    ora = build_oracle((7, 10), spec, "cxent", "adam", seed=6)
+    rs = np.random.RandomState(4)
+    for _ in range(3):
+        X, Y = rs.randn(10, 7, 10), onehot(rs, 10, 5)
+        close(net.learn_batch(X, Y)["cost"], ora.learn_batch(X, Y)["cost"], 1e-4)
+    close(net.layers.get_weights(), ora.get_weights(), 1e-4)
+
+
 def test_empty_batch(bf):
     op = bf.atomic.DenseOp()
     assert op.forward(np.zeros((0, 5)), np.ones((5, 3)), np.zeros(3)).shape == (0, 3)

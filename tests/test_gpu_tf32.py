@@ -108,6 +108,21 @@ def test_rnn_tf32(bf, O, T, B, D, H):
     close(dX, rX); close(gW, rW); close(gb, rb)
 
 
+@pytest.mark.parametrize("T,B,D,H", [(6, 50, 12, 20), (10, 300, 64, 128)])
+def test_gru_tf32(bf, O, T, B, D, H):
+    rs = np.random.RandomState(T + H)
+    X, W, b = rs.randn(T, B, D), rs.randn(D + H, 3 * H) * np.sqrt(2.0 / (D + 4 * H)), rs.randn(3 * H) * 0.1
+    op = bf.atomic.GRUOp("tanh")
+    hs, Z, Zk, gates = op.forward(X, W, b)
+    assert used_tensor_cores(bf)
+    rh, rZ, rZk, rg = O.gru_forward(X, W, b, "tanh")
+    close(hs, rh); close(Z, rZ); close(Zk, rZk); close(gates, rg)
+    E = rs.randn(T, B, H)
+    dX, gW, gb = op.backward(Z=rZ, Zk=rZk, gates=rg, E=E, W=W)
+    rX, rW, rb = O.gru_backward(rZ, rZk, rg, E, W, "tanh")
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
 @pytest.mark.parametrize("cfg,batch", [("cfg1", 20), ("cfg2", 32), ("cfg3", 16), ("cfg4", 4)])
 def test_configs_tf32(bf, cfg, batch):
     ishape, spec, cost, optimizer = CFG[cfg]

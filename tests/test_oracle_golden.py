@@ -101,6 +101,19 @@ def test_rnn_against_reference():
         close(st.L[0]["gW"], g[k + "gW"]); close(st.L[0]["gb"], g[k + "gb"])
 
 
+def test_gru_against_reference():
+    """GRU layer (layers/recurrent.py:116-190) against arrays produced by the reference (make_golden_rnn.py)."""
+    g = load_golden("rnn")
+    for seq in (0, 1):
+        for act in ("tanh", "relu"):
+            k = "gru_%s_seq%d_" % (act, seq)
+            st = O.Stack((6, 5), [("gru", 4, act, bool(seq))])
+            st.L[0]["W"], st.L[0]["b"] = g[k + "W"].copy(), g[k + "b"].copy()
+            close(st.feedforward(g[k + "X"]), g[k + "Y"])
+            close(st.backpropagate(g[k + "D"]), g[k + "dX"])
+            close(st.L[0]["gW"], g[k + "gW"]); close(st.L[0]["gb"], g[k + "gb"])
+
+
 def test_costs_bxent_hinge():
     """The remaining costs of the registry (metrics/costs.py:46-69) against values from the reference
     (tests/golden/make_golden_costs.py)."""
