@@ -76,6 +76,8 @@ SIGNATURES = {
     "bf_lstm_backward": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
     "bf_rnn_forward": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "bf_rnn_backward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
+    "bf_clockwork_forward": (_i, [_vp] * 6 + [_i] * 6 + [_vp]),
+    "bf_clockwork_backward": (_i, [_vp] * 8 + [_i] * 6 + [_vp]),
     "bf_gru_forward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
     "bf_gru_backward": (_i, [_vp] * 8 + [_i] * 6 + [_vp]),
     "bf_opt_step": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _vp]),

@@ -473,6 +473,40 @@ class RecurrentOp:
         return _ret(Z, dX, nablaW, nablab)
 
 
+# --------------------------------------------------------------------------- Clockwork
+class ClockworkOp:
+    """The time loops of the reference's ClockworkLayer (layers/recurrent.py:239-277; no atomic op in the reference).
+    X is time-major (T,B,D), W (D+H,H), tick (H) the layer's tick_array."""
+
+    def __init__(self, activation):
+        self.activation = activation
+        self.actfn = activations[activation]()
+
+    def forward(self, X, W, b, tick):
+        x, w, bd, tk = as_device(X), as_device(W), as_device(b), as_device(tick)
+        T, B, D = x.shape
+        H = w.shape[-1]
+        if w.shape[0] != D + H:
+            raise ValueError("clockwork weight shape %s does not match D+H=%d" % (w.shape, D + H))
+        O = DeviceArray.empty(T, B, H)
+        Z = DeviceArray.empty(T, B, D + H)
+        call(L.bf_clockwork_forward, x.ptr, w.ptr, bd.ptr, tk.ptr, O.ptr, Z.ptr, T, B, D, H, _lib.ACT[self.activation],
+             precision(), stream_ptr())
+        return _ret(X, O, Z)
+
+    def backward(self, Z, O, E, W, tick, nablaW=None, nablab=None):
+        z, o, e, w, tk = as_device(Z), as_device(O), as_device(E), as_device(W), as_device(tick)
+        T, B, ZD = z.shape
+        H = w.shape[-1]
+        D = ZD - H
+        dX = DeviceArray.empty(T, B, D)
+        nablaW = DeviceArray.empty(ZD, H) if nablaW is None else nablaW
+        nablab = DeviceArray.empty(H) if nablab is None else nablab
+        call(L.bf_clockwork_backward, z.ptr, o.ptr, e.ptr, w.ptr, tk.ptr, dX.ptr, nablaW.ptr, nablab.ptr, T, B, D, H,
+             _lib.ACT[self.activation], precision(), stream_ptr())
+        return _ret(Z, dX, nablaW, nablab)
+
+
 # --------------------------------------------------------------------------- GRU
 class GRUOp:
     """The time loops of the reference's GRU layer (layers/recurrent.py:123-190; it has no atomic op of its own).

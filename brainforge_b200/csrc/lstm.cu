@@ -575,6 +575,38 @@ struct EpiGruDz {
   }
 };
 
+// ---- Clockwork layer (layers/recurrent.py:193-283): a plain recurrence whose output columns only update on their ticks.
+// gate(t, n) = (t % tick[n] == 0) for t = 1..T  (:242; a zero tick never fires, like NumPy's nan remainder)
+__device__ __forceinline__ bool cw_gate(const float* tick, int n, int t) { return fmodf((float)t, __ldg(tick + n)) == 0.f; }
+// output = act(Z @ (W * gate) + b * gate)   (:243-246): gated-off columns see a zero pre-activation
+struct EpiCwFwd {
+  float* O; float* Znext; const float *b, *tick; int D, H, act, t;
+  __device__ void store(int m, int n, float v, int) const {
+    const float a = act_fwd_rt(act, cw_gate(tick, n, t) ? v + __ldg(b + n) : 0.f);
+    O[(long)m * H + n] = a;
+    if (Znext) Znext[(long)m * (D + H) + D + n] = a;
+  }
+};
+// G[t] = (dh + delta[t]) * act'(O[t]) * gate_t  -- the quantity every use of dh in :266-273 reduces to
+__global__ void cw_first_kernel(const float* __restrict__ delta, const float* __restrict__ O, const float* __restrict__ tick,
+                                float* __restrict__ G, long n, int H, int act, int t) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) G[i] = cw_gate(tick, (int)(i % H), t) ? delta[i] * act_bwd_rt(act, O[i]) : 0.f;
+}
+// deltaZ = G[t] @ W^T:  columns < D are dX[t];  the rest is dh for step t-1, turned into G[t-1] on the spot   (:273-275)
+struct EpiCwBwd {
+  float* dX; const float *delta_prev, *O_prev, *tick; float* G_prev; int D, H, act, t_prev;
+  __device__ void store(int m, int n, float v, int) const {
+    if (n < D) {
+      dX[(long)m * D + n] = v;
+    } else if (G_prev) {
+      const int j = n - D;
+      const long i = (long)m * H + j;
+      G_prev[i] = cw_gate(tick, j, t_prev) ? (v + __ldg(delta_prev + i)) * act_bwd_rt(act, __ldg(O_prev + i)) : 0.f;
+    }
+  }
+};
+
 }  // namespace bf
 
 using namespace bf;
@@ -1004,6 +1036,104 @@ int bf_gru_backward(const float* Z, const float* Zk, const float* gates, const f
     if (rc) return rc;
   }
   return BF_OK;
+}
+
+// ClockworkLayer.feedforward, layers/recurrent.py:239-257.  X (T,B,D) time-major, W (D+H,H), b (H), tick (H) the layer's
+// tick_array -> O (T,B,H) (self.cache), Z (T,B,D+H) (self.Zs).
+int bf_clockwork_forward(const float* X, const float* W, const float* b, const float* tick, float* O, float* Z, int T,
+                         int B, int D, int H, int act, int precision, void* stream) {
+  BF_REQUIRE(X && W && b && tick && O && Z, BF_ERR_ARG, "bf_clockwork_forward: null pointer");
+  BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_clockwork_forward: bad shape");
+  BF_REQUIRE(act == BF_ACT_TANH || act == BF_ACT_RELU || act == BF_ACT_SIGMOID || act == BF_ACT_LINEAR, BF_ERR_ARG,
+             "bf_clockwork_forward: bad activation %d", act);
+  if (T == 0 || B == 0) return BF_OK;
+  cudaStream_t s = as_stream(stream);
+  const long TB = (long)T * B, BH = (long)B * H;
+  const int ZD = D + H;
+  void* ws = nullptr;
+  int rc = workspace_require((size_t)ZD * H * sizeof(float), &ws);
+  if (rc) return rc;
+  float* Wt = (float*)ws;
+  const bool tma = precision == BF_PREC_TF32 && gemm_tma_ok(Z, Wt, B, H, ZD) && getenv("BF_LSTM_GATHER") == nullptr;
+  if (tma) {
+    lstm_transpose_kernel<<<dim3((H + 31) / 32, (ZD + 31) / 32), dim3(32, 8), 0, s>>>(W, Wt, ZD, H);
+    BF_LAUNCH_CHECK();
+  }
+  lstm_fill_z_kernel<<<ew_grid(TB * D + BH, 256), 256, 0, s>>>(X, Z, TB, B, D, H);
+  BF_LAUNCH_CHECK();
+  for (int t = 0; t < T; ++t) {
+    EpiCwFwd ep{O + (long)t * BH, t + 1 < T ? Z + (long)(t + 1) * B * ZD : nullptr, b, tick, D, H, act, t + 1};
+    if (tma) {
+      rc = launch_gemm_tma(Z + (long)t * B * ZD, Wt, B, H, ZD, ep, s);
+    } else {
+      LoadKContig al{Z + (long)t * B * ZD, (long)ZD};
+      LoadMNContig bl{W, (long)H};
+      rc = launch_gemm(precision, al, bl, ep, B, H, ZD, 1, (ZD + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
+    if (rc) return rc;
+  }
+  return BF_OK;
+}
+
+// ClockworkLayer.backpropagate, layers/recurrent.py:259-277.  delta (T,B,H) -> dX (T,B,D), nablaW (D+H,H), nablab (H).
+int bf_clockwork_backward(const float* Z, const float* O, const float* delta, const float* W, const float* tick, float* dX,
+                          float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream) {
+  BF_REQUIRE(Z && O && delta && W && tick && dX && nablaW && nablab, BF_ERR_ARG, "bf_clockwork_backward: null pointer");
+  BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_clockwork_backward: bad shape");
+  cudaStream_t s = as_stream(stream);
+  const long TB = (long)T * B, BH = (long)B * H;
+  const int ZD = D + H;
+  if (T == 0 || B == 0) {
+    BF_CUDA(cudaMemsetAsync(nablaW, 0, (size_t)ZD * H * sizeof(float), s));
+    BF_CUDA(cudaMemsetAsync(nablab, 0, (size_t)H * sizeof(float), s));
+    return BF_OK;
+  }
+  BF_REQUIRE(TB < 2147483647L, BF_ERR_ARG, "bf_clockwork_backward: T*B too large");
+  const int rows = ZD + 1;
+  int bm = rows <= 32 ? 32 : (rows <= 64 ? 64 : 128), bn = H <= 16 ? 16 : (H <= 32 ? 32 : (H <= 64 ? 64 : 128));
+  int tiles = ((rows + bm - 1) / bm) * ((H + bn - 1) / bn);
+  int kps = 0;
+  int splits = choose_splits(tiles, (int)TB, &kps);
+  const bool tf = precision == BF_PREC_TF32 && getenv("BF_LSTM_GATHER") == nullptr;
+  const bool use_mn = tf && gemm_tma_mn_ok(Z, nullptr, ZD, H, TB);
+  int mn_splits = num_sms() / (((ZD + 127) / 128) * ((H + 127) / 128));
+  if (mn_splits < 1) mn_splits = 1;
+  const size_t g_bytes = align_up((size_t)TB * H * sizeof(float));
+  const size_t partial_bytes = (size_t)(use_mn ? mn_splits : splits) * rows * H * sizeof(float);
+  void* ws = nullptr;
+  int rc = workspace_require(g_bytes + partial_bytes, &ws);
+  if (rc) return rc;
+  float* G = (float*)ws;
+  float* partial = (float*)((char*)ws + g_bytes);
+  cw_first_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(delta + (T - 1) * BH, O + (T - 1) * BH, tick, G + (T - 1) * BH, BH, H, act, T);
+  BF_LAUNCH_CHECK();
+  for (int t = T - 1; t >= 0; --t) {
+    const float* Gt = G + (long)t * BH;
+    EpiCwBwd ep{dX + (long)t * B * D, t ? delta + (long)(t - 1) * BH : nullptr, t ? O + (long)(t - 1) * BH : nullptr, tick,
+                t ? G + (long)(t - 1) * BH : nullptr, D, H, act, t};
+    if (tf && gemm_tma_ok(Gt, W, B, ZD, H)) {
+      rc = launch_gemm_tma(Gt, W, B, ZD, H, ep, s);          // B(n, k) = W[n * H + k]: K-major as stored
+    } else {
+      LoadKContig al{Gt, (long)H};
+      LoadKContig bl{W, (long)H};
+      rc = launch_gemm(precision, al, bl, ep, B, ZD, H, 1, (H + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+    }
+    if (rc) return rc;
+  }
+  if (use_mn) {
+    int used = 1;
+    rc = launch_gemm_tma_mn(Z, G, ZD, H, (int)TB, partial, partial_bytes, &used, s);
+    if (rc) return rc;
+    rc = launch_splitk_reduce(partial, nablaW, nablab, rows, H, ZD, used, 0, H, 1, s);
+  } else {
+    LoadMNContigOnes al{Z, (long)ZD, ZD};
+    LoadMNContig bl{G, (long)H};
+    EpiPartial ep{partial, (long)rows * H, H};
+    rc = launch_gemm(precision, al, bl, ep, rows, H, (int)TB, splits, kps, 0, s);
+    if (rc) return rc;
+    rc = launch_splitk_reduce(partial, nablaW, nablab, rows, H, ZD, splits, 0, H, 1, s);
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-"""layers/recurrent.py of the reference: RLayer, LSTM and GRU (Clockwork/Reservoir are out of scope)."""
+"""layers/recurrent.py of the reference: RLayer, LSTM, GRU and ClockworkLayer (Reservoir is out of scope)."""
 import ctypes
 
 import numpy as np
@@ -86,6 +86,79 @@ class GRU(FFBase):
             last = E[-1]
             call(_lib.lib.bf_act_forward, _lib.ACT["linear"], delta.ptr, last.ptr, last.size, stream_ptr())
         dX, _, _ = self.op.backward(Z=self.Zs[0], Zk=self.Zs[1], gates=self.gates, E=E, W=self.weights,
+                                    nablaW=self.nabla_w, nablab=self.nabla_b)
+        return _transpose01(dX)
+
+    @property
+    def outshape(self):
+        return self.neurons,
+
+    def __str__(self):
+        return self.__class__.__name__ + "-{}-{}".format(self.neurons, str(self.activation)[:4])
+
+
+def clockwork_init(indim, neurons, blocksizes, ticks):
+    """layers/recurrent.py:224-237, with its RNG consumption (U first, then one draw per block) and its block offsets
+    `start = i * bls` kept literally.  Returns (weights (H+D, H), tick_array (H))."""
+    W = np.zeros((neurons, neurons))
+    U = white(indim, neurons)
+    tick_array = np.zeros(neurons)
+    for i, bls in enumerate(blocksizes):
+        start = i * bls
+        end = start + bls
+        W[start:end, start:] = white(*W[start:end, start:].shape)
+        tick_array[start:end] = ticks[i]
+    return np.concatenate((W, U), axis=0), tick_array
+
+
+class ClockworkLayer(FFBase):
+    """layers/recurrent.py:193-283.  Input (B,T,D); the recurrent block W is block upper-triangular, block i updates
+    every ticktimes[i] steps."""
+
+    def __init__(self, neurons, activation, blocksizes=None, ticktimes=None, return_seq=False, **kw):
+        super().__init__(neurons, activation, **kw)
+        self.time = 0
+        self.return_seq = return_seq
+        if blocksizes is None:                                  # recurrent.py:198-201
+            block = neurons // 5
+            blocksizes = [block] * 5
+            blocksizes[0] += (neurons % block)
+        elif sum(blocksizes) != self.neurons:
+            raise RuntimeError("Please specify blocksizes so that they sum up to the number of neurons specified for "
+                               "this layer! ({})".format(neurons))
+        self.blocksizes = blocksizes
+        if ticktimes is None:
+            ticktimes = [2 ** i for i in range(len(self.blocksizes))]
+        elif min(ticktimes) < 0 or len(ticktimes) != len(self.blocksizes):
+            raise RuntimeError("Please specify the <ticks> parameter so, that its length is equal to the number of "
+                               "blocks specified (defaults to 5); timesteps < 0 are invalid!")
+        self.ticks = np.array(ticktimes)
+        self.tick_array = None
+        self.Z = 0
+        self.op = atomic.ClockworkOp(activation if isinstance(activation, str) else str(activation))
+
+    def connect(self, brain):
+        self.Z = brain.outshape[-1] + self.neurons
+        weights, ticks = clockwork_init(brain.outshape[-1], self.neurons, self.blocksizes, self.ticks)
+        self._init_params(weights, np.zeros(self.neurons))
+        self.tick_array = DeviceArray.from_host(ticks)
+        super().connect(brain)
+
+    def _fwd(self, x):
+        self.inputs = _transpose01(x)
+        self.time = self.inputs.shape[0]
+        self.cache, self.Zs = self.op.forward(self.inputs, self.weights, self.biases, self.tick_array)
+        self.output = _transpose01(self.cache) if self.return_seq else self.cache[-1]      # recurrent.py:252-255
+        return self.output
+
+    def _bwd(self, delta):
+        if self.return_seq:
+            E = _transpose01(delta)
+        else:
+            E = DeviceArray.zeros(self.time, len(delta), self.neurons)
+            last = E[-1]
+            call(_lib.lib.bf_act_forward, _lib.ACT["linear"], delta.ptr, last.ptr, last.size, stream_ptr())
+        dX, _, _ = self.op.backward(Z=self.Zs, O=self.cache, E=E, W=self.weights, tick=self.tick_array,
                                     nablaW=self.nabla_w, nablab=self.nabla_b)
         return _transpose01(dX)
 

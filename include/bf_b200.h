@@ -239,6 +239,16 @@ BF_API int bf_gru_forward(const float* X, const float* W, const float* b, float*
 BF_API int bf_gru_backward(const float* Z, const float* Zk, const float* gates, const float* delta, const float* W, float* dX,
                     float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream);
 
+/* ---- Clockwork layer: layers/recurrent.py:193-283 ---- */
+/* feedforward: X (T,B,D), W (D+H,H), b (H), tick (H) = the layer's tick_array -> O (T,B,H) = self.cache,
+ * Z (T,B,D+H) = self.Zs.  Column n updates at step t (1-based) iff t % tick[n] == 0, otherwise it sees a zero
+ * pre-activation (recurrent.py:242-246). */
+BF_API int bf_clockwork_forward(const float* X, const float* W, const float* b, const float* tick, float* O, float* Z, int T,
+                         int B, int D, int H, int act, int precision, void* stream);
+/* backpropagate: delta (T,B,H) -> dX (T,B,D), nablaW (D+H,H), nablab (H). */
+BF_API int bf_clockwork_backward(const float* Z, const float* O, const float* delta, const float* W, const float* tick, float* dX,
+                          float* nablaW, float* nablab, int T, int B, int D, int H, int act, int precision, void* stream);
+
 /* ---- optimizer step on the flat vectors: optimizers/*.py, learner/backpropagation.py:37-42 ---- */
 /* W <- optimize(W, g, m) in place.  s1 = velocity, s2 = memory (NULL where the rule has none).
  * hp: SGD{} MOMENTUM{mu} NESTEROV{mu} ADAGRAD{eps} RMSPROP{decay,eps} ADAM{decay_velocity,decay_memory,eps}.

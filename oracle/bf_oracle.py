@@ -219,6 +219,63 @@ def rnn_backward(Z, O, E, W, activation="tanh"):
 
 
 # --------------------------------------------------------------------------
+# Clockwork layer                               layers/recurrent.py:193-283
+# --------------------------------------------------------------------------
+def clockwork_init(indim, neurons, blocksizes=None, ticktimes=None):
+    """layers/recurrent.py:195-237: default blocks / ticks, then the weights with the reference's RNG consumption
+    (U first, one draw per block) and its `start = i * bls` offsets.  Returns (W (H+D,H), tick_array (H))."""
+    if blocksizes is None:
+        block = neurons // 5
+        blocksizes = [block] * 5
+        blocksizes[0] += (neurons % block)
+    if ticktimes is None:
+        ticktimes = [2 ** i for i in range(len(blocksizes))]
+    W = np.zeros((neurons, neurons))
+    U = white(indim, neurons)
+    tick_array = np.zeros(neurons)
+    for i, bls in enumerate(blocksizes):
+        start = i * bls
+        end = start + bls
+        W[start:end, start:] = white(*W[start:end, start:].shape)
+        tick_array[start:end] = ticktimes[i]
+    return np.concatenate((W, U), axis=0), tick_array
+
+
+def clockwork_forward(X, W, b, tick, activation="tanh"):
+    """layers/recurrent.py:239-250.  X (T,B,D) time-major.  Returns the outputs (T,B,H) and the operands Z (T,B,D+H)."""
+    T, B, D = X.shape
+    H = W.shape[-1]
+    out = np.zeros((B, H))
+    cache, Zs = [], []
+    for t in range(1, T + 1):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gate = np.equal(t % tick, 0.0)
+        Z = np.concatenate((X[t - 1], out), axis=-1)
+        out = act_forward(activation, Z.dot(W * gate[None, :]) + b * gate)
+        Zs.append(Z); cache.append(out)
+    return np.array(cache).reshape(T, B, H), np.array(Zs).reshape(T, B, D + H)
+
+
+def clockwork_backward(Z, O, delta, W, tick, activation="tanh"):
+    """layers/recurrent.py:259-277.  Returns dX (T,B,D), nablaW (D+H,H), nablab (H)."""
+    T, B, zdim = Z.shape
+    H = W.shape[-1]
+    dh = np.zeros((B, H))
+    dX = np.zeros((T, B, zdim - H))
+    nW, nb = np.zeros_like(W), np.zeros(H)
+    for t in range(T - 1, -1, -1):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gate = np.equal((t + 1) % tick, 0.0)
+        dh = (dh + delta[t]) * act_backward(activation, O[t])
+        nW += (Z[t].T @ dh) * gate[None, :]
+        nb += dh.sum(axis=0) * gate
+        deltaZ = dh @ (W * gate[None, :]).T
+        dX[t] = deltaZ[:, :-H]
+        dh = deltaZ[:, -H:]
+    return dX, nW, nb
+
+
+# --------------------------------------------------------------------------
 # GRU                                           layers/recurrent.py:116-190
 # --------------------------------------------------------------------------
 def gru_forward(X, W, b, activation="tanh"):
@@ -409,6 +466,7 @@ class Stack:
       ("lstm", neurons, activation, return_seq) layers/recurrent.py:12-47,80-113
       ("rnn", neurons, activation, return_seq)  layers/recurrent.py:12-47,50-77 (RLayer)
       ("gru", neurons, activation, return_seq)  layers/recurrent.py:12-47,116-190
+      ("clockwork", neurons, activation, return_seq[, blocksizes, ticktimes])  layers/recurrent.py:193-283
 
     Weights are drawn with ``white`` in stack order at construction, i.e. with
     the same RNG consumption as the reference's ``connect`` calls.
@@ -462,6 +520,12 @@ class Stack:
                 lay.update(act=s[2] if len(s) > 2 else "tanh", n=n,
                            return_seq=bool(s[3]) if len(s) > 3 else False,
                            W=white(zdim, 4 * n), b=np.zeros(4 * n) + 7.0)  # layers/recurrent.py:82,98
+                shape = (shape[0], n) if lay["return_seq"] else (n,)
+            elif kind == "clockwork":
+                n = int(s[1])
+                W, tick = clockwork_init(shape[-1], n, s[4] if len(s) > 4 else None, s[5] if len(s) > 5 else None)
+                lay.update(act=s[2] if len(s) > 2 else "tanh", n=n, return_seq=bool(s[3]) if len(s) > 3 else False,
+                           W=W, b=np.zeros(n), tick=tick)
                 shape = (shape[0], n) if lay["return_seq"] else (n,)
             elif kind == "gru":
                 n = int(s[1])
@@ -543,6 +607,10 @@ class Stack:
                 O, l["Z"], l["cache"] = lstm_forward(l["inputs"], l["W"], l["b"], l["act"])
                 l["O"] = O
                 X = O.transpose(1, 0, 2) if l["return_seq"] else O[-1]
+            elif k == "clockwork":                 # layers/recurrent.py:239-257
+                l["inputs"] = X.transpose(1, 0, 2)
+                l["O"], l["Z"] = clockwork_forward(l["inputs"], l["W"], l["b"], l["tick"], l["act"])
+                X = l["O"].transpose(1, 0, 2) if l["return_seq"] else l["O"][-1]
             elif k == "gru":                       # layers/recurrent.py:123-153
                 l["inputs"] = X.transpose(1, 0, 2)
                 hs, l["Z"], l["Zk"], l["gates"] = gru_forward(l["inputs"], l["W"], l["b"], l["act"])
@@ -587,6 +655,14 @@ class Stack:
                     E = np.zeros((l["inputs"].shape[0], len(error), l["n"]))
                     E[-1] = error
                 dX, l["gW"], l["gb"] = lstm_backward(l["Z"], l["O"], E, l["W"], l["cache"], l["act"])
+                error = dX.transpose(1, 0, 2)
+            elif k == "clockwork":                 # layers/recurrent.py:31-40,259-277
+                if l["return_seq"]:
+                    E = error.transpose(1, 0, 2)
+                else:
+                    E = np.zeros((l["inputs"].shape[0], len(error), l["n"]))
+                    E[-1] = error
+                dX, l["gW"], l["gb"] = clockwork_backward(l["Z"], l["O"], E, l["W"], l["tick"], l["act"])
                 error = dX.transpose(1, 0, 2)
             elif k == "gru":                       # layers/recurrent.py:31-40,155-190
                 if l["return_seq"]:

@@ -13,7 +13,7 @@ import numpy as np  # noqa: E402
 
 np.asscalar = lambda a: a.item()  # noqa: E731  (util/typing.py:11 needs it)
 from brainforge.atomic import RecurrentOp  # noqa: E402
-from brainforge.layers import RLayer, GRU  # noqa: E402
+from brainforge.layers import RLayer, GRU, ClockworkLayer  # noqa: E402
 from brainforge.util import testing  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -60,6 +60,24 @@ for seq in (False, True):
         k = "gru_%s_seq%d_" % (act, int(seq))
         out.update({k + "X": GX, k + "W": layer.weights.copy(), k + "b": layer.biases.copy(), k + "Y": y, k + "D": GD,
                     k + "dX": dx, k + "gW": layer.nabla_w.copy(), k + "gb": layer.nabla_b.copy()})
+# ClockworkLayer (layers/recurrent.py:193-283): default blocks (5 x 2, ticks 1,2,4,8,16) and a custom split
+import contextlib  # noqa: E402
+import io  # noqa: E402
+for tag, (neurons, kw) in {"def": (10, {}), "cus": (7, dict(blocksizes=[3, 2, 2], ticktimes=[1, 3, 2]))}.items():
+    for seq in (False, True):
+        brain = testing.NoBrainer(outshape=(9, 5))
+        np.random.seed(53)
+        with contextlib.redirect_stdout(io.StringIO()):
+            layer = ClockworkLayer(neurons, "tanh", return_seq=seq, **kw)
+            layer.connect(brain)
+        layer.biases = rs.randn(neurons) * 0.1
+        CX = rs.randn(6, 9, 5)
+        y = np.array(layer.feedforward(CX))
+        CD = rs.randn(*y.shape)
+        dx = np.array(layer.backpropagate(CD.copy()))
+        k = "cw_%s_seq%d_" % (tag, int(seq))
+        out.update({k + "X": CX, k + "W": layer.weights.copy(), k + "b": layer.biases.copy(), k + "tick": layer.tick_array.copy(),
+                    k + "Y": y, k + "D": CD, k + "dX": dx, k + "gW": layer.nabla_w.copy(), k + "gb": layer.nabla_b.copy()})
 path = os.path.join(HERE, "rnn.npz")
 np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
 print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), len(out), "arrays")

@@ -28,6 +28,10 @@ def build_b200(input_shape, spec, cost, optimizer, seed=None, **kw):
             layers.append(GlobalAveragePooling())
         elif k == "lstm":
             layers.append(LSTM(s[1], activation=s[2], return_seq=s[3] if len(s) > 3 else False))
+        elif k == "clockwork":
+            from brainforge_b200.layers import ClockworkLayer
+            layers.append(ClockworkLayer(s[1], s[2], blocksizes=s[4] if len(s) > 4 else None,
+                                         ticktimes=s[5] if len(s) > 5 else None, return_seq=s[3] if len(s) > 3 else False))
         elif k == "gru":
             from brainforge_b200.layers import GRU
             layers.append(GRU(s[1], activation=s[2], return_seq=s[3] if len(s) > 3 else False))

@@ -286,6 +286,53 @@ def test_gru_network_trains_like_oracle(bf):
     close(net.layers.get_weights(), ora.get_weights(), 1e-4)
 
 
+def test_clockwork_against_reference(bf):
+    """ClockworkLayer against arrays produced by the reference, initialiser included (same seed, same weights)."""
+    from conftest import load_golden
+    from brainforge_b200.layers import ClockworkLayer
+    g = load_golden("rnn")
+    for tag, (n, blocks, ticks) in {"def": (10, None, None), "cus": (7, [3, 2, 2], [1, 3, 2])}.items():
+        for seq in (0, 1):
+            k = "cw_%s_seq%d_" % (tag, seq)
+            np.random.seed(53)
+            stack = bf.LayerStack((9, 5), [ClockworkLayer(n, "tanh", blocksizes=blocks, ticktimes=ticks, return_seq=bool(seq))])
+            layer = stack.layers[-1]
+            close(layer.weights, g[k + "W"], 1e-7)
+            assert np.array_equal(layer.tick_array.numpy(), g[k + "tick"])
+            layer.set_weights([g[k + "W"], g[k + "b"]], fold=False)
+            close(layer.feedforward(g[k + "X"]), g[k + "Y"])
+            close(layer.backpropagate(g[k + "D"]), g[k + "dX"])
+            close(layer.nabla_w, g[k + "gW"]); close(layer.nabla_b, g[k + "gb"])
+
+
+@pytest.mark.parametrize("T,B,D,H,act", [(1, 1, 1, 5, "tanh"), (9, 33, 20, 17, "relu"), (12, 150, 64, 80, "tanh")])
+def test_clockwork_vs_oracle(bf, O, T, B, D, H, act):
+    rs = np.random.RandomState(T * 11 + H)
+    np.random.seed(T)
+    W, tick = O.clockwork_init(D, H)
+    X, b = rs.randn(T, B, D), rs.randn(H) * 0.1
+    op = bf.atomic.ClockworkOp(act)
+    O_, Z_ = op.forward(X, W, b, tick)
+    rO, rZ = O.clockwork_forward(X, W, b, tick, act)
+    close(O_, rO); close(Z_, rZ)
+    E = rs.randn(T, B, H)
+    dX, gW, gb = op.backward(Z=rZ, O=rO, E=E, W=W, tick=tick)
+    rX, rW, rb = O.clockwork_backward(rZ, rO, E, W, tick, act)
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
+def test_clockwork_network_trains_like_oracle(bf):
+    from helpers import build_b200, build_oracle, onehot
+    spec = [("clockwork", 10, "tanh", True), ("gru", 8, "tanh", False), ("dense", 5, "softmax")]
+    net = build_b200((7, 6), spec, "cxent", "adam", seed=8)
+    ora = build_oracle((7, 6), spec, "cxent", "adam", seed=8)
+    rs = np.random.RandomState(4)
+    for _ in range(3):
+        X, Y = rs.randn(10, 7, 6), onehot(rs, 10, 5)
+        close(net.learn_batch(X, Y)["cost"], ora.learn_batch(X, Y)["cost"], 1e-4)
+    close(net.layers.get_weights(), ora.get_weights(), 1e-4)
+
+
 def test_empty_batch(bf):
     op = bf.atomic.DenseOp()
     assert op.forward(np.zeros((0, 5)), np.ones((5, 3)), np.zeros(3)).shape == (0, 3)

@@ -123,6 +123,23 @@ def test_gru_tf32(bf, O, T, B, D, H):
     close(dX, rX); close(gW, rW); close(gb, rb)
 
 
+def test_clockwork_tf32(bf, O):
+    T, B, D, H = 10, 300, 64, 120
+    rs = np.random.RandomState(T + H)
+    np.random.seed(2)
+    W, tick = O.clockwork_init(D, H)
+    X, b = rs.randn(T, B, D), rs.randn(H) * 0.1
+    op = bf.atomic.ClockworkOp("tanh")
+    O_, Z_ = op.forward(X, W, b, tick)
+    assert used_tensor_cores(bf)
+    rO, rZ = O.clockwork_forward(X, W, b, tick, "tanh")
+    close(O_, rO); close(Z_, rZ)
+    E = rs.randn(T, B, H)
+    dX, gW, gb = op.backward(Z=rZ, O=rO, E=E, W=W, tick=tick)
+    rX, rW, rb = O.clockwork_backward(rZ, rO, E, W, tick, "tanh")
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
 @pytest.mark.parametrize("cfg,batch", [("cfg1", 20), ("cfg2", 32), ("cfg3", 16), ("cfg4", 4)])
 def test_configs_tf32(bf, cfg, batch):
     ishape, spec, cost, optimizer = CFG[cfg]

@@ -114,6 +114,25 @@ def test_gru_against_reference():
             close(st.L[0]["gW"], g[k + "gW"]); close(st.L[0]["gb"], g[k + "gb"])
 
 
+CW_CASES = {"def": (10, None, None), "cus": (7, [3, 2, 2], [1, 3, 2])}
+
+
+def test_clockwork_against_reference():
+    """ClockworkLayer (layers/recurrent.py:193-283) against arrays produced by the reference: the initialiser's RNG
+    consumption and block offsets (one neuron of the custom case never ticks), forward and backward."""
+    g = load_golden("rnn")
+    for tag, (n, blocks, ticks) in CW_CASES.items():
+        for seq in (0, 1):
+            k = "cw_%s_seq%d_" % (tag, seq)
+            np.random.seed(53)
+            st = O.Stack((9, 5), [("clockwork", n, "tanh", bool(seq), blocks, ticks)])
+            assert np.array_equal(st.L[0]["W"], g[k + "W"]) and np.array_equal(st.L[0]["tick"], g[k + "tick"])
+            st.L[0]["b"] = g[k + "b"].copy()
+            close(st.feedforward(g[k + "X"]), g[k + "Y"])
+            close(st.backpropagate(g[k + "D"]), g[k + "dX"])
+            close(st.L[0]["gW"], g[k + "gW"]); close(st.L[0]["gb"], g[k + "gb"])
+
+
 def test_costs_bxent_hinge():
     """The remaining costs of the registry (metrics/costs.py:46-69) against values from the reference
     (tests/golden/make_golden_costs.py)."""
