@@ -688,6 +688,13 @@ int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, floa
   int nsplit = num_sms() / nch;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > p.nstages) nsplit = p.nstages;
+  // small batches: every split costs a 160 KB partial that the reduction has to read back -- give a CTA at least four
+  // stages of work before adding another split
+  {
+    static const int min_stages = getenv("BF_DF_MIN_STAGES") ? atoi(getenv("BF_DF_MIN_STAGES")) : 4;
+    const int cap = (p.nstages + min_stages - 1) / min_stages;
+    if (nsplit > cap) nsplit = cap < 1 ? 1 : cap;
+  }
   p.nsplit = nsplit;
   const size_t part_bytes = al256((size_t)nsplit * nch * (ntaps + 1) * 128 * 32 * 4);
   void* ws = nullptr;

@@ -1,4 +1,6 @@
 // Dense layer contractions: atomic/core_op.py:9-20 (DenseOp.forward / backward).
+#include <stdlib.h>
+#include <stdint.h>
 #include "gemm_umma.cuh"
 
 namespace bf {
@@ -134,6 +136,69 @@ dense_skinny_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W
   }
 }
 
+// forward without staging: a warp owns DIRECT_ROWS rows, a lane four consecutive features of the PHYSICAL order (one
+// 128-bit load of X per row), W rows come straight from L1/L2 (n floats each, the whole matrix is a few tens of KB).
+// No per-CTA preamble: at small batch the staged kernel above spends its time copying W into shared memory once per CTA.
+constexpr int DIRECT_ROWS = 4;
+template <int NT>
+__global__ void __launch_bounds__(128)
+dense_skinny_fwd_direct_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
+                               float* __restrict__ out, int m, int k, int n, int act, int pc, int phw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m0 = (blockIdx.x * 4 + warp) * DIRECT_ROWS;
+  if (m0 >= m) return;
+  float acc[DIRECT_ROWS][NT];
+#pragma unroll
+  for (int r = 0; r < DIRECT_ROWS; ++r)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[r][j] = 0.f;
+  for (int kq = lane * 4; kq < k; kq += 128) {
+    float4 x[DIRECT_ROWS];
+#pragma unroll
+    for (int r = 0; r < DIRECT_ROWS; ++r)
+      x[r] = (m0 + r < m) ? __ldcs(reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * k + kq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // logical W row of physical feature kq: (c, yx) -> c * phw + yx; the four features of a quad share yx (pc % 4 == 0)
+    const int yx = pc ? kq / pc : 0;
+    const int kl0 = pc ? (kq - yx * pc) * phw + yx : kq;
+    const int kstep = pc ? phw : 1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2* wr = reinterpret_cast<const float2*>(W + (size_t)(kl0 + u * kstep) * n);   // n even: 8-byte aligned rows
+      float w[NT];
+#pragma unroll
+      for (int j = 0; j < NT; j += 2) {
+        const float2 t = (j < n) ? __ldg(wr + (j >> 1)) : make_float2(0.f, 0.f);
+        w[j] = t.x; w[j + 1] = t.y;
+      }
+#pragma unroll
+      for (int r = 0; r < DIRECT_ROWS; ++r) {
+        const float xv = u == 0 ? x[r].x : u == 1 ? x[r].y : u == 2 ? x[r].z : x[r].w;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[r][j] = fmaf(xv, w[j], acc[r][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < DIRECT_ROWS; ++r) {
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float t = warp_sum(acc[r][j]);
+      if (lane == j) mine = t;
+    }
+    const bool col = lane < n;
+    if (b && col) mine += __ldg(b + lane);
+    if (act == BF_ACT_SOFTMAX) {
+      const float mx = warp_max(col ? mine : -INFINITY);
+      const float e = col ? expf(mine - mx) : 0.f;
+      mine = e / warp_sum(e);
+    } else {
+      mine = act_fwd_rt(act, mine);
+    }
+    if (col && m0 + r < m) out[(size_t)(m0 + r) * n + lane] = mine;
+  }
+}
+
 // backward: CTA = (row chunk, 256-column slab of K), thread = one column kk.  Per row: dX[m][kk] = E[m,:] . W[kk,:]
 // and the running dW[kk,:] += X[m][kk] * E[m,:]; per-chunk partials (row k of a partial = db) go to the workspace and
 // are summed in chunk order by splitk_reduce_kernel (deterministic).
@@ -205,6 +270,18 @@ static inline bool skinny_ok(int m, int k, int n) {
 static int launch_skinny_fwd(const float* X, const float* W, const float* b, float* out, int m, int k, int n, int act,
                              int pc, int phw, cudaStream_t s) {
   const int nt = skinny_nt(n);
+  static const int direct_max = getenv("BF_DENSE_DIRECT_MAX") ? atoi(getenv("BF_DENSE_DIRECT_MAX")) : 2048;
+  if (m <= direct_max && (k & 3) == 0 && (n & 1) == 0 && n <= 16 && (pc == 0 || (pc & 3) == 0) && ((uintptr_t)X & 15) == 0 &&
+      ((uintptr_t)W & 7) == 0) {
+    const int dgrid = (m + 4 * DIRECT_ROWS - 1) / (4 * DIRECT_ROWS);
+    const int dnt = n <= 4 ? 4 : n <= 8 ? 8 : n <= 12 ? 12 : 16;
+#define BF_SKD(NT_) if (dnt == NT_) dense_skinny_fwd_direct_kernel<NT_><<<dgrid, 128, 0, s>>>(X, W, b, out, m, k, n, act, pc, phw);
+    BF_SKD(4) BF_SKD(8) BF_SKD(12) BF_SKD(16)
+#undef BF_SKD
+    BF_LAUNCH_CHECK();
+    set_last_path(0);
+    return BF_OK;
+  }
   const size_t smem = (size_t)k * (nt == 4 ? 4 : nt + 4) * 4;
   int grid = (m + 8 * SKINNY_ROWS - 1) / (8 * SKINNY_ROWS);
   if (grid > 4 * num_sms()) grid = 4 * num_sms();
