@@ -81,6 +81,7 @@ SIGNATURES = {
     "bf_gru_forward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
     "bf_gru_backward": (_i, [_vp] * 8 + [_i] * 6 + [_vp]),
     "bf_opt_step": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _vp]),
+    "bf_opt_step_allreduce": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _sz, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "bf_fitness_mlp": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
 }
 

@@ -251,6 +251,91 @@ __global__ void opt_kernel(float* __restrict__ W, float* __restrict__ G, float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Data-parallel step tail in ONE kernel: one-shot all-reduce of the flat gradient vector over peer memory (NVLink /
+// NVSwitch loads from every rank's symmetric buffer) fused with the optimizer update.
+//   every rank: barrier A -> g[i] = sum over ranks r = 0..world-1 of peer[r][i] (fixed order: all ranks compute the
+//   same bits) -> W, state updated for i < n_params -> barrier B (peers are done reading my buffer) -> my gradient
+//   slice is cleared (or set to the sum), the step scalars at the tail (cost sum, hits) are replaced by their sums.
+// Each CTA owns a contiguous slice and its own pair of flag slots in the signal pads, so there is no grid-wide sync:
+// slot (block * world + source rank) of rank d's pad is written only by CTA `block` of rank `source`.  Flag values are
+// a per-CTA epoch kept in device memory (2e-1 for barrier A, 2e for B), so the kernel replays unchanged in a CUDA graph.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {      // never served from this SM's L1
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_barrier(unsigned* const* pads, int rank, int world, unsigned value) {
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    __threadfence_system();
+    const int t = threadIdx.x;
+    st_release_sys(pads[t] + (size_t)blockIdx.x * world + rank, value);
+    const unsigned* mine = pads[rank] + (size_t)blockIdx.x * world + t;
+    while ((int)(ld_acquire_sys(mine) - value) < 0) {}
+  }
+  __syncthreads();
+}
+
+constexpr int AR_MAX_WORLD = 16;
+struct ArParams {
+  float* const* peers;        // device array [world] of every rank's gradient buffer (mine included)
+  unsigned* const* pads;      // device array [world] of signal pads
+  unsigned* epoch;            // [gridDim.x] local per-CTA epochs
+  float* gsum;                // local scratch [n_total]
+  int rank, world;
+  size_t n_params, n_total;   // multiples of 4
+};
+
+template <int KIND, bool HAS1, bool HAS2>
+__global__ void __launch_bounds__(256)
+opt_allreduce_kernel(float* __restrict__ W, float* __restrict__ G, float* __restrict__ S1, float* __restrict__ S2,
+                     ArParams p, OptHP h, int zero_grad) {
+  __shared__ unsigned s_epoch;
+  if (threadIdx.x == 0) s_epoch = ++p.epoch[blockIdx.x];
+  __syncthreads();
+  const unsigned e = s_epoch;
+  const size_t n4 = p.n_total >> 2, np4 = p.n_params >> 2;
+  const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
+  const size_t lo = per * blockIdx.x, hi = lo + per < n4 ? lo + per : n4;
+  peer_barrier(p.pads, p.rank, p.world, 2u * e - 1u);
+  float4* W4 = reinterpret_cast<float4*>(W);
+  float4* S14 = reinterpret_cast<float4*>(S1);
+  float4* S24 = reinterpret_cast<float4*>(S2);
+  float4* GS4 = reinterpret_cast<float4*>(p.gsum);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float4 g = zero4;
+    for (int r = 0; r < p.world; ++r) {
+      const float4 v = ld_peer4(p.peers[r] + 4 * i);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    if (i < np4) {
+      float4 w = W4[i];
+      float4 a = HAS1 ? S14[i] : zero4, b = HAS2 ? S24[i] : zero4;
+      opt_update<KIND>(w.x, g.x, a.x, b.x, h);
+      opt_update<KIND>(w.y, g.y, a.y, b.y, h);
+      opt_update<KIND>(w.z, g.z, a.z, b.z, h);
+      opt_update<KIND>(w.w, g.w, a.w, b.w, h);
+      W4[i] = w;
+      if (HAS1) S14[i] = a;
+      if (HAS2) S24[i] = b;
+    }
+    GS4[i] = g;
+  }
+  peer_barrier(p.pads, p.rank, p.world, 2u * e);
+  float4* G4 = reinterpret_cast<float4*>(G);
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) G4[i] = (zero_grad && i < np4) ? zero4 : GS4[i];
+}
+
 }  // namespace bf
 
 using namespace bf;
@@ -423,6 +508,53 @@ int bf_mul_rowmask(const float* x, const float* m, float* out, size_t rows, size
   if (rows * cols == 0) return BF_OK;
   BF_REQUIRE(x && out, BF_ERR_ARG, "bf_mul_rowmask: null pointer");
   mul_rowmask_kernel<<<ew_grid(rows * cols, 256), 256, 0, as_stream(stream)>>>(x, m, out, rows * cols, cols, scale);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+// Data-parallel optimizer step: all-reduce(sum) of the flat gradient vector over peer memory fused with bf_opt_step.
+// G is this rank's buffer inside a symmetric allocation; peers / pads are DEVICE arrays of `world` pointers (every
+// rank's buffer and signal pad, as torch's symmetric memory hands them out); epoch is a zero-initialised local array
+// of `blocks` counters, gsum a local scratch of n_total floats.  Elements [n_params, n_total) (the step scalars) are
+// summed but not optimised.  Every rank must make the same sequence of calls with the same `blocks`.
+int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float* s2, size_t n_params, size_t n_total, float eta,
+                          float m, float hp0, float hp1, float hp2, int zero_grad, void* const* peers, void* const* pads,
+                          unsigned* epoch, float* gsum, int rank, int world, int blocks, void* stream) {
+  BF_REQUIRE(W && G && peers && pads && epoch && gsum, BF_ERR_ARG, "bf_opt_step_allreduce: null pointer");
+  BF_REQUIRE(world >= 1 && world <= AR_MAX_WORLD && rank >= 0 && rank < world && blocks >= 1, BF_ERR_ARG,
+             "bf_opt_step_allreduce: bad rank/world/blocks %d/%d/%d", rank, world, blocks);
+  BF_REQUIRE((n_params & 3) == 0 && (n_total & 3) == 0 && n_params <= n_total && n_total > 0, BF_ERR_ARG,
+             "bf_opt_step_allreduce: sizes must be multiples of 4");
+  BF_REQUIRE(aligned16(W) && aligned16(G) && aligned16(gsum) && (!s1 || aligned16(s1)) && (!s2 || aligned16(s2)), BF_ERR_ARG,
+             "bf_opt_step_allreduce: buffers must be 16-byte aligned");
+  BF_REQUIRE(m > 0.f, BF_ERR_ARG, "bf_opt_step_allreduce: m must be positive");
+  cudaStream_t s = as_stream(stream);
+  OptHP h;
+  h.eta = eta; h.eta_m = eta / m; h.inv_m = 1.0f / m; h.hp0 = hp0; h.hp1 = hp1; h.hp2 = hp2;
+  ArParams p;
+  p.peers = reinterpret_cast<float* const*>(peers); p.pads = reinterpret_cast<unsigned* const*>(pads); p.epoch = epoch;
+  p.gsum = gsum; p.rank = rank; p.world = world; p.n_params = n_params; p.n_total = n_total;
+#define BF_AR(K_, H1_, H2_) opt_allreduce_kernel<K_, H1_, H2_><<<blocks, 256, 0, s>>>(W, G, s1, s2, p, h, zero_grad)
+  switch (kind) {
+    case BF_OPT_SGD: BF_AR(BF_OPT_SGD, false, false); break;
+    case BF_OPT_MOMENTUM:
+      BF_REQUIRE(s1, BF_ERR_ARG, "bf_opt_step_allreduce: momentum needs velocity (s1)");
+      BF_AR(BF_OPT_MOMENTUM, true, false); break;
+    case BF_OPT_NESTEROV:
+      BF_REQUIRE(s1 && s2, BF_ERR_ARG, "bf_opt_step_allreduce: nesterov needs velocity (s1) and memory (s2)");
+      BF_AR(BF_OPT_NESTEROV, true, true); break;
+    case BF_OPT_ADAGRAD:
+      BF_REQUIRE(s2, BF_ERR_ARG, "bf_opt_step_allreduce: adagrad needs memory (s2)");
+      BF_AR(BF_OPT_ADAGRAD, false, true); break;
+    case BF_OPT_RMSPROP:
+      BF_REQUIRE(s2, BF_ERR_ARG, "bf_opt_step_allreduce: rmsprop needs memory (s2)");
+      BF_AR(BF_OPT_RMSPROP, false, true); break;
+    case BF_OPT_ADAM:
+      BF_REQUIRE(s1 && s2, BF_ERR_ARG, "bf_opt_step_allreduce: adam needs velocity (s1) and memory (s2)");
+      BF_AR(BF_OPT_ADAM, true, true); break;
+    default: return fail(BF_ERR_ARG, "bf_opt_step_allreduce: unknown optimizer kind %d", kind);
+  }
+#undef BF_AR
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

@@ -42,6 +42,50 @@ def allreduce_sum(flat):
     return flat
 
 
+class SymmetricBuffer:
+    """A float32 vector allocated in NVLink-mapped symmetric memory: every rank can load every other rank's copy.
+    `torch.distributed._symmetric_memory` does the allocation and the handle exchange (plumbing); the kernel that
+    uses the peer pointers is ours (`bf_opt_step_allreduce`)."""
+    BLOCKS = 32
+
+    def __init__(self, tensor, handle):
+        self.t = tensor
+        self.handle = handle
+        self.rank, self.world = handle.rank, handle.world_size
+        self.peers_dev = int(handle.buffer_ptrs_dev)
+        self.pads_dev = int(handle.signal_pad_ptrs_dev)
+        cap = int(handle.signal_pad_size) // (4 * self.world)
+        self.blocks = max(1, min(self.BLOCKS, cap))
+        self.epoch = torch.zeros(self.blocks, dtype=torch.int32, device=tensor.device)
+        self.gsum = torch.zeros_like(tensor)
+
+
+_symm_failed = False
+
+
+def symmetric_zeros(n):
+    """Collective (all ranks, same order): a zeroed symmetric float32 vector, or None when the job is single-rank, not
+    on NCCL, switched off (BF_FUSED_ALLREDUCE=0) or the platform has no peer mapping -- the caller then keeps the
+    NCCL all-reduce."""
+    global _symm_failed
+    if world_size() == 1 or _symm_failed or td.get_backend() != "nccl" or os.environ.get("BF_FUSED_ALLREDUCE", "1") == "0":
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(n, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        handle = symm_mem.rendezvous(t, td.group.WORLD)
+        t.zero_()
+        torch.cuda.synchronize()
+        td.barrier()
+        return SymmetricBuffer(t, handle)
+    except Exception as exc:   # noqa: BLE001  (any failure here only costs the fast path)
+        _symm_failed = True
+        if rank() == 0:
+            print("[brainforge_b200] symmetric memory unavailable (%s: %s); using the NCCL all-reduce"
+                  % (type(exc).__name__, exc), flush=True)
+        return None
+
+
 def global_count(m_local):
     """Sum of per-rank batch sizes (equal shards: m_local * world_size, no collective needed)."""
     return m_local * world_size()

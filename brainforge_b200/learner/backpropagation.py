@@ -90,11 +90,16 @@ class Backpropagation(Learner):
         # learn_batch discards the delta w.r.t. the network input (learner/backpropagation.py:22 ignores the
         # return value), so the first layer's dX contraction is not computed here; backpropagate() still does.
         self._bwd(delta, need_input_delta=False)
+        m_global = m_global_static if m_global_static is not None else _dist.global_count(m_local)
         if _dist.world_size() > 1:
+            if update and self.layers.symm is not None:
+                # one kernel: sum of every rank's gradient vector (and step scalars) over NVLink peer loads + update
+                self.update(m_global, symm=self.layers.symm)
+                return
             # gradients + step scalars in ONE collective (scalars alone when no update follows)
             _dist.allreduce_sum(self.layers.flat_grads if update else sc)
         if update:
-            self.update(m_global_static if m_global_static is not None else _dist.global_count(m_local))
+            self.update(m_global)
 
     def _read_scalars(self, metrics, m_local):
         sc = self.layers.scalars().numpy()
@@ -164,12 +169,16 @@ class Backpropagation(Learner):
         out = self._bwd(as_device(error) if isinstance(error, DeviceArray) else DeviceArray.from_host(error))
         return out if isinstance(error, DeviceArray) else out.numpy()
 
-    def update(self, m):
+    def update(self, m, symm=None):
         """learner/backpropagation.py:37-42 without the host round trip: one fused kernel reads W, g (and
-        the optimizer state), writes W (and state) and clears g (zero_gradients, :68-73)."""
+        the optimizer state), writes W (and state) and clears g (zero_gradients, :68-73).  With `symm` (data-parallel
+        jobs) the same kernel first sums the gradient vectors of all ranks through their peer-mapped buffers."""
         L = self.layers
         L.flatten_parameters()
         n = L.flat_size
+        if symm is not None:
+            self.optimizer.optimize_allreduce(L.flat_weights, L.flat_grads, n, m, symm)
+            return
         self.optimizer.optimize(L.flat_weights[0:n], L.flat_grads[0:n], m, zero_grad=True)
 
     def get_weights(self, unfold=True):

@@ -10,6 +10,7 @@ data-parallel all-reduce therefore touch one contiguous vector and never round-t
 import numpy as np
 import torch
 
+from .. import dist as _dist
 from ..device import DeviceArray, as_device
 from ..layers.abstract_layer import LayerBase
 from ..layers.core import InputLayer
@@ -31,6 +32,7 @@ class LayerStack:
         self.flat_grads = None
         self._segments = []
         self._flat_dirty = True
+        self.symm = None
         self._add_input_layer(input_shape)
         for layer in layers:
             self.add(layer)
@@ -72,7 +74,10 @@ class LayerStack:
         self._scalar_off = total
         total += SEG_ALIGN
         W = torch.zeros(total, dtype=torch.float32, device="cuda")
-        G = torch.zeros(total, dtype=torch.float32, device="cuda")
+        # data-parallel jobs keep the gradient vector in symmetric (peer-mapped) memory: the step tail then is one
+        # kernel that sums every rank's copy over NVLink and applies the optimizer (bf_opt_step_allreduce)
+        self.symm = _dist.symmetric_zeros(total)
+        G = self.symm.t if self.symm is not None else torch.zeros(total, dtype=torch.float32, device="cuda")
         for layer, wname, gname, o, size in segs:
             w_old, g_old = getattr(layer, wname), getattr(layer, gname)
             W[o:o + size].copy_(w_old.t.reshape(-1))
