@@ -144,15 +144,17 @@ template <int NT>
 __global__ void __launch_bounds__(128)
 dense_skinny_fwd_direct_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
                                float* __restrict__ out, int m, int k, int n, int act, int pc, int phw) {
+  // the four warps of a CTA share DIRECT_ROWS rows and split K four ways (a single warp per row group left the
+  // L1/L2 latency of the W rows exposed); their partial sums meet in shared memory
+  __shared__ float red[4][DIRECT_ROWS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int m0 = (blockIdx.x * 4 + warp) * DIRECT_ROWS;
-  if (m0 >= m) return;
+  const int m0 = blockIdx.x * DIRECT_ROWS;
   float acc[DIRECT_ROWS][NT];
 #pragma unroll
   for (int r = 0; r < DIRECT_ROWS; ++r)
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[r][j] = 0.f;
-  for (int kq = lane * 4; kq < k; kq += 128) {
+  for (int kq = threadIdx.x * 4; kq < k; kq += 512) {
     float4 x[DIRECT_ROWS];
 #pragma unroll
     for (int r = 0; r < DIRECT_ROWS; ++r)
@@ -186,6 +188,12 @@ dense_skinny_fwd_direct_kernel(const float* __restrict__ X, const float* __restr
       const float t = warp_sum(acc[r][j]);
       if (lane == j) mine = t;
     }
+    red[warp][r][lane] = mine;
+  }
+  __syncthreads();
+  if (warp < DIRECT_ROWS && m0 + warp < m) {      // warp r finishes row m0 + r
+    const int r = warp;
+    float mine = (red[0][r][lane] + red[1][r][lane]) + (red[2][r][lane] + red[3][r][lane]);
     const bool col = lane < n;
     if (b && col) mine += __ldg(b + lane);
     if (act == BF_ACT_SOFTMAX) {
@@ -195,7 +203,7 @@ dense_skinny_fwd_direct_kernel(const float* __restrict__ X, const float* __restr
     } else {
       mine = act_fwd_rt(act, mine);
     }
-    if (col && m0 + r < m) out[(size_t)(m0 + r) * n + lane] = mine;
+    if (col) out[(size_t)(m0 + r) * n + lane] = mine;
   }
 }
 
@@ -273,7 +281,7 @@ static int launch_skinny_fwd(const float* X, const float* W, const float* b, flo
   static const int direct_max = getenv("BF_DENSE_DIRECT_MAX") ? atoi(getenv("BF_DENSE_DIRECT_MAX")) : 2048;
   if (m <= direct_max && (k & 3) == 0 && (n & 1) == 0 && n <= 16 && (pc == 0 || (pc & 3) == 0) && ((uintptr_t)X & 15) == 0 &&
       ((uintptr_t)W & 7) == 0) {
-    const int dgrid = (m + 4 * DIRECT_ROWS - 1) / (4 * DIRECT_ROWS);
+    const int dgrid = (m + DIRECT_ROWS - 1) / DIRECT_ROWS;
     const int dnt = n <= 4 ? 4 : n <= 8 ? 8 : n <= 12 ? 12 : 16;
 #define BF_SKD(NT_) if (dnt == NT_) dense_skinny_fwd_direct_kernel<NT_><<<dgrid, 128, 0, s>>>(X, W, b, out, m, k, n, act, pc, phw);
     BF_SKD(4) BF_SKD(8) BF_SKD(12) BF_SKD(16)
