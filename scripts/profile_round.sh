@@ -11,3 +11,10 @@ for K in conv_c3_fwd_kernel conv_c3_df_kernel conv_df_kernel conv_igemm_kernel p
   ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip 4 -c 1 -o $OUT/${TAG}_full_$K $CMD > $OUT/${TAG}_full_$K.log 2>&1
 done
 ls -la $OUT | tail -12
+# the other configs (bench lines only) and the LSTM launch list
+for C in cfg1 cfg2 cfg4 cfg5; do
+  python bench.py --workload $C --steps 20 --warmup 3 > $OUT/${TAG}_bench_$C.json 2> $OUT/${TAG}_bench_$C.err
+done
+python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_launches_cfg4.csv python bench.py --workload cfg4 --steps 1 --warmup 3 --no-cpu --no-graph > $OUT/${TAG}_launches_cfg4.log 2>&1
+ls -la $OUT | tail -12

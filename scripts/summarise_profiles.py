@@ -75,4 +75,31 @@ if os.path.exists(src):
     line = open(src).read().strip().splitlines()[-1]
     json.loads(line)
     open(os.path.join(P, tag + "_bench_cfg3_nhwc_tf32.json"), "w").write(line + "\n")
+for c in ("cfg1", "cfg2", "cfg4", "cfg5", "ref"):
+    src = os.path.join(G, "%s_bench_%s.json" % (tag, c))
+    if os.path.exists(src) and os.path.getsize(src):
+        line = open(src).read().strip().splitlines()[-1]
+        json.loads(line)
+        open(os.path.join(P, "%s_bench_%s.json" % (tag, c)), "w").write(line + "\n")
+# ---- LSTM (cfg4) launch list -> per-kernel table
+src = os.path.join(G, tag + "_launches_cfg4.csv")
+if os.path.exists(src):
+    rows = list(csv.reader(open(src)))
+    for i, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, start = r, i + 1
+            break
+    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg, tot = collections.OrderedDict(), 0.0
+    for r in rows[start:]:
+        if len(r) > iv:
+            v = float(r[iv].replace(",", ""))
+            v = v / 1000 if r[iu] == "ns" else (v if r[iu] in ("us", "usecond") else v * 1000)
+            a = agg.setdefault(r[ik], [0, 0.0]); a[0] += 1; a[1] += v; tot += v
+    with open(os.path.join(P, tag + "_launches_cfg4_summary.txt"), "w") as f:
+        f.write("# ncu launch list: python bench.py --workload cfg4 --steps 1 --warmup 3 --no-cpu --no-graph  (LSTM T=64, batch 1024, tf32 path)\n")
+        f.write("# gpu__time_duration.sum, --clock-control none, first 120 launches; cold-cache / serialised: compare SHARES.  %.1f us\n" % tot)
+        f.write("%-120s %5s %10s %6s\n" % ("kernel", "calls", "total_us", "share"))
+        for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-120s %5d %10.1f %5.1f%%\n" % (k[:120], n, v, 100 * v / tot))
 print("ok")
