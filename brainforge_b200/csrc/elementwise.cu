@@ -273,14 +273,21 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {      // never serve
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void peer_barrier(unsigned* const* pads, int rank, int world, unsigned value) {
+__device__ __forceinline__ void peer_barrier(unsigned* const* pads, int rank, int world, unsigned value, unsigned* timed_out) {
   __syncthreads();
   if ((int)threadIdx.x < world) {
     __threadfence_system();
     const int t = threadIdx.x;
     st_release_sys(pads[t] + (size_t)blockIdx.x * world + rank, value);
     const unsigned* mine = pads[rank] + (size_t)blockIdx.x * world + t;
-    while ((int)(ld_acquire_sys(mine) - value) < 0) {}
+    // a peer that never arrives (crashed rank, mismatched call sequence) must not wedge the GPU: give up after ~10 s
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - value) < 0) {
+      if (clock64() - t0 > 20000000000LL) {
+        if (timed_out) *timed_out = 1u;
+        break;
+      }
+    }
   }
   __syncthreads();
 }
@@ -289,7 +296,7 @@ constexpr int AR_MAX_WORLD = 16;
 struct ArParams {
   float* const* peers;        // device array [world] of every rank's gradient buffer (mine included)
   unsigned* const* pads;      // device array [world] of signal pads
-  unsigned* epoch;            // [gridDim.x] local per-CTA epochs
+  unsigned* epoch;            // [gridDim.x + 1] local per-CTA epochs; the last word is set if a barrier timed out
   float* gsum;                // local scratch [n_total]
   int rank, world;
   size_t n_params, n_total;   // multiples of 4
@@ -306,7 +313,7 @@ opt_allreduce_kernel(float* __restrict__ W, float* __restrict__ G, float* __rest
   const size_t n4 = p.n_total >> 2, np4 = p.n_params >> 2;
   const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
   const size_t lo = per * blockIdx.x, hi = lo + per < n4 ? lo + per : n4;
-  peer_barrier(p.pads, p.rank, p.world, 2u * e - 1u);
+  peer_barrier(p.pads, p.rank, p.world, 2u * e - 1u, p.epoch + gridDim.x);
   float4* W4 = reinterpret_cast<float4*>(W);
   float4* S14 = reinterpret_cast<float4*>(S1);
   float4* S24 = reinterpret_cast<float4*>(S2);
@@ -331,7 +338,7 @@ opt_allreduce_kernel(float* __restrict__ W, float* __restrict__ G, float* __rest
     }
     GS4[i] = g;
   }
-  peer_barrier(p.pads, p.rank, p.world, 2u * e);
+  peer_barrier(p.pads, p.rank, p.world, 2u * e, p.epoch + gridDim.x);
   float4* G4 = reinterpret_cast<float4*>(G);
   for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) G4[i] = (zero_grad && i < np4) ? zero4 : GS4[i];
 }
@@ -515,7 +522,8 @@ int bf_mul_rowmask(const float* x, const float* m, float* out, size_t rows, size
 // Data-parallel optimizer step: all-reduce(sum) of the flat gradient vector over peer memory fused with bf_opt_step.
 // G is this rank's buffer inside a symmetric allocation; peers / pads are DEVICE arrays of `world` pointers (every
 // rank's buffer and signal pad, as torch's symmetric memory hands them out); epoch is a zero-initialised local array
-// of `blocks` counters, gsum a local scratch of n_total floats.  Elements [n_params, n_total) (the step scalars) are
+// of `blocks` + 1 words (per-CTA epochs; the last one is set to 1 if a peer failed to arrive within ~10 s -- the
+// results of that step are then undefined), gsum a local scratch of n_total floats.  Elements [n_params, n_total) (the step scalars) are
 // summed but not optimised.  Every rank must make the same sequence of calls with the same `blocks`.
 int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float* s2, size_t n_params, size_t n_total, float eta,
                           float m, float hp0, float hp1, float hp2, int zero_grad, void* const* peers, void* const* pads,

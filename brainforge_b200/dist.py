@@ -56,8 +56,13 @@ class SymmetricBuffer:
         self.pads_dev = int(handle.signal_pad_ptrs_dev)
         cap = int(handle.signal_pad_size) // (4 * self.world)
         self.blocks = max(1, min(self.BLOCKS, cap))
-        self.epoch = torch.zeros(self.blocks, dtype=torch.int32, device=tensor.device)
+        self.epoch = torch.zeros(self.blocks + 1, dtype=torch.int32, device=tensor.device)   # [-1]: barrier time-out flag
         self.gsum = torch.zeros_like(tensor)
+
+
+    def timed_out(self):
+        """True if a peer failed to reach a barrier of bf_opt_step_allreduce (host sync; for diagnostics)."""
+        return bool(int(self.epoch[-1].item()))
 
 
 _symm_failed = False

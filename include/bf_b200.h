@@ -259,8 +259,9 @@ BF_API int bf_opt_step(int kind, float* W, float* g, float* s1, float* s2, size_
 /* Data-parallel form of the same step: all-reduce(sum) of the flat gradient vector over peer memory
  * (NVLink loads from every rank's symmetric buffer, fixed summation order) fused with the optimizer update.
  * G: this rank's gradient buffer inside a symmetric allocation; peers / pads: DEVICE arrays of `world` pointers to
- * every rank's buffer and signal pad; epoch: zero-initialised local array of `blocks` counters; gsum: local scratch
- * of n_total floats.  Elements [n_params, n_total) (the step scalars riding at the tail) are summed, not optimised.
+ * every rank's buffer and signal pad; epoch: zero-initialised local array of `blocks` + 1 words (the last one is set
+ * to 1 if a peer did not arrive within ~10 s: the step's results are then undefined); gsum: local scratch of n_total
+ * floats.  Elements [n_params, n_total) (the step scalars riding at the tail) are summed, not optimised.
  * Replaces `allreduce` + `optimizer.optimize` + `zero_gradients` (learner/backpropagation.py:37-42,68-73). */
 BF_API int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float* s2, size_t n_params, size_t n_total, float eta,
                           float m, float hp0, float hp1, float hp2, int zero_grad, void* const* peers, void* const* pads,

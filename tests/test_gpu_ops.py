@@ -120,6 +120,56 @@ def test_optimizers_golden(bf, golden_ops, name):
         close(W, g["opt_" + name][step], 2e-6)
 
 
+@pytest.mark.parametrize("world", [1, 4])
+@pytest.mark.parametrize("name", ["sgd", "adam"])
+def test_opt_step_allreduce_simulated_ranks(bf, name, world):
+    """bf_opt_step_allreduce with `world` simulated ranks on ONE device (one stream per rank, buffers and signal pads in
+    ordinary device memory): every replica ends at optimize(W, sum of the ranks' gradients), gradients are cleared, the
+    step scalars at the tail hold their sums.  (Across real GPUs: scripts/dp_check.py.)"""
+    import torch
+    from brainforge_b200 import _lib
+    from brainforge_b200.device import DeviceArray, call
+    rs = np.random.RandomState(world)
+    n_params, n_total, blocks, m = 4096 + 64, 4096 + 128, 4, 37.0
+    W0 = rs.randn(n_params).astype(np.float32)
+    Gs = [rs.randn(n_total).astype(np.float32) for _ in range(world)]
+    dev = torch.device("cuda")
+    G = [torch.tensor(g, device=dev) for g in Gs]
+    W = [torch.tensor(np.concatenate([W0, np.zeros(n_total - n_params, np.float32)]), device=dev) for _ in range(world)]
+    pads = [torch.zeros(blocks * world, dtype=torch.int32, device=dev) for _ in range(world)]
+    peers_t = torch.tensor([g.data_ptr() for g in G], dtype=torch.int64, device=dev)
+    pads_t = torch.tensor([p.data_ptr() for p in pads], dtype=torch.int64, device=dev)
+    epochs = [torch.zeros(blocks + 1, dtype=torch.int32, device=dev) for _ in range(world)]
+    gsum = [torch.zeros(n_total, device=dev) for _ in range(world)]
+    opts = [bf.optimizers.optimizers[name]() for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for step in range(2):
+        for r in range(world):
+            s1, s2 = opts[r]._state(n_params)
+            hp = opts[r]._hp()
+            call(_lib.lib.bf_opt_step_allreduce, _lib.OPT[name], W[r].data_ptr(), G[r].data_ptr(), s1, s2, n_params, n_total,
+                 float(opts[r].eta), m, float(hp[0]), float(hp[1]), float(hp[2]), 1, peers_t.data_ptr(), pads_t.data_ptr(),
+                 epochs[r].data_ptr(), gsum[r].data_ptr(), r, world, blocks, streams[r].cuda_stream)
+        torch.cuda.synchronize()
+        assert all(int(e[-1].item()) == 0 for e in epochs), "a simulated rank timed out at the barrier"
+        total = np.sum(np.stack(Gs).astype(np.float64), axis=0)
+        if step == 0:
+            ref = bf.optimizers.optimizers[name]()
+            Wref = DeviceArray.from_host(W0)
+        gref = DeviceArray.from_host(total[:n_params])
+        ref.optimize(Wref, gref, m)
+        for r in range(world):
+            close(W[r][:n_params].cpu().numpy(), Wref.numpy(), 1e-6)
+            assert not G[r][:n_params].any().item()
+            close(G[r][n_params:].cpu().numpy(), total[n_params:], 1e-6)
+            assert torch.equal(W[r], W[0])
+        Gs = [rs.randn(n_total).astype(np.float32) for _ in range(world)]       # next step's local gradients
+        for r in range(world):
+            G[r].copy_(torch.tensor(Gs[r], device=dev))
+        torch.cuda.synchronize()
+
+
 # ---------------------------------------------------------------- oracle at ragged / awkward shapes
 @pytest.mark.parametrize("m,k,n", [(1, 1, 1), (20, 784, 60), (20, 60, 10), (33, 17, 5), (257, 130, 129), (4096, 512, 10)])
 def test_dense_vs_oracle(bf, O, m, k, n):
