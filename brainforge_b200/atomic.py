@@ -560,7 +560,7 @@ class LSTMOp:
         O = DeviceArray.empty(T, B, H)
         Z = DeviceArray.empty(T, B, D + H)
         cache = DeviceArray.empty(6, T, B, H)
-        cache.bw = DeviceArray.empty(5, T, B, H)   # act'(.) of Ca,cand,f,i,o from the pre-activations
+        cache.bw = DeviceArray.empty(5, T, B, H)   # coefficients of the backward recurrence, from the pre-activations
         call(L.bf_lstm_forward, x.ptr, w.ptr, bd.ptr, O.ptr, Z.ptr, cache.ptr, cache.bw.ptr, T, B, D, H,
              _lib.ACT[self.activation], precision(), stream_ptr())
         return _ret(X, O, Z, cache)
@@ -569,13 +569,16 @@ class LSTMOp:
         z, o, e, w, c = as_device(Z), as_device(O), as_device(E), as_device(W), as_device(cache)
         bw = getattr(cache, "bw", None)
         if bw is None and not isinstance(cache, DeviceArray):
-            # host float64 cache: form the reference's bwCa / bwgates (recurrent_op.py:85-88) before narrowing
+            # host float64 cache: form the five coefficients of the backward recurrence from the reference's bwCa /
+            # bwgates (recurrent_op.py:85-88) before narrowing: o*act'(Ca), i*act'(cand), C[t-1]*f', cand*i', Ca*o'
             ch = np.asarray(cache, dtype=np.float64)
             def d(kind, a):
                 return {"sigmoid": a * (1. - a), "tanh": 1. - a ** 2, "relu": (a > 0.).astype(np.float64),
                         "linear": np.ones_like(a)}[kind]
-            bw = DeviceArray.from_host(np.stack([d(self.activation, ch[1]), d(self.activation, ch[2]),
-                                                 d("sigmoid", ch[3]), d("sigmoid", ch[4]), d("sigmoid", ch[5])]))
+            Cm, Ca, cand, f, ig, o = ch
+            Cprev = np.concatenate([np.zeros_like(Cm[:1]), Cm[:-1]])
+            bw = DeviceArray.from_host(np.stack([o * d(self.activation, Ca), ig * d(self.activation, cand),
+                                                 Cprev * d("sigmoid", f), cand * d("sigmoid", ig), Ca * d("sigmoid", o)]))
         T, B, ZD = z.shape
         H = w.shape[-1] // 4
         D = ZD - H

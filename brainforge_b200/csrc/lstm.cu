@@ -65,11 +65,13 @@ __global__ void lstm_gates_fwd_kernel(const float* __restrict__ P, const float* 
     if (bw) {
       // act'(.) of the five cached activations, evaluated from the PRE-activations: forming A(1-A) or
       // 1-A^2 from FP32-rounded saturated outputs (all biases start at +7) would cancel catastrophically
-      bw[idx] = act_deriv_from_z(act, c, ca);
-      bw[bw_stride + idx] = act_deriv_from_z(act, p[j], cv);
-      bw[2 * bw_stride + idx] = fv * sigmoidf_(-p[H + j]);
-      bw[3 * bw_stride + idx] = iv * sigmoidf_(-p[2 * H + j]);
-      bw[4 * bw_stride + idx] = ov * sigmoidf_(-p[3 * H + j]);
+      // stored as the five per-element COEFFICIENTS of the backward recurrence (recurrent_op.py:94-104):
+      // o*act'(C), i*act'(cand), C[t-1]*f', cand*i', Ca*o'
+      bw[idx] = ov * act_deriv_from_z(act, c, ca);
+      bw[bw_stride + idx] = iv * act_deriv_from_z(act, p[j], cv);
+      bw[2 * bw_stride + idx] = cp * (fv * sigmoidf_(-p[H + j]));
+      bw[3 * bw_stride + idx] = cv * (iv * sigmoidf_(-p[2 * H + j]));
+      bw[4 * bw_stride + idx] = ca * (ov * sigmoidf_(-p[3 * H + j]));
     }
     if (Znext) Znext[b * (D + H) + D + j] = out;
   }
@@ -88,22 +90,23 @@ __global__ void lstm_gates_bwd_kernel(const float* __restrict__ E, const float* 
     long b = idx / H;
     int j = (int)(idx - b * H);
     float e = E[idx] + (dH ? dH[idx] : 0.f);
-    float cav = Ca[idx], cv = cand[idx], fv = f[idx], iv = ig[idx], ov = o[idx];
-    float bCa, bcand, bf_, bi, bo;
+    float fv = f[idx];
+    float k0, k1, k2, k3, k4;      // o*act'(C), i*act'(cand), C[t-1]*f', cand*i', Ca*o'
     if (bw) {
-      bCa = bw[idx]; bcand = bw[bw_stride + idx]; bf_ = bw[2 * bw_stride + idx];
-      bi = bw[3 * bw_stride + idx]; bo = bw[4 * bw_stride + idx];
+      k0 = bw[idx]; k1 = bw[bw_stride + idx]; k2 = bw[2 * bw_stride + idx];
+      k3 = bw[3 * bw_stride + idx]; k4 = bw[4 * bw_stride + idx];
     } else {  // derivative-from-output exactly as recurrent_op.py:85-88 (FP32 cancellation when saturated)
-      bCa = act_bwd_rt(act, cav); bcand = act_bwd_rt(act, cv);
-      bf_ = fv * (1.f - fv); bi = iv * (1.f - iv); bo = ov * (1.f - ov);
+      float cav = Ca[idx], cv = cand[idx], iv = ig[idx], ov = o[idx];
+      float cp = Cprev ? Cprev[idx] : 0.f;
+      k0 = ov * act_bwd_rt(act, cav); k1 = iv * act_bwd_rt(act, cv);
+      k2 = cp * (fv * (1.f - fv)); k3 = cv * (iv * (1.f - iv)); k4 = cav * (ov * (1.f - ov));
     }
-    float dC = (first ? 0.f : deltaC[idx]) + e * ov * bCa;
-    float cp = Cprev ? Cprev[idx] : 0.f;
+    float dC = (first ? 0.f : deltaC[idx]) + e * k0;
     float* dg = dgates + b * 4 * H;
-    dg[j] = dC * iv * bcand;
-    dg[H + j] = dC * cp * bf_;
-    dg[2 * H + j] = dC * cv * bi;
-    dg[3 * H + j] = cav * e * bo;
+    dg[j] = dC * k1;
+    dg[H + j] = dC * k2;
+    dg[2 * H + j] = dC * k3;
+    dg[3 * H + j] = e * k4;
     deltaC[idx] = dC * fv;
   }
 }
@@ -246,11 +249,11 @@ lstm_step_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_cons
         c[i] = cp[i] * fv[i] + cv[i] * iv[i];       // recurrent_op.py:72
         ca[i] = act_fwd_rt(p.act, c[i]);
         out[i] = ca[i] * ov[i];                     // recurrent_op.py:74-75
-        d0[i] = act_deriv_from_z(p.act, c[i], ca[i]);
-        d1[i] = act_deriv_from_z(p.act, zc, cv[i]);
-        d2[i] = fv[i] * sigmoidf_(-zf);
-        d3[i] = iv[i] * sigmoidf_(-zi);
-        d4[i] = ov[i] * sigmoidf_(-zo);
+        d0[i] = ov[i] * act_deriv_from_z(p.act, c[i], ca[i]);
+        d1[i] = iv[i] * act_deriv_from_z(p.act, zc, cv[i]);
+        d2[i] = cp[i] * (fv[i] * sigmoidf_(-zf));
+        d3[i] = cv[i] * (iv[i] * sigmoidf_(-zi));
+        d4[i] = ca[i] * (ov[i] * sigmoidf_(-zo));
       }
       float* q = p.cache + off + row;
       store8(q, c, nvalid, vec);
@@ -408,7 +411,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[set]);      // the accumulator is in registers: the MMA warp may reuse the set
-      float ca[8], cv[8], fv[8], iv[8], ov[8], out[8], zc[8], zf[8], zi[8], zo[8];
+      float ca[8], cv[8], fv[8], iv[8], ov[8], out[8], zc[8], zf[8], zi[8], zo[8], cprev[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         zc[i] = __uint_as_float(pc[i]) + bc[i]; zf[i] = __uint_as_float(pf[i]) + bf_[i];
@@ -417,6 +420,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
         fv[i] = sigmoidf_(zf[i]);
         iv[i] = sigmoidf_(zi[i]);
         ov[i] = sigmoidf_(zo[i]);
+        cprev[i] = c[i];
         c[i] = c[i] * fv[i] + cv[i] * iv[i];        // recurrent_op.py:72
         ca[i] = act_fwd_rt(p.act, c[i]);
         out[i] = ca[i] * ov[i];                     // recurrent_op.py:74-75
@@ -424,7 +428,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
       const long off = (long)t * p.B * p.H;
       if (t + 1 < p.T) {
         if (live) store8(p.Z + ((long)(t + 1) * p.B + m) * (p.D + p.H) + p.D + jb, out, nvalid, vec);
-        __threadfence();
+        // the barrier orders every epilogue thread's stores before thread 128's gpu-scope release (cumulativity):
+        // no per-thread membar needed
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 128) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + (size_t)mt * p.T + t) : "memory");
       }
@@ -441,19 +446,19 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
           float d[8];
           float* w = p.bw + off + row;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] = act_deriv_from_z(p.act, c[i], ca[i]);
+          for (int i = 0; i < 8; ++i) d[i] = ov[i] * act_deriv_from_z(p.act, c[i], ca[i]);
           store8(w, d, nvalid, vec);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] = act_deriv_from_z(p.act, zc[i], cv[i]);
+          for (int i = 0; i < 8; ++i) d[i] = iv[i] * act_deriv_from_z(p.act, zc[i], cv[i]);
           store8(w + p.TBH, d, nvalid, vec);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] = fv[i] * sigmoidf_(-zf[i]);
+          for (int i = 0; i < 8; ++i) d[i] = cprev[i] * (fv[i] * sigmoidf_(-zf[i]));
           store8(w + 2 * p.TBH, d, nvalid, vec);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] = iv[i] * sigmoidf_(-zi[i]);
+          for (int i = 0; i < 8; ++i) d[i] = cv[i] * (iv[i] * sigmoidf_(-zi[i]));
           store8(w + 3 * p.TBH, d, nvalid, vec);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) d[i] = ov[i] * sigmoidf_(-zo[i]);
+          for (int i = 0; i < 8; ++i) d[i] = ca[i] * (ov[i] * sigmoidf_(-zo[i]));
           store8(w + 4 * p.TBH, d, nvalid, vec);
         }
       }
@@ -463,6 +468,213 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
   __syncthreads();
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * LF_N));
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The backward recurrence (BPTT) as ONE persistent cooperative kernel, the mirror image of lstm_seq_fwd_kernel.
+// A CTA owns 64 batch rows x 32 hidden units for all T steps:
+//   * its slice of W_h (rows D + j of W, 32 rows x 4H) is loaded once and stays in shared memory;
+//   * deltaC of a (row, unit) pair lives in the registers of the thread that owns it;
+//   * step t: the epilogue threads turn dH (their own accumulator columns of the previous GEMM) into the four gate
+//     deltas of their units (recurrent_op.py:94-104, coefficients from `bw`), store them into dgates[t] and publish a
+//     release/acquire counter per (batch tile, step); when all unit tiles of the batch tile have published, the
+//     producer streams dgates[t] (64 rows x 4H) through a TMA ring and the MMA warp forms dH for step t-1;
+//   * the input half of deltaZ (dX) is not on the recurrence: it is one large GEMM over all T*B rows afterwards.
+constexpr int LB_ROWS = 64, LB_UNITS = 32, LB_RING = 8, LB_THREADS = 384;
+constexpr uint32_t LB_A_BYTES = LB_ROWS * 128, LB_W_BYTES = LB_UNITS * 128;
+
+struct LstmBwdParams {
+  int T, B, D, H, nkb, m_tiles, n_tiles;
+  long TBH;
+  const float *E, *cache, *bw;
+  float* dgates;
+  unsigned* flags;      // [m_tiles][T], zeroed before the launch
+};
+
+__device__ __forceinline__ void load8(float (&v)[8], const float* p, int nvalid, bool vec, bool live) {
+  if (live && vec && nvalid == 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (live && i < nvalid) ? __ldg(p + i) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(LB_THREADS, 1)
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapW, LstmBwdParams p) {
+  extern __shared__ int dyn_smem[];
+  __shared__ __align__(8) uint64_t w_full, full[LB_RING], empty[LB_RING], t_full[2], t_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const uint32_t wbase = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const uint32_t ring = wbase + (uint32_t)p.nkb * LB_W_BYTES;
+  const int nt = blockIdx.x / p.m_tiles, mt = blockIdx.x - nt * p.m_tiles;
+  const int j0 = nt * LB_UNITS;
+
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * LB_UNITS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < LB_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_expect_tx(&w_full, (uint32_t)p.nkb * LB_W_BYTES);
+      for (int kb = 0; kb < p.nkb; ++kb)
+        tma_load_2d(wbase + (uint32_t)kb * LB_W_BYTES, &mapW, &w_full, kb * 32, p.D + j0);
+      int sl = 0, u = 0;
+      for (int t = p.T - 1; t >= 1; --t) {         // the GEMM of step t produces dH for step t-1
+        const unsigned* flag = p.flags + (size_t)mt * p.T + t;
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        } while (v < (unsigned)p.n_tiles);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          if (u > 0) mbar_wait(&empty[sl], (uint32_t)((u - 1) & 1));
+          mbar_expect_tx(&full[sl], LB_A_BYTES);
+          tma_load_3d(ring + (uint32_t)sl * LB_A_BYTES, &mapG, &full[sl], kb * 32, mt * LB_ROWS, t);
+          if (++sl == LB_RING) { sl = 0; ++u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one_sync();
+    constexpr uint32_t idesc = idesc_tf32(LB_ROWS, LB_UNITS);
+    mbar_wait(&w_full, 0);
+    int sl = 0, u = 0, it = 0;
+    for (int t = p.T - 1; t >= 1; --t, ++it) {
+      const int set = it & 1, tu = it >> 1;
+      if (tu > 0) mbar_wait(&t_empty[set], (uint32_t)((tu - 1) & 1));
+      tc_fence_after();
+      const uint32_t acc = tmem + (uint32_t)set * LB_UNITS;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(&full[sl], (uint32_t)(u & 1));
+        tc_fence_after();
+        if (leader) {
+          const uint64_t ad = desc_k_sw128(ring + (uint32_t)sl * LB_A_BYTES), bd = desc_k_sw128(wbase + (uint32_t)kb * LB_W_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&empty[sl]);
+        }
+        __syncwarp();
+        if (++sl == LB_RING) { sl = 0; ++u; }
+      }
+      if (leader) umma_commit(&t_full[set]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // M = 64 accumulators: row r sits in TMEM lane (r / 16) * 32 + r % 16 -> lanes 0..15 of each warp carry rows
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int m = mt * LB_ROWS + quad * 16 + (lane & 15);
+    const bool row_ok = lane < 16 && m < p.B;
+    const bool vec = (p.H & 3) == 0;
+    const int jb = j0 + half * 16;                 // this thread's 16 hidden units, as two chunks of 8
+    int nv[2];
+    nv[0] = p.H - jb; nv[0] = nv[0] > 8 ? 8 : (nv[0] < 0 ? 0 : nv[0]);
+    nv[1] = p.H - jb - 8; nv[1] = nv[1] > 8 ? 8 : (nv[1] < 0 ? 0 : nv[1]);
+    float dC[2][8];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dC[c][i] = 0.f;
+    int it = 0;
+    for (int t = p.T - 1; t >= 0; --t) {
+      const long base = ((long)t * p.B + m) * p.H + jb;
+      // operands of chunk 0 do not depend on the recurrence: fetched while the GEMM of step t+1 is still running
+      float e[8], fv[8], k0[8], k1[8], k2[8], k3[8], k4[8];
+      {
+        const bool live = row_ok && nv[0] > 0;
+        load8(e, p.E + base, nv[0], vec, live);
+        load8(fv, p.cache + 3 * p.TBH + base, nv[0], vec, live);
+        load8(k0, p.bw + base, nv[0], vec, live);
+        load8(k1, p.bw + p.TBH + base, nv[0], vec, live);
+        load8(k2, p.bw + 2 * p.TBH + base, nv[0], vec, live);
+        load8(k3, p.bw + 3 * p.TBH + base, nv[0], vec, live);
+        load8(k4, p.bw + 4 * p.TBH + base, nv[0], vec, live);
+      }
+      uint32_t dh[16];
+      if (t < p.T - 1) {
+        const int set = it & 1, tu = it >> 1;
+        mbar_wait(&t_full[set], (uint32_t)(tu & 1));
+        tc_fence_after();
+        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * LB_UNITS + half * 16), dh);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[set]);
+        ++it;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dh[i] = 0u;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float e2[8], fv2[8], q0[8], q1[8], q2[8], q3[8], q4[8];
+        if (c == 0) {                                   // issue chunk 1's loads before chunk 0's arithmetic and stores
+          const bool live = row_ok && nv[1] > 0;
+          load8(e2, p.E + base + 8, nv[1], vec, live);
+          load8(fv2, p.cache + 3 * p.TBH + base + 8, nv[1], vec, live);
+          load8(q0, p.bw + base + 8, nv[1], vec, live);
+          load8(q1, p.bw + p.TBH + base + 8, nv[1], vec, live);
+          load8(q2, p.bw + 2 * p.TBH + base + 8, nv[1], vec, live);
+          load8(q3, p.bw + 3 * p.TBH + base + 8, nv[1], vec, live);
+          load8(q4, p.bw + 4 * p.TBH + base + 8, nv[1], vec, live);
+        }
+        float g0[8], g1[8], g2[8], g3[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ev = e[i] + __uint_as_float(dh[c * 8 + i]);
+          const float d = dC[c][i] + ev * k0[i];
+          g0[i] = d * k1[i];
+          g1[i] = d * k2[i];
+          g2[i] = d * k3[i];
+          g3[i] = ev * k4[i];
+          dC[c][i] = d * fv[i];
+        }
+        if (row_ok && nv[c] > 0) {
+          float* dg = p.dgates + ((long)t * p.B + m) * 4 * p.H + jb + c * 8;
+          store8(dg, g0, nv[c], vec);
+          store8(dg + p.H, g1, nv[c], vec);
+          store8(dg + 2 * p.H, g2, nv[c], vec);
+          store8(dg + 3 * p.H, g3, nv[c], vec);
+        }
+        if (c == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { e[i] = e2[i]; fv[i] = fv2[i]; k0[i] = q0[i]; k1[i] = q1[i]; k2[i] = q2[i]; k3[i] = q3[i]; k4[i] = q4[i]; }
+        }
+      }
+      if (t >= 1) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 128) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + (size_t)mt * p.T + t) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * LB_UNITS));
+}
+
+// opt-in until it has been through the GPU parity suite: BF_LSTM_PERSIST_BWD=1
+static inline bool lstm_persistent_bwd_enabled() {
+  const char* e = getenv("BF_LSTM_PERSIST_BWD");
+  return e != nullptr && e[0] == '1';
+}
+
+struct EpiStoreLd {
+  float* out; long ld;
+  __device__ void store(int m, int n, float v, int) const { out[(long)m * ld + n] = v; }
+};
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -763,7 +975,56 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
   const float* f = cache + 3 * TB * H;
   const float* ig = cache + 4 * TB * H;
   const float* o = cache + 5 * TB * H;
-  for (int t = T - 1; t >= 0; --t) {
+  // persistent form: needs the coefficient rows `bw`, every tile resident at once, W_h slice + ring within shared memory
+  bool persistent_done = false;
+  if (precision == BF_PREC_TF32 && bw && T >= 1 && (N4 & 3) == 0 && (H & 3) == 0 && ((uintptr_t)W & 15) == 0 && tma_encode_fn() != nullptr &&
+      getenv("BF_LSTM_GATHER") == nullptr && getenv("BF_LSTM_STEPWISE") == nullptr && lstm_persistent_bwd_enabled()) {
+    const int nkb = (N4 + 31) / 32, m_tiles = (B + LB_ROWS - 1) / LB_ROWS, n_tiles = (H + LB_UNITS - 1) / LB_UNITS;
+    const size_t smem = 1024 + (size_t)nkb * LB_W_BYTES + (size_t)LB_RING * LB_A_BYTES;
+    const size_t flag_bytes = (size_t)m_tiles * T * sizeof(unsigned);
+    bool fits = m_tiles * n_tiles <= num_sms() && smem <= 220 * 1024 && flag_bytes <= (size_t)BH * sizeof(float);
+    if (fits) {
+      BF_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      BF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_seq_bwd_kernel, LB_THREADS, smem));
+      fits = (long)per_sm * num_sms() >= (long)m_tiles * n_tiles;
+    }
+    if (fits) {
+      CUtensorMap mG, mW;
+      {
+        uint64_t dims[3] = {(uint64_t)N4, (uint64_t)B, (uint64_t)T};
+        uint64_t str[2] = {(uint64_t)N4, (uint64_t)B * N4};
+        uint32_t box[3] = {32, LB_ROWS, 1};
+        if (!tma_make_map(&mG, dgates, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return fail(BF_ERR_CUDA, "bf_lstm_backward: cuTensorMapEncodeTiled failed (dgates)");
+      }
+      {
+        uint64_t dims[2] = {(uint64_t)N4, (uint64_t)ZD};
+        uint64_t str[1] = {(uint64_t)N4};
+        uint32_t box[2] = {32, LB_UNITS};
+        if (!tma_make_map(&mW, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return fail(BF_ERR_CUDA, "bf_lstm_backward: cuTensorMapEncodeTiled failed (W)");
+      }
+      unsigned* flags = (unsigned*)dH;          // the dH scratch is unused on this path
+      BF_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, s));
+      LstmBwdParams q;
+      q.T = T; q.B = B; q.D = D; q.H = H; q.nkb = nkb; q.m_tiles = m_tiles; q.n_tiles = n_tiles; q.TBH = TB * H;
+      q.E = E; q.cache = cache; q.bw = bw; q.dgates = dgates; q.flags = flags;
+      void* args[] = {(void*)&mG, (void*)&mW, (void*)&q};
+      BF_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_bwd_kernel, dim3(m_tiles * n_tiles), dim3(LB_THREADS), args, smem, s));
+      count_launch();
+      // dX = dgates @ W[:D]^T over all T*B rows at once: B(n, k) = W[n * 4H + k]
+      EpiStoreLd ep{dX, (long)D};
+      if (gemm_tma_ok(dgates, W, (int)TB, D, N4)) {
+        rc = launch_gemm_tma(dgates, W, (int)TB, D, N4, ep, s);
+      } else {
+        LoadKContig al{dgates, (long)N4};
+        LoadKContig bl{W, (long)N4};
+        rc = launch_gemm(precision, al, bl, ep, (int)TB, D, N4, 1, (N4 + GEMM_BK - 1) / GEMM_BK * GEMM_BK, 0, s);
+      }
+      if (rc) return rc;
+      persistent_done = true;
+    }
+  }
+  for (int t = T - 1; t >= 0 && !persistent_done; --t) {
     long off = (long)t * BH;
     float* dg_t = dgates + (long)t * B * N4;
     lstm_gates_bwd_kernel<<<ew_grid(BH, 256), 256, 0, s>>>(E + off, t == T - 1 ? nullptr : dH,

@@ -208,14 +208,17 @@ BF_API int bf_accuracy(const float* out, const float* tgt, int m, int n, float* 
 /* ---- LSTM: atomic/recurrent_op.py:46-112, llatomic/_lllstm.py:6-67 ---- */
 /* LSTMOp(act).forward(X,W,b) -> (O,Z,cache).  X (T,B,D) time-major, W (D+H,4H) gate order
  * [cand|f|i|o], b (4H); O (T,B,H), Z (T,B,D+H), cache (6,T,B,H) = C,Ca,cand,f,i,o.
- * bw (5,T,B,H) or NULL: act'(.) of Ca,cand,f,i,o (the reference's bwCa/bwgates, recurrent_op.py:85-88)
- * evaluated from the pre-activations, so that the saturated gates the +7 bias init produces do not
- * lose their derivative to FP32 cancellation in A(1-A). */
+ * bw (5,T,B,H) or NULL: the five per-element coefficients of the backward recurrence (recurrent_op.py:94-104),
+ * o*act'(C), i*act'(cand), C[t-1]*f', cand*i', Ca*o', with the derivatives (the reference's bwCa/bwgates, :85-88)
+ * evaluated from the pre-activations, so that the saturated gates the +7 bias init produces do not lose their
+ * derivative to FP32 cancellation in A(1-A). */
 BF_API int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
                     int T, int B, int D, int H, int act, int precision, void* stream);
 /* LSTMOp.backward(Z,O,E,W,cache) -> (dX (T,B,D), nablaW (D+H,4H), nablab (4H)); E (T,B,H) is read only.
- * bw as produced by bf_lstm_forward, or NULL to form the derivatives from the cached outputs in FP32.
- * Scratch (dgates, deltaC, split-K partials) comes from the workspace. */
+ * bw as produced by bf_lstm_forward, or NULL to form the coefficients from the cached outputs in FP32.
+ * Scratch (dgates, deltaC, split-K partials) comes from the workspace.  TF32 path with bw: the whole BPTT recurrence
+ * is one persistent kernel (W_h slice resident in shared memory, deltaC in registers, per-batch-tile flags), dX and
+ * the weight gradients are three large GEMMs over all T*B rows afterwards. */
 BF_API int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache,
                      const float* bw, float* dX, float* nablaW, float* nablab, int T, int B, int D, int H, int act,
                      int precision, void* stream);
