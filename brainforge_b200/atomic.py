@@ -575,10 +575,10 @@ class LSTMOp:
             def d(kind, a):
                 return {"sigmoid": a * (1. - a), "tanh": 1. - a ** 2, "relu": (a > 0.).astype(np.float64),
                         "linear": np.ones_like(a)}[kind]
-            Cm, Ca, cand, f, ig, o = ch
+            Cm, Ca, cand, fg, ig, og = ch
             Cprev = np.concatenate([np.zeros_like(Cm[:1]), Cm[:-1]])
-            bw = DeviceArray.from_host(np.stack([o * d(self.activation, Ca), ig * d(self.activation, cand),
-                                                 Cprev * d("sigmoid", f), cand * d("sigmoid", ig), Ca * d("sigmoid", o)]))
+            bw = DeviceArray.from_host(np.stack([og * d(self.activation, Ca), ig * d(self.activation, cand),
+                                                 Cprev * d("sigmoid", fg), cand * d("sigmoid", ig), Ca * d("sigmoid", og)]))
         T, B, ZD = z.shape
         H = w.shape[-1] // 4
         D = ZD - H

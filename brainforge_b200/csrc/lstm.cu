@@ -665,10 +665,10 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * LB_UNITS));
 }
 
-// opt-in until it has been through the GPU parity suite: BF_LSTM_PERSIST_BWD=1
+// BF_LSTM_PERSIST_BWD=0 keeps the per-step backward (gate kernel + GEMM per time step)
 static inline bool lstm_persistent_bwd_enabled() {
   const char* e = getenv("BF_LSTM_PERSIST_BWD");
-  return e != nullptr && e[0] == '1';
+  return e == nullptr || e[0] != '0';
 }
 
 struct EpiStoreLd {

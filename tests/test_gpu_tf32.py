@@ -93,6 +93,31 @@ def test_lstm_tf32(bf, O, T, B, D, H):
     close(dX, rX); close(gW, rW); close(gb, rb)
 
 
+@pytest.mark.parametrize("env", [{"BF_LSTM_STEPWISE": "1"}, {"BF_LSTM_PERSIST_BWD": "1"}, {"BF_LSTM_PERSIST_BWD": "0"},
+                                 {"BF_LSTM_UNFUSED": "1", "BF_LSTM_STEPWISE": "1"}])
+@pytest.mark.parametrize("T,B,D,H", [(5, 70, 12, 40), (8, 200, 64, 96)])
+def test_lstm_tf32_kernel_variants(bf, O, monkeypatch, env, T, B, D, H):
+    """Every LSTM kernel family behind the same entry points: persistent forward / per-step fused forward / GEMM + gate
+    kernel, persistent backward / per-step backward (the switches are read per call)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rs = np.random.RandomState(T + H)
+    X, W, b = rs.randn(T, B, D), rs.randn(D + H, 4 * H) * np.sqrt(2.0 / (D + 5 * H)), rs.randn(4 * H) * 0.1
+    op = bf.atomic.LSTMOp("tanh")
+    O_, Z_, C_ = op.forward(X, W, b)                      # device arrays carry the coefficient rows (cache.bw)
+    rO, rZ, rC = O.lstm_forward(X, W, b, "tanh")
+    close(O_, rO); close(Z_, rZ); close(C_, rC)
+    E = rs.randn(T, B, H)
+    from brainforge_b200.device import DeviceArray
+    Od, Zd, Cd = op.forward(DeviceArray.from_host(X), W, b)
+    dX, gW, gb = op.backward(Z=Zd, O=Od, E=DeviceArray.from_host(E), W=DeviceArray.from_host(W), cache=Cd)
+    rX, rW, rb = O.lstm_backward(rZ, rO, E, W, rC, "tanh")
+    close(dX.numpy(), rX); close(gW.numpy(), rW); close(gb.numpy(), rb)
+    # and from a host cache (coefficients formed on the host in float64)
+    dX, gW, gb = op.backward(Z=rZ, O=rO, E=E, W=W, cache=rC)
+    close(dX, rX); close(gW, rW); close(gb, rb)
+
+
 @pytest.mark.parametrize("T,B,D,H", [(6, 50, 12, 20), (10, 300, 64, 128)])
 def test_rnn_tf32(bf, O, T, B, D, H):
     rs = np.random.RandomState(T + H)
