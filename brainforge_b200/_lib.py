@@ -73,6 +73,7 @@ SIGNATURES = {
     "bf_cost_delta_value": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "bf_accuracy": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "bf_lstm_forward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
+    "bf_lstm_forward_bm": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
     "bf_lstm_backward": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
     "bf_rnn_forward": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "bf_rnn_backward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),

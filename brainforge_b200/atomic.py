@@ -551,9 +551,13 @@ class LSTMOp:
         self.activation = activation
         self.actfn = activations[activation]()
 
-    def forward(self, X, W, b):
+    def forward(self, X, W, b, batch_major=False):
+        """`batch_major=True`: X is (B,T,D) as the layer receives it (the transpose is folded into the kernel)."""
         x, w, bd = as_device(X), as_device(W), as_device(b)
-        T, B, D = x.shape
+        if batch_major:
+            B, T, D = x.shape
+        else:
+            T, B, D = x.shape
         H = w.shape[-1] // 4
         if w.shape[0] != D + H:
             raise ValueError("LSTM weight shape %s does not match D+H=%d" % (w.shape, D + H))
@@ -561,11 +565,11 @@ class LSTMOp:
         Z = DeviceArray.empty(T, B, D + H)
         cache = DeviceArray.empty(6, T, B, H)
         cache.bw = DeviceArray.empty(5, T, B, H)   # coefficients of the backward recurrence, from the pre-activations
-        call(L.bf_lstm_forward, x.ptr, w.ptr, bd.ptr, O.ptr, Z.ptr, cache.ptr, cache.bw.ptr, T, B, D, H,
-             _lib.ACT[self.activation], precision(), stream_ptr())
+        call(L.bf_lstm_forward_bm if batch_major else L.bf_lstm_forward, x.ptr, w.ptr, bd.ptr, O.ptr, Z.ptr, cache.ptr,
+             cache.bw.ptr, T, B, D, H, _lib.ACT[self.activation], precision(), stream_ptr())
         return _ret(X, O, Z, cache)
 
-    def backward(self, Z, O, E, W, cache, nablaW=None, nablab=None):
+    def backward(self, Z, O, E, W, cache, nablaW=None, nablab=None, need_dX=True):
         z, o, e, w, c = as_device(Z), as_device(O), as_device(E), as_device(W), as_device(cache)
         bw = getattr(cache, "bw", None)
         if bw is None and not isinstance(cache, DeviceArray):
@@ -582,10 +586,11 @@ class LSTMOp:
         T, B, ZD = z.shape
         H = w.shape[-1] // 4
         D = ZD - H
-        dX = DeviceArray.empty(T, B, D)
+        dX = DeviceArray.empty(T, B, D) if need_dX else None
         nablaW = DeviceArray.empty(ZD, 4 * H) if nablaW is None else nablaW
         nablab = DeviceArray.empty(4 * H) if nablab is None else nablab
-        call(L.bf_lstm_backward, z.ptr, o.ptr, e.ptr, w.ptr, c.ptr, bw.ptr if bw is not None else _NULL, dX.ptr,
+        call(L.bf_lstm_backward, z.ptr, o.ptr, e.ptr, w.ptr, c.ptr, bw.ptr if bw is not None else _NULL,
+             dX.ptr if dX is not None else _NULL,
              nablaW.ptr, nablab.ptr, T, B, D, H,
              _lib.ACT[self.activation], precision(), stream_ptr())
         return _ret(Z, dX, nablaW, nablab)

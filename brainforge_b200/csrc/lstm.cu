@@ -8,15 +8,22 @@
 
 namespace bf {
 
-// Z[t,b,0:D] = X[t,b,:] for all t;  Z[0,b,D:] = 0  (O[-1] is the still-zero last row, recurrent_op.py:60)
-__global__ void lstm_fill_z_kernel(const float* __restrict__ X, float* __restrict__ Z, long TB, int B, int D, int H) {
+// Z[t,b,0:D] = X[t,b,:] for all t;  Z[0,b,D:] = 0  (O[-1] is the still-zero last row, recurrent_op.py:60).
+// With `bm` the source is batch-major, X (B,T,D): the layer's `X.transpose(1, 0, 2)` (layers/recurrent.py:26) is folded in.
+__global__ void lstm_fill_z_kernel(const float* __restrict__ X, float* __restrict__ Z, long TB, int B, int D, int H, int T = 0,
+                                   int bm = 0) {
   long total = TB * D + (long)B * H;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     if (i < TB * D) {
       long r = i / D;
       int c = (int)(i - r * D);
-      Z[r * (D + H) + c] = X[i];
+      long src = i;
+      if (bm) {
+        const long t = r / B, b = r - t * B;
+        src = (b * T + t) * D + c;
+      }
+      Z[r * (D + H) + c] = X[src];
     } else {
       long j = i - TB * D;
       long r = j / H;
@@ -115,7 +122,7 @@ __global__ void lstm_gates_bwd_kernel(const float* __restrict__ E, const float* 
 struct EpiLstmDz {
   float* dX; float* dH; int D, H;
   __device__ void store(int m, int n, float v, int) const {
-    if (n < D) dX[(long)m * D + n] = v;
+    if (n < D) { if (dX) dX[(long)m * D + n] = v; }
     else dH[(long)m * H + (n - D)] = v;
   }
 };
@@ -512,13 +519,13 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
   const int j0 = nt * LB_UNITS;
 
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * LB_UNITS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(4 * LB_UNITS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
     mbar_init(&w_full, 1);
     for (int i = 0; i < LB_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 2); mbar_init(&t_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -547,7 +554,11 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 3) {
+    // two issuers: a single thread issues one of these small MMAs every 50-100 cycles, 4 * nkb of them per step would be
+    // the critical path.  Even K blocks accumulate into one 32-column accumulator, odd ones into a second; the epilogue
+    // adds the two.
+    const int which = warp == 1 ? 0 : 1;
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = idesc_tf32(LB_ROWS, LB_UNITS);
     mbar_wait(&w_full, 0);
@@ -556,18 +567,22 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
       const int set = it & 1, tu = it >> 1;
       if (tu > 0) mbar_wait(&t_empty[set], (uint32_t)((tu - 1) & 1));
       tc_fence_after();
-      const uint32_t acc = tmem + (uint32_t)set * LB_UNITS;
+      const uint32_t acc = tmem + (uint32_t)(set * 2 + which) * LB_UNITS;
+      bool first = true;
       for (int kb = 0; kb < p.nkb; ++kb) {
-        mbar_wait(&full[sl], (uint32_t)(u & 1));
-        tc_fence_after();
-        if (leader) {
-          const uint64_t ad = desc_k_sw128(ring + (uint32_t)sl * LB_A_BYTES), bd = desc_k_sw128(wbase + (uint32_t)kb * LB_W_BYTES);
+        if ((kb & 1) == which) {
+          mbar_wait(&full[sl], (uint32_t)(u & 1));
+          tc_fence_after();
+          if (leader) {
+            const uint64_t ad = desc_k_sw128(ring + (uint32_t)sl * LB_A_BYTES), bd = desc_k_sw128(wbase + (uint32_t)kb * LB_W_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-          umma_commit(&empty[sl]);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(acc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (!first || ks > 0) ? 1u : 0u);
+            umma_commit(&empty[sl]);
+          }
+          first = false;
+          __syncwarp();
         }
-        __syncwarp();
         if (++sl == LB_RING) { sl = 0; ++u; }
       }
       if (leader) umma_commit(&t_full[set]);
@@ -608,8 +623,12 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
         const int set = it & 1, tu = it >> 1;
         mbar_wait(&t_full[set], (uint32_t)(tu & 1));
         tc_fence_after();
-        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * LB_UNITS + half * 16), dh);
+        uint32_t dh1[16];
+        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * 2 * LB_UNITS + half * 16), dh);
+        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)((set * 2 + 1) * LB_UNITS + half * 16), dh1);
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dh[i] = __float_as_uint(__uint_as_float(dh[i]) + (p.nkb > 1 ? __uint_as_float(dh1[i]) : 0.f));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[set]);
@@ -662,7 +681,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * LB_UNITS));
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(4 * LB_UNITS));
 }
 
 // BF_LSTM_PERSIST_BWD=0 keeps the per-step backward (gate kernel + GEMM per time step)
@@ -825,8 +844,8 @@ using namespace bf;
 
 extern "C" {
 
-int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
-                    int T, int B, int D, int H, int act, int precision, void* stream) {
+static int lstm_forward_impl(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
+                             int T, int B, int D, int H, int act, int precision, void* stream, int x_batch_major) {
   BF_REQUIRE(X && W && b && O && Z && cache, BF_ERR_ARG, "bf_lstm_forward: null pointer");
   BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_lstm_forward: bad shape");
   BF_REQUIRE(act == BF_ACT_TANH || act == BF_ACT_RELU || act == BF_ACT_SIGMOID || act == BF_ACT_LINEAR, BF_ERR_ARG,
@@ -849,7 +868,7 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
     lstm_transpose_kernel<<<dim3((4 * H + 31) / 32, ((int)ZD + 31) / 32), dim3(32, 8), 0, s>>>(W, Wt, (int)ZD, 4 * H);
     BF_LAUNCH_CHECK();
   }
-  lstm_fill_z_kernel<<<ew_grid(TB * D + BH, 256), 256, 0, s>>>(X, Z, TB, B, D, H);
+  lstm_fill_z_kernel<<<ew_grid(TB * D + BH, 256), 256, 0, s>>>(X, Z, TB, B, D, H, T, x_batch_major);
   BF_LAUNCH_CHECK();
   float* C = cache;               // cache (6,T,B,H): C, Ca, cand, f, i, o  (recurrent_op.py:77)
   float* Ca = cache + 1 * TB * H;
@@ -930,11 +949,21 @@ int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, fl
   return BF_OK;
 }
 
+int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
+                    int T, int B, int D, int H, int act, int precision, void* stream) {
+  return lstm_forward_impl(X, W, b, O, Z, cache, bw, T, B, D, H, act, precision, stream, 0);
+}
+
+int bf_lstm_forward_bm(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
+                       int T, int B, int D, int H, int act, int precision, void* stream) {
+  return lstm_forward_impl(X, W, b, O, Z, cache, bw, T, B, D, H, act, precision, stream, 1);
+}
+
 int bf_lstm_backward(const float* Z, const float* O, const float* E, const float* W, const float* cache,
                      const float* bw, float* dX, float* nablaW, float* nablab, int T, int B, int D, int H, int act,
                      int precision, void* stream) {
   (void)O;
-  BF_REQUIRE(Z && E && W && cache && dX && nablaW && nablab, BF_ERR_ARG, "bf_lstm_backward: null pointer");
+  BF_REQUIRE(Z && E && W && cache && nablaW && nablab, BF_ERR_ARG, "bf_lstm_backward: null pointer");   // dX may be NULL
   BF_REQUIRE(T >= 0 && B >= 0 && D > 0 && H > 0, BF_ERR_ARG, "bf_lstm_backward: bad shape");
   cudaStream_t s = as_stream(stream);
   const long TB = (long)T * B, BH = (long)B * H;
@@ -1013,7 +1042,9 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
       count_launch();
       // dX = dgates @ W[:D]^T over all T*B rows at once: B(n, k) = W[n * 4H + k]
       EpiStoreLd ep{dX, (long)D};
-      if (gemm_tma_ok(dgates, W, (int)TB, D, N4)) {
+      if (dX == nullptr) {
+        rc = BF_OK;            // the caller discards the input delta (first layer inside learn_batch)
+      } else if (gemm_tma_ok(dgates, W, (int)TB, D, N4)) {
         rc = launch_gemm_tma(dgates, W, (int)TB, D, N4, ep, s);
       } else {
         LoadKContig al{dgates, (long)N4};
@@ -1033,7 +1064,7 @@ int bf_lstm_backward(const float* Z, const float* O, const float* E, const float
                                                           act, t == T - 1);
     BF_LAUNCH_CHECK();
     // deltaZ[t] = dgates[t] @ W^T : M=B, N=D+H, K=4H ; B(k, n) = W[n*4H + k]
-    EpiLstmDz ep{dX + (long)t * B * D, dH, D, H};
+    EpiLstmDz ep{dX ? dX + (long)t * B * D : nullptr, dH, D, H};
     if (precision == BF_PREC_TF32 && gemm_tma_ok(dg_t, W, B, ZD, N4) && getenv("BF_LSTM_GATHER") == nullptr) {
       rc = launch_gemm_tma(dg_t, W, B, ZD, N4, ep, s);     // both operands are K-major as stored: no copy, no transpose
     } else {

@@ -189,13 +189,27 @@ class LSTM(FFBase):
         self._init_params(white(self.Z, self.neurons * 4), np.zeros(self.neurons * 4) + self.bias_init_factor)
         super().connect(brain)
 
+    _can_skip_dx = True
+
+    @property
+    def inputs(self):
+        """(T,B,D) like the reference's `X.transpose(1, 0, 2)` (recurrent.py:26); materialised on demand -- the kernel
+        reads the batch-major array directly."""
+        if self._inputs_tm is None and self._inputs_bm is not None:
+            self._inputs_tm = _transpose01(self._inputs_bm)
+        return self._inputs_tm
+
+    @inputs.setter
+    def inputs(self, value):
+        self._inputs_tm, self._inputs_bm = value, None
+
     def _fwd(self, x):
-        self.inputs = _transpose01(x)                       # (B,T,D) -> (T,B,D), recurrent.py:26
-        self.time = self.inputs.shape[0]
-        self.output, self.Z, self.cache = self.op.forward(self.inputs, self.weights, self.biases)
+        self._inputs_tm, self._inputs_bm = None, x
+        self.time = x.shape[1]
+        self.output, self.Z, self.cache = self.op.forward(x, self.weights, self.biases, batch_major=True)
         return _transpose01(self.output) if self.return_seq else self.output[-1]
 
-    def _bwd(self, delta):
+    def _bwd(self, delta, need_dX=True):
         if self.return_seq:
             E = _transpose01(delta)                         # recurrent.py:35-36
         else:
@@ -203,8 +217,8 @@ class LSTM(FFBase):
             last = E[-1]
             call(_lib.lib.bf_act_forward, _lib.ACT["linear"], delta.ptr, last.ptr, last.size, stream_ptr())
         dX, _, _ = self.op.backward(Z=self.Z, O=self.output, E=E, W=self.weights, cache=self.cache,
-                                    nablaW=self.nabla_w, nablab=self.nabla_b)
-        return _transpose01(dX)
+                                    nablaW=self.nabla_w, nablab=self.nabla_b, need_dX=need_dX)
+        return _transpose01(dX) if dX is not None else None
 
     @property
     def outshape(self):

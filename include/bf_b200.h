@@ -214,8 +214,13 @@ BF_API int bf_accuracy(const float* out, const float* tgt, int m, int n, float* 
  * derivative to FP32 cancellation in A(1-A). */
 BF_API int bf_lstm_forward(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
                     int T, int B, int D, int H, int act, int precision, void* stream);
+/* Same with X batch-major (B,T,D) as the layer receives it: folds `X.transpose(1, 0, 2)` (layers/recurrent.py:26) into
+ * the pass that builds Z. */
+BF_API int bf_lstm_forward_bm(const float* X, const float* W, const float* b, float* O, float* Z, float* cache, float* bw,
+                       int T, int B, int D, int H, int act, int precision, void* stream);
 /* LSTMOp.backward(Z,O,E,W,cache) -> (dX (T,B,D), nablaW (D+H,4H), nablab (4H)); E (T,B,H) is read only.
  * bw as produced by bf_lstm_forward, or NULL to form the coefficients from the cached outputs in FP32.
+ * dX may be NULL when the caller discards the input delta (learner/backpropagation.py:22 ignores it for the first layer).
  * Scratch (dgates, deltaC, split-K partials) comes from the workspace.  TF32 path with bw: the whole BPTT recurrence
  * is one persistent kernel (W_h slice resident in shared memory, deltaC in registers, per-batch-tile flags), dX and
  * the weight gradients are three large GEMMs over all T*B rows afterwards. */
