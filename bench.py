@@ -268,7 +268,7 @@ def algorithmic_cost(label):
     if name == "bf_dense_backward":
         m, k, n = a[:3]
         return f * (2 * m * k + 2 * m * n + 2 * k * n + n), 4.0 * m * k * n
-    if name == "bf_lstm_forward":
+    if name in ("bf_lstm_forward", "bf_lstm_forward_bm"):
         T, B, D, H = a[:4]
         return f * T * B * (D + (D + H) + H + 11 * H) + f * (D + H) * 4 * H, 2.0 * T * B * (D + H) * 4 * H
     if name == "bf_lstm_backward":
