@@ -300,6 +300,18 @@ lstm_step_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_cons
 //   * of the thirteen output rows only O[t] -> Z[t+1] is on the critical path; it is stored and published first.
 constexpr int LS_RING = 6;
 
+// The recurrence's critical path evaluates five transcendentals per (row, unit) and step; this kernel only runs on the
+// TF32 path (5e-3 tolerance), so it uses the SFU forms: absolute error ~1e-7 for sigmoid, ~2e-7 for tanh.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_act(int act, float x) {
+  switch (act) {
+    case BF_ACT_SIGMOID: return fast_sigmoid(x);
+    case BF_ACT_TANH: return 2.f * fast_sigmoid(2.f * x) - 1.f;
+    case BF_ACT_RELU: return x > 0.f ? x : 0.f;
+    default: return x;
+  }
+}
+
 struct LstmSeqParams {
   int T, B, D, H, nkb, kb_dep, m_tiles, n_tiles, act;
   long TBH;
@@ -423,13 +435,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
       for (int i = 0; i < 8; ++i) {
         zc[i] = __uint_as_float(pc[i]) + bc[i]; zf[i] = __uint_as_float(pf[i]) + bf_[i];
         zi[i] = __uint_as_float(pi[i]) + bi[i]; zo[i] = __uint_as_float(po[i]) + bo[i];
-        cv[i] = act_fwd_rt(p.act, zc[i]);
-        fv[i] = sigmoidf_(zf[i]);
-        iv[i] = sigmoidf_(zi[i]);
-        ov[i] = sigmoidf_(zo[i]);
+        cv[i] = fast_act(p.act, zc[i]);
+        fv[i] = fast_sigmoid(zf[i]);
+        iv[i] = fast_sigmoid(zi[i]);
+        ov[i] = fast_sigmoid(zo[i]);
         cprev[i] = c[i];
         c[i] = c[i] * fv[i] + cv[i] * iv[i];        // recurrent_op.py:72
-        ca[i] = act_fwd_rt(p.act, c[i]);
+        ca[i] = fast_act(p.act, c[i]);
         out[i] = ca[i] * ov[i];                     // recurrent_op.py:74-75
       }
       const long off = (long)t * p.B * p.H;
