@@ -49,25 +49,34 @@ class Learner:
         self.layers.learning = True
         batch_size = 0
         # Learners that can stage a batch ahead of time (Backpropagation.stage_batch) get the NEXT batch's
-        # host->device copy overlapped with the current step: launch step i, upload batch i+1 on the copy
-        # stream, then read step i's scalars.  The generator is still drawn exactly updates_per_epoch times.
+        # host->device copy overlapped with the current step, and the host reads a step's scalars one step late
+        # (from a pinned snapshot taken right behind that step): launch step i, upload batch i+1 on the copy
+        # stream, read step i-1.  The device never waits for Python between steps.  The generator is still drawn
+        # exactly updates_per_epoch times and the history holds the same numbers in the same order.
         stage = getattr(self, "stage_batch", None) if "w" not in kw else None
-        staged = None
+        staged, pending_prev = None, None
+
+        def record(epoch_metrics):
+            history.record(epoch_metrics)
+            if verbose:
+                history.log(prefix="\rTraining ", end="", add_progress=True)
+
         for i in range(updates_per_epoch):
             if stage is None:
                 batch = next(generator)
                 batch_size = len(batch[0])
-                epoch_metrics = self.learn_batch(*batch, metrics=metrics, **kw)
+                record(self.learn_batch(*batch, metrics=metrics, **kw))
             else:
                 if staged is None:
                     staged = stage(*next(generator)[:2])
                 batch_size = len(staged)
-                pending = self.learn_batch_async(staged, None, metrics=metrics, **kw)
+                pending = self.learn_batch_async(staged, None, metrics=metrics, snapshot=True, **kw)
                 staged = stage(*next(generator)[:2]) if i + 1 < updates_per_epoch else None
-                epoch_metrics = pending()
-            history.record(epoch_metrics)
-            if verbose:
-                history.log(prefix="\rTraining ", end="", add_progress=True)
+                if pending_prev is not None:
+                    record(pending_prev())
+                pending_prev = pending
+        if pending_prev is not None:
+            record(pending_prev())
         self.layers.learning = False
         if verbose and validation:
             if type(validation) in (tuple, list):

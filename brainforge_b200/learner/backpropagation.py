@@ -50,21 +50,42 @@ class Backpropagation(Learner):
         rank's shard of the global batch; cost and metrics are those of the GLOBAL batch."""
         return self.learn_batch_async(X, Y, w=w, metrics=metrics, update=update)()
 
-    def learn_batch_async(self, X, Y, w=None, metrics=(), update=True):
+    def learn_batch_async(self, X, Y, w=None, metrics=(), update=True, snapshot=False):
         """Enqueue the whole device step and return a callable that reads the step's scalars back (the only
-        host synchronisation of a step).  `Learner.epoch` uses the gap to upload the NEXT batch on a copy stream."""
+        host synchronisation of a step).  `Learner.epoch` uses the gap to upload the NEXT batch on a copy stream.
+        With `snapshot` the scalars are also copied to pinned host memory right behind the step, so the callable stays
+        valid (and waits for THIS step only) after later steps have been enqueued."""
         metrics = [_metrics.get(m) for m in metrics]
         self.layers.flatten_parameters()
         if isinstance(X, StagedBatch):
             X.wait()
             X, Y = X.x, X.y
         if self.use_graph and w is None:
-            return self._launch_graph(X, Y, metrics, update)
-        x, y = as_device(X), as_device(Y)
-        wd = as_device(w) if w is not None else None
-        m_local = len(x)
-        self._step(x, y, wd, metrics, update, m_local, None)
-        return lambda: self._read_scalars(metrics, m_local)
+            reader = self._launch_graph(X, Y, metrics, update)
+            m_local = len(X)
+        else:
+            x, y = as_device(X), as_device(Y)
+            wd = as_device(w) if w is not None else None
+            m_local = len(x)
+            self._step(x, y, wd, metrics, update, m_local, None)
+            reader = lambda: self._read_scalars(metrics, m_local)   # noqa: E731
+        return self._snapshot_scalars(metrics, m_local) if snapshot else reader
+
+    def _snapshot_scalars(self, metrics, m_local):
+        sc = self.layers.scalars().t
+        if getattr(self, "_snap_host", None) is None or self._snap_host[0].numel() != sc.numel():
+            self._snap_host = [torch.empty(sc.numel(), dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._snap_ev = [torch.cuda.Event() for _ in range(4)]
+            self._snap_i = -1
+        self._snap_i = slot = (self._snap_i + 1) % 4
+        host, ev = self._snap_host[slot], self._snap_ev[slot]
+        host.copy_(sc, non_blocking=True)
+        ev.record()
+
+        def read():
+            ev.synchronize()
+            return self._scalars_to_dict(host.numpy(), metrics, m_local)
+        return read
 
     def stage_batch(self, X, Y):
         """Start the host->device copy of a batch on a side stream; the returned handle is accepted by
@@ -102,7 +123,10 @@ class Backpropagation(Learner):
             self.update(m_global)
 
     def _read_scalars(self, metrics, m_local):
-        sc = self.layers.scalars().numpy()
+        return self._scalars_to_dict(self.layers.scalars().numpy(), metrics, m_local)
+
+    @staticmethod
+    def _scalars_to_dict(sc, metrics, m_local):
         m = _dist.global_count(m_local)
         out = {"cost": float(sc[0]) / m}
         for metric in metrics:
