@@ -45,6 +45,7 @@ SIGNATURES = {
     "bf_act_backward": (_i, [_i, _vp, _vp, _vp, _sz, _vp]),
     "bf_dense_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "bf_dense_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "bf_dense_tma_supported": (_i, [_i] * 4),
     "bf_dense_forward_cl": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "bf_dense_backward_cl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "bf_conv_forward": (_i, [_vp, _vp, _vp, _vp] + [_i] * 11 + [_vp]),
@@ -82,8 +83,15 @@ SIGNATURES = {
     "bf_gru_forward": (_i, [_vp] * 7 + [_i] * 6 + [_vp]),
     "bf_gru_backward": (_i, [_vp] * 8 + [_i] * 6 + [_vp]),
     "bf_opt_step": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _vp]),
-    "bf_opt_step_allreduce": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _sz, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "bf_opt_step_allreduce": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _sz, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "bf_fill": (_i, [_vp, _sz, _f, _vp]),
+    "bf_dense_cl_supported": (_i, [_i, _i]),
     "bf_fitness_mlp": (_i, [_vp] * 4 + [_i] * 6 + [_vp]),
+    "bf_population_fitness": (_i, [_vp, _c.c_long, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "bf_population_relayout": (_i, [_vp, _c.c_long, _vp, _vp, _i, _i, _i, _vp]),
+    "bf_population_next_generation": (_i, [_vp, _vp, _c.c_long, _i, _i, _vp, _vp, _vp, _f, _c.c_uint, _c.c_uint, _vp, _vp, _vp,
+                                           _vp, _vp]),
+    "bf_gather_rows": (_i, [_vp, _vp, _vp, _i, _sz, _vp]),
 }
 
 

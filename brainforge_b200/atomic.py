@@ -42,8 +42,7 @@ class ActivationFunction:
 
     def backward(self, A):
         a = as_device(A)
-        ones = DeviceArray.empty_like(a)
-        call(L.bf_affine, a.pptr, ones.pptr, a.size, 0.0, 1.0, stream_ptr())
+        ones = DeviceArray.empty_like(a).fill(1.0)
         call(L.bf_act_backward, _lib.ACT[self.type], a.pptr, ones.pptr, ones.pptr, a.size, stream_ptr())
         return _ret(A, ones)
 
@@ -110,7 +109,7 @@ class DenseOp:
     def forward(X, W, b=None, activation="linear"):
         x, w = as_device(X), as_device(W)
         if x.cl_flat is not None:
-            if w.shape[1] <= 32 and x.shape[1] == w.shape[0]:
+            if w.shape[1] <= 32 and x.shape[1] == w.shape[0] and L.bf_dense_cl_supported(w.shape[0], w.shape[1]):
                 c, y, xx = x.cl_flat
                 bd = as_device(b) if b is not None else None
                 out = DeviceArray.empty(x.shape[0], w.shape[1])
@@ -132,7 +131,7 @@ class DenseOp:
     def backward(X, E, W, dW=None, db=None, accumulate=False, need_dX=True):
         x, e, w = as_device(X), as_device(E), as_device(W)
         if x.cl_flat is not None:
-            if w.shape[1] <= 32 and len(x) > 0:
+            if w.shape[1] <= 32 and len(x) > 0 and L.bf_dense_cl_supported(w.shape[0], w.shape[1]):
                 c, y, xx = x.cl_flat
                 m, n = x.shape[0], w.shape[1]
                 dW = DeviceArray.empty(*w.shape) if dW is None else dW
@@ -356,8 +355,7 @@ class PoolMask:
     def expand(self):
         im, ic, iy, ix = self.ashape
         if self.nhwc:   # scatter ones through the mask, then the usual layout change
-            ones = DeviceArray.empty_nhwc(im, ic, iy // self.fdim, ix // self.fdim)
-            call(L.bf_affine, ones.pptr, ones.pptr, ones.size, 0.0, 1.0, stream_ptr())
+            ones = DeviceArray.empty_nhwc(im, ic, iy // self.fdim, ix // self.fdim).fill(1.0)
             out = DeviceArray.empty_nhwc(im, ic, iy, ix)
             call(L.bf_pool_nhwc_backward, ones.pptr, self.wptr, _NULL, out.pptr, im, ic, iy, ix, self.fdim, stream_ptr())
             return out.to_nchw()
@@ -594,3 +592,59 @@ class LSTMOp:
              nablaW.ptr, nablab.ptr, T, B, D, H,
              _lib.ACT[self.activation], precision(), stream_ptr())
         return _ret(Z, dX, nablaW, nablab)
+
+
+# --------------------------------------------------------------------------- operand handling on the TF32 path
+_RZ, _RNA = ("rz", "rz"), ("rna", "rna")
+
+
+def tf32_operand_modes(kind, learn=True, **s):
+    """How the kernel family that `kind` + shape selects on the TF32 path hands its two operands to
+    `tcgen05.mma.kind::tf32`: {site: (mode_A, mode_B) | None}.  "rz": raw FP32 staged by TMA, the tensor core drops
+    the low 13 mantissa bits; "rna": rounded to nearest by the SIMT operand builder (cvt.rna.tf32.f32); None: the
+    site runs FP32 FMAs (no tensor core).  This is the documentation of record for the stated TF32 bounds
+    (DESIGN.md 4); tests/test_gpu_tf32_emulated.py feeds it to the emulating oracle.  `learn`: inside learn_batch
+    (first-layer filter gradient un-pools in-kernel) rather than op by op."""
+    if precision() != _lib.PREC["tf32"]:
+        return {}
+    if kind == "dense":
+        if s["n"] <= 32:
+            return {"dense.fwd": None, "dense.dW": None, "dense.dX": None}
+        return {site: (_RZ if L.bf_dense_tma_supported(s["m"], s["k"], s["n"], i) else _RNA)
+                for i, site in enumerate(("dense.fwd", "dense.dW", "dense.dX"))}
+    if kind == "conv":
+        route = ConvolutionOp._route(s.get("nhwc", False), s["ic"], s["iy"], s["ix"], s["nf"], s["fy"], s["fx"], "valid", "linear")
+        if route == "nhwc":
+            return {"conv.fwd": _RZ, "conv.dF": _RZ, "conv.dX": _RZ}
+        if route == "c3":
+            # forward: pixel stream and filter rounded while they are re-laid; filter gradient: patch rows rounded by the
+            # builder warps, E either rebuilt (rounded) by them from the pooling layer's delta (learn_batch) or a raw TMA
+            # box; the data gradient of a first layer runs on the NCHW gather kernel
+            return {"conv.fwd": _RNA, "conv.dF": _RNA if (learn and s.get("unpool", False)) else ("rna", "rz"), "conv.dX": _RNA}
+        return {"conv.fwd": _RNA, "conv.dF": _RNA, "conv.dX": _RNA}
+    if kind == "lstm":
+        zd = s["D"] + s["H"]
+        tma = zd % 4 == 0
+        return {"lstm.fwd": _RZ if tma else _RNA, "lstm.dZ": _RZ, "lstm.dW": _RZ if tma else _RNA}
+    raise ValueError(kind)
+
+
+def tf32_policy_for(net, learn=True):
+    """The per-layer form of `tf32_operand_modes` for a connected network: a callable (site, layer_index) ->
+    (mode_A, mode_B) | None with layer_index counting the layers behind the input layer from 0."""
+    from .layers.tensor import ConvLayer
+    table = {}
+    layers = net.layers.layers[1:]
+    for i, layer in enumerate(layers):
+        name = type(layer).__name__
+        if name == "Dense":
+            table[i] = tf32_operand_modes("dense", m=1 << 20, k=layer.weights.shape[0], n=layer.neurons)
+        elif isinstance(layer, ConvLayer):
+            ic, iy, ix = layer.inshape[-3:]
+            prev_cl = i > 0 and any(isinstance(p, ConvLayer) for p in layers[:i])
+            pool, _ = layer._pool_after()
+            table[i] = tf32_operand_modes("conv", learn=learn, ic=ic, iy=iy, ix=ix, nf=layer.nfilters, fy=layer.fy, fx=layer.fx,
+                                          nhwc=prev_cl, unpool=pool is not None and i == 0 and layer.fuse_pool)
+        elif name == "LSTM":
+            table[i] = tf32_operand_modes("lstm", D=layer.inshape[-1], H=layer.neurons)
+    return lambda site, li: table.get(li, {}).get(site)

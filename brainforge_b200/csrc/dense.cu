@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include <stdint.h>
 #include "gemm_umma.cuh"
+#include "gemm_tma.cuh"
 
 namespace bf {
 
@@ -325,11 +326,42 @@ static int launch_skinny_bwd(const float* X, const float* E, const float* W, flo
   return launch_splitk_reduce((const float*)ws, dW, db, k + 1, n, k, chunks, accumulate, n, 1, s);
 }
 
+// (rows x cols) -> (cols x rows): W^T as the K-major B operand of the TMA-fed forward GEMM
+__global__ void dense_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? __ldg(in + (size_t)r * cols + c) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// Which of the three contractions of a dense layer with n > 32 columns run on the TMA-fed tcgen05 GEMMs (operands
+// staged by TMA exactly as stored, north_star) rather than on the gather-staged core: 0 = forward (K = k), 1 = weight
+// gradient (both operands MN-major, K = m), 2 = data gradient (K = n).
+static inline bool dense_tma_site(int m, int k, int n, int site) {
+  if (tma_encode_fn() == nullptr || getenv("BF_DENSE_GATHER") != nullptr || m < 1) return false;
+  if (site == 0) return (k & 3) == 0 && k >= 4;
+  if (site == 1) return (k & 3) == 0 && (n & 3) == 0;
+  return (n & 3) == 0 && n >= 4;
+}
+
 }  // namespace bf
 
 using namespace bf;
 
 extern "C" {
+
+int bf_dense_cl_supported(int k, int n) { return skinny_ok(1, k, n) ? 1 : 0; }
+
+int bf_dense_tma_supported(int m, int k, int n, int site) {
+  return (n > 32 && site >= 0 && site <= 2 && dense_tma_site(m, k, n, site)) ? 1 : 0;
+}
 
 int bf_dense_forward(const float* X, const float* W, const float* b, float* out, int m, int k, int n, int act,
                      int precision, void* stream) {
@@ -341,7 +373,16 @@ int bf_dense_forward(const float* X, const float* W, const float* b, float* out,
   if (skinny_ok(m, k, n)) return launch_skinny_fwd(X, W, b, out, m, k, n, act, 0, 0, s);
   int ep_act = act == BF_ACT_SOFTMAX ? BF_ACT_LINEAR : act;
   int rc = BF_OK;
-  {
+  if (precision == BF_PREC_TF32 && dense_tma_site(m, k, n, 0) && ((uintptr_t)X & 15) == 0) {
+    // X is K-major as stored; W (k x n) becomes the K-major B operand by one small transpose into the workspace
+    void* ws = nullptr;
+    rc = workspace_require(((size_t)k * n * sizeof(float) + 255) & ~(size_t)255, &ws);
+    if (rc) return rc;
+    dense_transpose_kernel<<<dim3((n + 31) / 32, (k + 31) / 32), dim3(32, 8), 0, s>>>(W, (float*)ws, k, n);
+    BF_LAUNCH_CHECK();
+    EpiDenseFwd ep{out, b, n, ep_act};
+    rc = launch_gemm_tma(X, (const float*)ws, m, n, k, ep, s);
+  } else {
     LoadKContig al{X, (long)k};
     LoadMNContig bl{W, (long)n};
     EpiDenseFwd ep{out, b, n, ep_act};
@@ -370,7 +411,21 @@ int bf_dense_backward(const float* X, const float* E, const float* W, float* dW,
     void* ws = nullptr;
     rc = workspace_require((size_t)splits * rows * n * sizeof(float), &ws);
     if (rc) return rc;
-    if (m == 0) {
+    const bool tma_dw = precision == BF_PREC_TF32 && m > 0 && dense_tma_site(m, k, n, 1) && ((uintptr_t)X & 15) == 0 &&
+                        ((uintptr_t)E & 15) == 0;
+    if (tma_dw) {
+      // X (m x k) and E (m x n) are both MN-major for this contraction (K = m): read in place; db = column sums of E
+      // from the all-ones operand of the first M tile
+      const int tiles_mn = ((k + 127) / 128) * ((n + 127) / 128);
+      int want = num_sms() / tiles_mn;
+      if (want < 1) want = 1;
+      if (want > (m + 31) / 32) want = (m + 31) / 32;
+      const size_t pbytes = (size_t)want * rows * n * sizeof(float);
+      rc = workspace_require(pbytes, &ws);
+      if (rc) return rc;
+      rc = launch_gemm_tma_mn(X, E, k, n, m, (float*)ws, pbytes, &splits, s);
+      if (rc) return rc;
+    } else if (m == 0) {
       BF_CUDA(cudaMemsetAsync(ws, 0, (size_t)rows * n * sizeof(float), s));
     } else {
       LoadMNContigOnes al{X, (long)k, k};
@@ -384,10 +439,14 @@ int bf_dense_backward(const float* X, const float* E, const float* W, float* dW,
   }
   // dX = E @ W^T
   if (dX && m > 0) {
-    LoadKContig al{E, (long)n};
-    LoadKContig bl{W, (long)n};
     EpiPlain ep{dX, k};
-    rc = launch_gemm(precision, al, bl, ep, m, k, n, 1, (n + GEMM_KALIGN - 1) / GEMM_KALIGN * GEMM_KALIGN, 0, s);
+    if (precision == BF_PREC_TF32 && dense_tma_site(m, k, n, 2) && ((uintptr_t)E & 15) == 0 && ((uintptr_t)W & 15) == 0) {
+      rc = launch_gemm_tma(E, W, m, k, n, ep, s);       // E (m x n) and W (k x n) are both K-major as stored
+    } else {
+      LoadKContig al{E, (long)n};
+      LoadKContig bl{W, (long)n};
+      rc = launch_gemm(precision, al, bl, ep, m, k, n, 1, (n + GEMM_KALIGN - 1) / GEMM_KALIGN * GEMM_KALIGN, 0, s);
+    }
     if (rc) return rc;
   }
   return BF_OK;

@@ -252,14 +252,26 @@ __global__ void opt_kernel(float* __restrict__ W, float* __restrict__ G, float* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* __restrict__ x, size_t n, float v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] = v;
+}
+
 // Data-parallel step tail in ONE kernel: one-shot all-reduce of the flat gradient vector over peer memory (NVLink /
-// NVSwitch loads from every rank's symmetric buffer) fused with the optimizer update.
-//   every rank: barrier A -> g[i] = sum over ranks r = 0..world-1 of peer[r][i] (fixed order: all ranks compute the
-//   same bits) -> W, state updated for i < n_params -> barrier B (peers are done reading my buffer) -> my gradient
-//   slice is cleared (or set to the sum), the step scalars at the tail (cost sum, hits) are replaced by their sums.
-// Each CTA owns a contiguous slice and its own pair of flag slots in the signal pads, so there is no grid-wide sync:
-// slot (block * world + source rank) of rank d's pad is written only by CTA `block` of rank `source`.  Flag values are
-// a per-CTA epoch kept in device memory (2e-1 for barrier A, 2e for B), so the kernel replays unchanged in a CUDA graph.
+// NVSwitch) fused with the optimizer update.  PUSH form, one synchronisation per step:
+//   every rank r, CTA b (owner of slice b of the vector on every rank):
+//     1. stores its slice of G into slot r of every peer's receive buffer R[parity][r][.] (remote stores are fire and
+//        forget), clears (or keeps) its own G slice, and -- tail CTA -- posts its local sample count in the tail;
+//     2. release-stores its epoch into flag (b, r) of every peer's signal pad;
+//     3. waits until its own flags (b, 0..world-1) have reached the epoch: all world copies of slice b have landed;
+//     4. sums them in rank order (every rank adds the same numbers in the same order: identical bits everywhere),
+//        applies the optimizer to W[slice], writes the summed step scalars back to the tail of G.
+// The receive buffer is double-buffered by epoch parity: a peer can run at most one step ahead (it needs this rank's
+// next push to finish its own next step), so its next push lands in the other half while this rank is still summing.
+// The previous pull form needed a second barrier ("peers are done reading my G") before G could be reused.
+// A peer that never arrives (crashed rank, mismatched call sequence) must not wedge the GPU or corrupt the replica:
+// after ~10 s the CTA gives up, leaves W and the optimizer state of its slice untouched and raises *timeout (a word
+// in mapped host memory that the host checks when it reads the step's scalars).
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -268,38 +280,21 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float4 ld_peer4(const float* p) {      // never served from this SM's L1
+__device__ __forceinline__ float4 ld_recv4(const float* p) {      // written by a peer: never served from this SM's L1
   float4 v;
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void peer_barrier(unsigned* const* pads, int rank, int world, unsigned value, unsigned* timed_out) {
-  __syncthreads();
-  if ((int)threadIdx.x < world) {
-    __threadfence_system();
-    const int t = threadIdx.x;
-    st_release_sys(pads[t] + (size_t)blockIdx.x * world + rank, value);
-    const unsigned* mine = pads[rank] + (size_t)blockIdx.x * world + t;
-    // a peer that never arrives (crashed rank, mismatched call sequence) must not wedge the GPU: give up after ~10 s
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(mine) - value) < 0) {
-      if (clock64() - t0 > 20000000000LL) {
-        if (timed_out) *timed_out = 1u;
-        break;
-      }
-    }
-  }
-  __syncthreads();
-}
 
 constexpr int AR_MAX_WORLD = 16;
 struct ArParams {
-  float* const* peers;        // device array [world] of every rank's gradient buffer (mine included)
-  unsigned* const* pads;      // device array [world] of signal pads
-  unsigned* epoch;            // [gridDim.x + 1] local per-CTA epochs; the last word is set if a barrier timed out
-  float* gsum;                // local scratch [n_total]
+  float* const* recv;         // device array [world]: every rank's receive buffer R[2][world][n_total] (mine included)
+  unsigned* const* pads;      // device array [world] of signal pads, [blocks][world] words each
+  unsigned* epoch;            // [gridDim.x] local per-CTA epochs (device memory: the kernel replays unchanged in a CUDA graph)
+  unsigned* timeout;          // one word, mapped host memory: set when a peer failed to arrive
   int rank, world;
   size_t n_params, n_total;   // multiples of 4
+  float m_local;              // this rank's sample count, posted in tail slot 2 (the sum lets the host detect uneven shards)
 };
 
 template <int KIND, bool HAS1, bool HAS2>
@@ -307,22 +302,54 @@ __global__ void __launch_bounds__(256)
 opt_allreduce_kernel(float* __restrict__ W, float* __restrict__ G, float* __restrict__ S1, float* __restrict__ S2,
                      ArParams p, OptHP h, int zero_grad) {
   __shared__ unsigned s_epoch;
-  if (threadIdx.x == 0) s_epoch = ++p.epoch[blockIdx.x];
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) { s_epoch = ++p.epoch[blockIdx.x]; s_ok = 1; }
   __syncthreads();
   const unsigned e = s_epoch;
   const size_t n4 = p.n_total >> 2, np4 = p.n_params >> 2;
   const size_t per = (n4 + gridDim.x - 1) / gridDim.x;
   const size_t lo = per * blockIdx.x, hi = lo + per < n4 ? lo + per : n4;
-  peer_barrier(p.pads, p.rank, p.world, 2u * e - 1u, p.epoch + gridDim.x);
+  const size_t half = (size_t)p.world * p.n_total;                  // floats per parity half of a receive buffer
+  const size_t my_slot = (size_t)(e & 1u) * half + (size_t)p.rank * p.n_total;
+  float4* G4 = reinterpret_cast<float4*>(G);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // 1. push
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float4 g = G4[i];
+    if (i == np4) g.z = p.m_local;                                  // tail: [cost sum, hits, local m, -]
+    for (int d = 0; d < p.world; ++d) {
+      const int dst = (p.rank + d) % p.world;                       // start with myself, spread the peers
+      *reinterpret_cast<float4*>(p.recv[dst] + my_slot + 4 * i) = g;
+    }
+    if (zero_grad && i < np4) G4[i] = zero4;
+  }
+  // 2. signal, 3. wait
+  __syncthreads();
+  if ((int)threadIdx.x < p.world) {
+    __threadfence_system();
+    const int t = threadIdx.x;
+    st_release_sys(p.pads[t] + (size_t)blockIdx.x * p.world + p.rank, e);
+    const unsigned* mine = p.pads[p.rank] + (size_t)blockIdx.x * p.world + t;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - e) < 0) {
+      if (clock64() - t0 > 20000000000LL) {
+        s_ok = 0;
+        *reinterpret_cast<volatile unsigned*>(p.timeout) = 1u;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (!s_ok) return;                                                // replica left untouched; the host raises
+  // 4. sum in rank order + update
   float4* W4 = reinterpret_cast<float4*>(W);
   float4* S14 = reinterpret_cast<float4*>(S1);
   float4* S24 = reinterpret_cast<float4*>(S2);
-  float4* GS4 = reinterpret_cast<float4*>(p.gsum);
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* R = p.recv[p.rank] + (size_t)(e & 1u) * half;
   for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     float4 g = zero4;
     for (int r = 0; r < p.world; ++r) {
-      const float4 v = ld_peer4(p.peers[r] + 4 * i);
+      const float4 v = ld_recv4(R + (size_t)r * p.n_total + 4 * i);
       g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
     }
     if (i < np4) {
@@ -335,12 +362,11 @@ opt_allreduce_kernel(float* __restrict__ W, float* __restrict__ G, float* __rest
       W4[i] = w;
       if (HAS1) S14[i] = a;
       if (HAS2) S24[i] = b;
+      if (!zero_grad) G4[i] = g;
+    } else {
+      G4[i] = g;                                                    // summed step scalars
     }
-    GS4[i] = g;
   }
-  peer_barrier(p.pads, p.rank, p.world, 2u * e, p.epoch + gridDim.x);
-  float4* G4 = reinterpret_cast<float4*>(G);
-  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) G4[i] = (zero_grad && i < np4) ? zero4 : GS4[i];
 }
 
 }  // namespace bf
@@ -526,22 +552,22 @@ int bf_mul_rowmask(const float* x, const float* m, float* out, size_t rows, size
 // results of that step are then undefined), gsum a local scratch of n_total floats.  Elements [n_params, n_total) (the step scalars) are
 // summed but not optimised.  Every rank must make the same sequence of calls with the same `blocks`.
 int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float* s2, size_t n_params, size_t n_total, float eta,
-                          float m, float hp0, float hp1, float hp2, int zero_grad, void* const* peers, void* const* pads,
-                          unsigned* epoch, float* gsum, int rank, int world, int blocks, void* stream) {
-  BF_REQUIRE(W && G && peers && pads && epoch && gsum, BF_ERR_ARG, "bf_opt_step_allreduce: null pointer");
+                          float m, float hp0, float hp1, float hp2, int zero_grad, void* const* recv, void* const* pads,
+                          unsigned* epoch, unsigned* timeout, float m_local, int rank, int world, int blocks, void* stream) {
+  BF_REQUIRE(W && G && recv && pads && epoch && timeout, BF_ERR_ARG, "bf_opt_step_allreduce: null pointer");
   BF_REQUIRE(world >= 1 && world <= AR_MAX_WORLD && rank >= 0 && rank < world && blocks >= 1, BF_ERR_ARG,
              "bf_opt_step_allreduce: bad rank/world/blocks %d/%d/%d", rank, world, blocks);
-  BF_REQUIRE((n_params & 3) == 0 && (n_total & 3) == 0 && n_params <= n_total && n_total > 0, BF_ERR_ARG,
-             "bf_opt_step_allreduce: sizes must be multiples of 4");
-  BF_REQUIRE(aligned16(W) && aligned16(G) && aligned16(gsum) && (!s1 || aligned16(s1)) && (!s2 || aligned16(s2)), BF_ERR_ARG,
+  BF_REQUIRE((n_params & 3) == 0 && (n_total & 3) == 0 && n_params + 4 <= n_total, BF_ERR_ARG,
+             "bf_opt_step_allreduce: sizes must be multiples of 4 with a scalar tail behind the parameters");
+  BF_REQUIRE(aligned16(W) && aligned16(G) && (!s1 || aligned16(s1)) && (!s2 || aligned16(s2)), BF_ERR_ARG,
              "bf_opt_step_allreduce: buffers must be 16-byte aligned");
   BF_REQUIRE(m > 0.f, BF_ERR_ARG, "bf_opt_step_allreduce: m must be positive");
   cudaStream_t s = as_stream(stream);
   OptHP h;
   h.eta = eta; h.eta_m = eta / m; h.inv_m = 1.0f / m; h.hp0 = hp0; h.hp1 = hp1; h.hp2 = hp2;
   ArParams p;
-  p.peers = reinterpret_cast<float* const*>(peers); p.pads = reinterpret_cast<unsigned* const*>(pads); p.epoch = epoch;
-  p.gsum = gsum; p.rank = rank; p.world = world; p.n_params = n_params; p.n_total = n_total;
+  p.recv = reinterpret_cast<float* const*>(recv); p.pads = reinterpret_cast<unsigned* const*>(pads); p.epoch = epoch;
+  p.timeout = timeout; p.rank = rank; p.world = world; p.n_params = n_params; p.n_total = n_total; p.m_local = m_local;
 #define BF_AR(K_, H1_, H2_) opt_allreduce_kernel<K_, H1_, H2_><<<blocks, 256, 0, s>>>(W, G, s1, s2, p, h, zero_grad)
   switch (kind) {
     case BF_OPT_SGD: BF_AR(BF_OPT_SGD, false, false); break;
@@ -563,6 +589,21 @@ int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float* s2, si
     default: return fail(BF_ERR_ARG, "bf_opt_step_allreduce: unknown optimizer kind %d", kind);
   }
 #undef BF_AR
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+/* memory fills that do not read the destination (a NaN in it must not survive): zero through the copy engine, any other
+ * constant through a store-only kernel */
+int bf_fill(float* x, size_t n, float value, void* stream) {
+  if (n == 0) return BF_OK;
+  BF_REQUIRE(x, BF_ERR_ARG, "bf_fill: null pointer");
+  cudaStream_t s = as_stream(stream);
+  if (value == 0.0f) {
+    BF_CUDA(cudaMemsetAsync(x, 0, n * sizeof(float), s));
+    return BF_OK;
+  }
+  fill_kernel<<<ew_grid(n, 256), 256, 0, s>>>(x, n, value);
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

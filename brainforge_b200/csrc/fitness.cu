@@ -88,7 +88,8 @@ fitness_head_kernel(const float* __restrict__ Hbuf, const float* __restrict__ G,
 
 // fitness_tma.cu: the same computation on TMA-fed tcgen05 with the whole network in the epilogue
 bool fitness_tma_supported(int P, int N, int nin, int nh, int nout);
-int fitness_tma(const float* genomes, const float* X, const float* Y, float* fitness, int P, int N, int nin, int nh, int nout,
+int fitness_tma(const float* genomes, long ldg, const float* bt_resident, const int* inds, const float* X, const float* Y,
+                float* fitness, int P, int N, int nin, int nh, int nout,
                 cudaStream_t s);
 
 }  // namespace bf
@@ -105,7 +106,7 @@ int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* 
   if (P == 0) return BF_OK;
   cudaStream_t s = as_stream(stream);
   if (precision == BF_PREC_TF32 && fitness_tma_supported(P, N, nin, nh, nout) && getenv("BF_FITNESS_GATHER") == nullptr)
-    return fitness_tma(genomes, X, Y, fitness, P, N, nin, nh, nout, s);
+    return fitness_tma(genomes, (long)nin * nh + nh + (long)nh * nout + nout, nullptr, nullptr, X, Y, fitness, P, N, nin, nh, nout, s);
   const long loci = (long)nin * nh + nh + (long)nh * nout + nout;
   size_t per_ind = (size_t)nh * N * sizeof(float);
   size_t have = workspace_bytes();

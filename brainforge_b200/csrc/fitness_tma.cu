@@ -26,31 +26,43 @@ constexpr int FT_PARAM_F = FT_HP + FT_HP * FT_MAX_OUT + FT_MAX_OUT;   // b1 | W2
 
 struct FtParams {
   int P, N, nin, nh, nout, nkb, m_passes, n_tiles, ntiles;
-  long loci;
+  long loci;            // floats between consecutive genome rows of G (>= the number of loci: padded stores allowed)
   const float* G;
   const float* Y;
   float* partial;       // [P][m_passes * 8]
+  const int* inds;      // optional: slot j evaluates genome inds[j] (a subset / permutation of the store); null: j
+  int bt_by_genome;     // the K-major operand is the RESIDENT one (64 rows per genome id) instead of this call's scratch (per slot)
 };
+__device__ __forceinline__ int ft_genome(const FtParams& p, int slot) {
+  if (slot >= p.P) slot = p.P - 1;          // the padding slot of an odd count re-reads the last genome (result dropped)
+  return p.inds ? __ldg(p.inds + slot) : slot;
+}
 
 // Bt[p*64 + h][k] = (G[p][k*nh + h] - 0.5) * 20, zero padding for h >= nh and p >= P: every genome's (nin x nh) first
 // layer transposed through a padded shared-memory tile, so that the GEMM's B operand is K-major like A
 // (a variant moving 112-row chunks per block with per-element index divisions measured 1.5x slower)
-__global__ void fitness_relayout_kernel(const float* __restrict__ G, float* __restrict__ Bt, int P, int nin, int nh, long loci) {
+// `inds` (optional): block z handles genome inds[z]; `by_genome`: its rows go to the genome's own place in a resident
+// operand (Bt[g*64 + h]) instead of slot z of a scratch one.
+__global__ void fitness_relayout_kernel(const float* __restrict__ G, float* __restrict__ Bt, int P, int nin, int nh, long loci,
+                                        const int* __restrict__ inds, int by_genome) {
   __shared__ float tile[32][33];
-  const int p = blockIdx.z, k0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+  const int slot = blockIdx.z, k0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+  const int p = (slot < P && inds) ? __ldg(inds + slot) : slot;
+  const int prow = by_genome ? p : slot;
+  if (by_genome && slot >= P) return;
   const int tx = threadIdx.x, ty = threadIdx.y;     // 32 x 8
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int k = k0 + ty + j, h = h0 + tx;
     float v = 0.f;
-    if (p < P && k < nin && h < nh) v = (__ldg(G + (size_t)p * loci + (size_t)k * nh + h) - 0.5f) * 20.f;
+    if (slot < P && k < nin && h < nh) v = (__ldg(G + (size_t)p * loci + (size_t)k * nh + h) - 0.5f) * 20.f;
     tile[ty + j][tx] = v;
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int h = h0 + ty + j, k = k0 + tx;
-    if (k < nin) Bt[((size_t)p * FT_HP + h) * nin + k] = __uint_as_float(to_tf32(tile[tx][ty + j]));
+    if (k < nin) Bt[((size_t)prow * FT_HP + h) * nin + k] = __uint_as_float(to_tf32(tile[tx][ty + j]));
   }
 }
 
@@ -85,6 +97,8 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     int g = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int nt = tile / p.m_passes, mp = tile - nt * p.m_passes;       // consecutive tiles share the genome columns
+      const int r0 = (p.bt_by_genome ? ft_genome(p, nt * 2) : nt * 2) * FT_HP;
+      const int r1 = (p.bt_by_genome ? ft_genome(p, nt * 2 + 1) : nt * 2 + 1) * FT_HP;
       for (int kb = 0; kb < p.nkb; ++kb, ++g) {
         const int s = g % FT_STAGES, u = g / FT_STAGES;
         if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
@@ -93,7 +107,8 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           mbar_expect_tx(&full[s], FT_STAGE_BYTES);
           tma_load_2d(st, &mapA, &full[s], kb * 32, mp * 256);
           tma_load_2d(st + 128 * 128, &mapA, &full[s], kb * 32, mp * 256 + 128);
-          tma_load_2d(st + FT_A_BYTES, &mapB, &full[s], kb * 32, nt * 128);
+          tma_load_2d(st + FT_A_BYTES, &mapB, &full[s], kb * 32, r0);                     // 64 hidden rows of genome 0 of the tile
+          tma_load_2d(st + FT_A_BYTES + FT_HP * 128, &mapB, &full[s], kb * 32, r1);       // ... of genome 1
         }
       }
     }
@@ -132,7 +147,8 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int set = it & 1, tu = it >> 1;
       const int nt = tile / p.m_passes, mp = tile - nt * p.m_passes;
-      const int pg = nt * 2 + gi;
+      const int pg = nt * 2 + gi;                        // slot in this call's list; its genome row in the store:
+      const size_t grow = (size_t)ft_genome(p, pg) * p.loci;
       // second-layer parameters of the group's genome -> shared memory (as_weights applied), while the MMAs run
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");       // previous tile's readers are done
       // (b1 | W2 | b2 are one contiguous run of nh + nh*nout + nout loci behind W1: coalesced reads, scattered into the
@@ -143,7 +159,7 @@ fitness_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
       for (int q = 0; q < PF; ++q) {
         const int j = gt + q * 128;
-        pv[q] = (j < ntail && pg < p.P) ? __ldg(p.G + (size_t)pg * p.loci + (size_t)p.nin * p.nh + j) : 0.5f;
+        pv[q] = (j < ntail && pg < p.P) ? __ldg(p.G + grow + (size_t)p.nin * p.nh + j) : 0.5f;
       }
 #pragma unroll
       for (int q = 0; q < PF; ++q) {
@@ -231,28 +247,29 @@ bool fitness_tma_supported(int P, int N, int nin, int nh, int nout) {
   return tma_encode_fn() != nullptr && nh <= FT_HP && nout <= FT_MAX_OUT && (nin % 4) == 0 && P >= 1 && N >= 1;
 }
 
-int fitness_tma(const float* genomes, const float* X, const float* Y, float* fitness, int P, int N, int nin, int nh, int nout,
-                cudaStream_t s) {
-  const long loci = (long)nin * nh + nh + (long)nh * nout + nout;
+int fitness_tma(const float* genomes, long ldg, const float* bt_resident, const int* inds, const float* X, const float* Y,
+                float* fitness, int P, int N, int nin, int nh, int nout, cudaStream_t s) {
   const int Ppad = (P + 1) & ~1;
   FtParams p;
-  p.P = P; p.N = N; p.nin = nin; p.nh = nh; p.nout = nout; p.loci = loci;
+  p.P = P; p.N = N; p.nin = nin; p.nh = nh; p.nout = nout; p.loci = ldg;
   p.nkb = (nin + 31) / 32;
   p.m_passes = (N + 255) / 256;
   p.n_tiles = Ppad / 2;
   p.ntiles = p.n_tiles * p.m_passes;
-  p.G = genomes; p.Y = Y;
-  const size_t bt_bytes = ((size_t)nin * Ppad * FT_HP * 4 + 255) & ~(size_t)255;
+  p.G = genomes; p.Y = Y; p.inds = inds; p.bt_by_genome = bt_resident ? 1 : 0;
+  const size_t bt_bytes = bt_resident ? 0 : (((size_t)nin * Ppad * FT_HP * 4 + 255) & ~(size_t)255);
   const size_t part_bytes = (size_t)P * p.m_passes * 8 * 4;
   void* ws = nullptr;
   int rc = workspace_require(bt_bytes + part_bytes, &ws);
   if (rc) return rc;
-  float* Bt = (float*)ws;
+  const float* Bt = bt_resident ? bt_resident : (const float*)ws;
   p.partial = (float*)((char*)ws + bt_bytes);
-  BF_REQUIRE(((uintptr_t)X & 15) == 0 && (long long)Ppad * FT_HP < 2147483647LL, BF_ERR_ARG, "bf_fitness_mlp: operand alignment / size");
+  BF_REQUIRE(((uintptr_t)X & 15) == 0 && ((uintptr_t)Bt & 15) == 0, BF_ERR_ARG, "bf_fitness_mlp: operand alignment");
   BF_REQUIRE(Ppad <= 65535, BF_ERR_ARG, "bf_fitness_mlp: more than 65534 genomes per call");
-  fitness_relayout_kernel<<<dim3((nin + 31) / 32, FT_HP / 32, Ppad), dim3(32, 8), 0, s>>>(genomes, Bt, P, nin, nh, loci);
-  BF_LAUNCH_CHECK();
+  if (!bt_resident) {
+    fitness_relayout_kernel<<<dim3((nin + 31) / 32, FT_HP / 32, Ppad), dim3(32, 8), 0, s>>>(genomes, (float*)ws, P, nin, nh, ldg, inds, 0);
+    BF_LAUNCH_CHECK();
+  }
   CUtensorMap mA, mB;
   {
     uint64_t dims[2] = {(uint64_t)nin, (uint64_t)N};
@@ -262,9 +279,11 @@ int fitness_tma(const float* genomes, const float* X, const float* Y, float* fit
       return fail(BF_ERR_CUDA, "bf_fitness_mlp: cuTensorMapEncodeTiled failed (X)");
   }
   {
-    uint64_t dims[2] = {(uint64_t)nin, (uint64_t)Ppad * FT_HP};
+    // rows beyond the tensor are never addressed (slots are clamped), so the extent only has to cover the operand
+    uint64_t dims[2] = {(uint64_t)nin, (uint64_t)2147483647ull / (uint64_t)(nin > 0 ? nin : 1) / 8ull * 8ull};
+    if (!bt_resident) dims[1] = (uint64_t)Ppad * FT_HP;
     uint64_t str[1] = {(uint64_t)nin};
-    uint32_t box[2] = {32, 128};
+    uint32_t box[2] = {32, FT_HP};
     if (!tma_make_map(&mB, Bt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, false))
       return fail(BF_ERR_CUDA, "bf_fitness_mlp: cuTensorMapEncodeTiled failed (genome operand)");
   }
@@ -282,6 +301,15 @@ int fitness_tma(const float* genomes, const float* X, const float* Y, float* fit
   fitness_finish_kernel<<<(P + 127) / 128, 128, 0, s>>>(p.partial, fitness, P, p.m_passes * 8, N);
   BF_LAUNCH_CHECK();
   set_last_path(2);
+  return BF_OK;
+}
+
+// (re)build the resident K-major first-layer operand for the listed genomes (all P when inds is null)
+int fitness_relayout_resident(const float* genomes, long ldg, float* bt, const int* inds, int n, int nin, int nh, cudaStream_t s) {
+  if (n <= 0) return BF_OK;
+  BF_REQUIRE(n <= 65535, BF_ERR_ARG, "bf_population_relayout: more than 65535 genomes per call");
+  fitness_relayout_kernel<<<dim3((nin + 31) / 32, FT_HP / 32, n), dim3(32, 8), 0, s>>>(genomes, bt, n, nin, nh, ldg, inds, 1);
+  BF_LAUNCH_CHECK();
   return BF_OK;
 }
 

@@ -176,7 +176,7 @@ struct GmParams {
   float* partial;
 };
 
-__global__ void __launch_bounds__(GM_THREADS, 1)
+static __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tma_mn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GmParams p) {
   extern __shared__ int dyn_smem[];
   __shared__ __align__(8) uint64_t full[GM_STAGES], empty[GM_STAGES], done;

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-_state = {"workspace": None, "precision": _lib.PREC["fp32"]}
+_state = {"workspace": None, "precision": _lib.PREC["fp32"], "ws_generation": 0, "ws_retired": []}
 DEFAULT_WORKSPACE = 64 << 20
 
 
@@ -45,11 +45,22 @@ def _ensure_workspace(nbytes):
             raise RuntimeError("workspace must be sized before CUDA-graph capture (run the step once eagerly)")
         nbytes = max(int(nbytes), DEFAULT_WORKSPACE)
         torch.cuda.synchronize()
-        _state["workspace"] = None
+        if ws is not None:
+            # captured CUDA graphs have the old block's address baked into their kernels: it must stay allocated (and
+            # unused by anybody else) until those graphs are gone.  `workspace_generation()` tells graph owners to
+            # re-capture; they call `release_retired_workspaces()` once none of their graphs is older than that.
+            _state["ws_retired"].append(ws)
         ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         _state["workspace"] = ws
+        _state["ws_generation"] += 1
         _lib.check(_lib.lib.bf_set_workspace(ctypes.c_void_p(ws.data_ptr()), ws.numel()))
     return ws
+
+
+def workspace_generation():
+    """Bumped every time the scratch workspace is re-allocated: a CUDA graph captured under an older generation
+    references a retired block and has to be captured again before its next replay."""
+    return _state["ws_generation"]
 
 
 def call(fn, *args, tag=None):
@@ -259,14 +270,20 @@ class DeviceArray:
             call(_lib.lib.bf_act_forward, _lib.ACT["linear"], self.pptr, out.pptr, self.size, stream_ptr())
         return out
 
-    def fill_zero(self):
+    def fill(self, value):
+        """Every element = value, without reading the old contents (a NaN / Inf already there does not survive)."""
         if self.size:
-            call(_lib.lib.bf_affine, self.pptr, self.pptr, self.size, 0.0, 0.0, stream_ptr())
+            call(_lib.lib.bf_fill, self.pptr, self.size, float(value), stream_ptr())
         return self
+
+    def fill_zero(self):
+        return self.fill(0.0)
 
     def __imul__(self, scalar):
         # `layer.nabla_w *= 0` (learner/backpropagation.py:72-73) and friends
         s = float(scalar)
+        if s == 0.0:
+            return self.fill_zero()      # the reference's idiom for zero_gradients: must also clear non-finite values
         if self.size:
             call(_lib.lib.bf_affine, self.pptr, self.pptr, self.size, s, 0.0, stream_ptr())
         return self

@@ -43,46 +43,54 @@ def allreduce_sum(flat):
 
 
 class SymmetricBuffer:
-    """A float32 vector allocated in NVLink-mapped symmetric memory: every rank can load every other rank's copy.
-    `torch.distributed._symmetric_memory` does the allocation and the handle exchange (plumbing); the kernel that
-    uses the peer pointers is ours (`bf_opt_step_allreduce`)."""
-    BLOCKS = 32
+    """The receive side of the fused all-reduce + optimizer kernel (`bf_opt_step_allreduce`, push form): a float32
+    buffer of 2 (step parity) x world (source rank) x n slots in NVLink-mapped symmetric memory that every peer
+    stores its gradient vector into.  `torch.distributed._symmetric_memory` does the allocation and the handle
+    exchange (plumbing); the kernel that uses the peer pointers is ours."""
+    BLOCKS = 64
 
-    def __init__(self, tensor, handle):
+    def __init__(self, tensor, handle, n):
         self.t = tensor
         self.handle = handle
+        self.n = n
         self.rank, self.world = handle.rank, handle.world_size
         self.peers_dev = int(handle.buffer_ptrs_dev)
         self.pads_dev = int(handle.signal_pad_ptrs_dev)
         cap = int(handle.signal_pad_size) // (4 * self.world)
         self.blocks = max(1, min(self.BLOCKS, cap))
-        self.epoch = torch.zeros(self.blocks + 1, dtype=torch.int32, device=tensor.device)   # [-1]: barrier time-out flag
-        self.gsum = torch.zeros_like(tensor)
-
+        self.epoch = torch.zeros(self.blocks, dtype=torch.int32, device=tensor.device)
+        # barrier time-out word: mapped host memory, written by the kernel, read by the host for free
+        self.timeout = torch.zeros(4, dtype=torch.int32).pin_memory()
 
     def timed_out(self):
-        """True if a peer failed to reach a barrier of bf_opt_step_allreduce (host sync; for diagnostics)."""
-        return bool(int(self.epoch[-1].item()))
+        """True if a peer failed to reach the exchange of some step (valid once that step has been synchronised,
+        e.g. after its scalars were read back)."""
+        return bool(int(self.timeout[0]))
+
+    def check(self):
+        if self.timed_out():
+            raise RuntimeError("data-parallel step failed: a peer rank did not reach the gradient exchange within the "
+                               "time-out (crashed rank or mismatched learn_batch sequence); this replica was left un-updated")
 
 
 _symm_failed = False
 
 
-def symmetric_zeros(n):
-    """Collective (all ranks, same order): a zeroed symmetric float32 vector, or None when the job is single-rank, not
-    on NCCL, switched off (BF_FUSED_ALLREDUCE=0) or the platform has no peer mapping -- the caller then keeps the
-    NCCL all-reduce."""
+def symmetric_recv(n):
+    """Collective (all ranks, same order): the symmetric receive buffer for gradient vectors of n floats, or None when
+    the job is single-rank, not on NCCL, switched off (BF_FUSED_ALLREDUCE=0) or the platform has no peer mapping --
+    the caller then keeps the NCCL all-reduce."""
     global _symm_failed
     if world_size() == 1 or _symm_failed or td.get_backend() != "nccl" or os.environ.get("BF_FUSED_ALLREDUCE", "1") == "0":
         return None
     try:
         import torch.distributed._symmetric_memory as symm_mem
-        t = symm_mem.empty(n, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        t = symm_mem.empty(2 * world_size() * n, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
         handle = symm_mem.rendezvous(t, td.group.WORLD)
         t.zero_()
         torch.cuda.synchronize()
         td.barrier()
-        return SymmetricBuffer(t, handle)
+        return SymmetricBuffer(t, handle, n)
     except Exception as exc:   # noqa: BLE001  (any failure here only costs the fast path)
         _symm_failed = True
         if rank() == 0:
@@ -92,7 +100,9 @@ def symmetric_zeros(n):
 
 
 def global_count(m_local):
-    """Sum of per-rank batch sizes (equal shards: m_local * world_size, no collective needed)."""
+    """Sum of per-rank batch sizes, assuming equal shards (m_local * world_size: no collective needed).  The step
+    itself carries every rank's true count in the scalar tail of the gradient vector, so `Backpropagation` detects
+    an uneven split when it reads the step's scalars back and raises instead of training with a wrong 1/m."""
     return m_local * world_size()
 
 

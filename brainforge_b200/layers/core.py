@@ -1,7 +1,7 @@
 """layers/core.py of the reference: Dense, Activation, InputLayer, Reshape, Flatten."""
 import numpy as np
 
-from .. import atomic
+from .. import atomic, _lib
 from ..util import white
 from ..device import DeviceArray
 from .abstract_layer import LayerBase, NoParamMixin, FFBase
@@ -117,7 +117,7 @@ class Reshape(NoParamMixin, LayerBase):
     def _fwd(self, x):
         nxt = self._next_layer
         if (x.nhwc and not self._standalone and len(self.shape) == 1 and type(nxt).__name__ == "Dense"
-                and nxt.neurons <= 32):
+                and nxt.neurons <= 32 and _lib.lib.bf_dense_cl_supported(int(np.prod(x.shape[1:])), nxt.neurons)):
             # channels-last block -> skinny Dense: no data moves; the Dense kernels index W through the (c,y,x) <-> (y,x,c)
             # permutation (bf_dense_forward_cl), so the layout-change pass disappears
             im, c, y, xx = x.shape

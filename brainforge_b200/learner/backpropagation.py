@@ -13,7 +13,7 @@ import torch
 
 from .abstract_learner import Learner
 from .. import _lib
-from ..device import DeviceArray, as_device, call, stream_ptr
+from ..device import DeviceArray, as_device, call, stream_ptr, workspace_generation
 from ..metrics import metrics as _metrics
 from ..optimizers import optimizers, GradientDescent
 from .. import dist as _dist
@@ -114,10 +114,12 @@ class Backpropagation(Learner):
         m_global = m_global_static if m_global_static is not None else _dist.global_count(m_local)
         if _dist.world_size() > 1:
             if update and self.layers.symm is not None:
-                # one kernel: sum of every rank's gradient vector (and step scalars) over NVLink peer loads + update
-                self.update(m_global, symm=self.layers.symm)
+                # one kernel: every rank's gradient vector (and step scalars) pushed to all peers over NVLink, summed, + update
+                self.update(m_global, symm=self.layers.symm, m_local=m_local)
                 return
-            # gradients + step scalars in ONE collective (scalars alone when no update follows)
+            # gradients + step scalars in ONE collective (scalars alone when no update follows); slot 2 carries this
+            # rank's sample count so that the host can tell an uneven split from the sum
+            sc[2:3].fill(m_local)
             _dist.allreduce_sum(self.layers.flat_grads if update else sc)
         if update:
             self.update(m_global)
@@ -125,9 +127,16 @@ class Backpropagation(Learner):
     def _read_scalars(self, metrics, m_local):
         return self._scalars_to_dict(self.layers.scalars().numpy(), metrics, m_local)
 
-    @staticmethod
-    def _scalars_to_dict(sc, metrics, m_local):
+    def _scalars_to_dict(self, sc, metrics, m_local):
         m = _dist.global_count(m_local)
+        if _dist.world_size() > 1:
+            symm = self.layers.symm
+            if symm is not None:
+                symm.check()         # a peer missed the exchange: this replica skipped the update (raises)
+            if int(round(float(sc[2]))) != m:
+                raise ValueError("data-parallel learn_batch needs equal shards on every rank: the ranks hold %d samples in "
+                                 "total, this rank's %d x world_size %d = %d was used as the batch size of the update"
+                                 % (int(round(float(sc[2]))), m_local, _dist.world_size(), m))
         out = {"cost": float(sc[0]) / m}
         for metric in metrics:
             out[str(metric).lower()] = float(sc[1]) / m
@@ -165,6 +174,8 @@ class Backpropagation(Learner):
             return lambda: self._read_scalars(metrics, m_local)
         fill(entry["x"], X)
         fill(entry["y"], Y)
+        if entry["graph"] is not None and entry["ws_gen"] != workspace_generation():
+            entry["graph"] = None     # the scratch workspace moved since the capture: its old address is baked into the graph
         if entry["graph"] is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -174,7 +185,7 @@ class Backpropagation(Learner):
                 with torch.cuda.graph(g, stream=side):
                     self._step(entry["x"], entry["y"], None, metrics, update, m_local, entry["m_global"])
             torch.cuda.current_stream().wait_stream(side)
-            entry["graph"] = g
+            entry["graph"], entry["ws_gen"] = g, workspace_generation()
         entry["graph"].replay()
         return lambda: self._read_scalars(metrics, m_local)
 
@@ -193,7 +204,7 @@ class Backpropagation(Learner):
         out = self._bwd(as_device(error) if isinstance(error, DeviceArray) else DeviceArray.from_host(error))
         return out if isinstance(error, DeviceArray) else out.numpy()
 
-    def update(self, m, symm=None):
+    def update(self, m, symm=None, m_local=None):
         """learner/backpropagation.py:37-42 without the host round trip: one fused kernel reads W, g (and
         the optimizer state), writes W (and state) and clears g (zero_gradients, :68-73).  With `symm` (data-parallel
         jobs) the same kernel first sums the gradient vectors of all ranks through their peer-mapped buffers."""
@@ -201,7 +212,8 @@ class Backpropagation(Learner):
         L.flatten_parameters()
         n = L.flat_size
         if symm is not None:
-            self.optimizer.optimize_allreduce(L.flat_weights, L.flat_grads, n, m, symm)
+            self.optimizer.optimize_allreduce(L.flat_weights, L.flat_grads, n, m, symm,
+                                              m if m_local is None else m_local)
             return
         self.optimizer.optimize(L.flat_weights[0:n], L.flat_grads[0:n], m, zero_grad=True)
 

@@ -74,10 +74,10 @@ class LayerStack:
         self._scalar_off = total
         total += SEG_ALIGN
         W = torch.zeros(total, dtype=torch.float32, device="cuda")
-        # data-parallel jobs keep the gradient vector in symmetric (peer-mapped) memory: the step tail then is one
-        # kernel that sums every rank's copy over NVLink and applies the optimizer (bf_opt_step_allreduce)
-        self.symm = _dist.symmetric_zeros(total)
-        G = self.symm.t if self.symm is not None else torch.zeros(total, dtype=torch.float32, device="cuda")
+        # data-parallel jobs own a symmetric (peer-mapped) receive buffer: the step tail then is one kernel that pushes
+        # the gradient vector to every rank over NVLink, sums the copies and applies the optimizer (bf_opt_step_allreduce)
+        self.symm = _dist.symmetric_recv(total)
+        G = torch.zeros(total, dtype=torch.float32, device="cuda")
         for layer, wname, gname, o, size in segs:
             w_old, g_old = getattr(layer, wname), getattr(layer, gname)
             W[o:o + size].copy_(w_old.t.reshape(-1))

@@ -56,14 +56,15 @@ class GradientDescent(Optimizer):
              float(hp0), float(hp1), float(hp2), 1 if zero_grad else 0, stream_ptr())
         return Wd.numpy().reshape(np.shape(W)) if host else Wd
 
-    def optimize_allreduce(self, W, G, n_params, m, symm):
-        """Data-parallel step: G (this rank's symmetric gradient vector, step scalars at its tail) is summed over all
-        ranks and the update applied in one kernel; G's parameter part is cleared, its tail holds the summed scalars."""
+    def optimize_allreduce(self, W, G, n_params, m, symm, m_local):
+        """Data-parallel step: G (this rank's gradient vector, step scalars at its tail) is pushed into every rank's
+        symmetric receive buffer, the world copies are summed and the update applied in one kernel; G's parameter part
+        is cleared, its tail holds the summed scalars (cost sum, hits, sample count)."""
         s1, s2 = self._state(n_params)
         hp0, hp1, hp2 = self._hp()
         call(_lib.lib.bf_opt_step_allreduce, _lib.OPT[self.kind], W.ptr, G.ptr, s1, s2, n_params, G.size, float(self.eta),
              float(m), float(hp0), float(hp1), float(hp2), 1, symm.peers_dev, symm.pads_dev, symm.epoch.data_ptr(),
-             symm.gsum.data_ptr(), symm.rank, symm.world, symm.blocks, stream_ptr())
+             symm.timeout.data_ptr(), float(m_local), symm.rank, symm.world, symm.blocks, stream_ptr())
         return W
 
     def __str__(self):

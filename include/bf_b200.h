@@ -99,9 +99,17 @@ BF_API int bf_dense_forward(const float* X, const float* W, const float* b, floa
 BF_API int bf_dense_backward(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int k,
                       int n, int accumulate, int precision, void* stream);
 
+/* 1 when, on BF_PREC_TF32, the dense contraction `site` (0 forward, 1 weight gradient, 2 data gradient) of this shape runs
+ * on the TMA-staged tcgen05 GEMMs (operands read in place; the tensor core truncates them to TF32) rather than on the
+ * gather-staged core (operands rounded to nearest); 0 for n <= 32 (FP32 FMA kernels).  atomic/core_op.py:12-20. */
+BF_API int bf_dense_tma_supported(int m, int k, int n, int site);
+
 /* Dense layer (n <= 32 outputs) directly behind a channels-last convolutional block: X / dX (m, hw*chan) are in
  * physical channels-last feature order (yx, c); W / dW (chan*hw, n) keep the reference's NCHW-flatten row order
  * (c, yx) (layers/core.py:82-86 Flatten + :27-39 Dense).  Saves the two layout-change passes around Flatten. */
+/* 1 when bf_dense_forward_cl / bf_dense_backward_cl take a (k = chan*hw, n) layer (W fits the skinny kernels' shared
+ * memory); callers fall back to a layout change + bf_dense_forward / bf_dense_backward otherwise. */
+BF_API int bf_dense_cl_supported(int k, int n);
 BF_API int bf_dense_forward_cl(const float* X, const float* W, const float* b, float* out, int m, int chan, int hw, int n, int act,
                         void* stream);
 BF_API int bf_dense_backward_cl(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int chan,
@@ -264,16 +272,24 @@ BF_API int bf_clockwork_backward(const float* Z, const float* O, const float* de
 BF_API int bf_opt_step(int kind, float* W, float* g, float* s1, float* s2, size_t n, float eta, float m, float hp0, float hp1,
                 float hp2, int zero_grad, void* stream);
 
-/* Data-parallel form of the same step: all-reduce(sum) of the flat gradient vector over peer memory
- * (NVLink loads from every rank's symmetric buffer, fixed summation order) fused with the optimizer update.
- * G: this rank's gradient buffer inside a symmetric allocation; peers / pads: DEVICE arrays of `world` pointers to
- * every rank's buffer and signal pad; epoch: zero-initialised local array of `blocks` + 1 words (the last one is set
- * to 1 if a peer did not arrive within ~10 s: the step's results are then undefined); gsum: local scratch of n_total
- * floats.  Elements [n_params, n_total) (the step scalars riding at the tail) are summed, not optimised.
+/* Data-parallel form of the same step: all-reduce(sum) of the flat gradient vector over peer memory fused
+ * with the optimizer update, PUSH form: every rank stores its vector into its slot of every peer's receive buffer
+ * (NVLink stores), signals, waits for the world signals addressed to it, sums the world copies in rank order (identical
+ * bits on every rank) and updates its replica -- one synchronisation per step.
+ * G: this rank's gradient vector (ordinary device memory), n_total floats: [0, n_params) gradients, then a tail of step
+ * scalars [cost sum, hits, sample count, -] that is summed, not optimised (the kernel posts m_local in slot 2).
+ * recv / pads: DEVICE arrays of `world` pointers to every rank's receive buffer (2 * world * n_total floats, peer
+ * mapped) and signal pad (blocks * world words, zero-initialised); epoch: zero-initialised local array of `blocks`
+ * words; timeout: one word in mapped HOST memory, set to 1 if a peer did not arrive within ~10 s -- the CTAs that
+ * gave up leave W and the optimizer state untouched and the caller must treat the step as failed.
  * Replaces `allreduce` + `optimizer.optimize` + `zero_gradients` (learner/backpropagation.py:37-42,68-73). */
 BF_API int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float* s2, size_t n_params, size_t n_total, float eta,
-                          float m, float hp0, float hp1, float hp2, int zero_grad, void* const* peers, void* const* pads,
-                          unsigned* epoch, float* gsum, int rank, int world, int blocks, void* stream);
+                          float m, float hp0, float hp1, float hp2, int zero_grad, void* const* recv, void* const* pads,
+                          unsigned* epoch, unsigned* timeout, float m_local, int rank, int world, int blocks, void* stream);
+
+/* x[0..n) = value without reading x (a NaN already there does not survive): zero_gradients / fresh biases
+ * (learner/backpropagation.py:68-73, layers/abstract_layer.py:36-38). */
+BF_API int bf_fill(float* x, size_t n, float value, void* stream);
 
 /* ---- neuro-evolution fitness fan-out: evolution/_evolution.py:83-97 + learner/neuroevolution.py:20-22,34-37 ---- */
 /* For each of P genomes (rows of `genomes`, `loci` = nin*nh+nh+nh*nout+nout floats in U(0,1)):
@@ -282,6 +298,29 @@ BF_API int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float*
  * underflow where float64 does not).  Scratch for the hidden activations comes from the workspace. */
 BF_API int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* fitness, int P, int N, int nin, int nh,
                    int nout, int precision, void* stream);
+
+/* ---- device-resident Population: evolution/_evolution.py:83-141,143-208,245-261 ---- */
+/* The genome store G (Pstore, ldg) stays in HBM (ldg = loci rounded up to a multiple of 4 floats, padding zero) next to
+ * Bt (Pstore*64, nin), the K-major TF32 first-layer operand of the fitness kernel:
+ * Bt[g*64+h][k] = tf32((G[g][k*nh+h]-0.5)*20).  bf_population_fitness = bf_fitness_mlp for the `n` individuals listed
+ * in `inds` (device int32, NULL: individuals 0..n-1), read in place: no genome upload, no re-layout pass
+ * (`Population.update`, _evolution.py:83-97).  BF_PREC_TF32 only. */
+BF_API int bf_population_fitness(const float* G, long ldg, int Pstore, const float* Bt, const int* inds, int n, const float* X,
+                          const float* Y, float* fitness, int N, int nin, int nh, int nout, int precision, void* stream);
+/* Refresh Bt for the listed genomes (NULL: genomes 0..n-1) after their rows of G changed. */
+BF_API int bf_population_relayout(const float* G, long ldg, float* Bt, const int* inds, int n, int nin, int nh, void* stream);
+/* One generation step in a single pass over the store (_evolution.py:181-183,245-261): for every individual i
+ *   G_new[i] = survive[i] ? G_old[i] : where(coin < 0.5, G_old[left[i]], G_old[right[i]])      (mating)
+ * then every locus is replaced by a fresh U(0,1) draw with probability `rate` (mutation); mutant[i] = 1 where a row
+ * mutated.  Draws come from Philox4x32-10 keyed by (seed, generation), or -- when coin / mut_u / mut_val (P, loci) are
+ * given -- from the caller (parity tests replay the reference's recorded draws).  G_new must not alias G_old. */
+BF_API int bf_population_next_generation(const float* G_old, float* G_new, long ldg, int loci, int P, const unsigned char* survive,
+                                  const int* left, const int* right, float rate, unsigned seed, unsigned generation,
+                                  const float* coin, const float* mut_u, const float* mut_val, unsigned char* mutant,
+                                  void* stream);
+/* dst[r][:] = src[idx[r]][:] for rows of `row_floats` floats: the shuffled mini-batches of util/_nnutil.py:4-15 drawn from
+ * a data set that was uploaded once (learner/abstract_learner.py:41-54 `fit`). */
+BF_API int bf_gather_rows(const float* src, const int* idx, float* dst, int m, size_t row_floats, void* stream);
 
 #ifdef __cplusplus
 }

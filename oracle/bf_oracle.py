@@ -24,6 +24,59 @@ F64 = np.float64
 
 
 # --------------------------------------------------------------------------
+# TF32 operand emulation (checker for the tensor-core path)
+# --------------------------------------------------------------------------
+# `tcgen05.mma.kind::tf32` reads 19 bits of each FP32 operand (sign, 8 exponent, 10 mantissa bits) and accumulates in
+# FP32.  With a policy active every contraction below narrows its operands to FP32 (the device's storage type) and
+# then to TF32 the way the kernel that runs this site does it -- "rz": the low 13 bits are dropped (raw FP32 handed
+# to the MMA by TMA), "rna": round to nearest, ties away (cvt.rna.tf32.f32 / `+0x1000` in the operand builders) --
+# and accumulates in float64.  What is left between this and the device is FP32 accumulation order only, so the
+# tensor-core path can be held to ~1e-5 instead of the ~5e-4 of operand rounding.  A policy is a callable
+# (site, layer_index) -> (mode_A, mode_B) | None, or a dict {site: (mode_A, mode_B)}; sites are "dense.fwd",
+# "dense.dW", "dense.dX", "conv.fwd", "conv.dF", "conv.dX", "lstm.fwd", "lstm.dZ", "lstm.dW", "fit.l1".
+_TF32 = {"policy": None, "layer": None, "fp32_storage": False}
+
+
+def tf32_round(x, mode):
+    """x narrowed to FP32, then to TF32 by `mode` ("rz" | "rna" | None = FP32 only); returned as float64."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    if mode is None:
+        return a.astype(F64)
+    u = a.view(np.uint32)
+    if mode == "rna":
+        u = u + np.uint32(0x1000)
+    elif mode != "rz":
+        raise ValueError(mode)
+    return (u & np.uint32(0xFFFFE000)).view(np.float32).astype(F64)
+
+
+class tf32_emulation:
+    """Context manager: `with tf32_emulation(policy): ...` (see above)."""
+
+    def __init__(self, policy, fp32_storage=True):
+        self.policy, self.fp32_storage = policy, fp32_storage
+
+    def __enter__(self):
+        self.saved = dict(_TF32)
+        _TF32.update(policy=self.policy, fp32_storage=self.fp32_storage)
+        return self
+
+    def __exit__(self, *exc):
+        _TF32.update(self.saved)
+
+
+def _operands(site, A, B):
+    """The two operands of a contraction as the kernel behind `site` feeds them to the tensor core."""
+    pol = _TF32["policy"]
+    if pol is None:
+        return A, B
+    modes = pol(site, _TF32["layer"]) if callable(pol) else pol.get(site)
+    if modes is None:
+        return (tf32_round(A, None), tf32_round(B, None)) if _TF32["fp32_storage"] else (A, B)
+    return tf32_round(A, modes[0]), tf32_round(B, modes[1])
+
+
+# --------------------------------------------------------------------------
 # activations                                   atomic/activation_op.py:26-135
 # --------------------------------------------------------------------------
 def act_forward(kind, Z):
@@ -63,13 +116,16 @@ def act_backward(kind, A):
 # --------------------------------------------------------------------------
 def dense_forward(X, W, b=0.0):
     """atomic/core_op.py:12-13  Z = X@W + b."""
+    X, W = _operands("dense.fwd", X, W)
     return np.dot(X, W) + b
 
 
 def dense_backward(X, E, W):
     """atomic/core_op.py:16-20  returns (dW, db, dX); gradients are batch SUMS."""
-    dW = X.T @ E
-    dX = E @ W.T
+    Xa, Ea = _operands("dense.dW", X, E)
+    dW = Xa.T @ Ea
+    Eb, Wb = _operands("dense.dX", E, W)
+    dX = Eb @ Wb.T
     db = E.sum(axis=0)
     return dW, db, dX
 
@@ -100,17 +156,21 @@ def conv_full(A, F):
     return conv_valid(pA, F)
 
 
-def conv_forward(A, F, mode="valid"):
+def conv_forward(A, F, mode="valid", site="conv.fwd"):
     """atomic/tensor_op.py:42-46."""
+    if site is not None:
+        A, F = _operands(site, A, F)
     return conv_valid(A, F) if mode == "valid" else conv_full(A, F)
 
 
 def conv_backward(X, E, F):
     """atomic/tensor_op.py:49-61.  dF = valid(X^T(1023), E^T(1023))^T(1023);
     db = E.sum((0,2,3), keepdims) ; dX = full(E, flip_hw(F)^T(1023))."""
-    dF = conv_forward(X.transpose(1, 0, 2, 3), E.transpose(1, 0, 2, 3), "valid").transpose(1, 0, 2, 3)
+    Xa, Ea = _operands("conv.dF", X, E)
+    dF = conv_forward(Xa.transpose(1, 0, 2, 3), Ea.transpose(1, 0, 2, 3), "valid", site=None).transpose(1, 0, 2, 3)
     db = E.sum(axis=(0, 2, 3), keepdims=True)
-    dX = conv_forward(E, F[:, :, ::-1, ::-1].transpose(1, 0, 2, 3), "full")
+    Eb, Fb = _operands("conv.dX", E, F)
+    dX = conv_forward(Eb, Fb[:, :, ::-1, ::-1].transpose(1, 0, 2, 3), "full", site=None)
     return np.ascontiguousarray(dF), db, dX
 
 
@@ -340,7 +400,8 @@ def lstm_forward(X, W, b, activation="tanh"):
     C, f, i, o, cand, Ca = np.zeros((6, T, B, H))
     for t in range(T):
         Z[t] = np.concatenate((X[t], O[t - 1]), axis=-1)
-        p = np.dot(Z[t], W) + b
+        Zt, Wt = _operands("lstm.fwd", Z[t], W)
+        p = np.dot(Zt, Wt) + b
         p[:, :H] = act_forward(activation, p[:, :H])
         p[:, H:] = act_forward("sigmoid", p[:, H:])
         cand[t] = p[:, :H]
@@ -377,10 +438,12 @@ def lstm_backward(Z, O, E, W, cache, activation="tanh"):
         do = Ca[t] * E[t]
         dgates[t] = np.concatenate((dcand, df, di, do), axis=-1) * bwgates[t]
         deltaC *= f[t]
-        deltaZ[t] = np.dot(dgates[t], W.T)
+        dg, Wb = _operands("lstm.dZ", dgates[t], W)
+        deltaZ[t] = np.dot(dg, Wb.T)
         if t:
             E[t - 1] += deltaZ[t, :, D:]
-    nablaW = np.matmul(Z.transpose(0, 2, 1), dgates).sum(axis=0)
+    Za, dga = _operands("lstm.dW", Z, dgates)
+    nablaW = np.matmul(Za.transpose(0, 2, 1), dga).sum(axis=0)
     nablab = np.sum(dgates, axis=(0, 1))
     return deltaZ[:, :, :D], nablaW, nablab
 
@@ -582,7 +645,8 @@ class Stack:
     # ---- forward: model/layerstack.py:37-40
     def feedforward(self, X):
         X = np.asarray(X, dtype=F64)
-        for l in self.L:
+        for li, l in enumerate(self.L):
+            _TF32["layer"] = li
             k = l["kind"]
             if k == "dense":                       # layers/core.py:27-32
                 l["inputs"] = X
@@ -626,7 +690,9 @@ class Stack:
     # ---- backward: learner/backpropagation.py:32-35
     def backpropagate(self, error):
         error = np.array(error, dtype=F64, copy=True)
-        for l in self.L[::-1]:
+        for li in range(len(self.L) - 1, -1, -1):
+            l = self.L[li]
+            _TF32["layer"] = li
             k = l["kind"]
             if k == "dense":                       # layers/core.py:34-39 (ACCUMULATES)
                 error = error * act_backward(l["act"], l["output"])
@@ -721,19 +787,34 @@ def fitness(stack, genome, X, Y):
     return cost_value(stack.cost, out, Y) / len(X)
 
 
-def fitness_mlp_logsoftmax(genomes, X, Y, nin, nh, nout):
+def fitness_mlp_logsoftmax(genomes, X, Y, nin, nh, nout, chunk=64):
     """Vectorised, underflow-free float64 fitness of the Dense(nh,sigmoid) ->
     Dense(nout,softmax) MLP under cxent for a batch of genomes (P, loci):
     -sum(Y*log_softmax(logits))/m.  Equal to ``fitness`` wherever the literal
-    float64 formula does not hit log(0)."""
-    G = as_weights(np.asarray(genomes, dtype=F64))
+    float64 formula does not hit log(0).  The first layers of `chunk` genomes
+    are one BLAS product X @ [W1_0 | W1_1 | ...] (site "fit.l1" under TF32
+    emulation, where as_weights is evaluated in FP32 like the device does)."""
+    genomes = np.asarray(genomes)
+    X = np.asarray(X, dtype=F64)
+    Y = np.asarray(Y, dtype=F64)
     o1 = nin * nh
-    W1 = G[:, :o1].reshape(-1, nin, nh)
-    b1 = G[:, o1:o1 + nh]
-    W2 = G[:, o1 + nh:o1 + nh + nh * nout].reshape(-1, nh, nout)
-    b2 = G[:, o1 + nh + nh * nout:]
-    Hh = 1.0 / (1.0 + np.exp(-(np.einsum("nk,pkh->pnh", X, W1) + b1[:, None, :])))
-    L = np.einsum("pnh,pho->pno", Hh, W2) + b2[:, None, :]
-    L = L - L.max(axis=2, keepdims=True)
-    lsm = L - np.log(np.exp(L).sum(axis=2, keepdims=True))
-    return -(Y[None] * lsm).sum(axis=(1, 2)) / len(X)
+    out = np.zeros(len(genomes))
+    emul = _TF32["policy"] is not None
+    for p0 in range(0, len(genomes), chunk):
+        g = genomes[p0:p0 + chunk]
+        if emul:
+            G = ((g.astype(np.float32) - np.float32(0.5)) * np.float32(20.0)).astype(F64)
+        else:
+            G = as_weights(np.asarray(g, dtype=F64))
+        P = len(G)
+        W1 = G[:, :o1].reshape(P, nin, nh).transpose(1, 0, 2).reshape(nin, P * nh)
+        b1 = G[:, o1:o1 + nh]
+        W2 = G[:, o1 + nh:o1 + nh + nh * nout].reshape(P, nh, nout)
+        b2 = G[:, o1 + nh + nh * nout:]
+        Xa, W1a = _operands("fit.l1", X, W1)
+        Hh = 1.0 / (1.0 + np.exp(-((Xa @ W1a).reshape(len(X), P, nh).transpose(1, 0, 2) + b1[:, None, :])))
+        L = np.matmul(Hh, W2) + b2[:, None, :]
+        L = L - L.max(axis=2, keepdims=True)
+        lsm = L - np.log(np.exp(L).sum(axis=2, keepdims=True))
+        out[p0:p0 + chunk] = -(Y[None] * lsm).sum(axis=(1, 2)) / len(X)
+    return out

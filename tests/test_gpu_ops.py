@@ -123,9 +123,10 @@ def test_optimizers_golden(bf, golden_ops, name):
 @pytest.mark.parametrize("world", [1, 4])
 @pytest.mark.parametrize("name", ["sgd", "adam"])
 def test_opt_step_allreduce_simulated_ranks(bf, name, world):
-    """bf_opt_step_allreduce with `world` simulated ranks on ONE device (one stream per rank, buffers and signal pads in
-    ordinary device memory): every replica ends at optimize(W, sum of the ranks' gradients), gradients are cleared, the
-    step scalars at the tail hold their sums.  (Across real GPUs: scripts/dp_check.py.)"""
+    """bf_opt_step_allreduce with `world` simulated ranks on ONE device (one stream per rank, receive buffers and signal
+    pads in ordinary device memory): every replica ends at optimize(W, sum of the ranks' gradients), gradients are
+    cleared, the step scalars at the tail hold their sums, slot 2 of the tail the summed sample counts.  Three steps, so
+    that both parity halves of the receive buffers are reused.  (Across real GPUs: tests/test_gpu_multi.py.)"""
     import torch
     from brainforge_b200 import _lib
     from brainforge_b200.device import DeviceArray, call
@@ -136,24 +137,26 @@ def test_opt_step_allreduce_simulated_ranks(bf, name, world):
     dev = torch.device("cuda")
     G = [torch.tensor(g, device=dev) for g in Gs]
     W = [torch.tensor(np.concatenate([W0, np.zeros(n_total - n_params, np.float32)]), device=dev) for _ in range(world)]
+    recv = [torch.full((2 * world * n_total,), float("nan"), device=dev) for _ in range(world)]
     pads = [torch.zeros(blocks * world, dtype=torch.int32, device=dev) for _ in range(world)]
-    peers_t = torch.tensor([g.data_ptr() for g in G], dtype=torch.int64, device=dev)
+    recv_t = torch.tensor([g.data_ptr() for g in recv], dtype=torch.int64, device=dev)
     pads_t = torch.tensor([p.data_ptr() for p in pads], dtype=torch.int64, device=dev)
-    epochs = [torch.zeros(blocks + 1, dtype=torch.int32, device=dev) for _ in range(world)]
-    gsum = [torch.zeros(n_total, device=dev) for _ in range(world)]
+    epochs = [torch.zeros(blocks, dtype=torch.int32, device=dev) for _ in range(world)]
+    timeouts = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(world)]
     opts = [bf.optimizers.optimizers[name]() for _ in range(world)]
     streams = [torch.cuda.Stream() for _ in range(world)]
     torch.cuda.synchronize()
-    for step in range(2):
+    for step in range(3):
         for r in range(world):
             s1, s2 = opts[r]._state(n_params)
             hp = opts[r]._hp()
             call(_lib.lib.bf_opt_step_allreduce, _lib.OPT[name], W[r].data_ptr(), G[r].data_ptr(), s1, s2, n_params, n_total,
-                 float(opts[r].eta), m, float(hp[0]), float(hp[1]), float(hp[2]), 1, peers_t.data_ptr(), pads_t.data_ptr(),
-                 epochs[r].data_ptr(), gsum[r].data_ptr(), r, world, blocks, streams[r].cuda_stream)
+                 float(opts[r].eta), m, float(hp[0]), float(hp[1]), float(hp[2]), 1, recv_t.data_ptr(), pads_t.data_ptr(),
+                 epochs[r].data_ptr(), timeouts[r].data_ptr(), float(5 + r), r, world, blocks, streams[r].cuda_stream)
         torch.cuda.synchronize()
-        assert all(int(e[-1].item()) == 0 for e in epochs), "a simulated rank timed out at the barrier"
+        assert all(int(t[0]) == 0 for t in timeouts), "a simulated rank timed out at the exchange"
         total = np.sum(np.stack(Gs).astype(np.float64), axis=0)
+        total[n_params + 2] = sum(5 + r for r in range(world))          # the kernel posts each rank's sample count there
         if step == 0:
             ref = bf.optimizers.optimizers[name]()
             Wref = DeviceArray.from_host(W0)
@@ -168,6 +171,30 @@ def test_opt_step_allreduce_simulated_ranks(bf, name, world):
         for r in range(world):
             G[r].copy_(torch.tensor(Gs[r], device=dev))
         torch.cuda.synchronize()
+
+
+def test_opt_step_allreduce_times_out_without_touching_the_replica(bf):
+    """A peer that never arrives: the kernel gives up, raises the host-visible flag and leaves W and the optimizer state as
+    they were (a straggler must not make the replicas diverge silently).  The wait is ~10 s of GPU time."""
+    import torch
+    from brainforge_b200 import _lib
+    from brainforge_b200.device import call
+    dev = torch.device("cuda")
+    n_params, n_total, blocks, world = 256, 320, 2, 2
+    W = torch.ones(n_total, device=dev)
+    G = torch.ones(n_total, device=dev)
+    recv = [torch.zeros(2 * world * n_total, device=dev) for _ in range(world)]
+    pads = [torch.zeros(blocks * world, dtype=torch.int32, device=dev) for _ in range(world)]
+    recv_t = torch.tensor([g.data_ptr() for g in recv], dtype=torch.int64, device=dev)
+    pads_t = torch.tensor([p.data_ptr() for p in pads], dtype=torch.int64, device=dev)
+    epoch = torch.zeros(blocks, dtype=torch.int32, device=dev)
+    timeout = torch.zeros(4, dtype=torch.int32).pin_memory()
+    call(_lib.lib.bf_opt_step_allreduce, _lib.OPT["sgd"], W.data_ptr(), G.data_ptr(), None, None, n_params, n_total, 0.1, 4.0,
+         0.0, 0.0, 0.0, 1, recv_t.data_ptr(), pads_t.data_ptr(), epoch.data_ptr(), timeout.data_ptr(), 4.0, 0, world, blocks,
+         torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(timeout[0]) == 1
+    assert torch.equal(W, torch.ones_like(W)), "the replica was updated from a partial sum"
 
 
 # ---------------------------------------------------------------- oracle at ragged / awkward shapes
