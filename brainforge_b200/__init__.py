@@ -12,6 +12,6 @@ from .device import DeviceArray, set_precision, precision_name, pinned_empty, sy
 from . import atomic
 from .model import LayerStack
 from .learner import Backpropagation, NeuroEvolution, Learner
-from . import layers, optimizers, metrics, evolution, dist
+from . import layers, optimizers, metrics, evolution, dist, gradientcheck
 
 BackpropNetwork = Backpropagation       # the stale name the README / BASELINE.json still use

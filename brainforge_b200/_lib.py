@@ -91,6 +91,8 @@ SIGNATURES = {
     "bf_population_relayout": (_i, [_vp, _c.c_long, _vp, _vp, _i, _i, _i, _vp]),
     "bf_population_next_generation": (_i, [_vp, _vp, _c.c_long, _i, _i, _vp, _vp, _vp, _f, _c.c_uint, _c.c_uint, _vp, _vp, _vp,
                                            _vp, _vp]),
+    "bf_gradcheck_perturb": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _vp]),
+    "bf_gradcheck_cost": (_i, [_i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "bf_gather_rows": (_i, [_vp, _vp, _vp, _i, _sz, _vp]),
 }
 

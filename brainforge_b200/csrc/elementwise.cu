@@ -113,7 +113,8 @@ __global__ void mul_rowmask_kernel(const float* __restrict__ x, const float* __r
 template <int KIND>
 __global__ void cost_value_kernel(const float* __restrict__ o, const float* __restrict__ t, size_t total,
                                   double* __restrict__ partial, float* __restrict__ result, float* __restrict__ delta,
-                                  const float* __restrict__ w, int n) {
+                                  const float* __restrict__ w, int n, double* __restrict__ record = nullptr,
+                                  const unsigned* __restrict__ record_ctr = nullptr, int record_slot = 0) {
   __shared__ double sm[32];
   __shared__ bool last;
   pdl_launch_dependents();
@@ -157,7 +158,8 @@ __global__ void cost_value_kernel(const float* __restrict__ o, const float* __re
     __threadfence();
     double s = 0.0;
     for (unsigned int b = 0; b < gridDim.x; ++b) s += ((volatile double*)partial)[b];
-    result[0] = (float)s;
+    if (result) result[0] = (float)s;
+    if (record) record[3 * (size_t)record_ctr[0] + record_slot] = s;       // gradient check: the double-precision sum, by parameter
     g_reduce_ticket = 0;
   }
 }
@@ -447,7 +449,7 @@ int bf_cost_value(int kind, const float* out, const float* tgt, int m, int n, fl
   void* ws = nullptr;
   int rc = workspace_require((size_t)grid * sizeof(double), &ws);
   if (rc) return rc;
-#define BF_COST_CASE(K_) case K_: launch_pdl(cost_value_kernel<K_>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, (float*)nullptr, (const float*)nullptr, n); break;
+#define BF_COST_CASE(K_) case K_: launch_pdl(cost_value_kernel<K_>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, (float*)nullptr, (const float*)nullptr, n, (double*)nullptr, (const unsigned*)nullptr, 0); break;
   switch (kind) {
     BF_COST_CASE(BF_COST_MSE) BF_COST_CASE(BF_COST_CXENT) BF_COST_CASE(BF_COST_BXENT) BF_COST_CASE(BF_COST_HINGE)
     default: return fail(BF_ERR_ARG, "bf_cost_value: unknown cost kind %d", kind);
@@ -472,7 +474,7 @@ int bf_cost_delta_value(int kind, const float* out, const float* tgt, const floa
   void* ws = nullptr;
   int rc = workspace_require((size_t)grid * sizeof(double), &ws);
   if (rc) return rc;
-#define BF_COST_CASE(K_) case K_: launch_pdl(cost_value_kernel<K_>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, delta, w, n); break;
+#define BF_COST_CASE(K_) case K_: launch_pdl(cost_value_kernel<K_>, dim3(grid), dim3(256), 0, s, out, tgt, total, (double*)ws, result, delta, w, n, (double*)nullptr, (const unsigned*)nullptr, 0); break;
   switch (kind) {
     BF_COST_CASE(BF_COST_MSE) BF_COST_CASE(BF_COST_CXENT) BF_COST_CASE(BF_COST_BXENT) BF_COST_CASE(BF_COST_HINGE)
     default: break;
@@ -589,6 +591,51 @@ int bf_opt_step_allreduce(int kind, float* W, float* G, float* s1, float* s2, si
     default: return fail(BF_ERR_ARG, "bf_opt_step_allreduce: unknown optimizer kind %d", kind);
   }
 #undef BF_AR
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+// ---- batched on-device gradient check (gradientcheck/raw_gradients.py:15-42): building blocks, graph-capturable --------
+__global__ void gradcheck_perturb_kernel(float* __restrict__ W, const int* __restrict__ offsets, unsigned* __restrict__ counter,
+                                         float* __restrict__ saved, double* __restrict__ record, float eps, int phase) {
+  const unsigned c = counter[0];
+  float* w = W + offsets[c];
+  if (phase == 0) {
+    saved[0] = *w;
+    *w = saved[0] + eps;
+    record[3 * (size_t)c + 2] = (double)*w;
+  } else if (phase == 1) {
+    *w = saved[0] - eps;
+    record[3 * (size_t)c + 2] -= (double)*w;              // the step actually taken between the two FP32 weights
+  } else {
+    *w = saved[0];
+    counter[0] = c + 1;
+  }
+}
+
+int bf_gradcheck_perturb(float* W, const int* offsets, unsigned* counter, float* saved, double* record, float epsilon, int phase,
+                         void* stream) {
+  BF_REQUIRE(W && offsets && counter && saved && record && phase >= 0 && phase <= 2, BF_ERR_ARG, "bf_gradcheck_perturb: bad arguments");
+  gradcheck_perturb_kernel<<<1, 1, 0, as_stream(stream)>>>(W, offsets, counter, saved, record, epsilon, phase);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_gradcheck_cost(int kind, const float* out, const float* tgt, int m, int n, double* record, const unsigned* counter,
+                      int slot, void* stream) {
+  BF_REQUIRE(m > 0 && n > 0 && out && tgt && record && counter && (slot == 0 || slot == 1), BF_ERR_ARG, "bf_gradcheck_cost: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  const size_t total = (size_t)m * n;
+  int grid = ew_grid(total, 256, 1);
+  void* ws = nullptr;
+  int rc = workspace_require((size_t)grid * sizeof(double), &ws);
+  if (rc) return rc;
+#define BF_COST_CASE(K_) case K_: cost_value_kernel<K_><<<grid, 256, 0, s>>>(out, tgt, total, (double*)ws, (float*)nullptr, (float*)nullptr, (const float*)nullptr, n, record, counter, slot); break;
+  switch (kind) {
+    BF_COST_CASE(BF_COST_MSE) BF_COST_CASE(BF_COST_CXENT) BF_COST_CASE(BF_COST_BXENT) BF_COST_CASE(BF_COST_HINGE)
+    default: return fail(BF_ERR_ARG, "bf_gradcheck_cost: unknown cost kind %d", kind);
+  }
+#undef BF_COST_CASE
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

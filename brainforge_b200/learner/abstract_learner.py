@@ -1,4 +1,17 @@
-"""learner/abstract_learner.py of the reference: fit / epoch / evaluate loops (host orchestration)."""
+"""The training / evaluation loops behind the reference's `Learner` API (learner/abstract_learner.py: fit,
+fit_generator, epoch, evaluate, evaluate_stream, evaluate_batch, predict -- same names, arguments and results),
+organised around what the device needs instead of around host arrays:
+
+* `fit(X, Y, ...)` uploads the data set ONCE (`ResidentDataset`) and draws every mini-batch on the device: the
+  reference reshuffles the host arrays on every pass (util/_nnutil.py:4-15, a full copy of X and Y per pass); here the
+  same permutation is drawn from the same NumPy stream, but only its index vector travels and `bf_gather_rows` assembles
+  the batch in HBM.  Unshuffled batches are views.  Data sets that do not fit the memory budget stream from the host.
+* `epoch(generator, n)` drives a `StepPipeline`: a learner that can enqueue a step without waiting for it
+  (`learn_batch_async` + `stage_batch`, Backpropagation) has batch i+1's host->device copy in flight on a copy stream
+  while step i computes, and its scalars are read one step late from a pinned snapshot -- the device never waits for
+  Python.  The generator is still drawn exactly n times and the history holds the same numbers in the same order as n
+  serial `learn_batch` calls.
+"""
 import time
 
 import numpy as np
@@ -6,6 +19,91 @@ import numpy as np
 from ..model.layerstack import LayerStack
 from ..metrics import costs as _costs, metrics as _metrics
 from ..util import batch_stream, MetricLogs
+
+
+class ResidentDataset:
+    """Arrays with a common first dimension kept in HBM; `batches()` is `util.batch_stream` over them (same batch
+    sequence, same use of the global NumPy RNG) yielding DeviceArrays."""
+
+    BUDGET_FRACTION = 0.5      # of the currently free device memory
+
+    def __init__(self, arrays):
+        from ..device import DeviceArray
+        self.n = len(arrays[0])
+        self.shapes = [tuple(np.shape(a)[1:]) for a in arrays]
+        self.dev = [a if isinstance(a, DeviceArray) else DeviceArray.from_host(a) for a in arrays]
+
+    @classmethod
+    def fits(cls, arrays):
+        import torch
+        need = sum(4 * int(np.prod(np.shape(a))) for a in arrays)
+        free, _ = torch.cuda.mem_get_info()
+        return need <= cls.BUDGET_FRACTION * free
+
+    def _take(self, order_dev, start, stop):
+        import ctypes
+        from .. import _lib
+        from ..device import DeviceArray, call, stream_ptr
+        out = []
+        for arr, tail in zip(self.dev, self.shapes):
+            dst = DeviceArray.empty(stop - start, *tail)
+            row = int(np.prod(tail)) if tail else 1
+            call(_lib.lib.bf_gather_rows, arr.ptr, ctypes.c_void_p(order_dev.data_ptr() + 4 * start), dst.ptr, stop - start, row,
+                 stream_ptr())
+            out.append(dst)
+        return tuple(out)
+
+    def batches(self, m, shuffle=True, infinite=True):
+        import torch
+        while True:
+            order = np.arange(self.n)
+            if shuffle:
+                np.random.shuffle(order)                  # util/_nnutil.py:8-9: one permutation per pass
+                order_dev = torch.as_tensor(order.astype(np.int32), device="cuda")
+            for start in range(0, self.n, m):
+                stop = min(start + m, self.n)
+                if shuffle:
+                    yield self._take(order_dev, start, stop)
+                else:
+                    yield tuple(arr[start:stop] for arr in self.dev)
+            if not infinite:
+                return
+
+
+class StepPipeline:
+    """Feeds batches to a learner and collects the per-step results in order.  With an asynchronous learner the
+    result of step i is collected after step i+1 has been enqueued and batch i+2's upload has been started."""
+
+    def __init__(self, learner, metrics, sink, learn_kw):
+        self.learner, self.metrics, self.sink, self.kw = learner, metrics, sink, learn_kw
+        self.overlapped = hasattr(learner, "learn_batch_async") and "w" not in learn_kw
+        self.batch_size = 0
+
+    def _stage(self, batch):
+        from ..device import DeviceArray
+        x, y = batch[0], batch[1]
+        if isinstance(x, DeviceArray) and isinstance(y, DeviceArray):
+            return x, y                                   # already in HBM (ResidentDataset): nothing to copy
+        return self.learner.stage_batch(x, y), None
+
+    def run(self, generator, steps):
+        if not self.overlapped:
+            for _ in range(steps):
+                batch = next(generator)
+                self.batch_size = len(batch[0])
+                self.sink(self.learner.learn_batch(*batch, metrics=self.metrics, **self.kw))
+            return
+        in_flight = None                                  # reader of the previous step's scalars
+        staged = self._stage(next(generator)) if steps else None
+        for i in range(steps):
+            self.batch_size = len(staged[0])
+            reader = self.learner.learn_batch_async(staged[0], staged[1], metrics=self.metrics, snapshot=True, **self.kw)
+            staged = self._stage(next(generator)) if i + 1 < steps else None
+            if in_flight is not None:
+                self.sink(in_flight())
+            in_flight = reader
+        if in_flight is not None:
+            self.sink(in_flight())
 
 
 class Learner:
@@ -20,97 +118,90 @@ class Learner:
         self.age = 0
         self.cost = _costs.get(cost)
 
-    def fit_generator(self, generator, lessons_per_epoch, epochs=30, metrics=(), validation=(),
-                      validation_steps=None, verbose=1, **kw):
-        metrics = [_metrics.get(metric) for metric in metrics]
-        history = MetricLogs.from_metric_list(lessons_per_epoch, ("cost",), metrics)
-        lstr = len(str(epochs))
-        for epoch in range(1, epochs + 1):
-            if verbose:
-                print("Epoch {:>{w}}/{}".format(epoch, epochs, w=lstr))
-            epoch_history = self.epoch(generator, updates_per_epoch=lessons_per_epoch, metrics=metrics,
-                                       validation=validation, validation_steps=validation_steps,
-                                       verbose=verbose, **kw)
-            history.update(epoch_history)
-        return history
-
+    # ------------------------------------------------------------------ training
     def fit(self, X, Y, batch_size=20, epochs=30, metrics=(), validation=(), validation_steps=None, verbose=1,
             shuffle=True, **kw):
-        metrics = [_metrics.get(metric) for metric in metrics]
-        datastream = batch_stream(X, Y, m=batch_size, shuffle=shuffle)
-        return self.fit_generator(datastream, len(X) // batch_size, epochs, metrics, validation, validation_steps,
-                                  verbose, **kw)
+        """learner/abstract_learner.py:41-54."""
+        return self.fit_generator(self._batch_source(X, Y, batch_size, shuffle), len(X) // batch_size, epochs,
+                                  [_metrics.get(m) for m in metrics], validation, validation_steps, verbose, **kw)
 
-    def epoch(self, generator, updates_per_epoch, metrics=(), validation=None, validation_steps=None, verbose=1,
-              **kw):
-        start = time.time()
-        metrics = [_metrics.get(metric) for metric in metrics]
+    def _batch_source(self, X, Y, batch_size, shuffle, infinite=True):
+        resident = getattr(self, "resident_data", True) and hasattr(self, "learn_batch_async")
+        if resident and ResidentDataset.fits((X, Y)):
+            return ResidentDataset((X, Y)).batches(batch_size, shuffle=shuffle, infinite=infinite)
+        return batch_stream(X, Y, m=batch_size, shuffle=shuffle, infinite=infinite)
+
+    def fit_generator(self, generator, lessons_per_epoch, epochs=30, metrics=(), validation=(),
+                      validation_steps=None, verbose=1, **kw):
+        """learner/abstract_learner.py:21-39."""
+        metrics = [_metrics.get(m) for m in metrics]
+        history = MetricLogs.from_metric_list(lessons_per_epoch, ("cost",), metrics)
+        width = len(str(epochs))
+        for number in range(1, epochs + 1):
+            if verbose:
+                print("Epoch {:>{w}}/{}".format(number, epochs, w=width))
+            history.update(self.epoch(generator, updates_per_epoch=lessons_per_epoch, metrics=metrics, validation=validation,
+                                      validation_steps=validation_steps, verbose=verbose, **kw))
+        return history
+
+    def epoch(self, generator, updates_per_epoch, metrics=(), validation=None, validation_steps=None, verbose=1, **kw):
+        """learner/abstract_learner.py:56-87: `updates_per_epoch` lessons drawn from `generator`, then the validation
+        pass; returns the epoch's MetricLogs."""
+        began = time.time()
+        metrics = [_metrics.get(m) for m in metrics]
         history = MetricLogs.from_metric_list(updates_per_epoch, ["cost"], metrics)
-        self.layers.learning = True
-        batch_size = 0
-        # Learners that can stage a batch ahead of time (Backpropagation.stage_batch) get the NEXT batch's
-        # host->device copy overlapped with the current step, and the host reads a step's scalars one step late
-        # (from a pinned snapshot taken right behind that step): launch step i, upload batch i+1 on the copy
-        # stream, read step i-1.  The device never waits for Python between steps.  The generator is still drawn
-        # exactly updates_per_epoch times and the history holds the same numbers in the same order.
-        stage = getattr(self, "stage_batch", None) if "w" not in kw else None
-        staged, pending_prev = None, None
 
-        def record(epoch_metrics):
-            history.record(epoch_metrics)
+        def sink(step_metrics):
+            history.record(step_metrics)
             if verbose:
                 history.log(prefix="\rTraining ", end="", add_progress=True)
 
-        for i in range(updates_per_epoch):
-            if stage is None:
-                batch = next(generator)
-                batch_size = len(batch[0])
-                record(self.learn_batch(*batch, metrics=metrics, **kw))
-            else:
-                if staged is None:
-                    staged = stage(*next(generator)[:2])
-                batch_size = len(staged)
-                pending = self.learn_batch_async(staged, None, metrics=metrics, snapshot=True, **kw)
-                staged = stage(*next(generator)[:2]) if i + 1 < updates_per_epoch else None
-                if pending_prev is not None:
-                    record(pending_prev())
-                pending_prev = pending
-        if pending_prev is not None:
-            record(pending_prev())
-        self.layers.learning = False
+        self.layers.learning = True
+        pipe = StepPipeline(self, metrics, sink, kw)
+        try:
+            pipe.run(generator, updates_per_epoch)
+        finally:
+            self.layers.learning = False
         if verbose and validation:
-            if type(validation) in (tuple, list):
-                eval_history = self.evaluate(*validation, batch_size=batch_size, metrics=metrics, verbose=False)
+            if isinstance(validation, (tuple, list)):
+                report = self.evaluate(*validation, batch_size=pipe.batch_size, metrics=metrics, verbose=False)
+            elif validation_steps is None:
+                raise RuntimeError("If validating on a stream, validation_steps must be set to a positive integer.")
             else:
-                if validation_steps is None:
-                    raise RuntimeError("If validating on a stream, validation_steps must be set to a positive integer.")
-                eval_history = self.evaluate_stream(validation, validation_steps, metrics, verbose=False)
-            eval_history.log(prefix=" Validation ", suffix="", add_progress=False)
+                report = self.evaluate_stream(validation, validation_steps, metrics, verbose=False)
+            report.log(prefix=" Validation ", suffix="", add_progress=False)
         if verbose:
-            print(" took {:.2f} minutes".format((time.time() - start) / 60))
+            print(" took {:.2f} minutes".format((time.time() - began) / 60))
         self.age += updates_per_epoch
         return history
 
+    def learn_batch(self, X, Y, metrics=(), **kw) -> dict:
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ inference / evaluation
     def predict(self, X):
         return self.layers.feedforward(X)
 
     def evaluate_batch(self, x, y, metrics=()):
-        m = len(x)
-        preds = self.predict(x)
-        eval_metrics = {"cost": self.cost(self.output, y) / m}
-        if metrics:
-            for metric in metrics:
-                eval_metrics[str(metric).lower()] = metric(preds, y) / m
-        return eval_metrics
+        """learner/abstract_learner.py:92-99: cost and metrics of one batch, per sample."""
+        from ..device import as_device
+        count = len(x)
+        xd, yd = as_device(x), as_device(y)
+        preds = self.layers._fwd(xd)
+        report = {"cost": self.cost(preds, yd) / count}
+        for metric in metrics or ():
+            report[str(metric).lower()] = metric(preds, yd) / count
+        return report
 
     def evaluate_stream(self, stream, steps, metrics=(), verbose=False):
-        metrics = [_metrics.get(metric) for metric in metrics]
+        """learner/abstract_learner.py:101-114: mean of `steps` batch reports."""
+        metrics = [_metrics.get(m) for m in metrics]
         history = MetricLogs.from_metric_list(steps, ["cost"], metrics)
-        for i, (x, y) in enumerate(stream, start=1):
+        for seen, (x, y) in enumerate(stream, start=1):
             history.record(self.evaluate_batch(x, y, metrics))
             if verbose:
                 history.log("\r", end="")
-            if i >= steps:
+            if seen >= steps:
                 break
         if verbose:
             print()
@@ -118,15 +209,13 @@ class Learner:
         return history
 
     def evaluate(self, X, Y, batch_size=32, metrics=(), verbose=False):
-        N = X.shape[0]
-        batch_size = min(batch_size, N)
-        steps = int(round(N / batch_size))
-        stream = batch_stream(X, Y, m=batch_size, shuffle=False, infinite=False)
-        return self.evaluate_stream(stream, steps, metrics, verbose)
+        """learner/abstract_learner.py:116-123."""
+        total = X.shape[0]
+        batch_size = min(batch_size, total)
+        source = self._batch_source(X, Y, batch_size, shuffle=False, infinite=False)
+        return self.evaluate_stream(source, int(round(total / batch_size)), metrics, verbose)
 
-    def learn_batch(self, X, Y, metrics=(), **kw) -> dict:
-        raise NotImplementedError
-
+    # ------------------------------------------------------------------ shortcuts
     @property
     def output(self):
         return self.layers[-1].output

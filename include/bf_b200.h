@@ -299,6 +299,19 @@ BF_API int bf_fill(float* x, size_t n, float value, void* stream);
 BF_API int bf_fitness_mlp(const float* genomes, const float* X, const float* Y, float* fitness, int P, int N, int nin, int nh,
                    int nout, int precision, void* stream);
 
+/* ---- batched on-device gradient check: gradientcheck/raw_gradients.py:15-42 ---- */
+/* The reference perturbs one weight at a time on the host and reads two costs back per parameter.  Here the whole
+ * sweep stays on the device: a parameter counter lives in device memory, `bf_gradcheck_perturb` moves weight
+ * W[offsets[*counter]] (phase 0: save it, set w+eps; phase 1: w-eps; phase 2: restore, ++*counter) and
+ * `bf_gradcheck_cost` stores the double-precision cost of the current outputs in record[3*(*counter)+slot]
+ * (slot 0: cost(w+eps), 1: cost(w-eps); element 2 holds the FP32 step actually taken, (w+eps)-(w-eps)).  One sweep
+ * iteration (perturb, forward, cost, perturb, forward, cost, restore) is captured in a CUDA graph and replayed once
+ * per parameter; the host reads `record` once at the end. */
+BF_API int bf_gradcheck_perturb(float* W, const int* offsets, unsigned* counter, float* saved, double* record, float epsilon,
+                         int phase, void* stream);
+BF_API int bf_gradcheck_cost(int kind, const float* out, const float* tgt, int m, int n, double* record, const unsigned* counter,
+                      int slot, void* stream);
+
 /* ---- device-resident Population: evolution/_evolution.py:83-141,143-208,245-261 ---- */
 /* The genome store G (Pstore, ldg) stays in HBM (ldg = loci rounded up to a multiple of 4 floats, padding zero) next to
  * Bt (Pstore*64, nin), the K-major TF32 first-layer operand of the fitness kernel:

@@ -242,3 +242,43 @@ def test_epoch_prefetch_matches_learn_batch(use_graph):
     assert hist["accuracy"] == [r["accuracy"] for r in ref]
     assert np.array_equal(a.layers.get_weights(), b.layers.get_weights())
     assert a.age == 5
+
+
+@pytest.mark.parametrize("cfg", ["mlp", "conv"])
+def test_gradientcheck_run_on_device(cfg, capsys):
+    """`gradientcheck.run(network, X, Y)` -- the reference's integration test (gradientcheck/gradientcheck.py:8-24,
+    tests use it through the public API) -- against this back-end: the analytic gradients of the device backward pass
+    agree with the on-device batched central-difference sweep (bf_gradcheck_*, one CUDA-graph replay per parameter),
+    the graph sweep equals plain launches, and a deliberately broken gradient is caught."""
+    import brainforge_b200 as bf
+    from brainforge_b200.gradientcheck import raw_gradients
+    if cfg == "mlp":
+        ishape, spec = (12,), [("dense", 9, "sigmoid"), ("dense", 5, "tanh"), ("dense", 4, "softmax")]
+    else:       # linear conv activation: with bias-after-activation a nonlinear one makes db inexact in the reference too
+        ishape, spec = (2, 8, 8), [("conv", 3, 3, 3, "linear"), ("act", "tanh"), ("pool", 2), ("flatten",), ("dense", 4, "softmax")]
+    net = build_b200(ishape, spec, "cxent", "sgd", seed=2)
+    rs = np.random.RandomState(8)
+    X, Y = rs.randn(10, *ishape), onehot(rs, 10, 4)
+    w0 = net.layers.get_weights()
+    assert bf.gradientcheck.run(net, X, Y, epsilon=1e-5, throw=True, display=False)
+    assert "below the resolution of FP32" in capsys.readouterr().out
+    assert np.array_equal(net.layers.get_weights(), w0)                 # every weight restored exactly
+    analytic = raw_gradients.analytical_gradients(net, X, Y)
+    ng = raw_gradients.numerical_gradients(net, X, Y, 4e-3)
+    ne = raw_gradients.numerical_gradients(net, X, Y, 4e-3, use_graph=False)
+    assert np.array_equal(ng, ne)
+    assert relerr(analytic, ng) < 2e-3, relerr(analytic, ng)
+    # against the float64 oracle's analytic gradient as well
+    ora = build_oracle(ishape, spec, "cxent", "sgd", seed=2)
+    ora.learn_batch(X, Y, update=False)
+    assert relerr(ng, ora.get_gradients()) < 2e-3
+    # a wrong backward pass must fail the check: scale one layer's gradient
+    class Broken(type(net)):
+        def get_gradients(self, unfold=True):
+            g = super().get_gradients(unfold)
+            g[:5] *= 1.5
+            return g
+    net.__class__ = Broken
+    assert not bf.gradientcheck.run(net, X, Y, epsilon=4e-3, display=False)
+    with pytest.raises(RuntimeError, match="Gradient Check failed"):
+        bf.gradientcheck.run(net, X, Y, epsilon=4e-3, throw=True, display=False)
