@@ -8,8 +8,23 @@ import torch
 import torch.distributed as td
 
 
+_local = {"depth": 0}
+
+
+class local_mode:
+    """`with dist.local_mode(): ...` -- inside a multi-rank job, build and run networks that are NOT data-parallel
+    (world_size() reports 1): single-rank baselines in parity tests, per-rank evaluation."""
+
+    def __enter__(self):
+        _local["depth"] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _local["depth"] -= 1
+
+
 def initialized():
-    return td.is_available() and td.is_initialized()
+    return td.is_available() and td.is_initialized() and _local["depth"] == 0
 
 
 def world_size():

@@ -16,7 +16,7 @@ import numpy as np
 from .raw_gradients import analytical_gradients, numerical_gradients
 from .analyze_difference import analyze_difference_matrices, get_results
 
-MIN_EPSILON = 2e-3
+MIN_EPSILON = 4e-3
 
 
 def run(network, X=None, Y=None, epsilon=1e-5, throw=False, display=True):

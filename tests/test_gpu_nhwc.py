@@ -277,3 +277,57 @@ def test_cfg3_full_size_properties(bf):
     g2 = net.get_gradients(); net.zero_gradients()
     close(g, g1 + g2, 1e-4)
     assert abs(full["cost"] * 4096 - (h1["cost"] + h2["cost"]) * 2048) <= 1e-4 * abs(full["cost"] * 4096)
+
+
+def test_xp_conv_net_large_flatten_feeds_skinny_dense(bf, O):
+    """The reference's xperiments/xp_conv.py network under TF32: Conv32 -> ReLU -> Conv64 -> Pool2 -> ReLU -> Flatten ->
+    Dense10 on 1x28x28.  The flattened channels-last activation has k = 64*12*12 = 9216 features, more than the skinny
+    Dense kernels hold in shared memory (k <= 2560 for n = 10): the channels-last shortcut must step aside for a layout
+    change + the plain Dense path instead of failing."""
+    assert not bf._lib.lib.bf_dense_cl_supported(9216, 10) and bf._lib.lib.bf_dense_cl_supported(512, 10)
+    spec = [("conv", 32, 3, 3, "linear"), ("act", "relu"), ("conv", 64, 3, 3, "linear"), ("pool", 2), ("act", "relu"),
+            ("flatten",), ("dense", 10, "softmax")]
+    net = build_b200((1, 28, 28), spec, "cxent", "adam", seed=3)
+    ora = build_oracle((1, 28, 28), spec, "cxent", "adam", seed=3)
+    rs = np.random.RandomState(4)
+    X, Y = rs.randn(9, 1, 28, 28), onehot(rs, 9, 10)
+    a, b = net.learn_batch(X, Y, update=False), ora.learn_batch(X, Y, update=False)
+    close(a["cost"], b["cost"])
+    close(net.get_gradients(), ora.get_gradients(), 3e-2)
+    assert net.layers.layers[-1].inputs.cl_flat is None
+    for _ in range(2):
+        a, b = net.learn_batch(X, Y), ora.learn_batch(X, Y)
+        close(a["cost"], b["cost"], 2e-2)
+
+
+def test_workspace_regrowth_recaptures_graphs(bf):
+    """A CUDA graph has the scratch workspace's address baked in: when a later, larger call makes the workspace grow, the
+    old block stays allocated and the graph is captured again before its next replay -- the trajectory keeps
+    matching an eager twin bit for bit."""
+    from brainforge_b200 import device
+    net, _ = _cfg3(bf, 8, use_graph=True)
+    twin, _ = _cfg3(bf, 8)
+    rs = np.random.RandomState(9)
+    X, Y = rs.randn(8, 3, 30, 30), onehot(rs, 8, 10)
+    for _ in range(3):
+        a, b = net.learn_batch(X, Y), twin.learn_batch(X, Y)
+        assert a["cost"] == b["cost"]
+    gen = device.workspace_generation()
+    device._ensure_workspace(device._state["workspace"].numel() + (64 << 20))        # what a larger predict() would trigger
+    assert device.workspace_generation() == gen + 1 and device._state["ws_retired"]
+    device._state["ws_retired"][-1].fill_(255)                 # a replay through the stale address would now read garbage
+    for _ in range(3):
+        a, b = net.learn_batch(X, Y), twin.learn_batch(X, Y)
+        assert a["cost"] == b["cost"]
+    assert np.array_equal(net.layers.get_weights(), twin.layers.get_weights())
+
+
+def test_fill_zero_clears_non_finite_values(bf):
+    """zero_gradients / shuffle must clear NaN and Inf (0 * NaN = NaN: ADVICE r1)."""
+    a = bf.DeviceArray.from_host(np.array([np.nan, np.inf, -np.inf, 1.0, 2.0]))
+    a.fill_zero()
+    assert np.array_equal(a.numpy(), np.zeros(5))
+    a = bf.DeviceArray.from_host(np.array([np.nan, 3.0]))
+    a *= 0
+    assert np.array_equal(a.numpy(), np.zeros(2))
+    assert np.array_equal(bf.DeviceArray.empty(7).fill(2.5).numpy(), np.full(7, 2.5))
