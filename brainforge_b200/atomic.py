@@ -595,14 +595,14 @@ class LSTMOp:
 
 
 # --------------------------------------------------------------------------- operand handling on the TF32 path
-_RZ, _RNA = ("rz", "rz"), ("rna", "rna")
+_TMA, _RNA = ("tma", "tma"), ("rna", "rna")
 
 
 def tf32_operand_modes(kind, learn=True, **s):
     """How the kernel family that `kind` + shape selects on the TF32 path hands its two operands to
-    `tcgen05.mma.kind::tf32`: {site: (mode_A, mode_B) | None}.  "rz": raw FP32 staged by TMA, the tensor core drops
-    the low 13 mantissa bits; "rna": rounded to nearest by the SIMT operand builder (cvt.rna.tf32.f32); None: the
-    site runs FP32 FMAs (no tensor core).  This is the documentation of record for the stated TF32 bounds
+    `tcgen05.mma.kind::tf32`: {site: (mode_A, mode_B) | None}.  "tma": staged by a tensor map of type TFLOAT32 (the TMA
+    unit rounds FP32 to TF32, to nearest, while copying); "rna": rounded to nearest, ties away, by the SIMT operand
+    builder (cvt.rna.tf32.f32); None: the site runs FP32 FMAs (no tensor core).  No operand reaches an MMA unrounded.  This is the documentation of record for the stated TF32 bounds
     (DESIGN.md 4); tests/test_gpu_tf32_emulated.py feeds it to the emulating oracle.  `learn`: inside learn_batch
     (first-layer filter gradient un-pools in-kernel) rather than op by op."""
     if precision() != _lib.PREC["tf32"]:
@@ -610,22 +610,22 @@ def tf32_operand_modes(kind, learn=True, **s):
     if kind == "dense":
         if s["n"] <= 32:
             return {"dense.fwd": None, "dense.dW": None, "dense.dX": None}
-        return {site: (_RZ if L.bf_dense_tma_supported(s["m"], s["k"], s["n"], i) else _RNA)
+        return {site: (_TMA if L.bf_dense_tma_supported(s["m"], s["k"], s["n"], i) else _RNA)
                 for i, site in enumerate(("dense.fwd", "dense.dW", "dense.dX"))}
     if kind == "conv":
         route = ConvolutionOp._route(s.get("nhwc", False), s["ic"], s["iy"], s["ix"], s["nf"], s["fy"], s["fx"], "valid", "linear")
         if route == "nhwc":
-            return {"conv.fwd": _RZ, "conv.dF": _RZ, "conv.dX": _RZ}
+            return {"conv.fwd": _TMA, "conv.dF": _TMA, "conv.dX": _TMA}
         if route == "c3":
             # forward: pixel stream and filter rounded while they are re-laid; filter gradient: patch rows rounded by the
-            # builder warps, E either rebuilt (rounded) by them from the pooling layer's delta (learn_batch) or a raw TMA
+            # builder warps, E either rebuilt (rounded) by them from the pooling layer's delta (learn_batch) or a TMA
             # box; the data gradient of a first layer runs on the NCHW gather kernel
-            return {"conv.fwd": _RNA, "conv.dF": _RNA if (learn and s.get("unpool", False)) else ("rna", "rz"), "conv.dX": _RNA}
+            return {"conv.fwd": _RNA, "conv.dF": _RNA if (learn and s.get("unpool", False)) else ("rna", "tma"), "conv.dX": _RNA}
         return {"conv.fwd": _RNA, "conv.dF": _RNA, "conv.dX": _RNA}
     if kind == "lstm":
         zd = s["D"] + s["H"]
         tma = zd % 4 == 0
-        return {"lstm.fwd": _RZ if tma else _RNA, "lstm.dZ": _RZ, "lstm.dW": _RZ if tma else _RNA}
+        return {"lstm.fwd": _TMA if tma else _RNA, "lstm.dZ": _TMA, "lstm.dW": _TMA if tma else _RNA}
     raise ValueError(kind)
 
 

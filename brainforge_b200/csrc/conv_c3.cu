@@ -577,23 +577,29 @@ conv_c3_df_kernel(const __grid_constant__ CUtensorMap mapE, const float* __restr
 }
 
 // dF[f][r] = sum_cta partial[cta][r][f] (r = (c,ky,kx) in the reference's order);  db[f] = sum_cta partial[cta][Mrows][f]
-// block = 32 consecutive outputs x 8 slices of the CTA range; a fixed-order shared-memory tree adds the slices.
-__global__ void __launch_bounds__(256)
+// block = 32 consecutive outputs x 32 slices of the CTA range (a thread adds ~5 partials: the kernel is a chain of
+// dependent L2 latencies, so the chain is kept short); a fixed-order shared-memory tree adds the slices.
+constexpr int C3_RED_SLICES = 32;
+__global__ void __launch_bounds__(32 * C3_RED_SLICES)
 conv_c3_df_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
                          int nctas, int Mrows, int nf) {
-  __shared__ float red[8][33];
+  __shared__ float red[C3_RED_SLICES][33];
   pdl_launch_dependents();
   pdl_wait();
   const int total = nf * (Mrows + 1);
   const int o = blockIdx.x * 32 + threadIdx.x, zs = threadIdx.y;
   float s = 0.f;
   if (o < total)
-    for (int z = zs; z < nctas; z += 8) s += partial[(size_t)z * total + o];
+    for (int z = zs; z < nctas; z += C3_RED_SLICES) s += partial[(size_t)z * total + o];
   red[zs][threadIdx.x] = s;
   __syncthreads();
+#pragma unroll
+  for (int w = C3_RED_SLICES / 2; w >= 1; w >>= 1) {
+    if (zs < w) red[zs][threadIdx.x] += red[zs + w][threadIdx.x];
+    __syncthreads();
+  }
   if (zs == 0 && o < total) {
-    const float sum = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x])) +
-                      ((red[4][threadIdx.x] + red[5][threadIdx.x]) + (red[6][threadIdx.x] + red[7][threadIdx.x]));
+    const float sum = red[0][threadIdx.x];
     const int r = o / nf, f = o - r * nf;        // partial rows are [r][f]: consecutive threads -> consecutive filters
     if (r == Mrows) { if (db) db[f] = sum; }
     else dF[(size_t)f * Mrows + r] = sum;
@@ -767,7 +773,7 @@ static int c3_backward_filter_impl(const float* X, const float* E, const float* 
 #undef BF_C3DF_CASE
 #undef BF_C3DF_LAUNCH
   BF_LAUNCH_CHECK();
-  launch_pdl(conv_c3_df_reduce_kernel, dim3((nf * (Mrows + 1) + 31) / 32), dim3(dim3(32, 8)), 0, s, (const float*)ws, dF, db, ctas, Mrows, nf);
+  launch_pdl(conv_c3_df_reduce_kernel, dim3((nf * (Mrows + 1) + 31) / 32), dim3(32, C3_RED_SLICES), 0, s, (const float*)ws, dF, db, ctas, Mrows, nf);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;

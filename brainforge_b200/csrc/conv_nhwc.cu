@@ -368,18 +368,24 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
 }
 
 // dF[f][c][tap] = sum_z partial[z][c/32][tap][f][c%32];  db[f] = sum_z partial[z][0][ntaps][f][0]
-// Threads walk the PARTIAL's own order (32 channels innermost), so every split is read with full 128-byte lines;
-// the (small) result is scattered into the reference's (nf, ic, fy, fx) order.
-__global__ void conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
-                                           int nsplit, int nch, int ntaps, int nf, int ic) {
+// Threads walk the PARTIAL's own order (32 channels innermost), so every split is read with full 128-byte lines; the
+// (small) result is scattered into the reference's (nf, ic, fy, fx) order.  block = 32 outputs x 16 slices of the split
+// range: a thread adds ~9 partials instead of ~148 (the kernel is latency-, not bandwidth-bound), then a fixed-order
+// shared-memory tree adds the slices (deterministic).
+constexpr int DF_RED_SLICES = 16;
+__global__ void __launch_bounds__(32 * DF_RED_SLICES)
+conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
+                           int nsplit, int nch, int ntaps, int nf, int ic) {
+  __shared__ float red[DF_RED_SLICES][33];
   pdl_launch_dependents();
   pdl_wait();
   const long nmain = (long)nch * ntaps * nf * 32, total = nmain + nf;
   const size_t zstride = (size_t)nch * (ntaps + 1) * 128 * 32;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    size_t off;
-    long dst;
+  const long i = (long)blockIdx.x * 32 + threadIdx.x;
+  const int zs = threadIdx.y;
+  size_t off = 0;
+  long dst = 0;
+  if (i < total) {
     if (i < nmain) {
       const int cl = (int)(i & 31);
       long r = i >> 5;
@@ -393,16 +399,19 @@ __global__ void conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, fl
       off = ((size_t)ntaps * 128 + f) * 32;
       dst = -1 - f;
     }
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int z = 0;
-    for (; z + 4 <= nsplit; z += 4) {
-      s0 += partial[(size_t)z * zstride + off];
-      s1 += partial[(size_t)(z + 1) * zstride + off];
-      s2 += partial[(size_t)(z + 2) * zstride + off];
-      s3 += partial[(size_t)(z + 3) * zstride + off];
-    }
-    for (; z < nsplit; ++z) s0 += partial[(size_t)z * zstride + off];
-    const float sum = (s0 + s1) + (s2 + s3);
+  }
+  float s = 0.f;
+  if (i < total)
+    for (int z = zs; z < nsplit; z += DF_RED_SLICES) s += partial[(size_t)z * zstride + off];
+  red[zs][threadIdx.x] = s;
+  __syncthreads();
+#pragma unroll
+  for (int w = DF_RED_SLICES / 2; w >= 1; w >>= 1) {
+    if (zs < w) red[zs][threadIdx.x] += red[zs + w][threadIdx.x];
+    __syncthreads();
+  }
+  if (zs == 0 && i < total) {
+    const float sum = red[0][threadIdx.x];
     if (dst >= 0) dF[dst] = sum;
     else if (db) db[-1 - dst] = sum;
   }
@@ -724,8 +733,8 @@ int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, floa
   BF_DF_CASE(1) BF_DF_CASE(2) BF_DF_CASE(4)
 #undef BF_DF_CASE
   BF_LAUNCH_CHECK();
-  launch_pdl(conv_df_reduce_nhwc_kernel, dim3(ew_grid((size_t)nf * ic * ntaps + nf, 256)), dim3(256), 0, s, (const float*)ws, dF, db, nsplit,
-                                                                                         nch, ntaps, nf, ic);
+  launch_pdl(conv_df_reduce_nhwc_kernel, dim3((unsigned)(((size_t)nf * ic * ntaps + nf + 31) / 32)), dim3(32, DF_RED_SLICES), 0, s,
+             (const float*)ws, dF, db, nsplit, nch, ntaps, nf, ic);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;

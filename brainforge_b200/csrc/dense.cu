@@ -6,16 +6,30 @@
 
 namespace bf {
 
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, float* __restrict__ aux,
-                                     int rows, int N, int aux_row, int splits, int accumulate, long out_rs,
-                                     long out_cs) {
+constexpr int SK_RED_SLICES = 16;
+// block = 32 consecutive outputs x 16 slices of the split range, fixed-order tree (deterministic): the dense head's
+// 128-chunk partials used to be added by one thread per output, a 128-long chain of L2 latencies
+__global__ void __launch_bounds__(32 * SK_RED_SLICES)
+splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, float* __restrict__ aux,
+                     int rows, int N, int aux_row, int splits, int accumulate, long out_rs, long out_cs) {
+  __shared__ float red[SK_RED_SLICES][33];
   pdl_launch_dependents();
   pdl_wait();
-  long total = (long)rows * N;
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += ws[(long)z * total + i];
+  const long total = (long)rows * N;
+  const long i = (long)blockIdx.x * 32 + threadIdx.x;
+  const int zs = threadIdx.y;
+  float s = 0.f;
+  if (i < total)
+    for (int z = zs; z < splits; z += SK_RED_SLICES) s += ws[(long)z * total + i];
+  red[zs][threadIdx.x] = s;
+  __syncthreads();
+#pragma unroll
+  for (int w = SK_RED_SLICES / 2; w >= 1; w >>= 1) {
+    if (zs < w) red[zs][threadIdx.x] += red[zs + w][threadIdx.x];
+    __syncthreads();
+  }
+  if (zs == 0 && i < total) {
+    s = red[0][threadIdx.x];
     int r = (int)(i / N), c = (int)(i % N);
     float* dst;
     if (r == aux_row) dst = aux ? aux + c : nullptr;
@@ -28,8 +42,8 @@ int launch_splitk_reduce(const float* ws, float* out, float* aux, int rows, int 
                          int accumulate, long out_rs, long out_cs, cudaStream_t s) {
   long total = (long)rows * N;
   if (total == 0) return BF_OK;
-  launch_pdl(splitk_reduce_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, s, ws, out, aux, rows, N, aux_row, splits, accumulate,
-                                                             out_rs, out_cs);
+  launch_pdl(splitk_reduce_kernel, dim3((unsigned)((total + 31) / 32)), dim3(32, SK_RED_SLICES), 0, s, ws, out, aux, rows, N, aux_row,
+             splits, accumulate, out_rs, out_cs);
   BF_LAUNCH_CHECK();
   return BF_OK;
 }

@@ -28,23 +28,31 @@ F64 = np.float64
 # --------------------------------------------------------------------------
 # `tcgen05.mma.kind::tf32` reads 19 bits of each FP32 operand (sign, 8 exponent, 10 mantissa bits) and accumulates in
 # FP32.  With a policy active every contraction below narrows its operands to FP32 (the device's storage type) and
-# then to TF32 the way the kernel that runs this site does it -- "rz": the low 13 bits are dropped (raw FP32 handed
-# to the MMA by TMA), "rna": round to nearest, ties away (cvt.rna.tf32.f32 / `+0x1000` in the operand builders) --
-# and accumulates in float64.  What is left between this and the device is FP32 accumulation order only, so the
+# then to TF32 the way the kernel that runs this site does it -- "tma": staged by a tensor map of data type TFLOAT32
+# (the TMA unit rounds to nearest while it copies; tie rule TMA_TIES, pinned on the GPU by
+# tests/test_gpu_tf32_emulated.py::test_operand_rounding_modes_on_hardware), "rna": round to nearest, ties away
+# (cvt.rna.tf32.f32 / `+0x1000` in the SIMT operand builders), "rz": the low 13 bits dropped (what the MMA does to raw
+# FP32 bits that nobody rounded) -- and accumulates in float64.  Bias gradients that the kernels take from an all-ones
+# operand of the same MMA (db = ones^T E) see the rounded E as well.  What is left between this and the device is FP32 accumulation order only, so the
 # tensor-core path can be held to ~1e-5 instead of the ~5e-4 of operand rounding.  A policy is a callable
 # (site, layer_index) -> (mode_A, mode_B) | None, or a dict {site: (mode_A, mode_B)}; sites are "dense.fwd",
 # "dense.dW", "dense.dX", "conv.fwd", "conv.dF", "conv.dX", "lstm.fwd", "lstm.dZ", "lstm.dW", "fit.l1".
 _TF32 = {"policy": None, "layer": None, "fp32_storage": False}
+TMA_TIES = "even"      # tie rule of the TMA unit's FP32 -> TF32 conversion ("even" | "away")
 
 
 def tf32_round(x, mode):
-    """x narrowed to FP32, then to TF32 by `mode` ("rz" | "rna" | None = FP32 only); returned as float64."""
+    """x narrowed to FP32, then to TF32 by `mode` ("tma" | "rna" | "rne" | "rz" | None = FP32 only); returned as float64."""
     a = np.ascontiguousarray(x, dtype=np.float32)
     if mode is None:
         return a.astype(F64)
     u = a.view(np.uint32)
+    if mode == "tma":
+        mode = "rne" if TMA_TIES == "even" else "rna"
     if mode == "rna":
         u = u + np.uint32(0x1000)
+    elif mode == "rne":
+        u = u + np.uint32(0x0FFF) + ((u >> np.uint32(13)) & np.uint32(1))
     elif mode != "rz":
         raise ValueError(mode)
     return (u & np.uint32(0xFFFFE000)).view(np.float32).astype(F64)
@@ -65,12 +73,18 @@ class tf32_emulation:
         _TF32.update(self.saved)
 
 
-def _operands(site, A, B):
-    """The two operands of a contraction as the kernel behind `site` feeds them to the tensor core."""
+def _site_modes(site):
     pol = _TF32["policy"]
     if pol is None:
+        return None
+    return pol(site, _TF32["layer"]) if callable(pol) else pol.get(site)
+
+
+def _operands(site, A, B):
+    """The two operands of a contraction as the kernel behind `site` feeds them to the tensor core."""
+    if _TF32["policy"] is None:
         return A, B
-    modes = pol(site, _TF32["layer"]) if callable(pol) else pol.get(site)
+    modes = _site_modes(site)
     if modes is None:
         return (tf32_round(A, None), tf32_round(B, None)) if _TF32["fp32_storage"] else (A, B)
     return tf32_round(A, modes[0]), tf32_round(B, modes[1])
@@ -126,7 +140,7 @@ def dense_backward(X, E, W):
     dW = Xa.T @ Ea
     Eb, Wb = _operands("dense.dX", E, W)
     dX = Eb @ Wb.T
-    db = E.sum(axis=0)
+    db = (Ea if _site_modes("dense.dW") else E).sum(axis=0)      # ones-row of the same MMA: sees the rounded E
     return dW, db, dX
 
 
@@ -168,7 +182,7 @@ def conv_backward(X, E, F):
     db = E.sum((0,2,3), keepdims) ; dX = full(E, flip_hw(F)^T(1023))."""
     Xa, Ea = _operands("conv.dF", X, E)
     dF = conv_forward(Xa.transpose(1, 0, 2, 3), Ea.transpose(1, 0, 2, 3), "valid", site=None).transpose(1, 0, 2, 3)
-    db = E.sum(axis=(0, 2, 3), keepdims=True)
+    db = (Ea if _site_modes("conv.dF") else E).sum(axis=(0, 2, 3), keepdims=True)   # all-ones operand of the same MMA
     Eb, Fb = _operands("conv.dX", E, F)
     dX = conv_forward(Eb, Fb[:, :, ::-1, ::-1].transpose(1, 0, 2, 3), "full", site=None)
     return np.ascontiguousarray(dF), db, dX
@@ -444,7 +458,7 @@ def lstm_backward(Z, O, E, W, cache, activation="tanh"):
             E[t - 1] += deltaZ[t, :, D:]
     Za, dga = _operands("lstm.dW", Z, dgates)
     nablaW = np.matmul(Za.transpose(0, 2, 1), dga).sum(axis=0)
-    nablab = np.sum(dgates, axis=(0, 1))
+    nablab = np.sum(dga if _site_modes("lstm.dW") else dgates, axis=(0, 1))
     return deltaZ[:, :, :D], nablaW, nablab
 
 

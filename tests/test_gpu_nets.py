@@ -267,11 +267,12 @@ def test_gradientcheck_run_on_device(cfg, capsys):
     ng = raw_gradients.numerical_gradients(net, X, Y, 4e-3)
     ne = raw_gradients.numerical_gradients(net, X, Y, 4e-3, use_graph=False)
     assert np.array_equal(ng, ne)
-    assert relerr(analytic, ng) < 2e-3, relerr(analytic, ng)
+    tol = 2e-3 if cfg == "mlp" else 1e-2        # max-pool kinks inside the finite step
+    assert relerr(analytic, ng) < tol, relerr(analytic, ng)
     # against the float64 oracle's analytic gradient as well
     ora = build_oracle(ishape, spec, "cxent", "sgd", seed=2)
     ora.learn_batch(X, Y, update=False)
-    assert relerr(ng, ora.get_gradients()) < 2e-3
+    assert relerr(ng, ora.get_gradients()) < tol
     # a wrong backward pass must fail the check: scale one layer's gradient
     class Broken(type(net)):
         def get_gradients(self, unfold=True):

@@ -1,8 +1,8 @@
 """The tensor-core path against the TF32-EMULATING oracle, at the benchmarked shapes.
 
 `oracle.bf_oracle.tf32_emulation(policy)` narrows both operands of every contraction to TF32 the way the kernel
-behind that site feeds the tensor core ("rz": raw FP32 handed over by TMA, the MMA drops the low 13 mantissa bits;
-"rna": cvt.rna.tf32 / `+0x1000` in the SIMT operand builders) and accumulates in float64, so what remains between
+behind that site feeds the tensor core ("tma": rounded to nearest by the TMA unit of a TFLOAT32 tensor map; "rna":
+cvt.rna.tf32 / `+0x1000` in the SIMT operand builders) and accumulates in float64, so what remains between
 the oracle and the device is FP32 accumulation order.  That turns the 5e-3 / 3e-2 operand-rounding bounds of
 test_gpu_tf32.py into EMU_TOL below -- tight enough that a 0.1 % kernel error on the benchmarked path fails.  The
 float64 comparison stays as the second, looser assertion.
@@ -61,13 +61,35 @@ def O():
     return bf_oracle
 
 
-RZ, RNA = ("rz", "rz"), ("rna", "rna")
+def test_operand_rounding_modes_on_hardware(bf, O):
+    """Pins what the emulation assumes about the two ways operands reach `tcgen05.mma.kind::tf32`: probes whose FP32 bit
+    patterns sit on, just below and just above a TF32 rounding tie go through a TMA-staged GEMM (Dense, k % 4 == 0) and a
+    gather-staged one (k % 4 != 0) against a unit weight column; the products reveal the conversion bit for bit."""
+    probes = np.array([1 + 2.0 ** -11, 1 + 3 * 2.0 ** -11, 1 + 2.0 ** -11 - 2.0 ** -23, 1 + 2.0 ** -11 + 2.0 ** -23,
+                       -(1 + 2.0 ** -11), -(1 + 3 * 2.0 ** -11), 1 + 2.0 ** -12, 1 + 7 * 2.0 ** -13, 3.0, 0.1], dtype=np.float32)
+    op = bf.atomic.DenseOp()
+    found = {}
+    for name, k in (("tma", 64), ("rna", 66)):
+        assert bool(bf._lib.lib.bf_dense_tma_supported(len(probes), k, 64, 0)) == (name == "tma")
+        X = np.zeros((len(probes), k), np.float32)
+        X[:, 0] = probes
+        W = np.zeros((k, 64), np.float32)
+        W[0, :] = 1.0
+        got = op.forward(X, W)[:, 3].astype(np.float32)
+        match = [m for m in ("rne", "rna", "rz") if np.array_equal(got, O.tf32_round(probes, m).astype(np.float32))]
+        found[name] = match
+        record("rounding." + name + "." + "/".join(match or ["none"]), 0.0)
+    assert "rna" in found["rna"] and "rne" not in found["rna"], found
+    assert ("rne" if O.TMA_TIES == "even" else "rna") in found["tma"] and "rz" not in found["tma"], found
+
+
+TMA, RNA = ("tma", "tma"), ("rna", "rna")
 
 
 # ------------------------------------------------------------------------------------------------ single ops
 @pytest.mark.parametrize("m,k,n", [(128, 64, 128), (20, 784, 60), (257, 130, 129), (4096, 512, 64)])
 def test_dense_emulated(bf, O, m, k, n):
-    """Dense with n > 32 columns: TMA-staged tcgen05 GEMMs, operands handed over raw (rz)."""
+    """Dense with n > 32 columns: TMA-staged tcgen05 GEMMs where the shape allows, the gather-staged core otherwise."""
     rs = np.random.RandomState(m + k + n)
     X, W, b, E = rs.randn(m, k), rs.randn(k, n) * 0.2, rs.randn(n), rs.randn(m, n)
     op = bf.atomic.DenseOp()
@@ -78,7 +100,7 @@ def test_dense_emulated(bf, O, m, k, n):
     tag = "dense(%d,%d,%d)" % (m, k, n)
     close(tag + ".fwd", op.forward(X, W, b), r, EMU_TOL)
     dW, db, dX = op.backward(X, E, W)
-    close(tag + ".dW", dW, rW, EMU_TOL); close(tag + ".dX", dX, rX, EMU_TOL); close(tag + ".db", db, rb, 1e-5)
+    close(tag + ".dW", dW, rW, EMU_TOL); close(tag + ".dX", dX, rX, EMU_TOL); close(tag + ".db", db, rb, EMU_TOL)
     close(tag + ".fwd.f64", op.forward(X, W, b), O.dense_forward(X, W, b), F64_TOL)
 
 
@@ -99,7 +121,7 @@ def test_conv_emulated(bf, O, shape):
     with O.tf32_emulation(pol):
         rF, rb, rX = O.conv_backward(A, E, F)
     dF, db, dX = op.backward(X=A, E=E, F=F)
-    close(tag + ".dF", dF, rF, EMU_TOL); close(tag + ".db", db, rb, 1e-5); close(tag + ".dX", dX, rX, EMU_TOL)
+    close(tag + ".dF", dF, rF, EMU_TOL); close(tag + ".db", db, rb, EMU_TOL); close(tag + ".dX", dX, rX, EMU_TOL)
     r64 = O.conv_backward(A, E, F)
     close(tag + ".dF.f64", dF, r64[0], F64_TOL); close(tag + ".dX.f64", dX, r64[2], F64_TOL)
 
@@ -146,7 +168,7 @@ def test_fitness_bench_shape_emulated(bf, O):
     G = ne.population.individuals
     fit = ne.batch_fitness(G, X, Y).ravel()
     Gh = np.asarray(G, dtype=np.float32)
-    with O.tf32_emulation({"fit.l1": ("rz", "rna")}):
+    with O.tf32_emulation({"fit.l1": ("tma", "rna")}):
         ref = O.fitness_mlp_logsoftmax(Gh, X.astype(np.float32), Y, 784, 60, 10)
     # the hidden layer's sigmoid uses the SFU forms (__expf, __fdividef) and the +-10 weights give logits of several
     # hundred: FP32 evaluation of the head moves a fitness by ~1e-5 relative

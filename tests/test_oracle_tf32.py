@@ -21,9 +21,14 @@ def test_tf32_round_modes_bit_level():
     assert O.tf32_round(1.0 + 2 ** -11, "rna") == 1.0 + 2 ** -10                         # ties away from zero (cvt.rna)
     assert O.tf32_round(-(1.0 + 2 ** -11), "rna") == -(1.0 + 2 ** -10)
     assert O.tf32_round(1.0 + 2 ** -11, "rz") == 1.0
+    rne = O.tf32_round(x, "rne")
+    assert np.all(bits(rne) & 0x1FFF == 0) and np.all(np.abs(rne - np.float32(x)) <= ulp / 2 * (1 + 1e-6))
+    assert O.tf32_round(1.0 + 2 ** -11, "rne") == 1.0 and O.tf32_round(1.0 + 3 * 2 ** -11, "rne") == 1.0 + 2 ** -9   # ties to even
+    assert O.tf32_round(1.0 + 2 ** -11 + 2 ** -23, "rne") == 1.0 + 2 ** -10
+    assert np.array_equal(O.tf32_round(x, "tma"), rne if O.TMA_TIES == "even" else rna)
     assert np.array_equal(O.tf32_round(x, None), np.float32(x).astype(np.float64))       # None: FP32 storage only
     with pytest.raises(ValueError):
-        O.tf32_round(x, "rne")
+        O.tf32_round(x, "stochastic")
 
 
 def test_policy_applies_per_site_and_per_layer():
@@ -77,6 +82,6 @@ def test_conv_lstm_fitness_sites():
     assert np.allclose(f0, f0c, rtol=1e-13)
     one = np.array([O.fitness(O.Stack((4,), [("dense", 5, "sigmoid"), ("dense", 3, "softmax")], cost="cxent"), g, Xf, Yf) for g in G])
     assert np.allclose(f0, one, rtol=1e-10)
-    with O.tf32_emulation({"fit.l1": ("rz", "rna")}):
+    with O.tf32_emulation({"fit.l1": ("tma", "rna")}):
         f1 = O.fitness_mlp_logsoftmax(G, Xf, Yf, 4, 5, 3)
     assert 1e-7 < np.linalg.norm(f1 - f0) / np.linalg.norm(f0) < 1e-2

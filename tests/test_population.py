@@ -115,7 +115,7 @@ def test_resident_fitness_matches_oracle_and_upload_path(bf, fx):
     X, Y = fx["X"], fx["Y"]
     ne.population.update(None, 0, X=X, Y=Y)
     assert relerr(ne.population.grades, fx["grades0"]) < 1e-2                      # TF32 operands vs the float64 reference
-    with O.tf32_emulation({"fit.l1": ("rz", "rna")}):
+    with O.tf32_emulation({"fit.l1": ("tma", "rna")}):
         emu = O.fitness_mlp_logsoftmax(fx["individuals0"].astype(np.float32), X.astype(np.float32), Y, nin, nh, nout)
     assert relerr(ne.population.grades, emu) < 1e-4
     up = ne.batch_fitness(fx["individuals0"], X, Y).ravel()
