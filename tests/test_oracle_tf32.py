@@ -69,7 +69,10 @@ def test_conv_lstm_fitness_sites():
     for got, want in ((dF, ref[0]), (dX, ref[2])):
         e = np.linalg.norm(got - want) / np.linalg.norm(want)
         assert 1e-6 < e < 3e-3
-    assert np.array_equal(db, ref[1])                                                     # reductions are not tensor-core sites
+    # db comes from the all-ones operand of the dF MMA: it sees E as that site rounds it
+    assert np.array_equal(db, O.tf32_round(y, "rz").sum(axis=(0, 2, 3), keepdims=True))
+    with O.tf32_emulation({"conv.fwd": ("rz", "rz")}):
+        assert np.array_equal(O.conv_backward(A, y, F)[1], ref[1])            # no tensor-core site: the plain sum
     X, W, b = rs.randn(4, 3, 5), rs.randn(13, 32) * 0.3, rs.randn(32) * 0.1
     with O.tf32_emulation({"lstm.fwd": ("rz", "rz")}):
         o1 = O.lstm_forward(X, W, b)[0]
