@@ -340,6 +340,206 @@ static int launch_skinny_bwd(const float* X, const float* E, const float* W, flo
   return launch_splitk_reduce((const float*)ws, dW, db, k + 1, n, k, chunks, accumulate, n, 1, s);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused output head: Dense(n <= 32, act) forward + cost value + cost derivative + Dense backward in ONE kernel, for the
+// last layer of a network inside learn_batch (layers/core.py:27-39 + metrics/costs.py:19-37 + metrics/metrics.py:15-16 +
+// learner/backpropagation.py:19-22).  A CTA owns a chunk of R rows: their X rows are staged in shared memory ONCE and
+// serve both directions (forward dot products, then dW = X^T delta and dX = delta W^T); W (k x n) sits next to them.
+// The unfused sequence -- skinny forward, cost/delta kernel, accuracy, skinny backward, split reduction -- read X
+// twice and cost five launches of ~4-20 us each for ~8 MB of data (cfg3 head: 51 us; HBM floor ~3 us).
+//   out[m][n]  = act(X W + b)                                   (stored: layer.output)
+//   cost      += cost(out, Y) partials (double, per CTA; the last CTA adds them in CTA order: deterministic)
+//   hits      += argmax(out) == argmax(Y)
+//   delta      = (out - Y) * w_row * act'(out)                 (softmax / linear: act' = 1, activation_op.py:79,134)
+//   partial[cta] = [X^T delta ; column sums of delta]          (added by splitk_reduce_kernel in CTA order)
+//   dX[m][k]   = delta W^T                                     (physical column order of X)
+__device__ unsigned int g_head_ticket = 0;
+__device__ unsigned int g_head_hits = 0;
+
+template <int NT>
+__global__ void __launch_bounds__(256)
+dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
+                  const float* __restrict__ Y, const float* __restrict__ sw_rows, float* __restrict__ out,
+                  float* __restrict__ partial, float* __restrict__ dX, double* __restrict__ cost_partial,
+                  float* __restrict__ cost_out, float* __restrict__ hits_out, int m, int k, int n, int R, int act,
+                  int cost_kind, int pc, int phw) {
+  extern __shared__ __align__(16) float hs[];
+  constexpr int PITCH = NT == 4 ? 4 : NT + 4;
+  float* sW = hs;                                   // [k][PITCH], rows in X's PHYSICAL column order
+  float* sX = sW + (size_t)k * PITCH;               // [R][k]
+  float* sD = sX + (size_t)R * k;                   // [R][NT]  delta
+  __shared__ double s_cost[8];
+  __shared__ unsigned s_hits[8];
+  __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m0 = blockIdx.x * R;
+  int rows = m - m0;
+  if (rows > R) rows = R;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- stage W (permuted rows) and the chunk's X rows
+  for (int i = threadIdx.x; i < k * PITCH; i += blockDim.x) sW[i] = 0.f;
+  __syncthreads();
+  const int total = k * n;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < total ? __ldg(W + i) : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) {
+        const int kl = i / n;
+        const int kk = pc ? (kl % phw) * pc + kl / phw : kl;
+        sW[kk * PITCH + (i - kl * n)] = v[u];
+      }
+    }
+  }
+  if ((k & 3) == 0 && (((uintptr_t)X) & 15) == 0) {
+    const int k4 = k >> 2;
+    for (int i = threadIdx.x; i < rows * k4; i += blockDim.x) {
+      const int r = i / k4, c = i - r * k4;
+      reinterpret_cast<float4*>(sX)[(size_t)r * k4 + c] = __ldcs(reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * k) + c);
+    }
+  } else {
+    for (int i = threadIdx.x; i < rows * k; i += blockDim.x) sX[i] = __ldg(X + (size_t)m0 * k + i);
+  }
+  __syncthreads();
+  // ---- forward + cost + delta: one warp per row, lanes split K
+  double cost_acc = 0.0;
+  unsigned hits = 0;
+  for (int r = warp; r < rows; r += 8) {
+    float acc[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j] = 0.f;
+    const float* xr = sX + (size_t)r * k;
+#pragma unroll 4
+    for (int kk = lane; kk < k; kk += 32) {
+      const float x = xr[kk];
+      const float4* wr = reinterpret_cast<const float4*>(sW + kk * PITCH);
+#pragma unroll
+      for (int q = 0; q < NT / 4; ++q) {
+        const float4 w4 = wr[q];
+        acc[4 * q + 0] = fmaf(x, w4.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(x, w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(x, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x, w4.w, acc[4 * q + 3]);
+      }
+    }
+    float mine = 0.f;                        // lane j ends up with column j
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const float t = warp_sum(acc[j]);
+      if (lane == j) mine = t;
+    }
+    const bool col = lane < n;
+    if (b && col) mine += __ldg(b + lane);
+    if (act == BF_ACT_SOFTMAX) {
+      const float mx = warp_max(col ? mine : -INFINITY);
+      const float e = col ? expf(mine - mx) : 0.f;
+      mine = e / warp_sum(e);
+    } else {
+      mine = act_fwd_rt(act, mine);
+    }
+    const size_t row = (size_t)(m0 + r);
+    const float tv = col ? __ldg(Y + row * n + lane) : 0.f;
+    if (col) out[row * n + lane] = mine;
+    // cost terms (metrics/costs.py:26-27,36-37,48-49), summed in double like bf_cost_value
+    double c = 0.0;
+    if (col) {
+      if (cost_kind == BF_COST_MSE) { const float d = mine - tv; c = 0.5 * (double)d * (double)d; }
+      else if (cost_kind == BF_COST_CXENT) { if (tv != 0.0f) c = -(double)tv * (double)logf(mine); }
+      else {
+        if (tv != 0.0f) c -= (double)tv * (double)logf(mine);
+        if (tv != 1.0f) c -= (double)(1.0f - tv) * (double)logf(1.0f - mine);
+      }
+    }
+    cost_acc += warp_sum(c);
+    if (hits_out) {                          // first-index argmax of both rows (np.argmax)
+      float bo = col ? mine : -INFINITY, bt = col ? tv : -INFINITY;
+      int ao = lane, at = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float vo = __shfl_xor_sync(0xffffffffu, bo, o), vt = __shfl_xor_sync(0xffffffffu, bt, o);
+        const int io = __shfl_xor_sync(0xffffffffu, ao, o), it = __shfl_xor_sync(0xffffffffu, at, o);
+        if (vo > bo || (vo == bo && io < ao)) { bo = vo; ao = io; }
+        if (vt > bt || (vt == bt && it < at)) { bt = vt; at = it; }
+      }
+      hits += (ao == at) ? 1u : 0u;
+    }
+    float d = mine - tv;                     // costs.py:19-21 (hinge is not routed here)
+    if (sw_rows) d *= __ldg(sw_rows + row);
+    d *= act_bwd_rt(act, mine);              // layers/core.py:35 (1 for softmax / linear)
+    if (lane < NT) sD[r * NT + lane] = col ? d : 0.f;
+  }
+  if (lane == 0) { s_cost[warp] = cost_acc; s_hits[warp] = hits; }
+  __syncthreads();
+  // ---- backward: thread = physical column kk (strided), rows of the chunk from shared memory
+  float* part = partial + (size_t)blockIdx.x * (k + 1) * n;
+  for (int kk = threadIdx.x; kk < k; kk += blockDim.x) {
+    const int kl = pc ? (kk % pc) * phw + kk / pc : kk;          // row of W / dW this physical column belongs to
+    float w[NT], acc[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { w[j] = sW[kk * PITCH + j]; acc[j] = 0.f; }
+    for (int r = 0; r < rows; ++r) {
+      const float x = sX[(size_t)r * k + kk];
+      const float4* e4 = reinterpret_cast<const float4*>(sD + r * NT);
+      float dx = 0.f;
+#pragma unroll
+      for (int q = 0; q < NT / 4; ++q) {
+        const float4 e = e4[q];
+        dx = fmaf(e.x, w[4 * q + 0], dx); dx = fmaf(e.y, w[4 * q + 1], dx);
+        dx = fmaf(e.z, w[4 * q + 2], dx); dx = fmaf(e.w, w[4 * q + 3], dx);
+        acc[4 * q + 0] = fmaf(x, e.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(x, e.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(x, e.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x, e.w, acc[4 * q + 3]);
+      }
+      if (dX) dX[(size_t)(m0 + r) * k + kk] = dx;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      if (j < n) part[(size_t)kl * n + j] = acc[j];
+  }
+  if (threadIdx.x < n) {                     // db partial = column sums of the chunk's delta
+    float sacc = 0.f;
+    for (int r = 0; r < rows; ++r) sacc += sD[r * NT + threadIdx.x];
+    part[(size_t)k * n + threadIdx.x] = sacc;
+  }
+  // ---- cost / hits: per-CTA partial, the last CTA to arrive adds them in CTA order
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+    unsigned h = 0;
+    for (int w8 = 0; w8 < 8; ++w8) { c += s_cost[w8]; h += s_hits[w8]; }
+    cost_partial[blockIdx.x] = c;
+    if (hits_out && h) atomicAdd(&g_head_hits, h);
+    __threadfence();
+    s_last = atomicAdd(&g_head_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double c = 0.0;
+    for (unsigned i = 0; i < gridDim.x; ++i) c += ((volatile double*)cost_partial)[i];
+    cost_out[0] = (float)c;
+    if (hits_out) hits_out[0] = (float)atomicExch(&g_head_hits, 0u);
+    g_head_ticket = 0;
+  }
+}
+
+// rows per CTA and shared-memory bytes of the fused head for a (k, n) layer; R = 0: does not fit
+static inline int head_rows(int m, int k, int n, size_t* smem_out) {
+  if (n > 32 || k < 1) return 0;
+  const int nt = skinny_nt(n), pitch = nt == 4 ? 4 : nt + 4;
+  for (int R = 32; R >= 4; R >>= 1) {
+    const size_t smem = ((size_t)k * pitch + (size_t)R * k + (size_t)R * nt) * sizeof(float);
+    if (smem <= 200 * 1024) {
+      // about two CTAs per SM: every CTA pays for staging W once, so more, smaller chunks only help until the machine is full
+      int r = 4;
+      while (r < R && (m + r - 1) / r > 2 * num_sms()) r <<= 1;
+      *smem_out = ((size_t)k * pitch + (size_t)r * k + (size_t)r * nt) * sizeof(float);
+      return r;
+    }
+  }
+  return 0;
+}
+
 // (rows x cols) -> (cols x rows): W^T as the K-major B operand of the TMA-fed forward GEMM
 __global__ void dense_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
   __shared__ float tile[32][33];
@@ -372,6 +572,43 @@ using namespace bf;
 extern "C" {
 
 int bf_dense_cl_supported(int k, int n) { return skinny_ok(1, k, n) ? 1 : 0; }
+
+int bf_dense_head_supported(int k, int n, int act, int cost) {
+  size_t smem;
+  return (head_rows(1 << 20, k, n, &smem) > 0 && act >= BF_ACT_LINEAR && act <= BF_ACT_SOFTMAX && cost >= BF_COST_MSE &&
+          cost <= BF_COST_BXENT) ? 1 : 0;
+}
+
+int bf_dense_head(const float* X, const float* W, const float* b, const float* Y, const float* sample_w, float* out,
+                  float* dW, float* db, float* dX, float* cost_result, float* hits_result, int m, int chan, int hw, int n,
+                  int act, int cost, int channels_last, int accumulate, void* stream) {
+  const int k = chan * hw;
+  BF_REQUIRE(m > 0 && k > 0 && n > 0 && X && W && Y && out && dW && db && cost_result, BF_ERR_ARG, "bf_dense_head: bad arguments");
+  BF_REQUIRE(bf_dense_head_supported(k, n, act, cost), BF_ERR_ARG, "bf_dense_head: unsupported layer (k=%d n=%d act=%d cost=%d)", k, n, act, cost);
+  cudaStream_t s = as_stream(stream);
+  size_t smem = 0;
+  const int R = head_rows(m, k, n, &smem);
+  const int chunks = (m + R - 1) / R;
+  const size_t part_bytes = ((size_t)chunks * (k + 1) * n * sizeof(float) + 255) & ~(size_t)255;
+  void* ws = nullptr;
+  int rc = workspace_require(part_bytes + (size_t)chunks * sizeof(double), &ws);
+  if (rc) return rc;
+  float* partial = (float*)ws;
+  double* cpart = (double*)((char*)ws + part_bytes);
+  const int nt = skinny_nt(n);
+  const int pc = channels_last ? chan : 0, phw = channels_last ? hw : 0;
+#define BF_HEAD(NT_)                                                                                                       \
+  if (nt == NT_) {                                                                                                         \
+    BF_CUDA(cudaFuncSetAttribute(dense_head_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    launch_pdl(dense_head_kernel<NT_>, dim3(chunks), dim3(256), smem, s, X, W, b, Y, sample_w, out, partial, dX, cpart,    \
+               cost_result, hits_result, m, k, n, R, act, cost, pc, phw);                                                  \
+  }
+  BF_HEAD(4) BF_HEAD(8) BF_HEAD(16) BF_HEAD(32)
+#undef BF_HEAD
+  BF_LAUNCH_CHECK();
+  set_last_path(0);
+  return launch_splitk_reduce(partial, dW, db, k + 1, n, k, chunks, accumulate, n, 1, s);
+}
 
 int bf_dense_tma_supported(int m, int k, int n, int site) {
   return (n > 32 && site >= 0 && site <= 2 && dense_tma_site(m, k, n, site)) ? 1 : 0;

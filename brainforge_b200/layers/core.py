@@ -34,6 +34,34 @@ class Dense(FFBase):
                                     accumulate=True, need_dX=need_dX)        # core.py:37-38 `+=`
         return dX
 
+    # ---- fused output head (learn_batch only): forward + cost + accuracy + cost' + backward of the LAST layer in one kernel
+    def head_supported(self, cost):
+        k = self.weights.shape[0]
+        return (type(self) is Dense and self.neurons <= 32 and cost.kind in ("mse", "cxent", "bxent") and
+                bool(_lib.lib.bf_dense_head_supported(k, self.neurons, _lib.ACT[str(self.activation)], _lib.COST[cost.kind])))
+
+    def learn_head(self, x, y, w, cost, cost_out, hits_out, need_dX=True):
+        """What `_fwd` -> cost.derivative_and_value -> [accuracy] -> `_bwd` compute for this layer, in one pass over x
+        (bf_dense_head): sets inputs / output, accumulates nabla_w / nabla_b, fills the step scalars, returns dX."""
+        from ..device import call, stream_ptr
+        m, n = x.shape[0], self.neurons
+        cl = x.cl_flat is not None
+        if cl:
+            c, yy, xx = x.cl_flat
+            chan, hw = c, yy * xx
+        else:
+            chan, hw = x.shape[1], 1
+        self.inputs = x
+        self.output = DeviceArray.empty(m, n)
+        dX = None
+        if need_dX:
+            dX = DeviceArray(DeviceArray.empty(m, chan * hw).t, cl_flat=x.cl_flat) if cl else DeviceArray.empty(m, chan * hw)
+        call(_lib.lib.bf_dense_head, x.pptr, self.weights.ptr, self.biases.ptr, y.ptr, w.ptr if w is not None else None,
+             self.output.ptr, self.nabla_w.ptr, self.nabla_b.ptr, dX.pptr if dX is not None else None, cost_out.ptr,
+             hits_out.ptr if hits_out is not None else None, m, chan, hw, n, _lib.ACT[str(self.activation)],
+             _lib.COST[cost.kind], 1 if cl else 0, 1, stream_ptr())
+        return dX
+
     def __str__(self):
         return "Dense-{}-{}".format(self.neurons, str(self.activation)[:5])
 

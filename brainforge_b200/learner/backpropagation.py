@@ -8,6 +8,8 @@ Gradients are batch SUMS (atomic/core_op.py:17-19) and the 1/m lives in the opti
 (optimizers/gradient_descent.py:9), so sharding the batch over ranks and all-reducing the sums with the
 GLOBAL m is algebraically exact.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -40,6 +42,7 @@ class Backpropagation(Learner):
         self.optimizer.initialize(nparams=self.layers.num_params)
         self.layers.flatten_parameters()
         self.use_graph = kw.get("use_graph", False)
+        self.fused_head = kw.get("fused_head", os.environ.get("BF_FUSED_HEAD", "1") != "0")
         if any(type(l).__name__ == "DropOut" for l in self.layers.layers):
             self.use_graph = False       # the mask is drawn on the host every forward pass: nothing to replay
         self._graphs = {}
@@ -104,13 +107,22 @@ class Backpropagation(Learner):
     def _step(self, x, y, wd, metrics, update, m_local, m_global_static):
         """Device-only part of learn_batch (capturable in a CUDA graph: no host sync inside)."""
         sc = self.layers.scalars()
-        preds = self.layers._fwd(x)
-        delta = self.cost.derivative_and_value(preds, y, wd, sc[0:1])   # cost of the PRE-update forward pass (:26)
-        if metrics:
-            _metrics.accuracy.value_into(preds, y, sc[1:2])
-        # learn_batch discards the delta w.r.t. the network input (learner/backpropagation.py:22 ignores the
-        # return value), so the first layer's dX contraction is not computed here; backpropagate() still does.
-        self._bwd(delta, need_input_delta=False)
+        last = self.layers.layers[-1]
+        if self.fused_head and len(self.layers.layers) > 1 and getattr(last, "head_supported", None) and last.head_supported(self.cost):
+            # output head in one kernel: last Dense forward, cost value (of the PRE-update forward pass, :26), accuracy,
+            # cost derivative and the layer's backward pass (bf_dense_head) -- five launches and a second read of its input less
+            below = self.layers._fwd(x, stop=len(self.layers.layers) - 1)
+            delta = last.learn_head(below, y, wd, self.cost, sc[0:1], sc[1:2] if metrics else None,
+                                    need_dX=len(self.layers.layers) > 2)
+            self._bwd(delta, need_input_delta=False, below_last=True)
+        else:
+            preds = self.layers._fwd(x)
+            delta = self.cost.derivative_and_value(preds, y, wd, sc[0:1])   # cost of the PRE-update forward pass (:26)
+            if metrics:
+                _metrics.accuracy.value_into(preds, y, sc[1:2])
+            # learn_batch discards the delta w.r.t. the network input (learner/backpropagation.py:22 ignores the
+            # return value), so the first layer's dX contraction is not computed here; backpropagate() still does.
+            self._bwd(delta, need_input_delta=False)
         m_global = m_global_static if m_global_static is not None else _dist.global_count(m_local)
         if _dist.world_size() > 1:
             if update and self.layers.symm is not None:
@@ -190,9 +202,9 @@ class Backpropagation(Learner):
         return lambda: self._read_scalars(metrics, m_local)
 
     # ------------------------------------------------------------------ pieces of the public API
-    def _bwd(self, error, need_input_delta=True):
+    def _bwd(self, error, need_input_delta=True, below_last=False):
         first = self.layers[1] if len(self.layers.layers) > 1 else None
-        for layer in self.layers[-1:0:-1]:
+        for layer in self.layers[(-2 if below_last else -1):0:-1]:
             if layer is first and not need_input_delta and getattr(layer, "_can_skip_dx", False):
                 error = layer._bwd(error, need_dX=False)
             else:

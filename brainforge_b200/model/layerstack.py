@@ -98,8 +98,9 @@ class LayerStack:
         return self.flat_grads[self._scalar_off:self._scalar_off + SEG_ALIGN]
 
     # ---- compute
-    def _fwd(self, x):
-        for layer in self.layers:
+    def _fwd(self, x, stop=None):
+        """Forward through every layer (or the layers before index `stop`)."""
+        for layer in (self.layers if stop is None else self.layers[:stop]):
             x = layer._fwd(x)
         return x
 

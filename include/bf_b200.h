@@ -115,6 +115,19 @@ BF_API int bf_dense_forward_cl(const float* X, const float* W, const float* b, f
 BF_API int bf_dense_backward_cl(const float* X, const float* E, const float* W, float* dW, float* db, float* dX, int m, int chan,
                          int hw, int n, int accumulate, void* stream);
 
+/* Fused output head for learn_batch: the LAST Dense layer (n <= 32 outputs) forward, cost value, accuracy count, cost
+ * derivative and the layer's backward pass in one kernel (+ one split reduction) -- layers/core.py:27-39,
+ * metrics/costs.py:19-37, metrics/metrics.py:15-16, learner/backpropagation.py:19-22,26-29.
+ *   out = act(X W + b);  cost_result[0] = cost(out, Y) (sum, not mean);  hits_result[0] = #(argmax out == argmax Y)
+ *   delta = (out - Y) [* sample_w[row]] * act'(out);  dW (+)= X^T delta;  db (+)= delta.sum(0);  dX = delta W^T
+ * X (m, chan*hw): with channels_last != 0 its columns are in physical (yx, c) order while W's rows keep the
+ * reference's (c, yx) order (as bf_dense_forward_cl); otherwise chan*hw is simply k.  sample_w, hits_result, dX may be
+ * NULL.  BF_COST_HINGE is not supported (its derivative is not out - Y). */
+BF_API int bf_dense_head_supported(int k, int n, int act, int cost);
+BF_API int bf_dense_head(const float* X, const float* W, const float* b, const float* Y, const float* sample_w, float* out,
+                  float* dW, float* db, float* dX, float* cost_result, float* hits_result, int m, int chan, int hw, int n,
+                  int act, int cost, int channels_last, int accumulate, void* stream);
+
 /* ---- convolution: atomic/tensor_op.py:6-75, llatomic/lltensor_op.py:9-40,75-121 ---- */
 /* Y = act(corr(A,F)) + bias   (bias AFTER the activation: layers/tensor.py:77-78).
  * A (im,ic,iy,ix) NCHW, F (nf,ic,fy,fx), bias (nf) or NULL, stride 1.

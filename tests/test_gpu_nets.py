@@ -283,3 +283,59 @@ def test_gradientcheck_run_on_device(cfg, capsys):
     assert not bf.gradientcheck.run(net, X, Y, epsilon=4e-3, display=False)
     with pytest.raises(RuntimeError, match="Gradient Check failed"):
         bf.gradientcheck.run(net, X, Y, epsilon=4e-3, throw=True, display=False)
+
+
+@pytest.mark.parametrize("case", ["cfg1", "mse_tanh", "bxent_sigmoid", "cfg3_channels_last", "single_dense", "cfg2_wide_k"])
+def test_fused_output_head_matches_unfused_and_oracle(case):
+    """bf_dense_head (last Dense forward + cost + accuracy + cost' + backward in one kernel) against the layer-by-layer
+    sequence it replaces and against the float64 oracle: cost, accuracy, outputs, every gradient, the delta handed to the
+    layer below, a 3-step trajectory; with and without per-sample weights; rows > one chunk and ragged."""
+    import brainforge_b200 as bf
+    ncls = 10
+    if case == "cfg1":
+        ishape, spec, cost, opt, batch = CFG["cfg1"] + (20,)
+    elif case == "mse_tanh":
+        ishape, spec, cost, opt, batch = (33,), [("dense", 17, "relu"), ("dense", 6, "tanh")], "mse", "momentum", 301
+        ncls = 6
+    elif case == "bxent_sigmoid":
+        ishape, spec, cost, opt, batch = (12,), [("dense", 9, "tanh"), ("dense", 4, "sigmoid")], "bxent", "sgd", 77
+        ncls = 4
+    elif case == "cfg3_channels_last":
+        ishape, spec, cost, opt, batch = CFG["cfg3"] + (70,)
+    elif case == "single_dense":
+        ishape, spec, cost, opt, batch = (40,), [("dense", 10, "softmax")], "cxent", "adam", 1000
+    else:
+        ishape, spec, cost, opt, batch = CFG["cfg2"] + (45,)
+    rs = np.random.RandomState(len(case))
+    X, Y = rs.randn(batch, *ishape), onehot(rs, batch, ncls)
+    w = rs.rand(batch) + 0.5
+    for prec in ("fp32", "tf32"):
+        bf.set_precision(prec)
+        try:
+            fused = build_b200(ishape, spec, cost, opt, seed=5)
+            plain = build_b200(ishape, spec, cost, opt, seed=5, fused_head=False)
+            ora = build_oracle(ishape, spec, cost, opt, seed=5)
+            assert fused.layers.layers[-1].head_supported(fused.cost)
+            for weights in (None, w):
+                l0 = bf.device.launch_count()
+                a = fused.learn_batch(X, Y, w=weights, metrics=["acc"], update=False)
+                l1 = bf.device.launch_count()
+                b = plain.learn_batch(X, Y, w=weights, metrics=["acc"], update=False)
+                l2 = bf.device.launch_count()
+                assert l1 - l0 <= (l2 - l1) - 3, (l1 - l0, l2 - l1)           # the point of the fusion
+                assert a["accuracy"] == b["accuracy"]
+                assert relerr(a["cost"], b["cost"]) < 1e-6
+                assert relerr(np.asarray(fused.layers.layers[-1].output), np.asarray(plain.layers.layers[-1].output)) < 1e-6
+                assert relerr(fused.get_gradients(), plain.get_gradients()) < 2e-6, relerr(fused.get_gradients(), plain.get_gradients())
+                if prec == "fp32":
+                    c = ora.learn_batch(X, Y, w=weights, update=False, metrics=["acc"])
+                    assert relerr(a["cost"], c["cost"]) < 1e-5 and a["accuracy"] == c["accuracy"]
+                    assert relerr(fused.get_gradients(), ora.get_gradients()) < 1e-5
+                    ora.zero_gradients()
+                fused.zero_gradients(); plain.zero_gradients()
+            for _ in range(3):
+                a, b = fused.learn_batch(X, Y), plain.learn_batch(X, Y)
+                assert relerr(a["cost"], b["cost"]) < 1e-5
+            assert relerr(fused.layers.get_weights(), plain.layers.get_weights()) < 1e-5
+        finally:
+            bf.set_precision("fp32")

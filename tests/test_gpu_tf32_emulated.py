@@ -184,6 +184,50 @@ def _nets(cfg, **kw):
             build_oracle(ishape, spec, cost, optimizer, seed=1234))
 
 
+def impose_device_gates(net, emu, tag, tie=1e-3):
+    """After a forward pass of both: hand the device's discrete decisions (pooling masks, ReLU gates) to the oracle's
+    backward pass, after checking that wherever they differ from the oracle's own the oracle's forward values are a
+    NEAR-TIE (a pooling window whose two largest entries, or a pre-activation whose distance from zero, is within `tie` of
+    the layer's scale: the TF32 forward pass legitimately differs from the float64 one by ~1e-5 per layer, the FP32
+    one by ~1e-7).  One flipped decision moves the first layer's gradient by ~3e-4 (one of ~4e5 terms per filter).  Returns the
+    number of differing decisions."""
+    from brainforge_b200.layers import PoolLayer, Activation
+    emu.forced = {}
+    flips = 0
+    layers = net.layers.layers[1:]
+    for li, (layer, ol) in enumerate(zip(layers, emu.L)):
+        if isinstance(layer, PoolLayer):
+            dev = np.asarray(layer.filter)
+            src = emu.L[li - 1]["output"]                      # what the pooling layer saw
+            fd = ol["fdim"]
+            im, c, iy, ix = src.shape
+            win = src.reshape(im, c, iy // fd, fd, ix // fd, fd).transpose(0, 1, 2, 4, 3, 5).reshape(im, c, iy // fd, ix // fd, fd * fd)
+            mdev = dev.reshape(im, c, iy // fd, fd, ix // fd, fd).transpose(0, 1, 2, 4, 3, 5).reshape(win.shape)
+            mora = ol["filter"].reshape(im, c, iy // fd, fd, ix // fd, fd).transpose(0, 1, 2, 4, 3, 5).reshape(win.shape)
+            differ = (mdev != mora).any(axis=-1)
+            if differ.any():
+                w = win[differ]
+                top = np.sort(w, axis=-1)
+                gap = top[:, -1] - (w * mdev[differ]).max(axis=-1)    # how far below the oracle's max the device's pick sits
+                scale = np.abs(src).mean() + 1e-30
+                assert np.all(gap <= tie * scale), (tag, li, "pooling decision differs on a window that is not a near-tie", gap.max() / scale)
+            assert np.all(mdev.sum(axis=-1) >= 1)
+            flips += int(differ.sum())
+            emu.forced[li] = dev
+        elif isinstance(layer, Activation) and str(layer.activation) == "relu":
+            out = np.asarray(layer.output)
+            gate = (out > 0).astype(np.float64)
+            ref = ol["output"]
+            differ = gate != (ref > 0)
+            if differ.any():
+                scale = np.abs(ref).mean() + 1e-30
+                assert np.all(np.abs(ref[differ]) <= tie * scale) and np.all(np.abs(out[differ]) <= tie * scale), (tag, li, "ReLU gate differs away from zero")
+            flips += int(differ.sum())
+            emu.forced[li] = gate
+    record(tag + ".gate_decisions_differing", flips)
+    return flips
+
+
 @pytest.mark.parametrize("cfg,batch", [("cfg1", 20), ("cfg2", 32), ("cfg3", 64), ("cfg4", 6)])
 def test_configs_emulated(bf, O, cfg, batch):
     """cost, gradients and a 3-step trajectory of every training config against the emulating oracle."""
@@ -194,30 +238,38 @@ def test_configs_emulated(bf, O, cfg, batch):
     pol = bf.atomic.tf32_policy_for(net, learn=True)
     a = net.learn_batch(X, Y, update=False)
     with O.tf32_emulation(pol):
+        emu.feedforward(X)
+        impose_device_gates(net, emu, cfg)
         b = emu.learn_batch(X, Y, update=False)
     c = f64.learn_batch(X, Y, update=False)
     close(cfg + ".cost", a["cost"], b["cost"], EMU_TOL)
     close(cfg + ".grad", net.get_gradients(), emu.get_gradients(), 3 * EMU_TOL)
     close(cfg + ".grad.f64", net.get_gradients(), f64.get_gradients(), 3e-2)
     net.zero_gradients(); emu.zero_gradients()
+    emu.forced = {}
     for _ in range(3):
         a = net.learn_batch(X, Y)
         with O.tf32_emulation(pol):
             b = emu.learn_batch(X, Y)
         close(cfg + ".traj.cost", a["cost"], b["cost"], EMU_TOL_TRAJ)
-    close(cfg + ".traj.weights", net.layers.get_weights(), emu.get_weights(), EMU_TOL_TRAJ)
+    # free-running (no imposed decisions): a flipped gate in step 1 moves a few weights of the gated conv nets
+    close(cfg + ".traj.weights", net.layers.get_weights(), emu.get_weights(), EMU_TOL_TRAJ if cfg in ("cfg1", "cfg4") else 2e-2)
 
 
 def test_cfg3_input_delta_emulated(bf, O):
     """backpropagate() down to the network input (three ReLU / max-pool gates, the first layer's dX and the
-    materialising form of its filter gradient) against the emulating oracle: 1e-1 against float64 becomes EMU_TOL."""
+    materialising form of its filter gradient) against the emulating oracle: 1e-1 against float64 becomes 3 * EMU_TOL."""
     net, emu, _ = _nets("cfg3")
     rs = np.random.RandomState(5)
     X, Y = rs.randn(37, 3, 30, 30).astype(np.float32), onehot(rs, 37, 10)
     pol = bf.atomic.tf32_policy_for(net, learn=False)
-    d = net.backpropagate(net.cost.derivative(net.predict(X), Y))
+    preds = net.predict(X)
     with O.tf32_emulation(pol):
-        dref = emu.backpropagate(O.cost_derivative(emu.feedforward(X), Y))
+        po = emu.feedforward(X)
+        impose_device_gates(net, emu, "cfg3.backprop")
+    d = net.backpropagate(net.cost.derivative(preds, Y))
+    with O.tf32_emulation(pol):
+        dref = emu.backpropagate(O.cost_derivative(po, Y))
     close("cfg3.input_delta", d, dref, 3 * EMU_TOL)
     close("cfg3.backprop.grad", net.get_gradients(), emu.get_gradients(), 3 * EMU_TOL)
 
@@ -233,24 +285,33 @@ def test_cfg3_bench_batch_emulated(bf, O):
     a = net.learn_batch(X, Y, metrics=["acc"], update=False)
     g = net.get_gradients()
     with O.tf32_emulation(pol):
+        emu.feedforward(X)
+        flips = impose_device_gates(net, emu, "cfg3@4096")
         b = emu.learn_batch(X, Y, metrics=["acc"], update=False)
     ge = emu.get_gradients()
+    emu.forced = {}
+    # pooling windows + ReLU elements of the net: 4096 * (6272 + 2304 + 512 + 25088 + 9216 + 2048); a few dozen near-ties flip
+    assert flips <= 2e-5 * 4096 * 45440, flips
     close("cfg3@4096.cost", a["cost"], b["cost"], EMU_TOL)
     assert abs(a["accuracy"] - b["accuracy"]) * 4096 <= 2, (a, b)        # argmax count: at most a near-tie or two
-    close("cfg3@4096.grad", g, ge, 3 * EMU_TOL)
     s = 0
     for i, l in enumerate(emu.trainable):       # per segment: a small layer must not hide behind a large one
         n = l["W"].size + l["b"].size
         close("cfg3@4096.grad.layer%d" % i, g[s:s + n], ge[s:s + n], 3 * EMU_TOL)
         s += n
+    close("cfg3@4096.grad", g, ge, 3 * EMU_TOL)
     c = f64.learn_batch(X, Y, update=False)
-    g64 = f64.get_gradients()
-    close("cfg3@4096.grad.f64", g, g64, 3e-2)
+    close("cfg3@4096.grad.f64", g, f64.get_gradients(), 3e-2)
+    # the FP32 path against the plain float64 oracle at the same size: <= 1e-5 (north_star), decisions imposed likewise
+    # (near-ties within 1e-5 of the layer scale only)
     bf.set_precision("fp32")
     try:
-        net.zero_gradients()
+        net.zero_gradients(); f64.zero_gradients()
         a32 = net.learn_batch(X, Y, update=False)
+        flips32 = impose_device_gates(net, f64, "cfg3@4096.fp32", tie=1e-5)
+        assert flips32 <= 64, flips32
+        c = f64.learn_batch(X, Y, update=False)
         close("cfg3@4096.fp32.cost", a32["cost"], c["cost"], 1e-5)
-        close("cfg3@4096.fp32.grad", net.get_gradients(), g64, 1e-5)
+        close("cfg3@4096.fp32.grad", net.get_gradients(), f64.get_gradients(), 1e-5)
     finally:
         bf.set_precision("tf32")

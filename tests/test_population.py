@@ -150,7 +150,7 @@ def test_resident_population_run_at_scale(bf):
     best0 = first.min()
     ne.learn_batch(X, Y, epochs=2, survival_rate=0.5, mutation_rate=20.0)
     g2 = pop.individuals
-    assert g2.shape == g0.shape and g2.min() >= 0.0 and g2.max() < 1.0
+    assert g2.shape == g0.shape and g2.min() >= 0.0 and g2.max() <= 1.0      # (a float64 draw just below 1 narrows to 1.0f)
     assert pop.grades.min() <= best0 + 1e-6
     # children are loci-wise mixtures of two parents of the previous generation; after two epochs at most a few loci per
     # row are fresh draws (rate 20/47710 per locus and epoch): nearly every locus of every row exists in generation 0
@@ -182,7 +182,8 @@ def test_philox_draw_statistics(bf):
     rate = 1e-3
     mutants = store.next_generation(survive, left, right, rate, seed=123, generation=0)
     g = store.download()
-    assert np.array_equal(g[:2][g[:2] < 0.2], np.zeros_like(g[:2][g[:2] < 0.2]))
+    # survivors keep their genome except for the (rare) mutated loci
+    assert (g[0] == 0.0).mean() > 0.99 and (g[1] == 0.25).mean() > 0.99
     kids = g[2:]
     from_left = (kids == 0.0).sum()
     from_right = (kids == 0.25).sum()
