@@ -36,6 +36,8 @@ struct IgemmParams {
   int resident;   // the whole repacked filter stays in shared memory: no per-tap traffic or waits
   int nkp;        // K passes per stage: the contraction channels are staged KH*32 at a time (C = nkp * KH * 32)
   int na;         // depth of the A (activation tile) ring: HBM latency is hidden by na-1 tiles in flight
+  int fy;         // filter rows
+  int TS;         // positions between consecutive tiles of a stage: 128, or 128 - (fx - 1) when the filter columns are folded
   long long* prof;   // debug (BF_PROF_IGEMM=1): per-role cycle counters of CTA 0, else null
 };
 
@@ -44,7 +46,13 @@ struct IgemmParams {
 constexpr int IG_STAGE_LD = 36;                                  // floats per staged epilogue row (32 + 4 pad)
 constexpr int IG_STAGING_BYTES = 4 * 32 * IG_STAGE_LD * 4;       // four epilogue warps
 
-template <int NB, int KH, bool RELU>
+// FOLD: the fx taps of a filter row are folded into the N dimension of ONE MMA -- D'[q][tx*NB + n] = sum_c in[q + ty*PW][c] *
+// Wt[(ty,tx)][n][c] -- and the epilogue adds the fx column blocks with a shift of tx positions: out[q][n] = sum_tx D'[q + tx]
+// [tx*NB + n].  With NB = 32 an unfolded MMA (128 x 32 x 8) is bound by the 4 KB shared-memory read of its A operand
+// (40 clk for 16 clk of tensor work); folding amortises that read over 3x the columns and issues a third of the MMAs.
+// Tiles of a stage then overlap by fx - 1 positions (stride TS = 128 - (fx - 1)) so that every sum stays inside one tile.
+constexpr int IG_FOLD_ROWS = 132, IG_FOLD_LD = 20;      // 16 columns at a time (+4 pad: conflict-free float4 rows)
+template <int NB, int KH, bool RELU, bool FOLD = false>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, IgemmParams p,
                   float* __restrict__ out, const float* __restrict__ bias) {
@@ -95,11 +103,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     IG_T(tp);
     if (p.resident && leader) {
       mbar_expect_tx(&b_full[0], (uint32_t)(p.ntaps * p.nkp) * B_SLOT);
-      for (int kp = 0; kp < p.nkp; ++kp)
-        for (int tap = 0; tap < p.ntaps; ++tap)
+      if (FOLD) {     // [kp][ty][h][tx][n]: the fx taps of a row are one box (fx * NB consecutive operand rows)
+        for (int kp = 0; kp < p.nkp; ++kp)
+          for (int ty = 0; ty < p.fy; ++ty)
 #pragma unroll
-          for (int h = 0; h < KH; ++h)
-            tma_load_3d(b_base0 + (kp * p.ntaps + tap) * B_SLOT + h * NB * 128, &mapB, &b_full[0], (kp * KH + h) * 32, n0, tap);
+            for (int h = 0; h < KH; ++h)
+              tma_load_3d(b_base0 + (uint32_t)(((kp * p.fy + ty) * KH + h) * p.fx) * (NB * 128), &mapB, &b_full[0], (kp * KH + h) * 32,
+                          n0, ty * p.fx);
+      } else {
+        for (int kp = 0; kp < p.nkp; ++kp)
+          for (int tap = 0; tap < p.ntaps; ++tap)
+#pragma unroll
+            for (int h = 0; h < KH; ++h)
+              tma_load_3d(b_base0 + (kp * p.ntaps + tap) * B_SLOT + h * NB * 128, &mapB, &b_full[0], (kp * KH + h) * 32, n0, tap);
+      }
     }
     for (int st = blockIdx.x; st < p.nstages; st += gridDim.x) {
       const int grp = st / p.nbands, band = st - grp * p.nbands;
@@ -147,6 +164,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         { IG_T(t0); mbar_wait(&a_full[as], (uint32_t)(au & 1)); if (wsel == 0) IG_ACC(3, t0); }
         tc_fence_after();
         const uint64_t a_desc0 = desc_k_sw128(base + as * a_slot_bytes);
+        if (FOLD) {
+          if (as == 0 && au == 0) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+          const uint32_t idesc_f = idesc_tf32(128, NB * p.fx);
+          const uint32_t nbf = (uint32_t)(NB * p.fx);
+          for (int ty = 0; ty < p.fy; ++ty) {
+            const uint64_t a_row = a_desc0 + (uint64_t)((uint32_t)(ty * p.PW) * 8u);
+            const uint32_t b_row = b_base0 + (uint32_t)((kp * p.fy + ty) * KH * p.fx) * (NB * 128);
+            for (int t = wsel; t < p.T; t += 2) {
+#pragma unroll
+              for (int h = 0; h < KH; ++h) {
+                const uint64_t ad = a_row + (uint64_t)(h * half_units + (uint32_t)(t * p.TS) * 8u);
+                const uint64_t bd = desc_k_sw128(b_row + (uint32_t)(h * p.fx) * (NB * 128));
+                if (leader) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_tf32(acc + t * nbf, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc_f,
+                              (kp > 0 || ty > 0 || h > 0 || ks > 0) ? 1u : 0u);
+                }
+              }
+            }
+          }
+          if (leader) umma_commit(&a_empty[as]);
+          if (++as == p.na) { as = 0; ++au; }
+          continue;
+        }
         int ty = 0, tx = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           uint32_t bs;
@@ -197,13 +239,64 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       { IG_T(t0); mbar_wait(&t_full[as], (uint32_t)(au & 1)); if (warp == 3 && lane == 0) IG_ACC(5, t0); }
       tc_fence_after();
       for (int t = 0; t < p.T; ++t) {
-        const int q = t * 128 + quad * 32 + lane;
+        const int rloc = quad * 32 + lane;                              // row of the tile
+        const int q = t * p.TS + rloc;
         const int g = q / p.IR, ql = q - g * p.IR;
         const int y = ql / p.PW, x = ql - y * p.PW;
         const int img = grp * p.G + g, yo = band * p.RO + y;
-        const bool ok = g < p.G && img < p.nimg && y < p.RO && yo < p.out_y && x < p.out_x;
+        const bool ok = rloc < p.TS && g < p.G && img < p.nimg && y < p.RO && yo < p.out_y && x < p.out_x;
         const int orow = (img * p.out_y + yo) * p.out_x + x;          // output pixel index (rows of N floats)
         const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+        if (FOLD) {
+          // column blocks tx >= 1 go through a shared tile, shifted back by tx rows when they are read; all four
+          // epilogue warps pass the same named barriers (no early exit for a warp without valid rows)
+          float* fsh = reinterpret_cast<float*>(dyn_smem) + (stage_base + IG_STAGING_BYTES - smem_u32(dyn_smem)) / 4;
+          const uint32_t taddr_f = tmem + ((uint32_t)(quad * 32) << 16) + as * IG_ACCSET_COLS + (uint32_t)(t * NB * p.fx);
+#pragma unroll 1
+          for (int cb = 0; cb < NB; cb += 32) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+              for (int tx = 1; tx < p.fx; ++tx) {
+                uint32_t v[16];
+                tmem_ld16(taddr_f + tx * NB + cb + c0, v);
+                tmem_ld_wait();
+                float* dstrow = fsh + ((size_t)(tx - 1) * IG_FOLD_ROWS + rloc) * IG_FOLD_LD;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<uint4*>(dstrow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              uint32_t v[16];
+              tmem_ld16(taddr_f + cb + c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(&sbias[cb + c0 + j]);
+                float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3]));
+                for (int tx = 1; tx < p.fx; ++tx) {
+                  const float4 a = *reinterpret_cast<const float4*>(fsh + ((size_t)(tx - 1) * IG_FOLD_ROWS + rloc + tx) * IG_FOLD_LD + j);
+                  r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+                }
+                if (RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+                *reinterpret_cast<float4*>(stg + lane * IG_STAGE_LD + c0 + j) = r;
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3);
+              const int dst_row = __shfl_sync(0xffffffffu, orow, r);
+              const float4 val = *reinterpret_cast<const float4*>(stg + r * IG_STAGE_LD + (lane & 7) * 4);
+              if ((okmask >> r) & 1u)
+                *reinterpret_cast<float4*>(out + (size_t)dst_row * p.N + n0 + cb + (lane & 7) * 4) = val;
+            }
+            __syncwarp();
+          }
+          continue;
+        }
         if (okmask == 0u) continue;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + as * IG_ACCSET_COLS + t * NB;
 #pragma unroll
@@ -454,38 +547,44 @@ struct IgemmPlan {
   int PH_box;
   size_t smem;
   bool ok;
+  double score;
 };
 
 // Picks images-per-stage or output-row bands so that the accumulators fit one TMEM set and two A slots + the
-// filter (resident if it fits, else a ring of taps) + the epilogue staging fit shared memory.
+// filter (resident if it fits, else a ring of taps) + the epilogue staging fit shared memory.  With `allow_fold` the
+// column-folded form (see the kernel) competes as well, where fx * NB accumulator columns and a resident filter fit.
 static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N, int fy, int fx, int pad_y, int pad_x,
-                            int relu) {
+                            int relu, bool allow_fold, bool* folded) {
   IgemmPlan pl;
   pl.ok = false;
+  pl.score = -1;
+  *folded = false;
   const int PW = W + 2 * pad_x, PH = H + 2 * pad_y;
   const int out_y = PH - fy + 1, out_x = PW - fx + 1;
   if (out_y <= 0 || out_x <= 0 || PW > 256) return pl;
-  const int max_shift = (fy - 1) * PW + fx - 1;
-  const int Tmax = IG_ACCSET_COLS / NB;
   const int ntaps = fy * fx;
   const size_t b_slot = (size_t)KH * NB * 128;
-  const size_t fixed = 2048 + IG_STAGING_BYTES;
   double best = -1;
-  // cost model (cycles per stage on one SM): the MMAs are bound by shared-memory operand reads for NB < 128
-  // ((128 + NB) rows x 32 B per K=8 step at 128 B/clk) or by the tensor pipe (NB/2 clk per step); the loads by the
+  // cost model (cycles per stage on one SM): the MMAs are bound by shared-memory operand reads for small N
+  // ((128 + N) rows x 32 B per K=8 step at 128 B/clk) or by the tensor pipe (N/2 clk per step); the loads by the
   // SM's share of HBM/L2 bandwidth (~24 B/clk); a shallow ring leaves the load latency exposed.
-  auto consider = [&](int G, int nbands, int RO, int PHb) {
+  auto consider = [&](int G, int nbands, int RO, int PHb, bool fold) {
     const int IR = PHb * PW;
+    const int NBF = fold ? NB * fx : NB, TS = fold ? 128 - (fx - 1) : 128;
+    const int Tmax = IG_ACCSET_COLS / NBF;
+    const int max_shift = fold ? (fy - 1) * PW : (fy - 1) * PW + fx - 1;
+    const size_t fixed = 2048 + IG_STAGING_BYTES + (fold ? (size_t)(fx - 1) * IG_FOLD_ROWS * IG_FOLD_LD * 4 : 0);
     const long last = (long)(G - 1) * IR + (long)(RO - 1) * PW + out_x;   // positions to cover
-    const int T = (int)((last + 127) / 128);
-    if (T > Tmax) return false;
-    long rows = (long)T * 128 + max_shift;
+    const int T = (int)((last + TS - 1) / TS);
+    if (T > Tmax || T < 1) return false;
+    long rows = (long)(T - 1) * TS + 128 + max_shift;
     if (rows < (long)G * IR) rows = (long)G * IR;
     rows = (rows + 7) / 8 * 8;
     const size_t a_slot = (size_t)KH * rows * 128;
     if (2 * a_slot + 2 * b_slot + fixed > IG_SMEM_BUDGET) return false;
     const size_t b_all = (size_t)ntaps * nkp * b_slot;
     const bool resident = 2 * a_slot + b_all + fixed <= IG_SMEM_BUDGET;
+    if (fold && !resident) return false;
     int na, nbs;
     if (resident) {
       nbs = ntaps * nkp;
@@ -498,11 +597,11 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N,
       if (nbs > 16) nbs = 16;
     }
     if (na > 8) na = 8;
-    // per K=8 step a 128-row tile costs max(tensor NB/2, shared-memory operand reads (128+NB)/4) cycles, but one
+    // per K=8 step a 128-row tile costs max(tensor N/2, shared-memory operand reads (128+N)/4) cycles, but one
     // issuing thread sustains only ~1 MMA per 100 cycles (two issuers when T >= 2)
-    const double mma_step = NB / 2.0 > (128 + NB) / 4.0 ? NB / 2.0 : (128 + NB) / 4.0;
+    const double mma_step = NBF / 2.0 > (128 + NBF) / 4.0 ? NBF / 2.0 : (128 + NBF) / 4.0;
     const double issue = T >= 2 ? 60.0 : 120.0;
-    const double mma_clk = (double)ntaps * nkp * T * KH * 4 * (mma_step > issue ? mma_step : issue);
+    const double mma_clk = (double)(fold ? fy : ntaps) * nkp * T * KH * 4 * (mma_step > issue ? mma_step : issue);
     const double bytes = (double)KH * nkp * G * IR * 128 + (resident ? 0.0 : (double)b_all);
     double stage_clk = mma_clk > bytes / 24.0 ? mma_clk : bytes / 24.0;
     stage_clk += 600.0 + (na == 2 ? 1500.0 : 0.0) + (!resident && nbs < 4 ? 1500.0 : 0.0);
@@ -510,25 +609,30 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N,
     if (score > best) {
       best = score;
       pl.p = IgemmParams{nbands == 1 ? (B + G - 1) / G : B * nbands, nbands, G, IR, PW, T, (int)rows, ntaps, fx, -pad_x, -pad_y,
-                         RO, out_y, out_x, B, N, relu, nbs, resident ? 1 : 0, nkp, na, nullptr};
+                         RO, out_y, out_x, B, N, relu, nbs, resident ? 1 : 0, nkp, na, fy, TS, nullptr};
       pl.PH_box = PHb;
-      pl.smem = 1024 + (size_t)na * a_slot + (size_t)nbs * b_slot + IG_STAGING_BYTES;
+      pl.smem = 1024 + (size_t)na * a_slot + (size_t)nbs * b_slot + fixed - 2048;
       pl.ok = true;
+      pl.score = score;
+      *folded = fold;
     }
     return true;
   };
-  if (PH <= 256)
-    for (int G = 1; G <= 256 && G <= B + 8; ++G)
-      if (!consider(G, 1, out_y, PH)) break;
-  for (int RO = (out_y < 254 ? out_y - 1 : 254); RO >= 1; --RO) {
-    if (RO + fy - 1 > 256) continue;
-    consider(1, (out_y + RO - 1) / RO, RO, RO + fy - 1);
+  static const bool fold_off = getenv("BF_IGEMM_NOFOLD") != nullptr;
+  for (int fold = 0; fold <= ((allow_fold && !fold_off && fx >= 2 && fx <= 4 && NB * fx <= IG_ACCSET_COLS) ? 1 : 0); ++fold) {
+    if (PH <= 256)
+      for (int G = 1; G <= 256 && G <= B + 8; ++G)
+        if (!consider(G, 1, out_y, PH, fold != 0)) break;
+    for (int RO = (out_y < 254 ? out_y - 1 : 254); RO >= 1; --RO) {
+      if (RO + fy - 1 > 256) continue;
+      consider(1, (out_y + RO - 1) / RO, RO, RO + fy - 1, fold != 0);
+    }
   }
   return pl;
 }
 
 template <int NB, int KH>
-static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, IgemmPlan& pl, float* out, const float* bias,
+static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, IgemmPlan& pl, float* out, const float* bias, bool fold,
                         cudaStream_t s) {
   static long long* d_prof = nullptr;
   const bool prof = getenv("BF_PROF_IGEMM") != nullptr;
@@ -539,13 +643,19 @@ static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, IgemmPlan&
   }
   const int ctas = pl.p.nstages < num_sms() ? pl.p.nstages : num_sms();
   dim3 grid(ctas, pl.p.N / NB);
-  if (pl.p.relu) {
-    BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    launch_pdl(conv_igemm_kernel<NB, KH, true>, dim3(grid), dim3(IG_THREADS), pl.smem, s, mA, mB, pl.p, out, bias);
-  } else {
-    BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    launch_pdl(conv_igemm_kernel<NB, KH, false>, dim3(grid), dim3(IG_THREADS), pl.smem, s, mA, mB, pl.p, out, bias);
+#define BF_IG_LAUNCH(RELU_, FOLD_)                                                                                                          \
+  {                                                                                                                                        \
+    BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, RELU_, FOLD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));      \
+    launch_pdl(conv_igemm_kernel<NB, KH, RELU_, FOLD_>, dim3(grid), dim3(IG_THREADS), pl.smem, s, mA, mB, pl.p, out, bias);                 \
   }
+  if (fold) {
+    if constexpr (NB <= 64) {
+      if (pl.p.relu) BF_IG_LAUNCH(true, true) else BF_IG_LAUNCH(false, true)
+    }
+  } else {
+    if (pl.p.relu) BF_IG_LAUNCH(true, false) else BF_IG_LAUNCH(false, false)
+  }
+#undef BF_IG_LAUNCH
   BF_LAUNCH_CHECK();
   if (prof) {
     long long h[16];
@@ -574,15 +684,24 @@ bool conv_nhwc_supported(int C, int N, int fy, int fx) {
 
 // out[(b,y,x), n] = act( sum_{ty,tx,c} in[b, y - pad_y + ty, x - pad_x + tx, c] * Wt[(ty,tx)][n][c] ) + bias[n]
 static int conv_nhwc_igemm(const float* in, const float* Wt, const float* bias, float* out, int B, int H, int W, int C,
-                           int N, int fy, int fx, int pad_y, int pad_x, int relu, cudaStream_t s) {
-  const int KH = (C % 64 == 0) ? 2 : 1, nkp = C / (32 * KH), NB = pick_nb(N);
-  IgemmPlan pl = plan_igemm(B, H, W, KH, nkp, NB, N, fy, fx, pad_y, pad_x, relu);
+                           int N, int fy, int fx, int pad_y, int pad_x, int relu, bool allow_fold, cudaStream_t s) {
+  int KH = (C % 64 == 0) ? 2 : 1, nkp = C / (32 * KH);
+  const int NB = pick_nb(N);
+  bool fold = false;
+  IgemmPlan pl = plan_igemm(B, H, W, KH, nkp, NB, N, fy, fx, pad_y, pad_x, relu, allow_fold, &fold);
+  if (allow_fold && KH == 2) {
+    // 64 channels per stage may leave no room for the resident filter + the folded epilogue's tile next to whole images:
+    // 32 at a time (two K passes) competes
+    bool fold1 = false;
+    IgemmPlan pl1 = plan_igemm(B, H, W, 1, C / 32, NB, N, fy, fx, pad_y, pad_x, relu, true, &fold1);
+    if (pl1.ok && fold1 && (!pl.ok || pl1.score > pl.score)) { pl = pl1; fold = true; KH = 1; nkp = C / 32; }
+  }
   if (!pl.ok) return fail(BF_ERR_ARG, "conv_nhwc: no tiling for plane %dx%d, %d->%d channels", H, W, C, N);
   if ((long)B * pl.p.out_y * pl.p.out_x >= 2147483647L) return fail(BF_ERR_ARG, "conv_nhwc: too many output pixels");
   if (getenv("BF_DEBUG_PLAN"))
-    fprintf(stderr, "[igemm %dx%dx%d->%d pad %d] G=%d bands=%d RO=%d T=%d rows=%d KH=%d nkp=%d NB=%d na=%d nbs=%d resident=%d smem=%zu stages=%d\n",
-            H, W, C, N, pad_y, pl.p.G, pl.p.nbands, pl.p.RO, pl.p.T, pl.p.slot_rows, KH, nkp, NB, pl.p.na, pl.p.nbs, pl.p.resident, pl.smem,
-            pl.p.nstages);
+    fprintf(stderr, "[igemm %dx%dx%d->%d pad %d] G=%d bands=%d RO=%d T=%d rows=%d KH=%d nkp=%d NB=%d na=%d nbs=%d resident=%d fold=%d smem=%zu stages=%d\n",
+            H, W, C, N, pad_y, pl.p.G, pl.p.nbands, pl.p.RO, pl.p.T, pl.p.slot_rows, KH, nkp, NB, pl.p.na, pl.p.nbs, pl.p.resident, fold ? 1 : 0,
+            pl.smem, pl.p.nstages);
   CUtensorMap mA, mB;
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -594,11 +713,11 @@ static int conv_nhwc_igemm(const float* in, const float* Wt, const float* bias, 
   {
     uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)(fy * fx)};
     uint64_t str[2] = {(uint64_t)C, (uint64_t)C * N};
-    uint32_t box[3] = {32, (uint32_t)NB, 1};
+    uint32_t box[3] = {32, (uint32_t)NB, (uint32_t)(fold ? fx : 1)};
     if (!tma_make_map(&mB, Wt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return fail(BF_ERR_CUDA, "conv_nhwc: cuTensorMapEncodeTiled failed (filter)");
   }
-#define BF_IG_CASE(NB_, KH_) if (NB == NB_ && KH == KH_) return launch_igemm<NB_, KH_>(mA, mB, pl, out, bias, s);
+#define BF_IG_CASE(NB_, KH_) if (NB == NB_ && KH == KH_) return launch_igemm<NB_, KH_>(mA, mB, pl, out, bias, fold, s);
   BF_IG_CASE(32, 1) BF_IG_CASE(32, 2) BF_IG_CASE(64, 1) BF_IG_CASE(64, 2) BF_IG_CASE(128, 1) BF_IG_CASE(128, 2)
 #undef BF_IG_CASE
   return fail(BF_ERR_ARG, "conv_nhwc: unsupported channel counts %d -> %d", C, N);
@@ -622,7 +741,8 @@ int bf_conv_nhwc_forward(const float* X, const float* F, const float* bias, floa
   launch_pdl(conv_repack_nhwc_kernel, dim3(ew_grid((size_t)nf * ic * fy * fx, 256)), dim3(256), 0, s, F, (float*)ws, nf, ic, fy, fx, 0);
   BF_LAUNCH_CHECK();
   set_last_path(2);
-  return conv_nhwc_igemm(X, (const float*)ws, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act == BF_ACT_RELU ? 1 : 0, s);
+  return conv_nhwc_igemm(X, (const float*)ws, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act == BF_ACT_RELU ? 1 : 0,
+                         getenv("BF_IGEMM_FOLD_FWD") != nullptr, s);
 }
 
 // dX (im,iy,ix,ic) = full_corr(E (im,oy,ox,nf), flip(F)^T)                           [NHWC]
@@ -638,7 +758,8 @@ int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX, int im
   launch_pdl(conv_repack_nhwc_kernel, dim3(ew_grid((size_t)nf * ic * fy * fx, 256)), dim3(256), 0, s, F, (float*)ws, nf, ic, fy, fx, 1);
   BF_LAUNCH_CHECK();
   set_last_path(2);
-  return conv_nhwc_igemm(E, (const float*)ws, nullptr, dX, im, oy, ox, nf, ic, fy, fx, fy - 1, fx - 1, 0, s);
+  // few output channels (N = ic): the column-folded form, when its accumulators and the resident filter fit
+  return conv_nhwc_igemm(E, (const float*)ws, nullptr, dX, im, oy, ox, nf, ic, fy, fx, fy - 1, fx - 1, 0, true, s);
 }
 
 // dF (nf,ic,fy,fx), db (nf) from X (im,iy,ix,ic), E (im,oy,ox,nf)                      [NHWC activations]

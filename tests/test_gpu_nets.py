@@ -326,7 +326,9 @@ def test_fused_output_head_matches_unfused_and_oracle(case):
                 assert a["accuracy"] == b["accuracy"]
                 assert relerr(a["cost"], b["cost"]) < 1e-6
                 assert relerr(np.asarray(fused.layers.layers[-1].output), np.asarray(plain.layers.layers[-1].output)) < 1e-6
-                assert relerr(fused.get_gradients(), plain.get_gradients()) < 2e-6, relerr(fused.get_gradients(), plain.get_gradients())
+                # (TF32: a last-bit difference in the head's dX can flip the TF32 rounding of an operand further down)
+                gtol = 2e-6 if prec == "fp32" else 2e-4
+                assert relerr(fused.get_gradients(), plain.get_gradients()) < gtol, relerr(fused.get_gradients(), plain.get_gradients())
                 if prec == "fp32":
                     c = ora.learn_batch(X, Y, w=weights, update=False, metrics=["acc"])
                     assert relerr(a["cost"], c["cost"]) < 1e-5 and a["accuracy"] == c["accuracy"]
@@ -335,7 +337,7 @@ def test_fused_output_head_matches_unfused_and_oracle(case):
                 fused.zero_gradients(); plain.zero_gradients()
             for _ in range(3):
                 a, b = fused.learn_batch(X, Y), plain.learn_batch(X, Y)
-                assert relerr(a["cost"], b["cost"]) < 1e-5
-            assert relerr(fused.layers.get_weights(), plain.layers.get_weights()) < 1e-5
+                assert relerr(a["cost"], b["cost"]) < (1e-5 if prec == "fp32" else 1e-3)
+            assert relerr(fused.layers.get_weights(), plain.layers.get_weights()) < (1e-5 if prec == "fp32" else 1e-3)
         finally:
             bf.set_precision("fp32")
