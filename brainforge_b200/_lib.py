@@ -69,6 +69,9 @@ SIGNATURES = {
     "bf_layout_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "bf_pool_nhwc_forward": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
     "bf_pool_nhwc_backward": (_i, [_vp, _vp, _vp, _vp] + [_i] * 5 + [_vp]),
+    "bf_pool_nhwc_db_rows": (_i, [_i] * 5),
+    "bf_pool_nhwc_backward_db": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
+    "bf_conv_nhwc_backward_filter_dbp": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
     "bf_gap_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "bf_gap_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "bf_cost_delta": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),

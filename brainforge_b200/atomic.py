@@ -175,6 +175,7 @@ class ConvolutionOp:
       * anything else: the gather-staged implicit GEMM on NCHW (`bf_conv_forward/backward`)."""
 
     channels_last = True      # class-wide switch: False keeps every convolution on the NCHW gather kernels
+    db_from_pool = True       # take db from the channel sums the pooling backward pass leaves on E (no all-ones MMA)
 
     @staticmethod
     def _route(a_nhwc, ic, iy, ix, nf, fy, fx, mode, activation):
@@ -291,8 +292,13 @@ class ConvolutionOp:
             try:
                 if route == "nhwc":
                     xn = x.to_nhwc()
-                    call(L.bf_conv_nhwc_backward_filter, xn.pptr, en.pptr, dF.ptr, db.ptr, im, ic, iy, ix,
-                         nf, fy, fx, stream_ptr(), tag="dF")
+                    dbp = getattr(e, "db_partial", None) if ConvolutionOp.db_from_pool else None
+                    if dbp is not None and en is e:
+                        call(L.bf_conv_nhwc_backward_filter_dbp, xn.pptr, en.pptr, dF.ptr, db.ptr, ctypes.c_void_p(dbp[0].data_ptr()),
+                             dbp[1], im, ic, iy, ix, nf, fy, fx, stream_ptr(), tag="dF")
+                    else:
+                        call(L.bf_conv_nhwc_backward_filter, xn.pptr, en.pptr, dF.ptr, db.ptr, im, ic, iy, ix,
+                             nf, fy, fx, stream_ptr(), tag="dF")
                 else:
                     call(L.bf_conv_c3_backward_filter, x.ptr, en.pptr, dF.ptr, db.ptr, im, ic, iy, ix, nf, fy, fx,
                          stream_ptr(), tag="dF")
@@ -396,10 +402,12 @@ class MaxPoolOp:
         return out.numpy(), np.asarray(mask)
 
     @staticmethod
-    def backward(E, filt, gate=None):
+    def backward(E, filt, gate=None, want_db=False):
         """E (im,ic,oy,ox), filt = the mask from forward (PoolMask, or a host 0/1 array as the reference
         returns it).  Unlike the reference (tensor_op.py:118-119) the cached mask is not consumed.
-        gate (channels-last only): the pooled forward output; multiplies E by (gate > 0)."""
+        gate (channels-last only): the pooled forward output; multiplies E by (gate > 0).
+        want_db (channels-last, device arrays): also leave per-CTA channel sums of the result on it (`.db_partial`) for the
+        filter-gradient kernel of the convolution below."""
         import torch
         e = as_device(E)
         if isinstance(filt, PoolMask):
@@ -417,8 +425,16 @@ class MaxPoolOp:
         if mask.nhwc:
             dX = DeviceArray.empty_nhwc(im, ic, iy, ix)
             en = e.to_nhwc()
-            call(L.bf_pool_nhwc_backward, en.pptr, mask.wptr, gate.pptr if gate is not None else _NULL, dX.pptr,
-                 im, ic, iy, ix, mask.fdim, stream_ptr())
+            rows = L.bf_pool_nhwc_db_rows(im, ic, iy, ix, mask.fdim) if (want_db and isinstance(E, DeviceArray)) else 0
+            if rows > 0:
+                # the convolution below wants db = dX.sum((0,2,3)): per-CTA channel sums fall out of this pass for free
+                part = torch.empty((rows, ic), dtype=torch.float32, device="cuda")
+                call(L.bf_pool_nhwc_backward_db, en.pptr, mask.wptr, gate.pptr if gate is not None else _NULL, dX.pptr,
+                     ctypes.c_void_p(part.data_ptr()), im, ic, iy, ix, mask.fdim, stream_ptr())
+                dX.db_partial = (part, rows)
+            else:
+                call(L.bf_pool_nhwc_backward, en.pptr, mask.wptr, gate.pptr if gate is not None else _NULL, dX.pptr,
+                     im, ic, iy, ix, mask.fdim, stream_ptr())
         else:
             assert gate is None
             dX = DeviceArray.empty(im, ic, iy, ix)
@@ -615,7 +631,10 @@ def tf32_operand_modes(kind, learn=True, **s):
     if kind == "conv":
         route = ConvolutionOp._route(s.get("nhwc", False), s["ic"], s["iy"], s["ix"], s["nf"], s["fy"], s["fx"], "valid", "linear")
         if route == "nhwc":
-            return {"conv.fwd": _TMA, "conv.dF": _TMA, "conv.dX": _TMA}
+            # db: through an all-ones operand of the dF MMA (sees E as the TMA unit rounds it) unless the pooling layer
+            # above summed its own output in FP32 (`pooled`: learn_batch / backpropagate through a PoolLayer(2))
+            return {"conv.fwd": _TMA, "conv.dF": _TMA, "conv.dX": _TMA,
+                    "conv.db": None if (s.get("pooled", False) and ConvolutionOp.db_from_pool) else "tma"}
         if route == "c3":
             # forward: pixel stream and filter rounded while they are re-laid; filter gradient: patch rows rounded by the
             # builder warps, E either rebuilt (rounded) by them from the pooling layer's delta (learn_batch) or a TMA
@@ -643,8 +662,13 @@ def tf32_policy_for(net, learn=True):
             ic, iy, ix = layer.inshape[-3:]
             prev_cl = i > 0 and any(isinstance(p, ConvLayer) for p in layers[:i])
             pool, _ = layer._pool_after()
+            oy, ox = iy - layer.fy + 1, ix - layer.fx + 1
+            pooled = pool is not None and bool(L.bf_pool_nhwc_db_rows(1, layer.nfilters, oy, ox, 2))
             table[i] = tf32_operand_modes("conv", learn=learn, ic=ic, iy=iy, ix=ix, nf=layer.nfilters, fy=layer.fy, fx=layer.fx,
-                                          nhwc=prev_cl, unpool=pool is not None and i == 0 and layer.fuse_pool)
+                                          nhwc=prev_cl, unpool=pool is not None and i == 0 and layer.fuse_pool, pooled=pooled)
         elif name == "LSTM":
             table[i] = tf32_operand_modes("lstm", D=layer.inshape[-1], H=layer.neurons)
-    return lambda site, li: table.get(li, {}).get(site)
+    def policy(site, li):
+        return table.get(li, {}).get(site)
+    policy.declares = lambda site, li: site in table.get(li, {})
+    return policy

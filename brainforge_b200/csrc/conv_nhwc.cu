@@ -343,6 +343,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 struct DfParams {
   int nstages, nbands, G, IR, PW, RO, Krows, x_rows, ntaps, fx, nimg, nsplit, e_rows_box;
   int ns;   // ring depth (stages in flight)
+  int with_db;   // accumulate db through an all-ones operand (0: the caller has it from the kernel that produced E)
 };
 
 template <int MH>
@@ -359,7 +360,7 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
   const uint32_t total_bytes = (uint32_t)p.ns * (e_slot + x_slot) + 1024u;
   const int split = blockIdx.x, ch = blockIdx.y;
   pdl_launch_dependents();
-  const int ntap_acc = p.ntaps + (ch == 0 ? 1 : 0);   // channel half 0 also accumulates db (all-ones operand)
+  const int ntap_acc = p.ntaps + ((ch == 0 && p.with_db) ? 1 : 0);   // channel half 0 also accumulates db (all-ones operand)
 
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512));
@@ -424,7 +425,7 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
         if (leader) {
           for (int ty = 0; ty < fy; ++ty, bdr += row_step)
             umma_tf32(tmem + ty * p.fx * 32, ad, bdr, idesc_row, acc_flag);
-          if (ch == 0) umma_tf32(tmem + p.ntaps * 32, ad, ones_desc, idesc_one, acc_flag);
+          if (ch == 0 && p.with_db) umma_tf32(tmem + p.ntaps * 32, ad, ones_desc, idesc_one, acc_flag);
         }
       }
       if (leader) umma_commit(&empty[s]);
@@ -468,7 +469,7 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
 constexpr int DF_RED_SLICES = 16;
 __global__ void __launch_bounds__(32 * DF_RED_SLICES)
 conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
-                           int nsplit, int nch, int ntaps, int nf, int ic) {
+                           int nsplit, int nch, int ntaps, int nf, int ic, const float* __restrict__ dbp, int dbrows) {
   __shared__ float red[DF_RED_SLICES][33];
   pdl_launch_dependents();
   pdl_wait();
@@ -494,8 +495,13 @@ conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict_
     }
   }
   float s = 0.f;
-  if (i < total)
-    for (int z = zs; z < nsplit; z += DF_RED_SLICES) s += partial[(size_t)z * zstride + off];
+  if (i < total) {
+    if (dst < 0 && dbp) {            // db from the per-CTA channel sums of the kernel that wrote E (bf_pool_nhwc_backward_db)
+      for (int z = zs; z < dbrows; z += DF_RED_SLICES) s += dbp[(size_t)z * nf + (-1 - dst)];
+    } else {
+      for (int z = zs; z < nsplit; z += DF_RED_SLICES) s += partial[(size_t)z * zstride + off];
+    }
+  }
   red[zs][threadIdx.x] = s;
   __syncthreads();
 #pragma unroll
@@ -763,8 +769,8 @@ int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX, int im
 }
 
 // dF (nf,ic,fy,fx), db (nf) from X (im,iy,ix,ic), E (im,oy,ox,nf)                      [NHWC activations]
-int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix,
-                                 int nf, int fy, int fx, void* stream) {
+static int conv_nhwc_backward_filter_impl(const float* X, const float* E, float* dF, float* db, const float* db_partial,
+                                          int db_rows, int im, int ic, int iy, int ix, int nf, int fy, int fx, void* stream) {
   BF_REQUIRE(ic % 32 == 0 && (nf == 32 || nf == 64 || nf == 128) && fy * fx <= 15 && fx <= 8 && tma_encode_fn() != nullptr, BF_ERR_ARG,
              "bf_conv_nhwc_backward_filter: unsupported shape (ic=%d nf=%d)", ic, nf);
   cudaStream_t s = as_stream(stream);
@@ -798,7 +804,8 @@ int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, floa
     const double score = (double)G * RO * ox / stage_clk;
     if (score > best) {
       best = score;
-      p = DfParams{nbands == 1 ? (im + G - 1) / G : im * nbands, nbands, G, IRx, ix, RO, Krows, x_rows, ntaps, fx, im, 1, e_rows, ns};
+      p = DfParams{nbands == 1 ? (im + G - 1) / G : im * nbands, nbands, G, IRx, ix, RO, Krows, x_rows, ntaps, fx, im, 1, e_rows, ns,
+                   db_partial ? 0 : 1};
       smem = df_smem_bytes(MH, Krows, x_rows, ns);
       ok = true;
     }
@@ -855,10 +862,23 @@ int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, floa
 #undef BF_DF_CASE
   BF_LAUNCH_CHECK();
   launch_pdl(conv_df_reduce_nhwc_kernel, dim3((unsigned)(((size_t)nf * ic * ntaps + nf + 31) / 32)), dim3(32, DF_RED_SLICES), 0, s,
-             (const float*)ws, dF, db, nsplit, nch, ntaps, nf, ic);
+             (const float*)ws, dF, db, nsplit, nch, ntaps, nf, ic, db_partial, db_rows);
   BF_LAUNCH_CHECK();
   set_last_path(2);
   return BF_OK;
+}
+
+int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy, int ix,
+                                 int nf, int fy, int fx, void* stream) {
+  return conv_nhwc_backward_filter_impl(X, E, dF, db, nullptr, 0, im, ic, iy, ix, nf, fy, fx, stream);
+}
+
+// As above with db taken from `db_rows` rows of per-CTA channel sums of E (written by bf_pool_nhwc_backward_db, the kernel
+// that produced E): no all-ones MMA per K step.
+int bf_conv_nhwc_backward_filter_dbp(const float* X, const float* E, float* dF, float* db, const float* db_partial, int db_rows,
+                                     int im, int ic, int iy, int ix, int nf, int fy, int fx, void* stream) {
+  BF_REQUIRE(db_partial && db_rows > 0, BF_ERR_ARG, "bf_conv_nhwc_backward_filter_dbp: no partials");
+  return conv_nhwc_backward_filter_impl(X, E, dF, db, db_partial, db_rows, im, ic, iy, ix, nf, fy, fx, stream);
 }
 
 int bf_conv_nhwc_supported(int ic, int nf, int fy, int fx) {

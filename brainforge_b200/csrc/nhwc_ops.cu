@@ -108,12 +108,19 @@ __global__ void pool_nhwc_fwd_kernel(const float4* __restrict__ A, float4* __res
   }
 }
 
-template <int FD, bool GATE>
-__global__ void pool_nhwc_bwd_kernel(const float4* __restrict__ E, const uchar4* __restrict__ mask, const float4* __restrict__ gate,
-                                     float4* __restrict__ dX, long total, int oy, int ox, int c4, int ix) {
+// DBP: also emit, per CTA, the per-channel sums of everything written to dX (row blockIdx.x of `dbp`, c floats): the
+// bias gradient db = E.sum((0,2,3)) of the convolution below (atomic/tensor_op.py:55) as a by-product of the pass that
+// produces its E, instead of an extra all-ones MMA per K step in that layer's filter-gradient kernel.  Needs 256 % c4 == 0
+// (a thread then keeps its channel quad over the whole grid-stride loop); fixed-order block tree -> deterministic.
+template <int FD, bool GATE, bool DBP>
+__global__ void __launch_bounds__(256)
+pool_nhwc_bwd_kernel(const float4* __restrict__ E, const uchar4* __restrict__ mask, const float4* __restrict__ gate,
+                                     float4* __restrict__ dX, long total, int oy, int ox, int c4, int ix, float4* __restrict__ dbp) {
+  __shared__ float4 sred[DBP ? 256 : 1];
   pdl_launch_dependents();
   pdl_wait();
   constexpr int fd = FD;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     const int q = (int)(i % c4);
@@ -128,6 +135,10 @@ __global__ void pool_nhwc_bwd_kernel(const float4* __restrict__ E, const uchar4*
       const float4 g = gate[i];
       e.x = g.x > 0.f ? e.x : 0.f; e.y = g.y > 0.f ? e.y : 0.f; e.z = g.z > 0.f ? e.z : 0.f; e.w = g.w > 0.f ? e.w : 0.f;
     }
+    if (DBP) {     // a tied window writes its value to every tied element
+      acc.x += e.x * (float)__popc(mk.x); acc.y += e.y * (float)__popc(mk.y);
+      acc.z += e.z * (float)__popc(mk.z); acc.w += e.w * (float)__popc(mk.w);
+    }
     float4* dst = dX + ((b * oy * fd + (long)y * fd) * ix + (long)x * fd) * c4 + q;
 #pragma unroll
     for (int dy = 0; dy < fd; ++dy)
@@ -137,6 +148,20 @@ __global__ void pool_nhwc_bwd_kernel(const float4* __restrict__ E, const uchar4*
         dst[((long)dy * ix + dx) * c4] = make_float4((mk.x >> k) & 1 ? e.x : 0.f, (mk.y >> k) & 1 ? e.y : 0.f,
                                                      (mk.z >> k) & 1 ? e.z : 0.f, (mk.w >> k) & 1 ? e.w : 0.f);
       }
+  }
+  if (DBP) {
+    sred[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w >= c4; w >>= 1) {          // threads t and t + w hold the same channel quad (c4 divides w)
+      if ((int)threadIdx.x < w) {
+        const float4 o = sred[threadIdx.x + w];
+        float4 m = sred[threadIdx.x];
+        m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+        sred[threadIdx.x] = m;
+      }
+      __syncthreads();
+    }
+    if ((int)threadIdx.x < c4) dbp[(size_t)blockIdx.x * c4 + threadIdx.x] = sred[threadIdx.x];
   }
 }
 
@@ -285,8 +310,14 @@ int bf_pool_nhwc_forward(const float* A, float* out, uint8_t* mask, int im, int 
   return BF_OK;
 }
 
-int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate, float* dX, int im, int c, int iy, int ix,
-                          int fdim, void* stream) {
+// rows of the per-CTA bias-gradient partials bf_pool_nhwc_backward_db writes (0: that shape cannot produce them)
+int bf_pool_nhwc_db_rows(int im, int c, int iy, int ix, int fdim) {
+  if (fdim != 2 || im <= 0 || c <= 0 || (c & 3) || 256 % (c / 4) != 0 || (iy % 2) || (ix % 2)) return 0;
+  return ew_grid((size_t)im * (iy / 2) * (ix / 2) * (c / 4), 256);
+}
+
+static int pool_nhwc_backward_impl(const float* E, const uint8_t* mask, const float* gate, float* dX, float* db_partial, int im,
+                                   int c, int iy, int ix, int fdim, void* stream) {
   int rc = pool_nhwc_check("bf_pool_nhwc_backward", im, c, iy, ix, fdim);
   if (rc) return rc;
   if (im == 0) return BF_OK;
@@ -298,9 +329,13 @@ int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate
     const long total = (long)im * oy * ox * c4;
     if (total == 0) return BF_OK;
     const int grid = ew_grid(total, 256);
-#define BF_PB(FD_, G_) launch_pdl(pool_nhwc_bwd_kernel<FD_, G_>, dim3(grid), dim3(256), 0, s, (const float4*)E, (const uchar4*)mask, (const float4*)gate, (float4*)dX, total, oy, ox, c4, ix)
-    if (fdim == 2) { if (gate) BF_PB(2, true); else BF_PB(2, false); }
-    else { if (gate) BF_PB(1, true); else BF_PB(1, false); }
+#define BF_PB(FD_, G_, D_) launch_pdl(pool_nhwc_bwd_kernel<FD_, G_, D_>, dim3(grid), dim3(256), 0, s, (const float4*)E, (const uchar4*)mask, (const float4*)gate, (float4*)dX, total, oy, ox, c4, ix, (float4*)db_partial)
+    if (db_partial) {
+      BF_REQUIRE(fdim == 2 && 256 % c4 == 0 && grid == bf_pool_nhwc_db_rows(im, c, iy, ix, fdim), BF_ERR_ARG,
+                 "bf_pool_nhwc_backward: per-CTA bias-gradient partials need fdim 2 and a channel count dividing 1024");
+      if (gate) BF_PB(2, true, true); else BF_PB(2, false, true);
+    } else if (fdim == 2) { if (gate) BF_PB(2, true, false); else BF_PB(2, false, false); }
+    else { if (gate) BF_PB(1, true, false); else BF_PB(1, false, false); }
 #undef BF_PB
   } else {
     const long total = (long)im * oy * ox * c;
@@ -309,6 +344,17 @@ int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate
   }
   BF_LAUNCH_CHECK();
   return BF_OK;
+}
+
+int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate, float* dX, int im, int c, int iy, int ix,
+                          int fdim, void* stream) {
+  return pool_nhwc_backward_impl(E, mask, gate, dX, nullptr, im, c, iy, ix, fdim, stream);
+}
+
+int bf_pool_nhwc_backward_db(const float* E, const uint8_t* mask, const float* gate, float* dX, float* db_partial, int im, int c,
+                             int iy, int ix, int fdim, void* stream) {
+  BF_REQUIRE(db_partial && bf_pool_nhwc_db_rows(im, c, iy, ix, fdim) > 0, BF_ERR_ARG, "bf_pool_nhwc_backward_db: unsupported shape");
+  return pool_nhwc_backward_impl(E, mask, gate, dX, db_partial, im, c, iy, ix, fdim, stream);
 }
 
 int bf_gap_forward(const float* A, float* out, int im, int c, int hw, int nhwc, void* stream) {

@@ -65,10 +65,10 @@ class PoolLayer(NoParamMixin, LayerBase):
         if getattr(self, "_conv_src", None) is not None and not self._standalone:
             return FusedUnpool(self, delta)   # the convolution's filter-gradient kernel un-pools on the fly
         if getattr(self, "_fused_relu", False):
-            dX = self.op.backward(delta, self.filter, gate=self.output)   # pool' and relu' in one scatter
+            dX = self.op.backward(delta, self.filter, gate=self.output, want_db=not self._standalone)   # pool' and relu' in one scatter
             dX.relu_applied = True
             return dX
-        return self.op.backward(delta, self.filter)
+        return self.op.backward(delta, self.filter, want_db=not self._standalone)
 
     @property
     def outshape(self):
@@ -158,6 +158,7 @@ class ConvLayer(LayerBase):
             delta = delta.materialize()
         if str(self.activation) != "linear":
             delta = self.activation.backward_mul(self.output, delta)
+            delta.db_partial = None          # channel sums left by a pooling layer describe the delta BEFORE act'
         _, _, dX = self.op.backward(X=self.inputs, E=delta, F=self.weights, dF=self.nabla_w, db=self.nabla_b,
                                     need_dX=need_dX)
         return dX

@@ -153,6 +153,10 @@ BF_API int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX,
                                int fy, int fx, void* stream);
 BF_API int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy,
                                  int ix, int nf, int fy, int fx, void* stream);
+/* The same with db = sum of the `db_rows` rows of per-CTA channel sums the producer of E left in db_partial
+ * (bf_pool_nhwc_backward_db): the kernel then spends no MMA on the bias gradient. */
+BF_API int bf_conv_nhwc_backward_filter_dbp(const float* X, const float* E, float* dF, float* db, const float* db_partial, int db_rows,
+                                     int im, int ic, int iy, int ix, int nf, int fy, int fx, void* stream);
 
 /* First layer (ic <= 4 input channels, e.g. RGB): X stays NCHW as the reference holds it, the 32/64/128-channel
  * side (Y, E) is channels-last.  Forward = Toeplitz-descriptor implicit GEMM (no im2col), filter gradient = TMA-fed
@@ -205,6 +209,12 @@ BF_API int bf_pool_nhwc_forward(const float* A, float* out, uint8_t* mask, int i
                          void* stream);
 BF_API int bf_pool_nhwc_backward(const float* E, const uint8_t* mask, const float* gate, float* dX, int im, int c, int iy,
                           int ix, int fdim, void* stream);
+/* bf_pool_nhwc_backward that also writes, per CTA, the per-channel sums of dX into db_partial (bf_pool_nhwc_db_rows(..)
+ * rows of c floats): summed over the rows this is E.sum((0,2,3)), the bias gradient of the convolution whose output
+ * was pooled (atomic/tensor_op.py:55), handed to bf_conv_nhwc_backward_filter_dbp.  fdim 2, c dividing 1024. */
+BF_API int bf_pool_nhwc_db_rows(int im, int c, int iy, int ix, int fdim);
+BF_API int bf_pool_nhwc_backward_db(const float* E, const uint8_t* mask, const float* gate, float* dX, float* db_partial, int im, int c,
+                             int iy, int ix, int fdim, void* stream);
 
 /* ---- global average pooling: layers/tensor.py:95-114 ---- */
 /* out (im, c) = A.mean over the hw pixels of every (image, channel) plane; nhwc != 0: A is stored (im, hw, c). */

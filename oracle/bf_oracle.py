@@ -80,6 +80,15 @@ def _site_modes(site):
     return pol(site, _TF32["layer"]) if callable(pol) else pol.get(site)
 
 
+def _db_site_declared(pol):
+    """True when the policy speaks about the "conv.db" site for the current layer (a per-layer table marks it with the
+    attribute `declares`, a dict by containing the key)."""
+    if callable(pol):
+        decl = getattr(pol, "declares", None)
+        return bool(decl and decl("conv.db", _TF32["layer"]))
+    return "conv.db" in pol
+
+
 def _operands(site, A, B):
     """The two operands of a contraction as the kernel behind `site` feeds them to the tensor core."""
     if _TF32["policy"] is None:
@@ -182,7 +191,16 @@ def conv_backward(X, E, F):
     db = E.sum((0,2,3), keepdims) ; dX = full(E, flip_hw(F)^T(1023))."""
     Xa, Ea = _operands("conv.dF", X, E)
     dF = conv_forward(Xa.transpose(1, 0, 2, 3), Ea.transpose(1, 0, 2, 3), "valid", site=None).transpose(1, 0, 2, 3)
-    db = (Ea if _site_modes("conv.dF") else E).sum(axis=(0, 2, 3), keepdims=True)   # all-ones operand of the same MMA
+    # db: all-ones operand of the dF MMA (sees E as that operand is rounded) unless the policy says how db is formed
+    # ("conv.db": a rounding mode, or None = summed in FP32 by the kernel that produced E)
+    pol = _TF32["policy"]
+    if pol is None:
+        db = E.sum(axis=(0, 2, 3), keepdims=True)
+    elif _db_site_declared(pol):
+        m = _site_modes("conv.db")
+        db = (tf32_round(E, m) if m is not None else tf32_round(E, None)).sum(axis=(0, 2, 3), keepdims=True)
+    else:
+        db = (Ea if _site_modes("conv.dF") else E).sum(axis=(0, 2, 3), keepdims=True)
     Eb, Fb = _operands("conv.dX", E, F)
     dX = conv_forward(Eb, Fb[:, :, ::-1, ::-1].transpose(1, 0, 2, 3), "full", site=None)
     return np.ascontiguousarray(dF), db, dX
