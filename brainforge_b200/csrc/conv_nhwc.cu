@@ -26,7 +26,7 @@
 
 namespace bf {
 
-constexpr int IG_THREADS = 224;   // igemm: warp 0 TMA, warps 1-2 MMA issuers (tiles of even / odd index), warps 3-6 epilogue
+constexpr int IG_THREADS = 352;   // igemm: warp 0 TMA, warps 1-2 MMA issuers (tiles of even / odd index), warps 3-6 / 7-10 two epilogue groups (tiles of even / odd index)
 constexpr int DF_THREADS = 192;
 constexpr int IG_ACCSET_COLS = 256;   // two accumulator sets in the 512 TMEM columns
 
@@ -44,7 +44,7 @@ struct IgemmParams {
 #define IG_T(var) long long var = p.prof ? clock64() : 0
 #define IG_ACC(slot, t0) do { if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) p.prof[slot] += clock64() - (t0); } while (0)
 constexpr int IG_STAGE_LD = 36;                                  // floats per staged epilogue row (32 + 4 pad)
-constexpr int IG_STAGING_BYTES = 4 * 32 * IG_STAGE_LD * 4;       // four epilogue warps
+constexpr int IG_STAGING_BYTES = 8 * 32 * IG_STAGE_LD * 4;       // eight epilogue warps
 
 // FOLD: the fx taps of a filter row are folded into the N dimension of ONE MMA -- D'[q][tx*NB + n] = sum_c in[q + ty*PW][c] *
 // Wt[(ty,tx)][n][c] -- and the epilogue adds the fx column blocks with a shift of tx positions: out[q][n] = sum_tx D'[q + tx]
@@ -76,7 +76,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 2); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 2); mbar_init(&t_empty[i], 8); }
     for (int i = 0; i < 8; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
     for (int i = 0; i < 16; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -229,8 +229,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // ===================================================================== epilogue (TMEM lanes 32*(warp%4)..+31)
     // TMEM -> registers (+ReLU, +bias) -> a padded per-warp staging tile -> global, so that every store
     // instruction writes whole 128-byte lines (4 rows x 32 channels) instead of 32 scattered 16-byte pieces.
-    const int quad = warp & 3;
-    float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + quad * 32 * IG_STAGE_LD;
+    // two groups of four warps (one TMEM lane quadrant each); group eg drains the tiles of index eg, eg + 2, ...
+    const int quad = warp & 3, eg = (warp - 3) >> 2;
+    float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + (eg * 4 + quad) * 32 * IG_STAGE_LD;
     int it = 0;
     IG_T(te);
     for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
@@ -238,7 +239,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int grp = st / p.nbands, band = st - grp * p.nbands;
       { IG_T(t0); mbar_wait(&t_full[as], (uint32_t)(au & 1)); if (warp == 3 && lane == 0) IG_ACC(5, t0); }
       tc_fence_after();
-      for (int t = 0; t < p.T; ++t) {
+      for (int t = eg; t < p.T; t += 2) {
         const int rloc = quad * 32 + lane;                              // row of the tile
         const int q = t * p.TS + rloc;
         const int g = q / p.IR, ql = q - g * p.IR;
@@ -248,52 +249,70 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int orow = (img * p.out_y + yo) * p.out_x + x;          // output pixel index (rows of N floats)
         const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
         if (FOLD) {
-          // column blocks tx >= 1 go through a shared tile, shifted back by tx rows when they are read; all four
-          // epilogue warps pass the same named barriers (no early exit for a warp without valid rows)
-          float* fsh = reinterpret_cast<float*>(dyn_smem) + (stage_base + IG_STAGING_BYTES - smem_u32(dyn_smem)) / 4;
+          // column blocks tx >= 1 go through the group's shared tile, shifted back by tx rows when they are read; the sums
+          // return to the tile (slot 0, own row) for the coalesced copy-out.  All four warps of the group pass the same
+          // named barriers (no early exit for a warp without valid rows).  16 columns per pass.
+          float* fsh = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 +
+                       (size_t)eg * (p.fx - 1) * IG_FOLD_ROWS * IG_FOLD_LD;
           const uint32_t taddr_f = tmem + ((uint32_t)(quad * 32) << 16) + as * IG_ACCSET_COLS + (uint32_t)(t * NB * p.fx);
+          const int bar_id = 1 + eg;
 #pragma unroll 1
-          for (int cb = 0; cb < NB; cb += 32) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-              for (int tx = 1; tx < p.fx; ++tx) {
-                uint32_t v[16];
-                tmem_ld16(taddr_f + tx * NB + cb + c0, v);
-                tmem_ld_wait();
-                float* dstrow = fsh + ((size_t)(tx - 1) * IG_FOLD_ROWS + rloc) * IG_FOLD_LD;
+          for (int cc = 0; cc < NB; cc += 16) {
+            uint32_t v0[16], v1[16];
+            tmem_ld16(taddr_f + NB + cc, v0);
+            if (p.fx > 2) tmem_ld16(taddr_f + 2 * NB + cc, v1);
+            tmem_ld_wait();
+            {
+              float* d0 = fsh + (size_t)rloc * IG_FOLD_LD;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<uint4*>(dstrow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(d0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+              if (p.fx > 2) {
+                float* d1 = fsh + (size_t)(IG_FOLD_ROWS + rloc) * IG_FOLD_LD;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(d1 + j) = make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
               }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              uint32_t v[16];
-              tmem_ld16(taddr_f + cb + c0, v);
+            }
+            for (int tx = 3; tx < p.fx; ++tx) {
+              tmem_ld16(taddr_f + tx * NB + cc, v0);
               tmem_ld_wait();
+              float* d = fsh + ((size_t)(tx - 1) * IG_FOLD_ROWS + rloc) * IG_FOLD_LD;
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 bb = *reinterpret_cast<const float4*>(&sbias[cb + c0 + j]);
-                float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                       __uint_as_float(v[j + 3]));
-                for (int tx = 1; tx < p.fx; ++tx) {
-                  const float4 a = *reinterpret_cast<const float4*>(fsh + ((size_t)(tx - 1) * IG_FOLD_ROWS + rloc + tx) * IG_FOLD_LD + j);
-                  r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
-                }
-                if (RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-                r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
-                *reinterpret_cast<float4*>(stg + lane * IG_STAGE_LD + c0 + j) = r;
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(d + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+            }
+            tmem_ld16(taddr_f + cc, v0);                      // the unshifted block meanwhile
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            tmem_ld_wait();
+            float4 r4[4];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 r = make_float4(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1]), __uint_as_float(v0[j + 2]),
+                                     __uint_as_float(v0[j + 3]));
+              for (int tx = 1; tx < p.fx; ++tx) {
+                const float4 a = *reinterpret_cast<const float4*>(fsh + ((size_t)(tx - 1) * IG_FOLD_ROWS + rloc + tx) * IG_FOLD_LD + j);
+                r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
               }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              const float4 bb = *reinterpret_cast<const float4*>(&sbias[cc + j]);
+              if (RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+              r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+              r4[j >> 2] = r;
             }
-            __syncwarp();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");       // every shifted read of this pass is done
+            {
+              float* d0 = fsh + (size_t)rloc * IG_FOLD_LD;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + (lane >> 3);
-              const int dst_row = __shfl_sync(0xffffffffu, orow, r);
-              const float4 val = *reinterpret_cast<const float4*>(stg + r * IG_STAGE_LD + (lane & 7) * 4);
-              if ((okmask >> r) & 1u)
-                *reinterpret_cast<float4*>(out + (size_t)dst_row * p.N + n0 + cb + (lane & 7) * 4) = val;
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(d0 + 4 * j) = r4[j];
             }
             __syncwarp();
+            // copy-out: the warp's 32 rows x 16 columns, four lanes per row (64 contiguous bytes)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2);
+              const int dst_row = __shfl_sync(0xffffffffu, orow, r);
+              const float4 val = *reinterpret_cast<const float4*>(fsh + (size_t)(quad * 32 + r) * IG_FOLD_LD + (lane & 3) * 4);
+              if ((okmask >> r) & 1u)
+                *reinterpret_cast<float4*>(out + (size_t)dst_row * p.N + n0 + cc + (lane & 3) * 4) = val;
+            }
+            __syncwarp();         // the warp's rows of slot 0 are rewritten by the next pass
           }
           continue;
         }
@@ -579,7 +598,8 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N,
     const int NBF = fold ? NB * fx : NB, TS = fold ? 128 - (fx - 1) : 128;
     const int Tmax = IG_ACCSET_COLS / NBF;
     const int max_shift = fold ? (fy - 1) * PW : (fy - 1) * PW + fx - 1;
-    const size_t fixed = 2048 + IG_STAGING_BYTES + (fold ? (size_t)(fx - 1) * IG_FOLD_ROWS * IG_FOLD_LD * 4 : 0);
+    // epilogue scratch: per-warp staging tiles, or (folded) one shifted-read tile per epilogue group
+    const size_t fixed = 2048 + (fold ? (size_t)2 * (fx - 1) * IG_FOLD_ROWS * IG_FOLD_LD * 4 : (size_t)IG_STAGING_BYTES);
     const long last = (long)(G - 1) * IR + (long)(RO - 1) * PW + out_x;   // positions to cover
     const int T = (int)((last + TS - 1) / TS);
     if (T > Tmax || T < 1) return false;
