@@ -165,6 +165,28 @@ class ReshapeOp:
 
 
 # --------------------------------------------------------------------------- convolution
+class FilterPack:
+    """The two packed forms of a filter the channels-last kernels contract against (forward [tap][f][c]; data gradient,
+    flipped and transposed, [tap][c][f]), written by ONE launch in the forward pass and reused by the backward pass of
+    the same step.  `current(F)` is true only while no host-API call has written parameter memory since (device.mutations)."""
+
+    def __init__(self):
+        self.fwd = self.dx = None
+        self.stamp = self.src = None
+
+    def repack(self, f):
+        from .device import mutations
+        nf, ic, fy, fx = f.shape
+        if self.fwd is None or self.fwd.size != f.size:
+            self.fwd, self.dx = DeviceArray.empty(f.size), DeviceArray.empty(f.size)
+        call(L.bf_conv_nhwc_repack, f.ptr, self.fwd.ptr, self.dx.ptr, nf, ic, fy, fx, stream_ptr())
+        self.stamp, self.src = mutations(), f.t.data_ptr()
+
+    def current(self, f):
+        from .device import mutations
+        return self.dx is not None and self.stamp == mutations() and self.src == f.t.data_ptr() and self.dx.size == f.size
+
+
 class ConvolutionOp:
     """atomic/tensor_op.py:6-75 / llatomic/lltensor_op.py:75-121.  Filter layout (nf, fc, fy, fx).
 
@@ -192,7 +214,9 @@ class ConvolutionOp:
         return "generic"
 
     @staticmethod
-    def forward(A, F, mode="valid", bias=None, activation="linear"):
+    def forward(A, F, mode="valid", bias=None, activation="linear", pack=None):
+        """`pack` (a FilterPack owned by the calling layer): the channels-last route re-lays F into both packed forms
+        with one launch and leaves them there for the data gradient of the same step."""
         a, f = as_device(A), as_device(F)
         im, ic, iy, ix = a.shape
         nf, fc, fy, fx = f.shape
@@ -207,8 +231,13 @@ class ConvolutionOp:
             try:
                 if route == "nhwc":
                     an = a.to_nhwc()      # (a named local: a temporary's block could be reused before the launch)
-                    call(L.bf_conv_nhwc_forward, an.pptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
-                         _lib.ACT[activation], stream_ptr())
+                    if pack is not None:
+                        pack.repack(f)
+                        call(L.bf_conv_nhwc_forward_packed, an.pptr, pack.fwd.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
+                             _lib.ACT[activation], stream_ptr())
+                    else:
+                        call(L.bf_conv_nhwc_forward, an.pptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
+                             _lib.ACT[activation], stream_ptr())
                 else:
                     call(L.bf_conv_c3_forward, a.ptr, f.ptr, bptr, out.pptr, im, ic, iy, ix, nf, fy, fx,
                          _lib.ACT[activation], stream_ptr())
@@ -274,7 +303,7 @@ class ConvolutionOp:
         return ConvolutionOp.forward(A, F, "full")
 
     @staticmethod
-    def backward(X, E, F, dF=None, db=None, need_dX=True):
+    def backward(X, E, F, dF=None, db=None, need_dX=True, pack=None):
         """-> (dF, db, dX); keyword call like layers/tensor.py:83 (the two reference back-ends disagree on
         the positional order).  db has the NumPy back-end's shape (1,nf,1,1).  dX comes back in
         the storage layout of X where a channels-last kernel exists, NCHW otherwise."""
@@ -315,8 +344,12 @@ class ConvolutionOp:
             if route == "nhwc":
                 try:
                     dX = DeviceArray.empty_nhwc(im, ic, iy, ix)
-                    call(L.bf_conv_nhwc_backward_data, en.pptr, f.ptr, dX.pptr, im, ic, iy, ix, nf, fy, fx,
-                         stream_ptr(), tag="dX")
+                    if pack is not None and pack.current(f):
+                        call(L.bf_conv_nhwc_backward_data_packed, en.pptr, pack.dx.ptr, dX.pptr, im, ic, iy, ix, nf, fy, fx,
+                             stream_ptr(), tag="dX")
+                    else:
+                        call(L.bf_conv_nhwc_backward_data, en.pptr, f.ptr, dX.pptr, im, ic, iy, ix, nf, fy, fx,
+                             stream_ptr(), tag="dX")
                 except _lib.Unsupported:
                     dX = None
             if dX is None:

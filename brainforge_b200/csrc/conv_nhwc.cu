@@ -556,6 +556,32 @@ __global__ void conv_repack_nhwc_kernel(const float* __restrict__ F, float* __re
   }
 }
 
+// both forms in one pass over F: the forward operand and the flipped / transposed data-gradient operand
+__global__ void conv_repack_both_kernel(const float* __restrict__ F, float* __restrict__ Wf, float* __restrict__ Wd, int nf, int ic,
+                                        int fy, int fx) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int ntaps = fy * fx;
+  const long total = (long)ntaps * nf * ic;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    {   // forward: Wf[tap][n = f][k = c]
+      const int k = (int)(i % ic);
+      long r = i / ic;
+      const int n = (int)(r % nf), tap = (int)(r / nf);
+      const int ty = tap / fx, tx = tap - ty * fx;
+      Wf[i] = F[(((long)n * ic + k) * fy + ty) * fx + tx];
+    }
+    {   // data gradient: Wd[tap][n = c][k = f] = F[f][c][fy-1-ty][fx-1-tx]
+      const int k = (int)(i % nf);
+      long r = i / nf;
+      const int n = (int)(r % ic), tap = (int)(r / ic);
+      const int ty = tap / fx, tx = tap - ty * fx;
+      Wd[i] = F[(((long)k * ic + n) * fy + (fy - 1 - ty)) * fx + (fx - 1 - tx)];
+    }
+  }
+}
+
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 // dF kernel: [E slots | X slots | ones]; the A operand always spans four 32-filter groups (M = 128), so for
 // nf < 128 the junk groups read behind the last E slot must still fall inside the allocation
@@ -899,6 +925,34 @@ int bf_conv_nhwc_backward_filter_dbp(const float* X, const float* E, float* dF, 
                                      int im, int ic, int iy, int ix, int nf, int fy, int fx, void* stream) {
   BF_REQUIRE(db_partial && db_rows > 0, BF_ERR_ARG, "bf_conv_nhwc_backward_filter_dbp: no partials");
   return conv_nhwc_backward_filter_impl(X, E, dF, db, db_partial, db_rows, im, ic, iy, ix, nf, fy, fx, stream);
+}
+
+// ---- pre-packed filters: a layer re-lays its filter ONCE per weight update (both forms in one launch) and hands the
+// packed operands to the forward / data-gradient kernels, instead of one re-layout launch in front of each of them
+int bf_conv_nhwc_repack(const float* F, float* Wt_fwd, float* Wt_dx, int nf, int ic, int fy, int fx, void* stream) {
+  BF_REQUIRE(F && Wt_fwd && Wt_dx && nf > 0 && ic > 0 && fy > 0 && fx > 0, BF_ERR_ARG, "bf_conv_nhwc_repack: bad arguments");
+  launch_pdl(conv_repack_both_kernel, dim3(ew_grid((size_t)nf * ic * fy * fx, 256)), dim3(256), 0, as_stream(stream), F, Wt_fwd, Wt_dx,
+             nf, ic, fy, fx);
+  BF_LAUNCH_CHECK();
+  return BF_OK;
+}
+
+int bf_conv_nhwc_forward_packed(const float* X, const float* Wt_fwd, const float* bias, float* Y, int im, int ic, int iy, int ix,
+                                int nf, int fy, int fx, int act, void* stream) {
+  BF_REQUIRE(conv_nhwc_supported(ic, nf, fy, fx), BF_ERR_ARG, "bf_conv_nhwc_forward_packed: unsupported shape (ic=%d nf=%d)", ic, nf);
+  BF_REQUIRE(act == BF_ACT_LINEAR || act == BF_ACT_RELU, BF_ERR_ARG, "bf_conv_nhwc_forward_packed: only linear / relu are fused");
+  if (im <= 0) return BF_OK;
+  set_last_path(2);
+  return conv_nhwc_igemm(X, Wt_fwd, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act == BF_ACT_RELU ? 1 : 0,
+                         getenv("BF_IGEMM_FOLD_FWD") != nullptr, as_stream(stream));
+}
+
+int bf_conv_nhwc_backward_data_packed(const float* E, const float* Wt_dx, float* dX, int im, int ic, int iy, int ix, int nf, int fy,
+                                      int fx, void* stream) {
+  BF_REQUIRE(conv_nhwc_supported(nf, ic, fy, fx), BF_ERR_ARG, "bf_conv_nhwc_backward_data_packed: unsupported shape (ic=%d nf=%d)", ic, nf);
+  if (im <= 0) return BF_OK;
+  set_last_path(2);
+  return conv_nhwc_igemm(E, Wt_dx, nullptr, dX, im, iy - fy + 1, ix - fx + 1, nf, ic, fy, fx, fy - 1, fx - 1, 0, true, as_stream(stream));
 }
 
 int bf_conv_nhwc_supported(int ic, int nf, int fy, int fx) {

@@ -600,6 +600,8 @@ int bf_dense_head(const float* X, const float* W, const float* b, const float* Y
 #define BF_HEAD(NT_)                                                                                                       \
   if (nt == NT_) {                                                                                                         \
     BF_CUDA(cudaFuncSetAttribute(dense_head_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    /* several CTAs per SM: without the carve-out hint the driver sizes shared memory for ONE 75 KB CTA (measured: two waves) */ \
+    BF_CUDA(cudaFuncSetAttribute(dense_head_kernel<NT_>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
     launch_pdl(dense_head_kernel<NT_>, dim3(chunks), dim3(256), smem, s, X, W, b, Y, sample_w, out, partial, dX, cpart,    \
                cost_result, hits_result, m, k, n, R, act, cost, pc, phw);                                                  \
   }

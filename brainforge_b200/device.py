@@ -11,7 +11,17 @@ import torch
 
 from . import _lib
 
-_state = {"workspace": None, "precision": _lib.PREC["fp32"], "ws_generation": 0, "ws_retired": []}
+_state = {"workspace": None, "precision": _lib.PREC["fp32"], "ws_generation": 0, "ws_retired": [], "mutations": 0}
+
+
+def note_mutation():
+    """Called by everything that writes parameter memory from the host API (uploads, fills, optimizer steps): lets a layer
+    tell whether operands it derived from its weights during the forward pass (packed filters) are still current."""
+    _state["mutations"] += 1
+
+
+def mutations():
+    return _state["mutations"]
 DEFAULT_WORKSPACE = 64 << 20
 
 
@@ -158,6 +168,7 @@ class DeviceArray:
 
     def copy_from_host(self, a):
         assert not self.nhwc
+        note_mutation()
         a = np.asarray(a)
         if tuple(a.shape) != self.shape:
             a = a.reshape(self.shape)
@@ -272,6 +283,7 @@ class DeviceArray:
 
     def fill(self, value):
         """Every element = value, without reading the old contents (a NaN / Inf already there does not survive)."""
+        note_mutation()
         if self.size:
             call(_lib.lib.bf_fill, self.pptr, self.size, float(value), stream_ptr())
         return self
@@ -284,6 +296,7 @@ class DeviceArray:
         s = float(scalar)
         if s == 0.0:
             return self.fill_zero()      # the reference's idiom for zero_gradients: must also clear non-finite values
+        note_mutation()
         if self.size:
             call(_lib.lib.bf_affine, self.pptr, self.pptr, self.size, s, 0.0, stream_ptr())
         return self

@@ -133,7 +133,10 @@ class ConvLayer(LayerBase):
                 if fused is not None:
                     # the convolution output is not materialised; `self.output` re-runs the plain kernel on demand
                     return FusedConvPool(self, fused[0], fused[1], relu_in)
-        self._output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation))
+        if getattr(self, "_pack", None) is None:
+            self._pack = atomic.FilterPack()
+        self._output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation),
+                                       pack=self._pack if not self._standalone else None)
         return self._output
 
     @property
@@ -160,7 +163,7 @@ class ConvLayer(LayerBase):
             delta = self.activation.backward_mul(self.output, delta)
             delta.db_partial = None          # channel sums left by a pooling layer describe the delta BEFORE act'
         _, _, dX = self.op.backward(X=self.inputs, E=delta, F=self.weights, dF=self.nabla_w, db=self.nabla_b,
-                                    need_dX=need_dX)
+                                    need_dX=need_dX, pack=getattr(self, "_pack", None))
         return dX
 
     @property

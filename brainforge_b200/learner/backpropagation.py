@@ -15,7 +15,7 @@ import torch
 
 from .abstract_learner import Learner
 from .. import _lib
-from ..device import DeviceArray, as_device, call, stream_ptr, workspace_generation
+from ..device import DeviceArray, as_device, call, stream_ptr, workspace_generation, note_mutation
 from ..metrics import metrics as _metrics
 from ..optimizers import optimizers, GradientDescent
 from .. import dist as _dist
@@ -199,6 +199,7 @@ class Backpropagation(Learner):
             torch.cuda.current_stream().wait_stream(side)
             entry["graph"], entry["ws_gen"] = g, workspace_generation()
         entry["graph"].replay()
+        note_mutation()               # the replayed step updated the weights behind Python's back
         return lambda: self._read_scalars(metrics, m_local)
 
     # ------------------------------------------------------------------ pieces of the public API

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import dist as _dist
-from ..device import DeviceArray, as_device
+from ..device import DeviceArray, as_device, note_mutation
 from ..layers.abstract_layer import LayerBase
 from ..layers.core import InputLayer
 
@@ -86,6 +86,7 @@ class LayerStack:
             setattr(layer, gname, DeviceArray(G[o:o + size].view(g_old.shape)))
         self.flat_weights, self.flat_grads, self._segments = DeviceArray(W), DeviceArray(G), segs
         self._flat_dirty = False
+        note_mutation()
 
     @property
     def flat_size(self):

@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 
 from .. import _lib
-from ..device import DeviceArray, call, stream_ptr
+from ..device import DeviceArray, call, stream_ptr, note_mutation
 
 _NULL = ctypes.c_void_p(0)
 
@@ -52,6 +52,7 @@ class GradientDescent(Optimizer):
         gd = DeviceArray.from_host(np.asarray(gW).ravel()) if not isinstance(gW, DeviceArray) else gW
         s1, s2 = self._state(Wd.size)
         hp0, hp1, hp2 = self._hp()
+        note_mutation()
         call(_lib.lib.bf_opt_step, _lib.OPT[self.kind], Wd.ptr, gd.ptr, s1, s2, Wd.size, float(self.eta), float(m),
              float(hp0), float(hp1), float(hp2), 1 if zero_grad else 0, stream_ptr())
         return Wd.numpy().reshape(np.shape(W)) if host else Wd
@@ -62,6 +63,7 @@ class GradientDescent(Optimizer):
         is cleared, its tail holds the summed scalars (cost sum, hits, sample count)."""
         s1, s2 = self._state(n_params)
         hp0, hp1, hp2 = self._hp()
+        note_mutation()
         call(_lib.lib.bf_opt_step_allreduce, _lib.OPT[self.kind], W.ptr, G.ptr, s1, s2, n_params, G.size, float(self.eta),
              float(m), float(hp0), float(hp1), float(hp2), 1, symm.peers_dev, symm.pads_dev, symm.epoch.data_ptr(),
              symm.timeout.data_ptr(), float(m_local), symm.rank, symm.world, symm.blocks, stream_ptr())

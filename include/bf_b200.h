@@ -151,6 +151,15 @@ BF_API int bf_conv_nhwc_forward(const float* X, const float* F, const float* bia
                          int nf, int fy, int fx, int act, void* stream);
 BF_API int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX, int im, int ic, int iy, int ix, int nf,
                                int fy, int fx, void* stream);
+/* Pre-packed filter operands: bf_conv_nhwc_repack writes, in one launch, the forward operand Wt_fwd[tap][f][c] and the
+ * flipped / transposed data-gradient operand Wt_dx[tap][c][f] (nf*ic*fy*fx floats each) of F (nf,ic,fy,fx); the two
+ * _packed calls are bf_conv_nhwc_forward / bf_conv_nhwc_backward_data without their own re-layout launch.  A layer
+ * repacks once per weight change (layers/tensor.py ConvLayer). */
+BF_API int bf_conv_nhwc_repack(const float* F, float* Wt_fwd, float* Wt_dx, int nf, int ic, int fy, int fx, void* stream);
+BF_API int bf_conv_nhwc_forward_packed(const float* X, const float* Wt_fwd, const float* bias, float* Y, int im, int ic, int iy, int ix,
+                                int nf, int fy, int fx, int act, void* stream);
+BF_API int bf_conv_nhwc_backward_data_packed(const float* E, const float* Wt_dx, float* dX, int im, int ic, int iy, int ix, int nf,
+                                      int fy, int fx, void* stream);
 BF_API int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy,
                                  int ix, int nf, int fy, int fx, void* stream);
 /* The same with db = sum of the `db_rows` rows of per-CTA channel sums the producer of E left in db_partial
