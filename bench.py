@@ -272,7 +272,25 @@ def algorithmic_cost(label):
         X, E, F = im * ic * iy * ix, im * nf * oy * ox, nf * ic * fy * fx
         flops = 2.0 * im * oy * ox * nf * ic * fy * fx
         return (f * (X + E + F + nf), flops) if tag == "dF" else (f * (E + F + X), flops)
-    if name in ("bf_conv_nhwc_forward", "bf_conv_c3_forward"):
+    if name == "bf_conv_nhwc_backward_filter_dbp":   # leading int = rows of per-CTA channel sums left by the pooling pass
+        a = a[1:]
+        name = "bf_conv_nhwc_backward_filter"
+    if name == "bf_conv_nhwc_backward_data_packed":
+        name = "bf_conv_nhwc_backward_data"
+    if name == "bf_conv_nhwc_forward_pool_packed":   # read X, packed F, bias; write the POOLED output + 1 mask byte each
+        im, ic, iy, ix, nf, fy, fx = a[:7]
+        oy, ox = iy - fy + 1, ix - fx + 1
+        pooled = im * nf * (oy // 2) * (ox // 2)
+        return f * (im * ic * iy * ix + nf * ic * fy * fx + nf + pooled) + pooled, 2.0 * im * oy * ox * nf * ic * fy * fx
+    if name == "bf_pool_nhwc_backward_db":  # read E, mask, gate (pooled output); write dX + the per-CTA channel sums
+        im, c, iy, ix, fd = a[:5]
+        n = im * c * iy * ix
+        return f * n + 2 * f * n // (fd * fd) + n // (fd * fd), 0.0
+    if name == "bf_dense_head":             # X, W, b, Y read; out, dX written; dW, db read-modify-written
+        m, chan, hw, n = a[:4]
+        k = chan * hw
+        return f * (2 * m * k + 3 * m * n + 3 * k * n + 3 * n), 6.0 * m * k * n
+    if name in ("bf_conv_nhwc_forward", "bf_conv_c3_forward", "bf_conv_nhwc_forward_packed"):
         im, ic, iy, ix, nf, fy, fx = a[:7]
         oy, ox = iy - fy + 1, ix - fx + 1
         return f * (im * ic * iy * ix + nf * ic * fy * fx + nf + im * nf * oy * ox), 2.0 * im * oy * ox * nf * ic * fy * fx

@@ -73,6 +73,7 @@ SIGNATURES = {
     "bf_pool_nhwc_backward_db": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
     "bf_conv_nhwc_repack": (_i, [_vp] * 3 + [_i] * 4 + [_vp]),
     "bf_conv_nhwc_forward_packed": (_i, [_vp] * 4 + [_i] * 8 + [_vp]),
+    "bf_conv_nhwc_forward_pool_packed": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
     "bf_conv_nhwc_backward_data_packed": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),
     "bf_conv_nhwc_backward_filter_dbp": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
     "bf_gap_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

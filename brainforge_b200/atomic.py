@@ -7,6 +7,7 @@ Every op accepts host NumPy arrays (copied in, result copied back as float64 -- 
 tests do) or `DeviceArray`s (stay in HBM, what the layers use).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -198,6 +199,8 @@ class ConvolutionOp:
 
     channels_last = True      # class-wide switch: False keeps every convolution on the NCHW gather kernels
     db_from_pool = True       # take db from the channel sums the pooling backward pass leaves on E (no all-ones MMA)
+    # channels-last convolutions absorb a following [ReLU ->] PoolLayer(2) in their epilogue (BF_FUSE_POOL_NHWC=0: two kernels)
+    fuse_pool_nhwc = os.environ.get("BF_FUSE_POOL_NHWC", "1") != "0"
 
     @staticmethod
     def _route(a_nhwc, ic, iy, ix, nf, fy, fx, mode, activation):
@@ -251,28 +254,45 @@ class ConvolutionOp:
         return _ret(A, out)
 
     @staticmethod
-    def forward_pool(A, F, bias=None, activation="linear", relu_in=False):
-        """valid convolution (+ bias) -> [ReLU] -> 2x2 max pooling in ONE kernel, for the first-layer (ic <= 4) route:
-        returns (pooled, mask) exactly as `MaxPoolOp.forward([relu](ConvolutionOp.forward(A, F, bias=..)), 2)` would,
-        without the full-resolution activation ever reaching HBM; None when the shape cannot take the fused kernel."""
+    def forward_pool(A, F, bias=None, activation="linear", relu_in=False, pack=None):
+        """valid convolution (+ bias) -> [ReLU] -> 2x2 max pooling in ONE kernel: returns (pooled, mask) exactly as
+        `MaxPoolOp.forward([relu](ConvolutionOp.forward(A, F, bias=..)), 2)` would, without the full-resolution activation
+        ever reaching HBM; None when the shape cannot take a fused kernel.  First-layer route (ic <= 4, NCHW input):
+        bf_conv_c3_forward_pool; channels-last route (needs the layer's FilterPack): bf_conv_nhwc_forward_pool_packed."""
         a, f = as_device(A), as_device(F)
         im, ic, iy, ix = a.shape
         nf, fc, fy, fx = f.shape
-        if fc != ic or a.nhwc or ConvolutionOp._route(False, ic, iy, ix, nf, fy, fx, "valid", activation) != "c3":
+        if fc != ic or activation != "linear":
             return None
+        route = ConvolutionOp._route(a.nhwc, ic, iy, ix, nf, fy, fx, "valid", activation)
         oy, ox = iy - fy + 1, ix - fx + 1
-        if oy % 2 or ox % 2 or (128 // ix) < 2:
+        if route == "generic" or oy <= 0 or ox <= 0 or oy % 2 or ox % 2:
             return None
         import torch
         bd = as_device(bias).reshape(-1) if bias is not None else None
-        pooled = DeviceArray.empty_nhwc(im, nf, oy // 2, ox // 2)
-        words = torch.empty(max(pooled.size, 1), dtype=torch.uint8, device="cuda")
-        try:
-            call(L.bf_conv_c3_forward_pool, a.ptr, f.ptr, bd.ptr if bd is not None else _NULL, pooled.pptr,
-                 ctypes.c_void_p(words.data_ptr()), im, ic, iy, ix, nf, fy, fx, _lib.ACT[activation], 1 if relu_in else 0,
-                 stream_ptr())
-        except _lib.Unsupported:
-            return None
+        bptr = bd.ptr if bd is not None else _NULL
+        if route == "c3":
+            if a.nhwc or (128 // ix) < 2:
+                return None
+            pooled = DeviceArray.empty_nhwc(im, nf, oy // 2, ox // 2)
+            words = torch.empty(max(pooled.size, 1), dtype=torch.uint8, device="cuda")
+            try:
+                call(L.bf_conv_c3_forward_pool, a.ptr, f.ptr, bptr, pooled.pptr, ctypes.c_void_p(words.data_ptr()), im, ic, iy, ix,
+                     nf, fy, fx, _lib.ACT[activation], 1 if relu_in else 0, stream_ptr())
+            except _lib.Unsupported:
+                return None
+        else:
+            if pack is None or not ConvolutionOp.fuse_pool_nhwc:
+                return None
+            an = a.to_nhwc()
+            pooled = DeviceArray.empty_nhwc(im, nf, oy // 2, ox // 2)
+            words = torch.empty(max(pooled.size, 1), dtype=torch.uint8, device="cuda")
+            pack.repack(f)
+            try:
+                call(L.bf_conv_nhwc_forward_pool_packed, an.pptr, pack.fwd.ptr, bptr, pooled.pptr, ctypes.c_void_p(words.data_ptr()),
+                     im, ic, iy, ix, nf, fy, fx, 1 if relu_in else 0, stream_ptr())
+            except _lib.Unsupported:
+                return None
         return pooled, PoolMask(words, (im, nf, oy, ox), 2, nhwc=True)
 
     @staticmethod

@@ -38,6 +38,8 @@ struct IgemmParams {
   int na;         // depth of the A (activation tile) ring: HBM latency is hidden by na-1 tiles in flight
   int fy;         // filter rows
   int TS;         // positions between consecutive tiles of a stage: 128, or 128 - (fx - 1) when the filter columns are folded
+  int pool_relu;  // POOL: max(0, .) between the convolution (+ bias) and the pooling (an Activation("relu") layer in between)
+  uint8_t* pool_mask;   // POOL: 2x2 tie mask, one byte per pooled element, (im, out_y/2, out_x/2, N)
   long long* prof;   // debug (BF_PROF_IGEMM=1): per-role cycle counters of CTA 0, else null
 };
 
@@ -52,7 +54,11 @@ constexpr int IG_STAGING_BYTES = 8 * 32 * IG_STAGE_LD * 4;       // eight epilog
 // (40 clk for 16 clk of tensor work); folding amortises that read over 3x the columns and issues a third of the MMAs.
 // Tiles of a stage then overlap by fx - 1 positions (stride TS = 128 - (fx - 1)) so that every sum stays inside one tile.
 constexpr int IG_FOLD_ROWS = 132, IG_FOLD_LD = 20;      // 16 columns at a time (+4 pad: conflict-free float4 rows)
-template <int NB, int KH, bool RELU, bool FOLD = false>
+// POOL: ConvLayer -> [ReLU] -> PoolLayer(2) in one pass (layers/tensor.py:28-30,75-79; atomic/tensor_op.py:93-107): the
+// epilogue stages the stage's positions (whole images) 16 channels at a time in shared memory, max-pools the 2x2 windows
+// and writes the pooled tensor + tie mask; the full-resolution activation never goes to HBM.  `out` is the pooled tensor.
+constexpr int IG_POOL_LD = 20;
+template <int NB, int KH, bool RELU, bool FOLD = false, bool POOL = false>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, IgemmParams p,
                   float* __restrict__ out, const float* __restrict__ bias) {
@@ -239,6 +245,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int grp = st / p.nbands, band = st - grp * p.nbands;
       { IG_T(t0); mbar_wait(&t_full[as], (uint32_t)(au & 1)); if (warp == 3 && lane == 0) IG_ACC(5, t0); }
       tc_fence_after();
+      if (POOL) {
+        float* pt = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4;
+        const int et = (warp - 3) * 32 + lane;                       // 0..255 among the epilogue threads
+        const int PY = p.out_y >> 1, PX = p.out_x >> 1, wins = PY * PX, nitems = p.G * wins * 4;
+#pragma unroll 1
+        for (int cc = 0; cc < NB; cc += 16) {
+          for (int t = eg; t < p.T; t += 2) {
+            uint32_t v[16];
+            tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + as * IG_ACCSET_COLS + t * NB + cc, v);
+            tmem_ld_wait();
+            float* d = pt + (size_t)(t * 128 + quad * 32 + lane) * IG_POOL_LD;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(&sbias[cc + j]);
+              float4 r = make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
+                                     __uint_as_float(v[j + 3]) + bb.w);
+              if (p.pool_relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+              *reinterpret_cast<float4*>(d + j) = r;
+            }
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          for (int w = et; w < nitems; w += 256) {
+            const int win = w >> 2, c4 = w & 3;
+            const int g = win / wins, rem = win - g * wins;
+            const int py = rem / PX, px = rem - py * PX;
+            const int img = grp * p.G + g;
+            if (img < p.nimg) {
+              const float* s00 = pt + (size_t)(g * p.IR + (2 * py) * p.PW + 2 * px) * IG_POOL_LD + c4 * 4;
+              const float4 a = *reinterpret_cast<const float4*>(s00), b = *reinterpret_cast<const float4*>(s00 + IG_POOL_LD);
+              const float4 c = *reinterpret_cast<const float4*>(s00 + (size_t)p.PW * IG_POOL_LD);
+              const float4 d = *reinterpret_cast<const float4*>(s00 + (size_t)(p.PW + 1) * IG_POOL_LD);
+              float4 mx;
+              mx.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)); mx.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+              mx.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)); mx.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+              uchar4 mk;       // bit k = dy * 2 + dx set where the element equals the window's max (multi-hot on ties)
+              mk.x = (unsigned char)((a.x == mx.x) | ((b.x == mx.x) << 1) | ((c.x == mx.x) << 2) | ((d.x == mx.x) << 3));
+              mk.y = (unsigned char)((a.y == mx.y) | ((b.y == mx.y) << 1) | ((c.y == mx.y) << 2) | ((d.y == mx.y) << 3));
+              mk.z = (unsigned char)((a.z == mx.z) | ((b.z == mx.z) << 1) | ((c.z == mx.z) << 2) | ((d.z == mx.z) << 3));
+              mk.w = (unsigned char)((a.w == mx.w) | ((b.w == mx.w) << 1) | ((c.w == mx.w) << 2) | ((d.w == mx.w) << 3));
+              const size_t o = ((size_t)(img * PY + py) * PX + px) * p.N + n0 + cc + c4 * 4;
+              *reinterpret_cast<float4*>(out + o) = mx;
+              *reinterpret_cast<uchar4*>(p.pool_mask + o) = mk;
+            }
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[as]);
+        continue;
+      }
       for (int t = eg; t < p.T; t += 2) {
         const int rloc = quad * 32 + lane;                              // row of the tile
         const int q = t * p.TS + rloc;
@@ -378,6 +435,8 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
   const uint32_t x_base = base + (uint32_t)p.ns * e_slot, ones_base = x_base + (uint32_t)p.ns * x_slot;
   const uint32_t total_bytes = (uint32_t)p.ns * (e_slot + x_slot) + 1024u;
   const int split = blockIdx.x, ch = blockIdx.y;
+  constexpr int DF_M = MH <= 2 ? 64 : 128;         // rows of the accumulator (filters)
+  constexpr int DF_ROWS = MH * 32;                 // rows of a partial block
   pdl_launch_dependents();
   const int ntap_acc = p.ntaps + ((ch == 0 && p.with_db) ? 1 : 0);   // channel half 0 also accumulates db (all-ones operand)
 
@@ -425,9 +484,10 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
     const bool leader = elect_one_sync();
     // One MMA per filter ROW: the fx taps of a row are fx 32-channel N groups of the SAME operand, one pixel
     // (128 B = LBO) apart, landing in fx consecutive 32-column accumulators.
+    // nf <= 64: M = 64 MMAs (half the shared-memory read of the E operand per MMA, no junk filter groups)
     const int fy = p.ntaps / p.fx;
-    const uint32_t idesc_row = idesc_tf32(128, 32 * p.fx, true, true);
-    constexpr uint32_t idesc_one = idesc_tf32(128, 32, true, true);
+    const uint32_t idesc_row = idesc_tf32(DF_M, 32 * p.fx, true, true);
+    constexpr uint32_t idesc_one = idesc_tf32(DF_M, 32, true, true);
     const uint64_t ones_desc = desc_mn_sw128_32b(ones_base, 4096u, 512u);
     const uint32_t row_step = (uint32_t)(p.PW * 128) >> 4;   // descriptor units (16 B) per filter row
     int it = 0;
@@ -452,13 +512,14 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
     if (leader) umma_commit(&done);
   } else if (warp >= 2) {
     const int quad = warp & 3;
-    const int m = quad * 32 + lane;
+    // M = 128: row m of the accumulator is TMEM lane m; M = 64: row r sits in lane (r / 16) * 32 + r % 16
+    const int m = DF_M == 128 ? quad * 32 + lane : (lane < 16 ? quad * 16 + lane : DF_ROWS);
     if (my_stages > 0) {
       mbar_wait(&done, 0);
       tc_fence_after();
     }
-    // partial[split][ch][tap][m][32]
-    float* dst = partial + (((size_t)split * gridDim.y + ch) * (p.ntaps + 1)) * 128 * 32 + (size_t)m * 32;
+    // partial[split][ch][tap][m][32], m < DF_ROWS
+    float* dst = partial + (((size_t)split * gridDim.y + ch) * (p.ntaps + 1)) * DF_ROWS * 32 + (size_t)m * 32;
     for (int tap = 0; tap < p.ntaps + 1; ++tap) {
       uint32_t v[32];
       if (my_stages > 0 && tap < ntap_acc) {
@@ -468,10 +529,10 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
-      if (m < MH * 32) {
+      if (m < DF_ROWS) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(dst + (size_t)tap * 128 * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          *reinterpret_cast<uint4*>(dst + (size_t)tap * DF_ROWS * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
   }
@@ -493,7 +554,7 @@ conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict_
   pdl_launch_dependents();
   pdl_wait();
   const long nmain = (long)nch * ntaps * nf * 32, total = nmain + nf;
-  const size_t zstride = (size_t)nch * (ntaps + 1) * 128 * 32;
+  const size_t zstride = (size_t)nch * (ntaps + 1) * nf * 32;
   const long i = (long)blockIdx.x * 32 + threadIdx.x;
   const int zs = threadIdx.y;
   size_t off = 0;
@@ -505,11 +566,11 @@ conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict_
       const int f = (int)(r % nf);
       r /= nf;
       const int tap = (int)(r % ntaps), ch = (int)(r / ntaps);
-      off = ((size_t)(ch * (ntaps + 1) + tap) * 128 + f) * 32 + cl;
+      off = ((size_t)(ch * (ntaps + 1) + tap) * nf + f) * 32 + cl;
       dst = ((long)f * ic + ch * 32 + cl) * ntaps + tap;
     } else {
       const int f = (int)(i - nmain);
-      off = ((size_t)ntaps * 128 + f) * 32;
+      off = ((size_t)ntaps * nf + f) * 32;
       dst = -1 - f;
     }
   }
@@ -518,7 +579,16 @@ conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict_
     if (dst < 0 && dbp) {            // db from the per-CTA channel sums of the kernel that wrote E (bf_pool_nhwc_backward_db)
       for (int z = zs; z < dbrows; z += DF_RED_SLICES) s += dbp[(size_t)z * nf + (-1 - dst)];
     } else {
-      for (int z = zs; z < nsplit; z += DF_RED_SLICES) s += partial[(size_t)z * zstride + off];
+      float s1 = 0.f, s2 = 0.f, s3 = 0.f;        // independent chains: the loads of four splits are in flight together
+      int z = zs;
+      for (; z + 3 * DF_RED_SLICES < nsplit; z += 4 * DF_RED_SLICES) {
+        s += partial[(size_t)z * zstride + off];
+        s1 += partial[(size_t)(z + DF_RED_SLICES) * zstride + off];
+        s2 += partial[(size_t)(z + 2 * DF_RED_SLICES) * zstride + off];
+        s3 += partial[(size_t)(z + 3 * DF_RED_SLICES) * zstride + off];
+      }
+      for (; z < nsplit; z += DF_RED_SLICES) s += partial[(size_t)z * zstride + off];
+      s = (s + s1) + (s2 + s3);
     }
   }
   red[zs][threadIdx.x] = s;
@@ -605,7 +675,7 @@ struct IgemmPlan {
 // filter (resident if it fits, else a ring of taps) + the epilogue staging fit shared memory.  With `allow_fold` the
 // column-folded form (see the kernel) competes as well, where fx * NB accumulator columns and a resident filter fit.
 static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N, int fy, int fx, int pad_y, int pad_x,
-                            int relu, bool allow_fold, bool* folded) {
+                            int relu, bool allow_fold, bool* folded, bool pool = false) {
   IgemmPlan pl;
   pl.ok = false;
   pl.score = -1;
@@ -624,11 +694,13 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N,
     const int NBF = fold ? NB * fx : NB, TS = fold ? 128 - (fx - 1) : 128;
     const int Tmax = IG_ACCSET_COLS / NBF;
     const int max_shift = fold ? (fy - 1) * PW : (fy - 1) * PW + fx - 1;
-    // epilogue scratch: per-warp staging tiles, or (folded) one shifted-read tile per epilogue group
-    const size_t fixed = 2048 + (fold ? (size_t)2 * (fx - 1) * IG_FOLD_ROWS * IG_FOLD_LD * 4 : (size_t)IG_STAGING_BYTES);
     const long last = (long)(G - 1) * IR + (long)(RO - 1) * PW + out_x;   // positions to cover
     const int T = (int)((last + TS - 1) / TS);
     if (T > Tmax || T < 1) return false;
+    if (pool && nbands != 1) return true;            // pooling windows must not straddle stages: whole images only
+    // epilogue scratch: per-warp staging tiles, (folded) one shifted-read tile per epilogue group, or (pooling) the stage's positions
+    const size_t fixed = 2048 + (pool ? (size_t)T * 128 * IG_POOL_LD * 4
+                                      : fold ? (size_t)2 * (fx - 1) * IG_FOLD_ROWS * IG_FOLD_LD * 4 : (size_t)IG_STAGING_BYTES);
     long rows = (long)(T - 1) * TS + 128 + max_shift;
     if (rows < (long)G * IR) rows = (long)G * IR;
     rows = (rows + 7) / 8 * 8;
@@ -661,7 +733,7 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N,
     if (score > best) {
       best = score;
       pl.p = IgemmParams{nbands == 1 ? (B + G - 1) / G : B * nbands, nbands, G, IR, PW, T, (int)rows, ntaps, fx, -pad_x, -pad_y,
-                         RO, out_y, out_x, B, N, relu, nbs, resident ? 1 : 0, nkp, na, fy, TS, nullptr};
+                         RO, out_y, out_x, B, N, relu, nbs, resident ? 1 : 0, nkp, na, fy, TS, 0, nullptr, nullptr};
       pl.PH_box = PHb;
       pl.smem = 1024 + (size_t)na * a_slot + (size_t)nbs * b_slot + fixed - 2048;
       pl.ok = true;
@@ -685,7 +757,7 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N,
 
 template <int NB, int KH>
 static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, IgemmPlan& pl, float* out, const float* bias, bool fold,
-                        cudaStream_t s) {
+                        bool pool, cudaStream_t s) {
   static long long* d_prof = nullptr;
   const bool prof = getenv("BF_PROF_IGEMM") != nullptr;
   if (prof) {
@@ -700,7 +772,10 @@ static int launch_igemm(const CUtensorMap& mA, const CUtensorMap& mB, IgemmPlan&
     BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, RELU_, FOLD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));      \
     launch_pdl(conv_igemm_kernel<NB, KH, RELU_, FOLD_>, dim3(grid), dim3(IG_THREADS), pl.smem, s, mA, mB, pl.p, out, bias);                 \
   }
-  if (fold) {
+  if (pool) {
+    BF_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<NB, KH, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    launch_pdl(conv_igemm_kernel<NB, KH, false, false, true>, dim3(grid), dim3(IG_THREADS), pl.smem, s, mA, mB, pl.p, out, bias);
+  } else if (fold) {
     if constexpr (NB <= 64) {
       if (pl.p.relu) BF_IG_LAUNCH(true, true) else BF_IG_LAUNCH(false, true)
     }
@@ -736,12 +811,15 @@ bool conv_nhwc_supported(int C, int N, int fy, int fx) {
 
 // out[(b,y,x), n] = act( sum_{ty,tx,c} in[b, y - pad_y + ty, x - pad_x + tx, c] * Wt[(ty,tx)][n][c] ) + bias[n]
 static int conv_nhwc_igemm(const float* in, const float* Wt, const float* bias, float* out, int B, int H, int W, int C,
-                           int N, int fy, int fx, int pad_y, int pad_x, int relu, bool allow_fold, cudaStream_t s) {
+                           int N, int fy, int fx, int pad_y, int pad_x, int relu, bool allow_fold, cudaStream_t s,
+                           uint8_t* pool_mask = nullptr, int pool_relu = 0) {
   int KH = (C % 64 == 0) ? 2 : 1, nkp = C / (32 * KH);
   const int NB = pick_nb(N);
   bool fold = false;
-  IgemmPlan pl = plan_igemm(B, H, W, KH, nkp, NB, N, fy, fx, pad_y, pad_x, relu, allow_fold, &fold);
-  if (allow_fold && KH == 2) {
+  const bool pool = pool_mask != nullptr;
+  IgemmPlan pl = plan_igemm(B, H, W, KH, nkp, NB, N, fy, fx, pad_y, pad_x, relu, allow_fold && !pool, &fold, pool);
+  if (pool && pl.ok) { pl.p.pool_mask = pool_mask; pl.p.pool_relu = pool_relu; }
+  if (allow_fold && !pool && KH == 2) {
     // 64 channels per stage may leave no room for the resident filter + the folded epilogue's tile next to whole images:
     // 32 at a time (two K passes) competes
     bool fold1 = false;
@@ -769,7 +847,7 @@ static int conv_nhwc_igemm(const float* in, const float* Wt, const float* bias, 
     if (!tma_make_map(&mB, Wt, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return fail(BF_ERR_CUDA, "conv_nhwc: cuTensorMapEncodeTiled failed (filter)");
   }
-#define BF_IG_CASE(NB_, KH_) if (NB == NB_ && KH == KH_) return launch_igemm<NB_, KH_>(mA, mB, pl, out, bias, fold, s);
+#define BF_IG_CASE(NB_, KH_) if (NB == NB_ && KH == KH_) return launch_igemm<NB_, KH_>(mA, mB, pl, out, bias, fold, pool, s);
   BF_IG_CASE(32, 1) BF_IG_CASE(32, 2) BF_IG_CASE(64, 1) BF_IG_CASE(64, 2) BF_IG_CASE(128, 1) BF_IG_CASE(128, 2)
 #undef BF_IG_CASE
   return fail(BF_ERR_ARG, "conv_nhwc: unsupported channel counts %d -> %d", C, N);
@@ -844,10 +922,14 @@ static int conv_nhwc_backward_filter_impl(const float* X, const float* E, float*
     int ns = 8;
     while (ns >= 2 && df_smem_bytes(MH, Krows, x_rows, ns) > IG_SMEM_BUDGET) --ns;
     if (ns < 2) return false;
-    const double mma_clk = (Krows / 8) * (fy * ((128 + 32.0 * fx) / 4.0) + 40.0);
+    // one MMA per filter row and K step: max(shared-memory read of both operands at 128 B/clk, tensor floor 128 x N / 256)
+    const double m_rows = MH <= 2 ? 64.0 : 128.0, n_cols = 32.0 * fx;
+    const double one_mma = (m_rows + n_cols) / 4.0 > n_cols / 2.0 ? (m_rows + n_cols) / 4.0 : n_cols / 2.0;
+    const double mma_clk = (Krows / 8) * (fy * one_mma + 40.0);
     const double bytes = (double)G * (MH * e_rows + xr) * ix * 128.0;
     double stage_clk = (mma_clk > bytes / 24.0 ? mma_clk : bytes / 24.0) + 400.0 + (ns == 2 ? 3000.0 : ns == 3 ? 1000.0 : 0.0);
-    const double score = (double)G * RO * ox / stage_clk;
+    // useful filter-gradient pixels per stage: the last band of an image may be partly empty
+    const double score = (double)G * ((double)oy / nbands) * ox / stage_clk;
     if (score > best) {
       best = score;
       p = DfParams{nbands == 1 ? (im + G - 1) / G : im * nbands, nbands, G, IRx, ix, RO, Krows, x_rows, ntaps, fx, im, 1, e_rows, ns,
@@ -879,7 +961,7 @@ static int conv_nhwc_backward_filter_impl(const float* X, const float* E, float*
     if (nsplit > cap) nsplit = cap < 1 ? 1 : cap;
   }
   p.nsplit = nsplit;
-  const size_t part_bytes = al256((size_t)nsplit * nch * (ntaps + 1) * 128 * 32 * 4);
+  const size_t part_bytes = al256((size_t)nsplit * nch * (ntaps + 1) * nf * 32 * 4);
   void* ws = nullptr;
   int rc = workspace_require(part_bytes, &ws);
   if (rc) return rc;
@@ -945,6 +1027,19 @@ int bf_conv_nhwc_forward_packed(const float* X, const float* Wt_fwd, const float
   set_last_path(2);
   return conv_nhwc_igemm(X, Wt_fwd, bias, Y, im, iy, ix, ic, nf, fy, fx, 0, 0, act == BF_ACT_RELU ? 1 : 0,
                          getenv("BF_IGEMM_FOLD_FWD") != nullptr, as_stream(stream));
+}
+
+// ConvLayer -> [Activation("relu")] -> PoolLayer(2) in one kernel: P (im, oy/2, ox/2, nf) = maxpool2([relu](corr(X, F) + bias)),
+// mask = the pooling layer's tie mask (one byte per pooled element).  Returns BF_ERR_ARG when no whole-image tiling exists.
+int bf_conv_nhwc_forward_pool_packed(const float* X, const float* Wt_fwd, const float* bias, float* P, uint8_t* mask, int im, int ic,
+                                     int iy, int ix, int nf, int fy, int fx, int relu_in, void* stream) {
+  BF_REQUIRE(conv_nhwc_supported(ic, nf, fy, fx), BF_ERR_ARG, "bf_conv_nhwc_forward_pool_packed: unsupported shape (ic=%d nf=%d)", ic, nf);
+  const int oy = iy - fy + 1, ox = ix - fx + 1;
+  BF_REQUIRE(oy > 0 && ox > 0 && (oy & 1) == 0 && (ox & 1) == 0 && P && mask, BF_ERR_ARG,
+             "bf_conv_nhwc_forward_pool_packed: the convolution output %dx%d does not pool 2x2", oy, ox);
+  if (im <= 0) return BF_OK;
+  set_last_path(2);
+  return conv_nhwc_igemm(X, Wt_fwd, bias, P, im, iy, ix, ic, nf, fy, fx, 0, 0, 0, false, as_stream(stream), mask, relu_in ? 1 : 0);
 }
 
 int bf_conv_nhwc_backward_data_packed(const float* E, const float* Wt_dx, float* dX, int im, int ic, int iy, int ix, int nf, int fy,

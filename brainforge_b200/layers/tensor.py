@@ -25,7 +25,7 @@ class FusedUnpool:
         self.relu_applied = pool._fused_relu
 
     def materialize(self):
-        dX = self.pool.op.backward(self.delta, self.pool.filter, gate=self.gate)
+        dX = self.pool.op.backward(self.delta, self.pool.filter, gate=self.gate, want_db=True)
         if self.relu_applied:
             dX.relu_applied = True
         return dX
@@ -126,15 +126,15 @@ class ConvLayer(LayerBase):
             x = x.to_nhwc()          # converted once here, reused by the filter gradient
         self.inputs = x
         self._output = None
-        if self.fuse_pool and not self._standalone and route == "c3" and str(self.activation) == "linear":
+        if getattr(self, "_pack", None) is None:
+            self._pack = atomic.FilterPack()
+        if self.fuse_pool and not self._standalone and route in ("c3", "nhwc") and str(self.activation) == "linear":
             pool, relu_in = self._pool_after()
             if pool is not None:
-                fused = self.op.forward_pool(x, self.weights, bias=self.biases, relu_in=relu_in)
+                fused = self.op.forward_pool(x, self.weights, bias=self.biases, relu_in=relu_in, pack=self._pack)
                 if fused is not None:
                     # the convolution output is not materialised; `self.output` re-runs the plain kernel on demand
                     return FusedConvPool(self, fused[0], fused[1], relu_in)
-        if getattr(self, "_pack", None) is None:
-            self._pack = atomic.FilterPack()
         self._output = self.op.forward(x, self.weights, "valid", bias=self.biases, activation=str(self.activation),
                                        pack=self._pack if not self._standalone else None)
         return self._output

@@ -158,6 +158,13 @@ BF_API int bf_conv_nhwc_backward_data(const float* E, const float* F, float* dX,
 BF_API int bf_conv_nhwc_repack(const float* F, float* Wt_fwd, float* Wt_dx, int nf, int ic, int fy, int fx, void* stream);
 BF_API int bf_conv_nhwc_forward_packed(const float* X, const float* Wt_fwd, const float* bias, float* Y, int im, int ic, int iy, int ix,
                                 int nf, int fy, int fx, int act, void* stream);
+/* ConvLayer -> [Activation("relu")] -> PoolLayer(2) in ONE kernel (layers/tensor.py:28-30,75-79; atomic/tensor_op.py:93-107):
+ * P (im, oy/2, ox/2, nf) = maxpool2x2([relu](corr(X, F) + bias)), mask = one byte per pooled element (bit dy*2+dx set
+ * where the window element equals its max: multi-hot on ties, as bf_pool_nhwc_forward writes it).  The full-resolution
+ * convolution output never reaches HBM.  BF_ERR_ARG when the plane has no whole-image tiling (caller runs the two
+ * kernels). */
+BF_API int bf_conv_nhwc_forward_pool_packed(const float* X, const float* Wt_fwd, const float* bias, float* P, uint8_t* mask, int im,
+                                     int ic, int iy, int ix, int nf, int fy, int fx, int relu_in, void* stream);
 BF_API int bf_conv_nhwc_backward_data_packed(const float* E, const float* Wt_dx, float* dX, int im, int ic, int iy, int ix, int nf,
                                       int fy, int fx, void* stream);
 BF_API int bf_conv_nhwc_backward_filter(const float* X, const float* E, float* dF, float* db, int im, int ic, int iy,

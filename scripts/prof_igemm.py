@@ -20,6 +20,10 @@ for (ic, iy, nf) in ((32, 14, 64), (64, 6, 128)):
         print("== forward %d->%d" % (ic, nf), flush=True)
         y = op.forward(x, f)
         torch.cuda.synchronize()
+        print("== forward + relu + pool %d->%d" % (ic, nf), flush=True)
+        pk = bf.atomic.FilterPack()
+        fp = op.forward_pool(x, f, bias=None, relu_in=True, pack=pk)
+        torch.cuda.synchronize()
         print("== backward %d->%d" % (ic, nf), flush=True)
         dF, db, dX = op.backward(X=x, E=e, F=f)
         torch.cuda.synchronize()

@@ -139,6 +139,32 @@ def test_conv_pool_fused_epilogue_bit_exact(bf, O, shape, relu_in):
     close(fused[0], ro)
 
 
+@pytest.mark.parametrize("shape", [(5, 32, 14, 14, 64, 3, 3), (301, 32, 14, 14, 64, 3, 3), (7, 64, 6, 6, 128, 3, 3), (1100, 64, 6, 6, 128, 3, 3),
+                                   (3, 32, 10, 18, 32, 3, 3), (2, 64, 8, 8, 64, 3, 3), (4, 32, 5, 7, 128, 2, 2)])
+@pytest.mark.parametrize("relu_in", [False, True])
+def test_conv_pool_fused_epilogue_channels_last_bit_exact(bf, O, shape, relu_in):
+    """bf_conv_nhwc_forward_pool_packed == MaxPoolOp.forward([relu](ConvolutionOp.forward(..)), 2) bit for bit on the
+    channels-last implicit GEMM (the 32->64 and 64->128 layers of cfg3, more stages than CTAs, ragged last stage):
+    same MMA sequence per position, pooling done on the staged accumulators instead of a second pass over HBM."""
+    im, ic, iy, ix, nf, fy, fx = shape
+    rs = np.random.RandomState(sum(shape))
+    A, F, bias = rs.randn(im, ic, iy, ix), rs.randn(nf, ic, fy, fx) * 0.1, rs.randn(nf)
+    A[0, :, :4, :4] = 0.0            # all-zero windows after the ReLU: four-way ties, multi-hot mask
+    op, pool = bf.atomic.ConvolutionOp(), bf.atomic.MaxPoolOp()
+    a, f, b = bf.DeviceArray.from_host(A).to_nhwc(), bf.DeviceArray.from_host(F), bf.DeviceArray.from_host(bias * 0 if relu_in else bias)
+    pack = bf.atomic.FilterPack()
+    fused = op.forward_pool(a, f, bias=b, relu_in=relu_in, pack=pack)
+    assert fused is not None and bf._lib.lib.bf_last_path() == 2
+    y = op.forward(a, f, "valid", bias=b)
+    assert y.nhwc
+    ref_out, ref_mask = pool.forward(y, 2, relu_in=relu_in)
+    assert np.array_equal(fused[0].numpy(np.float32), ref_out.numpy(np.float32))
+    assert np.array_equal(np.asarray(fused[1]), np.asarray(ref_mask))
+    yo = O.conv_forward(A, F, "valid") + (bias * 0 if relu_in else bias)[None, :, None, None]
+    ro, _ = O.maxpool_forward(np.maximum(yo, 0) if relu_in else yo, 2)
+    close(fused[0], ro)
+
+
 @pytest.mark.parametrize("shape", [(3, 3, 30, 30, 32, 3, 3), (5, 1, 28, 28, 32, 3, 3), (2, 3, 18, 42, 64, 3, 3), (130, 3, 30, 30, 32, 3, 3),
                                    (2, 2, 13, 50, 128, 2, 3), (7, 3, 12, 12, 32, 3, 3)])
 @pytest.mark.parametrize("relu", [False, True])
