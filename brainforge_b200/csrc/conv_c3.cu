@@ -25,7 +25,8 @@ namespace bf {
 constexpr int C3_GROUPS = 4;          // epilogue groups of four warps; group g drains accumulator set g (tiles it = g mod 4)
 constexpr int C3_THREADS = 96 + C3_GROUPS * 128;   // warp 0 loads, warps 1-2 MMA (even / odd tiles), then the epilogue groups
 constexpr int C3_STAGE_LD = 36;
-constexpr int C3_STAGING_BYTES = C3_GROUPS * 4 * 32 * C3_STAGE_LD * 4;
+constexpr int C3_STAGE_TILE = 4 * 32 * C3_STAGE_LD;      // floats of one staged tile [128 positions][32 channels + pad]
+constexpr int C3_STAGING_BYTES = C3_GROUPS * 2 * C3_STAGE_TILE * 4;   // two tiles per group: one barrier per drain (see the epilogue)
 
 // 1-D bulk copy global -> shared (16-byte aligned on both sides, size a multiple of 16), completes on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -129,6 +130,10 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc = idesc_tf32(128, NB);
     int it = 0, as = 0, au = 0;
+    // descriptors: everything but the ring slot's offset is tile-invariant (the address field counts 16-byte units, so a
+    // slot or filter-row offset is a plain add on the encoded descriptor)
+    const uint64_t ad0 = desc_k_none(base, 16u, 128u), bd0 = desc_k_none(b_base, 128u, b_sbo);
+    const uint32_t a_slot_u = a_slot >> 4, row_u = (uint32_t)p.ix;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it, as = (as + 1 == p.na ? 0 : as + 1), au += (as == 0)) {
       if ((it & 1) != warp - 1) continue;
       const int acc_set = it & 3, tu = it >> 2;   // each MMA warp / epilogue group pair owns two sets
@@ -136,13 +141,18 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
       mbar_wait(&a_full[as], (uint32_t)(au & 1));
       tc_fence_after();
       if (leader) {
-        const uint32_t a0 = base + as * a_slot;
-        for (int ky = 0; ky < p.fy; ++ky) {
+        const uint64_t a0 = ad0 + (uint64_t)((uint32_t)as * a_slot_u);
+        const uint32_t d = tmem + acc_set * NB;
+        if (p.fy == 3) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t ad = desc_k_none(a0 + (uint32_t)(ky * p.ix) * 16u + j * 32u, 16u, 128u);
-            const uint64_t bd = desc_k_none(b_base + (uint32_t)(ky * 4 + j * 2) * 128u, 128u, b_sbo);
-            umma_tf32(tmem + acc_set * NB, ad, bd, idesc, (ky > 0 || j > 0) ? 1u : 0u);
+          for (int ky = 0; ky < 3; ++ky) {
+            umma_tf32(d, a0 + (uint64_t)(ky * row_u), bd0 + (uint64_t)(ky * 32), idesc, ky > 0 ? 1u : 0u);
+            umma_tf32(d, a0 + (uint64_t)(ky * row_u + 2u), bd0 + (uint64_t)(ky * 32 + 16), idesc, 1u);
+          }
+        } else {
+          for (int ky = 0; ky < p.fy; ++ky) {
+            umma_tf32(d, a0 + (uint64_t)(ky * row_u), bd0 + (uint64_t)(ky * 32), idesc, ky > 0 ? 1u : 0u);
+            umma_tf32(d, a0 + (uint64_t)(ky * row_u + 2u), bd0 + (uint64_t)(ky * 32 + 16), idesc, 1u);
           }
         }
         umma_commit(&a_empty[as]);
@@ -152,9 +162,23 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
   } else if (warp >= 3) {
     // C3_GROUPS epilogue groups of four warps (one warp per TMEM lane quadrant): group g drains accumulator set g,
     // so that the drains of consecutive tiles overlap (one drain is a serial TMEM -> shared -> global chain)
+    // The staged tile is double-buffered: drain k writes buffer k & 1, ONE group barrier separates its writes from its
+    // pooled reads, and a thread that has passed the barrier of drain k + 1 knows every thread finished reading drain k.
     const int quad = warp & 3, grp = (warp - 3) >> 2;
-    float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + (grp * 4 + quad) * 32 * C3_STAGE_LD;
-    int it = 0;
+    float* stg0 = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + grp * 2 * C3_STAGE_TILE + quad * 32 * C3_STAGE_LD;
+    int it = 0, drain = 0;
+    // bias of a 32-channel block in registers (loads from shared memory between the staging stores would be serialised
+    // behind them: the compiler must assume they alias)
+    float4 bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(&sbias[4 * j]);
+    // (image, tile of the image) of this group's next tile, advanced without divisions
+    const int step_b = (4 * (int)gridDim.x) / p.tiles_per_img, step_t = (4 * (int)gridDim.x) - step_b * p.tiles_per_img;
+    int b = 0, t = 0;
+    {
+      const int first = (int)blockIdx.x + grp * (int)gridDim.x;
+      b = first / p.tiles_per_img; t = first - b * p.tiles_per_img;
+    }
     const int m = quad * 32 + lane;
     const int r = m / p.ix, x = m - r * p.ix;
     // POOL: tile-invariant geometry of the (at most two) pooled items this thread produces per tile and channel block:
@@ -174,10 +198,9 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
         pi_ooff[i] = (py * pw + pxx) * p.N + q * 4;
       }
     }
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      if ((it & 3) != grp) continue;
-      const int acc_set = it & 3, tu = it >> 2;
-      const int b = tile / p.tiles_per_img, t = tile - b * p.tiles_per_img;
+    for (int tile = (int)blockIdx.x + grp * (int)gridDim.x; tile < p.ntiles;
+         tile += 4 * (int)gridDim.x, ++it, b += step_b, t += step_t, b += (t >= p.tiles_per_img), t -= (t >= p.tiles_per_img) ? p.tiles_per_img : 0) {
+      const int acc_set = grp, tu = it;
       const int y = t * p.RT + r;
       const bool ok = r < p.RT && x < p.ox && y < p.oy;
       const int orow = (b * p.oy + y) * p.ox + x;
@@ -187,21 +210,24 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
       if (POOL || okmask != 0u) {
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc_set * NB;
 #pragma unroll
-        for (int cb = 0; cb < NB; cb += 32) {
+        for (int cb = 0; cb < NB; cb += 32, ++drain) {
+          float* stg = stg0 + (drain & 1) * C3_STAGE_TILE;
+          if (NB > 32) {
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + cb + c0, v);
+            for (int j = 0; j < 8; ++j) bb[j] = *reinterpret_cast<const float4*>(&sbias[cb + 4 * j]);
+          }
+          {
+            uint32_t v[32];
+            tmem_ld32(taddr + cb, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sbias[cb + c0 + j]);
+            for (int j = 0; j < 32; j += 4) {
               float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                      __uint_as_float(v[j + 3]));
               if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              o.x += bb[j >> 2].x; o.y += bb[j >> 2].y; o.z += bb[j >> 2].z; o.w += bb[j >> 2].w;
               if (POOL && p.pool_relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              *reinterpret_cast<float4*>(stg + lane * C3_STAGE_LD + c0 + j) = o;
+              *reinterpret_cast<float4*>(stg + lane * C3_STAGE_LD + j) = o;
             }
           }
           if (POOL) {
@@ -230,7 +256,6 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
                 *reinterpret_cast<uchar4*>(p.mask + o) = mk;
               }
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // staging is rewritten by the next block / tile
           } else {
             __syncwarp();
 #pragma unroll

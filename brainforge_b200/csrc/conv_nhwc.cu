@@ -420,6 +420,8 @@ struct DfParams {
   int nstages, nbands, G, IR, PW, RO, Krows, x_rows, ntaps, fx, nimg, nsplit, e_rows_box;
   int ns;   // ring depth (stages in flight)
   int with_db;   // accumulate db through an all-ones operand (0: the caller has it from the kernel that produced E)
+  int kimg;      // > 0: K steps per image, E holds only the oy output rows of every image (no zero rows between images)
+                 // and the K loop restarts at every image of the stage (X rows of image g begin at g * IR); 0: one run of Krows
 };
 
 template <int MH>
@@ -465,12 +467,13 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
 
   if (warp == 0) {
     const bool leader = elect_one_sync();
-    int it = 0;
     const uint32_t e_box_bytes = (uint32_t)(p.G * p.e_rows_box * p.PW) * 128u;
     const uint32_t x_box_bytes = (uint32_t)(p.G * p.IR) * 128u;
-    for (int st = split; st < p.nstages; st += p.nsplit, ++it) {
-      const int s = it % p.ns, u = it / p.ns;
-      const int grp = st / p.nbands, band = st - grp * p.nbands;
+    // ring slot / use count and (image group, band) of the stage as running counters: no divisions in the loop
+    int s = 0, u = 0;
+    int grp = split / p.nbands, band = split - grp * p.nbands;
+    const int dgrp = p.nsplit / p.nbands, dband = p.nsplit - dgrp * p.nbands;
+    for (int st = split; st < p.nstages; st += p.nsplit) {
       if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
       if (leader) {
         mbar_expect_tx(&full[s], MH * e_box_bytes + x_box_bytes);
@@ -479,6 +482,9 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
           tma_load_4d(base + s * e_slot + h * e_half, &mapE, &full[s], h * 32, 0, band * p.RO, grp * p.G);
         tma_load_4d(x_base + s * x_slot, &mapX, &full[s], ch * 32, 0, band * p.RO, grp * p.G);
       }
+      if (++s == p.ns) { s = 0; ++u; }
+      grp += dgrp; band += dband;
+      if (band >= p.nbands) { band -= p.nbands; ++grp; }
     }
   } else if (warp == 1) {
     const bool leader = elect_one_sync();
@@ -490,24 +496,44 @@ conv_df_kernel(const __grid_constant__ CUtensorMap mapE, const __grid_constant__
     constexpr uint32_t idesc_one = idesc_tf32(DF_M, 32, true, true);
     const uint64_t ones_desc = desc_mn_sw128_32b(ones_base, 4096u, 512u);
     const uint32_t row_step = (uint32_t)(p.PW * 128) >> 4;   // descriptor units (16 B) per filter row
-    int it = 0;
-    const int ksteps = p.Krows / 8;
-    for (int st = split; st < p.nstages; st += p.nsplit, ++it) {
-      const int s = it % p.ns, u = it / p.ns;
+    // K runs: one of Krows / 8 steps, or (kimg > 0) one of kimg steps per image with the X operand restarting at the image
+    const int nrun = p.kimg > 0 ? p.G : 1, ksteps = p.kimg > 0 ? p.kimg : p.Krows / 8;
+    const uint32_t x_run = (uint32_t)(p.IR * 128) >> 4;      // descriptor units between the X rows of consecutive images
+    const bool with_db = ch == 0 && p.with_db;
+    const uint64_t ad0 = desc_mn_sw128_32b(base, e_half, 512u), bd0 = desc_mn_sw128_32b(x_base, 128u, 512u);
+    const uint32_t e_slot_u = e_slot >> 4, x_slot_u = x_slot >> 4;
+    const uint32_t acc_step = (uint32_t)(p.fx * 32);
+    int s = 0, u = 0;
+    uint32_t acc_flag = 0u;
+    for (int st = split; st < p.nstages; st += p.nsplit) {
       mbar_wait(&full[s], (uint32_t)(u & 1));
       tc_fence_after();
-      uint64_t ad = desc_mn_sw128_32b(base + s * e_slot, e_half, 512u);
-      uint64_t bd = desc_mn_sw128_32b(x_base + s * x_slot, 128u, 512u);
-      for (int ks = 0; ks < ksteps; ++ks, ad += 64, bd += 64) {   // 8 pixel rows = 1024 B per K step
-        const uint32_t acc_flag = (it > 0 || ks > 0) ? 1u : 0u;
-        uint64_t bdr = bd;
-        if (leader) {
-          for (int ty = 0; ty < fy; ++ty, bdr += row_step)
-            umma_tf32(tmem + ty * p.fx * 32, ad, bdr, idesc_row, acc_flag);
-          if (ch == 0 && p.with_db) umma_tf32(tmem + p.ntaps * 32, ad, ones_desc, idesc_one, acc_flag);
+      if (leader) {
+        uint64_t ad = ad0 + (uint64_t)((uint32_t)s * e_slot_u);
+        const uint64_t bds = bd0 + (uint64_t)((uint32_t)s * x_slot_u);
+        for (int g = 0; g < nrun; ++g) {
+          uint64_t bd = bds + (uint64_t)((uint32_t)g * x_run);
+          if (fy == 3 && !with_db) {
+#pragma unroll 2
+            for (int ks = 0; ks < ksteps; ++ks, ad += 64, bd += 64) {   // 8 pixel rows = 1024 B per K step
+              umma_tf32(tmem, ad, bd, idesc_row, acc_flag);
+              umma_tf32(tmem + acc_step, ad, bd + (uint64_t)row_step, idesc_row, acc_flag);
+              umma_tf32(tmem + 2 * acc_step, ad, bd + (uint64_t)(2 * row_step), idesc_row, acc_flag);
+              acc_flag = 1u;
+            }
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks, ad += 64, bd += 64) {
+              uint64_t bdr = bd;
+              for (int ty = 0; ty < fy; ++ty, bdr += row_step)
+                umma_tf32(tmem + ty * acc_step, ad, bdr, idesc_row, acc_flag);
+              if (with_db) umma_tf32(tmem + p.ntaps * 32, ad, ones_desc, idesc_one, acc_flag);
+              acc_flag = 1u;
+            }
+          }
         }
+        umma_commit(&empty[s]);
       }
-      if (leader) umma_commit(&empty[s]);
+      if (++s == p.ns) { s = 0; ++u; }
     }
     if (leader) umma_commit(&done);
   } else if (warp >= 2) {
@@ -913,10 +939,11 @@ static int conv_nhwc_backward_filter_impl(const float* X, const float* E, float*
   // candidates: G whole images per stage (E loaded with iy rows so that both operands share the row index) or
   // bands of RO filter-gradient rows of one image; score = useful pixels per estimated stage time, where a
   // ring of fewer than 4 stages leaves the load latency exposed
-  auto consider = [&](int G, int nbands, int RO, int e_rows, int xr) {
+  auto consider = [&](int G, int nbands, int RO, int e_rows, int xr, bool per_image = false) {
     const int IRx = xr * ix;
-    const int Krows = (G * (nbands == 1 ? IRx : RO * ix) + 7) / 8 * 8;
-    int x_rows = Krows + max_shift;
+    // per_image: E carries only the oy * ix rows of every image (a multiple of 8), the K loop restarts per image
+    const int Krows = per_image ? G * oy * ix : (G * (nbands == 1 ? IRx : RO * ix) + 7) / 8 * 8;
+    int x_rows = per_image ? (G - 1) * IRx + oy * ix + max_shift : Krows + max_shift;
     if (x_rows < G * IRx) x_rows = G * IRx;
     x_rows = (x_rows + 7) / 8 * 8;
     int ns = 8;
@@ -933,7 +960,7 @@ static int conv_nhwc_backward_filter_impl(const float* X, const float* E, float*
     if (score > best) {
       best = score;
       p = DfParams{nbands == 1 ? (im + G - 1) / G : im * nbands, nbands, G, IRx, ix, RO, Krows, x_rows, ntaps, fx, im, 1, e_rows, ns,
-                   db_partial ? 0 : 1};
+                   db_partial ? 0 : 1, per_image ? oy * ix / 8 : 0};
       smem = df_smem_bytes(MH, Krows, x_rows, ns);
       ok = true;
     }
@@ -942,14 +969,17 @@ static int conv_nhwc_backward_filter_impl(const float* X, const float* E, float*
   if (iy <= 256)
     for (int G = 1; G <= 256 && G <= im + 8; ++G)
       if (!consider(G, 1, oy, iy, iy)) break;
+  if (iy <= 256 && (oy * ix) % 8 == 0 && oy < iy)
+    for (int G = 1; G <= 256 && G <= im + 8; ++G)
+      if (!consider(G, 1, oy, oy, iy, true)) break;
   for (int RO = (oy < 254 ? oy - 1 : 254); RO >= 1; --RO) {
     if (RO + fy - 1 > 256) continue;
     consider(1, (oy + RO - 1) / RO, RO, RO, RO + fy - 1);
   }
   BF_REQUIRE(ok, BF_ERR_ARG, "bf_conv_nhwc_backward_filter: no tiling for plane %dx%d", iy, ix);
   if (getenv("BF_DEBUG_PLAN"))
-    fprintf(stderr, "[df %dx%dx%d->%d] G=%d bands=%d RO=%d Krows=%d x_rows=%d ns=%d smem=%zu stages=%d\n", iy, ix, ic, nf, p.G,
-            p.nbands, p.RO, p.Krows, p.x_rows, p.ns, smem, p.nstages);
+    fprintf(stderr, "[df %dx%dx%d->%d] G=%d bands=%d RO=%d Krows=%d x_rows=%d ns=%d kimg=%d smem=%zu stages=%d\n", iy, ix, ic, nf, p.G,
+            p.nbands, p.RO, p.Krows, p.x_rows, p.ns, p.kimg, smem, p.nstages);
   int nsplit = num_sms() / nch;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > p.nstages) nsplit = p.nstages;
