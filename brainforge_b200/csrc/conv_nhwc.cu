@@ -239,6 +239,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int quad = warp & 3, eg = (warp - 3) >> 2;
     float* stg = reinterpret_cast<float*>(dyn_smem) + (stage_base - smem_u32(dyn_smem)) / 4 + (eg * 4 + quad) * 32 * IG_STAGE_LD;
     int it = 0;
+    int pool_g[2] = {0, 0}, pool_py[2] = {0, 0}, pool_px[2] = {0, 0};
+    if (POOL) {
+      const int PX = p.out_x >> 1, wins = (p.out_y >> 1) * PX;
+#pragma unroll
+      for (int wi = 0; wi < 2; ++wi) {
+        const int win = ((warp - 3) * 32 + lane + wi * 256) >> 2;
+        pool_g[wi] = win / wins;
+        const int rem = win - pool_g[wi] * wins;
+        pool_py[wi] = rem / PX; pool_px[wi] = rem - pool_py[wi] * PX;
+      }
+    }
     IG_T(te);
     for (int st = blockIdx.x; st < p.nstages; st += gridDim.x, ++it) {
       const int as = it & 1, au = it >> 1;
@@ -251,6 +262,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int PY = p.out_y >> 1, PX = p.out_x >> 1, wins = PY * PX, nitems = p.G * wins * 4;
 #pragma unroll 1
         for (int cc = 0; cc < NB; cc += 16) {
+          // bias of the pass in registers BEFORE the staging stores (a load between them would have to wait for them: the
+          // compiler must assume the two shared arrays alias)
+          float4 bb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = *reinterpret_cast<const float4*>(&sbias[cc + 4 * j]);
           for (int t = eg; t < p.T; t += 2) {
             uint32_t v[16];
             tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + as * IG_ACCSET_COLS + t * NB + cc, v);
@@ -258,18 +274,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             float* d = pt + (size_t)(t * 128 + quad * 32 + lane) * IG_POOL_LD;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sbias[cc + j]);
-              float4 r = make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
-                                     __uint_as_float(v[j + 3]) + bb.w);
+              float4 r = make_float4(__uint_as_float(v[j]) + bb[j >> 2].x, __uint_as_float(v[j + 1]) + bb[j >> 2].y,
+                                     __uint_as_float(v[j + 2]) + bb[j >> 2].z, __uint_as_float(v[j + 3]) + bb[j >> 2].w);
               if (p.pool_relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
               *reinterpret_cast<float4*>(d + j) = r;
             }
           }
           asm volatile("bar.sync 3, 256;" ::: "memory");
-          for (int w = et; w < nitems; w += 256) {
-            const int win = w >> 2, c4 = w & 3;
-            const int g = win / wins, rem = win - g * wins;
-            const int py = rem / PX, px = rem - py * PX;
+          for (int w = et, wi = 0; w < nitems; w += 256, ++wi) {
+            // the geometry of a thread's first two items does not change from stage to stage (pool_geo, set up once)
+            int g, py, px;
+            const int c4 = w & 3;
+            if (wi < 2) { g = pool_g[wi]; py = pool_py[wi]; px = pool_px[wi]; }
+            else {
+              const int win = w >> 2;
+              g = win / wins;
+              const int rem = win - g * wins;
+              py = rem / PX; px = rem - py * PX;
+            }
             const int img = grp * p.G + g;
             if (img < p.nimg) {
               const float* s00 = pt + (size_t)(g * p.IR + (2 * py) * p.PW + 2 * px) * IG_POOL_LD + c4 * 4;
@@ -381,10 +403,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           for (int c0 = 0; c0 < 32; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + cb + c0, v);
+            float4 bb4[4];            // before the staging stores: a shared-memory load between them would wait for them
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb4[j] = *reinterpret_cast<const float4*>(&sbias[cb + c0 + 4 * j]);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(&sbias[cb + c0 + j]);
+              const float4 bb = bb4[j >> 2];
               float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                      __uint_as_float(v[j + 3]));
               if (RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }

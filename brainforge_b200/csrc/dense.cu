@@ -377,9 +377,24 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
   int rows = m - m0;
   if (rows > R) rows = R;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ---- stage W (permuted rows) and the chunk's X rows
+  // ---- stage W (permuted rows) and the chunk's X rows.  The rows of a chunk are one contiguous run of X: ONE bulk copy
+  // (cp.async.bulk, completes on an mbarrier) fetches them while the threads re-lay W; a per-thread load loop here was
+  // a chain of ~30 dependent HBM round trips (a third of the kernel).
+  __shared__ __align__(8) uint64_t xbar;
+  const float* xsrc = X + (size_t)m0 * k;
+  const uint32_t xbytes = (uint32_t)rows * (uint32_t)k * 4u;
+  const bool bulk = (xbytes & 15u) == 0 && (((uintptr_t)xsrc) & 15) == 0 && ((k * PITCH) & 3) == 0 && xbytes < (1u << 20);
+  if (threadIdx.x == 0) {
+    mbar_init(&xbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int i = threadIdx.x; i < k * PITCH; i += blockDim.x) sW[i] = 0.f;
   __syncthreads();
+  if (bulk && threadIdx.x == 0) {
+    mbar_expect_tx(&xbar, xbytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sX)), "l"(reinterpret_cast<uint64_t>(xsrc)), "r"(xbytes), "r"(smem_u32(&xbar)) : "memory");
+  }
   const int total = k * n;
   for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
     float v[8];
@@ -395,14 +410,10 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
       }
     }
   }
-  if ((k & 3) == 0 && (((uintptr_t)X) & 15) == 0) {
-    const int k4 = k >> 2;
-    for (int i = threadIdx.x; i < rows * k4; i += blockDim.x) {
-      const int r = i / k4, c = i - r * k4;
-      reinterpret_cast<float4*>(sX)[(size_t)r * k4 + c] = __ldcs(reinterpret_cast<const float4*>(X + (size_t)(m0 + r) * k) + c);
-    }
+  if (bulk) {
+    mbar_wait(&xbar, 0u);
   } else {
-    for (int i = threadIdx.x; i < rows * k; i += blockDim.x) sX[i] = __ldg(X + (size_t)m0 * k + i);
+    for (int i = threadIdx.x; i < rows * k; i += blockDim.x) sX[i] = __ldg(xsrc + i);
   }
   __syncthreads();
   // ---- forward + cost + delta: one warp per row, lanes split K
