@@ -356,8 +356,9 @@ static int launch_skinny_bwd(const float* X, const float* E, const float* W, flo
 __device__ unsigned int g_head_ticket = 0;
 __device__ unsigned int g_head_hits = 0;
 
+constexpr int HEAD_THREADS = 512;     // 16 warps: the kernel is a chain of latencies (staging, warp reductions), more warps hide them
 template <int NT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(HEAD_THREADS)
 dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
                   const float* __restrict__ Y, const float* __restrict__ sw_rows, float* __restrict__ out,
                   float* __restrict__ partial, float* __restrict__ dX, double* __restrict__ cost_partial,
@@ -368,8 +369,8 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
   float* sW = hs;                                   // [k][PITCH], rows in X's PHYSICAL column order
   float* sX = sW + (size_t)k * PITCH;               // [R][k]
   float* sD = sX + (size_t)R * k;                   // [R][NT]  delta
-  __shared__ double s_cost[8];
-  __shared__ unsigned s_hits[8];
+  __shared__ double s_cost[HEAD_THREADS / 32];
+  __shared__ unsigned s_hits[HEAD_THREADS / 32];
   __shared__ bool s_last;
   pdl_launch_dependents();
   pdl_wait();
@@ -419,7 +420,7 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
   // ---- forward + cost + delta: one warp per row, lanes split K
   double cost_acc = 0.0;
   unsigned hits = 0;
-  for (int r = warp; r < rows; r += 8) {
+  for (int r = warp; r < rows; r += HEAD_THREADS / 32) {
     float acc[NT];
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[j] = 0.f;
@@ -517,7 +518,7 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
   if (threadIdx.x == 0) {
     double c = 0.0;
     unsigned h = 0;
-    for (int w8 = 0; w8 < 8; ++w8) { c += s_cost[w8]; h += s_hits[w8]; }
+    for (int w8 = 0; w8 < HEAD_THREADS / 32; ++w8) { c += s_cost[w8]; h += s_hits[w8]; }
     cost_partial[blockIdx.x] = c;
     if (hits_out && h) atomicAdd(&g_head_hits, h);
     __threadfence();
@@ -613,7 +614,7 @@ int bf_dense_head(const float* X, const float* W, const float* b, const float* Y
     BF_CUDA(cudaFuncSetAttribute(dense_head_kernel<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     /* several CTAs per SM: without the carve-out hint the driver sizes shared memory for ONE 75 KB CTA (measured: two waves) */ \
     BF_CUDA(cudaFuncSetAttribute(dense_head_kernel<NT_>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
-    launch_pdl(dense_head_kernel<NT_>, dim3(chunks), dim3(256), smem, s, X, W, b, Y, sample_w, out, partial, dX, cpart,    \
+    launch_pdl(dense_head_kernel<NT_>, dim3(chunks), dim3(HEAD_THREADS), smem, s, X, W, b, Y, sample_w, out, partial, dX, cpart,    \
                cost_result, hits_result, m, k, n, R, act, cost, pc, phw);                                                  \
   }
   BF_HEAD(4) BF_HEAD(8) BF_HEAD(16) BF_HEAD(32)
