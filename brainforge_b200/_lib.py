@@ -47,6 +47,8 @@ SIGNATURES = {
     "bf_dense_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "bf_dense_tma_supported": (_i, [_i] * 4),
     "bf_dense_head_supported": (_i, [_i] * 4),
+    "bf_mlp2_step_supported": (_i, [_i] * 7),
+    "bf_mlp2_step": (_i, [_vp] * 15 + [_i] * 7 + [_vp]),
     "bf_dense_head": (_i, [_vp] * 11 + [_i] * 8 + [_vp]),
     "bf_dense_forward_cl": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "bf_dense_backward_cl": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

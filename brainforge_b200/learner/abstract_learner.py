@@ -79,11 +79,17 @@ class StepPipeline:
         self.overlapped = hasattr(learner, "learn_batch_async") and "w" not in learn_kw
         self.batch_size = 0
 
+    SMALL_BATCH_BYTES = 1 << 20     # below this a batch goes straight into the step's input buffers (see _stage)
+
     def _stage(self, batch):
         from ..device import DeviceArray
         x, y = batch[0], batch[1]
         if isinstance(x, DeviceArray) and isinstance(y, DeviceArray):
             return x, y                                   # already in HBM (ResidentDataset): nothing to copy
+        if getattr(x, "nbytes", 1 << 62) + getattr(y, "nbytes", 1 << 62) <= self.SMALL_BATCH_BYTES:
+            # a few KB: the copy takes microseconds, while a side-stream upload (two allocations, an event, two more
+            # device copies into the graph's input buffers) costs more host time than the whole device step
+            return x, y
         return self.learner.stage_batch(x, y), None
 
     def run(self, generator, steps):

@@ -108,7 +108,9 @@ class Backpropagation(Learner):
         """Device-only part of learn_batch (capturable in a CUDA graph: no host sync inside)."""
         sc = self.layers.scalars()
         last = self.layers.layers[-1]
-        if self.fused_head and len(self.layers.layers) > 1 and getattr(last, "head_supported", None) and last.head_supported(self.cost):
+        if self.fused_head and self._mlp2_step(x, y, wd, metrics, sc):
+            pass             # Dense -> Dense at small batch: forward, cost, both backward passes in one cluster kernel
+        elif self.fused_head and len(self.layers.layers) > 1 and getattr(last, "head_supported", None) and last.head_supported(self.cost):
             # output head in one kernel: last Dense forward, cost value (of the PRE-update forward pass, :26), accuracy,
             # cost derivative and the layer's backward pass (bf_dense_head) -- five launches and a second read of its input less
             below = self.layers._fwd(x, stop=len(self.layers.layers) - 1)
@@ -135,6 +137,31 @@ class Backpropagation(Learner):
             _dist.allreduce_sum(self.layers.flat_grads if update else sc)
         if update:
             self.update(m_global)
+
+    def _mlp2_step(self, x, y, wd, metrics, sc):
+        """InputLayer -> Dense -> Dense (BASELINE configs[0]) at batch <= 32: the device step up to the optimizer is ONE
+        launch (bf_mlp2_step).  Sets the layers' inputs / outputs and accumulates their gradients exactly like
+        _fwd -> cost -> _bwd; returns False when the stack or the shapes do not qualify."""
+        L = self.layers.layers
+        if len(L) != 3 or x.nhwc or len(x.shape) != 2 or getattr(x, "cl_flat", None) is not None:
+            return False
+        l1, l2 = L[1], L[2]
+        if type(l1).__name__ != "Dense" or type(l2).__name__ != "Dense" or not (l1.trainable and l2.trainable):
+            return False
+        if self.cost.kind not in ("mse", "cxent", "bxent"):
+            return False
+        m, k = x.shape
+        h, n = l1.neurons, l2.neurons
+        a1, a2, ck = _lib.ACT[str(l1.activation)], _lib.ACT[str(l2.activation)], _lib.COST[self.cost.kind]
+        if not _lib.lib.bf_mlp2_step_supported(m, k, h, n, a1, a2, ck):
+            return False
+        H, out = DeviceArray.empty(m, h), DeviceArray.empty(m, n)
+        call(_lib.lib.bf_mlp2_step, x.ptr, l1.weights.ptr, l1.biases.ptr, l2.weights.ptr, l2.biases.ptr, y.ptr,
+             wd.ptr if wd is not None else None, H.ptr, out.ptr, l1.nabla_w.ptr, l1.nabla_b.ptr, l2.nabla_w.ptr, l2.nabla_b.ptr,
+             sc[0:1].ptr, sc[1:2].ptr if metrics else None, m, k, h, n, a1, a2, ck, stream_ptr())
+        L[0]._fwd(x)
+        l1.inputs, l1.output, l2.inputs, l2.output = x, H, H, out
+        return True
 
     def _read_scalars(self, metrics, m_local):
         return self._scalars_to_dict(self.layers.scalars().numpy(), metrics, m_local)

@@ -124,6 +124,17 @@ BF_API int bf_dense_backward_cl(const float* X, const float* E, const float* W, 
  * reference's (c, yx) order (as bf_dense_forward_cl); otherwise chan*hw is simply k.  sample_w, hits_result, dX may be
  * NULL.  BF_COST_HINGE is not supported (its derivative is not out - Y). */
 BF_API int bf_dense_head_supported(int k, int n, int act, int cost);
+/* Whole learn_batch device step (minus the optimizer) of a two-layer perceptron at small batch in ONE kernel -- BASELINE
+ * configs[0], 784-60-10 at batch 20 (layers/core.py:27-39 twice, metrics/costs.py:19-37, metrics/metrics.py:15-16,
+ * learner/backpropagation.py:16-30): H = act1(X W1 + b1) (m,h); out = act2(H W2 + b2) (m,n); cost_result[0], hits_result[0]
+ * as bf_dense_head; gW2 += H^T delta2, gb2 += delta2.sum(0), gW1 += X^T dH, gb1 += dH.sum(0) with
+ * dH = (delta2 W2^T) * act1'(H).  A cluster of 8 CTAs splits the first layer's contraction index and exchanges the partial
+ * sums through distributed shared memory; FP32 FMA in a fixed order (deterministic).  Limits: m <= 32, h <= 64, n <= 16,
+ * k <= 1024; act1 in linear/sigmoid/tanh/relu; cost mse/cxent/bxent.  sample_w, hits_result may be NULL. */
+BF_API int bf_mlp2_step_supported(int m, int k, int h, int n, int act1, int act2, int cost);
+BF_API int bf_mlp2_step(const float* X, const float* W1, const float* b1, const float* W2, const float* b2, const float* Y,
+                 const float* sample_w, float* H, float* out, float* gW1, float* gb1, float* gW2, float* gb2, float* cost_result,
+                 float* hits_result, int m, int k, int h, int n, int act1, int act2, int cost, void* stream);
 BF_API int bf_dense_head(const float* X, const float* W, const float* b, const float* Y, const float* sample_w, float* out,
                   float* dW, float* db, float* dX, float* cost_result, float* hits_result, int m, int chan, int hw, int n,
                   int act, int cost, int channels_last, int accumulate, void* stream);

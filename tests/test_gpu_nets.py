@@ -324,10 +324,13 @@ def test_fused_output_head_matches_unfused_and_oracle(case):
                 l2 = bf.device.launch_count()
                 assert l1 - l0 <= (l2 - l1) - 3, (l1 - l0, l2 - l1)           # the point of the fusion
                 assert a["accuracy"] == b["accuracy"]
-                assert relerr(a["cost"], b["cost"]) < 1e-6
-                assert relerr(np.asarray(fused.layers.layers[-1].output), np.asarray(plain.layers.layers[-1].output)) < 1e-6
+                # cfg1 takes the whole-step cluster kernel (bf_mlp2_step: FP32 FMA under either setting) while the layer-by-layer
+                # route runs its first layer on the TF32 tensor cores: under "tf32" the two differ by the TF32 rounding
+                loose = case == "cfg1" and prec == "tf32"
+                assert relerr(a["cost"], b["cost"]) < (2e-3 if loose else 1e-6)
+                assert relerr(np.asarray(fused.layers.layers[-1].output), np.asarray(plain.layers.layers[-1].output)) < (2e-3 if loose else 1e-6)
                 # (TF32: a last-bit difference in the head's dX can flip the TF32 rounding of an operand further down)
-                gtol = 2e-6 if prec == "fp32" else 2e-4
+                gtol = 2e-6 if prec == "fp32" else (5e-3 if loose else 2e-4)
                 assert relerr(fused.get_gradients(), plain.get_gradients()) < gtol, relerr(fused.get_gradients(), plain.get_gradients())
                 if prec == "fp32":
                     c = ora.learn_batch(X, Y, w=weights, update=False, metrics=["acc"])
@@ -337,7 +340,52 @@ def test_fused_output_head_matches_unfused_and_oracle(case):
                 fused.zero_gradients(); plain.zero_gradients()
             for _ in range(3):
                 a, b = fused.learn_batch(X, Y), plain.learn_batch(X, Y)
-                assert relerr(a["cost"], b["cost"]) < (1e-5 if prec == "fp32" else 1e-3)
+                assert relerr(a["cost"], b["cost"]) < (1e-5 if prec == "fp32" else 2e-3)
             assert relerr(fused.layers.get_weights(), plain.layers.get_weights()) < (1e-5 if prec == "fp32" else 1e-3)
+        finally:
+            bf.set_precision("fp32")
+
+
+@pytest.mark.parametrize("m,k,h,n,act1,act2,cost,opt", [
+    (20, 784, 60, 10, "sigmoid", "softmax", "cxent", "sgd"),        # BASELINE configs[0]
+    (1, 784, 60, 10, "sigmoid", "softmax", "cxent", "adam"),
+    (32, 1024, 64, 16, "tanh", "softmax", "cxent", "momentum"),     # every limit of the kernel at once
+    (7, 37, 5, 3, "relu", "linear", "mse", "sgd"),                  # ragged: the last CTAs of the cluster own no rows
+    (13, 100, 33, 4, "linear", "sigmoid", "bxent", "sgd"),
+    (20, 3, 2, 1, "tanh", "tanh", "mse", "sgd")])
+def test_mlp2_whole_step_kernel(m, k, h, n, act1, act2, cost, opt):
+    """bf_mlp2_step (Dense -> Dense at batch <= 32: forward, cost, accuracy, both backward passes in ONE cluster kernel)
+    against the float64 oracle at the FP32 bound under BOTH precision settings (the kernel is FP32 FMA either way): cost,
+    accuracy, every layer output, every gradient, gradient accumulation over two calls, per-sample weights, a 3-step
+    trajectory; two launches per training step (this kernel + the fused optimizer)."""
+    import brainforge_b200 as bf
+    spec = [("dense", h, act1), ("dense", n, act2)]
+    rs = np.random.RandomState(m + k + h + n)
+    X = rs.randn(m, k)
+    Y = onehot(rs, m, n) if n > 1 else rs.rand(m, 1)
+    w = rs.rand(m) + 0.5
+    for prec in ("fp32", "tf32"):
+        bf.set_precision(prec)
+        try:
+            net = build_b200((k,), spec, cost, opt, seed=11)
+            ora = build_oracle((k,), spec, cost, opt, seed=11)
+            assert bf._lib.lib.bf_mlp2_step_supported(m, k, h, n, bf._lib.ACT[act1], bf._lib.ACT[act2], bf._lib.COST[cost])
+            for weights in (None, w):
+                l0 = bf.device.launch_count()
+                a = net.learn_batch(X, Y, w=weights, metrics=["acc"], update=False)
+                assert bf.device.launch_count() - l0 <= 5          # the kernel (+ the casts of the float64 host arrays)
+                b = ora.learn_batch(X, Y, w=weights, metrics=["acc"], update=False)
+                assert relerr(a["cost"], b["cost"]) < 1e-5 and a["accuracy"] == b["accuracy"], (a, b)
+                for i in (1, 2):
+                    assert relerr(np.asarray(net.layers.layers[i].output), ora.L[i - 1]["output"]) < 1e-5
+                assert relerr(net.get_gradients(), ora.get_gradients()) < 1e-5
+                a2 = net.learn_batch(X, Y, w=weights, update=False)      # Dense ACCUMULATES (core.py:37-38)
+                ora.learn_batch(X, Y, w=weights, update=False)
+                assert relerr(net.get_gradients(), ora.get_gradients()) < 1e-5 and relerr(a2["cost"], b["cost"]) < 1e-5
+                net.zero_gradients(); ora.zero_gradients()
+            for _ in range(3):
+                a, b = net.learn_batch(X, Y), ora.learn_batch(X, Y)
+                assert relerr(a["cost"], b["cost"]) < 1e-5
+            assert relerr(net.layers.get_weights(), ora.get_weights()) < 3e-5
         finally:
             bf.set_precision("fp32")
