@@ -18,7 +18,8 @@ namespace cg = cooperative_groups;
 namespace bf {
 
 constexpr int M2_CLUSTER = 8;
-constexpr int M2_THREADS = 256;
+constexpr int M2_THREADS = 512;          // 16 warps: every phase is a chain of shared-memory latencies
+constexpr int M2_GROUPS = M2_THREADS / 64;   // row / K groups next to the 64 columns of the hidden layer
 constexpr int M2_MAX_M = 32, M2_MAX_H = 64, M2_MAX_N = 16, M2_MAX_KS = 128;
 
 struct Mlp2Params {
@@ -59,24 +60,25 @@ __global__ void __launch_bounds__(M2_THREADS, 1) mlp2_step_kernel(Mlp2Params p) 
   for (int i = tid; i < h * n; i += M2_THREADS) W2s[i] = __ldg(p.W2 + i);
   __syncthreads();
 
-  // ---- 1. partial first-layer pre-activations: thread = (column j, row group), 64 columns x 4 row groups
+  // ---- 1. partial first-layer pre-activations: thread = (column j, row group), 64 columns x M2_GROUPS row groups
   {
+    constexpr int NR = M2_MAX_M / M2_GROUPS;
     const int j = tid & 63, rg = tid >> 6;
-    float acc[M2_MAX_M / 4];
+    float acc[NR];
 #pragma unroll
-    for (int i = 0; i < M2_MAX_M / 4; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
     if (j < h) {
       for (int kk = 0; kk < kn; ++kk) {
         const float w = W1s[kk * h + j];
 #pragma unroll
-        for (int i = 0; i < M2_MAX_M / 4; ++i) {
-          const int r = rg + 4 * i;
+        for (int i = 0; i < NR; ++i) {
+          const int r = rg + M2_GROUPS * i;
           if (r < m) acc[i] = fmaf(Xs[r * xp + kk], w, acc[i]);
         }
       }
 #pragma unroll
-      for (int i = 0; i < M2_MAX_M / 4; ++i) {
-        const int r = rg + 4 * i;
+      for (int i = 0; i < NR; ++i) {
+        const int r = rg + M2_GROUPS * i;
         if (r < m) Hp[r * h + j] = acc[i];
       }
     }
@@ -172,25 +174,29 @@ __global__ void __launch_bounds__(M2_THREADS, 1) mlp2_step_kernel(Mlp2Params p) 
     for (int r = 0; r < m; ++r) s += dH[r * h + tid];
     p.gb1[tid] += s;
   }
-  // ---- 4. this CTA's rows of dW1 = X[:, slice]^T dH
+  // ---- 4. this CTA's rows of dW1 = X[:, slice]^T dH: thread = (column j, K group), eight rows of W1 at a time so that one
+  // read of dH serves eight independent sums; the accumulating read-modify-write asks for its eight old values together
   {
     const int j = tid & 63, kg = tid >> 6;
     if (j < h) {
-      // the accumulating read-modify-write in two passes: all the old values are requested first (one round trip to L2
-      // for the lot; a load per loop iteration behind the previous store was 25 dependent round trips)
-      float old[M2_MAX_KS / 4];
+      for (int base = kg; base < kn; base += M2_GROUPS * 8) {
+        float old[8], sum[8];
 #pragma unroll
-      for (int i = 0; i < M2_MAX_KS / 4; ++i) {
-        const int kk = kg + 4 * i;
-        old[i] = kk < kn ? p.gW1[(size_t)(k0 + kk) * h + j] : 0.f;
-      }
+        for (int i = 0; i < 8; ++i) {
+          const int kk = base + M2_GROUPS * i;
+          old[i] = kk < kn ? p.gW1[(size_t)(k0 + kk) * h + j] : 0.f;
+          sum[i] = 0.f;
+        }
+        for (int r = 0; r < m; ++r) {
+          const float d = dH[r * h + j];
+          const float* xr = Xs + r * xp + base;          // (columns >= kn read zeros or the next array: never stored)
 #pragma unroll
-      for (int i = 0; i < M2_MAX_KS / 4; ++i) {
-        const int kk = kg + 4 * i;
-        if (kk < kn) {
-          float s = 0.f;
-          for (int r = 0; r < m; ++r) s = fmaf(Xs[r * xp + kk], dH[r * h + j], s);
-          p.gW1[(size_t)(k0 + kk) * h + j] = old[i] + s;
+          for (int i = 0; i < 8; ++i) sum[i] = fmaf(xr[M2_GROUPS * i], d, sum[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kk = base + M2_GROUPS * i;
+          if (kk < kn) p.gW1[(size_t)(k0 + kk) * h + j] = old[i] + sum[i];
         }
       }
     }
