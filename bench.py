@@ -357,17 +357,10 @@ def algorithmic_cost(label):
     return 0, 0.0
 
 
-KERNEL_OF_CALL = {   # C-ABI call -> its dominant kernel, for the kernels that have ONE instance per step (an ncu capture of
-    # the other families is one of several layer shapes and would not match the launch the roofline entry describes)
-    "bf_conv_c3_forward_pool": "conv_c3_fwd_kernel", "bf_conv_c3_forward": "conv_c3_fwd_kernel",
-    "bf_conv_c3_backward_filter": "conv_c3_df_kernel", "bf_conv_c3_backward_filter_unpool": "conv_c3_df_kernel",
-}
-
-
 def measured_traffic(label):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the call's dominant kernel, from the newest committed
     `ncu --set full` summary under profiles/ (None when that launch was not captured).  Entries are keyed by the call label
-    `name(int args)` -- one per layer shape -- or, for the kernels that have ONE instance per step, by kernel name."""
+    `name(int args)`: one per layer shape (scripts/summarise_profiles.py maps each captured kernel instance to its call)."""
     pdir = os.path.join(ROOT, "profiles")
     if not os.path.isdir(pdir):
         return None
@@ -381,8 +374,7 @@ def measured_traffic(label):
     key = label.split("[")[0]
     if key in table:
         return table[key].get("bytes")
-    kern = KERNEL_OF_CALL.get(parse_label(label)[0])
-    return table.get(kern, {}).get("bytes") if kern else None
+    return None          # this launch (shape) was not captured: no figure rather than another instance's
 
 
 def roofline_entry(times, peaks, tf32):

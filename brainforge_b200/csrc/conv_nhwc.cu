@@ -601,58 +601,74 @@ constexpr int DF_RED_SLICES = 16;
 __global__ void __launch_bounds__(32 * DF_RED_SLICES)
 conv_df_reduce_nhwc_kernel(const float* __restrict__ partial, float* __restrict__ dF, float* __restrict__ db,
                            int nsplit, int nch, int ntaps, int nf, int ic, const float* __restrict__ dbp, int dbrows) {
-  __shared__ float red[DF_RED_SLICES][33];
+  // thread = FOUR consecutive channels (one 16-byte load per split) of one (channel group, tap, filter) row x one slice of
+  // the split range; the last blocks take the nf bias sums (scalar)
+  __shared__ float4 red[DF_RED_SLICES][32];
   pdl_launch_dependents();
   pdl_wait();
-  const long nmain = (long)nch * ntaps * nf * 32, total = nmain + nf;
+  const long nmain4 = (long)nch * ntaps * nf * 8;               // float4 items of the filter gradient
+  const long main_blocks = (nmain4 + 31) / 32;
   const size_t zstride = (size_t)nch * (ntaps + 1) * nf * 32;
-  const long i = (long)blockIdx.x * 32 + threadIdx.x;
   const int zs = threadIdx.y;
-  size_t off = 0;
-  long dst = 0;
-  if (i < total) {
-    if (i < nmain) {
-      const int cl = (int)(i & 31);
-      long r = i >> 5;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  long dst = -1;
+  int dbf = -1;
+  if ((long)blockIdx.x < main_blocks) {
+    const long i = (long)blockIdx.x * 32 + threadIdx.x;
+    if (i < nmain4) {
+      const int c4 = (int)(i & 7);
+      long r = i >> 3;
       const int f = (int)(r % nf);
       r /= nf;
       const int tap = (int)(r % ntaps), ch = (int)(r / ntaps);
-      off = ((size_t)(ch * (ntaps + 1) + tap) * nf + f) * 32 + cl;
-      dst = ((long)f * ic + ch * 32 + cl) * ntaps + tap;
-    } else {
-      const int f = (int)(i - nmain);
-      off = ((size_t)ntaps * nf + f) * 32;
-      dst = -1 - f;
-    }
-  }
-  float s = 0.f;
-  if (i < total) {
-    if (dst < 0 && dbp) {            // db from the per-CTA channel sums of the kernel that wrote E (bf_pool_nhwc_backward_db)
-      for (int z = zs; z < dbrows; z += DF_RED_SLICES) s += dbp[(size_t)z * nf + (-1 - dst)];
-    } else {
-      float s1 = 0.f, s2 = 0.f, s3 = 0.f;        // independent chains: the loads of four splits are in flight together
+      const float4* src = reinterpret_cast<const float4*>(partial + ((size_t)(ch * (ntaps + 1) + tap) * nf + f) * 32) + c4;
+      const size_t z4 = zstride / 4;
+      float4 s1 = s, s2 = s, s3 = s;            // independent chains: four splits' loads in flight together
       int z = zs;
       for (; z + 3 * DF_RED_SLICES < nsplit; z += 4 * DF_RED_SLICES) {
-        s += partial[(size_t)z * zstride + off];
-        s1 += partial[(size_t)(z + DF_RED_SLICES) * zstride + off];
-        s2 += partial[(size_t)(z + 2 * DF_RED_SLICES) * zstride + off];
-        s3 += partial[(size_t)(z + 3 * DF_RED_SLICES) * zstride + off];
+        const float4 a0 = src[(size_t)z * z4], a1 = src[(size_t)(z + DF_RED_SLICES) * z4];
+        const float4 a2 = src[(size_t)(z + 2 * DF_RED_SLICES) * z4], a3 = src[(size_t)(z + 3 * DF_RED_SLICES) * z4];
+        s.x += a0.x; s.y += a0.y; s.z += a0.z; s.w += a0.w;
+        s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+        s2.x += a2.x; s2.y += a2.y; s2.z += a2.z; s2.w += a2.w;
+        s3.x += a3.x; s3.y += a3.y; s3.z += a3.z; s3.w += a3.w;
       }
-      for (; z < nsplit; z += DF_RED_SLICES) s += partial[(size_t)z * zstride + off];
-      s = (s + s1) + (s2 + s3);
+      for (; z < nsplit; z += DF_RED_SLICES) {
+        const float4 a0 = src[(size_t)z * z4];
+        s.x += a0.x; s.y += a0.y; s.z += a0.z; s.w += a0.w;
+      }
+      s.x = (s.x + s1.x) + (s2.x + s3.x); s.y = (s.y + s1.y) + (s2.y + s3.y);
+      s.z = (s.z + s1.z) + (s2.z + s3.z); s.w = (s.w + s1.w) + (s2.w + s3.w);
+      dst = ((long)f * ic + ch * 32 + c4 * 4) * ntaps + tap;
+    }
+  } else {
+    const int f = (int)(((long)blockIdx.x - main_blocks) * 32 + threadIdx.x);
+    if (f < nf) {
+      dbf = f;
+      if (dbp) {                                  // db from the per-CTA channel sums of the kernel that wrote E (bf_pool_nhwc_backward_db)
+        for (int z = zs; z < dbrows; z += DF_RED_SLICES) s.x += dbp[(size_t)z * nf + f];
+      } else {
+        const size_t off = ((size_t)ntaps * nf + f) * 32;
+        for (int z = zs; z < nsplit; z += DF_RED_SLICES) s.x += partial[(size_t)z * zstride + off];
+      }
     }
   }
   red[zs][threadIdx.x] = s;
   __syncthreads();
 #pragma unroll
   for (int w = DF_RED_SLICES / 2; w >= 1; w >>= 1) {
-    if (zs < w) red[zs][threadIdx.x] += red[zs + w][threadIdx.x];
+    if (zs < w) {
+      float4 a = red[zs][threadIdx.x];
+      const float4 c = red[zs + w][threadIdx.x];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      red[zs][threadIdx.x] = a;
+    }
     __syncthreads();
   }
-  if (zs == 0 && i < total) {
-    const float sum = red[0][threadIdx.x];
-    if (dst >= 0) dF[dst] = sum;
-    else if (db) db[-1 - dst] = sum;
+  if (zs == 0) {
+    const float4 sum = red[0][threadIdx.x];
+    if (dst >= 0) { dF[dst] = sum.x; dF[dst + ntaps] = sum.y; dF[dst + 2 * ntaps] = sum.z; dF[dst + 3 * ntaps] = sum.w; }
+    else if (dbf >= 0 && db) db[dbf] = sum.x;
   }
 }
 
@@ -1044,7 +1060,7 @@ static int conv_nhwc_backward_filter_impl(const float* X, const float* E, float*
   BF_DF_CASE(1) BF_DF_CASE(2) BF_DF_CASE(4)
 #undef BF_DF_CASE
   BF_LAUNCH_CHECK();
-  launch_pdl(conv_df_reduce_nhwc_kernel, dim3((unsigned)(((size_t)nf * ic * ntaps + nf + 31) / 32)), dim3(32, DF_RED_SLICES), 0, s,
+  launch_pdl(conv_df_reduce_nhwc_kernel, dim3((unsigned)(((size_t)nf * ic * ntaps / 4 + 31) / 32 + (nf + 31) / 32)), dim3(32, DF_RED_SLICES), 0, s,
              (const float*)ws, dF, db, nsplit, nch, ntaps, nf, ic, db_partial, db_rows);
   BF_LAUNCH_CHECK();
   set_last_path(2);

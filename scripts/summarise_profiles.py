@@ -39,36 +39,52 @@ with open(os.path.join(P, tag + "_launches_cfg3_nhwc_summary.txt"), "w") as f:
             f.write("%9.1f us  %s\n" % (v, k[:130]))
 os.replace(os.path.join(G, tag + "_launches_cfg3.csv"), os.path.join(P, tag + "_launches_cfg3_nhwc.csv"))
 
-# ---- --set full captures -> key metrics per kernel
+# ---- --set full capture of one whole step -> key metrics per kernel (launch order) + DRAM traffic per call
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_tc.sum", "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg"]
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+# kernel instance (template arguments) -> the C-ABI call of the cfg3 step at batch 4096 it serves (bench.py's call labels)
+CALL_OF = [
+    ("conv_c3_fwd_kernel<32, 0, 1>", "bf_conv_c3_forward_pool(4096,3,30,30,32,3,3,0,1)"),
+    ("conv_igemm_kernel<64, 1, 0, 0, 1>", "bf_conv_nhwc_forward_pool_packed(4096,32,14,14,64,3,3,1)"),
+    ("conv_igemm_kernel<128, 2, 0, 0, 1>", "bf_conv_nhwc_forward_pool_packed(4096,64,6,6,128,3,3,1)"),
+    ("dense_head_kernel<16>", "bf_dense_head(4096,128,4,10,4,1,1,1)"),
+    ("conv_df_kernel<4>", "bf_conv_nhwc_backward_filter_dbp(1184,4096,64,6,6,128,3,3)"),
+    ("conv_igemm_kernel<64, 2, 0, 0, 0>", "bf_conv_nhwc_backward_data_packed(4096,64,6,6,128,3,3)"),
+    ("conv_df_kernel<2>", "bf_conv_nhwc_backward_filter_dbp(1184,4096,32,14,14,64,3,3)"),
+    ("conv_igemm_kernel<32, 1, 0, 1, 0>", "bf_conv_nhwc_backward_data_packed(4096,32,14,14,64,3,3)"),
+    ("conv_c3_df_kernel<1, 27, 1>", "bf_conv_c3_backward_filter_unpool(4096,3,30,30,32,3,3)"),
+]
 traffic = {}
-with open(os.path.join(P, tag + "_ncu_full_nhwc.tsv"), "w") as f:
-    f.write("kernel\tmetric\tunit\tvalue\n")
-    for fn in sorted(os.listdir(G)):
-        if not (fn.startswith(tag + "_full_") and fn.endswith(".ncu-rep")):
-            continue
-        raw = subprocess.run(["ncu", "-i", os.path.join(G, fn), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        r = list(csv.reader(io.StringIO(raw)))
-        if len(r) < 3:
-            continue
-        h, u, v = r[0], r[1], r[2]
-        name = v[h.index("Kernel Name")] if "Kernel Name" in h else fn
-        for m in want:
-            if m in h:
-                j = h.index(m)
-                f.write("%s\t%s\t%s\t%s\n" % (name[:90], m, u[j], v[j]))
-        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tb = 0.0
-        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            j = h.index(m)
-            tb += float(v[j].replace(",", "")) * scale.get(u[j], 1)
-        fam = fn[len(tag + "_full_"):-len(".ncu-rep")]
-        traffic[fam] = {"bytes": tb, "instance": name[:120]}
-json.dump(traffic, open(os.path.join(P, tag + "_traffic.json"), "w"), indent=1)
+rep = os.path.join(G, tag + "_full_step.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(raw)))
+    h, u = r[0], r[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    with open(os.path.join(P, tag + "_ncu_full_step.tsv"), "w") as f:
+        f.write("# ncu --set full --clock-control none of ONE cfg3 training step (batch 4096, tf32 path, eager launches), launch order\n")
+        f.write("order\tkernel\t" + "\t".join(want) + "\n")
+        f.write("\t\t" + "\t".join(u[h.index(m)] if m in h else "" for m in want) + "\n")
+        pool_seen = 0
+        for i, v in enumerate(r[2:]):
+            name = v[h.index("Kernel Name")]
+            f.write("%d\t%s\t%s\n" % (i, name[:70], "\t".join(v[h.index(m)] if m in h else "" for m in want)))
+            tb = sum(float(v[h.index(m)].replace(",", "")) * scale.get(u[h.index(m)], 1) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            dur = float(v[h.index("gpu__time_duration.sum")].replace(",", ""))
+            dur = dur / 1000 if u[h.index("gpu__time_duration.sum")] in ("ns", "nsecond") else dur
+            entry = {"bytes": tb, "instance": name[:120], "ncu_us": dur,
+                     "tensor_pipe_pct": float(v[h.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")] or 0)}
+            for inst, call in CALL_OF:
+                if inst in name and call not in traffic:
+                    traffic[call] = entry
+            if "pool_nhwc_bwd_kernel" in name:       # two launches per step: 128-channel layer first, then the 64-channel one
+                call = ("bf_pool_nhwc_backward_db(4096,128,4,4,2)", "bf_pool_nhwc_backward_db(4096,64,12,12,2)")[min(pool_seen, 1)]
+                traffic.setdefault(call, entry)
+                pool_seen += 1
+    json.dump(traffic, open(os.path.join(P, tag + "_traffic.json"), "w"), indent=1)
 # ---- bench line
 src = os.path.join(G, tag + "_bench_cfg3.json")
 if os.path.exists(src):
