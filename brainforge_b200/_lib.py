@@ -32,6 +32,7 @@ SIGNATURES = {
     "bf_last_path": (_i, []),
     "bf_launch_count": (_c.c_ulonglong, []),
     "bf_memcpy_h2d": (_i, [_vp, _vp, _sz, _vp]),
+    "bf_upload_host": (_i, [_vp, _vp, _sz, _i, _vp]),
     "bf_memcpy_d2h": (_i, [_vp, _vp, _sz, _vp]),
     "bf_memcpy_d2d": (_i, [_vp, _vp, _sz, _vp]),
     "bf_stream_sync": (_i, [_vp]),

@@ -31,6 +31,9 @@ def require_cuda():
                            "The float64 CPU oracle lives under oracle/ and is test infrastructure only.")
 
 
+UPLOAD_POOL_MIN = 1 << 16      # elements: smaller pageable arrays take the plain copy (+ the device-side narrowing)
+
+
 def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -174,16 +177,26 @@ class DeviceArray:
             a = a.reshape(self.shape)
         if a.size == 0:
             return self
+        capturing = torch.cuda.is_current_stream_capturing()
         if a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]:
-            call(_lib.lib.bf_memcpy_h2d, self.ptr, ctypes.c_void_p(a.ctypes.data), a.nbytes, stream_ptr())
-            if not _is_pinned(a):
-                call(_lib.lib.bf_stream_sync, stream_ptr())  # pageable source may be reused by the caller
+            if _is_pinned(a) or a.size < UPLOAD_POOL_MIN or capturing:
+                call(_lib.lib.bf_memcpy_h2d, self.ptr, ctypes.c_void_p(a.ctypes.data), a.nbytes, stream_ptr())
+                if not _is_pinned(a):
+                    call(_lib.lib.bf_stream_sync, stream_ptr())  # pageable source may be reused by the caller
+            else:
+                # pageable: host threads copy it into pinned staging chunks (the driver's own staging runs on one thread)
+                call(_lib.lib.bf_upload_host, self.ptr, ctypes.c_void_p(a.ctypes.data), a.size, 0, stream_ptr())
         else:
             a64 = np.ascontiguousarray(a, dtype=np.float64)
-            stage = torch.empty(a64.size, dtype=torch.float64, device="cuda")
-            call(_lib.lib.bf_memcpy_h2d, _ptr(stage), ctypes.c_void_p(a64.ctypes.data), a64.nbytes, stream_ptr())
-            call(_lib.lib.bf_cast_f64_to_f32, _ptr(stage), self.ptr, a64.size, stream_ptr())
-            call(_lib.lib.bf_stream_sync, stream_ptr())
+            if a64.size >= UPLOAD_POOL_MIN and not capturing:
+                # the reference API's native arrays: narrowed on the host by a thread pool into pinned staging chunks, half
+                # the bytes over the host link (the values equal the device cast: round to nearest even)
+                call(_lib.lib.bf_upload_host, self.ptr, ctypes.c_void_p(a64.ctypes.data), a64.size, 1, stream_ptr())
+            else:
+                stage = torch.empty(a64.size, dtype=torch.float64, device="cuda")
+                call(_lib.lib.bf_memcpy_h2d, _ptr(stage), ctypes.c_void_p(a64.ctypes.data), a64.nbytes, stream_ptr())
+                call(_lib.lib.bf_cast_f64_to_f32, _ptr(stage), self.ptr, a64.size, stream_ptr())
+                call(_lib.lib.bf_stream_sync, stream_ptr())
         return self
 
     # ---- layout

@@ -62,6 +62,11 @@ BF_API int bf_set_workspace(void* d_ptr, size_t bytes);
 BF_API int bf_last_path(void);
 /* Number of kernels this library has launched so far in this process (for bench.py gpu_launches). */
 BF_API unsigned long long bf_launch_count(void);
+/* Upload of a PAGEABLE host array (the reference API's float64 NumPy inputs, layers' parameters, data sets): host threads
+ * narrow float64 -> float32 (round to nearest even, as bf_cast_f64_to_f32 does on the device) or copy float32 into two
+ * pinned staging buffers chunk by chunk while the previous chunk crosses the host link.  The source has been read when
+ * the call returns; the device copies are ordered on `stream`.  (No reference counterpart: the reference has no device.) */
+BF_API int bf_upload_host(float* d_dst, const void* h_src, size_t n, int src_is_f64, void* stream);
 BF_API int bf_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream);
 BF_API int bf_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream);
 BF_API int bf_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream);

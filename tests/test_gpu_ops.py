@@ -521,3 +521,20 @@ def test_large_cost_reduction_is_deterministic(bf, O):
     assert a == b
     close(a, O.cost_value("cxent", o, t), 1e-6)
     close(bf.metrics.mse(o, t), O.cost_value("mse", o, t), 1e-6)
+
+
+@pytest.mark.parametrize("n", [1 << 16, (4 << 20) + 3, (9 << 20) + 17])
+def test_pageable_upload_through_the_host_thread_pool(n):
+    """bf_upload_host: pageable float64 (the reference API's arrays) narrowed on the host by a thread pool into pinned staging
+    chunks == the device-side cast bit for bit (round to nearest even), pageable float32 copied unchanged; chunk boundaries,
+    back-to-back calls reusing the staging buffers, source overwritten right after the call."""
+    import brainforge_b200 as bf
+    rs = np.random.RandomState(n % 1000)
+    a64 = rs.randn(n) * np.exp(rs.uniform(-20, 20, n))          # wide exponent range: the rounding is exercised
+    want = a64.astype(np.float32)
+    d = bf.DeviceArray.from_host(a64)
+    a64[:] = 0.0                                                 # the call has read the source completely
+    e = bf.DeviceArray.from_host(want.copy())                    # pageable float32
+    assert np.array_equal(d.numpy(np.float32), want) and np.array_equal(e.numpy(np.float32), want)
+    small = rs.randn(1000)                                       # below the pool threshold: device-side cast
+    assert np.array_equal(bf.DeviceArray.from_host(small).numpy(np.float32), small.astype(np.float32))
