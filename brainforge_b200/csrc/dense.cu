@@ -396,20 +396,13 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(sX)), "l"(reinterpret_cast<uint64_t>(xsrc)), "r"(xbytes), "r"(smem_u32(&xbar)) : "memory");
   }
-  const int total = k * n;
-  for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < total ? __ldg(W + i) : 0.f; }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < total) {
-        const int kl = i / n;
-        const int kk = pc ? (kl % phw) * pc + kl / phw : kl;
-        sW[kk * PITCH + (i - kl * n)] = v[u];
-      }
-    }
+  // W by rows: thread = row kl of W (its n values are contiguous), ONE index permutation per row instead of two integer
+  // divisions per element (that loop was a fifth of the kernel's instructions)
+  for (int kl = threadIdx.x; kl < k; kl += blockDim.x) {
+    const int kk = pc ? (kl % phw) * pc + kl / phw : kl;
+    const float* wr = W + (size_t)kl * n;
+    float* dst = sW + kk * PITCH;
+    for (int j = 0; j < n; ++j) dst[j] = __ldg(wr + j);
   }
   if (bulk) {
     mbar_wait(&xbar, 0u);
@@ -505,9 +498,16 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
       }
       if (dX) dX[(size_t)(m0 + r) * k + kk] = dx;
     }
+    // the weight-gradient partial goes out through shared memory (W's row is dead for this column now): written
+    // directly, every thread's n values were a strided 40-byte store -- a quarter of the kernel's stall samples
 #pragma unroll
-    for (int j = 0; j < NT; ++j)
-      if (j < n) part[(size_t)kl * n + j] = acc[j];
+    for (int j = 0; j < NT; ++j) sW[kk * PITCH + j] = acc[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k * n; i += blockDim.x) {
+    const int kl = i / n, j = i - kl * n;
+    const int kk = pc ? (kl % phw) * pc + kl / phw : kl;
+    part[i] = sW[kk * PITCH + j];
   }
   if (threadIdx.x < n) {                     // db partial = column sums of the chunk's delta
     float sacc = 0.f;
