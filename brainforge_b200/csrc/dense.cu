@@ -539,12 +539,13 @@ dense_head_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
 static inline int head_rows(int m, int k, int n, size_t* smem_out) {
   if (n > 32 || k < 1) return 0;
   const int nt = skinny_nt(n), pitch = nt == 4 ? 4 : nt + 4;
-  for (int R = 32; R >= 4; R >>= 1) {
+  for (int R = 128; R >= 4; R >>= 1) {
     const size_t smem = ((size_t)k * pitch + (size_t)R * k + (size_t)R * nt) * sizeof(float);
     if (smem <= 200 * 1024) {
       // about two CTAs per SM: every CTA pays for staging W once, so more, smaller chunks only help until the machine is full
       int r = 4;
-      while (r < R && (m + r - 1) / r > 2 * num_sms()) r <<= 1;
+      static const int max_ctas = getenv("BF_HEAD_MAX_CTAS") ? atoi(getenv("BF_HEAD_MAX_CTAS")) : num_sms();
+      while (r < R && (m + r - 1) / r > max_ctas) r <<= 1;
       *smem_out = ((size_t)k * pitch + (size_t)r * k + (size_t)r * nt) * sizeof(float);
       return r;
     }
