@@ -234,7 +234,7 @@ def run_reference(args):
         cfgd = {"workload": WORKLOAD_NAME["cfg5"], "population": 4096, "samples": N}
     else:
         cfg = CFG[args.workload]
-        b = args.batch or pick_cpu_batch(cfg, K, W, 200.0)
+        b = args.batch or pick_cpu_batch(cfg, K, W, 120.0)
         val, spu, kind = cpu_arm(cfg, K, W, b)
         sample, unit, metric = "batch %d per step (of the %d-sample step)" % (b, cfg["batch"]), "samples/s", \
             "train samples/s (fwd+bwd+update)"
