@@ -601,8 +601,8 @@ def run_b200(args):
         "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_NAME[args.workload], "global_batch": gb, "per_gpu_batch": mb,
                    "parallelism": "dp%d" % ws, "precision_path": args.precision, "cuda_graph": bool(graphs),
-                   "allreduce": ("none" if ws == 1 else "fused with the optimizer step: peer loads over NVLink "
-                                 "(bf_opt_step_allreduce)" if getattr(net.layers, "symm", None) is not None
+                   "allreduce": ("none" if ws == 1 else "fused with the optimizer step: gradient slices pushed into the peers' "
+                                 "receive buffers over NVLink (bf_opt_step_allreduce)" if getattr(net.layers, "symm", None) is not None
                                  else "NCCL all-reduce + bf_opt_step"),
                    "input_delta": "first layer's dX is not computed inside learn_batch (the reference discards it; "
                                   "its FLOPs are excluded per SURVEY 8d)",
