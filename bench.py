@@ -481,13 +481,18 @@ def run_b200(args):
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    hist = net.epoch(batches(), updates_per_epoch=K, verbose=0)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    assert len(hist["cost"]) == K
+    # three K-step epochs, the MEDIAN is reported (all three are in the line): a host-side hiccup -- the loop is bound by the
+    # host link and one Python thread -- otherwise decides a 15 ms measurement
+    e2e_runs = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hist = net.epoch(batches(), updates_per_epoch=K, verbose=0)
+        e1.record()
+        barrier()
+        e2e_runs.append(e0.elapsed_time(e1))
+        assert len(hist["cost"]) == K
+    e2e_ms = sorted(e2e_runs)[1]
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for i in range(K):
@@ -609,6 +614,7 @@ def run_b200(args):
                    "l2": "4 rotating input batches + >1 GB of activations per step exceed the 126 MB L2",
                    "cost_last_step": out["cost"]},
         "e2e": {"value": gb * K / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms / K,
+                "ms_per_step_runs": [r / K for r in e2e_runs], "statistic": "median of 3 epochs of K steps (this rank)",
                 "h2d_bytes_per_step": h2d * ws, "d2h_bytes_per_step": 256 * ws,
                 "api": "Backpropagation.epoch(generator of pinned f32 host batches, K): learn_batch per step, "
                        "next batch's H2D overlapped on a copy stream"},
