@@ -814,6 +814,13 @@ static IgemmPlan plan_igemm(int B, int H, int W, int KH, int nkp, int NB, int N,
     if (PH <= 256)
       for (int G = 1; G <= 256 && G <= B + 8; ++G)
         if (!consider(G, 1, out_y, PH, fold != 0)) break;
+    // "full" correlation (data gradient, pad = f - 1): the bottom padding rows of an image need not be staged -- the reads
+    // that would touch them land in the TOP padding rows of the next image of the stage (zero-filled by TMA) or, behind the
+    // last image, in the never-written tail of the slot (zeros).  Every staged row is then an output row: on a 4x4 plane
+    // 48 instead of 64 positions per image.
+    if (pad_y > 0 && pad_y == fy - 1 && PH - pad_y <= 256)
+      for (int G = 1; G <= 256 && G <= B + 8; ++G)
+        if (!consider(G, 1, out_y, PH - pad_y, fold != 0)) break;
     for (int RO = (out_y < 254 ? out_y - 1 : 254); RO >= 1; --RO) {
       if (RO + fy - 1 > 256) continue;
       consider(1, (out_y + RO - 1) / RO, RO, RO + fy - 1, fold != 0);
