@@ -38,10 +38,44 @@ splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, floa
   }
 }
 
+// Few splits over a LARGE output (the LSTM weight gradient: 385 x 1024 outputs, 6 splits): one thread per four consecutive
+// outputs of a row, the splits added in order (deterministic) from 16-byte loads.  The sliced kernel above launches one
+// 512-thread block per 32 outputs -- 12 k blocks for that matrix, most of their threads without work (58 us).
+__global__ void __launch_bounds__(256)
+splitk_reduce_wide_kernel(const float* __restrict__ ws, float* __restrict__ out, float* __restrict__ aux, int rows, int N,
+                          int aux_row, int splits, int accumulate, long out_rs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n4 = N >> 2;
+  const long total4 = (long)rows * n4, stride4 = (long)rows * N / 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / n4), c4 = (int)(i - (long)r * n4);
+    const float4* src = reinterpret_cast<const float4*>(ws) + i;
+    float4 a = src[0];
+    for (int z = 1; z < splits; ++z) {
+      const float4 b = src[(long)z * stride4];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float* dst;
+    if (r == aux_row) dst = aux ? aux + c4 * 4 : nullptr;
+    else dst = out + (long)(r > aux_row && aux_row >= 0 ? r - 1 : r) * out_rs + c4 * 4;
+    if (dst) {
+      if (accumulate) { dst[0] += a.x; dst[1] += a.y; dst[2] += a.z; dst[3] += a.w; }
+      else { dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; }
+    }
+  }
+}
+
 int launch_splitk_reduce(const float* ws, float* out, float* aux, int rows, int N, int aux_row, int splits,
                          int accumulate, long out_rs, long out_cs, cudaStream_t s) {
   long total = (long)rows * N;
   if (total == 0) return BF_OK;
+  if (splits <= 16 && out_cs == 1 && (N & 3) == 0 && total >= (1L << 16) && (((uintptr_t)ws) & 15) == 0) {
+    launch_pdl(splitk_reduce_wide_kernel, dim3((unsigned)ew_grid((size_t)(total / 4), 256)), dim3(256), 0, s, ws, out, aux, rows, N,
+               aux_row, splits, accumulate, out_rs);
+    BF_LAUNCH_CHECK();
+    return BF_OK;
+  }
   launch_pdl(splitk_reduce_kernel, dim3((unsigned)((total + 31) / 32)), dim3(32, SK_RED_SLICES), 0, s, ws, out, aux, rows, N, aux_row,
              splits, accumulate, out_rs, out_cs);
   BF_LAUNCH_CHECK();
