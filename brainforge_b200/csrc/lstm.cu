@@ -318,16 +318,21 @@ struct LstmSeqParams {
   const float* bias;
   float *cache, *O, *Z, *bw;
   unsigned* flags;      // [m_tiles][T], zeroed before the launch
+  int tma_rows;         // the twelve bulk rows of a step (cache, O, bw) leave through TMA stores from a staged tile
 };
+constexpr uint32_t LS_ROW_TILE = 128 * LF_UNITS * 4;       // one staged [128 rows][16 units] tile of a bulk row
 
 __global__ void __launch_bounds__(LF_THREADS, 1)
-lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapW, LstmSeqParams p) {
+lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapW,
+                    const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapO,
+                    const __grid_constant__ CUtensorMap mapBW, LstmSeqParams p) {
   extern __shared__ int dyn_smem[];
   __shared__ __align__(8) uint64_t w_full, full[LS_RING], empty[LS_RING], t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t wbase = (smem_u32(dyn_smem) + 1023u) & ~1023u;
   const uint32_t ring = wbase + (uint32_t)p.nkb * LF_B_BYTES;
+  const uint32_t rowst = ring + (uint32_t)LS_RING * LF_A_BYTES;          // two staged row tiles (tma_rows)
   const int nt = blockIdx.x / p.m_tiles, mt = blockIdx.x - nt * p.m_tiles;
   const int j0 = nt * LF_UNITS;
 
@@ -452,7 +457,43 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 128) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + (size_t)mt * p.T + t) : "memory");
       }
-      if (live) {
+      if (p.tma_rows) {
+        // The twelve rows nobody waits for leave through the async proxy: staged 128 x 16 tile -> one TMA store per row.
+        // Written with ordinary stores they sat in front of the NEXT step's gpu-scope release (2.5-3 us of its ~10 us).
+        float dv[8];
+        const uint32_t mine = (uint32_t)((quad * 32 + lane) * LF_UNITS + half * 8) * 4u;
+#define LS_PUT_ROW(VALS, MAP, ROWIDX, SEQ)                                                                              \
+        {                                                                                                               \
+          const uint32_t tile = rowst + (uint32_t)((SEQ) & 1) * LS_ROW_TILE;                                            \
+          if (tid == 128) tma_store_wait_read<1>();          /* the store that read this tile two rows ago is done */   \
+          asm volatile("bar.sync 1, 256;" ::: "memory");                                                                \
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + mine), "f"(VALS[0]), "f"(VALS[1]), "f"(VALS[2]), "f"(VALS[3]) : "memory"); \
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + mine + 16u), "f"(VALS[4]), "f"(VALS[5]), "f"(VALS[6]), "f"(VALS[7]) : "memory"); \
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                                  \
+          asm volatile("bar.sync 1, 256;" ::: "memory");                                                                \
+          if (tid == 128) { tma_store_4d(&MAP, tile, j0, mt * 128, t, ROWIDX); tma_store_commit(); }                    \
+        }
+        LS_PUT_ROW(c, mapC, 0, 0) LS_PUT_ROW(ca, mapC, 1, 1) LS_PUT_ROW(cv, mapC, 2, 2) LS_PUT_ROW(fv, mapC, 3, 3)
+        LS_PUT_ROW(iv, mapC, 4, 4) LS_PUT_ROW(ov, mapC, 5, 5) LS_PUT_ROW(out, mapO, 0, 6)
+        if (p.bw) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = ov[i] * act_deriv_from_z(p.act, c[i], ca[i]);
+          LS_PUT_ROW(dv, mapBW, 0, 7)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = iv[i] * act_deriv_from_z(p.act, zc[i], cv[i]);
+          LS_PUT_ROW(dv, mapBW, 1, 8)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = cprev[i] * (fv[i] * sigmoidf_(-zf[i]));
+          LS_PUT_ROW(dv, mapBW, 2, 9)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = cv[i] * (iv[i] * sigmoidf_(-zi[i]));
+          LS_PUT_ROW(dv, mapBW, 3, 10)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = ca[i] * (ov[i] * sigmoidf_(-zo[i]));
+          LS_PUT_ROW(dv, mapBW, 4, 11)
+        }
+#undef LS_PUT_ROW
+      } else if (live) {
         float* q = p.cache + off + row;
         store8(q, c, nvalid, vec);
         store8(q + p.TBH, ca, nvalid, vec);
@@ -483,6 +524,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
       }
     }
   }
+  if (p.tma_rows && tid == 128) tma_store_wait<0>();       // every row store has left the staged tiles and landed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * LF_N));
@@ -907,8 +949,22 @@ static int lstm_forward_impl(const float* X, const float* W, const float* b, flo
     {
       // persistent form: every tile resident at once (one CTA per SM), W slice + A ring within shared memory
       const int nkb = (K + 31) / 32, m_tiles = (B + 127) / 128, n_tiles = (H + LF_UNITS - 1) / LF_UNITS;
-      const size_t smem = 1024 + (size_t)nkb * LF_B_BYTES + (size_t)LS_RING * LF_A_BYTES;
-      bool fits = m_tiles * n_tiles <= num_sms() && smem <= 220 * 1024 && getenv("BF_LSTM_STEPWISE") == nullptr;
+      // bulk rows through TMA stores: needs 16-byte row strides and room for two staged row tiles
+      CUtensorMap mC, mO, mBW;
+      memset(&mC, 0, sizeof(mC)); memset(&mO, 0, sizeof(mO)); memset(&mBW, 0, sizeof(mBW));
+      bool tma_rows = (H % 4) == 0 && getenv("BF_LSTM_TMA_ROWS") != nullptr &&   // opt-in until verified on the GPU
+                      1024 + (size_t)nkb * LF_B_BYTES + (size_t)LS_RING * LF_A_BYTES + 2 * LS_ROW_TILE <= 224 * 1024;
+      if (tma_rows) {
+        uint64_t str[3] = {(uint64_t)H, (uint64_t)B * H, (uint64_t)TB * H};
+        uint32_t box[4] = {LF_UNITS, 128, 1, 1};
+        uint64_t dc[4] = {(uint64_t)H, (uint64_t)B, (uint64_t)T, 6}, dO[4] = {(uint64_t)H, (uint64_t)B, (uint64_t)T, 1},
+                 db[4] = {(uint64_t)H, (uint64_t)B, (uint64_t)T, 5};
+        tma_rows = tma_make_map(&mC, cache, 4, dc, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, false) &&
+                   tma_make_map(&mO, O, 4, dO, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, false) &&
+                   (bw == nullptr || tma_make_map(&mBW, bw, 4, db, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, false));
+      }
+      const size_t smem = 1024 + (size_t)nkb * LF_B_BYTES + (size_t)LS_RING * LF_A_BYTES + (tma_rows ? 2 * LS_ROW_TILE : 0);
+      bool fits = m_tiles * n_tiles <= num_sms() && smem <= 224 * 1024 && getenv("BF_LSTM_STEPWISE") == nullptr;
       if (fits) {
         // the flag protocol needs every CTA resident: ask the runtime instead of assuming one CTA per SM is available
         BF_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -920,8 +976,9 @@ static int lstm_forward_impl(const float* X, const float* W, const float* b, flo
         LstmSeqParams q;
         q.T = T; q.B = B; q.D = D; q.H = H; q.nkb = nkb; q.kb_dep = D / 32; q.m_tiles = m_tiles; q.n_tiles = n_tiles;
         q.act = act; q.TBH = TB * H; q.bias = b; q.cache = cache; q.O = O; q.Z = Z; q.bw = bw; q.flags = flags;
+        q.tma_rows = tma_rows ? 1 : 0;
         BF_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, s));
-        void* args[] = {(void*)&mZ, (void*)&mW, (void*)&q};
+        void* args[] = {(void*)&mZ, (void*)&mW, (void*)&mC, (void*)&mO, (void*)&mBW, (void*)&q};
         BF_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_fwd_kernel, dim3(m_tiles * n_tiles), dim3(LF_THREADS), args, smem, s));
         count_launch();
         set_last_path(2);
