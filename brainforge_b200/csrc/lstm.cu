@@ -421,6 +421,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
       bi[i] = ok ? __ldg(p.bias + 2 * p.H + jb + i) : 0.f;
       bo[i] = ok ? __ldg(p.bias + 3 * p.H + jb + i) : 0.f;
     }
+    uint32_t rowseq = 0;             // staged row tiles written so far (tma_rows)
     for (int t = 0; t < p.T; ++t) {
       const int set = t & 1, tu = t >> 1;
       mbar_wait(&t_full[set], (uint32_t)(tu & 1));
@@ -464,7 +465,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
         const uint32_t mine = (uint32_t)((quad * 32 + lane) * LF_UNITS + half * 8) * 4u;
 #define LS_PUT_ROW(VALS, MAP, ROWIDX, SEQ)                                                                              \
         {                                                                                                               \
-          const uint32_t tile = rowst + (uint32_t)((SEQ) & 1) * LS_ROW_TILE;                                            \
+          const uint32_t tile = rowst + (rowseq++ & 1u) * LS_ROW_TILE;     /* alternates across rows AND steps */        \
           if (tid == 128) tma_store_wait_read<1>();          /* the store that read this tile two rows ago is done */   \
           asm volatile("bar.sync 1, 256;" ::: "memory");                                                                \
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + mine), "f"(VALS[0]), "f"(VALS[1]), "f"(VALS[2]), "f"(VALS[3]) : "memory"); \
