@@ -459,8 +459,10 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_const
         if (tid == 128) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + (size_t)mt * p.T + t) : "memory");
       }
       if (p.tma_rows) {
-        // The twelve rows nobody waits for leave through the async proxy: staged 128 x 16 tile -> one TMA store per row.
-        // Written with ordinary stores they sat in front of the NEXT step's gpu-scope release (2.5-3 us of its ~10 us).
+        // EXPERIMENT (BF_LSTM_TMA_ROWS=1, parity-green, off by default): the twelve rows nobody waits for leave through the
+        // async proxy -- staged 128 x 16 tile -> one TMA store per row -- so that they do not sit in front of the next step's
+        // gpu-scope release.  Measured SLOWER on a B200 (cfg4 forward 706 vs 635 us): the 24 group barriers and staging
+        // stores per step cost more than the release saves.
         float dv[8];
         const uint32_t mine = (uint32_t)((quad * 32 + lane) * LF_UNITS + half * 8) * 4u;
 #define LS_PUT_ROW(VALS, MAP, ROWIDX, SEQ)                                                                              \
@@ -953,7 +955,7 @@ static int lstm_forward_impl(const float* X, const float* W, const float* b, flo
       // bulk rows through TMA stores: needs 16-byte row strides and room for two staged row tiles
       CUtensorMap mC, mO, mBW;
       memset(&mC, 0, sizeof(mC)); memset(&mO, 0, sizeof(mO)); memset(&mBW, 0, sizeof(mBW));
-      bool tma_rows = (H % 4) == 0 && getenv("BF_LSTM_TMA_ROWS") != nullptr &&   // opt-in until verified on the GPU
+      bool tma_rows = (H % 4) == 0 && getenv("BF_LSTM_TMA_ROWS") != nullptr &&   // opt-in: measured slower (see the kernel)
                       1024 + (size_t)nkb * LF_B_BYTES + (size_t)LS_RING * LF_A_BYTES + 2 * LS_ROW_TILE <= 224 * 1024;
       if (tma_rows) {
         uint64_t str[3] = {(uint64_t)H, (uint64_t)B * H, (uint64_t)TB * H};
