@@ -102,3 +102,24 @@ def test_gloo_world_size_2():
     for p in procs:
         p.join(60)
     assert res == [(0, True, True, True, 14), (1, True, True, True, 14)], res
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys, timed on
+    the unmodified reference when oracle/_ref is present (else the oracle port), no GPU touched."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    import os
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"]
