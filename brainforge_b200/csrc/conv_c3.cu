@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
 conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, const float* __restrict__ F,
                    float* __restrict__ out, const float* __restrict__ bias) {
   extern __shared__ int dyn_smem[];
-  __shared__ __align__(8) uint64_t a_full[32], a_empty[32], t_full[4], t_empty[4];
+  __shared__ __align__(8) uint64_t a_full[32], a_empty[32], t_full[2 * C3_GROUPS], t_empty[2 * C3_GROUPS];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float sbias[NB];
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -79,6 +79,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
   const uint32_t b_bytes = (uint32_t)(NB / 8) * b_sbo;
   const uint32_t stage_base = (b_base + b_bytes + 127u) & ~127u;
   const int n0 = blockIdx.y * NB;
+  constexpr int NSETS = 2 * C3_GROUPS * NB <= 512 ? 2 * C3_GROUPS : C3_GROUPS;     // accumulator sets in the 512 TMEM columns
   pdl_launch_dependents();
 
   if (warp == 1) {
@@ -86,7 +87,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 2 * C3_GROUPS; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     for (int i = 0; i < 32; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -136,7 +137,10 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
     const uint32_t a_slot_u = a_slot >> 4, row_u = (uint32_t)p.ix;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it, as = (as + 1 == p.na ? 0 : as + 1), au += (as == 0)) {
       if ((it & 1) != warp - 1) continue;
-      const int acc_set = it & 3, tu = it >> 2;   // each MMA warp / epilogue group pair owns two sets
+      // NSETS accumulator sets: tile it -> set it % NSETS, drained by epilogue group it % C3_GROUPS.  With two sets per group
+      // (NB <= 64: 8 x NB <= 512 TMEM columns) the MMAs of a group's NEXT tile are issued while it drains the current one
+      // (ncu: with one set per group the epilogue warps spent a third of their time waiting for the accumulator)
+      const int acc_set = it % NSETS, tu = it / NSETS;
       if (tu > 0) mbar_wait(&t_empty[acc_set], (uint32_t)((tu - 1) & 1));
       mbar_wait(&a_full[as], (uint32_t)(au & 1));
       tc_fence_after();
@@ -200,7 +204,7 @@ conv_c3_fwd_kernel(const __grid_constant__ CUtensorMap mapX, C3FwdParams p, cons
     }
     for (int tile = (int)blockIdx.x + grp * (int)gridDim.x; tile < p.ntiles;
          tile += 4 * (int)gridDim.x, ++it, b += step_b, t += step_t, b += (t >= p.tiles_per_img), t -= (t >= p.tiles_per_img) ? p.tiles_per_img : 0) {
-      const int acc_set = grp, tu = it;
+      const int acc_set = NSETS == C3_GROUPS ? grp : grp + C3_GROUPS * (it & 1), tu = NSETS == C3_GROUPS ? it : it >> 1;
       const int y = t * p.RT + r;
       const bool ok = r < p.RT && x < p.ox && y < p.oy;
       const int orow = (b * p.oy + y) * p.ox + x;
