@@ -123,3 +123,31 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_bench_algorithmic_cost_formulas():
+    """The per-call algorithmic bytes / FLOPs behind `roofline.achieved` (bench.py::algorithmic_cost) against closed forms
+    of SURVEY 8d for the cfg3 layer shapes: every operand read once, every result written once, true-MAC FLOPs."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    B = 4096
+    # 32 -> 64 on 14x14: X 32*196, E 64*144, F 64*32*9 floats
+    X, E, F = B * 32 * 196, B * 64 * 144, 64 * 32 * 9
+    flops = 2.0 * B * 144 * 64 * 32 * 9
+    assert b.algorithmic_cost("bf_conv_nhwc_backward_filter_dbp(1184,4096,32,14,14,64,3,3)[dF]") == (4 * (X + E + F + 64), flops)
+    assert b.algorithmic_cost("bf_conv_nhwc_backward_data_packed(4096,32,14,14,64,3,3)[dX]") == (4 * (E + F + X), flops)
+    pooled = B * 64 * 36
+    assert b.algorithmic_cost("bf_conv_nhwc_forward_pool_packed(4096,32,14,14,64,3,3,1)") == (4 * (X + F + 64 + pooled) + pooled, flops)
+    # first layer, fused un-pooling filter gradient: X, the pooled-resolution delta and gate, one mask byte each
+    X1, P1, F1 = B * 3 * 900, B * 32 * 196, 32 * 27
+    by, fl = b.algorithmic_cost("bf_conv_c3_backward_filter_unpool(4096,3,30,30,32,3,3)[dF]")
+    assert by == 4 * (X1 + 2 * P1 + F1 + 32) + P1 and fl == 2.0 * B * 784 * 32 * 27
+    # per sample the forward FLOPs of the three layers add up to SURVEY's 9 022 464 (dense head excluded)
+    per = sum(b.algorithmic_cost(l)[1] for l in ("bf_conv_c3_forward_pool(4096,3,30,30,32,3,3,0,1)",
+                                                  "bf_conv_nhwc_forward_pool_packed(4096,32,14,14,64,3,3,1)",
+                                                  "bf_conv_nhwc_forward_pool_packed(4096,64,6,6,128,3,3,1)")) / B
+    assert per == 1354752 + 5308416 + 2359296
